@@ -1,0 +1,45 @@
+"""Index of the committed golden vectors (tests/golden, made by tests/golden/make_golden.py)."""
+import json
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class CountCase:
+    def __init__(self, name):
+        d = os.path.join(GOLDEN, name)
+        self.name = name
+        self.dir = d
+        if name == "cfg1":
+            self.ref = os.path.join(d, "cfg1.fa")
+            self.bed = os.path.join(d, "actb.bed")
+            self.vcf = None
+            self.bam = os.path.join(d, "reads_slamdunk_mapped_filtered.bam")
+            self.max_read_length, self.min_qual, self.conv_threshold = 100, 27, 1
+        else:
+            p = json.load(open(os.path.join(d, "params.json")))["count"]
+            self.ref = os.path.join(d, name + ".fa")
+            self.bed = os.path.join(d, name + ".bed")
+            self.vcf = os.path.join(d, name + ".vcf") if p["vcf"] else None
+            self.bam = os.path.join(d, name + ".bam")
+            self.max_read_length, self.min_qual, self.conv_threshold = p["max_read_length"], p["min_qual"], p["conv_threshold"]
+        self.tsv = os.path.join(d, "expected_tcount.tsv")
+        self.plus = os.path.join(d, "expected_tcount_plus.bedgraph")
+        self.minus = os.path.join(d, "expected_tcount_mins.bedgraph")
+
+
+class FilterCase:
+    def __init__(self, name):
+        d = os.path.join(GOLDEN, name)
+        self.name = name
+        self.dir = d
+        self.expected = json.load(open(os.path.join(d, "expected.json")))
+        self.bam = os.path.join(d, name + ".bam")
+        self.bed = os.path.join(d, name + ".bed") if self.expected["filter"]["bed"] else None
+        self.mq = self.expected["filter"]["mq"]
+        self.min_identity = self.expected["filter"]["min_identity"]
+        self.nm = self.expected["filter"]["nm"]
+
+
+COUNT_CASES = ["cfg1", "case_a", "case_b", "case_c", "case_d", "case_e"]
+FILTER_CASES = ["filt_default", "filt_nm", "filt_multimap", "filt_multimap_nm"]

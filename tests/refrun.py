@@ -1,0 +1,67 @@
+"""Run the UNMODIFIED reference (/root/reference/slamdunk) through the I/O shims.
+
+Test infrastructure only (oracle of last resort).
+/root/reference exists in the build container, not on the GPU box: everything that
+imports this module must skip when `available()` is False.
+"""
+import io
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get("SLAMDUNK_REFERENCE", "/root/reference")
+_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "slamdunk", "dunks"))
+
+
+def _prepare():
+    sys.dont_write_bytecode = True          # /root/reference is read-only
+    for p in (REFERENCE_ROOT, _SHIMS, _REPO):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+def reference_modules():
+    """-> (tcounter, filter) modules of the reference, imported verbatim."""
+    if not available():
+        raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
+    _prepare()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from slamdunk.dunks import tcounter, filter as rfilter
+    return tcounter, rfilter
+
+
+def run_count(ref, bed, vcf, bam, out_prefix, max_read_length=100, min_qual=27, conv_threshold=1):
+    """reference tcounter.computeTconversions -> (tsv, plus, minus, log text)."""
+    tcounter, _ = reference_modules()
+    tsv = out_prefix + "_tcount.tsv"
+    plus = out_prefix + "_tcount_plus.bedgraph"
+    minus = out_prefix + "_tcount_mins.bedgraph"
+    log = io.StringIO()
+    tcounter.computeTconversions(ref, bed, vcf, bam, max_read_length, min_qual, tsv, plus, minus,
+                                 conv_threshold, log)
+    return tsv, plus, minus, log.getvalue()
+
+
+def run_filter(in_bam, out_bam, bed=None, mq=2, min_identity=0.95, nm=-1):
+    """reference filter.Filter with `samtools sort` replaced by an in-process coordinate sort
+    (samtools is absent; the sort is I/O, not arithmetic). -> log text"""
+    _, rfilter = reference_modules()
+    from slamdunk_b200.io import bam as bamio
+
+    def bam_sort(outputBAM, log, newHeader, verbose):
+        text, refs, recs = bamio.read_bam(outputBAM)
+        if newHeader is not None:
+            hd = newHeader.to_dict() if hasattr(newHeader, "to_dict") else dict(newHeader)
+            text = bamio.header_dict_to_text(hd)
+        bamio.write_bam(outputBAM, text, refs, bamio.sort_records(recs))
+
+    rfilter.bamSort = bam_sort
+    log = io.StringIO()
+    rfilter.Filter(in_bam, out_bam, log, bed, mq, min_identity, nm, False, False, True)
+    return log.getvalue()

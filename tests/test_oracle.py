@@ -1,0 +1,114 @@
+"""The CPU oracle (oracle/) against the reference's golden vector, the committed
+reference-through-shim vectors, and -- where /root/reference is present -- the reference's own
+code run live on fresh random data.  CPU only."""
+import ast
+import io
+import os
+
+import pytest
+
+import goldens
+import refrun
+import simdata
+from oracle import oracle
+from slamdunk_b200.io import bam as bamio
+
+
+def _read(p):
+    with open(p) as fh:
+        return fh.read()
+
+
+@pytest.mark.parametrize("name", goldens.COUNT_CASES)
+def test_oracle_count_matches_golden(name, tmp_path):
+    c = goldens.CountCase(name)
+    out = str(tmp_path / "o")
+    log = io.StringIO()
+    oracle.count_files(c.ref, c.bed, c.vcf, c.bam, c.max_read_length, c.min_qual, out + ".tsv",
+                       out + "_plus.bedgraph", out + "_mins.bedgraph", c.conv_threshold, log, threads=2)
+    assert _read(out + ".tsv") == _read(c.tsv)
+    assert _read(out + "_plus.bedgraph") == _read(c.plus)
+    assert _read(out + "_mins.bedgraph") == _read(c.minus)
+
+
+def test_cfg1_is_the_reference_golden_row():
+    """slamdunk/test/data/reads_slamdunk_mapped_filtered_tcount.tsv:2"""
+    c = goldens.CountCase("cfg1")
+    body = "".join(l for l in open(c.tsv) if not l.startswith("#"))
+    assert body == _read(os.path.join(c.dir, "golden_body.tsv"))
+    assert body.split("\n")[1] == ("chr5\t120498\t122492\tActb\t1994\t+\t0.022222222222222223\t666666.6666666666\t"
+                                   "445\t90\t2\t8\t4\t0\t-1.0\t-1.0")
+
+
+def _check_filter(records, bam_names, bed_rows, mq, mi, nm, expected_ds, expected_records):
+    keep, rd, stats = oracle.filter_records(records, bam_names, bed_rows, mq, mi, nm)
+    ds = ast.literal_eval(expected_ds)
+    assert stats["mapped"] == ds["mapped"]
+    assert stats["mapped"] + stats["unmapped"] == ds["sequenced"]
+    for k in ("filtered", "mqfiltered", "idfiltered", "nmfiltered", "multimapper"):
+        assert stats[k] == ds[k], k
+    written = []
+    for i, r in enumerate(records):
+        if keep[i] == 1:
+            written.append(r.copy())
+        elif keep[i] == 2:
+            w = r.copy()
+            w.flag &= ~0x900
+            w.set_tag("RD", rd[i], "Z")
+            written.append(w)
+    got = [[r.qname, r.flag, r.ref_id, r.pos, r.get_tag("RD") if r.has_tag("RD") else None]
+           for r in bamio.sort_records(written)]
+    assert got == expected_records
+
+
+@pytest.mark.parametrize("name", goldens.FILTER_CASES)
+def test_oracle_filter_matches_golden(name):
+    c = goldens.FilterCase(name)
+    _text, refs, records = bamio.read_bam(c.bam)
+    bed_rows = oracle.read_bed(c.bed) if c.bed else None
+    _check_filter(records, [n for n, _ in refs], bed_rows, c.mq, c.min_identity, c.nm,
+                  c.expected["DS"], c.expected["records"])
+
+
+needs_ref = pytest.mark.skipif(not refrun.available(), reason="/root/reference not present")
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,thr,minq,vcf", [(101, 1, 27, True), (102, 3, 13, True), (103, 1, 30, False)])
+def test_oracle_vs_live_reference_count(seed, thr, minq, vcf, tmp_path):
+    c = simdata.make_case(str(tmp_path), seed=seed, n_reads=1500, complexity=1.5, snp_density=0.01)
+    rtsv, rplus, rminus, rlog = refrun.run_count(c.ref, c.bed, c.vcf if vcf else None, c.bam,
+                                                 str(tmp_path / "ref"), 100, minq, thr)
+    out = str(tmp_path / "orc")
+    log = io.StringIO()
+    oracle.count_files(c.ref, c.bed, c.vcf if vcf else None, c.bam, 100, minq, out + ".tsv", out + "_p.bg",
+                       out + "_m.bg", thr, log)
+    assert _read(out + ".tsv") == _read(rtsv)
+    assert _read(out + "_p.bg") == _read(rplus)
+    assert _read(out + "_m.bg") == _read(rminus)
+    assert log.getvalue() == rlog
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,bed,mq,mi,nm", [(201, False, 2, 0.95, -1), (202, True, 2, 0.95, -1), (203, True, 0, 0.85, 3)])
+def test_oracle_vs_live_reference_filter(seed, bed, mq, mi, nm, tmp_path):
+    c = simdata.make_filter_case(str(tmp_path), seed=seed, n_reads=800)
+    out_bam = str(tmp_path / "f.bam")
+    refrun.run_filter(c.bam, out_bam, c.bed if bed else None, mq, mi, nm)
+    text, refs, recs = bamio.read_bam(out_bam)
+    hdr = bamio.parse_header_text(text)
+    expected = [[r.qname, r.flag, r.ref_id, r.pos, r.get_tag("RD") if r.has_tag("RD") else None] for r in recs]
+    _t, refs0, records = bamio.read_bam(c.bam)
+    _check_filter(records, [n for n, _ in refs0], oracle.read_bed(c.bed) if bed else None, mq, mi, nm,
+                  hdr["RG"][0]["DS"], expected)
+
+
+def test_bam_codec_roundtrip(tmp_path):
+    c = simdata.make_case(str(tmp_path), seed=5, n_reads=300)
+    text, refs, recs = bamio.read_bam(c.bam)
+    assert refs == c.bam_refs and len(recs) == len(c.records)
+    for a, b in zip(recs, c.records):
+        assert (a.qname, a.flag, a.ref_id, a.pos, a.mapq, a.cigar, a.seq, a.qual) == \
+               (b.qname, b.flag, b.ref_id, b.pos, b.mapq, b.cigar, b.seq, b.qual)
+        assert [(t, v if ty != "f" else round(v, 5)) for t, ty, v in a.tags] == \
+               [(t, v if ty != "f" else round(v, 5)) for t, ty, v in b.tags]
