@@ -1,0 +1,319 @@
+/*
+ * slamdunk_b200.h -- C ABI of libslamdunk_b200.so, the B200-native `slamdunk count` hot path.
+ *
+ * The reference (t-neumann/slamdunk v0.4.3) is pure Python and has NO FFI / plugin boundary
+ * for this path; its boundary is the Python function
+ *     tcounter.computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputCSV,
+ *                                  outputBedgraphPlus, outputBedgraphMinus, conversionThreshold, log)
+ *     (slamdunk/dunks/tcounter.py:125) called from slamdunk.runCount (slamdunk/slamdunk.py:202),
+ * and filter.Filter(inputBAM, outputBAM, log, bed, MQ, minIdentity, NM, ...) (slamdunk/dunks/filter.py:213).
+ * slamdunk_b200/dunks/tcounter.py and filter.py keep those signatures and call the entry points
+ * below through ctypes (INTEGRATION.md shows the binding a reference maintainer would add).
+ * Each entry point names the reference code whose work it takes over.
+ *
+ * Conventions
+ *   - every function returns SD_OK (0) or a negative SD_ERR_* code; sd_last_error() gives text;
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - "device pointer" arguments are owned by the caller (a torch tensor's data_ptr()) and must
+ *     stay alive until the stream work that uses them has completed; the library owns only the
+ *     tables it derives (UTR index, reference planes) and frees them in sd_destroy;
+ *   - all device work is enqueued on the stream given to sd_create; functions documented as
+ *     "synchronous" wait for it, the others do not;
+ *   - a context is bound to one device and must be used from one host thread at a time;
+ *   - only integers cross the boundary: the three float divisions of a tcount row
+ *     (tcounter.py:252,297,303) are done by the Python host so the text is byte-identical.
+ */
+#ifndef SLAMDUNK_B200_H
+#define SLAMDUNK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_OK 0
+#define SD_ERR_CUDA (-1)
+#define SD_ERR_ARG (-2)
+#define SD_ERR_STATE (-3)
+#define SD_ERR_IO (-4)
+#define SD_ERR_FORMAT (-5)
+#define SD_ERR_LIMIT (-6)
+#define SD_ERR_NOMEM (-7)
+
+#define SD_ABI_VERSION 1
+
+typedef struct sd_ctx sd_ctx;
+
+/* ------------------------------------------------------------------ columnar read batch
+ *
+ * One record per BAM alignment, 20 bytes, array-of-structs so that one tile's records are a
+ * single contiguous bulk copy.  Replaces the pysam AlignedSegment attributes the reference
+ * reads (slamseq/SlamSeqFile.py:364-402, dunks/filter.py:233-256).
+ */
+#define SD_F_REVERSE 0x01u       /* BAM flag 0x10 */
+#define SD_F_UNMAPPED 0x02u      /* BAM flag 0x4, or no CIGAR (pysam reference_end is None) */
+#define SD_F_SECONDARY 0x04u     /* BAM flag 0x100 */
+#define SD_F_SUPPLEMENTARY 0x08u /* BAM flag 0x800 */
+#define SD_F_HAS_MP 0x10u        /* record carries NextGenMap's MP:Z tag (SlamSeqFile.py:318) */
+#define SD_F_SKIP 0x20u          /* not to be counted: padding record, chromosome not in the FASTA */
+#define SD_F_NEWNAME 0x40u       /* query name differs from the previous record in file order */
+#define SD_F_PAD 0x80u           /* tile padding, not a record */
+
+#define SD_REF_NONE 0xFFFFu      /* ref field: chromosome absent from the FASTA */
+
+typedef struct sd_read_rec {
+    int32_t pos;            /* 0-based leftmost reference position on its chromosome (BAM pos) */
+    uint32_t ref_mapq_flag; /* bits 0-15 chromosome index (FASTA order), 16-23 MAPQ, 24-31 SD_F_* */
+    float xi;               /* NextGenMap XI:f alignment identity (filter.py:246); NaN if absent */
+    uint32_t lseq_ncig;     /* bits 0-15 l_seq, 16-31 number of CIGAR ops */
+    uint32_t nm_nmp;        /* bits 0-15 NM tag (saturated), 16-31 number of MP entries stored */
+} sd_read_rec;
+
+/* Byte offsets of one tile's variable-length rows inside the seq / qual / cigar / mp columns.
+ * tiles[t+1] - tiles[t] is the tile's size; every offset is a multiple of 16. */
+typedef struct sd_tile {
+    uint64_t seq_off;
+    uint64_t qual_off;
+    uint64_t cig_off;
+    uint64_t mp_off;
+} sd_tile;
+
+/*
+ * Column layouts (rows of one tile are consecutive, in record order, tiles padded to 16 bytes):
+ *   seq   "sliced 4-bit": for every 8 bases one 32-bit word whose byte p (p = 0..3) is bit-plane
+ *         p of the BAM nibble code (bit0 A, bit1 C, bit2 G, bit3 T; N = all four, '=' = none);
+ *         bit i of each byte is base 8w+i.  ceil(l_seq/8) words per read, pad bits zero.
+ *   qual  l_seq bytes per read, BAM phred values as stored.
+ *   cigar n_cigar 32-bit words per read, BAM encoding (len << 4 | op).
+ *   mp    per stored MP entry one 32-bit word: bits 0-15 readPos-1, bits 16-31 refPos-1
+ *         (0-based, already decremented; entries with conv == 16 on forward reads and
+ *         conv == 2 on reverse reads only -- the only ones isTCMismatch can accept,
+ *         SlamSeqFile.py:137-141).  May be NULL when mismatches come from the CIGAR walk and
+ *         no cross-check is wanted.
+ */
+typedef struct sd_batch {
+    uint64_t n_reads;       /* real records (<= n_tiles * tile_reads) */
+    uint32_t n_tiles;
+    uint32_t tile_reads;    /* records per tile: 64, 128 or 256; rec[] is padded with SD_F_PAD */
+    const sd_read_rec *rec; /* [n_tiles * tile_reads] */
+    const uint32_t *seq;
+    const uint8_t *qual;
+    const uint32_t *cigar;
+    const uint32_t *mp;     /* may be NULL */
+    const sd_tile *tiles;   /* [n_tiles + 1] */
+    uint32_t max_lseq;      /* largest l_seq in the batch */
+    uint32_t max_tile_seq;  /* largest per-tile byte sizes (size the shared-memory stages) */
+    uint32_t max_tile_qual;
+    uint32_t max_tile_cig;
+    uint32_t max_tile_mp;
+    uint32_t reserved;
+} sd_batch;
+
+/* Where the per-read mismatch list comes from. */
+#define SD_MISMATCH_CIGAR 0 /* walk the CIGAR, compare SEQ with the reference planes (north star) */
+#define SD_MISMATCH_MP 1    /* take NextGenMap's MP entries as the reference code does */
+#define SD_MISMATCH_VERIFY 2 /* CIGAR walk, and count reads whose MP entries disagree with it */
+
+typedef struct sd_params {
+    int32_t min_qual;             /* minQual (tcounter.py:125; `>=` test SlamSeqFile.py:330) */
+    int32_t conversion_threshold; /* conversionThreshold (SlamSeqFile.py:397) */
+    int32_t mismatch_source;      /* SD_MISMATCH_* */
+    int32_t filter_on;            /* apply filter.py:241-251 predicates before counting */
+    int32_t filter_mq;            /* MQ */
+    int32_t filter_max_nm;        /* NM, -1 = off */
+    double filter_min_identity;   /* minIdentity */
+    int32_t force_slow_path;      /* testing: run every read through the per-base path */
+    int32_t reserved;
+} sd_params;
+
+/* Per-UTR integer counters, row-major [n_utr][SD_NCOUNTER], BED order. */
+#define SD_NCOUNTER 5
+#define SD_C_READS 0     /* readCount        tcounter.py:216-227 */
+#define SD_C_TCREADS 1   /* tcReadCount */
+#define SD_C_MULTIMAP 2  /* multimapCount */
+#define SD_C_COV_ON_T 3  /* coverageOnTs     tcounter.py:281 */
+#define SD_C_CONV_ON_T 4 /* conversionsOnTs  tcounter.py:282 */
+
+/* Run-level counters, int64[SD_NSTAT]. */
+#define SD_NSTAT 10
+#define SD_S_MAPPED 0       /* filter.py:235-239 (primary, mapped) */
+#define SD_S_UNMAPPED 1
+#define SD_S_FILTERED 2     /* filteredReads */
+#define SD_S_MQFILTERED 3
+#define SD_S_IDFILTERED 4
+#define SD_S_NMFILTERED 5
+#define SD_S_COUNTED 6      /* records that entered the T>C scan */
+#define SD_S_SLOWPATH 7     /* records handled by the per-base path */
+#define SD_S_MP_DISAGREE 8  /* SD_MISMATCH_VERIFY: records whose MP list != CIGAR walk */
+#define SD_S_TC_TOTAL 9     /* sum of per-read tcCount over counted reads (diagnostic) */
+
+/* ------------------------------------------------------------------ context */
+int sd_abi_version(void);
+/* device: CUDA ordinal.  stream: cudaStream_t (NULL = a private non-blocking stream). */
+int sd_create(int device, void *stream, sd_ctx **out);
+void sd_destroy(sd_ctx *ctx);
+const char *sd_last_error(const sd_ctx *ctx);
+int sd_device_synchronize(sd_ctx *ctx);
+
+/* ------------------------------------------------------------------ reference genome
+ * Replaces pysam.FastaFile.fetch(...).upper() (tcounter.py:181, SlamSeqFile.py:436).
+ * The genome is one linear bit space: chromosome c occupies bits [chrom_off[c], chrom_off[c] +
+ * chrom_len[c]); chrom_off[c] is a multiple of 32 and consecutive chromosomes are separated by
+ * at least 32 pad positions.  Three bit-planes of n_words uint32 (bit j of word w = position
+ * 32w+j): lo/hi = the two bits of the base code A=0 C=1 G=2 T=3, nmask = 1 where the upper-cased
+ * FASTA character is not one of ACGT (and on every pad position).  Device pointers; the planes
+ * are consumed (a derived table is built) before the call returns control to the stream.
+ */
+int sd_set_reference(sd_ctx *ctx, const uint32_t *d_lo, const uint32_t *d_hi, const uint32_t *d_nmask,
+                     uint64_t n_words, const uint32_t *h_chrom_off, const uint32_t *h_chrom_len,
+                     uint32_t n_chrom);
+/* SNP masks in the same bit space (replaces SNPDictionary.isTCSnp / isAGSnp, utils/SNPtools.py:53-60;
+ * the chrom+pos string-key collisions are resolved by the host when it builds the masks).
+ * Device pointers, NULL = no SNPs.  Call after sd_set_reference. */
+int sd_set_snps(sd_ctx *ctx, const uint32_t *d_tc_mask, const uint32_t *d_ag_mask);
+
+/* ------------------------------------------------------------------ annotation
+ * Replaces BedIterator + the per-UTR indexed fetch (tcounter.py:165, SlamSeqFile.py:441).
+ * Host arrays in BED order.  chrom[i] = FASTA chromosome index or SD_REF_NONE; start/stop as in
+ * the BED file (stop is clipped to the chromosome length internally, SlamSeqFile.py:441);
+ * strand 0 '+', 1 '-'.  in_bam[i] = 0 suppresses reads for rows whose chromosome is not in the
+ * BAM header (SlamSeqFile.py:440-445).
+ */
+int sd_set_utrs(sd_ctx *ctx, const uint32_t *h_chrom, const int64_t *h_start, const int64_t *h_stop,
+                const uint8_t *h_strand, const uint8_t *h_in_bam, uint32_t n_utr);
+/* Size (in int32 elements) of each per-position array; 0 before sd_set_utrs. */
+int sd_position_space(const sd_ctx *ctx, uint64_t *n_positions);
+/* For every BED row: offset of its first base in the per-position arrays (UINT64_MAX if the row
+ * has no device entry), and the number of in-chromosome bases it spans. */
+int sd_utr_layout(const sd_ctx *ctx, uint64_t *h_pos_off, uint32_t *h_pos_len);
+
+/* ------------------------------------------------------------------ outputs
+ * Caller-owned device buffers (so they can be handed to NCCL as torch tensors):
+ *   counters  int64 [n_utr * SD_NCOUNTER]
+ *   pos_cov   int32 [n_positions]  coverage (difference form until sd_finalize)
+ *   pos_tc    int32 [n_positions]  T>C conversions per position
+ *   stats     int64 [SD_NSTAT]
+ * sd_bind_outputs zero-fills them on the stream.
+ */
+int sd_bind_outputs(sd_ctx *ctx, int64_t *d_counters, int32_t *d_pos_cov, int32_t *d_pos_tc,
+                    int64_t *d_stats);
+
+/* ------------------------------------------------------------------ the hot path
+ * sd_count: filter predicates (filter.py:241-251) + per-read conversion scan
+ * (SlamSeqFile.py:313-402) + interval join and per-UTR reduction (tcounter.py:207-248)
+ * + per-position scatter, for one device-resident batch.  Asynchronous.
+ */
+int sd_count(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params);
+/* sd_count that also writes every record's tcCount (after the conversionThreshold rule, saturated at
+ * 255; 0 for records that were not counted) to d_read_tc[n_tiles * tile_reads] -- the per-read
+ * quantity SlamSeqBamIterator yields (SlamSeqFile.py:386,397); tests and read separation use it. */
+int sd_count_reads(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params, uint8_t *d_read_tc);
+/* Same, from HOST buffers: copies the batch to the device in chunks (pinned staging, copy
+ * stream overlapped with the kernel) and waits for completion.  Synchronous. */
+int sd_count_host(sd_ctx *ctx, const sd_batch *h_batch, const sd_params *params);
+/* Turn pos_cov from difference form into coverage (segment-local prefix sums).  Call once after
+ * the last sd_count (and after any cross-GPU reduction of the outputs).  Asynchronous. */
+int sd_finalize(sd_ctx *ctx);
+/* Tcontent per BED row (tcounter.py:177-189): count of T ('+') or A ('-') in the upper-cased
+ * FASTA slice.  d_tcontent: device int64[n_utr].  Asynchronous. */
+int sd_tcontent(sd_ctx *ctx, int64_t *d_tcontent);
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+int64_t sd_launch_count(const sd_ctx *ctx);
+/* Duration of the most recent sd_count kernel on its stream (CUDA events), ms; <0 if none. */
+float sd_last_kernel_ms(sd_ctx *ctx);
+
+/* ------------------------------------------------------------------ read filter
+ * filter.Filter decision logic (dunks/filter.py:225-271) for one device-resident batch in FILE
+ * order.  keep: device uint8[n_reads], 0 drop / 1 write / 2 write with secondary+supplementary
+ * cleared (multimapper retained by dumpBufferToBam, filter.py:56-65).  With h_utr_* == NULL the
+ * default branch (MQ / identity / NM) runs; otherwise the multimapper-retention branch, whose
+ * UTR intervals are [start, stop + 1) (utils/BedReader.py:28) and compare by name id.
+ * stats: device int64[SD_NSTAT].  Synchronous.
+ */
+int sd_filter(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params, const uint64_t *d_name_hash,
+              const uint32_t *h_utr_chrom, const int64_t *h_utr_start, const int64_t *h_utr_stop,
+              const uint32_t *h_utr_name_id, uint32_t n_utr, uint8_t *d_keep, int64_t *d_stats);
+
+/* ------------------------------------------------------------------ host decode (C++ threads)
+ * Replaces htslib/pysam for this path: BGZF inflate + BAM record decode into the columnar
+ * layout above, FASTA into bit-planes.  Buffers are page-locked and owned by the returned
+ * object; free with the matching *_free.
+ */
+typedef struct sd_hbatch {
+    sd_batch batch;          /* host pointers */
+    uint64_t *name_hash;     /* [n_reads] 64-bit hash of the query name (filter multimapper pass) */
+    char *header_text;       /* SAM header text, NUL-terminated */
+    uint32_t n_ref;          /* BAM reference sequences */
+    char **ref_names;
+    uint32_t *ref_lengths;
+    double seconds_inflate;  /* decode cost, reported separately from the counting kernels */
+    double seconds_decode;
+    uint64_t compressed_bytes;
+    uint64_t inflated_bytes;
+    void *opaque;
+} sd_hbatch;
+
+/* fasta_names / n_fasta: chromosome table of the FASTA (index = sd_read_rec ref field).
+ * want_mp: also decode MP tags into the mp column.  threads <= 0: hardware concurrency. */
+int sd_decode_bam(const char *path, const char *const *fasta_names, uint32_t n_fasta, int want_mp,
+                  uint32_t tile_reads, int threads, sd_hbatch **out, char *err, int errlen);
+void sd_hbatch_free(sd_hbatch *hb);
+
+typedef struct sd_hgenome {
+    uint32_t n_chrom;
+    char **names;
+    uint32_t *chrom_len;
+    uint32_t *chrom_off;   /* start of each chromosome in the linear bit space (multiple of 32) */
+    uint64_t n_words;
+    uint32_t *lo, *hi, *nmask;
+    double seconds;
+    void *opaque;
+} sd_hgenome;
+
+int sd_load_fasta(const char *path, int threads, sd_hgenome **out, char *err, int errlen);
+void sd_hgenome_free(sd_hgenome *g);
+
+/* ------------------------------------------------------------------ synthetic SLAM-seq reads
+ * Device-side generator of the BASELINE.json configurations (per-T Bernoulli conversions as in
+ * the reference's simulator, dunks/simulator.py:212-229).  Counter-based RNG keyed by
+ * (seed, read index): any sharding of the index range yields the same reads.
+ */
+typedef struct sd_synth_params {
+    uint64_t seed;
+    uint64_t first_read;      /* global index of the first read of this batch */
+    uint64_t n_reads;
+    uint32_t read_len;
+    uint32_t tile_reads;
+    float p_conv;             /* per reference T (A on '-') conversion probability */
+    float p_err;              /* other substitution errors per base */
+    float frac_softclip;      /* reads with <= 5 soft-clipped bases */
+    float frac_indel;         /* reads with one 1-3 bp insertion or deletion */
+    float frac_multimap;      /* mapq 0 */
+    float frac_antisense;     /* reads on the strand opposite to their UTR */
+    float frac_labelled;      /* reads that carry conversions at all */
+    uint32_t utr_first, utr_count; /* restrict placement to this range of the expression table */
+} sd_synth_params;
+
+/* Expression table: device arrays [n] of UTR global start, in-chromosome length, strand and
+ * cumulative weight (float64, last element = total).  Sizes the batch: fills h_sizes with the
+ * column byte sizes {rec, seq, qual, cigar, mp, tiles, triples} the caller must allocate. */
+int sd_synth_sizes(sd_ctx *ctx, const sd_synth_params *p, const uint32_t *d_utr_gstart,
+                   const uint32_t *d_utr_len, const uint8_t *d_utr_strand, const double *d_cum_weight,
+                   uint32_t n_utr, uint64_t *d_scratch_counts, uint64_t h_sizes[8]);
+/* Fill caller-allocated device columns (sizes from sd_synth_sizes); d_triples (optional) receives
+ * per read up to 24 (conv, readPos, refPos) int32 triples + count, the generator's own record of
+ * the mismatches it made (for the oracle's MP input).  Synchronous. */
+int sd_synth_fill(sd_ctx *ctx, const sd_synth_params *p, const uint32_t *d_utr_gstart,
+                  const uint32_t *d_utr_len, const uint8_t *d_utr_strand, const double *d_cum_weight,
+                  uint32_t n_utr, const uint64_t *d_scratch_counts, sd_batch *d_batch_out /* host struct, device ptrs */,
+                  int32_t *d_triples);
+/* Random genome planes: uniform ACGT with n_frac of positions inside N runs.  Device pointers. */
+int sd_synth_genome(sd_ctx *ctx, uint64_t seed, uint32_t *d_lo, uint32_t *d_hi, uint32_t *d_nmask,
+                    uint64_t n_words, const uint32_t *h_chrom_off, const uint32_t *h_chrom_len,
+                    uint32_t n_chrom, float n_frac);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAMDUNK_B200_H */

@@ -1,0 +1,149 @@
+"""ctypes binding of libslamdunk_b200.so (include/slamdunk_b200.h).
+
+There is no CPU fallback: if the library has not been built, loading raises.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libslamdunk_b200.so")
+
+SD_OK = 0
+SD_F_REVERSE, SD_F_UNMAPPED, SD_F_SECONDARY, SD_F_SUPPLEMENTARY = 0x01, 0x02, 0x04, 0x08
+SD_F_HAS_MP, SD_F_SKIP, SD_F_NEWNAME, SD_F_PAD = 0x10, 0x20, 0x40, 0x80
+SD_REF_NONE = 0xFFFF
+SD_MISMATCH_CIGAR, SD_MISMATCH_MP, SD_MISMATCH_VERIFY = 0, 1, 2
+SD_NCOUNTER = 5
+SD_C_READS, SD_C_TCREADS, SD_C_MULTIMAP, SD_C_COV_ON_T, SD_C_CONV_ON_T = range(5)
+SD_NSTAT = 10
+(SD_S_MAPPED, SD_S_UNMAPPED, SD_S_FILTERED, SD_S_MQFILTERED, SD_S_IDFILTERED, SD_S_NMFILTERED,
+ SD_S_COUNTED, SD_S_SLOWPATH, SD_S_MP_DISAGREE, SD_S_TC_TOTAL) = range(10)
+
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_u32p = ctypes.POINTER(ctypes.c_uint32)
+c_u64p = ctypes.POINTER(ctypes.c_uint64)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+class ReadRec(ctypes.Structure):
+    _fields_ = [("pos", ctypes.c_int32), ("ref_mapq_flag", ctypes.c_uint32), ("xi", ctypes.c_float),
+                ("lseq_ncig", ctypes.c_uint32), ("nm_nmp", ctypes.c_uint32)]
+
+
+class Tile(ctypes.Structure):
+    _fields_ = [("seq_off", ctypes.c_uint64), ("qual_off", ctypes.c_uint64), ("cig_off", ctypes.c_uint64),
+                ("mp_off", ctypes.c_uint64)]
+
+
+class Batch(ctypes.Structure):
+    _fields_ = [("n_reads", ctypes.c_uint64), ("n_tiles", ctypes.c_uint32), ("tile_reads", ctypes.c_uint32),
+                ("rec", ctypes.c_void_p), ("seq", ctypes.c_void_p), ("qual", ctypes.c_void_p),
+                ("cigar", ctypes.c_void_p), ("mp", ctypes.c_void_p), ("tiles", ctypes.c_void_p),
+                ("max_lseq", ctypes.c_uint32), ("max_tile_seq", ctypes.c_uint32), ("max_tile_qual", ctypes.c_uint32),
+                ("max_tile_cig", ctypes.c_uint32), ("max_tile_mp", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+class Params(ctypes.Structure):
+    _fields_ = [("min_qual", ctypes.c_int32), ("conversion_threshold", ctypes.c_int32),
+                ("mismatch_source", ctypes.c_int32), ("filter_on", ctypes.c_int32), ("filter_mq", ctypes.c_int32),
+                ("filter_max_nm", ctypes.c_int32), ("filter_min_identity", ctypes.c_double),
+                ("force_slow_path", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class HBatch(ctypes.Structure):
+    _fields_ = [("batch", Batch), ("name_hash", c_u64p), ("header_text", ctypes.c_char_p), ("n_ref", ctypes.c_uint32),
+                ("ref_names", ctypes.POINTER(ctypes.c_char_p)), ("ref_lengths", c_u32p),
+                ("seconds_inflate", ctypes.c_double), ("seconds_decode", ctypes.c_double),
+                ("compressed_bytes", ctypes.c_uint64), ("inflated_bytes", ctypes.c_uint64), ("opaque", ctypes.c_void_p)]
+
+
+class HGenome(ctypes.Structure):
+    _fields_ = [("n_chrom", ctypes.c_uint32), ("names", ctypes.POINTER(ctypes.c_char_p)), ("chrom_len", c_u32p),
+                ("chrom_off", c_u32p), ("n_words", ctypes.c_uint64), ("lo", c_u32p), ("hi", c_u32p), ("nmask", c_u32p),
+                ("seconds", ctypes.c_double), ("opaque", ctypes.c_void_p)]
+
+
+class SynthParams(ctypes.Structure):
+    _fields_ = [("seed", ctypes.c_uint64), ("first_read", ctypes.c_uint64), ("n_reads", ctypes.c_uint64),
+                ("read_len", ctypes.c_uint32), ("tile_reads", ctypes.c_uint32), ("p_conv", ctypes.c_float),
+                ("p_err", ctypes.c_float), ("frac_softclip", ctypes.c_float), ("frac_indel", ctypes.c_float),
+                ("frac_multimap", ctypes.c_float), ("frac_antisense", ctypes.c_float), ("frac_labelled", ctypes.c_float),
+                ("utr_first", ctypes.c_uint32), ("utr_count", ctypes.c_uint32)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/slamdunk_b200.h
+_VP = ctypes.c_void_p
+PROTOTYPES = {
+    "sd_abi_version": (ctypes.c_int, []),
+    "sd_create": (ctypes.c_int, [ctypes.c_int, _VP, ctypes.POINTER(_VP)]),
+    "sd_destroy": (None, [_VP]),
+    "sd_last_error": (ctypes.c_char_p, [_VP]),
+    "sd_device_synchronize": (ctypes.c_int, [_VP]),
+    "sd_set_reference": (ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.c_uint64, _VP, _VP, ctypes.c_uint32]),
+    "sd_set_snps": (ctypes.c_int, [_VP, _VP, _VP]),
+    "sd_set_utrs": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_uint32]),
+    "sd_position_space": (ctypes.c_int, [_VP, c_u64p]),
+    "sd_utr_layout": (ctypes.c_int, [_VP, _VP, _VP]),
+    "sd_bind_outputs": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "sd_count": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params)]),
+    "sd_count_reads": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params), _VP]),
+    "sd_count_host": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params)]),
+    "sd_finalize": (ctypes.c_int, [_VP]),
+    "sd_tcontent": (ctypes.c_int, [_VP, _VP]),
+    "sd_launch_count": (ctypes.c_int64, [_VP]),
+    "sd_last_kernel_ms": (ctypes.c_float, [_VP]),
+    "sd_filter": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params), _VP, _VP, _VP, _VP, _VP,
+                                 ctypes.c_uint32, _VP, _VP]),
+    "sd_decode_bam": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint32, ctypes.c_int,
+                                     ctypes.c_uint32, ctypes.c_int, ctypes.POINTER(ctypes.POINTER(HBatch)),
+                                     ctypes.c_char_p, ctypes.c_int]),
+    "sd_hbatch_free": (None, [ctypes.POINTER(HBatch)]),
+    "sd_load_fasta": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.POINTER(HGenome)),
+                                     ctypes.c_char_p, ctypes.c_int]),
+    "sd_hgenome_free": (None, [ctypes.POINTER(HGenome)]),
+    "sd_synth_sizes": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), _VP, _VP, _VP, _VP, ctypes.c_uint32, _VP, _VP]),
+    "sd_synth_fill": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), _VP, _VP, _VP, _VP, ctypes.c_uint32, _VP,
+                                     ctypes.POINTER(Batch), _VP]),
+    "sd_synth_genome": (ctypes.c_int, [_VP, ctypes.c_uint64, _VP, _VP, _VP, ctypes.c_uint64, _VP, _VP, ctypes.c_uint32,
+                                       ctypes.c_float]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the native library or raise -- the product path has no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libslamdunk_b200.so is not built (run `python -m slamdunk_b200.build`); "
+                           "slamdunk_b200 has no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    missing = []
+    for name, (res, args) in PROTOTYPES.items():
+        try:
+            fn = getattr(L, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    if missing:
+        raise RuntimeError("libslamdunk_b200.so is stale, it lacks %s; rebuild with `python -m slamdunk_b200.build`"
+                           % ", ".join(missing))
+    assert ctypes.sizeof(ReadRec) == 20 and ctypes.sizeof(Tile) == 32
+    _lib = L
+    return L
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def check(rc, ctx=None, what=""):
+    if rc != SD_OK:
+        msg = ""
+        if ctx:
+            msg = (load().sd_last_error(ctx) or b"").decode("utf-8", "replace")
+        raise NativeError("%s failed with code %d: %s" % (what or "native call", rc, msg))

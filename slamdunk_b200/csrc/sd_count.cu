@@ -1,0 +1,1209 @@
+// sd_count.cu -- the `slamdunk count` hot path for B200 (sm_100a).
+//
+// One persistent kernel streams the columnar read batch through shared memory with TMA bulk
+// copies (cp.async.bulk + mbarrier, a ring of stages per CTA) and does, per read (one thread per
+// read, one warp per 32-read group):
+//   1. the read filter predicates                      (reference: dunks/filter.py:241-251)
+//   2. the T>C / A>G conversion scan                   (slamseq/SlamSeqFile.py:313-348, 364-402)
+//      as word-parallel bit operations: the read's "is C" ("is G" on the minus strand) mask is
+//      one AND-reduction over the sliced 4-bit SEQ planes, aligned to reference coordinates by
+//      the CIGAR, and ANDed with the reference's "is T / not a SNP" planes of the read's window;
+//      base qualities are looked up only at the surviving candidate positions;
+//   3. the read -> UTR interval join (binned start-sorted table) and the per-UTR counters
+//      readCount / tcReadCount / multimapCount / coverageOnTs / conversionsOnTs
+//      (dunks/tcounter.py:207-248, 277-283) with warp-aggregated int64 atomics;
+//   4. the per-position coverage (difference form) and conversion scatter that the bedgraphs
+//      need (tcounter.py:229-231, 246-248, 285).
+// The path is integer streaming work bound by HBM bandwidth; there is no tensor-core use.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "sd_internal.h"
+
+// ------------------------------------------------------------------------------------------
+// small PTX wrappers (mbarrier + 1-D bulk async copy; SASS: SYNCS.*, UBLKCP)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------
+struct CountArgs {
+    // batch (device pointers)
+    const sd_read_rec *rec;
+    const uint32_t *seq;
+    const uint8_t *qual;
+    const uint32_t *cigar;
+    const uint32_t *mp;
+    const sd_tile *tiles;
+    uint32_t n_tiles;
+    uint32_t tile_reads;
+    // shared-memory stage layout (bytes, all multiples of 128)
+    uint32_t cap_rec, cap_seq, cap_qual, cap_cig, cap_mp;
+    uint32_t n_stages;
+    // reference
+    const uint2 *refx[2];
+    const uint32_t *chrom_off;
+    const uint32_t *chrom_len;
+    uint32_t n_chrom;
+    // annotation
+    const uint32_t *ustart[2];
+    const uint32_t *uend[2];
+    const uint32_t *urow[2];
+    const uint32_t *useg[2];
+    const uint32_t *bin_first[2];
+    uint32_t n_u[2];
+    uint32_t n_bins;
+    const uint32_t *seg_start[2];
+    const uint32_t *seg_end[2];
+    const uint64_t *seg_off[2];
+    // outputs
+    unsigned long long *counters;
+    int *pos_cov;
+    int *pos_tc;
+    unsigned long long *stats;
+    uint8_t *read_tc;  // optional per-read tcCount (saturated), may be null
+    // parameters
+    int min_qual;
+    int conv_threshold;
+    int mismatch_source;
+    int filter_on;
+    int filter_mq;
+    int filter_max_nm;
+    double filter_min_identity;
+    int force_slow;
+};
+
+__device__ __forceinline__ bool cigar_consumes_ref(uint32_t op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
+__device__ __forceinline__ bool cigar_is_match(uint32_t op) { return op == 0 || op == 7 || op == 8; }
+__device__ __forceinline__ bool cigar_consumes_query(uint32_t op) { return op == 0 || op == 1 || op == 4 || op == 7 || op == 8; }
+
+// bits [lo, hi) of the window restricted to word k
+__device__ __forceinline__ uint32_t range_word(int k, int lo, int hi) {
+    int a = lo - 32 * k, b = hi - 32 * k;
+    a = a < 0 ? 0 : a;
+    b = b > 32 ? 32 : b;
+    if (b <= a) return 0u;
+    uint32_t m = (b == 32) ? 0xFFFFFFFFu : ((1u << b) - 1u);
+    return m & ~((1u << a) - 1u);
+}
+
+// Warp-aggregated add into one UTR's counter row: lanes that hit the same row elect a leader.
+__device__ __forceinline__ void utr_accumulate(unsigned long long *counters, uint32_t row, uint32_t tcread,
+                                               uint32_t multimap, uint32_t cov_t, uint32_t conv_t) {
+    const unsigned active = __activemask();
+    const unsigned grp = __match_any_sync(active, row);
+    const uint32_t n = __popc(grp);
+    const uint32_t s_tc = __reduce_add_sync(grp, tcread);
+    const uint32_t s_mm = __reduce_add_sync(grp, multimap);
+    const uint32_t s_cov = __reduce_add_sync(grp, cov_t);
+    const uint32_t s_conv = __reduce_add_sync(grp, conv_t);
+    if ((threadIdx.x & 31) == (__ffs(grp) - 1)) {
+        unsigned long long *c = counters + (size_t)row * SD_NCOUNTER;
+        atomicAdd(c + SD_C_READS, (unsigned long long)n);
+        if (s_tc) atomicAdd(c + SD_C_TCREADS, (unsigned long long)s_tc);
+        if (s_mm) atomicAdd(c + SD_C_MULTIMAP, (unsigned long long)s_mm);
+        if (s_cov) atomicAdd(c + SD_C_COV_ON_T, (unsigned long long)s_cov);
+        if (s_conv) atomicAdd(c + SD_C_CONV_ON_T, (unsigned long long)s_conv);
+    }
+}
+
+// read mask word -> "is X" byte for 8 bases of sliced SEQ.  inv flips the planes that must be 0.
+__device__ __forceinline__ uint32_t sliced_is_base(uint32_t w, uint32_t inv) {
+    uint32_t x = w ^ inv;
+    x &= x >> 16;
+    x &= x >> 8;
+    return x & 0xFFu;
+}
+
+// Map a reference offset (relative to the alignment start) to the read index aligned to it.
+__device__ __forceinline__ int ref_to_read(const uint32_t *cig, uint32_t ncig, int o) {
+    int q = 0, r = 0;
+    for (uint32_t i = 0; i < ncig; i++) {
+        const uint32_t c = cig[i], op = c & 15u;
+        const int len = (int)(c >> 4);
+        if (cigar_is_match(op)) {
+            if (o < r + len) return q + (o - r);
+            q += len;
+            r += len;
+        } else if (op == 1 || op == 4) {
+            q += len;
+        } else if (op == 2 || op == 3) {
+            r += len;
+        }
+    }
+    return -1;
+}
+
+struct ReadView {
+    const uint32_t *seq;   // sliced words (shared memory)
+    const uint8_t *qual;   // bytes (shared memory)
+    const uint32_t *cig;   // ops (shared memory)
+    const uint32_t *mp;    // entries (shared memory) or null
+    uint32_t lseq, ncig, nmp;
+    uint32_t g;            // window start in the linear genome
+    int span;              // reference bases spanned (clipped to the chromosome)
+    int strand;            // 0 '+', 1 '-'
+    bool has_mp;
+};
+
+// ---------------------------------------------------------------------------------------
+// Per-base path: reads whose window does not fit the register window (long deletions / N skips,
+// reads longer than the instantiated window) and the testing cross-check (force_slow).
+// Same semantics as the word-parallel path, written as plain loops.
+// ---------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void slow_for_each_hit(const CountArgs &A, const ReadView &v, F f) {
+    const uint2 *rx = A.refx[v.strand];
+    if (A.mismatch_source == SD_MISMATCH_MP) {
+        if (!v.has_mp || v.mp == nullptr) return;
+        for (uint32_t i = 0; i < v.nmp; i++) {
+            const uint32_t e = v.mp[i];
+            const int rp = (int)(e & 0xFFFFu), o = (int)(e >> 16);
+            const int q = (rp >= (int)v.lseq) ? 0 : (int)v.qual[rp];
+            if (q < A.min_qual) continue;
+            const uint64_t gp = (uint64_t)v.g + (uint64_t)o;
+            const uint2 x = __ldg(&rx[gp >> 5]);
+            if ((x.y >> (gp & 31)) & 1u) continue;  // SNP
+            f(o, (bool)((x.x >> (gp & 31)) & 1u));
+        }
+        return;
+    }
+    if (!v.has_mp) return;  // no MP tag: the reference sees no mismatches (SlamSeqFile.py:318)
+    const uint32_t inv = v.strand ? 0xFF00FFFFu : 0xFFFF00FFu;
+    int q = 0, r = 0;
+    for (uint32_t i = 0; i < v.ncig; i++) {
+        const uint32_t c = v.cig[i], op = c & 15u;
+        const int len = (int)(c >> 4);
+        if (cigar_is_match(op)) {
+            for (int j = 0; j < len; j++) {
+                const int o = r + j, qi = q + j;
+                if (o >= v.span || qi >= (int)v.lseq) break;
+                const uint32_t isx = sliced_is_base(v.seq[qi >> 3], inv);
+                if (!((isx >> (qi & 7)) & 1u)) continue;
+                const uint64_t gp = (uint64_t)v.g + (uint64_t)o;
+                const uint2 x = __ldg(&rx[gp >> 5]);
+                const uint32_t bit = 1u << (gp & 31);
+                if (!(x.x & bit) || (x.y & bit)) continue;
+                if ((int)v.qual[qi] < A.min_qual) continue;
+                f(o, true);
+            }
+            q += len;
+            r += len;
+        } else if (op == 1 || op == 4) {
+            q += len;
+        } else if (op == 2 || op == 3) {
+            r += len;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t slow_count_t(const uint2 *rx, uint64_t ga, uint64_t gb) {
+    // number of set isX bits in [ga, gb)
+    uint32_t n = 0;
+    if (gb <= ga) return 0;
+    uint64_t w0 = ga >> 5, w1 = (gb - 1) >> 5;
+    for (uint64_t w = w0; w <= w1; w++) {
+        uint32_t x = __ldg(&rx[w]).x;
+        if (w == w0) x &= ~((1u << (ga & 31)) - 1u);
+        if (w == w1 && ((gb & 31) != 0)) x &= ((1u << (gb & 31)) - 1u);
+        n += __popc(x);
+    }
+    return n;
+}
+
+__device__ __noinline__ int slow_read(const CountArgs &A, const ReadView &v, uint32_t mapq) {
+    int tc = 0;
+    slow_for_each_hit(A, v, [&](int, bool) { tc++; });
+    const bool is_tc = tc >= A.conv_threshold;
+    if (!is_tc) tc = 0;
+    const int s = v.strand;
+    const uint32_t g = v.g, e = v.g + (uint32_t)v.span;
+    const uint32_t nU = A.n_u[s];
+    uint32_t i = A.bin_first[s][g >> SD_BIN_SHIFT];
+    uint32_t last_seg = 0xFFFFFFFFu;
+    while (i < nU) {
+        const uint32_t st = A.ustart[s][i];
+        if (st >= e) break;
+        const uint32_t en = A.uend[s][i];
+        if (en > g) {
+            const uint32_t a = st > g ? st : g, b = en < e ? en : e;
+            const uint32_t cov_t = slow_count_t(A.refx[s], a, b);
+            uint32_t conv = 0;
+            if (tc > 0)
+                slow_for_each_hit(A, v, [&](int o, bool on_t) {
+                    const uint32_t gp = g + (uint32_t)o;
+                    if (on_t && gp >= a && gp < b) conv++;
+                });
+            utr_accumulate(A.counters, A.urow[s][i], tc > 0 ? 1u : 0u, mapq == 0 ? 1u : 0u, cov_t, conv);
+            const uint32_t seg = A.useg[s][i];
+            if (seg != last_seg) {
+                last_seg = seg;
+                const uint32_t ss = A.seg_start[s][seg], se = A.seg_end[s][seg];
+                const uint64_t off = A.seg_off[s][seg];
+                const uint32_t pa = ss > g ? ss : g, pb = se < e ? se : e;
+                atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
+                atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
+                if (tc > 0)
+                    slow_for_each_hit(A, v, [&](int o, bool on_t) {
+                        const uint32_t gp = g + (uint32_t)o;
+                        if (on_t && gp >= pa && gp < pb) atomicAdd(&A.pos_tc[off + (gp - ss)], 1);
+                    });
+            }
+        }
+        i++;
+    }
+    return tc;
+}
+
+// ---------------------------------------------------------------------------------------
+// Word-parallel path.  W = window words (32 reference bases each).
+// ---------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, uint32_t mapq, uint32_t *scratch,
+                                         bool &mp_disagree) {
+    const int s = v.strand;
+    // --- reference window: isX (T or A) and SNP planes, shifted so that bit j = position g + j
+    uint32_t T[W], S[W];
+    {
+        const uint2 *rx = A.refx[s] + (v.g >> 5);
+        const uint32_t sh = v.g & 31u;
+        uint2 prev = __ldg(rx);
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            const uint2 next = __ldg(rx + k + 1);
+            const uint32_t m = range_word(k, 0, v.span);
+            T[k] = __funnelshift_r(prev.x, next.x, sh) & m;
+            S[k] = __funnelshift_r(prev.y, next.y, sh);
+            prev = next;
+        }
+    }
+    // --- read-side candidate mask in reference coordinates
+    uint32_t R[W];
+    const bool simple = (v.ncig == 1) && cigar_is_match(v.cig[0] & 15u);
+    if (A.mismatch_source == SD_MISMATCH_MP) {
+#pragma unroll
+        for (int k = 0; k < W; k++) R[k] = 0u;
+        if (v.has_mp && v.mp != nullptr) {
+            for (uint32_t i = 0; i < v.nmp; i++) {
+                const uint32_t e = v.mp[i];
+                const int rp = (int)(e & 0xFFFFu), o = (int)(e >> 16);
+                const int q = (rp >= (int)v.lseq) ? 0 : (int)v.qual[rp];
+                if (q >= A.min_qual) {
+#pragma unroll
+                    for (int k = 0; k < W; k++)
+                        if ((o >> 5) == k) R[k] |= 1u << (o & 31);
+                }
+            }
+        }
+    } else {
+        const uint32_t inv = s ? 0xFF00FFFFu : 0xFFFF00FFu;
+        const uint32_t nw8 = (v.lseq + 7u) >> 3;
+        uint32_t M[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+            if (4u * k + 0u < nw8) b0 = sliced_is_base(v.seq[4 * k + 0], inv);
+            if (4u * k + 1u < nw8) b1 = sliced_is_base(v.seq[4 * k + 1], inv);
+            if (4u * k + 2u < nw8) b2 = sliced_is_base(v.seq[4 * k + 2], inv);
+            if (4u * k + 3u < nw8) b3 = sliced_is_base(v.seq[4 * k + 3], inv);
+            M[k] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        }
+        if (simple) {
+#pragma unroll
+            for (int k = 0; k < W; k++) R[k] = M[k];
+        } else {
+            // place every aligned block [q, q+len) of the read at reference offset r
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                R[k] = 0u;
+                scratch[k] = M[k];
+            }
+            scratch[W] = 0u;
+            int q = 0, r = 0;
+            for (uint32_t i = 0; i < v.ncig; i++) {
+                const uint32_t c = v.cig[i], op = c & 15u;
+                const int len = (int)(c >> 4);
+                if (cigar_is_match(op)) {
+#pragma unroll
+                    for (int k = 0; k < W; k++) {
+                        const uint32_t m = range_word(k, r, r + len);
+                        if (m) {
+                            const int b = q - r + 32 * k;  // read-mask bit aligned to window bit 32k
+                            const int idx = b >> 5;        // arithmetic shift: floor
+                            const uint32_t lo = (idx >= 0 && idx <= W) ? scratch[idx] : 0u;
+                            const uint32_t hi = (idx + 1 >= 0 && idx + 1 <= W) ? scratch[idx + 1] : 0u;
+                            R[k] |= __funnelshift_r(lo, hi, (uint32_t)(b & 31)) & m;
+                        }
+                    }
+                    q += len;
+                    r += len;
+                } else if (op == 1 || op == 4) {
+                    q += len;
+                } else if (op == 2 || op == 3) {
+                    r += len;
+                }
+            }
+        }
+    }
+    // --- cross-check against NextGenMap's MP list (before quality / SNP masking)
+    if (A.mismatch_source == SD_MISMATCH_VERIFY && v.has_mp && v.mp != nullptr) {
+        uint32_t D[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) D[k] = R[k] & T[k];
+        bool bad = false;
+        for (uint32_t i = 0; i < v.nmp; i++) {
+            const uint32_t e = v.mp[i];
+            const int rp = (int)(e & 0xFFFFu), o = (int)(e >> 16);
+            bool found = false;
+#pragma unroll
+            for (int k = 0; k < W; k++)
+                if ((o >> 5) == k && ((D[k] >> (o & 31)) & 1u)) {
+                    D[k] &= ~(1u << (o & 31));
+                    found = true;
+                }
+            if (!found || (simple ? o : ref_to_read(v.cig, v.ncig, o)) != rp) bad = true;
+        }
+#pragma unroll
+        for (int k = 0; k < W; k++) bad |= (D[k] != 0u);
+        mp_disagree = bad;
+    }
+    // --- candidates: reference is T (A), read is C (G), not a SNP
+    uint32_t H[W];
+    int tc = 0;
+    if (A.mismatch_source == SD_MISMATCH_MP) {
+        // the reference counts tcCount from the MP entry alone (SlamSeqFile.py:343); the FASTA base is
+        // only consulted when conversions are summed over T positions (tcounter.py:279)
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            const uint32_t h = R[k] & ~S[k];
+            tc += __popc(h);
+            H[k] = h & T[k];
+        }
+    } else {
+        if (!v.has_mp) {
+#pragma unroll
+            for (int k = 0; k < W; k++) R[k] = 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            uint32_t h = R[k] & T[k] & ~S[k];
+            uint32_t rest = h;
+            while (rest) {  // base quality only where a candidate survived
+                const int bit = __ffs(rest) - 1;
+                rest &= rest - 1u;
+                const int o = 32 * k + bit;
+                const int qi = simple ? o : ref_to_read(v.cig, v.ncig, o);
+                if (qi < 0 || qi >= (int)v.lseq || (int)v.qual[qi] < A.min_qual) h &= ~(1u << bit);
+            }
+            H[k] = h;
+            tc += __popc(h);
+        }
+    }
+    if (tc < A.conv_threshold) {  // not a T>C read: conversions are dropped (tcounter.py:210-214)
+        tc = 0;
+#pragma unroll
+        for (int k = 0; k < W; k++) H[k] = 0u;
+    }
+    // --- interval join + per-UTR reduction + per-position scatter
+    const uint32_t g = v.g, e = v.g + (uint32_t)v.span;
+    const uint32_t nU = A.n_u[s];
+    const uint32_t *us = A.ustart[s], *ue = A.uend[s];
+    uint32_t i = __ldg(&A.bin_first[s][g >> SD_BIN_SHIFT]);
+    uint32_t last_seg = 0xFFFFFFFFu;
+    while (i < nU) {
+        const uint32_t st = __ldg(&us[i]);
+        if (st >= e) break;
+        const uint32_t en = __ldg(&ue[i]);
+        if (en > g) {
+            const int lo = st > g ? (int)(st - g) : 0;
+            const int hi = en < e ? (int)(en - g) : v.span;
+            uint32_t cov_t = 0, conv = 0;
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const uint32_t m = range_word(k, lo, hi);
+                cov_t += __popc(T[k] & m);
+                conv += __popc(H[k] & m);
+            }
+            utr_accumulate(A.counters, __ldg(&A.urow[s][i]), tc > 0 ? 1u : 0u, mapq == 0 ? 1u : 0u, cov_t, conv);
+            const uint32_t seg = __ldg(&A.useg[s][i]);
+            if (seg != last_seg) {
+                last_seg = seg;
+                const uint32_t ss = __ldg(&A.seg_start[s][seg]), se = __ldg(&A.seg_end[s][seg]);
+                const uint64_t off = __ldg(&A.seg_off[s][seg]);
+                const uint32_t pa = ss > g ? ss : g, pb = se < e ? se : e;
+                atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
+                atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
+                if (tc > 0) {
+#pragma unroll
+                    for (int k = 0; k < W; k++) {
+                        uint32_t h = H[k] & range_word(k, (int)(pa - g), (int)(pb - g));
+                        while (h) {
+                            const int bit = __ffs(h) - 1;
+                            h &= h - 1u;
+                            atomicAdd(&A.pos_tc[off + (g + 32u * k + bit - ss)], 1);
+                        }
+                    }
+                }
+            }
+        }
+        i++;
+    }
+    return tc;
+}
+
+// ---------------------------------------------------------------------------------------
+// The persistent streaming kernel
+// ---------------------------------------------------------------------------------------
+#define SD_SMEM_STATS 8
+
+template <int W>
+__global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ CountArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_qual + A.cap_cig + A.cap_mp;
+    unsigned char *stages = smem;
+    unsigned char *tail = smem + (size_t)A.n_stages * stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tail);                   // [n_stages]
+    uint32_t *s_stats = reinterpret_cast<uint32_t *>(tail + 64);           // [SD_SMEM_STATS]
+    uint32_t *s_wx = reinterpret_cast<uint32_t *>(tail + 128);             // [8] warp totals (seq words | ncig << 16)
+    unsigned long long *s_wy = reinterpret_cast<unsigned long long *>(tail + 192);  // [8] (qual bytes | nmp << 32)
+    uint32_t *s_scratch = reinterpret_cast<uint32_t *>(tail + 256);        // [blockDim * (W + 1)]
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t nwarps = blockDim.x >> 5;
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < A.n_stages; s++) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    if (tid < SD_SMEM_STATS) s_stats[tid] = 0u;
+    __syncthreads();
+
+    auto issue = [&](uint32_t tile, uint32_t stage) {
+        unsigned char *base = stages + (size_t)stage * stage_bytes;
+        const sd_tile t0 = A.tiles[tile], t1 = A.tiles[tile + 1];
+        const uint32_t b_rec = A.tile_reads * (uint32_t)sizeof(sd_read_rec);
+        const uint32_t b_seq = (uint32_t)(t1.seq_off - t0.seq_off);
+        const uint32_t b_qual = (uint32_t)(t1.qual_off - t0.qual_off);
+        const uint32_t b_cig = (uint32_t)(t1.cig_off - t0.cig_off);
+        const uint32_t b_mp = A.mp ? (uint32_t)(t1.mp_off - t0.mp_off) : 0u;
+        mbar_arrive_expect_tx(&bars[stage], b_rec + b_seq + b_qual + b_cig + b_mp);
+        bulk_g2s(base, reinterpret_cast<const unsigned char *>(A.rec) + (size_t)tile * b_rec, b_rec, &bars[stage]);
+        if (b_seq) bulk_g2s(base + A.cap_rec, reinterpret_cast<const unsigned char *>(A.seq) + t0.seq_off, b_seq, &bars[stage]);
+        if (b_qual) bulk_g2s(base + A.cap_rec + A.cap_seq, A.qual + t0.qual_off, b_qual, &bars[stage]);
+        if (b_cig)
+            bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_qual, reinterpret_cast<const unsigned char *>(A.cigar) + t0.cig_off,
+                     b_cig, &bars[stage]);
+        if (b_mp)
+            bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_qual + A.cap_cig,
+                     reinterpret_cast<const unsigned char *>(A.mp) + t0.mp_off, b_mp, &bars[stage]);
+    };
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < A.n_stages; s++) {
+            const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x;
+            if (t < A.n_tiles) issue((uint32_t)t, s);
+        }
+    }
+
+    uint32_t my_counted = 0, my_slow = 0, my_disagree = 0;
+    unsigned long long my_tc_total = 0;
+    uint32_t stage = 0, phase = 0;
+    for (uint64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+        mbar_wait(&bars[stage], phase);
+        const unsigned char *base = stages + (size_t)stage * stage_bytes;
+        const uint32_t *rw = reinterpret_cast<const uint32_t *>(base) + 5u * tid;
+        const int32_t pos = (int32_t)rw[0];
+        const uint32_t rmf = rw[1];
+        const float xi = __uint_as_float(rw[2]);
+        const uint32_t lseq = rw[3] & 0xFFFFu, ncig = rw[3] >> 16;
+        const uint32_t nm = rw[4] & 0xFFFFu, nmp = A.mp ? (rw[4] >> 16) : 0u;
+
+        // exclusive scan of this read's row sizes over the tile -> row offsets
+        uint32_t x = ((lseq + 7u) >> 3) | (ncig << 16);
+        unsigned long long y = (unsigned long long)lseq | ((unsigned long long)nmp << 32);
+        uint32_t xs = x;
+        unsigned long long ys = y;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t tx = __shfl_up_sync(0xFFFFFFFFu, xs, d);
+            const unsigned long long ty = __shfl_up_sync(0xFFFFFFFFu, ys, d);
+            if (lane >= (uint32_t)d) {
+                xs += tx;
+                ys += ty;
+            }
+        }
+        if (lane == 31) {
+            s_wx[warp] = xs;
+            s_wy[warp] = ys;
+        }
+        __syncthreads();
+        uint32_t xb = 0;
+        unsigned long long yb = 0;
+        for (uint32_t w = 0; w < warp; w++) {
+            xb += s_wx[w];
+            yb += s_wy[w];
+        }
+        xs = xs - x + xb;
+        ys = ys - y + yb;
+
+        const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu, ref = rmf & 0xFFFFu;
+        bool go = !(flags & SD_F_PAD);
+        if (go && A.filter_on) {
+            const bool primary = !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
+            const bool unmapped = (flags & SD_F_UNMAPPED) != 0;
+            if (primary) atomicAdd(&s_stats[unmapped ? SD_S_UNMAPPED : SD_S_MAPPED], 1u);
+            if (unmapped) go = false;
+            else if ((int)mapq < A.filter_mq) { atomicAdd(&s_stats[SD_S_MQFILTERED], 1u); go = false; }
+            else if ((double)xi < A.filter_min_identity) { atomicAdd(&s_stats[SD_S_IDFILTERED], 1u); go = false; }
+            else if (A.filter_max_nm > -1 && (int)nm > A.filter_max_nm) { atomicAdd(&s_stats[SD_S_NMFILTERED], 1u); go = false; }
+            else if (primary) atomicAdd(&s_stats[SD_S_FILTERED], 1u);
+        }
+        if (flags & (SD_F_UNMAPPED | SD_F_SKIP)) go = false;
+        if (ref >= A.n_chrom) go = false;
+
+        int tc = 0;
+        if (go) {
+            const uint32_t clen = __ldg(&A.chrom_len[ref]);
+            if (pos < 0 || (uint32_t)pos >= clen) go = false;
+            else {
+                ReadView v;
+                v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (xs & 0xFFFFu);
+                v.qual = base + A.cap_rec + A.cap_seq + (uint32_t)(ys & 0xFFFFFFFFull);
+                v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_qual) + (xs >> 16);
+                v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_qual + A.cap_cig) +
+                                  (uint32_t)(ys >> 32)
+                            : nullptr;
+                v.lseq = lseq;
+                v.ncig = ncig;
+                v.nmp = nmp;
+                v.g = __ldg(&A.chrom_off[ref]) + (uint32_t)pos;
+                v.strand = (flags & SD_F_REVERSE) ? 1 : 0;
+                v.has_mp = (flags & SD_F_HAS_MP) != 0;
+                uint32_t reflen = 0;
+                for (uint32_t i = 0; i < ncig; i++) {
+                    const uint32_t c = v.cig[i];
+                    if (cigar_consumes_ref(c & 15u)) reflen += c >> 4;
+                }
+                if (reflen == 0) reflen = 1;  // htslib bam_endpos
+                if ((uint64_t)pos + reflen > clen) reflen = clen - (uint32_t)pos;
+                v.span = (int)reflen;
+                bool fits = !A.force_slow && reflen <= 32u * W && lseq <= 32u * W;
+                if (fits && A.mismatch_source == SD_MISMATCH_MP && v.mp) {
+                    for (uint32_t i = 0; i < nmp; i++)
+                        if ((v.mp[i] >> 16) >= 32u * W) fits = false;
+                }
+                my_counted++;
+                if (fits) {
+                    bool bad = false;
+                    tc = fast_read<W>(A, v, mapq, s_scratch + (size_t)tid * (W + 1), bad);
+                    my_disagree += bad ? 1u : 0u;
+                } else {
+                    my_slow++;
+                    tc = slow_read(A, v, mapq);
+                }
+                my_tc_total += (unsigned long long)tc;
+            }
+        }
+        if (A.read_tc) A.read_tc[tile * A.tile_reads + tid] = (uint8_t)(tc > 255 ? 255 : tc);
+
+        __syncthreads();  // every thread is done with this stage
+        if (tid == 0) {
+            const uint64_t next = tile + (uint64_t)A.n_stages * gridDim.x;
+            if (next < A.n_tiles) issue((uint32_t)next, stage);
+        }
+        if (++stage == A.n_stages) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+
+    // flush run-level counters
+    my_counted = __reduce_add_sync(0xFFFFFFFFu, my_counted);
+    my_slow = __reduce_add_sync(0xFFFFFFFFu, my_slow);
+    my_disagree = __reduce_add_sync(0xFFFFFFFFu, my_disagree);
+    for (int d = 16; d > 0; d >>= 1) my_tc_total += __shfl_xor_sync(0xFFFFFFFFu, my_tc_total, d);
+    if (lane == 0) {
+        if (my_counted) atomicAdd(&A.stats[SD_S_COUNTED], (unsigned long long)my_counted);
+        if (my_slow) atomicAdd(&A.stats[SD_S_SLOWPATH], (unsigned long long)my_slow);
+        if (my_disagree) atomicAdd(&A.stats[SD_S_MP_DISAGREE], (unsigned long long)my_disagree);
+        if (my_tc_total) atomicAdd(&A.stats[SD_S_TC_TOTAL], my_tc_total);
+    }
+    __syncthreads();
+    if (tid < 6 && s_stats[tid]) atomicAdd(&A.stats[tid], (unsigned long long)s_stats[tid]);
+    (void)nwarps;
+}
+
+// ---------------------------------------------------------------------------------------
+// small kernels: reference planes, finalize scan, Tcontent
+// ---------------------------------------------------------------------------------------
+__global__ void sd_refx_kernel(const uint32_t *lo, const uint32_t *hi, const uint32_t *nm, uint64_t n_words,
+                               uint2 *rx_plus, uint2 *rx_minus) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words + SD_REF_PAD_WORDS) return;
+    uint32_t t = 0, a = 0;
+    if (i < n_words) {
+        const uint32_t l = lo[i], h = hi[i], n = nm[i];
+        t = l & h & ~n;
+        a = ~l & ~h & ~n;
+    }
+    rx_plus[i] = make_uint2(t, 0u);
+    rx_minus[i] = make_uint2(a, 0u);
+}
+
+__global__ void sd_snp_kernel(const uint32_t *tc, const uint32_t *ag, uint64_t n_words, uint2 *rx_plus, uint2 *rx_minus) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    rx_plus[i].y = tc ? tc[i] : 0u;
+    rx_minus[i].y = ag ? ag[i] : 0u;
+}
+
+// segment-local inclusive prefix sum of the coverage differences; one warp per segment
+__global__ void sd_finalize_kernel(const uint64_t *seg_off0, const uint32_t *seg_start0, const uint32_t *seg_end0, uint32_t n0,
+                                   const uint64_t *seg_off1, const uint32_t *seg_start1, const uint32_t *seg_end1, uint32_t n1,
+                                   int *pos_cov) {
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (wid >= n0 + n1) return;
+    uint64_t off;
+    uint32_t len;
+    if (wid < n0) {
+        off = seg_off0[wid];
+        len = seg_end0[wid] - seg_start0[wid] + 1u;
+    } else {
+        off = seg_off1[wid - n0];
+        len = seg_end1[wid - n0] - seg_start1[wid - n0] + 1u;
+    }
+    int carry = 0;
+    for (uint32_t b = 0; b < len; b += 32) {
+        const uint32_t i = b + lane;
+        int v = i < len ? pos_cov[off + i] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            if (lane >= (uint32_t)d) v += t;
+        }
+        v += carry;
+        if (i < len) pos_cov[off + i] = v;
+        carry = __shfl_sync(0xFFFFFFFFu, v, 31);
+    }
+}
+
+__global__ void sd_tcontent_kernel(const uint2 *rx_plus, const uint2 *rx_minus, const uint32_t *gstart, const uint32_t *gend,
+                                   const uint8_t *strand, uint32_t n, long long *out) {
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (wid >= n) return;
+    const uint32_t a = gstart[wid], b = gend[wid];
+    const uint2 *rx = strand[wid] ? rx_minus : rx_plus;
+    uint32_t cnt = 0;
+    if (b > a) {
+        const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
+        for (uint32_t w = w0 + lane; w <= w1; w += 32) {
+            uint32_t x = rx[w].x;
+            if (w == w0) x &= ~((1u << (a & 31)) - 1u);
+            if (w == w1 && (b & 31)) x &= (1u << (b & 31)) - 1u;
+            cnt += __popc(x);
+        }
+    }
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if (lane == 0) out[wid] = (long long)cnt;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+int sd_fail(sd_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+extern "C" int sd_abi_version(void) { return SD_ABI_VERSION; }
+
+extern "C" const char *sd_last_error(const sd_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int sd_create(int device, void *stream, sd_ctx **out) {
+    if (!out) return SD_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return SD_ERR_CUDA;
+    sd_ctx *ctx = new sd_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return SD_ERR_CUDA; }
+    if (stream) ctx->stream = (cudaStream_t)stream;
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SD_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreate(&ctx->ev_k0);
+    cudaEventCreate(&ctx->ev_k1);
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
+    }
+    cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    *out = ctx;
+    return SD_OK;
+}
+
+static void free_utr_tables(sd_ctx *ctx) {
+    for (int s = 0; s < 2; s++) {
+        cudaFree(ctx->d_ustart[s]); cudaFree(ctx->d_uend[s]); cudaFree(ctx->d_urow[s]); cudaFree(ctx->d_useg[s]);
+        cudaFree(ctx->d_bin_first[s]); cudaFree(ctx->d_seg_start[s]); cudaFree(ctx->d_seg_end[s]); cudaFree(ctx->d_seg_off[s]);
+        ctx->d_ustart[s] = ctx->d_uend[s] = ctx->d_urow[s] = ctx->d_useg[s] = ctx->d_bin_first[s] = nullptr;
+        ctx->d_seg_start[s] = ctx->d_seg_end[s] = nullptr;
+        ctx->d_seg_off[s] = nullptr;
+    }
+    cudaFree(ctx->d_row_gstart); cudaFree(ctx->d_row_gend); cudaFree(ctx->d_row_strand);
+    ctx->d_row_gstart = ctx->d_row_gend = nullptr;
+    ctx->d_row_strand = nullptr;
+}
+
+extern "C" void sd_destroy(sd_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_utr_tables(ctx);
+    cudaFree(ctx->refx[0]); cudaFree(ctx->refx[1]);
+    cudaFree(ctx->d_chrom_off); cudaFree(ctx->d_chrom_len);
+    cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
+    cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_copy[i]); cudaEventDestroy(ctx->ev_done[i]); }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int sd_device_synchronize(sd_ctx *ctx) {
+    if (!ctx) return SD_ERR_ARG;
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+extern "C" int sd_set_reference(sd_ctx *ctx, const uint32_t *d_lo, const uint32_t *d_hi, const uint32_t *d_nmask,
+                                uint64_t n_words, const uint32_t *h_chrom_off, const uint32_t *h_chrom_len, uint32_t n_chrom) {
+    if (!ctx || !d_lo || !d_hi || !d_nmask || !h_chrom_off || !h_chrom_len || n_chrom == 0) return sd_fail(ctx, SD_ERR_ARG, "sd_set_reference: null argument");
+    if (n_chrom >= SD_REF_NONE) return sd_fail(ctx, SD_ERR_LIMIT, "more than %u chromosomes", SD_REF_NONE - 1);
+    if (n_words * 32ull + 4096ull > 0xFFFFFFFFull) return sd_fail(ctx, SD_ERR_LIMIT, "genome exceeds the 32-bit linear coordinate space");
+    for (uint32_t c = 0; c < n_chrom; c++) {
+        if (h_chrom_off[c] & 31u) return sd_fail(ctx, SD_ERR_ARG, "chromosome offset %u not a multiple of 32", c);
+        if ((uint64_t)h_chrom_off[c] + h_chrom_len[c] > n_words * 32ull) return sd_fail(ctx, SD_ERR_ARG, "chromosome %u exceeds the planes", c);
+        if (c + 1 < n_chrom && (uint64_t)h_chrom_off[c] + h_chrom_len[c] + 32ull > h_chrom_off[c + 1])
+            return sd_fail(ctx, SD_ERR_ARG, "chromosomes %u and %u need >= 32 pad positions between them", c, c + 1);
+    }
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaFree(ctx->refx[0]); cudaFree(ctx->refx[1]); cudaFree(ctx->d_chrom_off); cudaFree(ctx->d_chrom_len);
+    ctx->refx[0] = ctx->refx[1] = nullptr;
+    ctx->n_words = n_words;
+    ctx->n_chrom = n_chrom;
+    ctx->chrom_off.assign(h_chrom_off, h_chrom_off + n_chrom);
+    ctx->chrom_len.assign(h_chrom_len, h_chrom_len + n_chrom);
+    const uint64_t tot = n_words + SD_REF_PAD_WORDS;
+    SD_CUDA(ctx, cudaMalloc(&ctx->refx[0], tot * sizeof(uint2)));
+    SD_CUDA(ctx, cudaMalloc(&ctx->refx[1], tot * sizeof(uint2)));
+    SD_CUDA(ctx, cudaMalloc(&ctx->d_chrom_off, n_chrom * sizeof(uint32_t)));
+    SD_CUDA(ctx, cudaMalloc(&ctx->d_chrom_len, n_chrom * sizeof(uint32_t)));
+    SD_CUDA(ctx, cudaMemcpyAsync(ctx->d_chrom_off, h_chrom_off, n_chrom * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(ctx->d_chrom_len, h_chrom_len, n_chrom * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned blocks = (unsigned)((tot + 255) / 256);
+    sd_refx_kernel<<<blocks, 256, 0, ctx->stream>>>(d_lo, d_hi, d_nmask, n_words, ctx->refx[0], ctx->refx[1]);
+    ctx->launches++;
+    SD_CUDA(ctx, cudaGetLastError());
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+extern "C" int sd_set_snps(sd_ctx *ctx, const uint32_t *d_tc_mask, const uint32_t *d_ag_mask) {
+    if (!ctx) return SD_ERR_ARG;
+    if (!ctx->refx[0]) return sd_fail(ctx, SD_ERR_STATE, "sd_set_snps before sd_set_reference");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const unsigned blocks = (unsigned)((ctx->n_words + 255) / 256);
+    sd_snp_kernel<<<blocks, 256, 0, ctx->stream>>>(d_tc_mask, d_ag_mask, ctx->n_words, ctx->refx[0], ctx->refx[1]);
+    ctx->launches++;
+    SD_CUDA(ctx, cudaGetLastError());
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+template <class T>
+static int upload(sd_ctx *ctx, T **dst, const std::vector<T> &v) {
+    const size_t n = v.size() ? v.size() : 1;
+    SD_CUDA(ctx, cudaMalloc(dst, n * sizeof(T)));
+    if (v.size()) SD_CUDA(ctx, cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return SD_OK;
+}
+
+extern "C" int sd_set_utrs(sd_ctx *ctx, const uint32_t *h_chrom, const int64_t *h_start, const int64_t *h_stop,
+                           const uint8_t *h_strand, const uint8_t *h_in_bam, uint32_t n_utr) {
+    if (!ctx || (n_utr && (!h_chrom || !h_start || !h_stop || !h_strand))) return sd_fail(ctx, SD_ERR_ARG, "sd_set_utrs: null argument");
+    if (!ctx->refx[0]) return sd_fail(ctx, SD_ERR_STATE, "sd_set_utrs before sd_set_reference");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    free_utr_tables(ctx);
+    ctx->n_utr = n_utr;
+    ctx->row_pos_off.assign(n_utr, UINT64_MAX);
+    ctx->row_pos_len.assign(n_utr, 0);
+    std::vector<uint32_t> row_gs(n_utr, 0), row_ge(n_utr, 0);
+    std::vector<uint8_t> row_st(n_utr, 0);
+    struct Ent { uint32_t gs, ge, row; };
+    std::vector<Ent> ent[2];
+    for (uint32_t i = 0; i < n_utr; i++) {
+        const int s = h_strand[i] ? 1 : 0;
+        row_st[i] = (uint8_t)s;
+        if (h_chrom[i] >= ctx->n_chrom) continue;
+        const int64_t clen = ctx->chrom_len[h_chrom[i]];
+        int64_t a = h_start[i] < 0 ? 0 : h_start[i];
+        int64_t b = h_stop[i] > clen ? clen : h_stop[i];
+        if (a >= b) continue;  // empty after clipping: no bases, no reads
+        const uint32_t off = ctx->chrom_off[h_chrom[i]];
+        row_gs[i] = off + (uint32_t)a;
+        row_ge[i] = off + (uint32_t)b;
+        ctx->row_pos_len[i] = (uint32_t)(b - a);
+        if (h_in_bam && !h_in_bam[i]) continue;
+        ent[s].push_back({row_gs[i], row_ge[i], i});
+    }
+    const uint64_t total_bits = ctx->n_words * 32ull;
+    ctx->n_bins = (uint32_t)((total_bits >> SD_BIN_SHIFT) + 2);
+    uint64_t pos_total = 0;
+    for (int s = 0; s < 2; s++) {
+        auto &E = ent[s];
+        std::stable_sort(E.begin(), E.end(), [](const Ent &x, const Ent &y) { return x.gs < y.gs || (x.gs == y.gs && x.ge < y.ge); });
+        const uint32_t n = (uint32_t)E.size();
+        std::vector<uint32_t> us(n), ue(n), ur(n), useg(n), maxend(n), sstart, send;
+        std::vector<uint64_t> soff;
+        uint32_t cur_end = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            us[i] = E[i].gs; ue[i] = E[i].ge; ur[i] = E[i].row;
+            maxend[i] = i ? std::max(maxend[i - 1], ue[i]) : ue[i];
+            if (sstart.empty() || us[i] >= cur_end) {  // new merged segment
+                sstart.push_back(us[i]);
+                send.push_back(ue[i]);
+                cur_end = ue[i];
+            } else if (ue[i] > cur_end) {
+                cur_end = ue[i];
+                send.back() = cur_end;
+            }
+            useg[i] = (uint32_t)sstart.size() - 1;
+        }
+        soff.resize(sstart.size());
+        for (size_t m = 0; m < sstart.size(); m++) {
+            soff[m] = pos_total;
+            pos_total += (uint64_t)(send[m] - sstart[m]) + 1ull;
+        }
+        for (uint32_t i = 0; i < n; i++) ctx->row_pos_off[ur[i]] = soff[useg[i]] + (us[i] - sstart[useg[i]]);
+        // bin -> first table index that can still overlap a window starting in the bin
+        std::vector<uint32_t> bins(ctx->n_bins);
+        uint32_t j = 0;
+        for (uint32_t b = 0; b < ctx->n_bins; b++) {
+            const uint64_t bstart = (uint64_t)b << SD_BIN_SHIFT;
+            while (j < n && (uint64_t)maxend[j] <= bstart) j++;
+            bins[b] = j;
+        }
+        ctx->n_u[s] = n;
+        ctx->n_seg[s] = (uint32_t)sstart.size();
+        int rc;
+        if ((rc = upload(ctx, &ctx->d_ustart[s], us))) return rc;
+        if ((rc = upload(ctx, &ctx->d_uend[s], ue))) return rc;
+        if ((rc = upload(ctx, &ctx->d_urow[s], ur))) return rc;
+        if ((rc = upload(ctx, &ctx->d_useg[s], useg))) return rc;
+        if ((rc = upload(ctx, &ctx->d_bin_first[s], bins))) return rc;
+        if ((rc = upload(ctx, &ctx->d_seg_start[s], sstart))) return rc;
+        if ((rc = upload(ctx, &ctx->d_seg_end[s], send))) return rc;
+        if ((rc = upload(ctx, &ctx->d_seg_off[s], soff))) return rc;
+        SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // vectors go out of scope
+    }
+    ctx->n_positions = pos_total;
+    int rc;
+    if ((rc = upload(ctx, &ctx->d_row_gstart, row_gs))) return rc;
+    if ((rc = upload(ctx, &ctx->d_row_gend, row_ge))) return rc;
+    if ((rc = upload(ctx, &ctx->d_row_strand, row_st))) return rc;
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->counters = nullptr;
+    ctx->pos_cov = ctx->pos_tc = nullptr;
+    return SD_OK;
+}
+
+extern "C" int sd_position_space(const sd_ctx *ctx, uint64_t *n_positions) {
+    if (!ctx || !n_positions) return SD_ERR_ARG;
+    *n_positions = ctx->n_positions;
+    return SD_OK;
+}
+
+extern "C" int sd_utr_layout(const sd_ctx *ctx, uint64_t *h_pos_off, uint32_t *h_pos_len) {
+    if (!ctx) return SD_ERR_ARG;
+    for (uint32_t i = 0; i < ctx->n_utr; i++) {
+        if (h_pos_off) h_pos_off[i] = ctx->row_pos_off[i];
+        if (h_pos_len) h_pos_len[i] = ctx->row_pos_len[i];
+    }
+    return SD_OK;
+}
+
+extern "C" int sd_bind_outputs(sd_ctx *ctx, int64_t *d_counters, int32_t *d_pos_cov, int32_t *d_pos_tc, int64_t *d_stats) {
+    if (!ctx || !d_counters || !d_stats) return sd_fail(ctx, SD_ERR_ARG, "sd_bind_outputs: null argument");
+    if (ctx->n_positions && (!d_pos_cov || !d_pos_tc)) return sd_fail(ctx, SD_ERR_ARG, "sd_bind_outputs: position arrays required");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->counters = d_counters;
+    ctx->pos_cov = d_pos_cov;
+    ctx->pos_tc = d_pos_tc;
+    ctx->stats = d_stats;
+    SD_CUDA(ctx, cudaMemsetAsync(d_counters, 0, (size_t)ctx->n_utr * SD_NCOUNTER * sizeof(int64_t), ctx->stream));
+    if (ctx->n_positions) {
+        SD_CUDA(ctx, cudaMemsetAsync(d_pos_cov, 0, ctx->n_positions * sizeof(int32_t), ctx->stream));
+        SD_CUDA(ctx, cudaMemsetAsync(d_pos_tc, 0, ctx->n_positions * sizeof(int32_t), ctx->stream));
+    }
+    SD_CUDA(ctx, cudaMemsetAsync(d_stats, 0, SD_NSTAT * sizeof(int64_t), ctx->stream));
+    return SD_OK;
+}
+
+static inline uint32_t align128(uint32_t x) { return (x + 127u) & ~127u; }
+
+template <int W>
+static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
+    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_qual + A.cap_cig + A.cap_mp;
+    const uint32_t tail = 256 + A.tile_reads * (W + 1) * 4;
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    // stages: as many as fit with two CTAs per SM (>= 2), at most 4
+    uint32_t n_stages = 4;
+    while (n_stages > 2 && (size_t)n_stages * stage_bytes + tail > (size_t)(max_smem / 2 - 1024)) n_stages--;
+    if ((size_t)n_stages * stage_bytes + tail > (size_t)max_smem)
+        return sd_fail(ctx, SD_ERR_LIMIT, "tile needs %u bytes of shared memory per stage; use a smaller tile_reads", stage_bytes);
+    A.n_stages = n_stages;
+    const size_t smem = (size_t)n_stages * stage_bytes + tail;
+    SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W>, (int)A.tile_reads, smem));
+    if (per_sm < 1) return sd_fail(ctx, SD_ERR_LIMIT, "count kernel does not fit on an SM (smem %zu)", smem);
+    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)A.n_tiles, (uint64_t)ctx->num_sms * per_sm);
+    if (timed) SD_CUDA(ctx, cudaEventRecord(ctx->ev_k0, stream));
+    sd_count_kernel<W><<<grid, A.tile_reads, smem, stream>>>(A);
+    if (timed) {
+        SD_CUDA(ctx, cudaEventRecord(ctx->ev_k1, stream));
+        ctx->have_kernel_time = true;
+    }
+    ctx->launches++;
+    SD_CUDA(ctx, cudaGetLastError());
+    return SD_OK;
+}
+
+static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, cudaStream_t stream, uint8_t *read_tc, bool timed) {
+    if (!ctx->refx[0]) return sd_fail(ctx, SD_ERR_STATE, "sd_count before sd_set_reference");
+    if (!ctx->counters) return sd_fail(ctx, SD_ERR_STATE, "sd_count before sd_bind_outputs");
+    if (b->n_tiles == 0) return SD_OK;
+    if (b->tile_reads != 64 && b->tile_reads != 128 && b->tile_reads != 256) return sd_fail(ctx, SD_ERR_ARG, "tile_reads must be 64, 128 or 256");
+    if (p->mismatch_source != SD_MISMATCH_CIGAR && !b->mp) return sd_fail(ctx, SD_ERR_ARG, "mismatch source needs the mp column");
+    CountArgs A;
+    memset(&A, 0, sizeof A);
+    A.rec = b->rec; A.seq = b->seq; A.qual = b->qual; A.cigar = b->cigar;
+    A.mp = (p->mismatch_source == SD_MISMATCH_CIGAR) ? nullptr : b->mp;
+    A.tiles = b->tiles; A.n_tiles = b->n_tiles; A.tile_reads = b->tile_reads;
+    A.cap_rec = align128(b->tile_reads * (uint32_t)sizeof(sd_read_rec));
+    A.cap_seq = align128(b->max_tile_seq);
+    A.cap_qual = align128(b->max_tile_qual);
+    A.cap_cig = align128(b->max_tile_cig);
+    A.cap_mp = A.mp ? align128(b->max_tile_mp) : 0;
+    for (int s = 0; s < 2; s++) {
+        A.refx[s] = ctx->refx[s];
+        A.ustart[s] = ctx->d_ustart[s]; A.uend[s] = ctx->d_uend[s]; A.urow[s] = ctx->d_urow[s]; A.useg[s] = ctx->d_useg[s];
+        A.bin_first[s] = ctx->d_bin_first[s]; A.n_u[s] = ctx->n_u[s];
+        A.seg_start[s] = ctx->d_seg_start[s]; A.seg_end[s] = ctx->d_seg_end[s]; A.seg_off[s] = ctx->d_seg_off[s];
+    }
+    A.chrom_off = ctx->d_chrom_off; A.chrom_len = ctx->d_chrom_len; A.n_chrom = ctx->n_chrom;
+    A.n_bins = ctx->n_bins;
+    A.counters = reinterpret_cast<unsigned long long *>(ctx->counters);
+    A.pos_cov = ctx->pos_cov; A.pos_tc = ctx->pos_tc;
+    A.stats = reinterpret_cast<unsigned long long *>(ctx->stats);
+    A.read_tc = read_tc;
+    A.min_qual = p->min_qual; A.conv_threshold = p->conversion_threshold; A.mismatch_source = p->mismatch_source;
+    A.filter_on = p->filter_on; A.filter_mq = p->filter_mq; A.filter_max_nm = p->filter_max_nm;
+    A.filter_min_identity = p->filter_min_identity; A.force_slow = p->force_slow_path;
+    if (b->max_lseq <= 128) return launch_count<4>(ctx, A, stream, timed);
+    if (b->max_lseq <= 256) return launch_count<8>(ctx, A, stream, timed);
+    return launch_count<16>(ctx, A, stream, timed);
+}
+
+extern "C" int sd_count(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params) {
+    if (!ctx || !d_batch || !params) return sd_fail(ctx, SD_ERR_ARG, "sd_count: null argument");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    return count_on_stream(ctx, d_batch, params, ctx->stream, nullptr, true);
+}
+
+// per-read tcCount output (tests, diagnostics; `alleyoop read-separator` would consume it)
+extern "C" int sd_count_reads(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params, uint8_t *d_read_tc) {
+    if (!ctx || !d_batch || !params) return sd_fail(ctx, SD_ERR_ARG, "sd_count_reads: null argument");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    return count_on_stream(ctx, d_batch, params, ctx->stream, d_read_tc, true);
+}
+
+extern "C" float sd_last_kernel_ms(sd_ctx *ctx) {
+    if (!ctx || !ctx->have_kernel_time) return -1.f;
+    cudaSetDevice(ctx->device);
+    if (cudaEventSynchronize(ctx->ev_k1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+extern "C" int64_t sd_launch_count(const sd_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// Host batch -> device in chunks of whole tiles, double buffered: the copy of chunk i+1 overlaps the
+// kernel of chunk i.  One staging allocation per buffer holds rec | seq | qual | cigar | mp | tiles.
+extern "C" int sd_count_host(sd_ctx *ctx, const sd_batch *hb, const sd_params *params) {
+    if (!ctx || !hb || !params) return sd_fail(ctx, SD_ERR_ARG, "sd_count_host: null argument");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (hb->n_tiles == 0) return SD_OK;
+    const bool use_mp = params->mismatch_source != SD_MISMATCH_CIGAR;
+    if (use_mp && !hb->mp) return sd_fail(ctx, SD_ERR_ARG, "mismatch source needs the mp column");
+    const uint64_t target = 256ull << 20;  // bytes per chunk
+    const sd_tile *T = hb->tiles;
+    const uint64_t rec_tile = (uint64_t)hb->tile_reads * sizeof(sd_read_rec);
+    auto chunk_bytes = [&](uint32_t t0, uint32_t t1) {
+        uint64_t b = (uint64_t)(t1 - t0) * rec_tile + (T[t1].seq_off - T[t0].seq_off) + (T[t1].qual_off - T[t0].qual_off) +
+                     (T[t1].cig_off - T[t0].cig_off) + (uint64_t)(t1 - t0 + 1) * sizeof(sd_tile) + 5 * 256;
+        if (use_mp) b += T[t1].mp_off - T[t0].mp_off;
+        return b;
+    };
+    // chunk boundaries
+    std::vector<uint32_t> cuts{0};
+    {
+        uint32_t t0 = 0;
+        while (t0 < hb->n_tiles) {
+            uint32_t lo = t0 + 1, hi = hb->n_tiles;
+            if (chunk_bytes(t0, hi) > target) {
+                while (lo < hi) {
+                    const uint32_t mid = lo + (hi - lo + 1) / 2;
+                    if (chunk_bytes(t0, mid) <= target) lo = mid; else hi = mid - 1;
+                }
+                hi = lo;
+            }
+            cuts.push_back(hi);
+            t0 = hi;
+        }
+    }
+    uint64_t need = 0;
+    for (size_t c = 0; c + 1 < cuts.size(); c++) need = std::max(need, chunk_bytes(cuts[c], cuts[c + 1]));
+    if (need > ctx->stage_cap) {
+        for (int i = 0; i < 2; i++) { cudaFree(ctx->d_stage[i]); ctx->d_stage[i] = nullptr; }
+        ctx->stage_cap = 0;
+        for (int i = 0; i < 2; i++) SD_CUDA(ctx, cudaMalloc(&ctx->d_stage[i], need));
+        ctx->stage_cap = need;
+    }
+    std::vector<std::vector<sd_tile>> rel_keep(2);
+    auto up256 = [](uint64_t x) { return (x + 255ull) & ~255ull; };
+    for (size_t c = 0; c + 1 < cuts.size(); c++) {
+        const int buf = (int)(c & 1);
+        const uint32_t t0 = cuts[c], t1 = cuts[c + 1], nt = t1 - t0;
+        // the previous kernel that used this buffer must be done before it is overwritten
+        if (c >= 2) SD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[buf], 0));
+        unsigned char *d = (unsigned char *)ctx->d_stage[buf];
+        uint64_t o = 0;
+        sd_batch db = *hb;
+        db.n_tiles = nt;
+        db.n_reads = (uint64_t)nt * hb->tile_reads;
+        const uint64_t b_rec = nt * rec_tile, b_seq = T[t1].seq_off - T[t0].seq_off, b_qual = T[t1].qual_off - T[t0].qual_off,
+                       b_cig = T[t1].cig_off - T[t0].cig_off, b_mp = use_mp ? T[t1].mp_off - T[t0].mp_off : 0;
+        db.rec = (const sd_read_rec *)(d + o);
+        SD_CUDA(ctx, cudaMemcpyAsync(d + o, (const unsigned char *)hb->rec + t0 * rec_tile, b_rec, cudaMemcpyHostToDevice, ctx->copy_stream));
+        o = up256(o + b_rec);
+        db.seq = (const uint32_t *)(d + o);
+        if (b_seq) SD_CUDA(ctx, cudaMemcpyAsync(d + o, (const unsigned char *)hb->seq + T[t0].seq_off, b_seq, cudaMemcpyHostToDevice, ctx->copy_stream));
+        o = up256(o + b_seq);
+        db.qual = (const uint8_t *)(d + o);
+        if (b_qual) SD_CUDA(ctx, cudaMemcpyAsync(d + o, hb->qual + T[t0].qual_off, b_qual, cudaMemcpyHostToDevice, ctx->copy_stream));
+        o = up256(o + b_qual);
+        db.cigar = (const uint32_t *)(d + o);
+        if (b_cig) SD_CUDA(ctx, cudaMemcpyAsync(d + o, (const unsigned char *)hb->cigar + T[t0].cig_off, b_cig, cudaMemcpyHostToDevice, ctx->copy_stream));
+        o = up256(o + b_cig);
+        db.mp = nullptr;
+        if (use_mp) {
+            db.mp = (const uint32_t *)(d + o);
+            if (b_mp) SD_CUDA(ctx, cudaMemcpyAsync(d + o, (const unsigned char *)hb->mp + T[t0].mp_off, b_mp, cudaMemcpyHostToDevice, ctx->copy_stream));
+            o = up256(o + b_mp);
+        }
+        auto &rl = rel_keep[buf];
+        rl.resize(nt + 1);
+        for (uint32_t t = 0; t <= nt; t++) {
+            rl[t].seq_off = T[t0 + t].seq_off - T[t0].seq_off;
+            rl[t].qual_off = T[t0 + t].qual_off - T[t0].qual_off;
+            rl[t].cig_off = T[t0 + t].cig_off - T[t0].cig_off;
+            rl[t].mp_off = T[t0 + t].mp_off - T[t0].mp_off;
+        }
+        db.tiles = (const sd_tile *)(d + o);
+        SD_CUDA(ctx, cudaMemcpyAsync(d + o, rl.data(), (size_t)(nt + 1) * sizeof(sd_tile), cudaMemcpyHostToDevice, ctx->copy_stream));
+        SD_CUDA(ctx, cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
+        SD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
+        int rc = count_on_stream(ctx, &db, params, ctx->stream, nullptr, false);
+        if (rc) return rc;
+        SD_CUDA(ctx, cudaEventRecord(ctx->ev_done[buf], ctx->stream));
+    }
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+extern "C" int sd_finalize(sd_ctx *ctx) {
+    if (!ctx) return SD_ERR_ARG;
+    if (!ctx->pos_cov || ctx->n_seg[0] + ctx->n_seg[1] == 0) return SD_OK;
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t nseg = ctx->n_seg[0] + ctx->n_seg[1];
+    const unsigned blocks = (nseg * 32u + 255u) / 256u;
+    sd_finalize_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_seg_off[0], ctx->d_seg_start[0], ctx->d_seg_end[0], ctx->n_seg[0],
+                                                        ctx->d_seg_off[1], ctx->d_seg_start[1], ctx->d_seg_end[1], ctx->n_seg[1],
+                                                        ctx->pos_cov);
+    ctx->launches++;
+    SD_CUDA(ctx, cudaGetLastError());
+    return SD_OK;
+}
+
+extern "C" int sd_tcontent(sd_ctx *ctx, int64_t *d_tcontent) {
+    if (!ctx || !d_tcontent) return SD_ERR_ARG;
+    if (!ctx->refx[0] || ctx->n_utr == 0) return SD_OK;
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const unsigned blocks = (ctx->n_utr * 32u + 255u) / 256u;
+    sd_tcontent_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->refx[0], ctx->refx[1], ctx->d_row_gstart, ctx->d_row_gend,
+                                                        ctx->d_row_strand, ctx->n_utr, reinterpret_cast<long long *>(d_tcontent));
+    ctx->launches++;
+    SD_CUDA(ctx, cudaGetLastError());
+    return SD_OK;
+}

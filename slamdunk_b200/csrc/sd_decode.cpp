@@ -1,0 +1,645 @@
+// sd_decode.cpp -- host-side decode for the count path: BGZF/BAM -> columnar batch, FASTA -> bit-planes.
+//
+// Takes over what htslib does for the reference behind pysam (AlignmentFile iteration,
+// FastaFile.fetch; call sites slamseq/SlamSeqFile.py:407-441, dunks/tcounter.py:127,181,
+// dunks/filter.py:225-256).  Written against the SAM/BAM specification; C++17 threads + zlib.
+// The decode cost is reported separately from the counting kernels (sd_hbatch.seconds_*).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <atomic>
+#include <chrono>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "slamdunk_b200.h"
+
+namespace {
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int fail(char *err, int errlen, int code, const char *fmt, ...) {
+    if (err && errlen > 0) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(err, (size_t)errlen, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+// Page-locked when a CUDA device is present (async H2D), plain aligned memory otherwise
+// (CPU-only decode tests).
+struct HostAlloc {
+    std::vector<std::pair<void *, bool>> blocks;
+    void *get(size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        bytes = (bytes + 255) & ~(size_t)255;
+        void *p = nullptr;
+        bool pinned = false;
+        static int have_dev = -1;
+        if (have_dev < 0) {
+            int n = 0;
+            have_dev = (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0;
+            cudaGetLastError();
+        }
+        if (have_dev && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) pinned = true;
+        else {
+            cudaGetLastError();
+            if (posix_memalign(&p, 256, bytes) != 0) return nullptr;
+        }
+        blocks.push_back({p, pinned});
+        return p;
+    }
+    ~HostAlloc() {
+        for (auto &b : blocks) {
+            if (b.second) cudaFreeHost(b.first);
+            else free(b.first);
+        }
+    }
+};
+
+template <class F>
+void parallel_for(size_t n, int threads, F f) {
+    if (threads <= 1 || n < 2) {
+        for (size_t i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::atomic<size_t> next(0);
+    const size_t grain = std::max<size_t>(1, n / ((size_t)threads * 16));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&]() {
+            for (;;) {
+                const size_t b = next.fetch_add(grain);
+                if (b >= n) break;
+                const size_t e = std::min(n, b + grain);
+                for (size_t i = b; i < e; i++) f(i);
+            }
+        });
+    for (auto &th : pool) th.join();
+}
+
+inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline int32_t rdi32(const uint8_t *p) { return (int32_t)rd32(p); }
+
+struct AuxInfo {
+    float xi;
+    uint32_t nm;
+    const char *mp;  // MP:Z payload or null
+    bool has_mp;
+};
+
+// Walk the BAM optional fields once.
+bool parse_aux(const uint8_t *p, const uint8_t *end, AuxInfo &a) {
+    a.xi = NAN;
+    a.nm = 0;
+    a.mp = nullptr;
+    a.has_mp = false;
+    while (p + 3 <= end) {
+        const uint8_t t0 = p[0], t1 = p[1], ty = p[2];
+        p += 3;
+        double num = 0;
+        bool is_num = false;
+        switch (ty) {
+            case 'A': case 'c': case 'C': {
+                if (p + 1 > end) return false;
+                num = (ty == 'c') ? (double)(int8_t)p[0] : (double)p[0];
+                is_num = ty != 'A';
+                p += 1;
+                break;
+            }
+            case 's': case 'S': {
+                if (p + 2 > end) return false;
+                num = (ty == 's') ? (double)(int16_t)rd16(p) : (double)rd16(p);
+                is_num = true;
+                p += 2;
+                break;
+            }
+            case 'i': case 'I': {
+                if (p + 4 > end) return false;
+                num = (ty == 'i') ? (double)rdi32(p) : (double)rd32(p);
+                is_num = true;
+                p += 4;
+                break;
+            }
+            case 'f': {
+                if (p + 4 > end) return false;
+                float f;
+                memcpy(&f, p, 4);
+                if (t0 == 'X' && t1 == 'I') a.xi = f;
+                num = f;
+                p += 4;
+                break;
+            }
+            case 'Z': case 'H': {
+                const uint8_t *z = (const uint8_t *)memchr(p, 0, (size_t)(end - p));
+                if (!z) return false;
+                if (ty == 'Z' && t0 == 'M' && t1 == 'P') {
+                    a.mp = (const char *)p;
+                    a.has_mp = true;
+                }
+                p = z + 1;
+                break;
+            }
+            case 'B': {
+                if (p + 5 > end) return false;
+                const uint8_t sub = p[0];
+                const uint32_t n = rd32(p + 1);
+                size_t sz = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+                p += 5 + (size_t)n * sz;
+                if (p > end) return false;
+                break;
+            }
+            default:
+                return false;
+        }
+        if (is_num) {
+            if (t0 == 'N' && t1 == 'M') a.nm = num < 0 ? 0u : (num > 65535.0 ? 65535u : (uint32_t)num);
+            if (t0 == 'X' && t1 == 'I') a.xi = (float)num;
+        }
+    }
+    return true;
+}
+
+// MP:Z is "conv:readPos:refPos,..." (slamseq/SlamSeqFile.py:321-324).  Calls f(readPos-1, refPos-1)
+// for entries whose conv equals `want`.  Returns false on malformed text.
+template <class F>
+bool mp_for_each(const char *s, int want, F f) {
+    while (*s) {
+        long v[3];
+        for (int k = 0; k < 3; k++) {
+            char *e;
+            v[k] = strtol(s, &e, 10);
+            if (e == s) return false;
+            s = e;
+            if (k < 2) {
+                if (*s != ':') return false;
+                s++;
+            }
+        }
+        if (v[0] == want) f(v[1] - 1, v[2] - 1);
+        if (*s == ',') s++;
+        else if (*s) return false;
+    }
+    return true;
+}
+
+struct SliceLut {
+    uint32_t v[256];
+    SliceLut() {
+        for (int b = 0; b < 256; b++) {
+            const int hi = b >> 4, lo = b & 15;  // BAM: first base in the high nibble
+            uint32_t w = 0;
+            for (int p = 0; p < 4; p++) w |= (uint32_t)(((hi >> p) & 1) | (((lo >> p) & 1) << 1)) << (8 * p);
+            v[b] = w;
+        }
+    }
+};
+const SliceLut kSlice;
+
+struct Owner {
+    HostAlloc mem;
+    std::vector<std::string> names;
+    std::vector<char *> name_ptrs;
+    std::vector<uint32_t> lengths;
+    std::string header;
+};
+
+}  // namespace
+
+extern "C" void sd_hbatch_free(sd_hbatch *hb) {
+    if (!hb) return;
+    delete (Owner *)hb->opaque;
+    delete hb;
+}
+
+extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, uint32_t n_fasta, int want_mp,
+                             uint32_t tile_reads, int threads, sd_hbatch **out, char *err, int errlen) {
+    if (!path || !out) return fail(err, errlen, SD_ERR_ARG, "sd_decode_bam: null argument");
+    *out = nullptr;
+    if (tile_reads != 64 && tile_reads != 128 && tile_reads != 256) return fail(err, errlen, SD_ERR_ARG, "tile_reads must be 64, 128 or 256");
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const double t0 = now_s();
+
+    // ---- read the file
+    FILE *fh = fopen(path, "rb");
+    if (!fh) return fail(err, errlen, SD_ERR_IO, "cannot open %s", path);
+    fseek(fh, 0, SEEK_END);
+    const long fsz = ftell(fh);
+    fseek(fh, 0, SEEK_SET);
+    std::vector<uint8_t> file((size_t)fsz);
+    if (fsz > 0 && fread(file.data(), 1, (size_t)fsz, fh) != (size_t)fsz) {
+        fclose(fh);
+        return fail(err, errlen, SD_ERR_IO, "short read on %s", path);
+    }
+    fclose(fh);
+
+    // ---- BGZF block table
+    struct Blk { size_t coff, clen, uoff, ulen; };
+    std::vector<Blk> blks;
+    size_t off = 0, utotal = 0;
+    while (off < file.size()) {
+        const uint8_t *h = file.data() + off;
+        if (off + 18 > file.size() || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4))
+            return fail(err, errlen, SD_ERR_FORMAT, "%s: not a BGZF block at offset %zu", path, off);
+        const uint32_t xlen = rd16(h + 10);
+        int bsize = -1;
+        size_t x = 12;
+        while (x + 4 <= 12 + (size_t)xlen) {
+            const uint32_t slen = rd16(h + x + 2);
+            if (h[x] == 66 && h[x + 1] == 67 && slen == 2) bsize = rd16(h + x + 4);
+            x += 4 + slen;
+        }
+        if (bsize < 0 || off + (size_t)bsize + 1 > file.size())
+            return fail(err, errlen, SD_ERR_FORMAT, "%s: truncated BGZF block at offset %zu", path, off);
+        const size_t total = (size_t)bsize + 1;
+        const uint32_t isize = rd32(h + total - 4);
+        blks.push_back({off + 12 + xlen, total - 12 - xlen - 8, utotal, isize});
+        utotal += isize;
+        off += total;
+    }
+    std::vector<uint8_t> raw(utotal);
+    std::atomic<int> bad(0);
+    parallel_for(blks.size(), threads, [&](size_t i) {
+        const Blk &b = blks[i];
+        if (b.ulen == 0) return;
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+        zs.next_in = file.data() + b.coff;
+        zs.avail_in = (uInt)b.clen;
+        zs.next_out = raw.data() + b.uoff;
+        zs.avail_out = (uInt)b.ulen;
+        const int rc = inflate(&zs, Z_FINISH);
+        if (rc != Z_STREAM_END || zs.avail_out != 0) bad = 1;
+        inflateEnd(&zs);
+        const uint32_t crc = rd32(file.data() + b.coff + b.clen);
+        if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), raw.data() + b.uoff, (uInt)b.ulen) != crc) bad = 1;
+    });
+    if (bad) return fail(err, errlen, SD_ERR_FORMAT, "%s: corrupt BGZF block", path);
+    const size_t compressed = file.size();
+    std::vector<uint8_t>().swap(file);
+    const double t1 = now_s();
+
+    // ---- BAM header
+    if (raw.size() < 12 || memcmp(raw.data(), "BAM\1", 4) != 0) return fail(err, errlen, SD_ERR_FORMAT, "%s: not a BAM file", path);
+    Owner *own = new Owner();
+    sd_hbatch *hb = new sd_hbatch();
+    memset(hb, 0, sizeof *hb);
+    hb->opaque = own;
+    auto bail = [&](int code, const char *msg) {
+        sd_hbatch_free(hb);
+        return fail(err, errlen, code, "%s: %s", path, msg);
+    };
+    size_t p = 4;
+    const int32_t l_text = rdi32(raw.data() + p);
+    p += 4;
+    if (l_text < 0 || p + (size_t)l_text + 4 > raw.size()) return bail(SD_ERR_FORMAT, "bad header length");
+    own->header.assign((const char *)raw.data() + p, strnlen((const char *)raw.data() + p, (size_t)l_text));
+    p += (size_t)l_text;
+    const int32_t n_ref = rdi32(raw.data() + p);
+    p += 4;
+    if (n_ref < 0) return bail(SD_ERR_FORMAT, "bad reference count");
+    std::unordered_map<std::string, uint32_t> fasta_idx;
+    for (uint32_t i = 0; i < n_fasta; i++) fasta_idx.emplace(fasta_names[i], i);
+    std::vector<uint32_t> ref_map((size_t)n_ref, SD_REF_NONE);
+    for (int32_t i = 0; i < n_ref; i++) {
+        if (p + 4 > raw.size()) return bail(SD_ERR_FORMAT, "truncated reference table");
+        const int32_t l_name = rdi32(raw.data() + p);
+        if (l_name < 1 || p + 4 + (size_t)l_name + 4 > raw.size()) return bail(SD_ERR_FORMAT, "truncated reference table");
+        std::string nm((const char *)raw.data() + p + 4, (size_t)l_name - 1);
+        own->lengths.push_back(rd32(raw.data() + p + 4 + l_name));
+        auto it = fasta_idx.find(nm);
+        if (it != fasta_idx.end()) ref_map[(size_t)i] = it->second;
+        own->names.push_back(nm);
+        p += 8 + (size_t)l_name;
+    }
+    for (auto &s : own->names) own->name_ptrs.push_back(const_cast<char *>(s.c_str()));
+    hb->header_text = const_cast<char *>(own->header.c_str());
+    hb->n_ref = (uint32_t)n_ref;
+    hb->ref_names = own->name_ptrs.data();
+    hb->ref_lengths = own->lengths.data();
+
+    // ---- record index
+    std::vector<size_t> recoff;
+    while (p + 4 <= raw.size()) {
+        const int32_t bs = rdi32(raw.data() + p);
+        if (bs < 32 || p + 4 + (size_t)bs > raw.size()) return bail(SD_ERR_FORMAT, "truncated alignment record");
+        recoff.push_back(p + 4);
+        p += 4 + (size_t)bs;
+    }
+    const size_t n = recoff.size();
+    const size_t n_tiles = (n + tile_reads - 1) / tile_reads;
+    if (n_tiles > 0xFFFFFFF0ull) return bail(SD_ERR_LIMIT, "too many records for one batch");
+
+    sd_read_rec *rec = (sd_read_rec *)own->mem.get(std::max<size_t>(1, n_tiles) * tile_reads * sizeof(sd_read_rec));
+    uint64_t *name_hash = (uint64_t *)own->mem.get(std::max<size_t>(1, n) * sizeof(uint64_t));
+    sd_tile *tiles = (sd_tile *)own->mem.get((n_tiles + 1) * sizeof(sd_tile));
+    if (!rec || !name_hash || !tiles) return bail(SD_ERR_NOMEM, "out of host memory");
+    std::vector<const char *> mp_ptr(n, nullptr);
+    std::atomic<int> fmt_err(0), limit_err(0);
+
+    // ---- pass A: fixed-size fields, tags, sizes
+    parallel_for(n, threads, [&](size_t i) {
+        const uint8_t *r = raw.data() + recoff[i];
+        const uint32_t bs = rd32(r - 4);
+        const int32_t ref_id = rdi32(r), pos = rdi32(r + 4);
+        const uint32_t l_name = r[8], mapq = r[9], n_cig = rd16(r + 12), flag = rd16(r + 14);
+        const int32_t l_seq = rdi32(r + 16);
+        const uint8_t *name = r + 32;
+        const uint8_t *cig = name + l_name;
+        const uint8_t *seq = cig + 4 * (size_t)n_cig;
+        const uint8_t *qual = seq + ((size_t)(l_seq > 0 ? l_seq : 0) + 1) / 2;
+        const uint8_t *aux = qual + (size_t)(l_seq > 0 ? l_seq : 0);
+        const uint8_t *end = r + bs;
+        if (l_seq < 0 || aux > end) { fmt_err = 1; return; }
+        if (l_seq > 65535) { limit_err = 1; return; }
+        AuxInfo a;
+        if (!parse_aux(aux, end, a)) { fmt_err = 1; return; }
+        uint32_t f = 0;
+        if (flag & 0x10) f |= SD_F_REVERSE;
+        if ((flag & 0x4) || n_cig == 0 || ref_id < 0) f |= SD_F_UNMAPPED;
+        if (flag & 0x100) f |= SD_F_SECONDARY;
+        if (flag & 0x800) f |= SD_F_SUPPLEMENTARY;
+        if (a.has_mp) f |= SD_F_HAS_MP;
+        uint32_t ref = SD_REF_NONE;
+        if (ref_id >= 0 && ref_id < n_ref) ref = ref_map[(size_t)ref_id];
+        if (ref == SD_REF_NONE) f |= SD_F_SKIP;
+        // query-name run boundaries (multimapper grouping, dunks/filter.py:115)
+        uint64_t h = 1469598103934665603ULL;
+        for (uint32_t k = 0; k + 1 < l_name; k++) { h ^= name[k]; h *= 1099511628211ULL; }
+        name_hash[i] = h;
+        bool newname = true;
+        if (i > 0) {
+            const uint8_t *pr = raw.data() + recoff[i - 1];
+            newname = !(pr[8] == l_name && memcmp(pr + 32, name, l_name) == 0);
+        }
+        if (newname) f |= SD_F_NEWNAME;
+        uint32_t nmp = 0;
+        if (want_mp && a.has_mp) {
+            bool range_ok = true;
+            if (!mp_for_each(a.mp, (flag & 0x10) ? 2 : 16, [&](long rp, long fp) {
+                    nmp++;
+                    if (rp < 0 || rp > 65535 || fp < 0 || fp > 65535) range_ok = false;
+                }))
+                { fmt_err = 1; return; }
+            if (!range_ok || nmp > 65535) { limit_err = 1; return; }
+            mp_ptr[i] = a.mp;
+        }
+        sd_read_rec &o = rec[i];
+        o.pos = pos;
+        o.ref_mapq_flag = (ref & 0xFFFFu) | (mapq << 16) | (f << 24);
+        o.xi = a.xi;
+        o.lseq_ncig = (uint32_t)l_seq | (n_cig << 16);
+        o.nm_nmp = a.nm | (nmp << 16);
+    });
+    if (fmt_err) return bail(SD_ERR_FORMAT, "malformed alignment record or tag");
+    if (limit_err) return bail(SD_ERR_LIMIT, "read longer than 65535 bases (or MP position out of range)");
+    for (size_t i = n; i < n_tiles * tile_reads; i++) {
+        rec[i].pos = 0;
+        rec[i].ref_mapq_flag = (uint32_t)SD_REF_NONE | ((uint32_t)(SD_F_PAD | SD_F_SKIP | SD_F_UNMAPPED) << 24);
+        rec[i].xi = 0.f;
+        rec[i].lseq_ncig = 0;
+        rec[i].nm_nmp = 0;
+    }
+
+    // ---- tile offsets
+    auto up16 = [](uint64_t x) { return (x + 15ull) & ~15ull; };
+    uint32_t max_lseq = 0, mt_seq = 0, mt_qual = 0, mt_cig = 0, mt_mp = 0;
+    {
+        sd_tile cur = {0, 0, 0, 0};
+        for (size_t t = 0; t < n_tiles; t++) {
+            tiles[t] = cur;
+            uint64_t bs = 0, bq = 0, bc = 0, bm = 0;
+            const size_t e = std::min(n, (t + 1) * (size_t)tile_reads);
+            for (size_t i = t * (size_t)tile_reads; i < e; i++) {
+                const uint32_t ls = rec[i].lseq_ncig & 0xFFFFu;
+                max_lseq = std::max(max_lseq, ls);
+                bs += 4ull * ((ls + 7u) >> 3);
+                bq += ls;
+                bc += 4ull * (rec[i].lseq_ncig >> 16);
+                bm += 4ull * (rec[i].nm_nmp >> 16);
+            }
+            bs = up16(bs); bq = up16(bq); bc = up16(bc); bm = up16(bm);
+            mt_seq = std::max<uint32_t>(mt_seq, (uint32_t)bs);
+            mt_qual = std::max<uint32_t>(mt_qual, (uint32_t)bq);
+            mt_cig = std::max<uint32_t>(mt_cig, (uint32_t)bc);
+            mt_mp = std::max<uint32_t>(mt_mp, (uint32_t)bm);
+            cur.seq_off += bs; cur.qual_off += bq; cur.cig_off += bc; cur.mp_off += bm;
+        }
+        tiles[n_tiles] = cur;
+    }
+    const sd_tile tot = tiles[n_tiles];
+    uint32_t *seqc = (uint32_t *)own->mem.get(tot.seq_off + 16);
+    uint8_t *qualc = (uint8_t *)own->mem.get(tot.qual_off + 16);
+    uint32_t *cigc = (uint32_t *)own->mem.get(tot.cig_off + 16);
+    uint32_t *mpc = want_mp ? (uint32_t *)own->mem.get(tot.mp_off + 16) : nullptr;
+    if (!seqc || !qualc || !cigc || (want_mp && !mpc)) return bail(SD_ERR_NOMEM, "out of host memory");
+
+    // ---- pass B: variable-length columns, one tile at a time
+    parallel_for(n_tiles, threads, [&](size_t t) {
+        uint8_t *ps = (uint8_t *)seqc + tiles[t].seq_off;
+        uint8_t *pq = qualc + tiles[t].qual_off;
+        uint8_t *pc = (uint8_t *)cigc + tiles[t].cig_off;
+        uint8_t *pm = mpc ? (uint8_t *)mpc + tiles[t].mp_off : nullptr;
+        const size_t e = std::min(n, (t + 1) * (size_t)tile_reads);
+        for (size_t i = t * (size_t)tile_reads; i < e; i++) {
+            const uint8_t *r = raw.data() + recoff[i];
+            const uint32_t l_name = r[8], n_cig = rd16(r + 12), flag = rd16(r + 14);
+            const uint32_t l_seq = rd32(r + 16);
+            const uint8_t *cig = r + 32 + l_name;
+            const uint8_t *seq = cig + 4 * (size_t)n_cig;
+            const uint8_t *qual = seq + ((size_t)l_seq + 1) / 2;
+            memcpy(pc, cig, 4 * (size_t)n_cig);
+            pc += 4 * (size_t)n_cig;
+            memcpy(pq, qual, l_seq);
+            pq += l_seq;
+            const uint32_t nbytes = (l_seq + 1) / 2;
+            for (uint32_t w = 0; w < (l_seq + 7) / 8; w++) {
+                uint32_t v = 0;
+                for (uint32_t k = 0; k < 4; k++) {
+                    const uint32_t bi = 4 * w + k;
+                    if (bi < nbytes) {
+                        uint8_t b = seq[bi];
+                        if (2 * bi + 1 >= l_seq) b &= 0xF0;  // odd length: ignore the pad nibble
+                        v |= kSlice.v[b] << (2 * k);
+                    }
+                }
+                memcpy(ps, &v, 4);
+                ps += 4;
+            }
+            if (pm && mp_ptr[i]) {
+                mp_for_each(mp_ptr[i], (flag & 0x10) ? 2 : 16, [&](long rp, long fp) {
+                    const uint32_t v = (uint32_t)rp | ((uint32_t)fp << 16);
+                    memcpy(pm, &v, 4);
+                    pm += 4;
+                });
+            }
+        }
+        // zero the 16-byte tile padding so the columns are deterministic
+        memset(ps, 0, (size_t)(((uint8_t *)seqc + tiles[t + 1].seq_off) - ps));
+        memset(pq, 0, (size_t)((qualc + tiles[t + 1].qual_off) - pq));
+        memset(pc, 0, (size_t)(((uint8_t *)cigc + tiles[t + 1].cig_off) - pc));
+        if (pm) memset(pm, 0, (size_t)(((uint8_t *)mpc + tiles[t + 1].mp_off) - pm));
+    });
+    const double t2 = now_s();
+
+    hb->batch.n_reads = n;
+    hb->batch.n_tiles = (uint32_t)n_tiles;
+    hb->batch.tile_reads = tile_reads;
+    hb->batch.rec = rec;
+    hb->batch.seq = seqc;
+    hb->batch.qual = qualc;
+    hb->batch.cigar = cigc;
+    hb->batch.mp = mpc;
+    hb->batch.tiles = tiles;
+    hb->batch.max_lseq = max_lseq;
+    hb->batch.max_tile_seq = mt_seq;
+    hb->batch.max_tile_qual = mt_qual;
+    hb->batch.max_tile_cig = mt_cig;
+    hb->batch.max_tile_mp = mt_mp;
+    hb->name_hash = name_hash;
+    hb->seconds_inflate = t1 - t0;
+    hb->seconds_decode = t2 - t1;
+    hb->compressed_bytes = compressed;
+    hb->inflated_bytes = utotal;
+    *out = hb;
+    return SD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// FASTA -> bit-planes
+// ------------------------------------------------------------------------------------------
+namespace {
+struct GenomeOwner {
+    HostAlloc mem;
+    std::vector<std::string> names;
+    std::vector<char *> name_ptrs;
+    std::vector<uint32_t> len, off;
+};
+}  // namespace
+
+extern "C" void sd_hgenome_free(sd_hgenome *g) {
+    if (!g) return;
+    delete (GenomeOwner *)g->opaque;
+    delete g;
+}
+
+extern "C" int sd_load_fasta(const char *path, int threads, sd_hgenome **out, char *err, int errlen) {
+    if (!path || !out) return fail(err, errlen, SD_ERR_ARG, "sd_load_fasta: null argument");
+    *out = nullptr;
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const double t0 = now_s();
+    FILE *fh = fopen(path, "rb");
+    if (!fh) return fail(err, errlen, SD_ERR_IO, "cannot open %s", path);
+    fseek(fh, 0, SEEK_END);
+    const long fsz = ftell(fh);
+    fseek(fh, 0, SEEK_SET);
+    std::vector<char> txt((size_t)fsz + 1);
+    if (fsz > 0 && fread(txt.data(), 1, (size_t)fsz, fh) != (size_t)fsz) {
+        fclose(fh);
+        return fail(err, errlen, SD_ERR_IO, "short read on %s", path);
+    }
+    fclose(fh);
+    txt[(size_t)fsz] = '\n';
+
+    // pass 1: record boundaries and lengths (whitespace inside sequence lines is skipped)
+    struct Rec { size_t body, end; uint64_t len; };
+    std::vector<Rec> recs;
+    GenomeOwner *own = new GenomeOwner();
+    {
+        size_t i = 0;
+        const size_t n = (size_t)fsz;
+        while (i < n) {
+            if (txt[i] == '>') {
+                size_t e = i + 1;
+                while (e < n && txt[e] != '\n') e++;
+                size_t ne = i + 1;
+                while (ne < e && txt[ne] != ' ' && txt[ne] != '\t' && txt[ne] != '\r') ne++;
+                own->names.emplace_back(txt.data() + i + 1, ne - i - 1);
+                recs.push_back({e + 1, n, 0});
+                if (recs.size() > 1) recs[recs.size() - 2].end = i;
+                i = e + 1;
+            } else {
+                while (i < n && txt[i] != '\n') i++;
+                i++;
+            }
+        }
+    }
+    if (recs.empty()) { delete own; return fail(err, errlen, SD_ERR_FORMAT, "%s: no FASTA records", path); }
+    parallel_for(recs.size(), threads, [&](size_t r) {
+        uint64_t L = 0;
+        for (size_t i = recs[r].body; i < recs[r].end && i < (size_t)fsz; i++) {
+            const char c = txt[i];
+            if (c != '\n' && c != '\r' && c != ' ' && c != '\t') L++;
+        }
+        recs[r].len = L;
+    });
+    uint64_t bits = 32;  // leading pad so that no chromosome starts at linear position 0
+    for (auto &r : recs) {
+        if (r.len > 0xFFFFFFF0ull) { delete own; return fail(err, errlen, SD_ERR_LIMIT, "chromosome too long"); }
+        own->off.push_back((uint32_t)bits);
+        own->len.push_back((uint32_t)r.len);
+        bits = ((bits + r.len + 31ull) & ~31ull) + 32ull;
+        if (bits + 4096ull > 0xFFFFFFFFull) { delete own; return fail(err, errlen, SD_ERR_LIMIT, "genome exceeds the 32-bit linear coordinate space"); }
+    }
+    const uint64_t n_words = bits / 32;
+    uint32_t *lo = (uint32_t *)own->mem.get(n_words * 4), *hi = (uint32_t *)own->mem.get(n_words * 4),
+             *nm = (uint32_t *)own->mem.get(n_words * 4);
+    if (!lo || !hi || !nm) { delete own; return fail(err, errlen, SD_ERR_NOMEM, "out of host memory"); }
+    memset(lo, 0, n_words * 4);
+    memset(hi, 0, n_words * 4);
+    memset(nm, 0xFF, n_words * 4);
+    // pass 2: encode (chromosomes start on word boundaries, so records are independent)
+    parallel_for(recs.size(), threads, [&](size_t r) {
+        uint64_t g = own->off[r];
+        uint32_t wl = 0, wh = 0, wn = 0;
+        int nb = 0;
+        auto flush = [&](uint64_t word) {
+            lo[word] = wl;
+            hi[word] = wh;
+            nm[word] = wn | (nb < 32 ? (0xFFFFFFFFu << nb) : 0u);
+            wl = wh = wn = 0;
+            nb = 0;
+        };
+        for (size_t i = recs[r].body; i < recs[r].end && i < (size_t)fsz; i++) {
+            char c = txt[i];
+            if (c == '\n' || c == '\r' || c == ' ' || c == '\t') continue;
+            c = (char)(c & ~0x20);  // upper-case ASCII letters (tcounter.py:181)
+            uint32_t code = 4;
+            if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2; else if (c == 'T') code = 3;
+            if (code < 4) {
+                wl |= (code & 1u) << nb;
+                wh |= (code >> 1) << nb;
+            } else wn |= 1u << nb;
+            nb++;
+            g++;
+            if (nb == 32) flush((g - 1) >> 5);
+        }
+        if (nb) flush(g >> 5);
+    });
+    for (auto &s : own->names) own->name_ptrs.push_back(const_cast<char *>(s.c_str()));
+    sd_hgenome *G = new sd_hgenome();
+    memset(G, 0, sizeof *G);
+    G->n_chrom = (uint32_t)recs.size();
+    G->names = own->name_ptrs.data();
+    G->chrom_len = own->len.data();
+    G->chrom_off = own->off.data();
+    G->n_words = n_words;
+    G->lo = lo; G->hi = hi; G->nmask = nm;
+    G->seconds = now_s() - t0;
+    G->opaque = own;
+    *out = G;
+    return SD_OK;
+}

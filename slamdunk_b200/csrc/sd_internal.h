@@ -1,0 +1,67 @@
+// Internal declarations shared by the translation units of libslamdunk_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "slamdunk_b200.h"
+
+#define SD_BIN_SHIFT 10   // interval-join bins of 1024 bp over the linear genome
+#define SD_REF_PAD_WORDS 64
+
+struct sd_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    bool have_kernel_time = false;
+    std::string err;
+    int num_sms = 0;
+    int64_t launches = 0;
+
+    // reference: per strand {isX, snpX} per 32 bp; strand 0: X = T / T>C SNPs, strand 1: X = A / A>G SNPs
+    uint2 *refx[2] = {nullptr, nullptr};
+    uint64_t n_words = 0;
+    std::vector<uint32_t> chrom_off, chrom_len;
+    uint32_t *d_chrom_off = nullptr, *d_chrom_len = nullptr;
+    uint32_t n_chrom = 0;
+
+    // annotation tables, per strand, sorted by global start
+    uint32_t n_utr = 0;
+    uint32_t n_u[2] = {0, 0};
+    uint32_t *d_ustart[2] = {nullptr, nullptr}, *d_uend[2] = {nullptr, nullptr};
+    uint32_t *d_urow[2] = {nullptr, nullptr}, *d_useg[2] = {nullptr, nullptr};
+    uint32_t *d_bin_first[2] = {nullptr, nullptr};
+    uint32_t n_bins = 0;
+    uint32_t n_seg[2] = {0, 0};
+    uint32_t *d_seg_start[2] = {nullptr, nullptr}, *d_seg_end[2] = {nullptr, nullptr};
+    uint64_t *d_seg_off[2] = {nullptr, nullptr};
+    uint64_t n_positions = 0;
+    // all BED rows (for Tcontent and host layout)
+    uint32_t *d_row_gstart = nullptr, *d_row_gend = nullptr;
+    uint8_t *d_row_strand = nullptr;
+    std::vector<uint64_t> row_pos_off;
+    std::vector<uint32_t> row_pos_len;
+
+    // caller-owned outputs
+    int64_t *counters = nullptr;
+    int32_t *pos_cov = nullptr, *pos_tc = nullptr;
+    int64_t *stats = nullptr;
+
+    // staging for sd_count_host
+    void *d_stage[2] = {nullptr, nullptr};
+    size_t stage_cap = 0;
+};
+
+int sd_fail(sd_ctx *ctx, int code, const char *fmt, ...);
+#define SD_CUDA(ctx, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return sd_fail((ctx), SD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                           __FILE__, __LINE__);                                                   \
+    } while (0)

@@ -1,0 +1,224 @@
+"""`slamdunk count` on the GPU: drop-in for the reference's tcounter.computeTconversions
+(slamdunk/dunks/tcounter.py:125-330), same positional signature, same three output files.
+
+What happens where
+  host   BAM / FASTA decode (C++ threads, libslamdunk_b200.so), BED / VCF parsing with the
+         reference's quirks, and every floating-point division + all text formatting, so the files
+         are byte-identical to the reference's (str(float) of the same Python expressions);
+  device filter predicates (optional), per-read T>C scan, interval join, per-UTR counters and the
+         per-position coverage / conversion arrays (sd_count / sd_finalize / sd_tcontent).
+"""
+from __future__ import print_function
+
+import os
+import time
+
+import numpy as np
+
+from .. import _lib as L
+from ..engine import CountEngine, HostBatch, HostGenome, make_params
+from ..utils.BedReader import BedIterator
+from ..utils.SNPtools import build_snp_masks
+from ..utils.misc import SlamSeqInfo, getSampleInfo, md5, parse_sam_header
+from ..version import __bam_version__, __count_version__, __version__
+
+HEADER = "\t".join(["Chromosome", "Start", "End", "Name", "Length", "Strand", "ConversionRate", "ReadsCPM", "Tcontent",
+                    "CoverageOnTs", "ConversionsOnTs", "ReadCount", "TcReadCount", "multimapCount",
+                    "ConversionRateLower", "ConversionRateUpper"])   # SlamSeqFile.py:80
+
+
+class NegativeStartError(RuntimeError, TypeError):
+    """tcounter.py:172-173 means to raise RuntimeError but concatenates str + BedEntry, so the
+    reference actually dies with TypeError; this is both."""
+
+
+def _row(utr, conversionRate, readsCPM, Tcontent, coverageOnTs, conversionsOnTs, readCount, tcReadCount, multimapCount):
+    """SlamSeqInterval.__repr__ (slamseq/SlamSeqFile.py:99-100)."""
+    return "\t".join([utr.chromosome, str(utr.start), str(utr.stop), utr.name, str(utr.stop - utr.start), utr.strand,
+                      str(conversionRate), str(readsCPM), str(Tcontent), str(coverageOnTs), str(conversionsOnTs),
+                      str(readCount), str(tcReadCount), str(multimapCount), str(-1.0), str(-1.0)])
+
+
+class CountTimings(dict):
+    pass
+
+
+# knobs that are not part of the reference signature (set by the CLI / tests)
+OPTIONS = {
+    "device": 0,
+    "threads": 0,                       # host decode threads (0 = all cores)
+    "mismatch_source": "verify",        # "cigar" | "mp" | "verify" (CIGAR walk cross-checked against MP)
+    "timings": None,                    # last run's CountTimings
+}
+
+
+def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputCSV, outputBedgraphPlus,
+                        outputBedgraphMinus, conversionThreshold, log, mle=False):
+    if mle:
+        raise NotImplementedError("mle=True (per-read output + R MLE fit) is not part of the GPU count path")
+    tm = CountTimings()
+    t0 = time.time()
+
+    genome = HostGenome(ref, OPTIONS["threads"])
+    tm["fasta_decode_s"] = genome.seconds
+    mode = {"cigar": L.SD_MISMATCH_CIGAR, "mp": L.SD_MISMATCH_MP, "verify": L.SD_MISMATCH_VERIFY}[OPTIONS["mismatch_source"]]
+    hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"])
+    tm["bam_inflate_s"] = hbatch.seconds_inflate
+    tm["bam_decode_s"] = hbatch.seconds_decode
+    tm["bam_reads"] = hbatch.n_reads
+
+    header = parse_sam_header(hbatch.header_text)
+    sampleInfo = getSampleInfo(header)                       # tcounter.py:129
+    slamseqInfo = SlamSeqInfo(header)                        # tcounter.py:131
+    readNumber = slamseqInfo.FilteredReads                   # tcounter.py:133
+    bedMD5 = md5(bed)
+
+    fileCSV = open(outputCSV, "w")
+    print("#slamdunk v" + __version__, __count_version__, "sample info:", sampleInfo.Name, sampleInfo.ID,
+          sampleInfo.Type, sampleInfo.Time, sep="\t", file=fileCSV)
+    print("#annotation:", os.path.basename(bed), bedMD5, sep="\t", file=fileCSV)
+    print(HEADER, file=fileCSV)
+
+    tc_mask, ag_mask = build_snp_masks(snpsFile, genome.names, genome.chrom_off, genome.chrom_len, genome.n_words,
+                                       warn=print)          # SNPtools.py:40-51
+
+    bamVersion = "None"                                      # SlamSeqFile.py:409-414
+    for pg in header.get("PG", []):
+        if pg.get("ID") == "slamdunk":
+            bamVersion = pg.get("VN")
+    if not bamVersion == __bam_version__:
+        raise RuntimeError("Wrong filtered BAM file version detected (" + str(bamVersion) + "). Expected version " +
+                           __bam_version__ + ". Please rerun slamdunk filter.")
+    if slamseqInfo.AnnotationMD5 != bedMD5:
+        print("Warning: MD5 checksum of annotation (" + bedMD5 + ") does not matched MD5 in filtered BAM files (" +
+              str(slamseqInfo.AnnotationMD5) + "). Most probably the annotation filed changed after the filtered BAM files were created.",
+              file=log)
+
+    # BED rows in file order; a bad row stops the run where the reference would (rows before it are written)
+    utrs = []
+    pending_error = None
+    for utr in BedIterator(bed):
+        if not utr.hasStrand():
+            pending_error = RuntimeError("Input BED file does not contain stranded intervals.")
+            break
+        if utr.start < 0:
+            pending_error = NegativeStartError("Negativ start coordinate found. Please check the following entry in your BED file: " + repr(utr))
+            break
+        utrs.append(utr)
+    bam_names = set(hbatch.ref_names)
+    n = len(utrs)
+    chrom_idx = np.array([genome.index.get(u.chromosome, L.SD_REF_NONE) for u in utrs], dtype=np.uint32)
+    start = np.array([u.start for u in utrs], dtype=np.int64)
+    stop = np.array([u.stop for u in utrs], dtype=np.int64)
+    strand = np.array([1 if u.strand == "-" else 0 for u in utrs], dtype=np.uint8)
+    in_bam = np.array([1 if u.chromosome in bam_names else 0 for u in utrs], dtype=np.uint8)
+    tm["host_prepare_s"] = time.time() - t0 - tm["fasta_decode_s"] - tm["bam_inflate_s"] - tm["bam_decode_s"]
+
+    t1 = time.time()
+    eng = CountEngine(OPTIONS["device"])
+    try:
+        eng.set_reference(genome.lo, genome.hi, genome.nmask, genome.chrom_off, genome.chrom_len)
+        if tc_mask is not None:
+            eng.set_snps(tc_mask, ag_mask)
+        eng.set_utrs(chrom_idx, start, stop, strand, in_bam)
+        params = make_params(min_qual=minQual, conversion_threshold=conversionThreshold, mismatch_source=mode)
+        eng.synchronize()
+        t2 = time.time()
+        eng.count_host(hbatch.batch, params)
+        stats = eng.stats.cpu().numpy()
+        if mode == L.SD_MISMATCH_VERIFY and stats[L.SD_S_MP_DISAGREE] > 0:
+            # the BAM's MP tags do not describe the same mismatches as SEQ/CIGAR vs this FASTA: the reference
+            # trusts MP, so do the same (still on the GPU) and say so
+            print("Warning: %d reads carry MP tags that disagree with a CIGAR walk against %s; counting from the MP tags as slamdunk does."
+                  % (int(stats[L.SD_S_MP_DISAGREE]), os.path.basename(ref)), file=log)
+            eng.reset_outputs()
+            params = make_params(min_qual=minQual, conversion_threshold=conversionThreshold, mismatch_source=L.SD_MISMATCH_MP)
+            eng.count_host(hbatch.batch, params)
+        eng.finalize()
+        res = eng.results()
+        tm["gpu_setup_s"] = t2 - t1
+        tm["gpu_count_s"] = time.time() - t2
+        tm["gpu_launches"] = eng.launch_count()
+        tm["stats"] = res["stats"].tolist()
+        pos_off, pos_len = eng.pos_off, eng.pos_len
+    finally:
+        eng.close()
+
+    t3 = time.time()
+    counters = res["counters"]
+    tcontent = res["tcontent"]
+    for i, utr in enumerate(utrs):
+        readCount = int(counters[i, L.SD_C_READS])
+        Tcontent = int(tcontent[i])
+        if readCount > 0:                                    # tcounter.py:251
+            coverageOnTs = int(counters[i, L.SD_C_COV_ON_T])
+            conversionsOnTs = int(counters[i, L.SD_C_CONV_ON_T])
+            readsCPM = 0
+            if readNumber > 0:                               # tcounter.py:295-297
+                readsCPM = readCount * 1000000.0 / readNumber
+            conversionRate = 0
+            if coverageOnTs > 0:                             # tcounter.py:301-303
+                conversionRate = float(conversionsOnTs) / float(coverageOnTs)
+            print(_row(utr, conversionRate, readsCPM, Tcontent, coverageOnTs, conversionsOnTs, readCount,
+                       int(counters[i, L.SD_C_TCREADS]), int(counters[i, L.SD_C_MULTIMAP])), file=fileCSV)
+        else:
+            print(_row(utr, 0, 0, Tcontent, 0, 0, 0, 0, 0), file=fileCSV)
+    fileCSV.close()
+    if pending_error is not None:
+        raise pending_error
+
+    _write_bedgraphs(utrs, chrom_idx, genome, res, pos_off, pos_len, counters, outputBedgraphPlus, outputBedgraphMinus)
+    tm["write_s"] = time.time() - t3
+    tm["total_s"] = time.time() - t0
+    OPTIONS["timings"] = tm
+    hbatch.close()
+    genome.close()
+
+
+def _bits(plane: np.ndarray, g0: int, g1: int) -> np.ndarray:
+    """bool array of plane bits [g0, g1) (bit j of word w = position 32 w + j)."""
+    w0, w1 = g0 >> 5, (g1 + 31) >> 5
+    b = np.unpackbits(plane[w0:w1].view(np.uint8), bitorder="little")
+    return b[g0 - (w0 << 5): g1 - (w0 << 5)].astype(bool)
+
+
+def _write_bedgraphs(utrs, chrom_idx, genome, res, pos_off, pos_len, counters, out_plus, out_minus):
+    """tcounter.py:277-285 + 315-326: one line per covered T (A on '-') position of every UTR that
+    had reads, in dict insertion order: BED order, ascending position, a position keeps the place of
+    its first insertion."""
+    pos_cov, pos_tc = res["pos_cov"], res["pos_tc"]
+    emitted = np.zeros(len(pos_cov), dtype=bool)
+    is_base = (genome.is_base_mask(0), genome.is_base_mask(1))
+    rate_cache = {}
+    files = (open(out_plus, "w"), open(out_minus, "w"))
+    try:
+        for i, utr in enumerate(utrs):
+            if counters[i, L.SD_C_READS] <= 0 or pos_len[i] == 0 or pos_off[i] == np.iinfo(np.uint64).max:
+                continue
+            s = 1 if utr.strand == "-" else 0
+            off, ln = int(pos_off[i]), int(pos_len[i])
+            cov = pos_cov[off:off + ln]
+            g0 = int(genome.chrom_off[chrom_idx[i]]) + max(0, utr.start)
+            sel = (cov > 0) & _bits(is_base[s], g0, g0 + ln) & ~emitted[off:off + ln]
+            idx = np.nonzero(sel)[0]
+            if len(idx) == 0:
+                continue
+            emitted[off + idx] = True
+            tc = pos_tc[off:off + ln][idx]
+            cv = cov[idx]
+            base = max(0, utr.start)
+            out = files[s]
+            chrom = utr.chromosome
+            lines = []
+            for p, t, c in zip(idx.tolist(), tc.tolist(), cv.tolist()):
+                key = (t, c)
+                r = rate_cache.get(key)
+                if r is None:
+                    r = str(t * 100.0 / c)                   # tcounter.py:252
+                    rate_cache[key] = r
+                q = base + p
+                lines.append("%s %d %d %s\n" % (chrom, q, q + 1, r))
+            out.write("".join(lines))
+    finally:
+        files[0].close()
+        files[1].close()

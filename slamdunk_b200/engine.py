@@ -1,0 +1,325 @@
+"""Host driver of the native count path: owns the device buffers (torch tensors) and calls the C ABI.
+
+torch is plumbing here -- device memory, streams, torch.distributed for the multi-GPU reduce; every
+kernel on the path lives in libslamdunk_b200.so (include/slamdunk_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _np_ptr(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _t_ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class HostGenome(object):
+    """FASTA decoded into the linear bit-plane space (sd_load_fasta)."""
+
+    def __init__(self, path: str, threads: int = 0):
+        lib = L.load()
+        err = ctypes.create_string_buffer(512)
+        out = ctypes.POINTER(L.HGenome)()
+        rc = lib.sd_load_fasta(os.fsencode(path), int(threads), ctypes.byref(out), err, len(err))
+        if rc != L.SD_OK:
+            raise L.NativeError("sd_load_fasta(%s) failed (%d): %s" % (path, rc, err.value.decode("utf-8", "replace")))
+        self._h = out
+        g = out.contents
+        self.n_chrom = int(g.n_chrom)
+        self.names = [g.names[i].decode() for i in range(self.n_chrom)]
+        self.index = {}
+        for i, n in enumerate(self.names):
+            self.index.setdefault(n, i)
+        self.chrom_len = np.ctypeslib.as_array(g.chrom_len, shape=(self.n_chrom,)).copy()
+        self.chrom_off = np.ctypeslib.as_array(g.chrom_off, shape=(self.n_chrom,)).copy()
+        self.n_words = int(g.n_words)
+        self.lo = np.ctypeslib.as_array(g.lo, shape=(self.n_words,))
+        self.hi = np.ctypeslib.as_array(g.hi, shape=(self.n_words,))
+        self.nmask = np.ctypeslib.as_array(g.nmask, shape=(self.n_words,))
+        self.seconds = float(g.seconds)
+
+    def close(self):
+        if self._h is not None:
+            self.lo = self.hi = self.nmask = None
+            L.load().sd_hgenome_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def is_base_mask(self, strand: int) -> np.ndarray:
+        """uint32 plane: bit set where the upper-cased FASTA base is T (strand 0) or A (strand 1)."""
+        if strand == 0:
+            return self.lo & self.hi & ~self.nmask
+        return ~self.lo & ~self.hi & ~self.nmask
+
+
+class HostBatch(object):
+    """A BAM file decoded into the columnar batch (sd_decode_bam); buffers are page-locked."""
+
+    def __init__(self, path: str, fasta_names: Sequence[str], want_mp: bool = True, tile_reads: int = 256,
+                 threads: int = 0):
+        lib = L.load()
+        err = ctypes.create_string_buffer(512)
+        out = ctypes.POINTER(L.HBatch)()
+        names = (ctypes.c_char_p * max(1, len(fasta_names)))(*[n.encode() for n in fasta_names])
+        rc = lib.sd_decode_bam(os.fsencode(path), names, len(fasta_names), 1 if want_mp else 0, int(tile_reads),
+                               int(threads), ctypes.byref(out), err, len(err))
+        if rc != L.SD_OK:
+            raise L.NativeError("sd_decode_bam(%s) failed (%d): %s" % (path, rc, err.value.decode("utf-8", "replace")))
+        self._h = out
+        h = out.contents
+        self.batch = h.batch
+        self.n_reads = int(h.batch.n_reads)
+        self.header_text = (h.header_text or b"").decode("utf-8", "replace")
+        self.ref_names = [h.ref_names[i].decode() for i in range(h.n_ref)]
+        self.ref_lengths = [int(h.ref_lengths[i]) for i in range(h.n_ref)]
+        self.seconds_inflate = float(h.seconds_inflate)
+        self.seconds_decode = float(h.seconds_decode)
+        self.compressed_bytes = int(h.compressed_bytes)
+        self.inflated_bytes = int(h.inflated_bytes)
+
+    # numpy views (tests, diagnostics)
+    def rec_array(self) -> np.ndarray:
+        b = self.batch
+        n = b.n_tiles * b.tile_reads
+        buf = (ctypes.c_uint32 * (5 * n)).from_address(b.rec) if n else None
+        return np.frombuffer(buf, dtype=np.uint32).reshape(n, 5) if n else np.zeros((0, 5), np.uint32)
+
+    def tiles_array(self) -> np.ndarray:
+        b = self.batch
+        buf = (ctypes.c_uint64 * (4 * (b.n_tiles + 1))).from_address(b.tiles)
+        return np.frombuffer(buf, dtype=np.uint64).reshape(b.n_tiles + 1, 4)
+
+    def column(self, which: str) -> np.ndarray:
+        b = self.batch
+        t = self.tiles_array()[-1]
+        if which == "seq":
+            n, addr, dt = int(t[0]) // 4, b.seq, ctypes.c_uint32
+        elif which == "qual":
+            n, addr, dt = int(t[1]), b.qual, ctypes.c_uint8
+        elif which == "cigar":
+            n, addr, dt = int(t[2]) // 4, b.cigar, ctypes.c_uint32
+        elif which == "mp":
+            n, addr, dt = int(t[3]) // 4, b.mp, ctypes.c_uint32
+        else:
+            raise KeyError(which)
+        if not n or not addr:
+            return np.zeros(0, dtype=np.dtype(dt))
+        return np.frombuffer((dt * n).from_address(addr), dtype=np.dtype(dt))
+
+    def name_hash(self) -> np.ndarray:
+        n = self.n_reads
+        if not n:
+            return np.zeros(0, np.uint64)
+        return np.ctypeslib.as_array(self._h.contents.name_hash, shape=(n,))
+
+    def close(self):
+        if self._h is not None:
+            L.load().sd_hbatch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceBatch(object):
+    """Columnar batch resident in HBM (torch uint8 tensors) plus the sd_batch that points at it."""
+
+    def __init__(self, batch: L.Batch, tensors: dict):
+        self.batch = batch
+        self.tensors = tensors
+
+    @staticmethod
+    def from_host(hb: L.Batch, device: torch.device) -> "DeviceBatch":
+        def up(addr, nbytes):
+            if not addr or nbytes == 0:
+                return torch.zeros(16, dtype=torch.uint8, device=device)
+            src = np.frombuffer((ctypes.c_uint8 * nbytes).from_address(addr), dtype=np.uint8)
+            return torch.from_numpy(src).to(device)
+        nt = hb.n_tiles
+        tiles = np.frombuffer((ctypes.c_uint64 * (4 * (nt + 1))).from_address(hb.tiles), dtype=np.uint64).reshape(nt + 1, 4)
+        tot = tiles[-1]
+        T = {
+            "rec": up(hb.rec, nt * hb.tile_reads * 20),
+            "seq": up(hb.seq, int(tot[0])),
+            "qual": up(hb.qual, int(tot[1])),
+            "cigar": up(hb.cigar, int(tot[2])),
+            "mp": up(hb.mp, int(tot[3])) if hb.mp else None,
+            "tiles": up(hb.tiles, (nt + 1) * 32),
+        }
+        b = L.Batch()
+        ctypes.memmove(ctypes.byref(b), ctypes.byref(hb), ctypes.sizeof(L.Batch))
+        b.rec, b.seq, b.qual, b.cigar = T["rec"].data_ptr(), T["seq"].data_ptr(), T["qual"].data_ptr(), T["cigar"].data_ptr()
+        b.mp = T["mp"].data_ptr() if T["mp"] is not None else None
+        b.tiles = T["tiles"].data_ptr()
+        return DeviceBatch(b, T)
+
+    def nbytes(self) -> int:
+        return sum(t.numel() for t in self.tensors.values() if t is not None)
+
+
+def make_params(min_qual=27, conversion_threshold=1, mismatch_source=L.SD_MISMATCH_CIGAR, filter_on=False,
+                filter_mq=0, filter_min_identity=0.0, filter_max_nm=-1, force_slow_path=False) -> L.Params:
+    p = L.Params()
+    p.min_qual = int(min_qual)
+    p.conversion_threshold = int(conversion_threshold)
+    p.mismatch_source = int(mismatch_source)
+    p.filter_on = 1 if filter_on else 0
+    p.filter_mq = int(filter_mq)
+    p.filter_max_nm = int(filter_max_nm)
+    p.filter_min_identity = float(filter_min_identity)
+    p.force_slow_path = 1 if force_slow_path else 0
+    return p
+
+
+class CountEngine(object):
+    """One context = one GPU.  Typical use:
+
+        eng = CountEngine(device=0)
+        eng.set_reference(lo, hi, nmask, chrom_off, chrom_len)      # numpy uint32 planes
+        eng.set_snps(tc_mask, ag_mask)                              # optional
+        eng.set_utrs(chrom_idx, start, stop, strand, in_bam)        # BED order
+        eng.count(device_batch, params) / eng.count_host(host_batch, params)   # any number of batches
+        (optionally all-reduce eng.counters / eng.pos_cov / eng.pos_tc across ranks)
+        eng.finalize(); res = eng.results()
+    """
+
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("slamdunk_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = L.load()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        ctx = ctypes.c_void_p()
+        L.check(self.lib.sd_create(device, ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(ctx)), None, "sd_create")
+        self.ctx = ctx
+        self.n_utr = 0
+        self.n_positions = 0
+        self.counters = self.pos_cov = self.pos_tc = self.stats = self.tcontent = None
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.sd_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        L.check(rc, self.ctx, what)
+
+    def synchronize(self):
+        self._chk(self.lib.sd_device_synchronize(self.ctx), "sd_device_synchronize")
+
+    # -- inputs ------------------------------------------------------------------------
+    def set_reference(self, lo, hi, nmask, chrom_off, chrom_len):
+        """lo/hi/nmask: numpy uint32 planes (host) or torch int32 tensors already on the device."""
+        def dev(x):
+            if isinstance(x, torch.Tensor):
+                return x
+            return torch.from_numpy(np.ascontiguousarray(x).view(np.int32)).to(self.device)
+        with torch.cuda.stream(self.stream):
+            d_lo, d_hi, d_n = dev(lo), dev(hi), dev(nmask)
+        self.stream.synchronize()
+        co = np.ascontiguousarray(chrom_off, dtype=np.uint32)
+        cl = np.ascontiguousarray(chrom_len, dtype=np.uint32)
+        self.n_words = int(d_lo.numel())
+        self._chk(self.lib.sd_set_reference(self.ctx, _t_ptr(d_lo), _t_ptr(d_hi), _t_ptr(d_n), self.n_words,
+                                            _np_ptr(co), _np_ptr(cl), len(co)), "sd_set_reference")
+        self.chrom_off, self.chrom_len = co, cl
+
+    def set_snps(self, tc_mask, ag_mask):
+        def dev(x):
+            if x is None or isinstance(x, torch.Tensor):
+                return x
+            return torch.from_numpy(np.ascontiguousarray(x).view(np.int32)).to(self.device)
+        with torch.cuda.stream(self.stream):
+            d_tc, d_ag = dev(tc_mask), dev(ag_mask)
+        self.stream.synchronize()
+        self._chk(self.lib.sd_set_snps(self.ctx, _t_ptr(d_tc), _t_ptr(d_ag)), "sd_set_snps")
+
+    def set_utrs(self, chrom_idx, start, stop, strand, in_bam=None):
+        ci = np.ascontiguousarray(chrom_idx, dtype=np.uint32)
+        st = np.ascontiguousarray(start, dtype=np.int64)
+        sp = np.ascontiguousarray(stop, dtype=np.int64)
+        sd = np.ascontiguousarray(strand, dtype=np.uint8)
+        ib = np.ascontiguousarray(in_bam, dtype=np.uint8) if in_bam is not None else None
+        n = len(ci)
+        self._chk(self.lib.sd_set_utrs(self.ctx, _np_ptr(ci), _np_ptr(st), _np_ptr(sp), _np_ptr(sd),
+                                       _np_ptr(ib) if ib is not None else None, n), "sd_set_utrs")
+        self.n_utr = n
+        npos = ctypes.c_uint64()
+        self._chk(self.lib.sd_position_space(self.ctx, ctypes.byref(npos)), "sd_position_space")
+        self.n_positions = int(npos.value)
+        self.pos_off = np.zeros(n, dtype=np.uint64)
+        self.pos_len = np.zeros(n, dtype=np.uint32)
+        self._chk(self.lib.sd_utr_layout(self.ctx, _np_ptr(self.pos_off), _np_ptr(self.pos_len)), "sd_utr_layout")
+        self.reset_outputs()
+
+    def reset_outputs(self):
+        with torch.cuda.stream(self.stream):
+            self.counters = torch.empty(max(1, self.n_utr) * L.SD_NCOUNTER, dtype=torch.int64, device=self.device)
+            self.pos_cov = torch.empty(max(1, self.n_positions), dtype=torch.int32, device=self.device)
+            self.pos_tc = torch.empty(max(1, self.n_positions), dtype=torch.int32, device=self.device)
+            self.stats = torch.empty(L.SD_NSTAT, dtype=torch.int64, device=self.device)
+            self.tcontent = torch.zeros(max(1, self.n_utr), dtype=torch.int64, device=self.device)
+        self._chk(self.lib.sd_bind_outputs(self.ctx, _t_ptr(self.counters), _t_ptr(self.pos_cov), _t_ptr(self.pos_tc),
+                                           _t_ptr(self.stats)), "sd_bind_outputs")
+
+    # -- the hot path ------------------------------------------------------------------
+    def count(self, dbatch: DeviceBatch, params: L.Params, read_tc: Optional[torch.Tensor] = None):
+        if read_tc is not None:
+            self._chk(self.lib.sd_count_reads(self.ctx, ctypes.byref(dbatch.batch), ctypes.byref(params), _t_ptr(read_tc)),
+                      "sd_count_reads")
+        else:
+            self._chk(self.lib.sd_count(self.ctx, ctypes.byref(dbatch.batch), ctypes.byref(params)), "sd_count")
+
+    def count_host(self, hbatch: L.Batch, params: L.Params):
+        self._chk(self.lib.sd_count_host(self.ctx, ctypes.byref(hbatch), ctypes.byref(params)), "sd_count_host")
+
+    def finalize(self):
+        self._chk(self.lib.sd_finalize(self.ctx), "sd_finalize")
+        self._chk(self.lib.sd_tcontent(self.ctx, _t_ptr(self.tcontent)), "sd_tcontent")
+
+    def last_kernel_ms(self) -> float:
+        return float(self.lib.sd_last_kernel_ms(self.ctx))
+
+    def launch_count(self) -> int:
+        return int(self.lib.sd_launch_count(self.ctx))
+
+    # -- outputs -----------------------------------------------------------------------
+    def results(self):
+        """-> dict of host numpy arrays: counters [n_utr, 5], tcontent [n_utr], stats [SD_NSTAT],
+        pos_cov / pos_tc [n_positions]."""
+        self.synchronize()
+        n = self.n_utr
+        return {
+            "counters": self.counters.cpu().numpy().reshape(-1, L.SD_NCOUNTER)[:n],
+            "tcontent": self.tcontent.cpu().numpy()[:n],
+            "stats": self.stats.cpu().numpy(),
+            "pos_cov": self.pos_cov.cpu().numpy()[:self.n_positions],
+            "pos_tc": self.pos_tc.cpu().numpy()[:self.n_positions],
+        }

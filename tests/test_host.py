@@ -1,0 +1,212 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports what include/*.h
+declares, the native BAM / FASTA decoders agree with the plain Python codec, the SNP masks
+reproduce the reference's chrom+pos string-key semantics."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import goldens
+import simdata
+from slamdunk_b200 import _lib as L
+from slamdunk_b200.io import bam as bamio
+from slamdunk_b200.utils import SNPtools
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    text = open(os.path.join(ROOT, "include", "slamdunk_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(sd_[a-z_0-9]+)\s*\(", text))
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "library does not export " + name
+    assert declared == set(L.PROTOTYPES.keys())
+    assert lib.sd_abi_version() == 1
+
+
+def _decode(path, fasta_names, want_mp=True, tile_reads=64, threads=3):
+    from slamdunk_b200.engine import HostBatch
+    return HostBatch(path, fasta_names, want_mp=want_mp, tile_reads=tile_reads, threads=threads)
+
+
+def _unslice(words, lseq):
+    out = []
+    for i in range(lseq):
+        w = int(words[i >> 3])
+        b = i & 7
+        nib = sum((((w >> (8 * p + b)) & 1) << p) for p in range(4))
+        out.append(bamio.SEQ_NIBBLES[nib])
+    return "".join(out)
+
+
+@pytest.mark.parametrize("tile_reads", [64, 256])
+def test_bam_decoder_matches_python_codec(tmp_path, tile_reads):
+    c = simdata.make_case(str(tmp_path), seed=77, n_reads=700, complexity=2.0)
+    text, refs, recs = bamio.read_bam(c.bam)
+    fasta_names = list(c.genome.keys())
+    hb = _decode(c.bam, fasta_names, tile_reads=tile_reads)
+    assert hb.n_reads == len(recs)
+    assert hb.header_text == text
+    assert hb.ref_names == [n for n, _ in refs] and hb.ref_lengths == [l for _, l in refs]
+    rec = hb.rec_array()
+    tiles = hb.tiles_array()
+    seq, qual, cig, mp = hb.column("seq"), hb.column("qual"), hb.column("cigar"), hb.column("mp")
+    assert (tiles % 16 == 0).all()
+    T = tile_reads
+    prev_name = None
+    for t in range(hb.batch.n_tiles):
+        so, qo, co, mo = (int(x) for x in tiles[t])
+        so //= 4; co //= 4; mo //= 4
+        for k in range(T):
+            i = t * T + k
+            w = rec[i]
+            flags = int(w[1]) >> 24
+            if i >= len(recs):
+                assert flags & L.SD_F_PAD
+                continue
+            r = recs[i]
+            lseq, ncig = int(w[3]) & 0xFFFF, int(w[3]) >> 16
+            nm, nmp = int(w[4]) & 0xFFFF, int(w[4]) >> 16
+            assert np.int32(w[0]) == r.pos
+            assert lseq == len(r.seq) and ncig == len(r.cigar)
+            assert (int(w[1]) >> 16) & 0xFF == r.mapq
+            ref = int(w[1]) & 0xFFFF
+            bam_name = refs[r.ref_id][0]
+            assert ref == (fasta_names.index(bam_name) if bam_name in fasta_names else L.SD_REF_NONE)
+            assert bool(flags & L.SD_F_REVERSE) == bool(r.flag & 16)
+            assert bool(flags & L.SD_F_SECONDARY) == bool(r.flag & 0x100)
+            assert bool(flags & L.SD_F_HAS_MP) == r.has_tag("MP")
+            assert bool(flags & L.SD_F_NEWNAME) == (r.qname != prev_name)
+            assert not (flags & L.SD_F_PAD)
+            prev_name = r.qname
+            assert nm == r.get_tag("NM")
+            assert np.float32(np.uint32(w[2]).view(np.float32)) == np.float32(r.get_tag("XI"))
+            nw = (lseq + 7) // 8
+            assert _unslice(seq[so:so + nw], lseq) == r.seq.upper()
+            assert list(qual[qo:qo + lseq]) == r.qual
+            assert [(int(x) & 15, int(x) >> 4) for x in cig[co:co + ncig]] == r.cigar
+            want = []
+            if r.has_tag("MP"):
+                for ent in r.get_tag("MP").split(","):
+                    conv, rp, fp = (int(x) for x in ent.split(":"))
+                    if conv == (2 if r.flag & 16 else 16):
+                        want.append(((rp - 1) | ((fp - 1) << 16)))
+            assert [int(x) for x in mp[mo:mo + nmp]] == want
+            so += nw; qo += lseq; co += ncig; mo += nmp
+    hb.close()
+
+
+def test_bam_decoder_unmapped_and_missing_tags(tmp_path):
+    recs = [bamio.BamRecord("u1", 4, -1, -1, 0, [], "ACGTN", [30] * 5, []),
+            bamio.BamRecord("m1", 0, 0, 10, 7, "5M", "ACGTA", None, [("NM", "i", 70000)]),
+            bamio.BamRecord("m1", 16, 0, 12, 0, "2S3M", "ACGTA", [1, 2, 3, 4, 5], [("XI", "f", 0.5), ("MP", "Z", "2:3:1,16:4:2")])]
+    p = str(tmp_path / "x.bam")
+    bamio.write_bam(p, "@HD\tVN:1.0\n@SQ\tSN:c\tLN:100\n", [("c", 100)], recs)
+    hb = _decode(p, ["c"])
+    rec = hb.rec_array()
+    f = [int(w[1]) >> 24 for w in rec[:3]]
+    assert f[0] & L.SD_F_UNMAPPED and f[0] & L.SD_F_SKIP
+    assert not (f[1] & L.SD_F_UNMAPPED) and math.isnan(float(np.uint32(rec[1][2]).view(np.float32)))
+    assert int(rec[1][4]) & 0xFFFF == 65535          # NM saturates
+    assert not (f[2] & L.SD_F_NEWNAME) and f[1] & L.SD_F_NEWNAME
+    assert int(rec[2][4]) >> 16 == 1                 # only the A>G entry of a reverse read is kept
+    assert list(hb.column("mp")[:1]) == [2 | (0 << 16)]
+    hb.close()
+
+
+def test_decoder_rejects_garbage(tmp_path):
+    from slamdunk_b200.engine import HostBatch
+    p = str(tmp_path / "bad.bam")
+    open(p, "wb").write(b"this is not a bam file at all, not even close......")
+    with pytest.raises(L.NativeError):
+        HostBatch(p, ["c"])
+    with pytest.raises(L.NativeError):
+        HostBatch(str(tmp_path / "missing.bam"), ["c"])
+
+
+def test_fasta_loader_matches_python(tmp_path):
+    from slamdunk_b200.engine import HostGenome
+    c = simdata.make_case(str(tmp_path), seed=3, n_reads=10)
+    g = HostGenome(c.ref, threads=2)
+    assert g.names == list(c.genome.keys())
+    assert list(g.chrom_len) == [len(s) for s in c.genome.values()]
+    for ci, (name, s) in enumerate(c.genome.items()):
+        off = int(g.chrom_off[ci])
+        assert off % 32 == 0
+        up = s.upper()
+        for plane, fn in ((g.is_base_mask(0), lambda ch: ch == "T"), (g.is_base_mask(1), lambda ch: ch == "A"),
+                          (g.nmask, lambda ch: ch not in "ACGT")):
+            bits = np.unpackbits(plane.view(np.uint8), bitorder="little")[off:off + len(s)]
+            want = np.array([fn(ch) for ch in up], dtype=np.uint8)
+            assert (bits == want).all()
+        if ci + 1 < g.n_chrom:
+            assert off + len(s) + 32 <= int(g.chrom_off[ci + 1])
+    # pad positions are N
+    bits = np.unpackbits(g.nmask.view(np.uint8), bitorder="little")
+    assert bits[:int(g.chrom_off[0])].all()
+    g.close()
+
+
+def test_fasta_loader_multiline_and_description(tmp_path):
+    from slamdunk_b200.engine import HostGenome
+    p = str(tmp_path / "m.fa")
+    open(p, "w").write(">chrA some description\nACGT\nacgtNN\r\n\n>chrB\nTTTT")
+    g = HostGenome(p)
+    assert g.names == ["chrA", "chrB"] and list(g.chrom_len) == [10, 4]
+    t = np.unpackbits(g.is_base_mask(0).view(np.uint8), bitorder="little")
+    a0, b0 = int(g.chrom_off[0]), int(g.chrom_off[1])
+    assert list(t[a0:a0 + 10]) == [0, 0, 0, 1, 0, 0, 0, 1, 0, 0] and list(t[b0:b0 + 4]) == [1, 1, 1, 1]
+    g.close()
+
+
+def _reference_snp_sets(records):
+    """utils/SNPtools.py:30-38 verbatim semantics"""
+    tc, ag = {}, {}
+    for ch, pos, ref, alt in records:
+        if ref.upper() == "T" and alt.upper() == "C":
+            tc[ch + pos] = True
+        if ref.upper() == "A" and alt.upper() == "G":
+            ag[ch + pos] = True
+    return tc, ag
+
+
+def test_snp_masks_reproduce_string_key_collisions():
+    names = ["chr1", "chr12", "chr2", "2", "chrX"]
+    lens = [30000, 4000, 500, 25000, 100]
+    off, o = [], 32
+    for l in lens:
+        off.append(o)
+        o = ((o + l + 31) // 32) * 32 + 32
+    n_words = o // 32
+    records = [("chr12", "345", "T", "C"), ("chr1", "2345", "A", "G"), ("chr1", "77", "t", "c"), ("chr1", "0077", "T", "C"),
+               ("chr2", "12", "A", "G"), ("chr", "2100", "T", "C"), ("chrX", "5", "T", "C,G"), ("chrX", "6", "A", "g"),
+               ("chr1", "23456", "T", "C"), ("chr12", "3999", "A", "G"), ("2", "17", "T", "C"), ("chr1", "99999", "T", "C"),
+               ("chr10", "55", "T", "C")]
+    sm = SNPtools.SNPMasks(names, off, lens, n_words)
+    for r in records:
+        sm.add(*r)
+    tcm, agm = sm.masks()
+    tc, ag = _reference_snp_sets(records)
+    tb = np.unpackbits(tcm.view(np.uint8), bitorder="little")
+    ab = np.unpackbits(agm.view(np.uint8), bitorder="little")
+    for ci, name in enumerate(names):
+        for p in range(lens[ci]):
+            key = name + str(p + 1)                        # SNPtools.py:53-60
+            assert bool(tb[off[ci] + p]) == (key in tc), (name, p)
+            assert bool(ab[off[ci] + p]) == (key in ag), (name, p)
+    assert tb.sum() == sum(1 for ci, n in enumerate(names) for p in range(lens[ci]) if n + str(p + 1) in tc)
+
+
+def test_bed_reader_quirks(tmp_path):
+    from slamdunk_b200.utils.BedReader import BedIterator
+    p = str(tmp_path / "a.bed")
+    open(p, "w").write("chr1\t5\t10\tn1\t0\t+\nchr1\t7\t9\tn2\nchr2\t1\t2\tn3\t.\t-\textra\n")
+    rows = list(BedIterator(p))
+    assert [(r.chromosome, r.start, r.stop, r.name, r.strand) for r in rows] == \
+        [("chr1", 5, 10, "n1", "+"), ("chr1", 7, 9, "n2", "."), ("chr2", 1, 2, "n3", "-")]
+    assert rows[0].hasStrand() and not rows[1].hasStrand() and rows[0].getLength() == 5
