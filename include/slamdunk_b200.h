@@ -255,7 +255,8 @@ typedef struct sd_hbatch {
 } sd_hbatch;
 
 /* fasta_names / n_fasta: chromosome table of the FASTA (index = sd_read_rec ref field).
- * want_mp: also decode MP tags into the mp column.  threads <= 0: hardware concurrency. */
+ * want_mp: also decode MP tags into the mp column.  tile_reads: 64, 128, 256 or 0 = the largest
+ * that keeps a tile's shared-memory stage small.  threads <= 0: hardware concurrency. */
 int sd_decode_bam(const char *path, const char *const *fasta_names, uint32_t n_fasta, int want_mp,
                   uint32_t tile_reads, int threads, sd_hbatch **out, char *err, int errlen);
 void sd_hbatch_free(sd_hbatch *hb);
@@ -295,20 +296,37 @@ typedef struct sd_synth_params {
     uint32_t utr_first, utr_count; /* restrict placement to this range of the expression table */
 } sd_synth_params;
 
-/* Expression table: device arrays [n] of UTR global start, in-chromosome length, strand and
- * cumulative weight (float64, last element = total).  Sizes the batch: fills h_sizes with the
- * column byte sizes {rec, seq, qual, cigar, mp, tiles, triples} the caller must allocate. */
-int sd_synth_sizes(sd_ctx *ctx, const sd_synth_params *p, const uint32_t *d_utr_gstart,
-                   const uint32_t *d_utr_len, const uint8_t *d_utr_strand, const double *d_cum_weight,
-                   uint32_t n_utr, uint64_t *d_scratch_counts, uint64_t h_sizes[8]);
-/* Fill caller-allocated device columns (sizes from sd_synth_sizes); d_triples (optional) receives
- * per read up to 24 (conv, readPos, refPos) int32 triples + count, the generator's own record of
- * the mismatches it made (for the oracle's MP input).  Synchronous. */
-int sd_synth_fill(sd_ctx *ctx, const sd_synth_params *p, const uint32_t *d_utr_gstart,
-                  const uint32_t *d_utr_len, const uint8_t *d_utr_strand, const double *d_cum_weight,
-                  uint32_t n_utr, const uint64_t *d_scratch_counts, sd_batch *d_batch_out /* host struct, device ptrs */,
-                  int32_t *d_triples);
-/* Random genome planes: uniform ACGT with n_frac of positions inside N runs.  Device pointers. */
+/* Device-resident tables the generator reads. */
+typedef struct sd_synth_tables {
+    const uint32_t *lo, *hi, *nmask; /* genome planes as for sd_set_reference */
+    const uint32_t *chrom_off;       /* device copies of the chromosome table */
+    const uint32_t *chrom_len;
+    uint32_t n_chrom;
+    uint32_t n_utr;                  /* expression table: one entry per UTR */
+    const uint32_t *utr_chrom;       /* chromosome index */
+    const uint32_t *utr_start;       /* chromosome-local start / end (end clipped to the chromosome) */
+    const uint32_t *utr_end;
+    const uint8_t *utr_strand;
+    const double *utr_cum_weight;    /* inclusive cumulative expression weight */
+} sd_synth_tables;
+
+#define SD_SYNTH_MAX_TRIPLES 40
+
+/* Pass 1: simulate every read once to learn its CIGAR and MP entry counts.
+ * d_counts: device uint32[n_reads] scratch (n_cigar | n_mp << 16), d_tiles: device sd_tile[n_tiles + 1]
+ * (filled), h_totals: host uint64[4] = total bytes of the seq, qual, cigar and mp columns.  Synchronous. */
+int sd_synth_plan(sd_ctx *ctx, const sd_synth_params *p, const sd_synth_tables *t, uint32_t *d_counts,
+                  sd_tile *d_tiles, uint64_t h_totals[4]);
+/* Pass 2: fill caller-allocated device columns.  `out` is a host struct whose pointers are device
+ * buffers of the sizes pass 1 reported (rec: n_tiles * tile_reads records; tiles = d_tiles of pass 1);
+ * its scalar fields are filled in.  d_triples (optional): int32 [n_reads][1 + 3 * SD_SYNTH_MAX_TRIPLES],
+ * per read the number of mismatching aligned columns followed by (conv, readPos, refPos) triples as
+ * NextGenMap would list them in MP:Z -- the generator's own record of what it mutated, not a re-walk
+ * of the encoded alignment.  Synchronous. */
+int sd_synth_fill(sd_ctx *ctx, const sd_synth_params *p, const sd_synth_tables *t, const uint32_t *d_counts,
+                  sd_batch *out, int32_t *d_triples);
+/* Random genome planes: uniform ACGT, a fraction n_frac of 64-bp blocks all N; pad positions N.
+ * Device pointers; chromosome table on the host.  Synchronous. */
 int sd_synth_genome(sd_ctx *ctx, uint64_t seed, uint32_t *d_lo, uint32_t *d_hi, uint32_t *d_nmask,
                     uint64_t n_words, const uint32_t *h_chrom_off, const uint32_t *h_chrom_len,
                     uint32_t n_chrom, float n_frac);

@@ -71,6 +71,15 @@ class SynthParams(ctypes.Structure):
                 ("utr_first", ctypes.c_uint32), ("utr_count", ctypes.c_uint32)]
 
 
+class SynthTables(ctypes.Structure):
+    _fields_ = [("lo", ctypes.c_void_p), ("hi", ctypes.c_void_p), ("nmask", ctypes.c_void_p),
+                ("chrom_off", ctypes.c_void_p), ("chrom_len", ctypes.c_void_p), ("n_chrom", ctypes.c_uint32),
+                ("n_utr", ctypes.c_uint32), ("utr_chrom", ctypes.c_void_p), ("utr_start", ctypes.c_void_p),
+                ("utr_end", ctypes.c_void_p), ("utr_strand", ctypes.c_void_p), ("utr_cum_weight", ctypes.c_void_p)]
+
+
+SD_SYNTH_MAX_TRIPLES = 40
+
 # name -> (restype, argtypes); every symbol declared in include/slamdunk_b200.h
 _VP = ctypes.c_void_p
 PROTOTYPES = {
@@ -101,8 +110,8 @@ PROTOTYPES = {
     "sd_load_fasta": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.POINTER(HGenome)),
                                      ctypes.c_char_p, ctypes.c_int]),
     "sd_hgenome_free": (None, [ctypes.POINTER(HGenome)]),
-    "sd_synth_sizes": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), _VP, _VP, _VP, _VP, ctypes.c_uint32, _VP, _VP]),
-    "sd_synth_fill": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), _VP, _VP, _VP, _VP, ctypes.c_uint32, _VP,
+    "sd_synth_plan": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP, _VP, c_u64p]),
+    "sd_synth_fill": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP,
                                      ctypes.POINTER(Batch), _VP]),
     "sd_synth_genome": (ctypes.c_int, [_VP, ctypes.c_uint64, _VP, _VP, _VP, ctypes.c_uint64, _VP, _VP, ctypes.c_uint32,
                                        ctypes.c_float]),

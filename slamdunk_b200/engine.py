@@ -71,7 +71,7 @@ class HostGenome(object):
 class HostBatch(object):
     """A BAM file decoded into the columnar batch (sd_decode_bam); buffers are page-locked."""
 
-    def __init__(self, path: str, fasta_names: Sequence[str], want_mp: bool = True, tile_reads: int = 256,
+    def __init__(self, path: str, fasta_names: Sequence[str], want_mp: bool = True, tile_reads: int = 0,
                  threads: int = 0):
         lib = L.load()
         err = ctypes.create_string_buffer(512)

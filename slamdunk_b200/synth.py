@@ -1,0 +1,205 @@
+"""Synthetic SLAM-seq workloads (BASELINE.json configs) generated on the device.
+
+Host side: genome layout, UTR annotation and expression profile (numpy, seeded).  Device side:
+sd_synth_genome / sd_synth_plan / sd_synth_fill in libslamdunk_b200.so write the genome planes and
+the columnar read batches.  SURVEY.md section 8(d) gives the recipe (cfg2: ~100 Mb genome on 21
+contigs, 20 000 UTRs with log-normal lengths, geometric expression profile, 100 bp reads, 2.5 %
+T>C per reference T, 0.2 % errors, 5 % soft clips, 2 % indels, 3 % mapq 0, 98 % sense strand).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import CountEngine, DeviceBatch
+
+MOUSE_LIKE_CHROMS = ["chr%d" % i for i in range(1, 20)] + ["chrX", "chrY"]
+
+
+def genome_layout(chrom_len):
+    """chromosome starts in the linear bit space: multiples of 32, >= 32 pad positions between."""
+    off, bits = [], 32
+    for l in chrom_len:
+        off.append(bits)
+        bits = ((bits + int(l) + 31) // 32) * 32 + 32
+    return np.array(off, dtype=np.uint32), bits // 32
+
+
+class Annotation(object):
+    """UTRs sorted by genome position (BED order = genome order) with expression weights."""
+
+    def __init__(self, chrom, start, stop, strand, weight):
+        self.chrom = np.asarray(chrom, dtype=np.uint32)
+        self.start = np.asarray(start, dtype=np.int64)
+        self.stop = np.asarray(stop, dtype=np.int64)
+        self.strand = np.asarray(strand, dtype=np.uint8)
+        self.weight = np.asarray(weight, dtype=np.float64)
+
+    def __len__(self):
+        return len(self.chrom)
+
+
+def make_annotation(seed, chrom_len, n_utr, overlap_frac=0.05):
+    rng = np.random.RandomState(seed)
+    chrom_len = np.asarray(chrom_len, dtype=np.int64)
+    share = chrom_len / chrom_len.sum()
+    per = np.floor(share * n_utr).astype(int)
+    per[0] += n_utr - per.sum()
+    chrom, start, stop, strand = [], [], [], []
+    for c, k in enumerate(per):
+        if k <= 0:
+            continue
+        ln = np.clip(np.exp(rng.normal(np.log(1000.0), 0.8, size=k)), 200, 10000).astype(np.int64)
+        slot = chrom_len[c] // k
+        ln = np.minimum(ln, max(50, slot - 10))
+        base = np.arange(k, dtype=np.int64) * slot
+        st = base + (rng.rand(k) * np.maximum(1, slot - ln)).astype(np.int64)
+        ov = rng.rand(k) < overlap_frac                      # overlap the previous UTR
+        ov[0] = False
+        prev_stop = np.roll(st + ln, 1)
+        st = np.where(ov, np.maximum(0, prev_stop - (ln // 3 + 1)), st)
+        sp = np.minimum(st + ln, chrom_len[c])
+        chrom.append(np.full(k, c)); start.append(st); stop.append(sp); strand.append(rng.randint(0, 2, size=k))
+    chrom = np.concatenate(chrom); start = np.concatenate(start); stop = np.concatenate(stop); strand = np.concatenate(strand)
+    order = np.lexsort((start, chrom))
+    chrom, start, stop, strand = chrom[order], start[order], stop[order], strand[order]
+    # geometric expression profile over a random ranking of the UTRs
+    n = len(chrom)
+    rank = rng.permutation(n)
+    p = 8.0 / n
+    weight = np.power(1.0 - p, rank.astype(np.float64)) + 1e-4
+    return Annotation(chrom, start, stop, strand, weight)
+
+
+class SynthWorkload(object):
+    """Genome + annotation resident on one GPU; hands out read batches."""
+
+    def __init__(self, engine: CountEngine, seed=1, genome_bp=100_000_000, n_utr=20000, chrom_names=None,
+                 n_frac=0.001):
+        self.eng = engine
+        self.lib = engine.lib
+        dev = engine.device
+        self.names = list(chrom_names or MOUSE_LIKE_CHROMS)
+        nc = len(self.names)
+        # mouse-like decreasing chromosome sizes
+        w = np.linspace(1.6, 0.5, nc)
+        self.chrom_len = np.maximum(2000, (w / w.sum() * genome_bp)).astype(np.uint32)
+        self.chrom_off, self.n_words = genome_layout(self.chrom_len)
+        with torch.cuda.stream(engine.stream):
+            self.lo = torch.empty(self.n_words, dtype=torch.int32, device=dev)
+            self.hi = torch.empty(self.n_words, dtype=torch.int32, device=dev)
+            self.nmask = torch.empty(self.n_words, dtype=torch.int32, device=dev)
+            self.d_chrom_off = torch.from_numpy(self.chrom_off.view(np.int32)).to(dev)
+            self.d_chrom_len = torch.from_numpy(self.chrom_len.view(np.int32)).to(dev)
+        engine.stream.synchronize()
+        engine._chk(self.lib.sd_synth_genome(engine.ctx, seed, self.lo.data_ptr(), self.hi.data_ptr(), self.nmask.data_ptr(),
+                                             self.n_words, self.chrom_off.ctypes.data, self.chrom_len.ctypes.data, nc,
+                                             ctypes.c_float(n_frac)), "sd_synth_genome")
+        self.ann = make_annotation(seed + 1, self.chrom_len, n_utr)
+        a = self.ann
+        cum = np.cumsum(a.weight)
+        with torch.cuda.stream(engine.stream):
+            self.d_utr_chrom = torch.from_numpy(a.chrom.astype(np.int32)).to(dev)
+            self.d_utr_start = torch.from_numpy(a.start.astype(np.int32)).to(dev)
+            self.d_utr_end = torch.from_numpy(a.stop.astype(np.int32)).to(dev)
+            self.d_utr_strand = torch.from_numpy(a.strand.astype(np.uint8)).to(dev)
+            self.d_cum = torch.from_numpy(cum).to(dev)
+        engine.stream.synchronize()
+        self.cum_weight = cum
+        t = L.SynthTables()
+        t.lo, t.hi, t.nmask = self.lo.data_ptr(), self.hi.data_ptr(), self.nmask.data_ptr()
+        t.chrom_off, t.chrom_len, t.n_chrom = self.d_chrom_off.data_ptr(), self.d_chrom_len.data_ptr(), nc
+        t.n_utr = len(a)
+        t.utr_chrom, t.utr_start, t.utr_end = self.d_utr_chrom.data_ptr(), self.d_utr_start.data_ptr(), self.d_utr_end.data_ptr()
+        t.utr_strand, t.utr_cum_weight = self.d_utr_strand.data_ptr(), self.d_cum.data_ptr()
+        self.tables = t
+
+    def install(self):
+        """Hand genome and annotation to the engine (sd_set_reference / sd_set_utrs)."""
+        self.eng.set_reference(self.lo, self.hi, self.nmask, self.chrom_off, self.chrom_len)
+        a = self.ann
+        self.eng.set_utrs(a.chrom, a.start, a.stop, a.strand, None)
+
+    def region_split(self, n_parts):
+        """Contiguous UTR ranges (genome order) with equal expected read counts -> [(first, count)]."""
+        cum = self.cum_weight
+        cuts = [0]
+        for k in range(1, n_parts):
+            cuts.append(int(np.searchsorted(cum, cum[-1] * k / n_parts)))
+        cuts.append(len(cum))
+        for k in range(1, len(cuts)):
+            cuts[k] = max(cuts[k], cuts[k - 1] + 1)
+        cuts[-1] = len(cum)
+        return [(cuts[k], cuts[k + 1] - cuts[k]) for k in range(n_parts)]
+
+    def params(self, seed, first_read, n_reads, read_len=100, tile_reads=256, p_conv=0.025, p_err=0.002,
+               frac_softclip=0.05, frac_indel=0.02, frac_multimap=0.03, frac_antisense=0.02, frac_labelled=1.0,
+               utr_first=0, utr_count=0) -> L.SynthParams:
+        p = L.SynthParams()
+        p.seed, p.first_read, p.n_reads = int(seed), int(first_read), int(n_reads)
+        p.read_len, p.tile_reads = int(read_len), int(tile_reads)
+        p.p_conv, p.p_err = p_conv, p_err
+        p.frac_softclip, p.frac_indel, p.frac_multimap = frac_softclip, frac_indel, frac_multimap
+        p.frac_antisense, p.frac_labelled = frac_antisense, frac_labelled
+        p.utr_first, p.utr_count = int(utr_first), int(utr_count)
+        return p
+
+    def generate(self, p: L.SynthParams, want_mp=False, want_triples=False):
+        """-> (DeviceBatch, triples tensor or None)"""
+        eng, dev = self.eng, self.eng.device
+        n = int(p.n_reads)
+        T = int(p.tile_reads)
+        n_tiles = (n + T - 1) // T
+        with torch.cuda.stream(eng.stream):
+            counts = torch.empty(n, dtype=torch.int32, device=dev)
+            tiles = torch.empty((n_tiles + 1) * 4, dtype=torch.int64, device=dev)
+        eng.stream.synchronize()
+        totals = (ctypes.c_uint64 * 4)()
+        eng._chk(self.lib.sd_synth_plan(eng.ctx, ctypes.byref(p), ctypes.byref(self.tables), counts.data_ptr(),
+                                        tiles.data_ptr(), totals), "sd_synth_plan")
+        with torch.cuda.stream(eng.stream):
+            tens = {
+                "rec": torch.empty(n_tiles * T * 20, dtype=torch.uint8, device=dev),
+                "seq": torch.empty(max(16, totals[0]), dtype=torch.uint8, device=dev),
+                "qual": torch.zeros(max(16, totals[1]), dtype=torch.uint8, device=dev),
+                "cigar": torch.zeros(max(16, totals[2]), dtype=torch.uint8, device=dev),
+                "mp": torch.zeros(max(16, totals[3]), dtype=torch.uint8, device=dev) if want_mp else None,
+                "tiles": tiles,
+            }
+            triples = torch.zeros((n, 1 + 3 * L.SD_SYNTH_MAX_TRIPLES), dtype=torch.int32, device=dev) if want_triples else None
+        eng.stream.synchronize()
+        b = L.Batch()
+        b.rec, b.seq, b.qual, b.cigar = tens["rec"].data_ptr(), tens["seq"].data_ptr(), tens["qual"].data_ptr(), tens["cigar"].data_ptr()
+        b.mp = tens["mp"].data_ptr() if want_mp else None
+        b.tiles = tiles.data_ptr()
+        eng._chk(self.lib.sd_synth_fill(eng.ctx, ctypes.byref(p), ctypes.byref(self.tables), counts.data_ptr(),
+                                        ctypes.byref(b), triples.data_ptr() if want_triples else None), "sd_synth_fill")
+        return DeviceBatch(b, tens), triples
+
+
+def algorithmic_bytes_per_read(read_len, mean_cigar_ops):
+    """Compulsory bytes per read of the columnar layout, each touched once by the count kernel
+    (DESIGN.md): sliced 4-bit SEQ rounded to 8 bases, QUAL, CIGAR ops, the 20-byte record."""
+    return 4 * ((read_len + 7) // 8) + read_len + 4.0 * mean_cigar_ops + 20
+
+
+def batch_to_host(db: DeviceBatch):
+    """Pinned host copy of a device batch -> (L.Batch with host pointers, keep-alive dict)."""
+    host = {}
+    for k, t in db.tensors.items():
+        if t is None:
+            host[k] = None
+            continue
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        host[k] = h
+    b = L.Batch()
+    ctypes.memmove(ctypes.byref(b), ctypes.byref(db.batch), ctypes.sizeof(L.Batch))
+    b.rec, b.seq, b.qual, b.cigar = host["rec"].data_ptr(), host["seq"].data_ptr(), host["qual"].data_ptr(), host["cigar"].data_ptr()
+    b.mp = host["mp"].data_ptr() if host["mp"] is not None else None
+    b.tiles = host["tiles"].data_ptr()
+    return b, host

@@ -1,0 +1,153 @@
+"""The device-side synthetic generator and the count path on its output, against the oracle."""
+import numpy as np
+import pytest
+
+import oracle_bridge as ob
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(genome_bp=3_000_000, n_utr=600, seed=5):
+    from slamdunk_b200.engine import CountEngine
+    from slamdunk_b200.synth import SynthWorkload
+    eng = CountEngine(0)
+    wl = SynthWorkload(eng, seed=seed, genome_bp=genome_bp, n_utr=n_utr, n_frac=0.01)
+    wl.install()
+    return eng, wl
+
+
+def _oracle(wl, db, triples, min_qual, thr, threads=4):
+    g = ob.genome_from_planes(wl.names, wl.chrom_off, wl.chrom_len, wl.lo.cpu().numpy().view(np.uint32),
+                              wl.hi.cpu().numpy().view(np.uint32), wl.nmask.cpu().numpy().view(np.uint32))
+    reads, qual, mp = ob.batch_to_oracle(ob.device_batch_to_numpy(db), triples.cpu().numpy())
+    return oracle.count_arrays(g, reads, qual, ob.annotation_to_oracle(wl.ann, len(wl.names)), min_qual, thr,
+                               None, mp_triples=mp, threads=threads)
+
+
+@pytest.mark.parametrize("read_len,n_reads,mode", [(100, 200_000, "cigar"), (100, 100_000, "verify"), (150, 100_000, "mp"),
+                                                   (250, 60_000, "cigar"), (36, 50_000, "verify")])
+def test_synthetic_reads_count_like_the_oracle(read_len, n_reads, mode):
+    from slamdunk_b200 import _lib as L
+    from slamdunk_b200.engine import make_params
+    eng, wl = _setup()
+    p = wl.params(seed=9, first_read=0, n_reads=n_reads, read_len=read_len, frac_softclip=0.1, frac_indel=0.08,
+                  frac_antisense=0.05, frac_labelled=0.8)
+    db, triples = wl.generate(p, want_mp=True, want_triples=True)
+    eng.count(db, make_params(27, 1, {"cigar": 0, "mp": 1, "verify": 2}[mode]))
+    eng.finalize()
+    res = eng.results()
+    rows, bg = _oracle(wl, db, triples, 27, 1)
+    assert res["stats"][L.SD_S_COUNTED] == n_reads
+    assert res["stats"][L.SD_S_MP_DISAGREE] == 0
+    assert rows["read_count"].sum() > n_reads * 0.9
+    assert rows["conversions_on_ts"].sum() > 0
+    assert ob.compare(res, rows, bg, wl.ann, eng.pos_off, wl.chrom_off) == []
+    eng.close()
+
+
+def test_generator_is_index_keyed_and_shards_add_up():
+    """Any split of the read-index range gives the same reads, and per-shard counters sum to the
+    unsharded result (the multi-GPU contract: integer sums are partition independent)."""
+    import torch
+    from slamdunk_b200.engine import make_params
+    eng, wl = _setup()
+    n = 90_000
+    params = make_params(27, 1, 0)
+    whole, _ = wl.generate(wl.params(seed=3, first_read=0, n_reads=n))
+    eng.count(whole, params)
+    eng.synchronize()
+    ref_counters = eng.counters.clone()
+    ref_cov = eng.pos_cov.clone()
+    ref_tc = eng.pos_tc.clone()
+    eng.reset_outputs()
+    for first, cnt in ((0, 25_600), (25_600, 40_192), (65_792, n - 65_792)):
+        part, _ = wl.generate(wl.params(seed=3, first_read=first, n_reads=cnt))
+        if first == 0:
+            a = whole.tensors["rec"][:cnt * 20]
+            assert torch.equal(a, part.tensors["rec"][:cnt * 20])
+            assert torch.equal(whole.tensors["qual"][:cnt * 100], part.tensors["qual"][:cnt * 100])
+        eng.count(part, params)
+    eng.synchronize()
+    assert torch.equal(eng.counters, ref_counters)
+    assert torch.equal(eng.pos_cov, ref_cov) and torch.equal(eng.pos_tc, ref_tc)
+    eng.close()
+
+
+def test_region_sharding_matches_unsharded():
+    """UTR-owner region sharding: reads generated per region and counted separately
+    sum to the same table as all of them counted together."""
+    import torch
+    from slamdunk_b200.engine import make_params
+    eng, wl = _setup()
+    params = make_params(27, 1, 0)
+    parts = wl.region_split(4)
+    assert sum(c for _f, c in parts) == len(wl.ann)
+    batches = [wl.generate(wl.params(seed=11 + k, first_read=0, n_reads=30_000, utr_first=f, utr_count=c))[0]
+               for k, (f, c) in enumerate(parts)]
+    total = torch.zeros_like(eng.counters)
+    for b in batches:
+        eng.reset_outputs()
+        eng.count(b, params)
+        eng.synchronize()
+        total += eng.counters
+    eng.reset_outputs()
+    for b in batches:
+        eng.count(b, params)
+    eng.synchronize()
+    assert torch.equal(total, eng.counters)
+    eng.close()
+
+
+def test_count_host_equals_count_device():
+    """The end-to-end entry (host buffers, chunked H2D overlapped with the kernel) == device-resident."""
+    import torch
+    from slamdunk_b200.engine import make_params
+    from slamdunk_b200.synth import batch_to_host
+    eng, wl = _setup()
+    params = make_params(27, 1, 0)
+    db, _ = wl.generate(wl.params(seed=21, first_read=0, n_reads=300_000))
+    eng.count(db, params)
+    eng.synchronize()
+    want = (eng.counters.clone(), eng.pos_cov.clone(), eng.pos_tc.clone(), eng.stats.clone())
+    hb, keep = batch_to_host(db)
+    eng.reset_outputs()
+    eng.count_host(hb, params)
+    got = (eng.counters, eng.pos_cov, eng.pos_tc, eng.stats)
+    for w, g in zip(want, got):
+        assert torch.equal(w, g)
+    eng.close()
+
+
+def test_filter_predicates_fused_into_count():
+    """filter_on: the default-branch predicates of filter.Filter (filter.py:241-251) run in front of the
+    scan; stats equal the oracle's filter, counters equal counting only the survivors."""
+    from slamdunk_b200 import _lib as L
+    from slamdunk_b200.engine import make_params
+    eng, wl = _setup()
+    n = 80_000
+    db, triples = wl.generate(wl.params(seed=31, first_read=0, n_reads=n, p_err=0.02, frac_indel=0.2, frac_multimap=0.2),
+                              want_triples=True)
+    eng.count(db, make_params(27, 1, 0, filter_on=True, filter_mq=2, filter_min_identity=0.95, filter_max_nm=3))
+    eng.finalize()
+    res = eng.results()
+    bn = ob.device_batch_to_numpy(db)
+    rec = bn["rec"][:n]
+    fr = np.zeros(n, dtype=oracle.FREAD_DT)
+    flags = rec[:, 1] >> 24
+    fr["flag"] = np.where(flags & L.SD_F_REVERSE, 16, 0)
+    fr["mapq"] = (rec[:, 1] >> 16) & 0xFF
+    fr["xi"] = rec[:, 2].view(np.float32)
+    fr["nm"] = rec[:, 4] & 0xFFFF
+    keep = np.zeros(n, dtype=np.uint8)
+    stats = np.zeros(7, dtype=np.int64)
+    oracle.lib().orc_filter_default(fr.ctypes.data, n, 2, 0.95, 3, keep.ctypes.data, stats.ctypes.data)
+    assert res["stats"][:6].tolist() == stats[:6].tolist()
+    assert 0 < stats[2] < n and stats[3] > 0 and stats[4] > 0 and stats[5] > 0
+    g = ob.genome_from_planes(wl.names, wl.chrom_off, wl.chrom_len, wl.lo.cpu().numpy().view(np.uint32),
+                              wl.hi.cpu().numpy().view(np.uint32), wl.nmask.cpu().numpy().view(np.uint32))
+    reads, qual, mp = ob.batch_to_oracle(bn, triples.cpu().numpy())
+    rows, bg = oracle.count_arrays(g, reads[keep.astype(bool)], qual, ob.annotation_to_oracle(wl.ann, len(wl.names)),
+                                   27, 1, None, mp_triples=mp, threads=4)
+    assert ob.compare(res, rows, bg, wl.ann, eng.pos_off, wl.chrom_off) == []
+    eng.close()
