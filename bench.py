@@ -101,7 +101,7 @@ class ClockSampler(object):
 
 
 def build_workload(local_rank, rank, world, n_reads, read_len, genome_bp, n_utr, want_triples=False, first_read=None,
-                   want_mp=False):
+                   want_mp=False, coordinate_sorted=True):
     from slamdunk_b200.engine import CountEngine
     from slamdunk_b200.synth import SynthWorkload
     eng = CountEngine(local_rank)
@@ -110,7 +110,7 @@ def build_workload(local_rank, rank, world, n_reads, read_len, genome_bp, n_utr,
     first, count = (0, 0) if world == 1 else wl.region_split(world)[rank]
     fr = rank * n_reads if first_read is None else first_read
     p = wl.params(seed=3, first_read=fr, n_reads=n_reads, read_len=read_len, utr_first=first, utr_count=count)
-    db, triples = wl.generate(p, want_mp=want_mp, want_triples=want_triples)
+    db, triples = wl.generate(p, want_mp=want_mp, want_triples=want_triples, coordinate_sorted=coordinate_sorted)
     return eng, wl, db, triples
 
 
@@ -180,7 +180,7 @@ def workload_config(args, sample_reads=None):
                      "2.5%% T>C per reference T" % (args.reads, args.read_len, args.utrs, args.genome_bp / 1e6),
          "reads_per_gpu": args.reads, "read_len": args.read_len, "n_utr": args.utrs,
          "filter": "MQ>=2, identity>=0.95 (slamdunk defaults)", "min_base_qual": MIN_QUAL, "conversion_threshold": CONV_THRESHOLD,
-         "mismatch_source": "cigar_walk", "sharding": "utr_owner_regions" if args.gpus > 1 else "none",
+         "mismatch_source": "cigar_walk", "read_order": args.order, "sharding": "utr_owner_regions" if args.gpus > 1 else "none",
          "l2_policy": "inputs (~%.1f GB per GPU) far exceed the 126 MB L2; no explicit flush" % (args.reads * 176.3 / 1e9)}
     if sample_reads is not None:
         c["sample_reads"] = sample_reads
@@ -198,6 +198,9 @@ def main():
     ap.add_argument("--utrs", type=int, default=20000)
     ap.add_argument("--genome-bp", type=int, default=100_000_000, dest="genome_bp")
     ap.add_argument("--cpu-sample", type=int, default=4_000_000, dest="cpu_sample")
+    ap.add_argument("--order", default="sorted", choices=["sorted", "mapper"],
+                    help="read order inside the batch: coordinate-sorted (what `slamdunk count` reads: the sorted BAM "
+                         "written by `slamdunk filter`) or mapper order (random placement, the filter's input)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -223,7 +226,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    eng, wl, db, _ = build_workload(local_rank, rank, world, args.reads, args.read_len, args.genome_bp, args.utrs)
+    eng, wl, db, _ = build_workload(local_rank, rank, world, args.reads, args.read_len, args.genome_bp, args.utrs,
+                                    coordinate_sorted=(args.order == "sorted"))
     params = make_params(MIN_QUAL, CONV_THRESHOLD, L.SD_MISMATCH_CIGAR, **FILTER)
     n_reads = args.reads
 
@@ -319,7 +323,7 @@ def main():
         import oracle_bridge as ob
         sample = min(n_reads, args.cpu_sample)
         p = wl.params(seed=3, first_read=0, n_reads=sample, read_len=args.read_len)
-        sdb, triples = wl.generate(p, want_triples=True)
+        sdb, triples = wl.generate(p, want_triples=True, coordinate_sorted=(args.order == "sorted"))
         inp = oracle_inputs(wl, sdb, triples)
         threads = oracle.max_threads()
         dt, rows, bg, ostats = oracle_pass(*inp, threads=threads)

@@ -294,6 +294,8 @@ typedef struct sd_synth_params {
     float frac_antisense;     /* reads on the strand opposite to their UTR */
     float frac_labelled;      /* reads that carry conversions at all */
     uint32_t utr_first, utr_count; /* restrict placement to this range of the expression table */
+    const uint32_t *order;    /* optional device uint32[n_reads]: batch slot j holds read first_read + order[j]
+                                 (e.g. the coordinate-sort permutation, as `slamdunk filter` sorts its output) */
 } sd_synth_params;
 
 /* Device-resident tables the generator reads. */
@@ -312,6 +314,9 @@ typedef struct sd_synth_tables {
 
 #define SD_SYNTH_MAX_TRIPLES 40
 
+/* Linear genome position of every read's alignment start (placement only), device uint32[n_reads];
+ * argsort it to build sd_synth_params.order.  Ignores p->order.  Synchronous. */
+int sd_synth_positions(sd_ctx *ctx, const sd_synth_params *p, const sd_synth_tables *t, uint32_t *d_gpos);
 /* Pass 1: simulate every read once to learn its CIGAR and MP entry counts.
  * d_counts: device uint32[n_reads] scratch (n_cigar | n_mp << 16), d_tiles: device sd_tile[n_tiles + 1]
  * (filled), h_totals: host uint64[4] = total bytes of the seq, qual, cigar and mp columns.  Synchronous. */

@@ -68,7 +68,7 @@ class SynthParams(ctypes.Structure):
                 ("read_len", ctypes.c_uint32), ("tile_reads", ctypes.c_uint32), ("p_conv", ctypes.c_float),
                 ("p_err", ctypes.c_float), ("frac_softclip", ctypes.c_float), ("frac_indel", ctypes.c_float),
                 ("frac_multimap", ctypes.c_float), ("frac_antisense", ctypes.c_float), ("frac_labelled", ctypes.c_float),
-                ("utr_first", ctypes.c_uint32), ("utr_count", ctypes.c_uint32)]
+                ("utr_first", ctypes.c_uint32), ("utr_count", ctypes.c_uint32), ("order", ctypes.c_void_p)]
 
 
 class SynthTables(ctypes.Structure):
@@ -110,6 +110,7 @@ PROTOTYPES = {
     "sd_load_fasta": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.POINTER(HGenome)),
                                      ctypes.c_char_p, ctypes.c_int]),
     "sd_hgenome_free": (None, [ctypes.POINTER(HGenome)]),
+    "sd_synth_positions": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP]),
     "sd_synth_plan": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP, _VP, c_u64p]),
     "sd_synth_fill": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP,
                                      ctypes.POINTER(Batch), _VP]),

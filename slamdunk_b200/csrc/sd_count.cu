@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -294,29 +295,82 @@ __device__ __noinline__ int slow_read(const CountArgs &A, const ReadView &v, uin
 
 // ---------------------------------------------------------------------------------------
 // Word-parallel path.  W = window words (32 reference bases each).
+//
+// The alignment is reduced to at most three match blocks [r0, r1) of the window, each with the
+// offset `sh` that turns a window position into a read index (one block: plain or soft-clipped
+// read; two: one insertion or deletion; three: two indels).  With |sh| < 32 every block is a
+// multi-word funnel shift of the read mask, all in registers.  Anything else (more blocks,
+// larger shifts) goes through a shared-memory scratch copy of the read mask.
 // ---------------------------------------------------------------------------------------
+struct Blocks {
+    int n;               // match blocks found (only the first three are described below)
+    int r1a, r1b;        // window end of block 0 / 1 (block 2 runs to the end)
+    int r0b, r0c;        // window start of block 1 / 2 (block 0 starts at 0 ... its own r0a below)
+    int r0a, r1c;
+    int sha, shb, shc;   // read index = window position + sh
+    bool regs_ok;        // describable by <= 3 blocks with |sh| < 32
+};
+
+__device__ __forceinline__ int parse_cigar(const uint32_t *cig, uint32_t ncig, Blocks &B) {
+    int q = 0, r = 0;
+    B.n = 0;
+    B.r0a = B.r1a = B.r0b = B.r1b = B.r0c = B.r1c = 0;
+    B.sha = B.shb = B.shc = 0;
+    for (uint32_t i = 0; i < ncig; i++) {
+        const uint32_t c = cig[i], op = c & 15u;
+        const int len = (int)(c >> 4);
+        if (cigar_is_match(op)) {
+            if (B.n == 0) { B.r0a = r; B.r1a = r + len; B.sha = q - r; }
+            else if (B.n == 1) { B.r0b = r; B.r1b = r + len; B.shb = q - r; }
+            else if (B.n == 2) { B.r0c = r; B.r1c = r + len; B.shc = q - r; }
+            B.n++;
+            q += len;
+            r += len;
+        } else if (op == 1 || op == 4) {
+            q += len;
+        } else if (op == 2 || op == 3) {
+            r += len;
+        }
+    }
+    auto small = [](int s) { return s > -32 && s < 32; };
+    B.regs_ok = B.n <= 3 && small(B.sha) && small(B.shb) && small(B.shc);
+    return r;  // reference length
+}
+
+// window word k of the read mask M shifted so that window position p reads M bit p + sh, |sh| < 32
 template <int W>
-__device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, uint32_t mapq, uint32_t *scratch,
-                                         bool &mp_disagree) {
+__device__ __forceinline__ uint32_t shifted_word(const uint32_t (&M)[W], int k, int sh) {
+    if (sh >= 0) return __funnelshift_r(M[k], (k + 1 < W) ? M[k + 1] : 0u, (uint32_t)sh);
+    return __funnelshift_r(k > 0 ? M[k - 1] : 0u, M[k], (uint32_t)(32 + sh));
+}
+
+__device__ __forceinline__ int block_read_index(const Blocks &B, int o) {
+    if (B.n <= 1 || o < B.r1a) return o + B.sha;
+    if (B.n == 2 || o < B.r1b) return o + B.shb;
+    return o + B.shc;
+}
+
+template <int W>
+__device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, const Blocks &B, uint32_t mapq,
+                                         uint32_t *scratch, bool &mp_disagree) {
     const int s = v.strand;
     // --- reference window: isX (T or A) and SNP planes, shifted so that bit j = position g + j
     uint32_t T[W], S[W];
     {
         const uint2 *rx = A.refx[s] + (v.g >> 5);
         const uint32_t sh = v.g & 31u;
-        uint2 prev = __ldg(rx);
+        uint2 x[W + 1];
+#pragma unroll
+        for (int k = 0; k <= W; k++) x[k] = __ldg(rx + k);
 #pragma unroll
         for (int k = 0; k < W; k++) {
-            const uint2 next = __ldg(rx + k + 1);
-            const uint32_t m = range_word(k, 0, v.span);
-            T[k] = __funnelshift_r(prev.x, next.x, sh) & m;
-            S[k] = __funnelshift_r(prev.y, next.y, sh);
-            prev = next;
+            T[k] = __funnelshift_r(x[k].x, x[k + 1].x, sh) & range_word(k, 0, v.span);
+            S[k] = __funnelshift_r(x[k].y, x[k + 1].y, sh);
         }
     }
-    // --- read-side candidate mask in reference coordinates
+    // --- read-side candidate mask in window coordinates
     uint32_t R[W];
-    const bool simple = (v.ncig == 1) && cigar_is_match(v.cig[0] & 15u);
+    const bool regs = B.regs_ok;
     if (A.mismatch_source == SD_MISMATCH_MP) {
 #pragma unroll
         for (int k = 0; k < W; k++) R[k] = 0u;
@@ -345,11 +399,27 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             if (4u * k + 3u < nw8) b3 = sliced_is_base(v.seq[4 * k + 3], inv);
             M[k] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
         }
-        if (simple) {
+        if (regs) {
+            if (B.n <= 1) {
+                // one block: bits past its end are cleared by T (masked to the span) later on
+                if (B.sha == 0) {
 #pragma unroll
-            for (int k = 0; k < W; k++) R[k] = M[k];
+                    for (int k = 0; k < W; k++) R[k] = M[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < W; k++) R[k] = shifted_word<W>(M, k, B.sha) & range_word(k, B.r0a, B.r1a);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    uint32_t r = shifted_word<W>(M, k, B.sha) & range_word(k, B.r0a, B.r1a);
+                    r |= shifted_word<W>(M, k, B.shb) & range_word(k, B.r0b, B.r1b);
+                    if (B.n > 2) r |= shifted_word<W>(M, k, B.shc) & range_word(k, B.r0c, B.r1c);
+                    R[k] = r;
+                }
+            }
         } else {
-            // place every aligned block [q, q+len) of the read at reference offset r
+            // generic placement through a scratch copy of the read mask
 #pragma unroll
             for (int k = 0; k < W; k++) {
                 R[k] = 0u;
@@ -398,7 +468,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                     D[k] &= ~(1u << (o & 31));
                     found = true;
                 }
-            if (!found || (simple ? o : ref_to_read(v.cig, v.ncig, o)) != rp) bad = true;
+            if (!found || (regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o)) != rp) bad = true;
         }
 #pragma unroll
         for (int k = 0; k < W; k++) bad |= (D[k] != 0u);
@@ -417,23 +487,20 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             H[k] = h & T[k];
         }
     } else {
-        if (!v.has_mp) {
 #pragma unroll
-            for (int k = 0; k < W; k++) R[k] = 0u;
-        }
+        for (int k = 0; k < W; k++) H[k] = v.has_mp ? (R[k] & T[k] & ~S[k]) : 0u;
+        // base quality only where a candidate survived: one byte from the qual column per candidate
 #pragma unroll
         for (int k = 0; k < W; k++) {
-            uint32_t h = R[k] & T[k] & ~S[k];
-            uint32_t rest = h;
-            while (rest) {  // base quality only where a candidate survived
+            uint32_t rest = H[k];
+            while (rest) {
                 const int bit = __ffs(rest) - 1;
                 rest &= rest - 1u;
                 const int o = 32 * k + bit;
-                const int qi = simple ? o : ref_to_read(v.cig, v.ncig, o);
-                if (qi < 0 || qi >= (int)v.lseq || (int)v.qual[qi] < A.min_qual) h &= ~(1u << bit);
+                const int qi = regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o);
+                if (qi < 0 || qi >= (int)v.lseq || (int)__ldg(v.qual + qi) < A.min_qual) H[k] &= ~(1u << bit);
             }
-            H[k] = h;
-            tc += __popc(h);
+            tc += __popc(H[k]);
         }
     }
     if (tc < A.conv_threshold) {  // not a T>C read: conversions are dropped (tcounter.py:210-214)
@@ -441,6 +508,9 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #pragma unroll
         for (int k = 0; k < W; k++) H[k] = 0u;
     }
+    uint32_t pop_t = 0;
+#pragma unroll
+    for (int k = 0; k < W; k++) pop_t += __popc(T[k]);
     // --- interval join + per-UTR reduction + per-position scatter
     const uint32_t g = v.g, e = v.g + (uint32_t)v.span;
     const uint32_t nU = A.n_u[s];
@@ -452,14 +522,22 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
         if (st >= e) break;
         const uint32_t en = __ldg(&ue[i]);
         if (en > g) {
-            const int lo = st > g ? (int)(st - g) : 0;
-            const int hi = en < e ? (int)(en - g) : v.span;
-            uint32_t cov_t = 0, conv = 0;
+            uint32_t cov_t = pop_t, conv = (uint32_t)tc;
+            if (st > g || en < e) {  // the UTR covers only part of the read
+                const int lo = st > g ? (int)(st - g) : 0;
+                const int hi = en < e ? (int)(en - g) : v.span;
+                cov_t = 0;
+                conv = 0;
 #pragma unroll
-            for (int k = 0; k < W; k++) {
-                const uint32_t m = range_word(k, lo, hi);
-                cov_t += __popc(T[k] & m);
-                conv += __popc(H[k] & m);
+                for (int k = 0; k < W; k++) {
+                    const uint32_t m = range_word(k, lo, hi);
+                    cov_t += __popc(T[k] & m);
+                    conv += __popc(H[k] & m);
+                }
+            } else if (A.mismatch_source == SD_MISMATCH_MP) {
+                conv = 0;
+#pragma unroll
+                for (int k = 0; k < W; k++) conv += __popc(H[k]);
             }
             utr_accumulate(A.counters, __ldg(&A.urow[s][i]), tc > 0 ? 1u : 0u, mapq == 0 ? 1u : 0u, cov_t, conv);
             const uint32_t seg = __ldg(&A.useg[s][i]);
@@ -471,9 +549,11 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                 atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
                 atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
                 if (tc > 0) {
+                    const bool whole = (pa == g && pb == e);
 #pragma unroll
                     for (int k = 0; k < W; k++) {
-                        uint32_t h = H[k] & range_word(k, (int)(pa - g), (int)(pb - g));
+                        uint32_t h = H[k];
+                        if (!whole) h &= range_word(k, (int)(pa - g), (int)(pb - g));
                         while (h) {
                             const int bit = __ffs(h) - 1;
                             h &= h - 1u;
@@ -489,168 +569,174 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 }
 
 // ---------------------------------------------------------------------------------------
-// The persistent streaming kernel
+// The persistent streaming kernel.
+//
+// One CTA = NW consumer warps (one read per thread, a tile = 32 * NW reads) + one producer warp.
+// The producer's elected lane keeps a ring of shared-memory stages filled with TMA bulk copies
+// (records, sliced SEQ, CIGAR ops and, when needed, MP entries of one tile per stage).  Consumer
+// warps never synchronize with each other: each waits on the stage's "full" mbarrier, derives its
+// rows' offsets from the records of the warps before it, works, and arrives on the stage's "empty"
+// mbarrier.  The QUAL column is not staged: a base quality is needed only where the read shows a
+// C over a reference T (about one base per read), so it is fetched from global memory right
+// there -- this keeps the shared-memory footprint per warp small enough for high occupancy and
+// leaves most of the qual column's DRAM sectors untouched.
 // ---------------------------------------------------------------------------------------
 #define SD_SMEM_STATS 8
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int W>
-__global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ CountArgs A) {
+__global__ void __launch_bounds__(288) sd_count_kernel(const __grid_constant__ CountArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_qual + A.cap_cig + A.cap_mp;
+    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
     unsigned char *stages = smem;
     unsigned char *tail = smem + (size_t)A.n_stages * stage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tail);                   // [n_stages]
-    uint32_t *s_stats = reinterpret_cast<uint32_t *>(tail + 64);           // [SD_SMEM_STATS]
-    uint32_t *s_wx = reinterpret_cast<uint32_t *>(tail + 128);             // [8] warp totals (seq words | ncig << 16)
-    unsigned long long *s_wy = reinterpret_cast<unsigned long long *>(tail + 192);  // [8] (qual bytes | nmp << 32)
-    uint32_t *s_scratch = reinterpret_cast<uint32_t *>(tail + 256);        // [blockDim * (W + 1)]
+    uint64_t *full = reinterpret_cast<uint64_t *>(tail);                   // [n_stages]
+    uint64_t *empty = reinterpret_cast<uint64_t *>(tail + 64);             // [n_stages]
+    uint32_t *s_stats = reinterpret_cast<uint32_t *>(tail + 128);          // [SD_SMEM_STATS]
+    uint32_t *s_scratch = reinterpret_cast<uint32_t *>(tail + 192);        // [tile_reads * (W + 1)]
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t nwarps = blockDim.x >> 5;
+    const uint32_t NW = A.tile_reads >> 5;   // consumer warps; warp NW is the producer
 
     if (tid == 0) {
-        for (uint32_t s = 0; s < A.n_stages; s++) mbar_init(&bars[s], 1);
+        for (uint32_t s = 0; s < A.n_stages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NW);
+        }
         mbar_fence_init();
     }
     if (tid < SD_SMEM_STATS) s_stats[tid] = 0u;
     __syncthreads();
 
-    auto issue = [&](uint32_t tile, uint32_t stage) {
-        unsigned char *base = stages + (size_t)stage * stage_bytes;
-        const sd_tile t0 = A.tiles[tile], t1 = A.tiles[tile + 1];
-        const uint32_t b_rec = A.tile_reads * (uint32_t)sizeof(sd_read_rec);
-        const uint32_t b_seq = (uint32_t)(t1.seq_off - t0.seq_off);
-        const uint32_t b_qual = (uint32_t)(t1.qual_off - t0.qual_off);
-        const uint32_t b_cig = (uint32_t)(t1.cig_off - t0.cig_off);
-        const uint32_t b_mp = A.mp ? (uint32_t)(t1.mp_off - t0.mp_off) : 0u;
-        mbar_arrive_expect_tx(&bars[stage], b_rec + b_seq + b_qual + b_cig + b_mp);
-        bulk_g2s(base, reinterpret_cast<const unsigned char *>(A.rec) + (size_t)tile * b_rec, b_rec, &bars[stage]);
-        if (b_seq) bulk_g2s(base + A.cap_rec, reinterpret_cast<const unsigned char *>(A.seq) + t0.seq_off, b_seq, &bars[stage]);
-        if (b_qual) bulk_g2s(base + A.cap_rec + A.cap_seq, A.qual + t0.qual_off, b_qual, &bars[stage]);
-        if (b_cig)
-            bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_qual, reinterpret_cast<const unsigned char *>(A.cigar) + t0.cig_off,
-                     b_cig, &bars[stage]);
-        if (b_mp)
-            bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_qual + A.cap_cig,
-                     reinterpret_cast<const unsigned char *>(A.mp) + t0.mp_off, b_mp, &bars[stage]);
-    };
-
-    if (tid == 0) {
-        for (uint32_t s = 0; s < A.n_stages; s++) {
-            const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x;
-            if (t < A.n_tiles) issue((uint32_t)t, s);
-        }
-    }
-
     uint32_t my_counted = 0, my_slow = 0, my_disagree = 0;
     unsigned long long my_tc_total = 0;
-    uint32_t stage = 0, phase = 0;
-    for (uint64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-        mbar_wait(&bars[stage], phase);
-        const unsigned char *base = stages + (size_t)stage * stage_bytes;
-        const uint32_t *rw = reinterpret_cast<const uint32_t *>(base) + 5u * tid;
-        const int32_t pos = (int32_t)rw[0];
-        const uint32_t rmf = rw[1];
-        const float xi = __uint_as_float(rw[2]);
-        const uint32_t lseq = rw[3] & 0xFFFFu, ncig = rw[3] >> 16;
-        const uint32_t nm = rw[4] & 0xFFFFu, nmp = A.mp ? (rw[4] >> 16) : 0u;
 
-        // exclusive scan of this read's row sizes over the tile -> row offsets
-        uint32_t x = ((lseq + 7u) >> 3) | (ncig << 16);
-        unsigned long long y = (unsigned long long)lseq | ((unsigned long long)nmp << 32);
-        uint32_t xs = x;
-        unsigned long long ys = y;
+    if (warp == NW) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, it++) {
+                const uint32_t stage = it % A.n_stages, use = it / A.n_stages;
+                if (use > 0) mbar_wait(&empty[stage], (use - 1u) & 1u);
+                unsigned char *base = stages + (size_t)stage * stage_bytes;
+                const sd_tile t0 = A.tiles[tile], t1 = A.tiles[tile + 1];
+                const uint32_t b_rec = A.tile_reads * (uint32_t)sizeof(sd_read_rec);
+                const uint32_t b_seq = (uint32_t)(t1.seq_off - t0.seq_off);
+                const uint32_t b_cig = (uint32_t)(t1.cig_off - t0.cig_off);
+                const uint32_t b_mp = A.mp ? (uint32_t)(t1.mp_off - t0.mp_off) : 0u;
+                mbar_arrive_expect_tx(&full[stage], b_rec + b_seq + b_cig + b_mp);
+                bulk_g2s(base, reinterpret_cast<const unsigned char *>(A.rec) + (size_t)tile * b_rec, b_rec, &full[stage]);
+                if (b_seq) bulk_g2s(base + A.cap_rec, reinterpret_cast<const unsigned char *>(A.seq) + t0.seq_off, b_seq, &full[stage]);
+                if (b_cig)
+                    bulk_g2s(base + A.cap_rec + A.cap_seq, reinterpret_cast<const unsigned char *>(A.cigar) + t0.cig_off, b_cig,
+                             &full[stage]);
+                if (b_mp)
+                    bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_cig, reinterpret_cast<const unsigned char *>(A.mp) + t0.mp_off,
+                             b_mp, &full[stage]);
+            }
+        }
+    } else {
+        // ---------------- consumers ----------------
+        uint32_t it = 0;
+        for (uint64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, it++) {
+            const uint32_t stage = it % A.n_stages, phase = (it / A.n_stages) & 1u;
+            mbar_wait(&full[stage], phase);
+            const unsigned char *base = stages + (size_t)stage * stage_bytes;
+            const uint32_t *recs = reinterpret_cast<const uint32_t *>(base);
+            const uint32_t *rw = recs + 5u * tid;
+            const int32_t pos = (int32_t)rw[0];
+            const uint32_t rmf = rw[1];
+            const float xi = __uint_as_float(rw[2]);
+            const uint32_t lseq = rw[3] & 0xFFFFu, ncig = rw[3] >> 16;
+            const uint32_t nm = rw[4] & 0xFFFFu, nmp = A.mp ? (rw[4] >> 16) : 0u;
+
+            // row offsets: sizes of the records of the warps before this one, then a warp scan
+            uint32_t bx = 0, bq = 0, bm = 0;   // seq words | ncig << 16, qual bytes, mp entries
+            for (uint32_t j = lane; j < 32u * warp; j += 32u) {
+                const uint32_t w3 = recs[5u * j + 3u];
+                bx += (((w3 & 0xFFFFu) + 7u) >> 3) | (w3 & 0xFFFF0000u);
+                bq += w3 & 0xFFFFu;
+                if (A.mp) bm += recs[5u * j + 4u] >> 16;
+            }
+            bx = __reduce_add_sync(0xFFFFFFFFu, bx);
+            bq = __reduce_add_sync(0xFFFFFFFFu, bq);
+            if (A.mp) bm = __reduce_add_sync(0xFFFFFFFFu, bm);
+            const uint32_t x = ((lseq + 7u) >> 3) | (ncig << 16);
+            uint32_t xs = x, qs = lseq, ms = nmp;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t tx = __shfl_up_sync(0xFFFFFFFFu, xs, d);
-            const unsigned long long ty = __shfl_up_sync(0xFFFFFFFFu, ys, d);
-            if (lane >= (uint32_t)d) {
-                xs += tx;
-                ys += ty;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t tx = __shfl_up_sync(0xFFFFFFFFu, xs, d);
+                const uint32_t tq = __shfl_up_sync(0xFFFFFFFFu, qs, d);
+                const uint32_t tm = A.mp ? __shfl_up_sync(0xFFFFFFFFu, ms, d) : 0u;
+                if (lane >= (uint32_t)d) {
+                    xs += tx;
+                    qs += tq;
+                    ms += tm;
+                }
             }
-        }
-        if (lane == 31) {
-            s_wx[warp] = xs;
-            s_wy[warp] = ys;
-        }
-        __syncthreads();
-        uint32_t xb = 0;
-        unsigned long long yb = 0;
-        for (uint32_t w = 0; w < warp; w++) {
-            xb += s_wx[w];
-            yb += s_wy[w];
-        }
-        xs = xs - x + xb;
-        ys = ys - y + yb;
+            xs = xs - x + bx;
+            qs = qs - lseq + bq;
+            ms = ms - nmp + bm;
 
-        const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu, ref = rmf & 0xFFFFu;
-        bool go = !(flags & SD_F_PAD);
-        if (go && A.filter_on) {
-            const bool primary = !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
-            const bool unmapped = (flags & SD_F_UNMAPPED) != 0;
-            if (primary) atomicAdd(&s_stats[unmapped ? SD_S_UNMAPPED : SD_S_MAPPED], 1u);
-            if (unmapped) go = false;
-            else if ((int)mapq < A.filter_mq) { atomicAdd(&s_stats[SD_S_MQFILTERED], 1u); go = false; }
-            else if ((double)xi < A.filter_min_identity) { atomicAdd(&s_stats[SD_S_IDFILTERED], 1u); go = false; }
-            else if (A.filter_max_nm > -1 && (int)nm > A.filter_max_nm) { atomicAdd(&s_stats[SD_S_NMFILTERED], 1u); go = false; }
-            else if (primary) atomicAdd(&s_stats[SD_S_FILTERED], 1u);
-        }
-        if (flags & (SD_F_UNMAPPED | SD_F_SKIP)) go = false;
-        if (ref >= A.n_chrom) go = false;
-
-        int tc = 0;
-        if (go) {
-            const uint32_t clen = __ldg(&A.chrom_len[ref]);
-            if (pos < 0 || (uint32_t)pos >= clen) go = false;
-            else {
-                ReadView v;
-                v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (xs & 0xFFFFu);
-                v.qual = base + A.cap_rec + A.cap_seq + (uint32_t)(ys & 0xFFFFFFFFull);
-                v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_qual) + (xs >> 16);
-                v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_qual + A.cap_cig) +
-                                  (uint32_t)(ys >> 32)
-                            : nullptr;
-                v.lseq = lseq;
-                v.ncig = ncig;
-                v.nmp = nmp;
-                v.g = __ldg(&A.chrom_off[ref]) + (uint32_t)pos;
-                v.strand = (flags & SD_F_REVERSE) ? 1 : 0;
-                v.has_mp = (flags & SD_F_HAS_MP) != 0;
-                uint32_t reflen = 0;
-                for (uint32_t i = 0; i < ncig; i++) {
-                    const uint32_t c = v.cig[i];
-                    if (cigar_consumes_ref(c & 15u)) reflen += c >> 4;
-                }
-                if (reflen == 0) reflen = 1;  // htslib bam_endpos
-                if ((uint64_t)pos + reflen > clen) reflen = clen - (uint32_t)pos;
-                v.span = (int)reflen;
-                bool fits = !A.force_slow && reflen <= 32u * W && lseq <= 32u * W;
-                if (fits && A.mismatch_source == SD_MISMATCH_MP && v.mp) {
-                    for (uint32_t i = 0; i < nmp; i++)
-                        if ((v.mp[i] >> 16) >= 32u * W) fits = false;
-                }
-                my_counted++;
-                if (fits) {
-                    bool bad = false;
-                    tc = fast_read<W>(A, v, mapq, s_scratch + (size_t)tid * (W + 1), bad);
-                    my_disagree += bad ? 1u : 0u;
-                } else {
-                    my_slow++;
-                    tc = slow_read(A, v, mapq);
-                }
-                my_tc_total += (unsigned long long)tc;
+            const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu, ref = rmf & 0xFFFFu;
+            bool go = !(flags & SD_F_PAD);
+            if (go && A.filter_on) {
+                const bool primary = !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
+                const bool unmapped = (flags & SD_F_UNMAPPED) != 0;
+                if (primary) atomicAdd(&s_stats[unmapped ? SD_S_UNMAPPED : SD_S_MAPPED], 1u);
+                if (unmapped) go = false;
+                else if ((int)mapq < A.filter_mq) { atomicAdd(&s_stats[SD_S_MQFILTERED], 1u); go = false; }
+                else if ((double)xi < A.filter_min_identity) { atomicAdd(&s_stats[SD_S_IDFILTERED], 1u); go = false; }
+                else if (A.filter_max_nm > -1 && (int)nm > A.filter_max_nm) { atomicAdd(&s_stats[SD_S_NMFILTERED], 1u); go = false; }
+                else if (primary) atomicAdd(&s_stats[SD_S_FILTERED], 1u);
             }
-        }
-        if (A.read_tc) A.read_tc[tile * A.tile_reads + tid] = (uint8_t)(tc > 255 ? 255 : tc);
+            if (flags & (SD_F_UNMAPPED | SD_F_SKIP)) go = false;
+            if (ref >= A.n_chrom) go = false;
 
-        __syncthreads();  // every thread is done with this stage
-        if (tid == 0) {
-            const uint64_t next = tile + (uint64_t)A.n_stages * gridDim.x;
-            if (next < A.n_tiles) issue((uint32_t)next, stage);
-        }
-        if (++stage == A.n_stages) {
-            stage = 0;
-            phase ^= 1u;
+            int tc = 0;
+            if (go) {
+                const uint32_t clen = __ldg(&A.chrom_len[ref]);
+                if (pos >= 0 && (uint32_t)pos < clen) {
+                    ReadView v;
+                    v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (xs & 0xFFFFu);
+                    v.qual = A.qual + A.tiles[tile].qual_off + qs;
+                    v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + (xs >> 16);
+                    v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
+                    v.lseq = lseq;
+                    v.ncig = ncig;
+                    v.nmp = nmp;
+                    v.g = __ldg(&A.chrom_off[ref]) + (uint32_t)pos;
+                    v.strand = (flags & SD_F_REVERSE) ? 1 : 0;
+                    v.has_mp = (flags & SD_F_HAS_MP) != 0;
+                    Blocks B;
+                    uint32_t reflen = (uint32_t)parse_cigar(v.cig, ncig, B);
+                    if (reflen == 0) reflen = 1;  // htslib bam_endpos
+                    if ((uint64_t)pos + reflen > clen) reflen = clen - (uint32_t)pos;
+                    v.span = (int)reflen;
+                    bool fits = !A.force_slow && reflen <= 32u * W && lseq <= 32u * W;
+                    if (fits && A.mismatch_source == SD_MISMATCH_MP && v.mp) {
+                        for (uint32_t i = 0; i < nmp; i++)
+                            if ((v.mp[i] >> 16) >= 32u * W) fits = false;
+                    }
+                    my_counted++;
+                    if (fits) {
+                        bool bad = false;
+                        tc = fast_read<W>(A, v, B, mapq, s_scratch + (size_t)tid * (W + 1), bad);
+                        my_disagree += bad ? 1u : 0u;
+                    } else {
+                        my_slow++;
+                        tc = slow_read(A, v, mapq);
+                    }
+                    my_tc_total += (unsigned long long)tc;
+                }
+            }
+            if (A.read_tc) A.read_tc[tile * A.tile_reads + tid] = (uint8_t)(tc > 255 ? 255 : tc);
+
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage
         }
     }
 
@@ -667,7 +753,6 @@ __global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ C
     }
     __syncthreads();
     if (tid < 6 && s_stats[tid]) atomicAdd(&A.stats[tid], (unsigned long long)s_stats[tid]);
-    (void)nwarps;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1000,24 +1085,38 @@ static inline uint32_t align128(uint32_t x) { return (x + 127u) & ~127u; }
 
 template <int W>
 static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
-    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_qual + A.cap_cig + A.cap_mp;
-    const uint32_t tail = 256 + A.tile_reads * (W + 1) * 4;
+    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
+    const uint32_t tail = 192 + A.tile_reads * (W + 1) * 4;
+    const int threads = (int)A.tile_reads + 32;   // consumer warps + the producer warp
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    // stages: as many as fit with two CTAs per SM (>= 2), at most 4
-    uint32_t n_stages = 4;
-    while (n_stages > 2 && (size_t)n_stages * stage_bytes + tail > (size_t)(max_smem / 2 - 1024)) n_stages--;
-    if ((size_t)n_stages * stage_bytes + tail > (size_t)max_smem)
+    if ((size_t)2 * stage_bytes + tail > (size_t)max_smem)
         return sd_fail(ctx, SD_ERR_LIMIT, "tile needs %u bytes of shared memory per stage; use a smaller tile_reads", stage_bytes);
+    // stage count: 3 when that still leaves >= 4 resident CTAs per SM, else 2 (SD_STAGES overrides, for tuning)
+    static int forced_stages = -1;
+    if (forced_stages < 0) {
+        const char *e = getenv("SD_STAGES");
+        forced_stages = e ? atoi(e) : 0;
+    }
+    auto resident = [&](uint32_t ns) {
+        const size_t smem = (size_t)ns * stage_bytes + tail;
+        if (smem > (size_t)max_smem) return 0;
+        if (cudaFuncSetAttribute(sd_count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W>, threads, smem) != cudaSuccess) return 0;
+        return per_sm;
+    };
+    uint32_t n_stages = 2;
+    if (forced_stages >= 2 && forced_stages <= 8 && resident((uint32_t)forced_stages) > 0) n_stages = (uint32_t)forced_stages;
+    else if (resident(3) >= 4) n_stages = 3;
+    cudaGetLastError();
     A.n_stages = n_stages;
     const size_t smem = (size_t)n_stages * stage_bytes + tail;
-    SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W>, (int)A.tile_reads, smem));
+    const int per_sm = resident(n_stages);
     if (per_sm < 1) return sd_fail(ctx, SD_ERR_LIMIT, "count kernel does not fit on an SM (smem %zu)", smem);
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)A.n_tiles, (uint64_t)ctx->num_sms * per_sm);
     if (timed) SD_CUDA(ctx, cudaEventRecord(ctx->ev_k0, stream));
-    sd_count_kernel<W><<<grid, A.tile_reads, smem, stream>>>(A);
+    sd_count_kernel<W><<<grid, threads, smem, stream>>>(A);
     if (timed) {
         SD_CUDA(ctx, cudaEventRecord(ctx->ev_k1, stream));
         ctx->have_kernel_time = true;
@@ -1040,7 +1139,7 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     A.tiles = b->tiles; A.n_tiles = b->n_tiles; A.tile_reads = b->tile_reads;
     A.cap_rec = align128(b->tile_reads * (uint32_t)sizeof(sd_read_rec));
     A.cap_seq = align128(b->max_tile_seq);
-    A.cap_qual = align128(b->max_tile_qual);
+    A.cap_qual = 0;  // the qual column is read in place (see the kernel's header comment)
     A.cap_cig = align128(b->max_tile_cig);
     A.cap_mp = A.mp ? align128(b->max_tile_mp) : 0;
     for (int s = 0; s < 2; s++) {

@@ -143,11 +143,19 @@ struct CountEm {
 __global__ void synth_plan_kernel(sd_synth_params P, sd_synth_tables T, uint32_t *counts) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_reads) return;
-    Rng rng(P.seed, P.first_read + i);
+    Rng rng(P.seed, P.first_read + (P.order ? (uint64_t)P.order[i] : i));
     const Plan pl = make_plan(rng, P, T);
     CountEm em{pl.strand ? 2u : 16u, 0u, 0u};
     simulate(rng, P, T, pl, em);
     counts[i] = pl.ncig | (em.nmp << 16);
+}
+
+__global__ void synth_positions_kernel(sd_synth_params P, sd_synth_tables T, uint32_t *gpos) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_reads) return;
+    Rng rng(P.seed, P.first_read + i);
+    const Plan pl = make_plan(rng, P, T);
+    gpos[i] = T.chrom_off[pl.chrom] + pl.pos;
 }
 
 // per tile: padded byte sizes of the four columns
@@ -242,7 +250,7 @@ __global__ void synth_fill_kernel(sd_synth_params P, sd_synth_tables T, const ui
     em.mp = mp ? mp + t.mp_off / 4 + mp_before : nullptr;
     em.triples = triples ? triples + i * (1 + 3 * SD_SYNTH_MAX_TRIPLES) : nullptr;
     for (uint32_t w = 0; w < words; w++) em.seq[w] = 0u;
-    Rng rng(P.seed, P.first_read + i);
+    Rng rng(P.seed, P.first_read + (P.order ? (uint64_t)P.order[i] : i));
     const Plan pl = make_plan(rng, P, T);
     em.want = pl.strand ? 2u : 16u;
     em.nmp = 0;
@@ -296,6 +304,17 @@ __global__ void synth_genome_pad_kernel(uint32_t *nm, uint64_t n_words, const ui
 }
 
 }  // namespace
+
+extern "C" int sd_synth_positions(sd_ctx *ctx, const sd_synth_params *p, const sd_synth_tables *t, uint32_t *d_gpos) {
+    if (!ctx || !p || !t || !d_gpos) return sd_fail(ctx, SD_ERR_ARG, "sd_synth_positions: null argument");
+    if (t->n_utr == 0 || p->utr_first >= t->n_utr || p->utr_first + p->utr_count > t->n_utr) return sd_fail(ctx, SD_ERR_ARG, "bad UTR range");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    synth_positions_kernel<<<(unsigned)((p->n_reads + 255) / 256), 256, 0, ctx->stream>>>(*p, *t, d_gpos);
+    ctx->launches++;
+    SD_CUDA(ctx, cudaGetLastError());
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
 
 extern "C" int sd_synth_plan(sd_ctx *ctx, const sd_synth_params *p, const sd_synth_tables *t, uint32_t *d_counts,
                              sd_tile *d_tiles, uint64_t h_totals[4]) {

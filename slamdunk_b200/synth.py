@@ -148,12 +148,26 @@ class SynthWorkload(object):
         p.utr_first, p.utr_count = int(utr_first), int(utr_count)
         return p
 
-    def generate(self, p: L.SynthParams, want_mp=False, want_triples=False):
-        """-> (DeviceBatch, triples tensor or None)"""
+    def generate(self, p: L.SynthParams, want_mp=False, want_triples=False, coordinate_sorted=False):
+        """-> (DeviceBatch, triples tensor or None).  coordinate_sorted: order the batch by alignment
+        start like the sorted BAM `slamdunk count` reads (triples follow the batch order)."""
         eng, dev = self.eng, self.eng.device
         n = int(p.n_reads)
         T = int(p.tile_reads)
         n_tiles = (n + T - 1) // T
+        order = None
+        if coordinate_sorted:
+            with torch.cuda.stream(eng.stream):
+                gpos = torch.empty(n, dtype=torch.int32, device=dev)
+            eng.stream.synchronize()
+            p.order = None
+            eng._chk(self.lib.sd_synth_positions(eng.ctx, ctypes.byref(p), ctypes.byref(self.tables), gpos.data_ptr()),
+                     "sd_synth_positions")
+            with torch.cuda.stream(eng.stream):
+                order = torch.argsort(gpos.to(torch.int64) & 0xFFFFFFFF, stable=True).to(torch.int32)
+                del gpos
+            eng.stream.synchronize()
+            p.order = order.data_ptr()
         with torch.cuda.stream(eng.stream):
             counts = torch.empty(n, dtype=torch.int32, device=dev)
             tiles = torch.empty((n_tiles + 1) * 4, dtype=torch.int64, device=dev)
@@ -178,6 +192,8 @@ class SynthWorkload(object):
         b.tiles = tiles.data_ptr()
         eng._chk(self.lib.sd_synth_fill(eng.ctx, ctypes.byref(p), ctypes.byref(self.tables), counts.data_ptr(),
                                         ctypes.byref(b), triples.data_ptr() if want_triples else None), "sd_synth_fill")
+        p.order = None
+        del order
         return DeviceBatch(b, tens), triples
 
 
