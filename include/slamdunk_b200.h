@@ -95,7 +95,7 @@ typedef struct sd_tile {
 typedef struct sd_batch {
     uint64_t n_reads;       /* real records (<= n_tiles * tile_reads) */
     uint32_t n_tiles;
-    uint32_t tile_reads;    /* records per tile: 64, 128 or 256; rec[] is padded with SD_F_PAD */
+    uint32_t tile_reads;    /* records per tile: 32 (one tile per warp); rec[] is padded with SD_F_PAD */
     const sd_read_rec *rec; /* [n_tiles * tile_reads] */
     const uint32_t *seq;
     const uint8_t *qual;
@@ -255,8 +255,8 @@ typedef struct sd_hbatch {
 } sd_hbatch;
 
 /* fasta_names / n_fasta: chromosome table of the FASTA (index = sd_read_rec ref field).
- * want_mp: also decode MP tags into the mp column.  tile_reads: 64, 128, 256 or 0 = the largest
- * that keeps a tile's shared-memory stage small.  threads <= 0: hardware concurrency. */
+ * want_mp: also decode MP tags into the mp column.  tile_reads: 32 (0 = default).
+ * threads <= 0: hardware concurrency. */
 int sd_decode_bam(const char *path, const char *const *fasta_names, uint32_t n_fasta, int want_mp,
                   uint32_t tile_reads, int threads, sd_hbatch **out, char *err, int errlen);
 void sd_hbatch_free(sd_hbatch *hb);

@@ -48,16 +48,17 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Blocks in hardware (try_wait with a suspend-time hint) instead of spinning on issue slots.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok = 0;
     const uint32_t addr = smem_u32(bar);
     while (!ok) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(200000u)
             : "memory");
     }
 }
@@ -489,10 +490,36 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
     } else {
 #pragma unroll
         for (int k = 0; k < W; k++) H[k] = v.has_mp ? (R[k] & T[k] & ~S[k]) : 0u;
-        // base quality only where a candidate survived: one byte from the qual column per candidate
+        // Base quality only where a candidate survived: one byte of the qual column per candidate.
+        // The two lowest candidates of every window word are fetched together (independent global
+        // loads in flight), the rare rest one at a time.
+        int cb0[W], cb1[W];
+        uint32_t cq0[W], cq1[W], crest[W];
 #pragma unroll
         for (int k = 0; k < W; k++) {
-            uint32_t rest = H[k];
+            uint32_t h = H[k];
+            cb0[k] = __ffs(h) - 1;
+            h &= h - 1u;
+            cb1[k] = __ffs(h) - 1;
+            h &= h - 1u;
+            crest[k] = h;
+            cq0[k] = cq1[k] = 255u;
+            if (cb0[k] >= 0) {
+                const int o = 32 * k + cb0[k];
+                const int qi = regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o);
+                cq0[k] = (qi < 0 || qi >= (int)v.lseq) ? 0u : (uint32_t)__ldg(v.qual + qi);
+            }
+            if (cb1[k] >= 0) {
+                const int o = 32 * k + cb1[k];
+                const int qi = regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o);
+                cq1[k] = (qi < 0 || qi >= (int)v.lseq) ? 0u : (uint32_t)__ldg(v.qual + qi);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            if (cb0[k] >= 0 && (int)cq0[k] < A.min_qual) H[k] &= ~(1u << cb0[k]);
+            if (cb1[k] >= 0 && (int)cq1[k] < A.min_qual) H[k] &= ~(1u << cb1[k]);
+            uint32_t rest = crest[k];
             while (rest) {
                 const int bit = __ffs(rest) - 1;
                 rest &= rest - 1u;
@@ -571,172 +598,158 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 // ---------------------------------------------------------------------------------------
 // The persistent streaming kernel.
 //
-// One CTA = NW consumer warps (one read per thread, a tile = 32 * NW reads) + one producer warp.
-// The producer's elected lane keeps a ring of shared-memory stages filled with TMA bulk copies
-// (records, sliced SEQ, CIGAR ops and, when needed, MP entries of one tile per stage).  Consumer
-// warps never synchronize with each other: each waits on the stage's "full" mbarrier, derives its
-// rows' offsets from the records of the warps before it, works, and arrives on the stage's "empty"
-// mbarrier.  The QUAL column is not staged: a base quality is needed only where the read shows a
-// C over a reference T (about one base per read), so it is fetched from global memory right
-// there -- this keeps the shared-memory footprint per warp small enough for high occupancy and
-// leaves most of the qual column's DRAM sectors untouched.
+// A tile is 32 consecutive reads = one warp's worth; a warp is a self-contained stream processor.
+// Each warp owns a small ring of shared-memory stages and its own mbarriers: its elected lane
+// issues the TMA bulk copies (records, sliced SEQ, CIGAR ops and, when needed, MP entries of one
+// tile per stage) two tiles ahead, all lanes wait on the stage's mbarrier, each lane handles one
+// read, and the lane re-arms the stage.  No warp ever waits for another warp, there is no block
+// barrier in the loop and no producer thread spinning.  The QUAL column is not staged: a base
+// quality is needed only where the read shows a C over a reference T (about one base per read),
+// so it is fetched from global memory right there -- this keeps the shared-memory footprint per
+// warp small enough for high occupancy and leaves most of the qual column's DRAM sectors untouched.
 // ---------------------------------------------------------------------------------------
 #define SD_SMEM_STATS 8
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
+#define SD_TILE_READS 32
 
 template <int W>
-__global__ void __launch_bounds__(288) sd_count_kernel(const __grid_constant__ CountArgs A) {
+__global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ CountArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
-    unsigned char *stages = smem;
-    unsigned char *tail = smem + (size_t)A.n_stages * stage_bytes;
-    uint64_t *full = reinterpret_cast<uint64_t *>(tail);                   // [n_stages]
-    uint64_t *empty = reinterpret_cast<uint64_t *>(tail + 64);             // [n_stages]
-    uint32_t *s_stats = reinterpret_cast<uint32_t *>(tail + 128);          // [SD_SMEM_STATS]
-    uint32_t *s_scratch = reinterpret_cast<uint32_t *>(tail + 192);        // [tile_reads * (W + 1)]
-
+    const uint32_t warp_bytes = A.n_stages * stage_bytes + 128u + 32u * (W + 1) * 4u;   // stages | barriers | scratch
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t NW = A.tile_reads >> 5;   // consumer warps; warp NW is the producer
+    const uint32_t nwarp = blockDim.x >> 5;
+    uint32_t *s_stats = reinterpret_cast<uint32_t *>(smem);                 // [SD_SMEM_STATS], first 128 bytes
+    unsigned char *mine = smem + 128u + (size_t)warp * warp_bytes;
+    unsigned char *stages = mine;
+    uint64_t *full = reinterpret_cast<uint64_t *>(mine + (size_t)A.n_stages * stage_bytes);   // [n_stages]
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(mine + (size_t)A.n_stages * stage_bytes + 128u) + lane * (W + 1);
 
-    if (tid == 0) {
-        for (uint32_t s = 0; s < A.n_stages; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], NW);
-        }
+    if (tid < SD_SMEM_STATS) s_stats[tid] = 0u;
+    if (lane == 0) {
+        for (uint32_t s = 0; s < A.n_stages; s++) mbar_init(&full[s], 1);
         mbar_fence_init();
     }
-    if (tid < SD_SMEM_STATS) s_stats[tid] = 0u;
     __syncthreads();
+
+    const uint64_t gw = (uint64_t)blockIdx.x * nwarp + warp, total_warps = (uint64_t)gridDim.x * nwarp;
+
+    auto issue = [&](uint64_t tile, uint32_t stage) {
+        unsigned char *base = stages + (size_t)stage * stage_bytes;
+        const sd_tile t0 = A.tiles[tile], t1 = A.tiles[tile + 1];
+        const uint32_t b_rec = SD_TILE_READS * (uint32_t)sizeof(sd_read_rec);
+        const uint32_t b_seq = (uint32_t)(t1.seq_off - t0.seq_off);
+        const uint32_t b_cig = (uint32_t)(t1.cig_off - t0.cig_off);
+        const uint32_t b_mp = A.mp ? (uint32_t)(t1.mp_off - t0.mp_off) : 0u;
+        mbar_arrive_expect_tx(&full[stage], b_rec + b_seq + b_cig + b_mp);
+        bulk_g2s(base, reinterpret_cast<const unsigned char *>(A.rec) + tile * b_rec, b_rec, &full[stage]);
+        if (b_seq) bulk_g2s(base + A.cap_rec, reinterpret_cast<const unsigned char *>(A.seq) + t0.seq_off, b_seq, &full[stage]);
+        if (b_cig)
+            bulk_g2s(base + A.cap_rec + A.cap_seq, reinterpret_cast<const unsigned char *>(A.cigar) + t0.cig_off, b_cig, &full[stage]);
+        if (b_mp)
+            bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_cig, reinterpret_cast<const unsigned char *>(A.mp) + t0.mp_off, b_mp,
+                     &full[stage]);
+    };
+
+    if (lane == 0) {
+        for (uint32_t s = 0; s < A.n_stages; s++) {
+            const uint64_t t = gw + (uint64_t)s * total_warps;
+            if (t < A.n_tiles) issue(t, s);
+        }
+    }
 
     uint32_t my_counted = 0, my_slow = 0, my_disagree = 0;
     unsigned long long my_tc_total = 0;
+    uint32_t stage = 0, phase = 0;
+    for (uint64_t tile = gw; tile < A.n_tiles; tile += total_warps) {
+        mbar_wait(&full[stage], phase);
+        const unsigned char *base = stages + (size_t)stage * stage_bytes;
+        const uint32_t *rw = reinterpret_cast<const uint32_t *>(base) + 5u * lane;
+        const int32_t pos = (int32_t)rw[0];
+        const uint32_t rmf = rw[1];
+        const float xi = __uint_as_float(rw[2]);
+        const uint32_t lseq = rw[3] & 0xFFFFu, ncig = rw[3] >> 16;
+        const uint32_t nm = rw[4] & 0xFFFFu, nmp = A.mp ? (rw[4] >> 16) : 0u;
 
-    if (warp == NW) {
-        // ---------------- producer ----------------
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (uint64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, it++) {
-                const uint32_t stage = it % A.n_stages, use = it / A.n_stages;
-                if (use > 0) mbar_wait(&empty[stage], (use - 1u) & 1u);
-                unsigned char *base = stages + (size_t)stage * stage_bytes;
-                const sd_tile t0 = A.tiles[tile], t1 = A.tiles[tile + 1];
-                const uint32_t b_rec = A.tile_reads * (uint32_t)sizeof(sd_read_rec);
-                const uint32_t b_seq = (uint32_t)(t1.seq_off - t0.seq_off);
-                const uint32_t b_cig = (uint32_t)(t1.cig_off - t0.cig_off);
-                const uint32_t b_mp = A.mp ? (uint32_t)(t1.mp_off - t0.mp_off) : 0u;
-                mbar_arrive_expect_tx(&full[stage], b_rec + b_seq + b_cig + b_mp);
-                bulk_g2s(base, reinterpret_cast<const unsigned char *>(A.rec) + (size_t)tile * b_rec, b_rec, &full[stage]);
-                if (b_seq) bulk_g2s(base + A.cap_rec, reinterpret_cast<const unsigned char *>(A.seq) + t0.seq_off, b_seq, &full[stage]);
-                if (b_cig)
-                    bulk_g2s(base + A.cap_rec + A.cap_seq, reinterpret_cast<const unsigned char *>(A.cigar) + t0.cig_off, b_cig,
-                             &full[stage]);
-                if (b_mp)
-                    bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_cig, reinterpret_cast<const unsigned char *>(A.mp) + t0.mp_off,
-                             b_mp, &full[stage]);
+        // row offsets inside the tile: exclusive warp scan of the row sizes
+        const uint32_t x = ((lseq + 7u) >> 3) | (ncig << 16);   // seq words | ncig << 16
+        uint32_t xs = x, qs = lseq, ms = nmp;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t tx = __shfl_up_sync(0xFFFFFFFFu, xs, d);
+            const uint32_t tq = __shfl_up_sync(0xFFFFFFFFu, qs, d);
+            const uint32_t tm = A.mp ? __shfl_up_sync(0xFFFFFFFFu, ms, d) : 0u;
+            if (lane >= (uint32_t)d) {
+                xs += tx;
+                qs += tq;
+                ms += tm;
             }
         }
-    } else {
-        // ---------------- consumers ----------------
-        uint32_t it = 0;
-        for (uint64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, it++) {
-            const uint32_t stage = it % A.n_stages, phase = (it / A.n_stages) & 1u;
-            mbar_wait(&full[stage], phase);
-            const unsigned char *base = stages + (size_t)stage * stage_bytes;
-            const uint32_t *recs = reinterpret_cast<const uint32_t *>(base);
-            const uint32_t *rw = recs + 5u * tid;
-            const int32_t pos = (int32_t)rw[0];
-            const uint32_t rmf = rw[1];
-            const float xi = __uint_as_float(rw[2]);
-            const uint32_t lseq = rw[3] & 0xFFFFu, ncig = rw[3] >> 16;
-            const uint32_t nm = rw[4] & 0xFFFFu, nmp = A.mp ? (rw[4] >> 16) : 0u;
+        xs -= x;
+        qs -= lseq;
+        ms -= nmp;
 
-            // row offsets: sizes of the records of the warps before this one, then a warp scan
-            uint32_t bx = 0, bq = 0, bm = 0;   // seq words | ncig << 16, qual bytes, mp entries
-            for (uint32_t j = lane; j < 32u * warp; j += 32u) {
-                const uint32_t w3 = recs[5u * j + 3u];
-                bx += (((w3 & 0xFFFFu) + 7u) >> 3) | (w3 & 0xFFFF0000u);
-                bq += w3 & 0xFFFFu;
-                if (A.mp) bm += recs[5u * j + 4u] >> 16;
-            }
-            bx = __reduce_add_sync(0xFFFFFFFFu, bx);
-            bq = __reduce_add_sync(0xFFFFFFFFu, bq);
-            if (A.mp) bm = __reduce_add_sync(0xFFFFFFFFu, bm);
-            const uint32_t x = ((lseq + 7u) >> 3) | (ncig << 16);
-            uint32_t xs = x, qs = lseq, ms = nmp;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t tx = __shfl_up_sync(0xFFFFFFFFu, xs, d);
-                const uint32_t tq = __shfl_up_sync(0xFFFFFFFFu, qs, d);
-                const uint32_t tm = A.mp ? __shfl_up_sync(0xFFFFFFFFu, ms, d) : 0u;
-                if (lane >= (uint32_t)d) {
-                    xs += tx;
-                    qs += tq;
-                    ms += tm;
+        const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu, ref = rmf & 0xFFFFu;
+        bool go = !(flags & SD_F_PAD);
+        if (go && A.filter_on) {
+            const bool primary = !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
+            const bool unmapped = (flags & SD_F_UNMAPPED) != 0;
+            if (primary) atomicAdd(&s_stats[unmapped ? SD_S_UNMAPPED : SD_S_MAPPED], 1u);
+            if (unmapped) go = false;
+            else if ((int)mapq < A.filter_mq) { atomicAdd(&s_stats[SD_S_MQFILTERED], 1u); go = false; }
+            else if ((double)xi < A.filter_min_identity) { atomicAdd(&s_stats[SD_S_IDFILTERED], 1u); go = false; }
+            else if (A.filter_max_nm > -1 && (int)nm > A.filter_max_nm) { atomicAdd(&s_stats[SD_S_NMFILTERED], 1u); go = false; }
+            else if (primary) atomicAdd(&s_stats[SD_S_FILTERED], 1u);
+        }
+        if (flags & (SD_F_UNMAPPED | SD_F_SKIP)) go = false;
+        if (ref >= A.n_chrom) go = false;
+
+        int tc = 0;
+        if (go) {
+            const uint32_t clen = __ldg(&A.chrom_len[ref]);
+            if (pos >= 0 && (uint32_t)pos < clen) {
+                ReadView v;
+                v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (xs & 0xFFFFu);
+                v.qual = A.qual + __ldg(&A.tiles[tile].qual_off) + qs;
+                v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + (xs >> 16);
+                v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
+                v.lseq = lseq;
+                v.ncig = ncig;
+                v.nmp = nmp;
+                v.g = __ldg(&A.chrom_off[ref]) + (uint32_t)pos;
+                v.strand = (flags & SD_F_REVERSE) ? 1 : 0;
+                v.has_mp = (flags & SD_F_HAS_MP) != 0;
+                Blocks B;
+                uint32_t reflen = (uint32_t)parse_cigar(v.cig, ncig, B);
+                if (reflen == 0) reflen = 1;  // htslib bam_endpos
+                if ((uint64_t)pos + reflen > clen) reflen = clen - (uint32_t)pos;
+                v.span = (int)reflen;
+                bool fits = !A.force_slow && reflen <= 32u * W && lseq <= 32u * W;
+                if (fits && A.mismatch_source == SD_MISMATCH_MP && v.mp) {
+                    for (uint32_t i = 0; i < nmp; i++)
+                        if ((v.mp[i] >> 16) >= 32u * W) fits = false;
                 }
-            }
-            xs = xs - x + bx;
-            qs = qs - lseq + bq;
-            ms = ms - nmp + bm;
-
-            const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu, ref = rmf & 0xFFFFu;
-            bool go = !(flags & SD_F_PAD);
-            if (go && A.filter_on) {
-                const bool primary = !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
-                const bool unmapped = (flags & SD_F_UNMAPPED) != 0;
-                if (primary) atomicAdd(&s_stats[unmapped ? SD_S_UNMAPPED : SD_S_MAPPED], 1u);
-                if (unmapped) go = false;
-                else if ((int)mapq < A.filter_mq) { atomicAdd(&s_stats[SD_S_MQFILTERED], 1u); go = false; }
-                else if ((double)xi < A.filter_min_identity) { atomicAdd(&s_stats[SD_S_IDFILTERED], 1u); go = false; }
-                else if (A.filter_max_nm > -1 && (int)nm > A.filter_max_nm) { atomicAdd(&s_stats[SD_S_NMFILTERED], 1u); go = false; }
-                else if (primary) atomicAdd(&s_stats[SD_S_FILTERED], 1u);
-            }
-            if (flags & (SD_F_UNMAPPED | SD_F_SKIP)) go = false;
-            if (ref >= A.n_chrom) go = false;
-
-            int tc = 0;
-            if (go) {
-                const uint32_t clen = __ldg(&A.chrom_len[ref]);
-                if (pos >= 0 && (uint32_t)pos < clen) {
-                    ReadView v;
-                    v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (xs & 0xFFFFu);
-                    v.qual = A.qual + A.tiles[tile].qual_off + qs;
-                    v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + (xs >> 16);
-                    v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
-                    v.lseq = lseq;
-                    v.ncig = ncig;
-                    v.nmp = nmp;
-                    v.g = __ldg(&A.chrom_off[ref]) + (uint32_t)pos;
-                    v.strand = (flags & SD_F_REVERSE) ? 1 : 0;
-                    v.has_mp = (flags & SD_F_HAS_MP) != 0;
-                    Blocks B;
-                    uint32_t reflen = (uint32_t)parse_cigar(v.cig, ncig, B);
-                    if (reflen == 0) reflen = 1;  // htslib bam_endpos
-                    if ((uint64_t)pos + reflen > clen) reflen = clen - (uint32_t)pos;
-                    v.span = (int)reflen;
-                    bool fits = !A.force_slow && reflen <= 32u * W && lseq <= 32u * W;
-                    if (fits && A.mismatch_source == SD_MISMATCH_MP && v.mp) {
-                        for (uint32_t i = 0; i < nmp; i++)
-                            if ((v.mp[i] >> 16) >= 32u * W) fits = false;
-                    }
-                    my_counted++;
-                    if (fits) {
-                        bool bad = false;
-                        tc = fast_read<W>(A, v, B, mapq, s_scratch + (size_t)tid * (W + 1), bad);
-                        my_disagree += bad ? 1u : 0u;
-                    } else {
-                        my_slow++;
-                        tc = slow_read(A, v, mapq);
-                    }
-                    my_tc_total += (unsigned long long)tc;
+                my_counted++;
+                if (fits) {
+                    bool bad = false;
+                    tc = fast_read<W>(A, v, B, mapq, scratch, bad);
+                    my_disagree += bad ? 1u : 0u;
+                } else {
+                    my_slow++;
+                    tc = slow_read(A, v, mapq);
                 }
+                my_tc_total += (unsigned long long)tc;
             }
-            if (A.read_tc) A.read_tc[tile * A.tile_reads + tid] = (uint8_t)(tc > 255 ? 255 : tc);
+        }
+        if (A.read_tc) A.read_tc[tile * SD_TILE_READS + lane] = (uint8_t)(tc > 255 ? 255 : tc);
 
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage
+        __syncwarp();   // every lane is done with this stage
+        if (lane == 0) {
+            const uint64_t next = tile + (uint64_t)A.n_stages * total_warps;
+            if (next < A.n_tiles) issue(next, stage);
+        }
+        if (++stage == A.n_stages) {
+            stage = 0;
+            phase ^= 1u;
         }
     }
 
@@ -1086,35 +1099,34 @@ static inline uint32_t align128(uint32_t x) { return (x + 127u) & ~127u; }
 template <int W>
 static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
     const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
-    const uint32_t tail = 192 + A.tile_reads * (W + 1) * 4;
-    const int threads = (int)A.tile_reads + 32;   // consumer warps + the producer warp
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    if ((size_t)2 * stage_bytes + tail > (size_t)max_smem)
-        return sd_fail(ctx, SD_ERR_LIMIT, "tile needs %u bytes of shared memory per stage; use a smaller tile_reads", stage_bytes);
-    // stage count: 3 when that still leaves >= 4 resident CTAs per SM, else 2 (SD_STAGES overrides, for tuning)
-    static int forced_stages = -1;
+    static int forced_stages = -1, forced_warps = -1;
     if (forced_stages < 0) {
         const char *e = getenv("SD_STAGES");
         forced_stages = e ? atoi(e) : 0;
+        e = getenv("SD_WARPS");
+        forced_warps = e ? atoi(e) : 0;
     }
-    auto resident = [&](uint32_t ns) {
-        const size_t smem = (size_t)ns * stage_bytes + tail;
-        if (smem > (size_t)max_smem) return 0;
-        if (cudaFuncSetAttribute(sd_count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W>, threads, smem) != cudaSuccess) return 0;
-        return per_sm;
-    };
-    uint32_t n_stages = 2;
-    if (forced_stages >= 2 && forced_stages <= 8 && resident((uint32_t)forced_stages) > 0) n_stages = (uint32_t)forced_stages;
-    else if (resident(3) >= 4) n_stages = 3;
-    cudaGetLastError();
+    // per-warp ring of n_stages tiles; as many warps per CTA (<= 8) as the shared memory allows
+    uint32_t n_stages = (forced_stages >= 1 && forced_stages <= 8) ? (uint32_t)forced_stages : 2u;
+    auto warp_bytes = [&](uint32_t ns) { return (size_t)ns * stage_bytes + 128u + 32u * (W + 1) * 4u; };
+    if (128u + warp_bytes(n_stages) > (size_t)max_smem) n_stages = 1;
+    if (128u + warp_bytes(n_stages) > (size_t)max_smem)
+        return sd_fail(ctx, SD_ERR_LIMIT, "a 32-read tile needs %u bytes of shared memory; reads are too long for this kernel", stage_bytes);
+    uint32_t warps = (forced_warps >= 1 && forced_warps <= 8) ? (uint32_t)forced_warps : 8u;
+    while (warps > 1 && 128u + warps * warp_bytes(n_stages) > (size_t)max_smem / 2) warps--;   // keep >= 2 CTAs per SM possible
+    while (warps > 1 && 128u + warps * warp_bytes(n_stages) > (size_t)max_smem) warps--;
     A.n_stages = n_stages;
-    const size_t smem = (size_t)n_stages * stage_bytes + tail;
-    const int per_sm = resident(n_stages);
+    const size_t smem = 128u + warps * warp_bytes(n_stages);
+    const int threads = (int)warps * 32;
+    SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W>, threads, smem));
     if (per_sm < 1) return sd_fail(ctx, SD_ERR_LIMIT, "count kernel does not fit on an SM (smem %zu)", smem);
-    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)A.n_tiles, (uint64_t)ctx->num_sms * per_sm);
+    const uint64_t want_ctas = ((uint64_t)A.n_tiles + warps - 1) / warps;
+    uint32_t grid = (uint32_t)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * per_sm);
+    if (grid == 0) grid = 1;
     if (timed) SD_CUDA(ctx, cudaEventRecord(ctx->ev_k0, stream));
     sd_count_kernel<W><<<grid, threads, smem, stream>>>(A);
     if (timed) {
@@ -1130,14 +1142,14 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     if (!ctx->refx[0]) return sd_fail(ctx, SD_ERR_STATE, "sd_count before sd_set_reference");
     if (!ctx->counters) return sd_fail(ctx, SD_ERR_STATE, "sd_count before sd_bind_outputs");
     if (b->n_tiles == 0) return SD_OK;
-    if (b->tile_reads != 64 && b->tile_reads != 128 && b->tile_reads != 256) return sd_fail(ctx, SD_ERR_ARG, "tile_reads must be 64, 128 or 256");
+    if (b->tile_reads != 32) return sd_fail(ctx, SD_ERR_ARG, "tile_reads must be 32 (one tile per warp)");
     if (p->mismatch_source != SD_MISMATCH_CIGAR && !b->mp) return sd_fail(ctx, SD_ERR_ARG, "mismatch source needs the mp column");
     CountArgs A;
     memset(&A, 0, sizeof A);
     A.rec = b->rec; A.seq = b->seq; A.qual = b->qual; A.cigar = b->cigar;
     A.mp = (p->mismatch_source == SD_MISMATCH_CIGAR) ? nullptr : b->mp;
     A.tiles = b->tiles; A.n_tiles = b->n_tiles; A.tile_reads = b->tile_reads;
-    A.cap_rec = align128(b->tile_reads * (uint32_t)sizeof(sd_read_rec));
+    A.cap_rec = align128(32u * (uint32_t)sizeof(sd_read_rec));
     A.cap_seq = align128(b->max_tile_seq);
     A.cap_qual = 0;  // the qual column is read in place (see the kernel's header comment)
     A.cap_cig = align128(b->max_tile_cig);

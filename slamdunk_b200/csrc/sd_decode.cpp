@@ -228,10 +228,8 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
                              uint32_t tile_reads, int threads, sd_hbatch **out, char *err, int errlen) {
     if (!path || !out) return fail(err, errlen, SD_ERR_ARG, "sd_decode_bam: null argument");
     *out = nullptr;
-    if (tile_reads != 0 && tile_reads != 64 && tile_reads != 128 && tile_reads != 256)
-        return fail(err, errlen, SD_ERR_ARG, "tile_reads must be 0 (auto), 64, 128 or 256");
-    const bool auto_tile = (tile_reads == 0);
-    if (auto_tile) tile_reads = 256;
+    if (tile_reads != 0 && tile_reads != 32) return fail(err, errlen, SD_ERR_ARG, "tile_reads must be 32 (or 0 = default)");
+    tile_reads = 32;
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     const double t0 = now_s();
 
@@ -343,25 +341,6 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         p += 4 + (size_t)bs;
     }
     const size_t n = recoff.size();
-    if (auto_tile) {
-        // largest tile whose shared-memory stage (records + seq + qual + cigar [+ mp]) stays under ~48 KiB,
-        // so that several stages of two resident CTAs fit in an SM's 227 KiB
-        for (uint32_t cand : {256u, 128u, 64u}) {
-            tile_reads = cand;
-            uint64_t worst = 0;
-            for (size_t t0 = 0; t0 < n; t0 += cand) {
-                uint64_t b = (uint64_t)cand * sizeof(sd_read_rec);
-                const size_t e = std::min(n, t0 + cand);
-                for (size_t i = t0; i < e; i++) {
-                    const uint8_t *r = raw.data() + recoff[i];
-                    const uint64_t ls = (uint64_t)std::max(0, rdi32(r + 16));
-                    b += 4 * ((ls + 7) / 8) + ls + 4ull * rd16(r + 12) + (want_mp ? ls / 8 : 0);
-                }
-                worst = std::max(worst, b);
-            }
-            if (worst <= 48 * 1024) break;
-        }
-    }
     const size_t n_tiles = (n + tile_reads - 1) / tile_reads;
     if (n_tiles > 0xFFFFFFF0ull) return bail(SD_ERR_LIMIT, "too many records for one batch");
 

@@ -220,19 +220,23 @@ struct FillEm {
     }
 };
 
-// one block per tile, one thread per read
+// one warp per tile (32 reads), one thread per read
 __global__ void synth_fill_kernel(sd_synth_params P, sd_synth_tables T, const uint32_t *counts, const sd_tile *tiles,
                                   sd_read_rec *rec, uint32_t *seq, uint8_t *qual, uint32_t *cig, uint32_t *mp, int32_t *triples) {
-    typedef cub::BlockScan<uint32_t, 256> Scan;
-    __shared__ typename Scan::TempStorage tmp1, tmp2;
-    const uint32_t tile = blockIdx.x, k = threadIdx.x;
-    const uint64_t i = (uint64_t)tile * P.tile_reads + k;
-    const bool live = k < P.tile_reads && i < P.n_reads;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t tile = i >> 5;
+    const uint64_t n_pad = ((P.n_reads + 31ull) >> 5) << 5;
+    if (i >= n_pad) return;   // whole warps only: n_pad is a multiple of 32
+    const bool live = i < P.n_reads;
     const uint32_t c = live ? counts[i] : 0u;
-    uint32_t cig_before, mp_before;
-    Scan(tmp1).ExclusiveSum(c & 0xFFFFu, cig_before);
-    Scan(tmp2).ExclusiveSum(c >> 16, mp_before);
-    if (k >= P.tile_reads) return;
+    uint32_t cs = c & 0xFFFFu, ms = c >> 16;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t tc_ = __shfl_up_sync(0xFFFFFFFFu, cs, d), tm_ = __shfl_up_sync(0xFFFFFFFFu, ms, d);
+        if (lane >= (uint32_t)d) { cs += tc_; ms += tm_; }
+    }
+    const uint32_t cig_before = cs - (c & 0xFFFFu), mp_before = ms - (c >> 16);
     sd_read_rec &o = rec[i];
     if (!live) {
         o.pos = 0;
@@ -242,6 +246,7 @@ __global__ void synth_fill_kernel(sd_synth_params P, sd_synth_tables T, const ui
         o.nm_nmp = 0;
         return;
     }
+    const uint32_t k = lane;
     const sd_tile t = tiles[tile];
     const uint32_t words = (P.read_len + 7u) >> 3;
     FillEm em;
@@ -319,7 +324,7 @@ extern "C" int sd_synth_positions(sd_ctx *ctx, const sd_synth_params *p, const s
 extern "C" int sd_synth_plan(sd_ctx *ctx, const sd_synth_params *p, const sd_synth_tables *t, uint32_t *d_counts,
                              sd_tile *d_tiles, uint64_t h_totals[4]) {
     if (!ctx || !p || !t || !d_counts || !d_tiles || !h_totals) return sd_fail(ctx, SD_ERR_ARG, "sd_synth_plan: null argument");
-    if (p->tile_reads != 64 && p->tile_reads != 128 && p->tile_reads != 256) return sd_fail(ctx, SD_ERR_ARG, "tile_reads must be 64, 128 or 256");
+    if (p->tile_reads != 32) return sd_fail(ctx, SD_ERR_ARG, "tile_reads must be 32");
     if (p->read_len == 0 || p->read_len > 65535 || p->n_reads == 0) return sd_fail(ctx, SD_ERR_ARG, "bad read_len / n_reads");
     if (t->n_utr == 0 || p->utr_first >= t->n_utr || p->utr_first + p->utr_count > t->n_utr) return sd_fail(ctx, SD_ERR_ARG, "bad UTR range");
     SD_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -360,7 +365,7 @@ extern "C" int sd_synth_fill(sd_ctx *ctx, const sd_synth_params *p, const sd_syn
         return sd_fail(ctx, SD_ERR_ARG, "sd_synth_fill: null argument");
     SD_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t n_tiles = (uint32_t)((p->n_reads + p->tile_reads - 1) / p->tile_reads);
-    synth_fill_kernel<<<n_tiles, 256, 0, ctx->stream>>>(*p, *t, d_counts, out->tiles, const_cast<sd_read_rec *>(out->rec),
+    synth_fill_kernel<<<(unsigned)(((uint64_t)n_tiles * 32 + 255) / 256), 256, 0, ctx->stream>>>(*p, *t, d_counts, out->tiles, const_cast<sd_read_rec *>(out->rec),
                                                         const_cast<uint32_t *>(out->seq), const_cast<uint8_t *>(out->qual),
                                                         const_cast<uint32_t *>(out->cigar), const_cast<uint32_t *>(out->mp), d_triples);
     ctx->launches++;

@@ -136,7 +136,7 @@ class SynthWorkload(object):
         cuts[-1] = len(cum)
         return [(cuts[k], cuts[k + 1] - cuts[k]) for k in range(n_parts)]
 
-    def params(self, seed, first_read, n_reads, read_len=100, tile_reads=256, p_conv=0.025, p_err=0.002,
+    def params(self, seed, first_read, n_reads, read_len=100, tile_reads=32, p_conv=0.025, p_err=0.002,
                frac_softclip=0.05, frac_indel=0.02, frac_multimap=0.03, frac_antisense=0.02, frac_labelled=1.0,
                utr_first=0, utr_count=0) -> L.SynthParams:
         p = L.SynthParams()

@@ -61,7 +61,7 @@ def test_generator_is_index_keyed_and_shards_add_up():
     ref_cov = eng.pos_cov.clone()
     ref_tc = eng.pos_tc.clone()
     eng.reset_outputs()
-    for first, cnt in ((0, 25_600), (25_600, 40_192), (65_792, n - 65_792)):
+    for first, cnt in ((0, 25_600), (25_600, 40_192), (65_792, n - 65_792)):   # multiples of the tile size
         part, _ = wl.generate(wl.params(seed=3, first_read=first, n_reads=cnt))
         if first == 0:
             a = whole.tensors["rec"][:cnt * 20]
