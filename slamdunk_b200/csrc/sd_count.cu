@@ -89,6 +89,8 @@ struct CountArgs {
     const uint32_t *uend[2];
     const uint32_t *urow[2];
     const uint32_t *useg[2];
+    const uint4 *utab[2];   // {start, end, row, seg}
+    const uint4 *stab[2];   // {start, end, off_lo, off_hi}
     const uint32_t *bin_first[2];
     uint32_t n_u[2];
     uint32_t n_bins;
@@ -124,6 +126,13 @@ __device__ __forceinline__ uint32_t range_word(int k, int lo, int hi) {
     if (b <= a) return 0u;
     uint32_t m = (b == 32) ? 0xFFFFFFFFu : ((1u << b) - 1u);
     return m & ~((1u << a) - 1u);
+}
+
+// bits [0, hi) of the window restricted to word k
+__device__ __forceinline__ uint32_t prefix_word(int k, int hi) {
+    int b = hi - 32 * k;
+    b = b < 0 ? 0 : (b > 32 ? 32 : b);
+    return (uint32_t)((1ull << b) - 1ull);
 }
 
 // Warp-aggregated add into one UTR's counter row: lanes that hit the same row elect a leader.
@@ -320,18 +329,15 @@ __device__ __forceinline__ int parse_cigar(const uint32_t *cig, uint32_t ncig, B
     for (uint32_t i = 0; i < ncig; i++) {
         const uint32_t c = cig[i], op = c & 15u;
         const int len = (int)(c >> 4);
-        if (cigar_is_match(op)) {
+        // op classes as bit sets over MIDNSHP=X: match {M,=,X}, query-only {I,S}, reference-only {D,N}
+        if ((0x181u >> op) & 1u) {
             if (B.n == 0) { B.r0a = r; B.r1a = r + len; B.sha = q - r; }
             else if (B.n == 1) { B.r0b = r; B.r1b = r + len; B.shb = q - r; }
             else if (B.n == 2) { B.r0c = r; B.r1c = r + len; B.shc = q - r; }
             B.n++;
-            q += len;
-            r += len;
-        } else if (op == 1 || op == 4) {
-            q += len;
-        } else if (op == 2 || op == 3) {
-            r += len;
         }
+        q += ((0x193u >> op) & 1u) ? len : 0;
+        r += ((0x18Du >> op) & 1u) ? len : 0;
     }
     auto small = [](int s) { return s > -32 && s < 32; };
     B.regs_ok = B.n <= 3 && small(B.sha) && small(B.shb) && small(B.shc);
@@ -365,7 +371,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
         for (int k = 0; k <= W; k++) x[k] = __ldg(rx + k);
 #pragma unroll
         for (int k = 0; k < W; k++) {
-            T[k] = __funnelshift_r(x[k].x, x[k + 1].x, sh) & range_word(k, 0, v.span);
+            T[k] = __funnelshift_r(x[k].x, x[k + 1].x, sh) & prefix_word(k, v.span);
             S[k] = __funnelshift_r(x[k].y, x[k + 1].y, sh);
         }
     }
@@ -490,45 +496,23 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
     } else {
 #pragma unroll
         for (int k = 0; k < W; k++) H[k] = v.has_mp ? (R[k] & T[k] & ~S[k]) : 0u;
-        // Base quality only where a candidate survived: one byte of the qual column per candidate.
-        // The two lowest candidates of every window word are fetched together (independent global
-        // loads in flight), the rare rest one at a time.
-        int cb0[W], cb1[W];
-        uint32_t cq0[W], cq1[W], crest[W];
+        // Base quality only where a candidate survived: one byte of the qual column per candidate,
+        // visited in one loop over the whole window (64 bits at a time).
 #pragma unroll
-        for (int k = 0; k < W; k++) {
-            uint32_t h = H[k];
-            cb0[k] = __ffs(h) - 1;
-            h &= h - 1u;
-            cb1[k] = __ffs(h) - 1;
-            h &= h - 1u;
-            crest[k] = h;
-            cq0[k] = cq1[k] = 255u;
-            if (cb0[k] >= 0) {
-                const int o = 32 * k + cb0[k];
-                const int qi = regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o);
-                cq0[k] = (qi < 0 || qi >= (int)v.lseq) ? 0u : (uint32_t)__ldg(v.qual + qi);
-            }
-            if (cb1[k] >= 0) {
-                const int o = 32 * k + cb1[k];
-                const int qi = regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o);
-                cq1[k] = (qi < 0 || qi >= (int)v.lseq) ? 0u : (uint32_t)__ldg(v.qual + qi);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < W; k++) {
-            if (cb0[k] >= 0 && (int)cq0[k] < A.min_qual) H[k] &= ~(1u << cb0[k]);
-            if (cb1[k] >= 0 && (int)cq1[k] < A.min_qual) H[k] &= ~(1u << cb1[k]);
-            uint32_t rest = crest[k];
+        for (int k2 = 0; k2 < W; k2 += 2) {
+            unsigned long long rest = (unsigned long long)H[k2] | ((unsigned long long)H[k2 + 1] << 32), fail = 0ull;
             while (rest) {
-                const int bit = __ffs(rest) - 1;
-                rest &= rest - 1u;
-                const int o = 32 * k + bit;
+                const int bit = __ffsll((long long)rest) - 1;
+                rest &= rest - 1ull;
+                const int o = 32 * k2 + bit;
                 const int qi = regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o);
-                if (qi < 0 || qi >= (int)v.lseq || (int)__ldg(v.qual + qi) < A.min_qual) H[k] &= ~(1u << bit);
+                if (qi < 0 || qi >= (int)v.lseq || (int)__ldg(v.qual + qi) < A.min_qual) fail |= 1ull << bit;
             }
-            tc += __popc(H[k]);
+            H[k2] &= ~(uint32_t)fail;
+            H[k2 + 1] &= ~(uint32_t)(fail >> 32);
         }
+#pragma unroll
+        for (int k = 0; k < W; k++) tc += __popc(H[k]);
     }
     if (tc < A.conv_threshold) {  // not a T>C read: conversions are dropped (tcounter.py:210-214)
         tc = 0;
@@ -541,23 +525,22 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
     // --- interval join + per-UTR reduction + per-position scatter
     const uint32_t g = v.g, e = v.g + (uint32_t)v.span;
     const uint32_t nU = A.n_u[s];
-    const uint32_t *us = A.ustart[s], *ue = A.uend[s];
+    const uint4 *ut = A.utab[s];
     uint32_t i = __ldg(&A.bin_first[s][g >> SD_BIN_SHIFT]);
     uint32_t last_seg = 0xFFFFFFFFu;
     while (i < nU) {
-        const uint32_t st = __ldg(&us[i]);
-        if (st >= e) break;
-        const uint32_t en = __ldg(&ue[i]);
-        if (en > g) {
+        const uint4 u = __ldg(&ut[i]);   // {start, end, row, seg}
+        if (u.x >= e) break;
+        if (u.y > g) {
             uint32_t cov_t = pop_t, conv = (uint32_t)tc;
-            if (st > g || en < e) {  // the UTR covers only part of the read
-                const int lo = st > g ? (int)(st - g) : 0;
-                const int hi = en < e ? (int)(en - g) : v.span;
+            if (u.x > g || u.y < e) {  // the UTR covers only part of the read
+                const int lo = u.x > g ? (int)(u.x - g) : 0;
+                const int hi = u.y < e ? (int)(u.y - g) : v.span;
                 cov_t = 0;
                 conv = 0;
 #pragma unroll
                 for (int k = 0; k < W; k++) {
-                    const uint32_t m = range_word(k, lo, hi);
+                    const uint32_t m = prefix_word(k, hi) & ~prefix_word(k, lo);
                     cov_t += __popc(T[k] & m);
                     conv += __popc(H[k] & m);
                 }
@@ -566,25 +549,30 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #pragma unroll
                 for (int k = 0; k < W; k++) conv += __popc(H[k]);
             }
-            utr_accumulate(A.counters, __ldg(&A.urow[s][i]), tc > 0 ? 1u : 0u, mapq == 0 ? 1u : 0u, cov_t, conv);
-            const uint32_t seg = __ldg(&A.useg[s][i]);
-            if (seg != last_seg) {
-                last_seg = seg;
-                const uint32_t ss = __ldg(&A.seg_start[s][seg]), se = __ldg(&A.seg_end[s][seg]);
-                const uint64_t off = __ldg(&A.seg_off[s][seg]);
+            utr_accumulate(A.counters, u.z, tc > 0 ? 1u : 0u, mapq == 0 ? 1u : 0u, cov_t, conv);
+            if (u.w != last_seg) {
+                last_seg = u.w;
+                const uint4 sg = __ldg(&A.stab[s][u.w]);   // {start, end, off_lo, off_hi}
+                const uint32_t ss = sg.x, se = sg.y;
+                const uint64_t off = (uint64_t)sg.z | ((uint64_t)sg.w << 32);
                 const uint32_t pa = ss > g ? ss : g, pb = se < e ? se : e;
                 atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
                 atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
                 if (tc > 0) {
+                    int *tcbase = A.pos_tc + ((long long)off + ((long long)g - (long long)ss));   // may point before the segment; only in-range bits are used
                     const bool whole = (pa == g && pb == e);
 #pragma unroll
-                    for (int k = 0; k < W; k++) {
-                        uint32_t h = H[k];
-                        if (!whole) h &= range_word(k, (int)(pa - g), (int)(pb - g));
+                    for (int k2 = 0; k2 < W; k2 += 2) {
+                        uint32_t h0 = H[k2], h1 = H[k2 + 1];
+                        if (!whole) {
+                            h0 &= prefix_word(k2, (int)(pb - g)) & ~prefix_word(k2, (int)(pa - g));
+                            h1 &= prefix_word(k2 + 1, (int)(pb - g)) & ~prefix_word(k2 + 1, (int)(pa - g));
+                        }
+                        unsigned long long h = (unsigned long long)h0 | ((unsigned long long)h1 << 32);
                         while (h) {
-                            const int bit = __ffs(h) - 1;
-                            h &= h - 1u;
-                            atomicAdd(&A.pos_tc[off + (g + 32u * k + bit - ss)], 1);
+                            const int bit = __ffsll((long long)h) - 1;
+                            h &= h - 1ull;
+                            atomicAdd(tcbase + (32 * k2 + bit), 1);
                         }
                     }
                 }
@@ -887,6 +875,7 @@ extern "C" int sd_create(int device, void *stream, sd_ctx **out) {
 static void free_utr_tables(sd_ctx *ctx) {
     for (int s = 0; s < 2; s++) {
         cudaFree(ctx->d_ustart[s]); cudaFree(ctx->d_uend[s]); cudaFree(ctx->d_urow[s]); cudaFree(ctx->d_useg[s]);
+        cudaFree(ctx->d_utab[s]); cudaFree(ctx->d_stab[s]); ctx->d_utab[s] = ctx->d_stab[s] = nullptr;
         cudaFree(ctx->d_bin_first[s]); cudaFree(ctx->d_seg_start[s]); cudaFree(ctx->d_seg_end[s]); cudaFree(ctx->d_seg_off[s]);
         ctx->d_ustart[s] = ctx->d_uend[s] = ctx->d_urow[s] = ctx->d_useg[s] = ctx->d_bin_first[s] = nullptr;
         ctx->d_seg_start[s] = ctx->d_seg_end[s] = nullptr;
@@ -1049,6 +1038,11 @@ extern "C" int sd_set_utrs(sd_ctx *ctx, const uint32_t *h_chrom, const int64_t *
         if ((rc = upload(ctx, &ctx->d_seg_start[s], sstart))) return rc;
         if ((rc = upload(ctx, &ctx->d_seg_end[s], send))) return rc;
         if ((rc = upload(ctx, &ctx->d_seg_off[s], soff))) return rc;
+        std::vector<uint4> utab(n), stab(sstart.size());
+        for (uint32_t i = 0; i < n; i++) utab[i] = make_uint4(us[i], ue[i], ur[i], useg[i]);
+        for (size_t m = 0; m < sstart.size(); m++) stab[m] = make_uint4(sstart[m], send[m], (uint32_t)(soff[m] & 0xFFFFFFFFull), (uint32_t)(soff[m] >> 32));
+        if ((rc = upload(ctx, &ctx->d_utab[s], utab))) return rc;
+        if ((rc = upload(ctx, &ctx->d_stab[s], stab))) return rc;
         SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // vectors go out of scope
     }
     ctx->n_positions = pos_total;
@@ -1157,6 +1151,7 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     for (int s = 0; s < 2; s++) {
         A.refx[s] = ctx->refx[s];
         A.ustart[s] = ctx->d_ustart[s]; A.uend[s] = ctx->d_uend[s]; A.urow[s] = ctx->d_urow[s]; A.useg[s] = ctx->d_useg[s];
+        A.utab[s] = ctx->d_utab[s]; A.stab[s] = ctx->d_stab[s];
         A.bin_first[s] = ctx->d_bin_first[s]; A.n_u[s] = ctx->n_u[s];
         A.seg_start[s] = ctx->d_seg_start[s]; A.seg_end[s] = ctx->d_seg_end[s]; A.seg_off[s] = ctx->d_seg_off[s];
     }

@@ -35,6 +35,8 @@ struct sd_ctx {
     uint32_t n_u[2] = {0, 0};
     uint32_t *d_ustart[2] = {nullptr, nullptr}, *d_uend[2] = {nullptr, nullptr};
     uint32_t *d_urow[2] = {nullptr, nullptr}, *d_useg[2] = {nullptr, nullptr};
+    uint4 *d_utab[2] = {nullptr, nullptr};   // {start, end, row, seg} per table entry (one 128-bit load)
+    uint4 *d_stab[2] = {nullptr, nullptr};   // {start, end, off_lo, off_hi} per merged segment
     uint32_t *d_bin_first[2] = {nullptr, nullptr};
     uint32_t n_bins = 0;
     uint32_t n_seg[2] = {0, 0};
