@@ -254,7 +254,8 @@ typedef struct sd_hbatch {
     void *opaque;
 } sd_hbatch;
 
-/* fasta_names / n_fasta: chromosome table of the FASTA (index = sd_read_rec ref field).
+/* fasta_names / n_fasta: chromosome table of the FASTA (index = sd_read_rec ref field); n_fasta = 0:
+ * the ref field is the BAM reference id itself (what sd_filter works in).
  * want_mp: also decode MP tags into the mp column.  tile_reads: 32 (0 = default).
  * threads <= 0: hardware concurrency. */
 int sd_decode_bam(const char *path, const char *const *fasta_names, uint32_t n_fasta, int want_mp,

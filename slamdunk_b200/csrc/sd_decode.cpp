@@ -321,8 +321,12 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         if (l_name < 1 || p + 4 + (size_t)l_name + 4 > raw.size()) return bail(SD_ERR_FORMAT, "truncated reference table");
         std::string nm((const char *)raw.data() + p + 4, (size_t)l_name - 1);
         own->lengths.push_back(rd32(raw.data() + p + 4 + l_name));
-        auto it = fasta_idx.find(nm);
-        if (it != fasta_idx.end()) ref_map[(size_t)i] = it->second;
+        if (n_fasta == 0) {   // no FASTA table: chromosome index = BAM reference id (the filter's coordinate space)
+            if ((uint32_t)i < SD_REF_NONE) ref_map[(size_t)i] = (uint32_t)i;
+        } else {
+            auto it = fasta_idx.find(nm);
+            if (it != fasta_idx.end()) ref_map[(size_t)i] = it->second;
+        }
         own->names.push_back(nm);
         p += 8 + (size_t)l_name;
     }

@@ -81,3 +81,26 @@ class SlamSeqInfo(object):
                 % (self.SequencedReads, self.MappedReads, self.FilteredReads, self.MQFilteredReads,
                    self.IdFilteredReads, self.NmFilteredReads, self.MultimapperReads, self.DedupReads, self.SNPs,
                    self.AnnotationName, self.AnnotationMD5))
+
+
+def files_exist(files):
+    """utils/misc.py:125-133"""
+    if type(files) is list:
+        return all(os.path.exists(f) for f in files)
+    return os.path.exists(files)
+
+
+def checkStep(inFiles, outFiles, force=False):
+    """make-style skipping, utils/misc.py:147-164"""
+    if not files_exist(inFiles):
+        raise RuntimeError("One or more input files don't exist: " + str(inFiles))
+    inFileDate = os.path.getmtime(inFiles[0])
+    for x in inFiles[1:]:
+        inFileDate = max(inFileDate, os.path.getmtime(x))
+    if len(outFiles) > 0 and files_exist(outFiles):
+        outFileDate = os.path.getmtime(outFiles[0])
+        for x in outFiles[1:]:
+            outFileDate = min(outFileDate, os.path.getmtime(x))
+        if outFileDate > inFileDate:
+            return True if force == True else False   # noqa: E712 (kept literal)
+    return True
