@@ -16,6 +16,7 @@ import time
 import numpy as np
 
 from .. import _lib as L
+from .. import parallel
 from ..engine import CountEngine, HostBatch, HostGenome, make_params
 from ..utils.BedReader import BedIterator
 from ..utils.SNPtools import build_snp_masks
@@ -58,6 +59,11 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
         raise NotImplementedError("mle=True (per-read output + R MLE fit) is not part of the GPU count path")
     tm = CountTimings()
     t0 = time.time()
+    # multi-GPU: when the caller joined a process group (parallel.init / torchrun), every rank counts a slice of
+    # the BAM's tiles, the integer outputs are all-reduced and rank 0 writes the files
+    rank, world = 0, 1
+    if parallel.dist.is_available() and parallel.dist.is_initialized():
+        rank, world = parallel.dist.get_rank(), parallel.dist.get_world_size()
 
     genome = HostGenome(ref, OPTIONS["threads"])
     tm["fasta_decode_s"] = genome.seconds
@@ -73,6 +79,8 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
     readNumber = slamseqInfo.FilteredReads                   # tcounter.py:133
     bedMD5 = md5(bed)
 
+    if rank != 0:
+        outputCSV = outputBedgraphPlus = outputBedgraphMinus = os.devnull
     fileCSV = open(outputCSV, "w")
     print("#slamdunk v" + __version__, __count_version__, "sample info:", sampleInfo.Name, sampleInfo.ID,
           sampleInfo.Type, sampleInfo.Time, sep="\t", file=fileCSV)
@@ -115,7 +123,7 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
     tm["host_prepare_s"] = time.time() - t0 - tm["fasta_decode_s"] - tm["bam_inflate_s"] - tm["bam_decode_s"]
 
     t1 = time.time()
-    eng = CountEngine(OPTIONS["device"])
+    eng = CountEngine(OPTIONS["device"] if world == 1 else parallel.env()[2])
     try:
         eng.set_reference(genome.lo, genome.hi, genome.nmask, genome.chrom_off, genome.chrom_len)
         if tc_mask is not None:
@@ -124,7 +132,12 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
         params = make_params(min_qual=minQual, conversion_threshold=conversionThreshold, mismatch_source=mode)
         eng.synchronize()
         t2 = time.time()
-        eng.count_host(hbatch.batch, params)
+        my_batch = hbatch.batch
+        if world > 1:
+            my_batch = parallel.sub_batch(hbatch.batch, *parallel.shard_range(hbatch.batch.n_tiles, rank, world))
+        eng.count_host(my_batch, params)
+        if world > 1:
+            parallel.reduce_engine_outputs(eng, positions=True)
         stats = eng.stats.cpu().numpy()
         if mode == L.SD_MISMATCH_VERIFY and stats[L.SD_S_MP_DISAGREE] > 0:
             # the BAM's MP tags do not describe the same mismatches as SEQ/CIGAR vs this FASTA: the reference
@@ -133,7 +146,9 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
                   % (int(stats[L.SD_S_MP_DISAGREE]), os.path.basename(ref)), file=log)
             eng.reset_outputs()
             params = make_params(min_qual=minQual, conversion_threshold=conversionThreshold, mismatch_source=L.SD_MISMATCH_MP)
-            eng.count_host(hbatch.batch, params)
+            eng.count_host(my_batch, params)
+            if world > 1:
+                parallel.reduce_engine_outputs(eng, positions=True)
         eng.finalize()
         res = eng.results()
         tm["gpu_setup_s"] = t2 - t1

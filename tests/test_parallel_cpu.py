@@ -1,0 +1,119 @@
+"""World-size-2 gloo run on CPU of the multi-rank host logic: tile sharding + integer all-reduce.
+Each rank counts its slice of the reads with the CPU oracle; the reduced table must equal the
+unsharded count bit for bit (the property the GPU path relies on)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import simdata
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _count_slice(case_dir, lo, hi):
+    """oracle counters for records [lo, hi) of the case's BAM -> int64 [n_utr, 5] + per-position dict arrays"""
+    from oracle import oracle
+    from slamdunk_b200.io import bam as bamio
+    ref, bed, bam = (os.path.join(case_dir, "c" + e) for e in (".fa", ".bed", ".bam"))
+    text, refs, records = bamio.read_bam(bam)
+    fasta = bamio.read_fasta(ref)
+    genome = oracle.Genome(list(fasta.keys()), [s.encode() for s in fasta.values()])
+    names = [n for n, _ in refs]
+    reads = np.zeros(hi - lo, dtype=oracle.READ_DT)
+    quals, mps = [], []
+    qo = mo = 0
+    for k, r in enumerate(records[lo:hi]):
+        reads[k]["chrom"] = genome.index.get(names[r.ref_id], -1)
+        reads[k]["pos"], reads[k]["end"] = r.pos, r.reference_end
+        reads[k]["l_qual"], reads[k]["flag"], reads[k]["mapq"] = len(r.qual), r.flag, r.mapq
+        reads[k]["qual_off"] = qo
+        quals.append(bytes(r.qual)); qo += len(r.qual)
+        if r.has_tag("MP"):
+            mp_ = r.get_tag("MP").encode()
+            reads[k]["has_mp"], reads[k]["mp_off"], reads[k]["mp_len"] = 1, mo, len(mp_)
+            mps.append(mp_); mo += len(mp_)
+    reads = reads[reads["chrom"] >= 0]
+    rows = oracle.read_bed(bed)
+    utrs = np.zeros(len(rows), dtype=oracle.UTR_DT)
+    ids = {}
+    for i, (ch, s, e, _n, st) in enumerate(rows):
+        utrs[i] = (genome.index.get(ch, -1), 1 if ch in names else 0, s, e, 1 if st == "-" else 0, ids.setdefault(ch, len(ids)))
+    out, bg = oracle.count_arrays(genome, reads, np.frombuffer(b"".join(quals), dtype=np.uint8), utrs, 27, 1, None,
+                                  mp_text=b"".join(mps))
+    table = np.stack([out[k] for k in ("read_count", "tc_read_count", "multimap_count", "coverage_on_ts", "conversions_on_ts")], axis=1)
+    return table.astype(np.int64), len(records)
+
+
+def _worker(rank, world, port, case_dir, n_records, result_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from slamdunk_b200 import parallel
+    r, w, _lr = parallel.init("gloo")
+    assert (r, w) == (rank, world)
+    # shard by 32-read tiles like the GPU path
+    n_tiles = (n_records + 31) // 32
+    t0, t1 = parallel.shard_range(n_tiles, rank, world)
+    lo, hi = t0 * 32, min(n_records, t1 * 32)
+    table, _ = _count_slice(case_dir, lo, hi)
+    t = torch.from_numpy(table.copy())
+    parallel.allreduce_sum_([t])
+    if rank == 0:
+        np.save(result_path, t.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_range_partitions_exactly():
+    from slamdunk_b200 import parallel
+    for n in (0, 1, 7, 32, 1000, 1001):
+        for w in (1, 2, 3, 8):
+            parts = [parallel.shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_gloo_reduce_equals_unsharded(tmp_path):
+    c = simdata.make_case(str(tmp_path), seed=909, n_reads=1500, name="c")
+    whole, n_records = _count_slice(str(tmp_path), 0, 1500)
+    port = _free_port()
+    result = str(tmp_path / "reduced.npy")
+    mp.spawn(_worker, args=(2, port, str(tmp_path), n_records, result), nprocs=2, join=True)
+    reduced = np.load(result)
+    assert whole[:, 0].sum() > 0
+    assert np.array_equal(reduced, whole)
+
+
+def test_sub_batch_views(tmp_path):
+    """sub_batch() slices a decoded host batch by tiles without copying; slices tile the whole."""
+    from slamdunk_b200 import parallel
+    from slamdunk_b200.engine import HostBatch
+    c = simdata.make_case(str(tmp_path), seed=910, n_reads=300, name="c")
+    hb = HostBatch(c.bam, list(c.genome.keys()))
+    nt = hb.batch.n_tiles
+    total = 0
+    for r in range(3):
+        t0, t1 = parallel.shard_range(nt, r, 3)
+        sb = parallel.sub_batch(hb.batch, t0, t1)
+        assert sb.n_tiles == t1 - t0 and sb.tile_reads == 32
+        assert sb.rec == hb.batch.rec + t0 * 32 * 20 and sb.tiles == hb.batch.tiles + t0 * 32
+        assert sb.seq == hb.batch.seq and sb.qual == hb.batch.qual
+        total += sb.n_reads
+    assert total == hb.n_reads
+    hb.close()
