@@ -397,6 +397,62 @@ def read_bam(path: str):
     return text, refs, records
 
 
+def head_records(path: str, n: int = 1000) -> List[BamRecord]:
+    """First n alignment records, inflating only as many BGZF blocks as needed (pysam's AlignmentFile.head)."""
+    out: List[BamRecord] = []
+    buf = b""
+    off = 0
+    header_done = False
+    with open(path, "rb") as fh:
+        while len(out) < n:
+            head = fh.read(18)
+            if len(head) < 18:
+                break
+            xlen = struct.unpack_from("<H", head, 10)[0]
+            extra = head[12:] + fh.read(xlen - 6)
+            bsize = None
+            x = 0
+            while x + 4 <= len(extra):
+                si1, si2, slen = struct.unpack_from("<BBH", extra, x)
+                if si1 == 66 and si2 == 67:
+                    bsize = struct.unpack_from("<H", extra, x + 4)[0]
+                x += 4 + slen
+            if bsize is None:
+                raise ValueError("not a BGZF file: " + path)
+            rest = fh.read(bsize + 1 - 12 - xlen)
+            buf += zlib.decompress(rest[:-8], -15)
+            if not header_done:
+                if len(buf) < 12:
+                    continue
+                l_text = struct.unpack_from("<i", buf, 4)[0]
+                if len(buf) < 12 + l_text:
+                    continue
+                p = 8 + l_text
+                n_ref = struct.unpack_from("<i", buf, p)[0]
+                p += 4
+                ok = True
+                for _ in range(n_ref):
+                    if len(buf) < p + 4:
+                        ok = False
+                        break
+                    l_name = struct.unpack_from("<i", buf, p)[0]
+                    if len(buf) < p + 8 + l_name:
+                        ok = False
+                        break
+                    p += 8 + l_name
+                if not ok:
+                    continue
+                off = p
+                header_done = True
+            while len(out) < n and len(buf) >= off + 4:
+                bs = struct.unpack_from("<i", buf, off)[0]
+                if len(buf) < off + 4 + bs:
+                    break
+                rec, off = decode_record(buf, off)
+                out.append(rec)
+    return out
+
+
 def sort_records(records: List[BamRecord]) -> List[BamRecord]:
     """Coordinate sort like `samtools sort` (unmapped ref_id=-1 last; ties keep input order)."""
     def key(r: BamRecord):

@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""`slamdunk` command line with the count / filter steps on the GPU.
+
+Same sub-commands, options, defaults, output file names and directory layout as the reference CLI
+(slamdunk/slamdunk.py:332-524): `count`, `filter`, `all` (and `map` / `snp`, which -- exactly like
+the reference -- only build the command lines of the external NextGenMap / samtools / VarScan
+binaries and shell out; they are not part of the accelerated path).  `-t` is the number of host
+decode threads: samples are processed one after the other on the GPU instead of one joblib worker
+process per BAM (slamdunk.py:516).  Extra, opt-in: `--device`, `--mismatch-source`.
+"""
+from __future__ import print_function
+
+import os
+import random
+import subprocess
+import sys
+from argparse import SUPPRESS, ArgumentDefaultsHelpFormatter, ArgumentParser
+from os.path import basename
+from time import sleep
+
+from .utils.misc import checkStep, replaceExtension
+from .version import __ngm_version__, __version__
+
+mainOutput = sys.stderr
+printOnly = False
+verbose = False
+
+
+def message(msg):
+    print(msg, file=mainOutput)
+
+
+def stepFinished():
+    print(".", end="", file=mainOutput)
+
+
+def dunkFinished():
+    print("", file=mainOutput)
+
+
+def createDir(directory):
+    if not os.path.exists(directory):
+        message("Creating output directory: " + directory)
+        os.makedirs(directory)
+
+
+def getLogFile(path):
+    return open(path, "a")
+
+
+def _run(cmd, log, dry=False):
+    """utils/misc.py:184-196"""
+    if verbose or dry:
+        print(cmd, file=log)
+    if not dry:
+        p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, shell=True)
+        for line in iter(p.stdout.readline, b""):
+            print(line.decode("utf-8", "replace"), end="", file=log)
+        p.wait()
+        if p.returncode != 0:
+            raise RuntimeError("Error while executing command: \"" + cmd + "\"")
+
+
+def readSampleFile(fileName):
+    """slamdunk.py:82-101"""
+    samples, infos = [], []
+    with open(fileName, "r") as ins:
+        for line in ins:
+            line = line.strip()
+            if len(line) > 1:
+                if fileName.endswith(".tsv"):
+                    cols = line.split("\t")
+                elif fileName.endswith(".csv"):
+                    cols = line.split(",")
+                else:
+                    raise RuntimeError("Unknown file extension found: " + fileName)
+                if len(cols) < 4:
+                    raise RuntimeError("Invalid sample file found: " + fileName)
+                samples.append(cols[0])
+                infos.append(cols[1] + ":" + cols[2] + ":" + cols[3])
+    return samples, infos
+
+
+def getSamples(bams, runOnly=-1):
+    """slamdunk.py:103-123"""
+    if len(bams) == 1 and (bams[0].endswith(".tsv") or bams[0].endswith(".csv")):
+        samples, samplesInfos = readSampleFile(bams[0])
+    else:
+        samples = bams
+        samplesInfos = [""] * len(samples)
+    if runOnly > 0:
+        if runOnly > len(samples):
+            raise RuntimeError("Sample index out of range. " + str(runOnly) + " > " + str(len(samples)) + ". Check -i/--sample-index")
+        message("Running only job " + str(runOnly))
+        samples = [samples[runOnly - 1]]
+        samplesInfos = [samplesInfos[runOnly - 1]]
+    elif runOnly == 0:
+        raise RuntimeError("Sample index (" + str(runOnly) + ") out of range. Starts with 1. Check -i/--sample-index")
+    return samples, samplesInfos
+
+
+def estimateMaxReadLength(bam):
+    """utils/misc.py:91-107: first 1000 reads, query_length + XA tag; spread <= 10 -> max + 10 else -1."""
+    from .io import bam as bamio
+    minLength, maxLength = sys.maxsize, 0
+    for read in bamio.head_records(bam, 1000):
+        ln = len(read.seq) + read.get_tag("XA")
+        minLength = min(minLength, ln)
+        maxLength = max(maxLength, ln)
+    return maxLength + 10 if (maxLength - minLength) <= 10 else -1
+
+
+# ------------------------------------------------------------------ steps
+def runMap(tid, inputBAM, referenceFile, threads, trim5p, maxPolyA, quantseqMapping, endtoendMapping, topn, sampleDescription,
+           outputDirectory, skipSAM):
+    """slamdunk.py:125-151 + dunks/mapper.py:77-109: NextGenMap command line (external binary)."""
+    ext = ".bam" if skipSAM else ".sam"
+    outputSAM = os.path.join(outputDirectory, replaceExtension(basename(inputBAM), ext, "_slamdunk_mapped"))
+    outputLOG = os.path.join(outputDirectory, replaceExtension(basename(inputBAM), ".log", "_slamdunk_mapped"))
+    sampleName = replaceExtension(basename(inputBAM), ".bam", "")
+    sampleType, sampleTime = "NA", "-1"
+    if sampleDescription != "":
+        d = sampleDescription.split(":")
+        if len(d) >= 1:
+            sampleName = d[0]
+        if len(d) >= 2:
+            typeDict = {"p": "pulse", "c": "chase", "pulse": "pulse", "chase": "chase", "": "NA"}
+            sampleType = typeDict.get(d[1], d[1])
+        if len(d) >= 3:
+            sampleTime = d[2]
+    parameter = "--no-progress" if quantseqMapping is True else "--no-progress --slam-seq 2"
+    if trim5p > 0:
+        parameter += " -5 " + str(trim5p)
+    if maxPolyA > -1:
+        parameter += " --max-polya " + str(maxPolyA)
+    parameter += " -e " if endtoendMapping is True else " -l "
+    parameter += " --rg-id " + str(tid)
+    if sampleName != "":
+        parameter += " --rg-sm " + sampleName + ":" + sampleType + ":" + str(sampleTime)
+    if topn > 1:
+        parameter += " -n " + str(topn) + " --strata "
+    log = getLogFile(outputLOG)
+    if checkStep([referenceFile, inputBAM], [replaceExtension(outputSAM, ".bam")], False):
+        flag = "" if outputSAM.endswith(".sam") else "-b "
+        _run("ngm " + flag + "-r " + referenceFile + " -q " + inputBAM + " -t " + str(threads) + " " + parameter + " -o " + outputSAM,
+             log, dry=printOnly)
+    else:
+        print("Skipped mapping for " + inputBAM, file=log)
+    log.close()
+    stepFinished()
+
+
+def runSam2Bam(tid, bam, threads, outputDirectory):
+    """slamdunk.py:153-157 + dunks/mapper.py:28-74 (samtools view, no sort)."""
+    inputSAM = os.path.join(outputDirectory, replaceExtension(basename(bam), ".sam", "_slamdunk_mapped"))
+    outputBAM = os.path.join(outputDirectory, replaceExtension(basename(bam), ".bam", "_slamdunk_mapped"))
+    log = getLogFile(os.path.join(outputDirectory, replaceExtension(basename(bam), ".log", "_slamdunk_mapped")))
+    if os.path.exists(inputSAM) and checkStep([inputSAM], [outputBAM + ".bai"]):
+        _run(" ".join(["samtools view", "-@", str(threads), "-Sb", "-o", outputBAM, inputSAM]), log, dry=printOnly)
+        if not printOnly and os.path.exists(inputSAM):
+            os.remove(inputSAM)
+    else:
+        print("Skipped sorting for " + inputSAM, file=log)
+    log.close()
+    stepFinished()
+
+
+def runFilter(tid, bam, bed, mq, minIdentity, maxNM, outputDirectory):
+    """slamdunk.py:167-171 -> GPU filter"""
+    from .dunks import filter as gfilter
+    outputBAM = os.path.join(outputDirectory, replaceExtension(basename(bam), ".bam", "_filtered"))
+    outputLOG = os.path.join(outputDirectory, replaceExtension(basename(bam), ".log", "_filtered"))
+    log = getLogFile(outputLOG)
+    gfilter.Filter(bam, outputBAM, log, bed, mq, minIdentity, maxNM, printOnly, verbose)
+    log.close()
+    stepFinished()
+
+
+def runSnp(tid, referenceFile, minCov, minVarFreq, minQual, inputBAM, outputDirectory):
+    """slamdunk.py:173-177 + dunks/snps.py:25-44: samtools mpileup | varscan mpileup2snp (external)."""
+    outputSNP = os.path.join(outputDirectory, replaceExtension(basename(inputBAM), ".vcf", "_snp"))
+    log = getLogFile(os.path.join(outputDirectory, replaceExtension(basename(inputBAM), ".log", "_snp")))
+    if checkStep([inputBAM, referenceFile], [outputSNP], False):
+        mpileupCmd = "samtools mpileup -B -A -f " + referenceFile + " " + inputBAM
+        varscanCmd = ("varscan mpileup2snp  --strand-filter 0 --output-vcf --min-var-freq " + str(minVarFreq) +
+                      " --min-coverage " + str(minCov) + " --variants 1")
+        if verbose:
+            print(mpileupCmd, file=log)
+            print(varscanCmd, file=log)
+        if not printOnly:
+            with open(outputSNP, "w") as fileSNP:
+                mpileup = subprocess.Popen(mpileupCmd, shell=True, stdout=subprocess.PIPE, stderr=log)
+                varscan = subprocess.Popen(varscanCmd, shell=True, stdin=mpileup.stdout, stdout=fileSNP, stderr=log)
+                varscan.wait()
+    else:
+        print("Skipping SNP calling", file=log)
+    log.close()
+    stepFinished()
+
+
+def runCount(tid, bam, ref, bed, maxLength, minQual, conversionThreshold, outputDirectory, snpDirectory, vcfFile):
+    """slamdunk.py:179-204 -> GPU count"""
+    from .dunks import tcounter
+    outputCSV = os.path.join(outputDirectory, replaceExtension(basename(bam), ".tsv", "_tcount"))
+    outputBedgraphPlus = os.path.join(outputDirectory, replaceExtension(basename(bam), ".bedgraph", "_tcount_plus"))
+    outputBedgraphMinus = os.path.join(outputDirectory, replaceExtension(basename(bam), ".bedgraph", "_tcount_mins"))
+    outputLOG = os.path.join(outputDirectory, replaceExtension(basename(bam), ".log", "_tcount"))
+    if vcfFile is not None:
+        inputSNP = vcfFile
+    elif snpDirectory is not None:
+        inputSNP = os.path.join(snpDirectory, replaceExtension(basename(bam), ".vcf", "_snp"))
+    else:
+        inputSNP = None
+    if maxLength is None:
+        maxLength = estimateMaxReadLength(bam)
+    if maxLength < 0:
+        print("Difference between minimum and maximum read length is > 10. Please specify --max-read-length parameter.")
+        sys.exit(0)
+    log = getLogFile(outputLOG)
+    print("Using " + str(maxLength) + " as maximum read length.", file=log)
+    tcounter.computeTconversions(ref, bed, inputSNP, bam, maxLength, minQual, outputCSV, outputBedgraphPlus, outputBedgraphMinus,
+                                 conversionThreshold, log)
+    log.close()
+    stepFinished()
+    return outputCSV
+
+
+def runAll(args):
+    """slamdunk.py:206-330"""
+    message("slamdunk all")
+    if args.sampleIndex > -1:
+        sec = random.randrange(200, 2000) / 1000.0
+        message("Waiting " + str(sec) + " seconds")
+        sleep(sec)
+    outputDirectory = args.outputDir
+    createDir(outputDirectory)
+    n = args.threads
+    referenceFile = args.referenceFile
+    dunkPath = os.path.join(outputDirectory, "map")
+    createDir(dunkPath)
+    samples, samplesInfos = getSamples(args.files, runOnly=args.sampleIndex)
+    message("Running slamDunk map for " + str(len(samples)) + " files (" + str(n) + " threads)")
+    for i in range(0, len(samples)):
+        bam = samples[i]
+        if not args.sampleName or len(samples) > 1:
+            sampleName = replaceExtension(basename(bam), "", "")
+        else:
+            sampleName = args.sampleName
+        sampleInfo = samplesInfos[i]
+        if sampleInfo == "":
+            sampleInfo = sampleName + ":" + args.sampleType + ":" + str(args.sampleTime)
+        tid = args.sampleIndex if args.sampleIndex > -1 else i
+        runMap(tid, bam, referenceFile, n, args.trim5, args.maxPolyA, args.quantseq, args.endtoend, args.topn, sampleInfo, dunkPath, args.skipSAM)
+    dunkFinished()
+    if not args.skipSAM:
+        message("Running slamDunk sam2bam for " + str(len(samples)) + " files (" + str(n) + " threads)")
+        for tid in range(0, len(samples)):
+            runSam2Bam(tid, samples[tid], n, dunkPath)
+        dunkFinished()
+    dunkbufferIn = [os.path.join(dunkPath, replaceExtension(basename(f), ".bam", "_slamdunk_mapped")) for f in samples]
+    bed = args.bed
+    if args.filterbed:
+        bed = args.filterbed
+        args.multimap = True
+    if not args.multimap:
+        bed = None
+    dunkPath = os.path.join(outputDirectory, "filter")
+    createDir(dunkPath)
+    message("Running slamDunk filter for " + str(len(samples)) + " files (" + str(n) + " threads)")
+    for tid in range(0, len(samples)):
+        runFilter(tid, dunkbufferIn[tid], bed, args.mq, args.identity, args.nm, dunkPath)
+    dunkFinished()
+    dunkbufferIn = [os.path.join(dunkPath, replaceExtension(basename(f), ".bam", "_filtered")) for f in dunkbufferIn]
+    snpDirectory, vcfFile = None, None
+    if "vcfFile" not in args:
+        dunkPath = os.path.join(outputDirectory, "snp")
+        createDir(dunkPath)
+        message("Running slamDunk SNP for " + str(len(samples)) + " files (" + str(max(1, int(n / 2)) if n > 1 else n) + " threads)")
+        for tid in range(0, len(samples)):
+            runSnp(tid, referenceFile, args.cov, args.var, args.minQual, dunkbufferIn[tid], dunkPath)
+        snpDirectory = os.path.join(outputDirectory, "snp")
+        dunkFinished()
+    else:
+        vcfFile = args.vcfFile
+    dunkPath = os.path.join(outputDirectory, "count")
+    createDir(dunkPath)
+    message("Running slamDunk tcount for " + str(len(samples)) + " files (" + str(n) + " threads)")
+    for tid in range(0, len(samples)):
+        runCount(tid, dunkbufferIn[tid], referenceFile, args.bed, args.maxLength, args.minQual, args.conversionThreshold, dunkPath,
+                 snpDirectory, vcfFile)
+    dunkFinished()
+
+
+def build_parser():
+    """Argument surface of slamdunk.py:336-430, verbatim, plus the opt-in GPU knobs."""
+    usage = "SLAMdunk software for analyzing SLAM-seq data"
+    parser = ArgumentParser(description=usage, formatter_class=ArgumentDefaultsHelpFormatter)
+    parser.add_argument("--version", action="version", version="%(prog)s " + __version__)
+    parser.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
+    parser.add_argument("--mismatch-source", default="verify", choices=["verify", "cigar", "mp"], dest="mismatchSource",
+                        help="where per-read mismatches come from: CIGAR walk cross-checked against the MP tags, CIGAR walk only, or MP tags only")
+    subparsers = parser.add_subparsers(help="", dest="command")
+
+    mapparser = subparsers.add_parser("map", help="Map SLAM-seq read data", formatter_class=ArgumentDefaultsHelpFormatter)
+    mapparser.add_argument("files", action="store", help="Single csv/tsv file (recommended) containing all sample files and sample info or a list of all sample BAM/FASTA(gz)/FASTQ(gz) files", nargs="+")
+    mapparser.add_argument("-r", "--reference", type=str, required=True, dest="referenceFile", default=SUPPRESS, help="Reference fasta file")
+    mapparser.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", default=SUPPRESS, help="Output directory for mapped BAM files.")
+    mapparser.add_argument("-5", "--trim-5p", type=int, required=False, dest="trim5", default=12, help="Number of bp removed from 5' end of all reads.")
+    mapparser.add_argument("-n", "--topn", type=int, required=False, dest="topn", default=1, help="Max. number of alignments to report per read")
+    mapparser.add_argument("-a", "--max-polya", type=int, required=False, dest="maxPolyA", default=4, help="Max number of As at the 3' end of a read.")
+    mapparser.add_argument("-t", "--threads", type=int, required=False, dest="threads", default=1, help="Thread number")
+    mapparser.add_argument("-q", "--quantseq", dest="quantseq", action="store_true", required=False, help="Run plain Quantseq alignment without SLAM-seq scoring")
+    mapparser.add_argument("-e", "--endtoend", action="store_true", dest="endtoend", help="Use a end to end alignment algorithm for mapping.")
+    mapparser.add_argument("-sn", "--sampleName", type=str, dest="sampleName", required=False, help="Use this sample name for all supplied samples")
+    mapparser.add_argument("-sy", "--sampleType", type=str, dest="sampleType", required=False, default="pulse", help="Use this sample type for all supplied samples")
+    mapparser.add_argument("-st", "--sampleTime", type=int, dest="sampleTime", required=False, default=0, help="Use this sample time for all supplied samples")
+    mapparser.add_argument("-i", "--sample-index", type=int, required=False, default=-1, dest="sampleIndex", help="Run analysis only for sample <i>. Use for distributing slamdunk analysis on a cluster (index is 1-based).")
+    mapparser.add_argument("-ss", "--skip-sam", action="store_true", dest="skipSAM", help="Output BAM while mapping. Slower but, uses less hard disk.")
+
+    filterparser = subparsers.add_parser("filter", help="Filter SLAM-seq aligned data")
+    filterparser.add_argument("bam", action="store", help="Bam file(s)", nargs="+")
+    filterparser.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", help="Output directory for mapped BAM files.")
+    filterparser.add_argument("-b", "--bed", type=str, required=False, dest="bed", help="BED file, overrides MQ filter to 0")
+    filterparser.add_argument("-mq", "--min-mq", type=int, required=False, default=2, dest="mq", help="Minimum mapping quality (default: %(default)d)")
+    filterparser.add_argument("-mi", "--min-identity", type=float, required=False, default=0.95, dest="identity", help="Minimum alignment identity (default: %(default)s)")
+    filterparser.add_argument("-nm", "--max-nm", type=int, required=False, default=-1, dest="nm", help="Maximum NM for alignments (default: %(default)d)")
+    filterparser.add_argument("-t", "--threads", type=int, required=False, dest="threads", default=1, help="Thread number (default: %(default)d)")
+
+    snpparser = subparsers.add_parser("snp", help="Call SNPs on SLAM-seq aligned data", formatter_class=ArgumentDefaultsHelpFormatter)
+    snpparser.add_argument("bam", action="store", help="Bam file(s)", nargs="+")
+    snpparser.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", default=SUPPRESS, help="Output directory for mapped BAM files.")
+    snpparser.add_argument("-r", "--reference", required=True, dest="fasta", type=str, default=SUPPRESS, help="Reference fasta file")
+    snpparser.add_argument("-c", "--min-coverage", required=False, dest="cov", type=int, help="Minimimum coverage to call variant", default=10)
+    snpparser.add_argument("-f", "--var-fraction", required=False, dest="var", type=float, help="Minimimum variant fraction to call variant", default=0.8)
+    snpparser.add_argument("-t", "--threads", type=int, required=False, default=1, dest="threads", help="Thread number")
+
+    countparser = subparsers.add_parser("count", help="Count T/C conversions in SLAM-seq aligned data")
+    countparser.add_argument("bam", action="store", help="Bam file(s)", nargs="+")
+    countparser.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", default=SUPPRESS, help="Output directory for mapped BAM files.")
+    countparser.add_argument("-s", "--snp-directory", type=str, required=False, dest="snpDir", default=SUPPRESS, help="Directory containing SNP files.")
+    countparser.add_argument("-v", "--vcf", type=str, required=False, dest="vcfFile", default=SUPPRESS, help="Externally provided custom variant file.")
+    countparser.add_argument("-r", "--reference", type=str, required=True, dest="ref", default=SUPPRESS, help="Reference fasta file")
+    countparser.add_argument("-b", "--bed", type=str, required=True, dest="bed", default=SUPPRESS, help="BED file")
+    countparser.add_argument("-c", "--conversion-threshold", type=int, dest="conversionThreshold", required=False, default=1, help="Number of T>C conversions required to count read as T>C read (default: %(default)d)")
+    countparser.add_argument("-l", "--max-read-length", type=int, required=False, dest="maxLength", help="Max read length in BAM file")
+    countparser.add_argument("-q", "--min-base-qual", type=int, default=27, required=False, dest="minQual", help="Min base quality for T -> C conversions (default: %(default)d)")
+    countparser.add_argument("-t", "--threads", type=int, required=False, default=1, dest="threads", help="Thread number (default: %(default)d)")
+
+    allparser = subparsers.add_parser("all", help="Run entire SLAMdunk analysis")
+    allparser.add_argument("files", action="store", help="Single csv/tsv file (recommended) containing all sample files and sample info or a list of all sample BAM/FASTA(gz)/FASTQ(gz) files", nargs="+")
+    allparser.add_argument("-r", "--reference", type=str, required=True, dest="referenceFile", help="Reference fasta file")
+    allparser.add_argument("-b", "--bed", type=str, required=True, dest="bed", help="BED file with 3'UTR coordinates")
+    allparser.add_argument("-fb", "--filterbed", type=str, required=False, dest="filterbed", help="BED file with 3'UTR coordinates to filter multimappers (activates -m)")
+    allparser.add_argument("-v", "--vcf", type=str, required=False, dest="vcfFile", default=SUPPRESS, help="Skip SNP step and provide custom variant file.")
+    allparser.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", help="Output directory for slamdunk run.")
+    allparser.add_argument("-5", "--trim-5p", type=int, required=False, dest="trim5", default=12, help="Number of bp removed from 5' end of all reads (default: %(default)s)")
+    allparser.add_argument("-a", "--max-polya", type=int, required=False, dest="maxPolyA", default=4, help="Max number of As at the 3' end of a read (default: %(default)s)")
+    allparser.add_argument("-n", "--topn", type=int, required=False, dest="topn", default=1, help="Max. number of alignments to report per read (default: %(default)s)")
+    allparser.add_argument("-t", "--threads", type=int, required=False, default=1, dest="threads", help="Thread number (default: %(default)s)")
+    allparser.add_argument("-q", "--quantseq", dest="quantseq", action="store_true", required=False, help="Run plain Quantseq alignment without SLAM-seq scoring")
+    allparser.add_argument("-e", "--endtoend", action="store_true", dest="endtoend", help="Use a end to end alignment algorithm for mapping.")
+    allparser.add_argument("-m", "--multimap", action="store_true", dest="multimap", help="Use reference to resolve multimappers (requires -n > 1).")
+    allparser.add_argument("-mq", "--min-mq", type=int, required=False, default=2, dest="mq", help="Minimum mapping quality (default: %(default)s)")
+    allparser.add_argument("-mi", "--min-identity", type=float, required=False, default=0.95, dest="identity", help="Minimum alignment identity (default: %(default)s)")
+    allparser.add_argument("-nm", "--max-nm", type=int, required=False, default=-1, dest="nm", help="Maximum NM for alignments (default: %(default)s)")
+    allparser.add_argument("-mc", "--min-coverage", required=False, dest="cov", type=int, help="Minimimum coverage to call variant (default: %(default)s)", default=10)
+    allparser.add_argument("-mv", "--var-fraction", required=False, dest="var", type=float, help="Minimimum variant fraction to call variant (default: %(default)s)", default=0.8)
+    allparser.add_argument("-c", "--conversion-threshold", type=int, dest="conversionThreshold", required=False, default=1, help="Number of T>C conversions required to count read as T>C read (default: %(default)d)")
+    allparser.add_argument("-rl", "--max-read-length", type=int, required=False, dest="maxLength", help="Max read length in BAM file")
+    allparser.add_argument("-mbq", "--min-base-qual", type=int, default=27, required=False, dest="minQual", help="Min base quality for T -> C conversions (default: %(default)d)")
+    allparser.add_argument("-sn", "--sampleName", type=str, dest="sampleName", required=False, help="Use this sample name for all supplied samples")
+    allparser.add_argument("-sy", "--sampleType", type=str, dest="sampleType", required=False, default="pulse", help="Use this sample type for all supplied samples")
+    allparser.add_argument("-st", "--sampleTime", type=int, dest="sampleTime", required=False, default=0, help="Use this sample time for all supplied samples")
+    allparser.add_argument("-i", "--sample-index", type=int, required=False, default=-1, dest="sampleIndex", help="Run analysis only for sample <i>. Use for distributing slamdunk analysis on a cluster (index is 1-based).")
+    allparser.add_argument("-ss", "--skip-sam", action="store_true", dest="skipSAM", help="Output BAM while mapping. Slower but, uses less hard disk.")
+    return parser
+
+
+def run(argv=None):
+    parser = build_parser()
+    args = parser.parse_args(argv)
+    command = args.command
+    if command in ("count", "filter", "all"):
+        from .dunks import filter as gfilter
+        from .dunks import tcounter
+        tcounter.OPTIONS["device"] = gfilter.OPTIONS["device"] = args.device
+        tcounter.OPTIONS["threads"] = gfilter.OPTIONS["threads"] = args.threads
+        tcounter.OPTIONS["mismatch_source"] = args.mismatchSource
+
+    if command == "map":
+        createDir(args.outputDir)
+        n = args.threads
+        samples, samplesInfos = getSamples(args.files, runOnly=args.sampleIndex)
+        message("Running slamDunk map for " + str(len(samples)) + " files (" + str(n) + " threads)")
+        for i in range(0, len(samples)):
+            bam = samples[i]
+            sampleName = replaceExtension(basename(bam), "", "") if (not args.sampleName or len(samples) > 1) else args.sampleName
+            sampleInfo = samplesInfos[i]
+            if sampleInfo == "":
+                sampleInfo = sampleName + ":" + args.sampleType + ":" + str(args.sampleTime)
+            tid = args.sampleIndex if args.sampleIndex > -1 else i
+            runMap(tid, bam, args.referenceFile, n, args.trim5, args.maxPolyA, args.quantseq, args.endtoend, args.topn, sampleInfo,
+                   args.outputDir, args.skipSAM)
+        dunkFinished()
+        if not args.skipSAM:
+            message("Running slamDunk sam2bam for " + str(len(samples)) + " files (" + str(n) + " threads)")
+            for tid in range(0, len(samples)):
+                runSam2Bam(tid, samples[tid], n, args.outputDir)
+            dunkFinished()
+    elif command == "filter":
+        createDir(args.outputDir)
+        message("Running slamDunk filter for " + str(len(args.bam)) + " files (" + str(args.threads) + " threads)")
+        for tid in range(0, len(args.bam)):
+            runFilter(tid, args.bam[tid], args.bed, args.mq, args.identity, args.nm, args.outputDir)
+        dunkFinished()
+    elif command == "snp":
+        createDir(args.outputDir)
+        n = args.threads
+        if n > 1:
+            n = int(n / 2)
+        message("Running slamDunk SNP for " + str(len(args.bam)) + " files (" + str(n) + " threads)")
+        for tid in range(0, len(args.bam)):
+            runSnp(tid, args.fasta, args.cov, args.var, 15, args.bam[tid], args.outputDir)
+        dunkFinished()
+    elif command == "count":
+        createDir(args.outputDir)
+        snpDirectory = args.snpDir if "snpDir" in args else None
+        vcfFile = args.vcfFile if "vcfFile" in args else None
+        message("Running slamDunk tcount for " + str(len(args.bam)) + " files (" + str(args.threads) + " threads)")
+        for tid in range(0, len(args.bam)):
+            runCount(tid, args.bam[tid], args.ref, args.bed, args.maxLength, args.minQual, args.conversionThreshold, args.outputDir,
+                     snpDirectory, vcfFile)
+        dunkFinished()
+    elif command == "all":
+        runAll(args)
+        dunkFinished()
+    else:
+        parser.error("Too few arguments.")
+
+
+if __name__ == "__main__":
+    run()
