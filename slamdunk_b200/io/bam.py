@@ -1,13 +1,12 @@
 """Pure-Python BGZF/BAM codec (struct + zlib only).
 
-Small, slow and complete enough for fixtures: it writes the BAM files the tests,
-the golden-vector generator and the synthetic SLAM-seq generator feed to both the
-reference (through tests/shims/pysam) and to the native decoder
-(slamdunk_b200/csrc/host_decode.cpp), and it reads them back so the native
-decoder can be cross-checked record by record.
+Small, slow and complete: it writes the BAM files that the tests and the golden-vector
+generator feed to both the reference (through tests/shims/pysam) and the native decoder
+(slamdunk_b200/csrc/sd_decode.cpp), reads them back so the native decoder can be cross-checked
+record by record, and is what `dunks/filter.py` uses to write the filtered BAM until the native
+BAM writer exists.
 
-The product's BAM hot path is the C++ decoder; nothing on the counting path
-imports this module.
+The count path never imports this module: its BAM input goes through the C++ decoder.
 
 Format follows the SAM/BAM specification (SAMv1 section 4): BGZF blocks are gzip
 members carrying a 'BC' extra sub-field, the BAM stream is little-endian.
