@@ -118,6 +118,7 @@ __device__ __forceinline__ bool cigar_consumes_ref(uint32_t op) { return op == 0
 __device__ __forceinline__ bool cigar_is_match(uint32_t op) { return op == 0 || op == 7 || op == 8; }
 __device__ __forceinline__ bool cigar_consumes_query(uint32_t op) { return op == 0 || op == 1 || op == 4 || op == 7 || op == 8; }
 
+// @region helpers
 // bits [lo, hi) of the window restricted to word k
 __device__ __forceinline__ uint32_t range_word(int k, int lo, int hi) {
     int a = lo - 32 * k, b = hi - 32 * k;
@@ -128,6 +129,7 @@ __device__ __forceinline__ uint32_t range_word(int k, int lo, int hi) {
     return m & ~((1u << a) - 1u);
 }
 
+// @region helpers
 // bits [0, hi) of the window restricted to word k
 __device__ __forceinline__ uint32_t prefix_word(int k, int hi) {
     int b = hi - 32 * k;
@@ -135,6 +137,7 @@ __device__ __forceinline__ uint32_t prefix_word(int k, int hi) {
     return (uint32_t)((1ull << b) - 1ull);
 }
 
+// @region utr_accumulate
 // Warp-aggregated add into one UTR's counter row: lanes that hit the same row elect a leader.
 __device__ __forceinline__ void utr_accumulate(unsigned long long *counters, uint32_t row, uint32_t tcread,
                                                uint32_t multimap, uint32_t cov_t, uint32_t conv_t) {
@@ -155,6 +158,7 @@ __device__ __forceinline__ void utr_accumulate(unsigned long long *counters, uin
     }
 }
 
+// @region sliced_is_base
 // read mask word -> "is X" byte for 8 bases of sliced SEQ.  inv flips the planes that must be 0.
 __device__ __forceinline__ uint32_t sliced_is_base(uint32_t w, uint32_t inv) {
     uint32_t x = w ^ inv;
@@ -163,6 +167,7 @@ __device__ __forceinline__ uint32_t sliced_is_base(uint32_t w, uint32_t inv) {
     return x & 0xFFu;
 }
 
+// @region slow_and_generic
 // Map a reference offset (relative to the alignment start) to the read index aligned to it.
 __device__ __forceinline__ int ref_to_read(const uint32_t *cig, uint32_t ncig, int o) {
     int q = 0, r = 0;
@@ -321,6 +326,7 @@ struct Blocks {
     bool regs_ok;        // describable by <= 3 blocks with |sh| < 32
 };
 
+// @region parse_cigar
 __device__ __forceinline__ int parse_cigar(const uint32_t *cig, uint32_t ncig, Blocks &B) {
     int q = 0, r = 0;
     B.n = 0;
@@ -344,6 +350,7 @@ __device__ __forceinline__ int parse_cigar(const uint32_t *cig, uint32_t ncig, B
     return r;  // reference length
 }
 
+// @region block_index
 // window word k of the read mask M shifted so that window position p reads M bit p + sh, |sh| < 32
 template <int W>
 __device__ __forceinline__ uint32_t shifted_word(const uint32_t (&M)[W], int k, int sh) {
@@ -361,6 +368,12 @@ template <int W>
 __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, const Blocks &B, uint32_t mapq,
                                          uint32_t *scratch, bool &mp_disagree) {
     const int s = v.strand;
+    const uint32_t g = v.g, e = v.g + (uint32_t)v.span;
+    const uint32_t nU = A.n_u[s];
+    const uint4 *ut = A.utab[s];
+    // the interval-join entry point is fetched up front so that its latency overlaps the bit work below
+    uint32_t i = __ldg(&A.bin_first[s][g >> SD_BIN_SHIFT]);
+    // @region window
     // --- reference window: isX (T or A) and SNP planes, shifted so that bit j = position g + j
     uint32_t T[W], S[W];
     {
@@ -375,6 +388,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             S[k] = __funnelshift_r(x[k].y, x[k + 1].y, sh);
         }
     }
+    // @region read_mask
     // --- read-side candidate mask in window coordinates
     uint32_t R[W];
     const bool regs = B.regs_ok;
@@ -459,6 +473,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             }
         }
     }
+    // @region verify
     // --- cross-check against NextGenMap's MP list (before quality / SNP masking)
     if (A.mismatch_source == SD_MISMATCH_VERIFY && v.has_mp && v.mp != nullptr) {
         uint32_t D[W];
@@ -481,6 +496,9 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
         for (int k = 0; k < W; k++) bad |= (D[k] != 0u);
         mp_disagree = bad;
     }
+    uint4 u = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);   // first table entry {start, end, row, seg}, in flight during the quality test
+    if (i < nU) u = __ldg(&ut[i]);
+    // @region candidates_qual
     // --- candidates: reference is T (A), read is C (G), not a SNP
     uint32_t H[W];
     int tc = 0;
@@ -497,7 +515,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #pragma unroll
         for (int k = 0; k < W; k++) H[k] = v.has_mp ? (R[k] & T[k] & ~S[k]) : 0u;
         // Base quality only where a candidate survived: one byte of the qual column per candidate,
-        // visited in one loop over the whole window (64 bits at a time).
+        // visited in one loop per 64 window positions.
 #pragma unroll
         for (int k2 = 0; k2 < W; k2 += 2) {
             unsigned long long rest = (unsigned long long)H[k2] | ((unsigned long long)H[k2 + 1] << 32), fail = 0ull;
@@ -514,6 +532,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #pragma unroll
         for (int k = 0; k < W; k++) tc += __popc(H[k]);
     }
+    // @region threshold_popt
     if (tc < A.conv_threshold) {  // not a T>C read: conversions are dropped (tcounter.py:210-214)
         tc = 0;
 #pragma unroll
@@ -522,14 +541,10 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
     uint32_t pop_t = 0;
 #pragma unroll
     for (int k = 0; k < W; k++) pop_t += __popc(T[k]);
+    // @region utr_join
     // --- interval join + per-UTR reduction + per-position scatter
-    const uint32_t g = v.g, e = v.g + (uint32_t)v.span;
-    const uint32_t nU = A.n_u[s];
-    const uint4 *ut = A.utab[s];
-    uint32_t i = __ldg(&A.bin_first[s][g >> SD_BIN_SHIFT]);
     uint32_t last_seg = 0xFFFFFFFFu;
     while (i < nU) {
-        const uint4 u = __ldg(&ut[i]);   // {start, end, row, seg}
         if (u.x >= e) break;
         if (u.y > g) {
             uint32_t cov_t = pop_t, conv = (uint32_t)tc;
@@ -579,6 +594,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             }
         }
         i++;
+        if (i < nU) u = __ldg(&ut[i]);
     }
     return tc;
 }
@@ -596,6 +612,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 // so it is fetched from global memory right there -- this keeps the shared-memory footprint per
 // warp small enough for high occupancy and leaves most of the qual column's DRAM sectors untouched.
 // ---------------------------------------------------------------------------------------
+// @region kernel_setup
 #define SD_SMEM_STATS 8
 #define SD_TILE_READS 32
 
@@ -610,6 +627,7 @@ __global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ C
     unsigned char *mine = smem + 128u + (size_t)warp * warp_bytes;
     unsigned char *stages = mine;
     uint64_t *full = reinterpret_cast<uint64_t *>(mine + (size_t)A.n_stages * stage_bytes);   // [n_stages]
+    unsigned long long *s_qoff = reinterpret_cast<unsigned long long *>(mine + (size_t)A.n_stages * stage_bytes + 64u);  // [n_stages]
     uint32_t *scratch = reinterpret_cast<uint32_t *>(mine + (size_t)A.n_stages * stage_bytes + 128u) + lane * (W + 1);
 
     if (tid < SD_SMEM_STATS) s_stats[tid] = 0u;
@@ -621,6 +639,7 @@ __global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ C
 
     const uint64_t gw = (uint64_t)blockIdx.x * nwarp + warp, total_warps = (uint64_t)gridDim.x * nwarp;
 
+    // @region tma_issue
     auto issue = [&](uint64_t tile, uint32_t stage) {
         unsigned char *base = stages + (size_t)stage * stage_bytes;
         const sd_tile t0 = A.tiles[tile], t1 = A.tiles[tile + 1];
@@ -628,6 +647,7 @@ __global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ C
         const uint32_t b_seq = (uint32_t)(t1.seq_off - t0.seq_off);
         const uint32_t b_cig = (uint32_t)(t1.cig_off - t0.cig_off);
         const uint32_t b_mp = A.mp ? (uint32_t)(t1.mp_off - t0.mp_off) : 0u;
+        s_qoff[stage] = t0.qual_off;
         mbar_arrive_expect_tx(&full[stage], b_rec + b_seq + b_cig + b_mp);
         bulk_g2s(base, reinterpret_cast<const unsigned char *>(A.rec) + tile * b_rec, b_rec, &full[stage]);
         if (b_seq) bulk_g2s(base + A.cap_rec, reinterpret_cast<const unsigned char *>(A.seq) + t0.seq_off, b_seq, &full[stage]);
@@ -645,6 +665,7 @@ __global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ C
         }
     }
 
+    // @region tile_wait_rec
     uint32_t my_counted = 0, my_slow = 0, my_disagree = 0;
     unsigned long long my_tc_total = 0;
     uint32_t stage = 0, phase = 0;
@@ -658,6 +679,7 @@ __global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ C
         const uint32_t lseq = rw[3] & 0xFFFFu, ncig = rw[3] >> 16;
         const uint32_t nm = rw[4] & 0xFFFFu, nmp = A.mp ? (rw[4] >> 16) : 0u;
 
+        // @region row_scan
         // row offsets inside the tile: exclusive warp scan of the row sizes
         const uint32_t x = ((lseq + 7u) >> 3) | (ncig << 16);   // seq words | ncig << 16
         uint32_t xs = x, qs = lseq, ms = nmp;
@@ -676,6 +698,7 @@ __global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ C
         qs -= lseq;
         ms -= nmp;
 
+        // @region filter
         const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu, ref = rmf & 0xFFFFu;
         bool go = !(flags & SD_F_PAD);
         if (go && A.filter_on) {
@@ -691,13 +714,14 @@ __global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ C
         if (flags & (SD_F_UNMAPPED | SD_F_SKIP)) go = false;
         if (ref >= A.n_chrom) go = false;
 
+        // @region view_setup
         int tc = 0;
         if (go) {
             const uint32_t clen = __ldg(&A.chrom_len[ref]);
             if (pos >= 0 && (uint32_t)pos < clen) {
                 ReadView v;
                 v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (xs & 0xFFFFu);
-                v.qual = A.qual + __ldg(&A.tiles[tile].qual_off) + qs;
+                v.qual = A.qual + s_qoff[stage] + qs;
                 v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + (xs >> 16);
                 v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
                 v.lseq = lseq;
@@ -730,6 +754,7 @@ __global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ C
         }
         if (A.read_tc) A.read_tc[tile * SD_TILE_READS + lane] = (uint8_t)(tc > 255 ? 255 : tc);
 
+        // @region tile_end
         __syncwarp();   // every lane is done with this stage
         if (lane == 0) {
             const uint64_t next = tile + (uint64_t)A.n_stages * total_warps;
@@ -741,6 +766,7 @@ __global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ C
         }
     }
 
+    // @region kernel_tail
     // flush run-level counters
     my_counted = __reduce_add_sync(0xFFFFFFFFu, my_counted);
     my_slow = __reduce_add_sync(0xFFFFFFFFu, my_slow);
