@@ -366,7 +366,7 @@ __device__ __forceinline__ int block_read_index(const Blocks &B, int o) {
 
 template <int W>
 __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, const Blocks &B, uint32_t mapq,
-                                         uint32_t *scratch, bool &mp_disagree) {
+                                         bool &mp_disagree) {
     const int s = v.strand;
     const uint32_t g = v.g, e = v.g + (uint32_t)v.span;
     const uint32_t nU = A.n_u[s];
@@ -440,7 +440,9 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                 }
             }
         } else {
-            // generic placement through a scratch copy of the read mask
+            // generic placement through a scratch copy of the read mask (dynamically indexed, so it lives in
+            // local memory; only alignments with > 3 match blocks or shifts >= 32 come here)
+            uint32_t scratch[W + 1];
 #pragma unroll
             for (int k = 0; k < W; k++) {
                 R[k] = 0u;
@@ -615,12 +617,15 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 // @region kernel_setup
 #define SD_SMEM_STATS 8
 #define SD_TILE_READS 32
+#ifndef SD_MIN_CTAS
+#define SD_MIN_CTAS(W) ((W) == 4 ? 4 : ((W) == 8 ? 3 : 1))   // resident 256-thread CTAs per SM the register budget is tuned for
+#endif
 
 template <int W>
-__global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ CountArgs A) {
+__global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __grid_constant__ CountArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
-    const uint32_t warp_bytes = A.n_stages * stage_bytes + 128u + 32u * (W + 1) * 4u;   // stages | barriers | scratch
+    const uint32_t warp_bytes = A.n_stages * stage_bytes + 128u;   // stages | barriers + tile qual offsets
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t nwarp = blockDim.x >> 5;
     uint32_t *s_stats = reinterpret_cast<uint32_t *>(smem);                 // [SD_SMEM_STATS], first 128 bytes
@@ -628,7 +633,6 @@ __global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ C
     unsigned char *stages = mine;
     uint64_t *full = reinterpret_cast<uint64_t *>(mine + (size_t)A.n_stages * stage_bytes);   // [n_stages]
     unsigned long long *s_qoff = reinterpret_cast<unsigned long long *>(mine + (size_t)A.n_stages * stage_bytes + 64u);  // [n_stages]
-    uint32_t *scratch = reinterpret_cast<uint32_t *>(mine + (size_t)A.n_stages * stage_bytes + 128u) + lane * (W + 1);
 
     if (tid < SD_SMEM_STATS) s_stats[tid] = 0u;
     if (lane == 0) {
@@ -743,7 +747,7 @@ __global__ void __launch_bounds__(256) sd_count_kernel(const __grid_constant__ C
                 my_counted++;
                 if (fits) {
                     bool bad = false;
-                    tc = fast_read<W>(A, v, B, mapq, scratch, bad);
+                    tc = fast_read<W>(A, v, B, mapq, bad);
                     my_disagree += bad ? 1u : 0u;
                 } else {
                     my_slow++;
@@ -1115,6 +1119,7 @@ extern "C" int sd_bind_outputs(sd_ctx *ctx, int64_t *d_counters, int32_t *d_pos_
 }
 
 static inline uint32_t align128(uint32_t x) { return (x + 127u) & ~127u; }
+static inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
 template <int W>
 static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
@@ -1130,7 +1135,7 @@ static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool tim
     }
     // per-warp ring of n_stages tiles; as many warps per CTA (<= 8) as the shared memory allows
     uint32_t n_stages = (forced_stages >= 1 && forced_stages <= 8) ? (uint32_t)forced_stages : 2u;
-    auto warp_bytes = [&](uint32_t ns) { return (size_t)ns * stage_bytes + 128u + 32u * (W + 1) * 4u; };
+    auto warp_bytes = [&](uint32_t ns) { return (size_t)ns * stage_bytes + 128u; };
     if (128u + warp_bytes(n_stages) > (size_t)max_smem) n_stages = 1;
     if (128u + warp_bytes(n_stages) > (size_t)max_smem)
         return sd_fail(ctx, SD_ERR_LIMIT, "a 32-read tile needs %u bytes of shared memory; reads are too long for this kernel", stage_bytes);
@@ -1169,11 +1174,15 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     A.rec = b->rec; A.seq = b->seq; A.qual = b->qual; A.cigar = b->cigar;
     A.mp = (p->mismatch_source == SD_MISMATCH_CIGAR) ? nullptr : b->mp;
     A.tiles = b->tiles; A.n_tiles = b->n_tiles; A.tile_reads = b->tile_reads;
-    A.cap_rec = align128(32u * (uint32_t)sizeof(sd_read_rec));
-    A.cap_seq = align128(b->max_tile_seq);
+    A.cap_rec = align16(32u * (uint32_t)sizeof(sd_read_rec));
+    A.cap_seq = align16(b->max_tile_seq);
     A.cap_qual = 0;  // the qual column is read in place (see the kernel's header comment)
-    A.cap_cig = align128(b->max_tile_cig);
-    A.cap_mp = A.mp ? align128(b->max_tile_mp) : 0;
+    A.cap_cig = align16(b->max_tile_cig);
+    A.cap_mp = A.mp ? align16(b->max_tile_mp) : 0;
+    {   // keep every warp's region 128-byte aligned
+        const uint32_t sum = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
+        A.cap_cig += align128(sum) - sum;
+    }
     for (int s = 0; s < 2; s++) {
         A.refx[s] = ctx->refx[s];
         A.ustart[s] = ctx->d_ustart[s]; A.uend[s] = ctx->d_uend[s]; A.urow[s] = ctx->d_urow[s]; A.useg[s] = ctx->d_useg[s];
