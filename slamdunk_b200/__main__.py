@@ -1,3 +1,3 @@
-from .slamdunk import run
+from .cli import run
 
 run()

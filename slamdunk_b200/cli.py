@@ -18,7 +18,7 @@ from argparse import SUPPRESS, ArgumentDefaultsHelpFormatter, ArgumentParser
 from os.path import basename
 from time import sleep
 
-from .utils.misc import checkStep, replaceExtension
+from .utils.samheader import checkStep, replaceExtension
 from .version import __ngm_version__, __version__
 
 mainOutput = sys.stderr
@@ -291,88 +291,92 @@ def runAll(args):
     dunkFinished()
 
 
+# ---------------------------------------------------------------------------------------------
+# Argument surface.  Flags, destinations, types and defaults are those of the reference CLI
+# (slamdunk/slamdunk.py:345-430) so existing command lines keep working; they are kept as data.
+# (flags, dest, type, default, required, help) ; type "flag" = store_true ; default SUPPRESS = absent unless given
+# ---------------------------------------------------------------------------------------------
+_S = SUPPRESS
+_SAMPLE_OPTS = [
+    (("-sn", "--sampleName"), "sampleName", str, None, False, "sample name used for every input"),
+    (("-sy", "--sampleType"), "sampleType", str, "pulse", False, "sample type used for every input"),
+    (("-st", "--sampleTime"), "sampleTime", int, 0, False, "sample time used for every input"),
+    (("-i", "--sample-index"), "sampleIndex", int, -1, False, "process only sample <i> (1-based), for cluster arrays"),
+    (("-ss", "--skip-sam"), "skipSAM", "flag", False, False, "let the mapper write BAM directly"),
+]
+_MAP_OPTS = [
+    (("-5", "--trim-5p"), "trim5", int, 12, False, "bases trimmed from the 5' end of every read"),
+    (("-n", "--topn"), "topn", int, 1, False, "alignments reported per read"),
+    (("-a", "--max-polya"), "maxPolyA", int, 4, False, "As tolerated at the 3' end"),
+    (("-t", "--threads"), "threads", int, 1, False, "threads"),
+    (("-q", "--quantseq"), "quantseq", "flag", False, False, "plain QuantSeq alignment (no SLAM-seq scoring)"),
+    (("-e", "--endtoend"), "endtoend", "flag", False, False, "end-to-end instead of local alignment"),
+]
+_FILTER_OPTS = [
+    (("-mq", "--min-mq"), "mq", int, 2, False, "minimum mapping quality"),
+    (("-mi", "--min-identity"), "identity", float, 0.95, False, "minimum alignment identity"),
+    (("-nm", "--max-nm"), "nm", int, -1, False, "maximum NM per alignment (-1: off)"),
+]
+_COUNT_OPTS = [
+    (("-c", "--conversion-threshold"), "conversionThreshold", int, 1, False, "T>C conversions that make a read a T>C read"),
+    (("-q", "--min-base-qual"), "minQual", int, 27, False, "minimum base quality of a counted conversion"),
+]
+SUBCOMMANDS = {
+    "map": dict(help="Map SLAM-seq read data", positional=("files", "sample sheet (csv/tsv) or read files"), options=[
+        (("-r", "--reference"), "referenceFile", str, _S, True, "reference FASTA"),
+        (("-o", "--outputDir"), "outputDir", str, _S, True, "output directory"),
+    ] + _MAP_OPTS + _SAMPLE_OPTS),
+    "filter": dict(help="Filter SLAM-seq aligned data", positional=("bam", "BAM file(s)"), options=[
+        (("-o", "--outputDir"), "outputDir", str, None, True, "output directory"),
+        (("-b", "--bed"), "bed", str, None, False, "BED file: switches to multimapper retention (no MQ cut)"),
+    ] + _FILTER_OPTS + [(("-t", "--threads"), "threads", int, 1, False, "host decode threads")]),
+    "snp": dict(help="Call SNPs on SLAM-seq aligned data", positional=("bam", "BAM file(s)"), options=[
+        (("-o", "--outputDir"), "outputDir", str, _S, True, "output directory"),
+        (("-r", "--reference"), "fasta", str, _S, True, "reference FASTA"),
+        (("-c", "--min-coverage"), "cov", int, 10, False, "minimum coverage of a variant"),
+        (("-f", "--var-fraction"), "var", float, 0.8, False, "minimum variant fraction"),
+        (("-t", "--threads"), "threads", int, 1, False, "threads"),
+    ]),
+    "count": dict(help="Count T/C conversions in SLAM-seq aligned data", positional=("bam", "BAM file(s)"), options=[
+        (("-o", "--outputDir"), "outputDir", str, _S, True, "output directory"),
+        (("-s", "--snp-directory"), "snpDir", str, _S, False, "directory with <sample>_snp.vcf files"),
+        (("-v", "--vcf"), "vcfFile", str, _S, False, "one variant file for all samples"),
+        (("-r", "--reference"), "ref", str, _S, True, "reference FASTA"),
+        (("-b", "--bed"), "bed", str, _S, True, "BED file of the 3' UTRs"),
+        (("-l", "--max-read-length"), "maxLength", int, None, False, "maximum read length in the BAM"),
+        (("-t", "--threads"), "threads", int, 1, False, "host decode threads"),
+    ] + _COUNT_OPTS),
+    "all": dict(help="Run entire SLAMdunk analysis", positional=("files", "sample sheet (csv/tsv) or read files"), options=[
+        (("-r", "--reference"), "referenceFile", str, None, True, "reference FASTA"),
+        (("-b", "--bed"), "bed", str, None, True, "BED file of the 3' UTRs"),
+        (("-fb", "--filterbed"), "filterbed", str, None, False, "BED file for multimapper retention (implies -m)"),
+        (("-v", "--vcf"), "vcfFile", str, _S, False, "skip SNP calling, use this variant file"),
+        (("-o", "--outputDir"), "outputDir", str, None, True, "output directory"),
+        (("-m", "--multimap"), "multimap", "flag", False, False, "resolve multimappers with the annotation (needs -n > 1)"),
+        (("-mc", "--min-coverage"), "cov", int, 10, False, "minimum coverage of a variant"),
+        (("-mv", "--var-fraction"), "var", float, 0.8, False, "minimum variant fraction"),
+        (("-c", "--conversion-threshold"), "conversionThreshold", int, 1, False, "T>C conversions that make a read a T>C read"),
+        (("-rl", "--max-read-length"), "maxLength", int, None, False, "maximum read length in the BAM"),
+        (("-mbq", "--min-base-qual"), "minQual", int, 27, False, "minimum base quality of a counted conversion"),
+    ] + _MAP_OPTS + _FILTER_OPTS + _SAMPLE_OPTS),
+}
+
+
 def build_parser():
-    """Argument surface of slamdunk.py:336-430, verbatim, plus the opt-in GPU knobs."""
-    usage = "SLAMdunk software for analyzing SLAM-seq data"
-    parser = ArgumentParser(description=usage, formatter_class=ArgumentDefaultsHelpFormatter)
+    parser = ArgumentParser(description="SLAMdunk software for analyzing SLAM-seq data", formatter_class=ArgumentDefaultsHelpFormatter)
     parser.add_argument("--version", action="version", version="%(prog)s " + __version__)
     parser.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
     parser.add_argument("--mismatch-source", default="verify", choices=["verify", "cigar", "mp"], dest="mismatchSource",
-                        help="where per-read mismatches come from: CIGAR walk cross-checked against the MP tags, CIGAR walk only, or MP tags only")
-    subparsers = parser.add_subparsers(help="", dest="command")
-
-    mapparser = subparsers.add_parser("map", help="Map SLAM-seq read data", formatter_class=ArgumentDefaultsHelpFormatter)
-    mapparser.add_argument("files", action="store", help="Single csv/tsv file (recommended) containing all sample files and sample info or a list of all sample BAM/FASTA(gz)/FASTQ(gz) files", nargs="+")
-    mapparser.add_argument("-r", "--reference", type=str, required=True, dest="referenceFile", default=SUPPRESS, help="Reference fasta file")
-    mapparser.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", default=SUPPRESS, help="Output directory for mapped BAM files.")
-    mapparser.add_argument("-5", "--trim-5p", type=int, required=False, dest="trim5", default=12, help="Number of bp removed from 5' end of all reads.")
-    mapparser.add_argument("-n", "--topn", type=int, required=False, dest="topn", default=1, help="Max. number of alignments to report per read")
-    mapparser.add_argument("-a", "--max-polya", type=int, required=False, dest="maxPolyA", default=4, help="Max number of As at the 3' end of a read.")
-    mapparser.add_argument("-t", "--threads", type=int, required=False, dest="threads", default=1, help="Thread number")
-    mapparser.add_argument("-q", "--quantseq", dest="quantseq", action="store_true", required=False, help="Run plain Quantseq alignment without SLAM-seq scoring")
-    mapparser.add_argument("-e", "--endtoend", action="store_true", dest="endtoend", help="Use a end to end alignment algorithm for mapping.")
-    mapparser.add_argument("-sn", "--sampleName", type=str, dest="sampleName", required=False, help="Use this sample name for all supplied samples")
-    mapparser.add_argument("-sy", "--sampleType", type=str, dest="sampleType", required=False, default="pulse", help="Use this sample type for all supplied samples")
-    mapparser.add_argument("-st", "--sampleTime", type=int, dest="sampleTime", required=False, default=0, help="Use this sample time for all supplied samples")
-    mapparser.add_argument("-i", "--sample-index", type=int, required=False, default=-1, dest="sampleIndex", help="Run analysis only for sample <i>. Use for distributing slamdunk analysis on a cluster (index is 1-based).")
-    mapparser.add_argument("-ss", "--skip-sam", action="store_true", dest="skipSAM", help="Output BAM while mapping. Slower but, uses less hard disk.")
-
-    filterparser = subparsers.add_parser("filter", help="Filter SLAM-seq aligned data")
-    filterparser.add_argument("bam", action="store", help="Bam file(s)", nargs="+")
-    filterparser.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", help="Output directory for mapped BAM files.")
-    filterparser.add_argument("-b", "--bed", type=str, required=False, dest="bed", help="BED file, overrides MQ filter to 0")
-    filterparser.add_argument("-mq", "--min-mq", type=int, required=False, default=2, dest="mq", help="Minimum mapping quality (default: %(default)d)")
-    filterparser.add_argument("-mi", "--min-identity", type=float, required=False, default=0.95, dest="identity", help="Minimum alignment identity (default: %(default)s)")
-    filterparser.add_argument("-nm", "--max-nm", type=int, required=False, default=-1, dest="nm", help="Maximum NM for alignments (default: %(default)d)")
-    filterparser.add_argument("-t", "--threads", type=int, required=False, dest="threads", default=1, help="Thread number (default: %(default)d)")
-
-    snpparser = subparsers.add_parser("snp", help="Call SNPs on SLAM-seq aligned data", formatter_class=ArgumentDefaultsHelpFormatter)
-    snpparser.add_argument("bam", action="store", help="Bam file(s)", nargs="+")
-    snpparser.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", default=SUPPRESS, help="Output directory for mapped BAM files.")
-    snpparser.add_argument("-r", "--reference", required=True, dest="fasta", type=str, default=SUPPRESS, help="Reference fasta file")
-    snpparser.add_argument("-c", "--min-coverage", required=False, dest="cov", type=int, help="Minimimum coverage to call variant", default=10)
-    snpparser.add_argument("-f", "--var-fraction", required=False, dest="var", type=float, help="Minimimum variant fraction to call variant", default=0.8)
-    snpparser.add_argument("-t", "--threads", type=int, required=False, default=1, dest="threads", help="Thread number")
-
-    countparser = subparsers.add_parser("count", help="Count T/C conversions in SLAM-seq aligned data")
-    countparser.add_argument("bam", action="store", help="Bam file(s)", nargs="+")
-    countparser.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", default=SUPPRESS, help="Output directory for mapped BAM files.")
-    countparser.add_argument("-s", "--snp-directory", type=str, required=False, dest="snpDir", default=SUPPRESS, help="Directory containing SNP files.")
-    countparser.add_argument("-v", "--vcf", type=str, required=False, dest="vcfFile", default=SUPPRESS, help="Externally provided custom variant file.")
-    countparser.add_argument("-r", "--reference", type=str, required=True, dest="ref", default=SUPPRESS, help="Reference fasta file")
-    countparser.add_argument("-b", "--bed", type=str, required=True, dest="bed", default=SUPPRESS, help="BED file")
-    countparser.add_argument("-c", "--conversion-threshold", type=int, dest="conversionThreshold", required=False, default=1, help="Number of T>C conversions required to count read as T>C read (default: %(default)d)")
-    countparser.add_argument("-l", "--max-read-length", type=int, required=False, dest="maxLength", help="Max read length in BAM file")
-    countparser.add_argument("-q", "--min-base-qual", type=int, default=27, required=False, dest="minQual", help="Min base quality for T -> C conversions (default: %(default)d)")
-    countparser.add_argument("-t", "--threads", type=int, required=False, default=1, dest="threads", help="Thread number (default: %(default)d)")
-
-    allparser = subparsers.add_parser("all", help="Run entire SLAMdunk analysis")
-    allparser.add_argument("files", action="store", help="Single csv/tsv file (recommended) containing all sample files and sample info or a list of all sample BAM/FASTA(gz)/FASTQ(gz) files", nargs="+")
-    allparser.add_argument("-r", "--reference", type=str, required=True, dest="referenceFile", help="Reference fasta file")
-    allparser.add_argument("-b", "--bed", type=str, required=True, dest="bed", help="BED file with 3'UTR coordinates")
-    allparser.add_argument("-fb", "--filterbed", type=str, required=False, dest="filterbed", help="BED file with 3'UTR coordinates to filter multimappers (activates -m)")
-    allparser.add_argument("-v", "--vcf", type=str, required=False, dest="vcfFile", default=SUPPRESS, help="Skip SNP step and provide custom variant file.")
-    allparser.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", help="Output directory for slamdunk run.")
-    allparser.add_argument("-5", "--trim-5p", type=int, required=False, dest="trim5", default=12, help="Number of bp removed from 5' end of all reads (default: %(default)s)")
-    allparser.add_argument("-a", "--max-polya", type=int, required=False, dest="maxPolyA", default=4, help="Max number of As at the 3' end of a read (default: %(default)s)")
-    allparser.add_argument("-n", "--topn", type=int, required=False, dest="topn", default=1, help="Max. number of alignments to report per read (default: %(default)s)")
-    allparser.add_argument("-t", "--threads", type=int, required=False, default=1, dest="threads", help="Thread number (default: %(default)s)")
-    allparser.add_argument("-q", "--quantseq", dest="quantseq", action="store_true", required=False, help="Run plain Quantseq alignment without SLAM-seq scoring")
-    allparser.add_argument("-e", "--endtoend", action="store_true", dest="endtoend", help="Use a end to end alignment algorithm for mapping.")
-    allparser.add_argument("-m", "--multimap", action="store_true", dest="multimap", help="Use reference to resolve multimappers (requires -n > 1).")
-    allparser.add_argument("-mq", "--min-mq", type=int, required=False, default=2, dest="mq", help="Minimum mapping quality (default: %(default)s)")
-    allparser.add_argument("-mi", "--min-identity", type=float, required=False, default=0.95, dest="identity", help="Minimum alignment identity (default: %(default)s)")
-    allparser.add_argument("-nm", "--max-nm", type=int, required=False, default=-1, dest="nm", help="Maximum NM for alignments (default: %(default)s)")
-    allparser.add_argument("-mc", "--min-coverage", required=False, dest="cov", type=int, help="Minimimum coverage to call variant (default: %(default)s)", default=10)
-    allparser.add_argument("-mv", "--var-fraction", required=False, dest="var", type=float, help="Minimimum variant fraction to call variant (default: %(default)s)", default=0.8)
-    allparser.add_argument("-c", "--conversion-threshold", type=int, dest="conversionThreshold", required=False, default=1, help="Number of T>C conversions required to count read as T>C read (default: %(default)d)")
-    allparser.add_argument("-rl", "--max-read-length", type=int, required=False, dest="maxLength", help="Max read length in BAM file")
-    allparser.add_argument("-mbq", "--min-base-qual", type=int, default=27, required=False, dest="minQual", help="Min base quality for T -> C conversions (default: %(default)d)")
-    allparser.add_argument("-sn", "--sampleName", type=str, dest="sampleName", required=False, help="Use this sample name for all supplied samples")
-    allparser.add_argument("-sy", "--sampleType", type=str, dest="sampleType", required=False, default="pulse", help="Use this sample type for all supplied samples")
-    allparser.add_argument("-st", "--sampleTime", type=int, dest="sampleTime", required=False, default=0, help="Use this sample time for all supplied samples")
-    allparser.add_argument("-i", "--sample-index", type=int, required=False, default=-1, dest="sampleIndex", help="Run analysis only for sample <i>. Use for distributing slamdunk analysis on a cluster (index is 1-based).")
-    allparser.add_argument("-ss", "--skip-sam", action="store_true", dest="skipSAM", help="Output BAM while mapping. Slower but, uses less hard disk.")
+                        help="per-read mismatches from: CIGAR walk cross-checked against the MP tags, CIGAR walk only, MP tags only")
+    sub = parser.add_subparsers(help="", dest="command")
+    for name, spec in SUBCOMMANDS.items():
+        sp = sub.add_parser(name, help=spec["help"], formatter_class=ArgumentDefaultsHelpFormatter)
+        sp.add_argument(spec["positional"][0], action="store", nargs="+", help=spec["positional"][1])
+        for flags, dest, typ, default, required, helptext in spec["options"]:
+            if typ == "flag":
+                sp.add_argument(*flags, dest=dest, action="store_true", required=False, help=helptext)
+            else:
+                sp.add_argument(*flags, dest=dest, type=typ, default=default, required=required, help=helptext)
     return parser
 
 

@@ -17,8 +17,8 @@ import numpy as np
 from .. import _lib as L
 from ..engine import CountEngine, DeviceBatch, HostBatch, make_params
 from ..io import bam as bamio
-from ..utils.BedReader import BedIterator
-from ..utils.misc import SlamSeqInfo, checkStep, md5
+from ..utils.bed import BedIterator
+from ..utils.samheader import SlamSeqInfo, checkStep, md5
 from ..version import __bam_version__, __version__
 
 OPTIONS = {"device": 0, "threads": 0, "stats": None}

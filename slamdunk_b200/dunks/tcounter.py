@@ -18,9 +18,9 @@ import numpy as np
 from .. import _lib as L
 from .. import parallel
 from ..engine import CountEngine, HostBatch, HostGenome, make_params
-from ..utils.BedReader import BedIterator
-from ..utils.SNPtools import build_snp_masks
-from ..utils.misc import SlamSeqInfo, getSampleInfo, md5, parse_sam_header
+from ..utils.bed import BedIterator
+from ..utils.snpmask import build_snp_masks
+from ..utils.samheader import SlamSeqInfo, getSampleInfo, md5, parse_sam_header
 from ..version import __bam_version__, __count_version__, __version__
 
 HEADER = "\t".join(["Chromosome", "Start", "End", "Name", "Length", "Strand", "ConversionRate", "ReadsCPM", "Tcontent",

@@ -8,7 +8,7 @@ import goldens
 
 
 def _ns(argv):
-    from slamdunk_b200.slamdunk import build_parser
+    from slamdunk_b200.cli import build_parser
     return build_parser().parse_args(argv)
 
 
@@ -35,7 +35,7 @@ def test_filter_and_all_defaults_match_reference():
 def test_estimate_max_read_length(tmp_path):
     """utils/misc.py:91-107"""
     from slamdunk_b200.io import bam as bamio
-    from slamdunk_b200.slamdunk import estimateMaxReadLength
+    from slamdunk_b200.cli import estimateMaxReadLength
     recs = [bamio.BamRecord("r%d" % i, 0, 0, 10 + i, 60, "%dM" % (50 + i % 5), "A" * (50 + i % 5), [30] * (50 + i % 5), [("XA", "i", 2)])
             for i in range(1500)]
     p = str(tmp_path / "a.bam")
@@ -50,7 +50,7 @@ def test_estimate_max_read_length(tmp_path):
 @pytest.mark.gpu
 def test_count_cli_end_to_end(tmp_path):
     """`slamdunk count` file naming (slamdunk.py:180-183) and content on the reference's own sample."""
-    from slamdunk_b200.slamdunk import run
+    from slamdunk_b200.cli import run
     c = goldens.CountCase("cfg1")
     out = str(tmp_path / "count")
     run(["count", "-r", c.ref, "-b", c.bed, "-o", out, "-l", "100", "-q", "27", c.bam])

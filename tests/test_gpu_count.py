@@ -51,8 +51,8 @@ def _engine_run(case_files, min_qual, thr, mode, force_slow=False, tile_reads=32
     import torch
     from slamdunk_b200 import _lib as L
     from slamdunk_b200.engine import CountEngine, DeviceBatch, HostBatch, HostGenome, make_params
-    from slamdunk_b200.utils.BedReader import BedIterator
-    from slamdunk_b200.utils.SNPtools import build_snp_masks
+    from slamdunk_b200.utils.bed import BedIterator
+    from slamdunk_b200.utils.snpmask import build_snp_masks
     ref, bed, vcf, bam = case_files
     g = HostGenome(ref)
     hb = HostBatch(bam, g.names, want_mp=True, tile_reads=tile_reads)

@@ -151,3 +151,55 @@ def test_filter_predicates_fused_into_count():
                                    27, 1, None, mp_triples=mp, threads=4)
     assert ob.compare(res, rows, bg, wl.ann, eng.pos_off, wl.chrom_off) == []
     eng.close()
+
+
+def test_snp_masks_at_scale_including_key_collisions():
+    """cfg4-style: a dense VCF (1 SNP / 500 bp of annotated sequence) on chromosomes whose names collide under
+    the reference's chrom+pos string key (chr1 / chr12 / chr19 ..., utils/SNPtools.py:33,54), 250 bp reads, 15 % mapq 0."""
+    from slamdunk_b200.engine import make_params
+    from slamdunk_b200.utils.snpmask import SNPMasks
+    eng, wl = _setup(genome_bp=2_500_000, n_utr=500, seed=8)
+    rng = np.random.RandomState(4)
+    lo = wl.lo.cpu().numpy().view(np.uint32)
+    hi = wl.hi.cpu().numpy().view(np.uint32)
+    nm = wl.nmask.cpu().numpy().view(np.uint32)
+    g = ob.genome_from_planes(wl.names, wl.chrom_off, wl.chrom_len, lo, hi, nm)
+    records = []
+    for u in range(len(wl.ann)):
+        c, s, e = int(wl.ann.chrom[u]), int(wl.ann.start[u]), int(wl.ann.stop[u])
+        seq = g.seqs[c]
+        for p in rng.randint(s, e, size=max(1, (e - s) // 500)):
+            b = chr(seq[p])
+            if b == "T":
+                records.append((wl.names[c], str(p + 1), "T", rng.choice(["C", "C", "G", "C,A"])))
+            elif b == "A":
+                records.append((wl.names[c], str(p + 1), "A", rng.choice(["G", "G", "g", "T"])))
+    # positions on chr1x that alias positions on chr1 under the string key: 'chr1' + '2345' == 'chr12' + '345'
+    for c, name in enumerate(wl.names):
+        if name.startswith("chr1") and len(name) == 5:
+            for p in rng.randint(1, min(int(wl.chrom_len[c]), 9999), size=300):
+                records.append((name, str(p), "T", "C"))
+                records.append((name, str(p), "A", "G"))
+    sm = SNPMasks(wl.names, wl.chrom_off, wl.chrom_len, wl.n_words)
+    for r in records:
+        sm.add(*r)
+    tcm, agm = sm.masks()
+    assert sm.n_tc > len([r for r in records if r[2] == "T" and r[3] == "C"]) * 0.5
+    eng.set_snps(tcm, agm)
+    n = 60_000
+    db, triples = wl.generate(wl.params(seed=77, first_read=0, n_reads=n, read_len=250, frac_multimap=0.15, p_conv=0.03),
+                              want_mp=True, want_triples=True, coordinate_sorted=True)
+    eng.count(db, make_params(27, 1, 2))
+    eng.finalize()
+    res = eng.results()
+    reads, qual, mp = ob.batch_to_oracle(ob.device_batch_to_numpy(db), triples.cpu().numpy())
+    h = oracle.make_snps(records)
+    try:
+        rows, bg = oracle.count_arrays(g, reads, qual, ob.annotation_to_oracle(wl.ann, len(wl.names)), 27, 1, h, mp_triples=mp, threads=4)
+        rows0, _ = oracle.count_arrays(g, reads, qual, ob.annotation_to_oracle(wl.ann, len(wl.names)), 27, 1, None, mp_triples=mp, threads=4)
+    finally:
+        oracle.free_snps(h)
+    assert rows0["conversions_on_ts"].sum() > rows["conversions_on_ts"].sum() > 0      # the mask removes conversions
+    assert rows["multimap_count"].sum() > 0
+    assert ob.compare(res, rows, bg, wl.ann, eng.pos_off, wl.chrom_off) == []
+    eng.close()

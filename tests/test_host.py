@@ -12,7 +12,7 @@ import goldens
 import simdata
 from slamdunk_b200 import _lib as L
 from slamdunk_b200.io import bam as bamio
-from slamdunk_b200.utils import SNPtools
+from slamdunk_b200.utils import snpmask as SNPtools
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -203,7 +203,7 @@ def test_snp_masks_reproduce_string_key_collisions():
 
 
 def test_bed_reader_quirks(tmp_path):
-    from slamdunk_b200.utils.BedReader import BedIterator
+    from slamdunk_b200.utils.bed import BedIterator
     p = str(tmp_path / "a.bed")
     open(p, "w").write("chr1\t5\t10\tn1\t0\t+\nchr1\t7\t9\tn2\nchr2\t1\t2\tn3\t.\t-\textra\n")
     rows = list(BedIterator(p))
