@@ -240,9 +240,13 @@ int sd_filter(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params, con
  * layout above, FASTA into bit-planes.  Buffers are page-locked and owned by the returned
  * object; free with the matching *_free.
  */
+#define SD_DECODE_MP 1
+#define SD_DECODE_GROUP 2
+
 typedef struct sd_hbatch {
     sd_batch batch;          /* host pointers */
-    uint64_t *name_hash;     /* [n_reads] 64-bit hash of the query name (filter multimapper pass) */
+    uint64_t *name_hash;     /* [n_reads] 64-bit hash of the query name, in FILE order (filter multimapper pass) */
+    uint32_t *order;         /* [n_reads] batch slot -> index of the record in the file (identity unless grouped) */
     char *header_text;       /* SAM header text, NUL-terminated */
     uint32_t n_ref;          /* BAM reference sequences */
     char **ref_names;
@@ -256,9 +260,11 @@ typedef struct sd_hbatch {
 
 /* fasta_names / n_fasta: chromosome table of the FASTA (index = sd_read_rec ref field); n_fasta = 0:
  * the ref field is the BAM reference id itself (what sd_filter works in).
- * want_mp: also decode MP tags into the mp column.  tile_reads: 32 (0 = default).
+ * options: SD_DECODE_MP also decodes the MP tags into the mp column; SD_DECODE_GROUP orders the batch by
+ * alignment shape and strand (plain single-match-block reads first, each group in file order) so that the
+ * count kernel's warps are homogeneous -- use file order (no grouping) for sd_filter.  tile_reads: 32 (0 = default).
  * threads <= 0: hardware concurrency. */
-int sd_decode_bam(const char *path, const char *const *fasta_names, uint32_t n_fasta, int want_mp,
+int sd_decode_bam(const char *path, const char *const *fasta_names, uint32_t n_fasta, int options,
                   uint32_t tile_reads, int threads, sd_hbatch **out, char *err, int errlen);
 void sd_hbatch_free(sd_hbatch *hb);
 
@@ -315,9 +321,10 @@ typedef struct sd_synth_tables {
 
 #define SD_SYNTH_MAX_TRIPLES 40
 
-/* Linear genome position of every read's alignment start (placement only), device uint32[n_reads];
- * argsort it to build sd_synth_params.order.  Ignores p->order.  Synchronous. */
-int sd_synth_positions(sd_ctx *ctx, const sd_synth_params *p, const sd_synth_tables *t, uint32_t *d_gpos);
+/* Linear genome position of every read's alignment start (placement only), device uint32[n_reads], and
+ * optionally its grouping class (device uint8[n_reads]: bit 0 strand, bit 1 "not a plain match block", the
+ * classes sd_decode_bam groups by); argsort them to build sd_synth_params.order.  Ignores p->order.  Synchronous. */
+int sd_synth_positions(sd_ctx *ctx, const sd_synth_params *p, const sd_synth_tables *t, uint32_t *d_gpos, uint8_t *d_cls);
 /* Pass 1: simulate every read once to learn its CIGAR and MP entry counts.
  * d_counts: device uint32[n_reads] scratch (n_cigar | n_mp << 16), d_tiles: device sd_tile[n_tiles + 1]
  * (filled), h_totals: host uint64[4] = total bytes of the seq, qual, cigar and mp columns.  Synchronous. */

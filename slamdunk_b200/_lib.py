@@ -14,6 +14,7 @@ SD_F_HAS_MP, SD_F_SKIP, SD_F_NEWNAME, SD_F_PAD = 0x10, 0x20, 0x40, 0x80
 SD_REF_NONE = 0xFFFF
 SD_MISMATCH_CIGAR, SD_MISMATCH_MP, SD_MISMATCH_VERIFY = 0, 1, 2
 SD_NCOUNTER = 5
+SD_DECODE_MP, SD_DECODE_GROUP = 1, 2
 SD_C_READS, SD_C_TCREADS, SD_C_MULTIMAP, SD_C_COV_ON_T, SD_C_CONV_ON_T = range(5)
 SD_NSTAT = 10
 (SD_S_MAPPED, SD_S_UNMAPPED, SD_S_FILTERED, SD_S_MQFILTERED, SD_S_IDFILTERED, SD_S_NMFILTERED,
@@ -51,7 +52,7 @@ class Params(ctypes.Structure):
 
 
 class HBatch(ctypes.Structure):
-    _fields_ = [("batch", Batch), ("name_hash", c_u64p), ("header_text", ctypes.c_char_p), ("n_ref", ctypes.c_uint32),
+    _fields_ = [("batch", Batch), ("name_hash", c_u64p), ("order", c_u32p), ("header_text", ctypes.c_char_p), ("n_ref", ctypes.c_uint32),
                 ("ref_names", ctypes.POINTER(ctypes.c_char_p)), ("ref_lengths", c_u32p),
                 ("seconds_inflate", ctypes.c_double), ("seconds_decode", ctypes.c_double),
                 ("compressed_bytes", ctypes.c_uint64), ("inflated_bytes", ctypes.c_uint64), ("opaque", ctypes.c_void_p)]
@@ -110,7 +111,7 @@ PROTOTYPES = {
     "sd_load_fasta": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.POINTER(HGenome)),
                                      ctypes.c_char_p, ctypes.c_int]),
     "sd_hgenome_free": (None, [ctypes.POINTER(HGenome)]),
-    "sd_synth_positions": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP]),
+    "sd_synth_positions": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP, _VP]),
     "sd_synth_plan": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP, _VP, c_u64p]),
     "sd_synth_fill": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP,
                                      ctypes.POINTER(Batch), _VP]),

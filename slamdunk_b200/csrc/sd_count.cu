@@ -364,7 +364,9 @@ __device__ __forceinline__ int block_read_index(const Blocks &B, int o) {
     return o + B.shc;
 }
 
-template <int W>
+// SIMPLE: every read of the tile is one match block without clips (the decoder groups such reads into
+// their own tiles), so the read mask needs no placement and a window position is a read index.
+template <int W, bool SIMPLE>
 __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, const Blocks &B, uint32_t mapq,
                                          bool &mp_disagree) {
     const int s = v.strand;
@@ -391,7 +393,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
     // @region read_mask
     // --- read-side candidate mask in window coordinates
     uint32_t R[W];
-    const bool regs = B.regs_ok;
+    const bool regs = SIMPLE || B.regs_ok;
     if (A.mismatch_source == SD_MISMATCH_MP) {
 #pragma unroll
         for (int k = 0; k < W; k++) R[k] = 0u;
@@ -420,7 +422,10 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             if (4u * k + 3u < nw8) b3 = sliced_is_base(v.seq[4 * k + 3], inv);
             M[k] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
         }
-        if (regs) {
+        if (SIMPLE) {
+#pragma unroll
+            for (int k = 0; k < W; k++) R[k] = M[k];
+        } else if (regs) {
             if (B.n <= 1) {
                 // one block: bits past its end are cleared by T (masked to the span) later on
                 if (B.sha == 0) {
@@ -492,7 +497,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                     D[k] &= ~(1u << (o & 31));
                     found = true;
                 }
-            if (!found || (regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o)) != rp) bad = true;
+            if (!found || (SIMPLE ? o : (regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o))) != rp) bad = true;
         }
 #pragma unroll
         for (int k = 0; k < W; k++) bad |= (D[k] != 0u);
@@ -525,7 +530,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                 const int bit = __ffsll((long long)rest) - 1;
                 rest &= rest - 1ull;
                 const int o = 32 * k2 + bit;
-                const int qi = regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o);
+                const int qi = SIMPLE ? o : (regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o));
                 if (qi < 0 || qi >= (int)v.lseq || (int)__ldg(v.qual + qi) < A.min_qual) fail |= 1ull << bit;
             }
             H[k2] &= ~(uint32_t)fail;
@@ -718,6 +723,10 @@ __global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __g
         if (flags & (SD_F_UNMAPPED | SD_F_SKIP)) go = false;
         if (ref >= A.n_chrom) go = false;
 
+        // Is every read of this tile a single match block (no clips, no indels)?  Warp-uniform: the decoder and
+        // the generator group such reads into their own tiles, so most warps take the lean path.
+        const uint32_t cig0 = ncig ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq)[xs >> 16] : 0u;
+        const bool uni_simple = __all_sync(0xFFFFFFFFu, !go || (ncig == 1u && ((0x181u >> (cig0 & 15u)) & 1u)));
         // @region view_setup
         int tc = 0;
         if (go) {
@@ -735,7 +744,16 @@ __global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __g
                 v.strand = (flags & SD_F_REVERSE) ? 1 : 0;
                 v.has_mp = (flags & SD_F_HAS_MP) != 0;
                 Blocks B;
-                uint32_t reflen = (uint32_t)parse_cigar(v.cig, ncig, B);
+                uint32_t reflen;
+                if (uni_simple) {   // one match block starting at window position 0
+                    B.n = 1;
+                    B.r0a = 0;
+                    B.r1a = (int)(cig0 >> 4);
+                    B.r0b = B.r1b = B.r0c = B.r1c = 0;
+                    B.sha = B.shb = B.shc = 0;
+                    B.regs_ok = true;
+                    reflen = cig0 >> 4;
+                } else reflen = (uint32_t)parse_cigar(v.cig, ncig, B);
                 if (reflen == 0) reflen = 1;  // htslib bam_endpos
                 if ((uint64_t)pos + reflen > clen) reflen = clen - (uint32_t)pos;
                 v.span = (int)reflen;
@@ -747,7 +765,7 @@ __global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __g
                 my_counted++;
                 if (fits) {
                     bool bad = false;
-                    tc = fast_read<W>(A, v, B, mapq, bad);
+                    tc = uni_simple ? fast_read<W, true>(A, v, B, mapq, bad) : fast_read<W, false>(A, v, B, mapq, bad);
                     my_disagree += bad ? 1u : 0u;
                 } else {
                     my_slow++;

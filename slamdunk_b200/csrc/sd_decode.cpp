@@ -224,10 +224,11 @@ extern "C" void sd_hbatch_free(sd_hbatch *hb) {
     delete hb;
 }
 
-extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, uint32_t n_fasta, int want_mp,
+extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, uint32_t n_fasta, int options,
                              uint32_t tile_reads, int threads, sd_hbatch **out, char *err, int errlen) {
     if (!path || !out) return fail(err, errlen, SD_ERR_ARG, "sd_decode_bam: null argument");
     *out = nullptr;
+    const bool want_mp = (options & SD_DECODE_MP) != 0, group = (options & SD_DECODE_GROUP) != 0;
     if (tile_reads != 0 && tile_reads != 32) return fail(err, errlen, SD_ERR_ARG, "tile_reads must be 32 (or 0 = default)");
     tile_reads = 32;
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -419,6 +420,31 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         rec[i].nm_nmp = 0;
     }
 
+    // ---- optional grouping: reads that are one plain match block first (plus strand before minus strand), the
+    // rest after, each group in file order -- counting is order independent, and homogeneous tiles let whole warps
+    // take the kernel's lean path.  order[slot] = record index in the file.
+    uint32_t *order = (uint32_t *)own->mem.get(std::max<size_t>(1, n) * sizeof(uint32_t));
+    if (!order) return bail(SD_ERR_NOMEM, "out of host memory");
+    for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    if (group && n > 0) {
+        auto cls = [&](size_t i) -> uint32_t {
+            const uint8_t *r = raw.data() + recoff[i];
+            const uint32_t n_cig = rd16(r + 12), flag = rd16(r + 14);
+            bool simple = false;
+            if (n_cig == 1) {
+                const uint32_t op = rd32(r + 32 + r[8]) & 15u;
+                simple = (op == 0 || op == 7 || op == 8);
+            }
+            return (simple ? 0u : 2u) | ((flag & 0x10) ? 1u : 0u);
+        };
+        size_t count[4] = {0, 0, 0, 0};
+        for (size_t i = 0; i < n; i++) count[cls(i)]++;
+        size_t start[4] = {0, count[0], count[0] + count[1], count[0] + count[1] + count[2]};
+        for (size_t i = 0; i < n; i++) order[start[cls(i)]++] = (uint32_t)i;
+        std::vector<sd_read_rec> tmp(rec, rec + n);
+        parallel_for(n, threads, [&](size_t k) { rec[k] = tmp[order[k]]; });
+    }
+
     // ---- tile offsets
     auto up16 = [](uint64_t x) { return (x + 15ull) & ~15ull; };
     uint32_t max_lseq = 0, mt_seq = 0, mt_qual = 0, mt_cig = 0, mt_mp = 0;
@@ -459,7 +485,8 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         uint8_t *pc = (uint8_t *)cigc + tiles[t].cig_off;
         uint8_t *pm = mpc ? (uint8_t *)mpc + tiles[t].mp_off : nullptr;
         const size_t e = std::min(n, (t + 1) * (size_t)tile_reads);
-        for (size_t i = t * (size_t)tile_reads; i < e; i++) {
+        for (size_t k = t * (size_t)tile_reads; k < e; k++) {
+            const size_t i = order[k];
             const uint8_t *r = raw.data() + recoff[i];
             const uint32_t l_name = r[8], n_cig = rd16(r + 12), flag = rd16(r + 14);
             const uint32_t l_seq = rd32(r + 16);
@@ -515,6 +542,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     hb->batch.max_tile_cig = mt_cig;
     hb->batch.max_tile_mp = mt_mp;
     hb->name_hash = name_hash;
+    hb->order = order;
     hb->seconds_inflate = t1 - t0;
     hb->seconds_decode = t2 - t1;
     hb->compressed_bytes = compressed;

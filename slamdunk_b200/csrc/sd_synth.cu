@@ -150,12 +150,13 @@ __global__ void synth_plan_kernel(sd_synth_params P, sd_synth_tables T, uint32_t
     counts[i] = pl.ncig | (em.nmp << 16);
 }
 
-__global__ void synth_positions_kernel(sd_synth_params P, sd_synth_tables T, uint32_t *gpos) {
+__global__ void synth_positions_kernel(sd_synth_params P, sd_synth_tables T, uint32_t *gpos, uint8_t *cls) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_reads) return;
     Rng rng(P.seed, P.first_read + i);
     const Plan pl = make_plan(rng, P, T);
     gpos[i] = T.chrom_off[pl.chrom] + pl.pos;
+    if (cls) cls[i] = (uint8_t)((pl.ncig == 1 ? 0u : 2u) | pl.strand);   // same classes as sd_decode_bam's grouping
 }
 
 // per tile: padded byte sizes of the four columns
@@ -310,11 +311,11 @@ __global__ void synth_genome_pad_kernel(uint32_t *nm, uint64_t n_words, const ui
 
 }  // namespace
 
-extern "C" int sd_synth_positions(sd_ctx *ctx, const sd_synth_params *p, const sd_synth_tables *t, uint32_t *d_gpos) {
+extern "C" int sd_synth_positions(sd_ctx *ctx, const sd_synth_params *p, const sd_synth_tables *t, uint32_t *d_gpos, uint8_t *d_cls) {
     if (!ctx || !p || !t || !d_gpos) return sd_fail(ctx, SD_ERR_ARG, "sd_synth_positions: null argument");
     if (t->n_utr == 0 || p->utr_first >= t->n_utr || p->utr_first + p->utr_count > t->n_utr) return sd_fail(ctx, SD_ERR_ARG, "bad UTR range");
     SD_CUDA(ctx, cudaSetDevice(ctx->device));
-    synth_positions_kernel<<<(unsigned)((p->n_reads + 255) / 256), 256, 0, ctx->stream>>>(*p, *t, d_gpos);
+    synth_positions_kernel<<<(unsigned)((p->n_reads + 255) / 256), 256, 0, ctx->stream>>>(*p, *t, d_gpos, d_cls);
     ctx->launches++;
     SD_CUDA(ctx, cudaGetLastError());
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -68,7 +68,7 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
     genome = HostGenome(ref, OPTIONS["threads"])
     tm["fasta_decode_s"] = genome.seconds
     mode = {"cigar": L.SD_MISMATCH_CIGAR, "mp": L.SD_MISMATCH_MP, "verify": L.SD_MISMATCH_VERIFY}[OPTIONS["mismatch_source"]]
-    hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"])
+    hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True)
     tm["bam_inflate_s"] = hbatch.seconds_inflate
     tm["bam_decode_s"] = hbatch.seconds_decode
     tm["bam_reads"] = hbatch.n_reads

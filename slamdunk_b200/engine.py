@@ -72,12 +72,13 @@ class HostBatch(object):
     """A BAM file decoded into the columnar batch (sd_decode_bam); buffers are page-locked."""
 
     def __init__(self, path: str, fasta_names: Sequence[str], want_mp: bool = True, tile_reads: int = 0,
-                 threads: int = 0):
+                 threads: int = 0, group: bool = False):
         lib = L.load()
         err = ctypes.create_string_buffer(512)
         out = ctypes.POINTER(L.HBatch)()
         names = (ctypes.c_char_p * max(1, len(fasta_names)))(*[n.encode() for n in fasta_names])
-        rc = lib.sd_decode_bam(os.fsencode(path), names, len(fasta_names), 1 if want_mp else 0, int(tile_reads),
+        rc = lib.sd_decode_bam(os.fsencode(path), names, len(fasta_names),
+                               (L.SD_DECODE_MP if want_mp else 0) | (L.SD_DECODE_GROUP if group else 0), int(tile_reads),
                                int(threads), ctypes.byref(out), err, len(err))
         if rc != L.SD_OK:
             raise L.NativeError("sd_decode_bam(%s) failed (%d): %s" % (path, rc, err.value.decode("utf-8", "replace")))
@@ -121,6 +122,13 @@ class HostBatch(object):
         if not n or not addr:
             return np.zeros(0, dtype=np.dtype(dt))
         return np.frombuffer((dt * n).from_address(addr), dtype=np.dtype(dt))
+
+    def order(self) -> np.ndarray:
+        """batch slot -> record index in the file"""
+        n = self.n_reads
+        if not n:
+            return np.zeros(0, np.uint32)
+        return np.ctypeslib.as_array(self._h.contents.order, shape=(n,))
 
     def name_hash(self) -> np.ndarray:
         n = self.n_reads

@@ -148,24 +148,32 @@ class SynthWorkload(object):
         p.utr_first, p.utr_count = int(utr_first), int(utr_count)
         return p
 
-    def generate(self, p: L.SynthParams, want_mp=False, want_triples=False, coordinate_sorted=False):
-        """-> (DeviceBatch, triples tensor or None).  coordinate_sorted: order the batch by alignment
-        start like the sorted BAM `slamdunk count` reads (triples follow the batch order)."""
+    def generate(self, p: L.SynthParams, want_mp=False, want_triples=False, coordinate_sorted=False, group=None):
+        """-> (DeviceBatch, triples tensor or None).
+        coordinate_sorted: order the reads by alignment start like the sorted BAM `slamdunk count` reads;
+        group (default: same as coordinate_sorted): additionally order them by alignment shape and strand the way
+        sd_decode_bam's SD_DECODE_GROUP does (plain match blocks first).  Triples follow the batch order."""
         eng, dev = self.eng, self.eng.device
         n = int(p.n_reads)
         T = int(p.tile_reads)
         n_tiles = (n + T - 1) // T
         order = None
-        if coordinate_sorted:
+        if group is None:
+            group = coordinate_sorted
+        if coordinate_sorted or group:
             with torch.cuda.stream(eng.stream):
                 gpos = torch.empty(n, dtype=torch.int32, device=dev)
+                cls = torch.empty(n, dtype=torch.uint8, device=dev)
             eng.stream.synchronize()
             p.order = None
-            eng._chk(self.lib.sd_synth_positions(eng.ctx, ctypes.byref(p), ctypes.byref(self.tables), gpos.data_ptr()),
-                     "sd_synth_positions")
+            eng._chk(self.lib.sd_synth_positions(eng.ctx, ctypes.byref(p), ctypes.byref(self.tables), gpos.data_ptr(),
+                                                 cls.data_ptr()), "sd_synth_positions")
             with torch.cuda.stream(eng.stream):
-                order = torch.argsort(gpos.to(torch.int64) & 0xFFFFFFFF, stable=True).to(torch.int32)
-                del gpos
+                key = (gpos.to(torch.int64) & 0xFFFFFFFF) if coordinate_sorted else torch.arange(n, device=dev, dtype=torch.int64)
+                if group:
+                    key = key | (cls.to(torch.int64) << 40)
+                order = torch.argsort(key, stable=True).to(torch.int32)
+                del gpos, cls, key
             eng.stream.synchronize()
             p.order = order.data_ptr()
         with torch.cuda.stream(eng.stream):
