@@ -203,3 +203,27 @@ def test_snp_masks_at_scale_including_key_collisions():
     assert rows["multimap_count"].sum() > 0
     assert ob.compare(res, rows, bg, wl.ann, eng.pos_off, wl.chrom_off) == []
     eng.close()
+
+
+def test_file_pipeline_on_a_synthetic_bam(tmp_path):
+    """cfg2 in miniature through the FILE interface: generator -> FASTA/BED/BAM on disk -> computeTconversions
+    (C++ decode with shape grouping, GPU count) versus the oracle's count_files on the same files."""
+    import io
+    import synth_files
+    from slamdunk_b200.dunks import tcounter
+    eng, wl = _setup(genome_bp=4_000_000, n_utr=800, seed=21)
+    db, triples = wl.generate(wl.params(seed=5, first_read=0, n_reads=120_000, frac_multimap=0.05), want_triples=True,
+                              coordinate_sorted=True, group=False)
+    ref, bed, bam, n = synth_files.write_workload_files(str(tmp_path), wl, db, triples)
+    eng.close()
+    out, orc = str(tmp_path / "gpu"), str(tmp_path / "orc")
+    glog, olog = io.StringIO(), io.StringIO()
+    tcounter.computeTconversions(ref, bed, None, bam, 100, 27, out + ".tsv", out + ".p", out + ".m", 1, glog)
+    tm = tcounter.OPTIONS["timings"]
+    oracle.count_files(ref, bed, None, bam, 100, 27, orc + ".tsv", orc + ".p", orc + ".m", 1, olog, threads=8)
+    for ext in (".tsv", ".p", ".m"):
+        assert open(out + ext).read() == open(orc + ext).read(), ext
+    assert glog.getvalue() == olog.getvalue() == ""
+    assert tm["bam_reads"] == n and tm["stats"][8] == 0       # no MP / CIGAR-walk disagreement
+    print("decode: inflate %.3fs records %.3fs; gpu count %.3fs; write %.3fs for %d reads"
+          % (tm["bam_inflate_s"], tm["bam_decode_s"], tm["gpu_count_s"], tm["write_s"], n))

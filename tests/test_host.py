@@ -210,3 +210,42 @@ def test_bed_reader_quirks(tmp_path):
     assert [(r.chromosome, r.start, r.stop, r.name, r.strand) for r in rows] == \
         [("chr1", 5, 10, "n1", "+"), ("chr1", 7, 9, "n2", "."), ("chr2", 1, 2, "n3", "-")]
     assert rows[0].hasStrand() and not rows[1].hasStrand() and rows[0].getLength() == 5
+
+
+def test_decoder_grouping_is_a_stable_partition(tmp_path):
+    """SD_DECODE_GROUP: plain single-match-block reads first (plus then minus strand), the rest after, each
+    group in file order; `order` maps batch slots back to file records and the columns follow it."""
+    c = simdata.make_case(str(tmp_path), seed=78, n_reads=600, complexity=2.0)
+    _t, refs, recs = bamio.read_bam(c.bam)
+    names = list(c.genome.keys())
+    from slamdunk_b200.engine import HostBatch
+    hb = HostBatch(c.bam, names, want_mp=True, group=True)
+    order = hb.order().tolist()
+    assert sorted(order) == list(range(len(recs)))
+
+    def cls(r):
+        simple = len(r.cigar) == 1 and r.cigar[0][0] in (0, 7, 8)
+        return (0 if simple else 2) | (1 if r.flag & 16 else 0)
+    keys = [(cls(recs[i]), i) for i in order]
+    assert keys == sorted(keys)
+    assert len(set(k for k, _ in keys)) >= 3
+    rec = hb.rec_array()
+    tiles = hb.tiles_array()
+    seq, qual = hb.column("seq"), hb.column("qual")
+    for t in range(hb.batch.n_tiles):
+        so, qo = int(tiles[t][0]) // 4, int(tiles[t][1])
+        for k in range(32):
+            slot = t * 32 + k
+            if slot >= len(recs):
+                break
+            r = recs[order[slot]]
+            lseq = int(rec[slot][3]) & 0xFFFF
+            assert lseq == len(r.seq) and np.int32(rec[slot][0]) == r.pos
+            assert _unslice(seq[so:so + (lseq + 7) // 8], lseq) == r.seq.upper()
+            assert list(qual[qo:qo + lseq]) == r.qual
+            so += (lseq + 7) // 8
+            qo += lseq
+    hb.close()
+    plain = HostBatch(c.bam, names, want_mp=True, group=False)
+    assert plain.order().tolist() == list(range(len(recs)))
+    plain.close()
