@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libslamdunk_b200.so")
+LIB_PATH = os.environ.get("SLAMDUNK_B200_LIB") or os.path.join(HERE, "libslamdunk_b200.so")   # env: kernel experiments
 
 SD_OK = 0
 SD_F_REVERSE, SD_F_UNMAPPED, SD_F_SECONDARY, SD_F_SUPPLEMENTARY = 0x01, 0x02, 0x04, 0x08

@@ -31,8 +31,8 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, out_path=None):
+    if out_path is None and not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     objs = []
@@ -40,7 +40,8 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
+        extra = os.environ.get("SD_NVCC_DEFS", "").split()     # e.g. "-DSD_EXPERIMENT=1" for kernel experiments
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(obj)
     for src, p in procs:
@@ -49,10 +50,11 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
         if verbose:
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lz", "-lpthread"]
+    cmd = [nvcc, "-shared", "-o", out_path or LIB] + objs + ["-lz", "-lpthread"]
     subprocess.check_call(cmd)
-    return LIB
+    return out_path or LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out_path=out))
