@@ -117,7 +117,8 @@ def test_per_read_tc_counts_match_mp_tags():
 
 
 @pytest.mark.parametrize("seed,thr,minq,read_len,reads", [(301, 1, 27, (40, 100), 20000), (302, 2, 20, (100, 100), 20000),
-                                                          (303, 1, 27, (150, 250), 8000), (304, 1, 27, (300, 400), 3000)])
+                                                          (303, 1, 27, (150, 250), 8000), (304, 1, 27, (300, 400), 3000),
+                                                          (305, 1, 27, (480, 700), 1500)])
 def test_count_matches_oracle_on_random_data(seed, thr, minq, read_len, reads, tmp_path):
     """Seeded data sets too big for the Python reference but quick for the C oracle."""
     c = simdata.make_case(str(tmp_path), seed=seed, n_reads=reads, read_len=read_len, n_utr=120, complexity=1.5,
