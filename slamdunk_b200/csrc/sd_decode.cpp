@@ -93,6 +93,20 @@ inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); 
 inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 inline int32_t rdi32(const uint8_t *p) { return (int32_t)rd32(p); }
 
+// Byte buffer without the zero fill of std::vector (the decoder overwrites every byte anyway).
+struct RawBuf {
+    uint8_t *p = nullptr;
+    size_t n = 0;
+    RawBuf() {}
+    explicit RawBuf(size_t bytes) : p((uint8_t *)malloc(bytes ? bytes : 1)), n(bytes) {}
+    RawBuf(const RawBuf &) = delete;
+    RawBuf &operator=(const RawBuf &) = delete;
+    ~RawBuf() { free(p); }
+    void release() { free(p); p = nullptr; n = 0; }
+    uint8_t *data() const { return p; }
+    size_t size() const { return n; }
+};
+
 struct AuxInfo {
     float xi;
     uint32_t nm;
@@ -233,6 +247,14 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     tile_reads = 32;
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     const double t0 = now_s();
+    const bool timing = getenv("SD_DECODE_TIMING") != nullptr;
+    double tp = t0;
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const double t = now_s();
+        fprintf(stderr, "[sd_decode_bam] %-14s %.4f s\n", what, t - tp);
+        tp = t;
+    };
 
     // ---- read the file
     FILE *fh = fopen(path, "rb");
@@ -240,13 +262,15 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     fseek(fh, 0, SEEK_END);
     const long fsz = ftell(fh);
     fseek(fh, 0, SEEK_SET);
-    std::vector<uint8_t> file((size_t)fsz);
+    RawBuf file((size_t)fsz);
+    if (!file.data()) { fclose(fh); return fail(err, errlen, SD_ERR_NOMEM, "out of host memory"); }
     if (fsz > 0 && fread(file.data(), 1, (size_t)fsz, fh) != (size_t)fsz) {
         fclose(fh);
         return fail(err, errlen, SD_ERR_IO, "short read on %s", path);
     }
     fclose(fh);
 
+    lap("read file");
     // ---- BGZF block table
     struct Blk { size_t coff, clen, uoff, ulen; };
     std::vector<Blk> blks;
@@ -271,7 +295,8 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         utotal += isize;
         off += total;
     }
-    std::vector<uint8_t> raw(utotal);
+    RawBuf raw(utotal);
+    if (!raw.data()) return fail(err, errlen, SD_ERR_NOMEM, "out of host memory");
     std::atomic<int> bad(0);
     parallel_for(blks.size(), threads, [&](size_t i) {
         const Blk &b = blks[i];
@@ -291,8 +316,9 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     });
     if (bad) return fail(err, errlen, SD_ERR_FORMAT, "%s: corrupt BGZF block", path);
     const size_t compressed = file.size();
-    std::vector<uint8_t>().swap(file);
+    file.release();
     const double t1 = now_s();
+    lap("inflate");
 
     // ---- BAM header
     if (raw.size() < 12 || memcmp(raw.data(), "BAM\1", 4) != 0) return fail(err, errlen, SD_ERR_FORMAT, "%s: not a BAM file", path);
@@ -338,14 +364,95 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     hb->ref_lengths = own->lengths.data();
 
     // ---- record index
+    // BAM records carry no sync marker, so finding them is a dependent chain of block_size reads.  The chain is cut
+    // into chunks: each chunk guesses its first record by a plausibility test that must hold for a run of consecutive
+    // records, walks from there, and the pieces are accepted only if every chunk ends exactly where the next one
+    // started -- which proves the guesses were on the true chain.  Otherwise the plain serial walk is used.
+    const size_t rec_begin = p;
     std::vector<size_t> recoff;
-    while (p + 4 <= raw.size()) {
-        const int32_t bs = rdi32(raw.data() + p);
-        if (bs < 32 || p + 4 + (size_t)bs > raw.size()) return bail(SD_ERR_FORMAT, "truncated alignment record");
-        recoff.push_back(p + 4);
-        p += 4 + (size_t)bs;
+    {
+        const uint8_t *R = raw.data();
+        const size_t N = raw.size();
+        auto plausible = [&](size_t at) -> long long {   // -> block_size if a record could start at `at`, else -1
+            if (at + 36 > N) return -1;
+            const int32_t bs = rdi32(R + at);
+            if (bs < 34 || (size_t)bs > (64u << 20) || at + 4 + (size_t)bs > N) return -1;
+            const uint8_t *r = R + at + 4;
+            const int32_t ref_id = rdi32(r), pos = rdi32(r + 4), l_seq = rdi32(r + 16), nref = rdi32(r + 20);
+            const uint32_t l_name = r[8], n_cig = rd16(r + 12);
+            if (ref_id < -1 || ref_id >= n_ref || pos < -1 || l_seq < 0 || nref < -1 || nref >= n_ref || l_name < 1) return -1;
+            const size_t need = 32 + (size_t)l_name + 4 * (size_t)n_cig + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
+            if (need > (size_t)bs) return -1;
+            if (r[32 + l_name - 1] != 0) return -1;
+            for (uint32_t k = 0; k + 1 < l_name; k++)
+                if (r[32 + k] < 33 || r[32 + k] > 126) return -1;
+            for (uint32_t k = 0; k < n_cig; k++)
+                if ((rd32(r + 32 + l_name + 4 * k) & 15u) > 8u) return -1;
+            return bs;
+        };
+        const size_t span = N - rec_begin;
+        const char *par_min_env = getenv("SD_DECODE_PAR_MIN");   // bytes of records below which the serial walk is used (tests lower it)
+        const size_t par_min = par_min_env ? (size_t)atoll(par_min_env) : (size_t)(8u << 20);
+        size_t n_chunks = (threads > 1 && span > par_min && span > 4096) ? (size_t)threads * 2 : 1;
+        bool ok = n_chunks > 1;
+        if (ok) {
+            const size_t chunk = span / n_chunks;
+            std::vector<size_t> first(n_chunks, 0), last(n_chunks, 0);
+            std::vector<std::vector<size_t>> part(n_chunks);
+            std::atomic<int> failed(0);
+            parallel_for(n_chunks, threads, [&](size_t c) {
+                const size_t lo = rec_begin + c * chunk, hi = (c + 1 == n_chunks) ? N : rec_begin + (c + 1) * chunk;
+                size_t at = lo;
+                if (c > 0) {   // search the first offset from which 6 consecutive records look right
+                    bool found = false;
+                    for (; at < hi && at + 36 <= N; at++) {
+                        size_t q = at;
+                        int good = 0;
+                        while (good < 6) {
+                            const long long bs = plausible(q);
+                            if (bs < 0) break;
+                            good++;
+                            q += 4 + (size_t)bs;
+                            if (q == N) { good = 6; break; }
+                        }
+                        if (good == 6) { found = true; break; }
+                    }
+                    if (!found) { failed = 1; return; }
+                }
+                first[c] = at;
+                std::vector<size_t> &v = part[c];
+                v.reserve((hi - lo) / 150 + 16);
+                while (at < hi) {   // records that START inside this chunk
+                    if (at + 4 > N) { failed = 1; return; }
+                    const int32_t bs = rdi32(R + at);
+                    if (bs < 32 || at + 4 + (size_t)bs > N) { failed = 1; return; }
+                    v.push_back(at + 4);
+                    at += 4 + (size_t)bs;
+                }
+                last[c] = at;
+            });
+            ok = !failed;
+            for (size_t c = 0; ok && c + 1 < n_chunks; c++) ok = (last[c] == first[c + 1]);
+            ok = ok && last[n_chunks - 1] == N;
+            if (ok) {
+                size_t total = 0;
+                for (auto &v : part) total += v.size();
+                recoff.reserve(total);
+                for (auto &v : part) recoff.insert(recoff.end(), v.begin(), v.end());
+            }
+        }
+        if (!ok) {
+            recoff.clear();
+            while (p + 4 <= N) {
+                const int32_t bs = rdi32(R + p);
+                if (bs < 32 || p + 4 + (size_t)bs > N) return bail(SD_ERR_FORMAT, "truncated alignment record");
+                recoff.push_back(p + 4);
+                p += 4 + (size_t)bs;
+            }
+        }
     }
     const size_t n = recoff.size();
+    lap("record index");
     const size_t n_tiles = (n + tile_reads - 1) / tile_reads;
     if (n_tiles > 0xFFFFFFF0ull) return bail(SD_ERR_LIMIT, "too many records for one batch");
 
@@ -356,6 +463,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     std::vector<const char *> mp_ptr(n, nullptr);
     std::atomic<int> fmt_err(0), limit_err(0);
 
+    lap("alloc");
     // ---- pass A: fixed-size fields, tags, sizes
     parallel_for(n, threads, [&](size_t i) {
         const uint8_t *r = raw.data() + recoff[i];
@@ -420,6 +528,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         rec[i].nm_nmp = 0;
     }
 
+    lap("pass A");
     // ---- optional grouping: reads that are one plain match block first (plus strand before minus strand), the
     // rest after, each group in file order -- counting is order independent, and homogeneous tiles let whole warps
     // take the kernel's lean path.  order[slot] = record index in the file.
@@ -437,14 +546,35 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
             }
             return (simple ? 0u : 2u) | ((flag & 0x10) ? 1u : 0u);
         };
-        size_t count[4] = {0, 0, 0, 0};
-        for (size_t i = 0; i < n; i++) count[cls(i)]++;
-        size_t start[4] = {0, count[0], count[0] + count[1], count[0] + count[1] + count[2]};
-        for (size_t i = 0; i < n; i++) order[start[cls(i)]++] = (uint32_t)i;
+        // stable counting sort over four classes, chunked so that the class scan and the scatter run on all threads
+        const size_t n_chunks = (size_t)std::max(1, threads) * 4;
+        const size_t chunk = (n + n_chunks - 1) / n_chunks;
+        std::vector<size_t> cnt(n_chunks * 4, 0);
+        std::vector<uint8_t> cl(n);
+        parallel_for(n_chunks, threads, [&](size_t c) {
+            const size_t b = c * chunk, e = std::min(n, b + chunk);
+            for (size_t i = b; i < e; i++) {
+                cl[i] = (uint8_t)cls(i);
+                cnt[c * 4 + cl[i]]++;
+            }
+        });
+        std::vector<size_t> start(n_chunks * 4, 0);
+        size_t run = 0;
+        for (int k = 0; k < 4; k++)
+            for (size_t c = 0; c < n_chunks; c++) {
+                start[c * 4 + k] = run;
+                run += cnt[c * 4 + k];
+            }
+        parallel_for(n_chunks, threads, [&](size_t c) {
+            const size_t b = c * chunk, e = std::min(n, b + chunk);
+            size_t pos[4] = {start[c * 4 + 0], start[c * 4 + 1], start[c * 4 + 2], start[c * 4 + 3]};
+            for (size_t i = b; i < e; i++) order[pos[cl[i]]++] = (uint32_t)i;
+        });
         std::vector<sd_read_rec> tmp(rec, rec + n);
         parallel_for(n, threads, [&](size_t k) { rec[k] = tmp[order[k]]; });
     }
 
+    lap("grouping");
     // ---- tile offsets
     auto up16 = [](uint64_t x) { return (x + 15ull) & ~15ull; };
     uint32_t max_lseq = 0, mt_seq = 0, mt_qual = 0, mt_cig = 0, mt_mp = 0;
@@ -478,6 +608,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     uint32_t *mpc = want_mp ? (uint32_t *)own->mem.get(tot.mp_off + 16) : nullptr;
     if (!seqc || !qualc || !cigc || (want_mp && !mpc)) return bail(SD_ERR_NOMEM, "out of host memory");
 
+    lap("tiles+alloc");
     // ---- pass B: variable-length columns, one tile at a time
     parallel_for(n_tiles, threads, [&](size_t t) {
         uint8_t *ps = (uint8_t *)seqc + tiles[t].seq_off;
@@ -526,6 +657,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         if (pm) memset(pm, 0, (size_t)(((uint8_t *)mpc + tiles[t + 1].mp_off) - pm));
     });
     const double t2 = now_s();
+    lap("pass B");
 
     hb->batch.n_reads = n;
     hb->batch.n_tiles = (uint32_t)n_tiles;

@@ -249,3 +249,21 @@ def test_decoder_grouping_is_a_stable_partition(tmp_path):
     plain = HostBatch(c.bam, names, want_mp=True, group=False)
     assert plain.order().tolist() == list(range(len(recs)))
     plain.close()
+
+
+def test_parallel_record_index_equals_serial_walk(tmp_path, monkeypatch):
+    """The chunked, verified record indexing gives the same batch as the serial walk (threads = 1)."""
+    from slamdunk_b200.engine import HostBatch
+    c = simdata.make_case(str(tmp_path), seed=79, n_reads=3000, complexity=2.0)
+    names = list(c.genome.keys())
+    serial = HostBatch(c.bam, names, want_mp=True, group=True, threads=1)
+    monkeypatch.setenv("SD_DECODE_PAR_MIN", "0")
+    for threads in (2, 5):
+        par = HostBatch(c.bam, names, want_mp=True, group=True, threads=threads)
+        assert par.n_reads == serial.n_reads == 3000
+        assert np.array_equal(par.rec_array(), serial.rec_array()) and np.array_equal(par.order(), serial.order())
+        for col in ("seq", "qual", "cigar", "mp"):
+            assert np.array_equal(par.column(col), serial.column(col)), col
+        assert np.array_equal(par.name_hash(), serial.name_hash())
+        par.close()
+    serial.close()
