@@ -227,3 +227,59 @@ def test_file_pipeline_on_a_synthetic_bam(tmp_path):
     assert tm["bam_reads"] == n and tm["stats"][8] == 0       # no MP / CIGAR-walk disagreement
     print("decode: inflate %.3fs records %.3fs; gpu count %.3fs; write %.3fs for %d reads"
           % (tm["bam_inflate_s"], tm["bam_decode_s"], tm["gpu_count_s"], tm["write_s"], n))
+
+
+def test_full_size_cfg2_properties():
+    """BASELINE.json configs[1] at full size (50 M x 100 bp, 20 000 UTRs, 100 Mb genome): too big for the oracle, so
+    size-independent properties -- counting the tile range in three uneven pieces equals counting it whole, a second
+    pass reproduces the first bit for bit (integer atomics: order independent), every counted read is attributed
+    consistently, and the coverage integral equals the summed clipped read spans recorded in difference form."""
+    import ctypes
+    import torch
+    from slamdunk_b200 import _lib as L
+    from slamdunk_b200.engine import CountEngine, DeviceBatch, make_params
+    from slamdunk_b200.synth import SynthWorkload
+    eng = CountEngine(0)
+    wl = SynthWorkload(eng, seed=1, genome_bp=100_000_000, n_utr=20000)
+    wl.install()
+    n = 50_000_000
+    db, _ = wl.generate(wl.params(seed=3, first_read=0, n_reads=n), coordinate_sorted=True)
+    params = make_params(27, 1, L.SD_MISMATCH_CIGAR, filter_on=True, filter_mq=2, filter_min_identity=0.95)
+    eng.count(db, params)
+    eng.synchronize()
+    whole = (eng.counters.clone(), eng.pos_cov.clone(), eng.pos_tc.clone(), eng.stats.clone())
+    # idempotence
+    eng.reset_outputs()
+    eng.count(db, params)
+    eng.synchronize()
+    for a, b in zip(whole, (eng.counters, eng.pos_cov, eng.pos_tc, eng.stats)):
+        assert torch.equal(a, b)
+    # three uneven tile ranges (device sub-batches: record and tile-table pointers advance, columns stay)
+    nt = db.batch.n_tiles
+    cuts = [0, nt // 7, nt // 7 + nt // 2, nt]
+    eng.reset_outputs()
+    for t0, t1 in zip(cuts[:-1], cuts[1:]):
+        sb = L.Batch()
+        ctypes.memmove(ctypes.byref(sb), ctypes.byref(db.batch), ctypes.sizeof(L.Batch))
+        sb.n_tiles = t1 - t0
+        sb.n_reads = min(n, t1 * 32) - t0 * 32
+        sb.rec = db.batch.rec + t0 * 32 * 20
+        sb.tiles = db.batch.tiles + t0 * 32
+        eng.count(DeviceBatch(sb, db.tensors), params)
+    eng.synchronize()
+    for a, b in zip(whole, (eng.counters, eng.pos_cov, eng.pos_tc, eng.stats)):
+        assert torch.equal(a, b)
+    st = whole[3].cpu().numpy()
+    c = whole[0].cpu().numpy().reshape(-1, L.SD_NCOUNTER)
+    assert st[L.SD_S_MAPPED] == n and st[L.SD_S_FILTERED] == st[L.SD_S_COUNTED] < n     # mapq-0 reads (3 %) are filtered
+    assert st[L.SD_S_MQFILTERED] + st[L.SD_S_IDFILTERED] + st[L.SD_S_FILTERED] == n
+    assert c[:, L.SD_C_READS].sum() >= 0.9 * st[L.SD_S_COUNTED]                         # ~98 % sense-strand reads hit their UTR
+    assert (c[:, L.SD_C_TCREADS] <= c[:, L.SD_C_READS]).all() and (c[:, L.SD_C_CONV_ON_T] <= c[:, L.SD_C_COV_ON_T]).all()
+    assert c[:, L.SD_C_MULTIMAP].sum() == 0                                             # filtered out by MQ >= 2
+    # difference form: +1 / -1 per (read, segment) cancel; after the scan no position is negative
+    assert int(whole[1].sum()) == 0
+    eng.finalize()
+    eng.synchronize()
+    assert int(eng.pos_cov.min()) >= 0 and int(eng.pos_tc.min()) >= 0
+    assert int((eng.pos_tc > eng.pos_cov).sum()) == 0                                   # conversions only where covered
+    eng.close()
