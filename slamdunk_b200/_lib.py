@@ -111,6 +111,9 @@ PROTOTYPES = {
     "sd_load_fasta": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.POINTER(HGenome)),
                                      ctypes.c_char_p, ctypes.c_int]),
     "sd_hgenome_free": (None, [ctypes.POINTER(HGenome)]),
+    "sd_format_repr": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p]),
+    "sd_write_bedgraphs": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p), _VP, _VP,
+                                          _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_uint64]),
     "sd_synth_positions": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP, _VP]),
     "sd_synth_plan": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP, _VP, c_u64p]),
     "sd_synth_fill": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP,

@@ -205,50 +205,26 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
     hbatch.close()
 
 
-def _bits(plane: np.ndarray, g0: int, g1: int) -> np.ndarray:
-    """bool array of plane bits [g0, g1) (bit j of word w = position 32 w + j)."""
-    w0, w1 = g0 >> 5, (g1 + 31) >> 5
-    b = np.unpackbits(plane[w0:w1].view(np.uint8), bitorder="little")
-    return b[g0 - (w0 << 5): g1 - (w0 << 5)].astype(bool)
-
-
 def _write_bedgraphs(utrs, chrom_idx, genome, res, pos_off, pos_len, counters, out_plus, out_minus):
-    """tcounter.py:277-285 + 315-326: one line per covered T (A on '-') position of every UTR that
-    had reads, in dict insertion order: BED order, ascending position, a position keeps the place of
-    its first insertion."""
-    pos_cov, pos_tc = res["pos_cov"], res["pos_tc"]
-    emitted = np.zeros(len(pos_cov), dtype=bool)
-    is_base = (genome.is_base_mask(0), genome.is_base_mask(1))
-    rate_cache = {}
-    files = (open(out_plus, "w"), open(out_minus, "w"))
-    try:
-        for i, utr in enumerate(utrs):
-            if counters[i, L.SD_C_READS] <= 0 or pos_len[i] == 0 or pos_off[i] == np.iinfo(np.uint64).max:
-                continue
-            s = 1 if utr.strand == "-" else 0
-            off, ln = int(pos_off[i]), int(pos_len[i])
-            cov = pos_cov[off:off + ln]
-            g0 = int(genome.chrom_off[chrom_idx[i]]) + max(0, utr.start)
-            sel = (cov > 0) & _bits(is_base[s], g0, g0 + ln) & ~emitted[off:off + ln]
-            idx = np.nonzero(sel)[0]
-            if len(idx) == 0:
-                continue
-            emitted[off + idx] = True
-            tc = pos_tc[off:off + ln][idx]
-            cv = cov[idx]
-            base = max(0, utr.start)
-            out = files[s]
-            chrom = utr.chromosome
-            lines = []
-            for p, t, c in zip(idx.tolist(), tc.tolist(), cv.tolist()):
-                key = (t, c)
-                r = rate_cache.get(key)
-                if r is None:
-                    r = str(t * 100.0 / c)                   # tcounter.py:252
-                    rate_cache[key] = r
-                q = base + p
-                lines.append("%s %d %d %s\n" % (chrom, q, q + 1, r))
-            out.write("".join(lines))
-    finally:
-        files[0].close()
-        files[1].close()
+    """tcounter.py:277-285 + 315-326: one line per covered T (A on '-') position of every UTR that had reads, in
+    dict insertion order (BED order, ascending position, a position keeps the place of its first insertion).
+    Written by the native writer (sd_write_bedgraphs), which prints rates like Python's repr(float)."""
+    import ctypes
+    lib = L.load()
+    n = len(utrs)
+    names = (ctypes.c_char_p * max(1, n))(*[u.chromosome.encode() for u in utrs])
+    first = np.array([max(0, u.start) for u in utrs], dtype=np.int64)
+    strand = np.array([1 if u.strand == "-" else 0 for u in utrs], dtype=np.uint8)
+    has = np.ascontiguousarray(counters[:n, L.SD_C_READS] > 0, dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    gstart = np.array([(int(genome.chrom_off[chrom_idx[i]]) + int(first[i])) if chrom_idx[i] != L.SD_REF_NONE else 0
+                       for i in range(n)], dtype=np.uint64)
+    po = np.ascontiguousarray(pos_off, dtype=np.uint64)
+    pl = np.ascontiguousarray(pos_len, dtype=np.uint32)
+    isx = (np.ascontiguousarray(genome.is_base_mask(0)), np.ascontiguousarray(genome.is_base_mask(1)))
+    cov = np.ascontiguousarray(res["pos_cov"], dtype=np.int32)
+    tc = np.ascontiguousarray(res["pos_tc"], dtype=np.int32)
+    ptr = lambda a: ctypes.c_void_p(a.ctypes.data)    # noqa: E731
+    rc = lib.sd_write_bedgraphs(os.fsencode(out_plus), os.fsencode(out_minus), n, names, ptr(first), ptr(strand), ptr(has), ptr(po),
+                                ptr(pl), ptr(gstart), ptr(isx[0]), ptr(isx[1]), ptr(cov), ptr(tc), len(cov))
+    if rc != L.SD_OK:
+        raise L.NativeError("sd_write_bedgraphs failed with code %d" % rc)

@@ -267,3 +267,30 @@ def test_parallel_record_index_equals_serial_walk(tmp_path, monkeypatch):
         assert np.array_equal(par.name_hash(), serial.name_hash())
         par.close()
     serial.close()
+
+
+def test_native_float_repr_equals_python_repr():
+    """sd_format_repr must print what Python's repr(float) prints: the bedgraph rates and nothing else go through it."""
+    import ctypes
+    import random
+    import struct
+    lib = L.load()
+    buf = ctypes.create_string_buffer(64)
+
+    def fmt(x):
+        n = lib.sd_format_repr(ctypes.c_double(x), buf)
+        return buf.value[:n].decode()
+    rng = random.Random(7)
+    samples = [0.0, 1.0, 100.0, 0.5, 1e16, 1e15, 9999999999999998.0, 1e-4, 1e-5, 0.0001234, 123456789.125, 1 / 3, 2 / 3, 1e22, 5e-324,
+               1.7976931348623157e308, 14.285714285714286, 16.666666666666668, 0.022222222222222223, 666666.6666666666]
+    for _ in range(20000):
+        tc, cov = rng.randint(1, 5000), rng.randint(1, 200000)
+        samples.append(tc * 100.0 / cov)
+        samples.append(float(tc) / float(cov))
+        samples.append(tc * 1000000.0 / cov)
+    for _ in range(20000):
+        x = struct.unpack("<d", struct.pack("<Q", rng.getrandbits(64)))[0]
+        if x == x and abs(x) != float("inf"):
+            samples.append(x)
+    for x in samples:
+        assert fmt(x) == repr(x), (x, fmt(x), repr(x))
