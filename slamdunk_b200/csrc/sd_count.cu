@@ -103,6 +103,7 @@ struct CountArgs {
     int *pos_tc;
     unsigned long long *stats;
     uint8_t *read_tc;  // optional per-read tcCount (saturated), may be null
+    unsigned int *tile_counter;   // work queue head: warps claim chunks of consecutive tiles
     // parameters
     int min_qual;
     int conv_threshold;
@@ -622,6 +623,9 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 // @region kernel_setup
 #define SD_SMEM_STATS 8
 #define SD_TILE_READS 32
+#ifndef SD_CLAIM
+#define SD_CLAIM 8   // consecutive tiles claimed per atomic
+#endif
 #ifndef SD_MIN_CTAS
 #define SD_MIN_CTAS(W) ((W) == 4 ? 4 : ((W) == 8 ? 3 : 1))   // resident 256-thread CTAs per SM the register budget is tuned for
 #endif
@@ -646,8 +650,19 @@ __global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __g
     }
     __syncthreads();
 
-    const uint64_t gw = (uint64_t)blockIdx.x * nwarp + warp, total_warps = (uint64_t)gridDim.x * nwarp;
-
+    // Tiles are handed out dynamically in chunks of SD_CLAIM consecutive tiles (one atomic per chunk): warps that hit
+    // expensive tiles simply claim fewer, so the grid drains evenly, and a warp's consecutive tiles share reference
+    // windows and table rows in L1.
+    uint32_t *s_tile = reinterpret_cast<uint32_t *>(mine + (size_t)A.n_stages * stage_bytes + 96u);   // [n_stages] tile held by each stage
+    uint32_t claim_next = 0, claim_end = 0;   // lane 0 only
+    auto claim = [&]() -> uint32_t {          // next tile for this warp, or 0xFFFFFFFF when the queue is empty
+        if (claim_next == claim_end) {
+            claim_next = atomicAdd(A.tile_counter, (unsigned int)SD_CLAIM);
+            claim_end = claim_next + SD_CLAIM;
+        }
+        const uint32_t t = claim_next++;
+        return t < A.n_tiles ? t : 0xFFFFFFFFu;
+    };
     // @region tma_issue
     auto issue = [&](uint64_t tile, uint32_t stage) {
         unsigned char *base = stages + (size_t)stage * stage_bytes;
@@ -669,16 +684,20 @@ __global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __g
 
     if (lane == 0) {
         for (uint32_t s = 0; s < A.n_stages; s++) {
-            const uint64_t t = gw + (uint64_t)s * total_warps;
-            if (t < A.n_tiles) issue(t, s);
+            const uint32_t t = claim();
+            s_tile[s] = t;
+            if (t != 0xFFFFFFFFu) issue(t, s);
         }
     }
+    __syncwarp();
 
     // @region tile_wait_rec
     uint32_t my_counted = 0, my_slow = 0, my_disagree = 0;
     unsigned long long my_tc_total = 0;
     uint32_t stage = 0, phase = 0;
-    for (uint64_t tile = gw; tile < A.n_tiles; tile += total_warps) {
+    for (;;) {
+        const uint64_t tile = s_tile[stage];
+        if (tile == 0xFFFFFFFFull) break;   // the queue ran dry (claims are monotonic: later stages are empty too)
         mbar_wait(&full[stage], phase);
         const unsigned char *base = stages + (size_t)stage * stage_bytes;
         const uint32_t *rw = reinterpret_cast<const uint32_t *>(base) + 5u * lane;
@@ -779,9 +798,11 @@ __global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __g
         // @region tile_end
         __syncwarp();   // every lane is done with this stage
         if (lane == 0) {
-            const uint64_t next = tile + (uint64_t)A.n_stages * total_warps;
-            if (next < A.n_tiles) issue(next, stage);
+            const uint32_t next = claim();
+            s_tile[stage] = next;
+            if (next != 0xFFFFFFFFu) issue(next, stage);
         }
+        __syncwarp();
         if (++stage == A.n_stages) {
             stage = 0;
             phase ^= 1u;
@@ -942,6 +963,7 @@ extern "C" void sd_destroy(sd_ctx *ctx) {
     cudaFree(ctx->refx[0]); cudaFree(ctx->refx[1]);
     cudaFree(ctx->d_chrom_off); cudaFree(ctx->d_chrom_len);
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
+    cudaFree(ctx->d_tile_counter);
     cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_copy[i]); cudaEventDestroy(ctx->ev_done[i]); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1152,7 +1174,7 @@ static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool tim
         forced_warps = e ? atoi(e) : 0;
     }
     // per-warp ring of n_stages tiles; as many warps per CTA (<= 8) as the shared memory allows
-    uint32_t n_stages = (forced_stages >= 1 && forced_stages <= 8) ? (uint32_t)forced_stages : 2u;
+    uint32_t n_stages = (forced_stages >= 1 && forced_stages <= 4) ? (uint32_t)forced_stages : 2u;
     auto warp_bytes = [&](uint32_t ns) { return (size_t)ns * stage_bytes + 128u; };
     if (128u + warp_bytes(n_stages) > (size_t)max_smem) n_stages = 1;
     if (128u + warp_bytes(n_stages) > (size_t)max_smem)
@@ -1214,6 +1236,9 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     A.pos_cov = ctx->pos_cov; A.pos_tc = ctx->pos_tc;
     A.stats = reinterpret_cast<unsigned long long *>(ctx->stats);
     A.read_tc = read_tc;
+    if (!ctx->d_tile_counter) SD_CUDA(ctx, cudaMalloc(&ctx->d_tile_counter, sizeof(unsigned int)));
+    SD_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned int), stream));
+    A.tile_counter = ctx->d_tile_counter;
     A.min_qual = p->min_qual; A.conv_threshold = p->conversion_threshold; A.mismatch_source = p->mismatch_source;
     A.filter_on = p->filter_on; A.filter_mq = p->filter_mq; A.filter_max_nm = p->filter_max_nm;
     A.filter_min_identity = p->filter_min_identity; A.force_slow = p->force_slow_path;

@@ -54,6 +54,8 @@ struct sd_ctx {
     int32_t *pos_cov = nullptr, *pos_tc = nullptr;
     int64_t *stats = nullptr;
 
+    unsigned int *d_tile_counter = nullptr;   // work-queue head of the count kernel
+
     // staging for sd_count_host
     void *d_stage[2] = {nullptr, nullptr};
     size_t stage_cap = 0;
