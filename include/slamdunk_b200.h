@@ -229,11 +229,12 @@ float sd_last_kernel_ms(sd_ctx *ctx);
  * cleared (multimapper retained by dumpBufferToBam, filter.py:56-65).  With h_utr_* == NULL the
  * default branch (MQ / identity / NM) runs; otherwise the multimapper-retention branch, whose
  * UTR intervals are [start, stop + 1) (utils/BedReader.py:28) and compare by name id.
- * stats: device int64[SD_NSTAT].  Synchronous.
+ * stats: device int64[SD_NSTAT].  d_state (optional): device uint8[n_reads], bits 0-1 survivor class (0 dropped by the
+ * predicates, 1 unique survivor, 2 multimapper survivor), bit 2: the alignment overlaps a UTR interval.  Synchronous.
  */
 int sd_filter(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params, const uint64_t *d_name_hash,
               const uint32_t *h_utr_chrom, const int64_t *h_utr_start, const int64_t *h_utr_stop,
-              const uint32_t *h_utr_name_id, uint32_t n_utr, uint8_t *d_keep, int64_t *d_stats);
+              const uint32_t *h_utr_name_id, uint32_t n_utr, uint8_t *d_keep, int64_t *d_stats, uint8_t *d_state);
 
 /* ------------------------------------------------------------------ host decode (C++ threads)
  * Replaces htslib/pysam for this path: BGZF inflate + BAM record decode into the columnar
@@ -281,6 +282,16 @@ typedef struct sd_hgenome {
 
 int sd_load_fasta(const char *path, int threads, sd_hgenome **out, char *err, int errlen);
 void sd_hgenome_free(sd_hgenome *g);
+
+/* ------------------------------------------------------------------ filtered BAM output (host, C++ threads + zlib)
+ * Replaces pysam's outfile.write / dumpBufferToBam and `samtools sort` after the decisions of sd_filter
+ * (dunks/filter.py:56-65, 191, 273-310).  keep[i] as produced by sd_filter; state[i] (sd_filter's optional output:
+ * bits 0-1 survivor class 0 none / 1 unique / 2 multimapper, bit 2 "overlaps a UTR") is needed when any keep[i] == 2, to
+ * rebuild the reference's RD:Z text.  Kept records are copied byte for byte; sort != 0: coordinate sort like samtools
+ * (tid, pos, strand; stable).  header_text: the new SAM header text.  level: zlib level 1-9. */
+int sd_rewrite_bam(const char *in_path, const char *out_path, const char *header_text, const uint8_t *keep,
+                   const uint8_t *state, uint64_t n_records, int sort, int level, int threads, uint64_t *n_written,
+                   char *err, int errlen);
 
 /* ------------------------------------------------------------------ host text output
  * sd_format_repr: x printed like Python's repr(float) (what the reference's print() of a rate produces); buf >= 32 bytes.

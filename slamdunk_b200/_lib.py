@@ -103,7 +103,9 @@ PROTOTYPES = {
     "sd_launch_count": (ctypes.c_int64, [_VP]),
     "sd_last_kernel_ms": (ctypes.c_float, [_VP]),
     "sd_filter": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params), _VP, _VP, _VP, _VP, _VP,
-                                 ctypes.c_uint32, _VP, _VP]),
+                                 ctypes.c_uint32, _VP, _VP, _VP]),
+    "sd_rewrite_bam": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, _VP, _VP, ctypes.c_uint64, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, c_u64p, ctypes.c_char_p, ctypes.c_int]),
     "sd_decode_bam": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint32, ctypes.c_int,
                                      ctypes.c_uint32, ctypes.c_int, ctypes.POINTER(ctypes.POINTER(HBatch)),
                                      ctypes.c_char_p, ctypes.c_int]),

@@ -1,0 +1,288 @@
+// sd_bamwrite.cpp -- host-side writer of the filtered BAM of `slamdunk filter`.
+//
+// Takes over what pysam + `samtools sort` do for the reference after the filter decisions are made
+// (dunks/filter.py:56-65 dumpBufferToBam, :191 outfile.write, :273-310 header rewrite + bamSort): the kept records are
+// copied byte for byte from the (inflated) input, multimapper-retained records get secondary/supplementary cleared and the
+// RD:Z tag, everything is coordinate sorted (tid, pos, strand; stable) and written as BGZF with deflate on all threads.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "sd_bamio.h"
+#include "slamdunk_b200.h"
+
+namespace {
+
+int wfail(char *err, int errlen, int code, const char *fmt, ...) {
+    if (err && errlen > 0) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(err, (size_t)errlen, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+inline uint16_t g16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t g32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline void p16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+inline void p32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+
+template <class F>
+void pfor(size_t n, int threads, F f) {
+    if (threads <= 1 || n < 2) {
+        for (size_t i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= n) break;
+                f(i);
+            }
+        });
+    for (auto &th : pool) th.join();
+}
+
+// size of one BAM optional field starting at p (tag[2] type value), 0 on malformed data
+size_t aux_field_size(const uint8_t *p, const uint8_t *end) {
+    if (p + 3 > end) return 0;
+    const uint8_t ty = p[2];
+    size_t n = 3;
+    switch (ty) {
+        case 'A': case 'c': case 'C': n += 1; break;
+        case 's': case 'S': n += 2; break;
+        case 'i': case 'I': case 'f': n += 4; break;
+        case 'Z': case 'H': {
+            const uint8_t *z = (const uint8_t *)memchr(p + 3, 0, (size_t)(end - p - 3));
+            if (!z) return 0;
+            n = (size_t)(z - p) + 1;
+            break;
+        }
+        case 'B': {
+            if (p + 8 > end) return 0;
+            const uint8_t sub = p[3];
+            const size_t cnt = g32(p + 4), sz = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+            n = 8 + cnt * sz;
+            break;
+        }
+        default: return 0;
+    }
+    return p + n <= end ? n : 0;
+}
+
+struct Span { const uint8_t *p; size_t n; };
+
+}  // namespace
+
+extern "C" int sd_rewrite_bam(const char *in_path, const char *out_path, const char *header_text, const uint8_t *keep,
+                              const uint8_t *state, uint64_t n_records, int sort, int level, int threads, uint64_t *n_written,
+                              char *err, int errlen) {
+    if (!in_path || !out_path || !header_text || !keep) return wfail(err, errlen, SD_ERR_ARG, "sd_rewrite_bam: null argument");
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (level < 1 || level > 9) level = 6;
+    RawBuf raw;
+    int rc = sd_bam_inflate_file(in_path, threads, raw, nullptr, err, errlen);
+    if (rc != SD_OK) return rc;
+    std::string old_text;
+    std::vector<std::string> names;
+    std::vector<uint32_t> lengths;
+    size_t p = 0;
+    if ((rc = sd_bam_parse_header(raw, in_path, old_text, names, lengths, &p, err, errlen)) != SD_OK) return rc;
+    std::vector<size_t> recoff;
+    if ((rc = sd_bam_index_records(raw, p, (int32_t)names.size(), threads, recoff, in_path, err, errlen)) != SD_OK) return rc;
+    if (recoff.size() != n_records)
+        return wfail(err, errlen, SD_ERR_ARG, "%s holds %zu records, %llu decisions given", in_path, recoff.size(), (unsigned long long)n_records);
+    const uint8_t *R = raw.data();
+
+    // ---- RD:Z texts of the retained multimappers (the reference's multimapList, filter.py:170 and its resets)
+    std::vector<std::string> rd_text(n_records ? 1 : 0);
+    std::vector<uint32_t> rd_slot;
+    bool any2 = false;
+    for (uint64_t i = 0; i < n_records; i++) any2 |= keep[i] == 2;
+    if (any2) {
+        if (!state) return wfail(err, errlen, SD_ERR_ARG, "sd_rewrite_bam: retained multimappers need the state array");
+        rd_slot.assign(n_records, 0);
+        rd_text.assign(1, std::string());
+        std::vector<uint64_t> mlist;
+        const uint8_t *prev = nullptr;
+        uint32_t prev_len = 0;
+        bool buffer_nonempty = false;
+        long long open_retained = -1;
+        auto flush = [&]() {
+            if (open_retained >= 0) {
+                std::string t;
+                for (size_t k = 0; k < mlist.size(); k++) {
+                    const uint8_t *r = R + recoff[mlist[k]];
+                    const int32_t ref_id = (int32_t)g32(r), pos = (int32_t)g32(r + 4);
+                    const uint32_t l_name = r[8], n_cig = g16(r + 12);
+                    uint32_t reflen = 0;
+                    for (uint32_t c = 0; c < n_cig; c++) {
+                        const uint32_t op = g32(r + 32 + l_name + 4 * c);
+                        if ((0x18Du >> (op & 15u)) & 1u) reflen += op >> 4;
+                    }
+                    if (reflen == 0) reflen = 1;
+                    char tmp[64];
+                    snprintf(tmp, sizeof tmp, ":%d-%d", pos, pos + (int32_t)reflen);
+                    if (k) t += ' ';
+                    t += (ref_id >= 0 && (size_t)ref_id < names.size()) ? names[(size_t)ref_id] : std::string("*");
+                    t += tmp;
+                }
+                rd_slot[(size_t)open_retained] = (uint32_t)rd_text.size();
+                rd_text.push_back(t);
+            }
+            open_retained = -1;
+            buffer_nonempty = false;
+            mlist.clear();
+        };
+        for (uint64_t i = 0; i < n_records; i++) {
+            const uint32_t st = state[i] & 3u;
+            if (st == 0) continue;
+            const uint8_t *r = R + recoff[i];
+            const uint8_t *name = r + 32;
+            const uint32_t l_name = r[8];
+            if (st == 2) {
+                if (prev && !(prev_len == l_name && memcmp(prev, name, l_name) == 0)) flush();   // filter.py:115-133
+                mlist.push_back(i);
+            } else if (buffer_nonempty) flush();                                                 // filter.py:176-187
+            prev = name;
+            prev_len = l_name;
+            if (st == 2 && (state[i] & 4u)) buffer_nonempty = true;
+            if (keep[i] == 2) open_retained = (long long)i;
+        }
+        flush();                                                                                 // filter.py:197-199
+    }
+
+    // ---- kept records, in output order
+    std::vector<uint32_t> order;
+    order.reserve(n_records);
+    for (uint64_t i = 0; i < n_records; i++)
+        if (keep[i]) order.push_back((uint32_t)i);
+    if (sort)   // samtools sort: (tid, pos, reverse strand), unmapped tid = -1 last; stable
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            const uint8_t *ra = R + recoff[a], *rb = R + recoff[b];
+            const uint32_t ta = g32(ra), tb = g32(rb);   // -1 as unsigned sorts last
+            if (ta != tb) return ta < tb;
+            const int32_t pa = (int32_t)g32(ra + 4), pb = (int32_t)g32(rb + 4);
+            if (pa != pb) return pa < pb;
+            return ((g16(ra + 14) >> 4) & 1u) < ((g16(rb + 14) >> 4) & 1u);
+        });
+
+    // ---- modified copies of the retained multimappers
+    std::vector<std::vector<uint8_t>> owned;
+    std::vector<Span> spans;
+    spans.reserve(order.size() + 1);
+    std::vector<uint8_t> head;
+    {
+        const size_t lt = strlen(header_text);
+        head.insert(head.end(), {'B', 'A', 'M', 1});
+        uint8_t b4[4];
+        p32(b4, (uint32_t)lt);
+        head.insert(head.end(), b4, b4 + 4);
+        head.insert(head.end(), header_text, header_text + lt);
+        p32(b4, (uint32_t)names.size());
+        head.insert(head.end(), b4, b4 + 4);
+        for (size_t k = 0; k < names.size(); k++) {
+            p32(b4, (uint32_t)names[k].size() + 1);
+            head.insert(head.end(), b4, b4 + 4);
+            head.insert(head.end(), names[k].begin(), names[k].end());
+            head.push_back(0);
+            p32(b4, lengths[k]);
+            head.insert(head.end(), b4, b4 + 4);
+        }
+    }
+    spans.push_back({head.data(), head.size()});
+    owned.reserve(64);
+    size_t n_mod = 0;
+    for (uint32_t i : order) n_mod += keep[i] == 2;
+    owned.resize(n_mod);
+    size_t mi = 0;
+    for (uint32_t i : order) {
+        const uint8_t *r = R + recoff[i];
+        const uint32_t bs = g32(r - 4);
+        if (keep[i] != 2) {
+            spans.push_back({r - 4, (size_t)bs + 4});
+            continue;
+        }
+        const uint32_t l_name = r[8], n_cig = g16(r + 12);
+        const int32_t l_seq = (int32_t)g32(r + 16);
+        const uint8_t *aux = r + 32 + l_name + 4 * (size_t)n_cig + ((size_t)l_seq + 1) / 2 + (size_t)l_seq, *end = r + bs;
+        std::vector<uint8_t> &o = owned[mi++];
+        o.assign(r - 4, aux);
+        for (const uint8_t *a = aux; a < end;) {   // drop an existing RD tag (pysam set_tag replaces it)
+            const size_t fs = aux_field_size(a, end);
+            if (!fs) return wfail(err, errlen, SD_ERR_FORMAT, "%s: malformed tag in record %u", in_path, i);
+            if (!(a[0] == 'R' && a[1] == 'D')) o.insert(o.end(), a, a + fs);
+            a += fs;
+        }
+        const std::string &t = rd_text[rd_slot.empty() ? 0 : rd_slot[i]];
+        o.push_back('R'); o.push_back('D'); o.push_back('Z');
+        o.insert(o.end(), t.begin(), t.end());
+        o.push_back(0);
+        p32(o.data(), (uint32_t)o.size() - 4);
+        p16(o.data() + 4 + 14, g16(o.data() + 4 + 14) & ~0x900u);   // is_secondary = is_supplementary = False
+        spans.push_back({o.data(), o.size()});
+    }
+
+    // ---- BGZF: the output stream is cut into 0xFF00-byte payloads, compressed independently
+    std::vector<size_t> start(spans.size() + 1, 0);
+    for (size_t k = 0; k < spans.size(); k++) start[k + 1] = start[k] + spans[k].n;
+    const size_t total = start.back();
+    const size_t payload = 0xFF00;
+    const size_t n_blocks = (total + payload - 1) / payload;
+    std::vector<std::vector<uint8_t>> blocks(n_blocks);
+    std::atomic<int> bad(0);
+    pfor(n_blocks, threads, [&](size_t b) {
+        const size_t lo = b * payload, hi = std::min(total, lo + payload), len = hi - lo;
+        std::vector<uint8_t> in(len);
+        size_t k = (size_t)(std::upper_bound(start.begin(), start.end(), lo) - start.begin()) - 1, w = 0, at = lo;
+        while (w < len) {
+            const size_t off = at - start[k], take = std::min(spans[k].n - off, len - w);
+            memcpy(in.data() + w, spans[k].p + off, take);
+            w += take;
+            at += take;
+            k++;
+        }
+        std::vector<uint8_t> &out = blocks[b];
+        out.resize(0x10000 + 64);
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = 1; return; }
+        zs.next_in = in.data();
+        zs.avail_in = (uInt)len;
+        zs.next_out = out.data() + 18;
+        zs.avail_out = (uInt)(0x10000 - 18 - 8);
+        const int zr = deflate(&zs, Z_FINISH);
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        if (zr != Z_STREAM_END) { bad = 1; return; }
+        const size_t bsize = 18 + clen + 8;
+        static const uint8_t hd[12] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0};
+        memcpy(out.data(), hd, 12);
+        out[12] = 66; out[13] = 67; out[14] = 2; out[15] = 0;
+        p16(out.data() + 16, (uint32_t)bsize - 1);
+        p32(out.data() + 18 + clen, (uint32_t)crc32(crc32(0L, Z_NULL, 0), in.data(), (uInt)len));
+        p32(out.data() + 18 + clen + 4, (uint32_t)len);
+        out.resize(bsize);
+    });
+    if (bad) return wfail(err, errlen, SD_ERR_LIMIT, "BGZF compression failed (block does not fit 64 KiB)");
+    FILE *fh = fopen(out_path, "wb");
+    if (!fh) return wfail(err, errlen, SD_ERR_IO, "cannot create %s", out_path);
+    for (auto &b : blocks)
+        if (fwrite(b.data(), 1, b.size(), fh) != b.size()) { fclose(fh); return wfail(err, errlen, SD_ERR_IO, "short write on %s", out_path); }
+    static const uint8_t eof_block[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 66, 67, 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    fwrite(eof_block, 1, sizeof eof_block, fh);
+    fclose(fh);
+    if (n_written) *n_written = order.size();
+    return SD_OK;
+}

@@ -19,6 +19,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "sd_bamio.h"
 #include "slamdunk_b200.h"
 
 namespace {
@@ -92,20 +93,6 @@ void parallel_for(size_t n, int threads, F f) {
 inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 inline int32_t rdi32(const uint8_t *p) { return (int32_t)rd32(p); }
-
-// Byte buffer without the zero fill of std::vector (the decoder overwrites every byte anyway).
-struct RawBuf {
-    uint8_t *p = nullptr;
-    size_t n = 0;
-    RawBuf() {}
-    explicit RawBuf(size_t bytes) : p((uint8_t *)malloc(bytes ? bytes : 1)), n(bytes) {}
-    RawBuf(const RawBuf &) = delete;
-    RawBuf &operator=(const RawBuf &) = delete;
-    ~RawBuf() { free(p); }
-    void release() { free(p); p = nullptr; n = 0; }
-    uint8_t *data() const { return p; }
-    size_t size() const { return n; }
-};
 
 struct AuxInfo {
     float xi;
@@ -232,30 +219,8 @@ struct Owner {
 
 }  // namespace
 
-extern "C" void sd_hbatch_free(sd_hbatch *hb) {
-    if (!hb) return;
-    delete (Owner *)hb->opaque;
-    delete hb;
-}
-
-extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, uint32_t n_fasta, int options,
-                             uint32_t tile_reads, int threads, sd_hbatch **out, char *err, int errlen) {
-    if (!path || !out) return fail(err, errlen, SD_ERR_ARG, "sd_decode_bam: null argument");
-    *out = nullptr;
-    const bool want_mp = (options & SD_DECODE_MP) != 0, group = (options & SD_DECODE_GROUP) != 0;
-    if (tile_reads != 0 && tile_reads != 32) return fail(err, errlen, SD_ERR_ARG, "tile_reads must be 32 (or 0 = default)");
-    tile_reads = 32;
+int sd_bam_inflate_file(const char *path, int threads, RawBuf &raw, size_t *compressed_bytes, char *err, int errlen) {
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    const double t0 = now_s();
-    const bool timing = getenv("SD_DECODE_TIMING") != nullptr;
-    double tp = t0;
-    auto lap = [&](const char *what) {
-        if (!timing) return;
-        const double t = now_s();
-        fprintf(stderr, "[sd_decode_bam] %-14s %.4f s\n", what, t - tp);
-        tp = t;
-    };
-
     // ---- read the file
     FILE *fh = fopen(path, "rb");
     if (!fh) return fail(err, errlen, SD_ERR_IO, "cannot open %s", path);
@@ -270,7 +235,6 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     }
     fclose(fh);
 
-    lap("read file");
     // ---- BGZF block table
     struct Blk { size_t coff, clen, uoff, ulen; };
     std::vector<Blk> blks;
@@ -295,7 +259,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         utotal += isize;
         off += total;
     }
-    RawBuf raw(utotal);
+    raw.reset(utotal);
     if (!raw.data()) return fail(err, errlen, SD_ERR_NOMEM, "out of host memory");
     std::atomic<int> bad(0);
     parallel_for(blks.size(), threads, [&](size_t i) {
@@ -317,59 +281,46 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     if (bad) return fail(err, errlen, SD_ERR_FORMAT, "%s: corrupt BGZF block", path);
     const size_t compressed = file.size();
     file.release();
-    const double t1 = now_s();
-    lap("inflate");
+    if (compressed_bytes) *compressed_bytes = file.size();
+    return SD_OK;
+}
 
-    // ---- BAM header
+int sd_bam_parse_header(const RawBuf &raw, const char *path, std::string &text, std::vector<std::string> &names,
+                        std::vector<uint32_t> &lengths, size_t *after, char *err, int errlen) {
     if (raw.size() < 12 || memcmp(raw.data(), "BAM\1", 4) != 0) return fail(err, errlen, SD_ERR_FORMAT, "%s: not a BAM file", path);
-    Owner *own = new Owner();
-    sd_hbatch *hb = new sd_hbatch();
-    memset(hb, 0, sizeof *hb);
-    hb->opaque = own;
-    auto bail = [&](int code, const char *msg) {
-        sd_hbatch_free(hb);
-        return fail(err, errlen, code, "%s: %s", path, msg);
-    };
     size_t p = 4;
     const int32_t l_text = rdi32(raw.data() + p);
     p += 4;
-    if (l_text < 0 || p + (size_t)l_text + 4 > raw.size()) return bail(SD_ERR_FORMAT, "bad header length");
-    own->header.assign((const char *)raw.data() + p, strnlen((const char *)raw.data() + p, (size_t)l_text));
+    if (l_text < 0 || p + (size_t)l_text + 4 > raw.size()) return fail(err, errlen, SD_ERR_FORMAT, "%s: bad header length", path);
+    text.assign((const char *)raw.data() + p, strnlen((const char *)raw.data() + p, (size_t)l_text));
     p += (size_t)l_text;
     const int32_t n_ref = rdi32(raw.data() + p);
     p += 4;
-    if (n_ref < 0) return bail(SD_ERR_FORMAT, "bad reference count");
-    std::unordered_map<std::string, uint32_t> fasta_idx;
-    for (uint32_t i = 0; i < n_fasta; i++) fasta_idx.emplace(fasta_names[i], i);
-    std::vector<uint32_t> ref_map((size_t)n_ref, SD_REF_NONE);
+    if (n_ref < 0) return fail(err, errlen, SD_ERR_FORMAT, "%s: bad reference count", path);
+    names.clear();
+    lengths.clear();
     for (int32_t i = 0; i < n_ref; i++) {
-        if (p + 4 > raw.size()) return bail(SD_ERR_FORMAT, "truncated reference table");
+        if (p + 4 > raw.size()) return fail(err, errlen, SD_ERR_FORMAT, "%s: truncated reference table", path);
         const int32_t l_name = rdi32(raw.data() + p);
-        if (l_name < 1 || p + 4 + (size_t)l_name + 4 > raw.size()) return bail(SD_ERR_FORMAT, "truncated reference table");
-        std::string nm((const char *)raw.data() + p + 4, (size_t)l_name - 1);
-        own->lengths.push_back(rd32(raw.data() + p + 4 + l_name));
-        if (n_fasta == 0) {   // no FASTA table: chromosome index = BAM reference id (the filter's coordinate space)
-            if ((uint32_t)i < SD_REF_NONE) ref_map[(size_t)i] = (uint32_t)i;
-        } else {
-            auto it = fasta_idx.find(nm);
-            if (it != fasta_idx.end()) ref_map[(size_t)i] = it->second;
-        }
-        own->names.push_back(nm);
+        if (l_name < 1 || p + 4 + (size_t)l_name + 4 > raw.size()) return fail(err, errlen, SD_ERR_FORMAT, "%s: truncated reference table", path);
+        names.emplace_back((const char *)raw.data() + p + 4, (size_t)l_name - 1);
+        lengths.push_back(rd32(raw.data() + p + 4 + l_name));
         p += 8 + (size_t)l_name;
     }
-    for (auto &s : own->names) own->name_ptrs.push_back(const_cast<char *>(s.c_str()));
-    hb->header_text = const_cast<char *>(own->header.c_str());
-    hb->n_ref = (uint32_t)n_ref;
-    hb->ref_names = own->name_ptrs.data();
-    hb->ref_lengths = own->lengths.data();
+    *after = p;
+    return SD_OK;
+}
 
-    // ---- record index
+int sd_bam_index_records(const RawBuf &raw, size_t begin, int32_t n_ref, int threads, std::vector<size_t> &recoff,
+                         const char *path, char *err, int errlen) {
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     // BAM records carry no sync marker, so finding them is a dependent chain of block_size reads.  The chain is cut
     // into chunks: each chunk guesses its first record by a plausibility test that must hold for a run of consecutive
     // records, walks from there, and the pieces are accepted only if every chunk ends exactly where the next one
     // started -- which proves the guesses were on the true chain.  Otherwise the plain serial walk is used.
-    const size_t rec_begin = p;
-    std::vector<size_t> recoff;
+    const size_t rec_begin = begin;
+    size_t p = begin;
+    recoff.clear();
     {
         const uint8_t *R = raw.data();
         const size_t N = raw.size();
@@ -445,11 +396,85 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
             recoff.clear();
             while (p + 4 <= N) {
                 const int32_t bs = rdi32(R + p);
-                if (bs < 32 || p + 4 + (size_t)bs > N) return bail(SD_ERR_FORMAT, "truncated alignment record");
+                if (bs < 32 || p + 4 + (size_t)bs > N) return fail(err, errlen, SD_ERR_FORMAT, "%s: truncated alignment record", path);
                 recoff.push_back(p + 4);
                 p += 4 + (size_t)bs;
             }
         }
+    }
+    return SD_OK;
+}
+
+extern "C" void sd_hbatch_free(sd_hbatch *hb) {
+    if (!hb) return;
+    delete (Owner *)hb->opaque;
+    delete hb;
+}
+
+extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, uint32_t n_fasta, int options,
+                             uint32_t tile_reads, int threads, sd_hbatch **out, char *err, int errlen) {
+    if (!path || !out) return fail(err, errlen, SD_ERR_ARG, "sd_decode_bam: null argument");
+    *out = nullptr;
+    const bool want_mp = (options & SD_DECODE_MP) != 0, group = (options & SD_DECODE_GROUP) != 0;
+    if (tile_reads != 0 && tile_reads != 32) return fail(err, errlen, SD_ERR_ARG, "tile_reads must be 32 (or 0 = default)");
+    tile_reads = 32;
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const double t0 = now_s();
+    const bool timing = getenv("SD_DECODE_TIMING") != nullptr;
+    double tp = t0;
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const double t = now_s();
+        fprintf(stderr, "[sd_decode_bam] %-14s %.4f s\n", what, t - tp);
+        tp = t;
+    };
+
+    RawBuf raw;
+    size_t compressed = 0;
+    {
+        const int rc = sd_bam_inflate_file(path, threads, raw, &compressed, err, errlen);
+        if (rc != SD_OK) return rc;
+    }
+    const double t1 = now_s();
+    lap("inflate");
+
+    // ---- BAM header
+    Owner *own = new Owner();
+    sd_hbatch *hb = new sd_hbatch();
+    memset(hb, 0, sizeof *hb);
+    hb->opaque = own;
+    auto bail = [&](int code, const char *msg) {
+        sd_hbatch_free(hb);
+        return fail(err, errlen, code, "%s: %s", path, msg);
+    };
+    size_t p = 0;
+    {
+        const int rc = sd_bam_parse_header(raw, path, own->header, own->names, own->lengths, &p, err, errlen);
+        if (rc != SD_OK) { sd_hbatch_free(hb); return rc; }
+    }
+    const int32_t n_ref = (int32_t)own->names.size();
+    std::unordered_map<std::string, uint32_t> fasta_idx;
+    for (uint32_t i = 0; i < n_fasta; i++) fasta_idx.emplace(fasta_names[i], i);
+    std::vector<uint32_t> ref_map((size_t)n_ref, SD_REF_NONE);
+    for (int32_t i = 0; i < n_ref; i++) {
+        if (n_fasta == 0) {   // no FASTA table: chromosome index = BAM reference id (the filter's coordinate space)
+            if ((uint32_t)i < SD_REF_NONE) ref_map[(size_t)i] = (uint32_t)i;
+        } else {
+            auto it = fasta_idx.find(own->names[(size_t)i]);
+            if (it != fasta_idx.end()) ref_map[(size_t)i] = it->second;
+        }
+    }
+    for (auto &s_ : own->names) own->name_ptrs.push_back(const_cast<char *>(s_.c_str()));
+    hb->header_text = const_cast<char *>(own->header.c_str());
+    hb->n_ref = (uint32_t)n_ref;
+    hb->ref_names = own->name_ptrs.data();
+    hb->ref_lengths = own->lengths.data();
+
+    // ---- record index
+    std::vector<size_t> recoff;
+    {
+        const int rc = sd_bam_index_records(raw, p, n_ref, threads, recoff, path, err, errlen);
+        if (rc != SD_OK) { sd_hbatch_free(hb); return rc; }
     }
     const size_t n = recoff.size();
     lap("record index");
@@ -678,7 +703,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     hb->seconds_inflate = t1 - t0;
     hb->seconds_decode = t2 - t1;
     hb->compressed_bytes = compressed;
-    hb->inflated_bytes = utotal;
+    hb->inflated_bytes = raw.size();
     *out = hb;
     return SD_OK;
 }

@@ -130,7 +130,7 @@ __device__ int utr_hits(const FilterTables &T, uint32_t chrom, int64_t pos, int6
 }
 
 __global__ void filter_pass2(const ReadInfo *info, const uint64_t *name_hash, uint64_t n, FilterTables T, uint8_t *keep,
-                             unsigned long long *stats) {
+                             uint8_t *utr_hit, unsigned long long *stats) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || info[i].state != 2) return;
     // group head?  the previous survivor must be unique or carry another name (filter.py:115,173)
@@ -157,6 +157,7 @@ __global__ void filter_pass2(const ReadInfo *info, const uint64_t *name_hash, ui
         if (r.state != 2 || name_hash[k] != h0) break;
         uint32_t bed[SD_FILTER_MAX_HITS], name[SD_FILTER_MAX_HITS];
         const int nh = utr_hits(T, r.chrom, r.pos, r.end, bed, name, &overflow);
+        if (nh > 0 && utr_hit) utr_hit[k] = 4u;   // remembered for the RD tag text (every multimapper belongs to one group)
         const bool first_group = (n_keys == 0);                       // filter.py:147
         for (int h = 0; h < nh; h++) {
             int found = -1;
@@ -178,6 +179,11 @@ __global__ void filter_pass2(const ReadInfo *info, const uint64_t *name_hash, ui
     }
 }
 
+__global__ void export_state(const ReadInfo *info, uint64_t n, uint8_t *state) {   // state[] arrives holding the UTR-hit bits
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) state[i] = (uint8_t)((info[i].state == 3u ? 0u : info[i].state) | state[i]);
+}
+
 template <class T>
 int to_device(sd_ctx *ctx, T **dst, const std::vector<T> &v) {
     SD_CUDA(ctx, cudaMalloc(dst, std::max<size_t>(1, v.size()) * sizeof(T)));
@@ -189,7 +195,7 @@ int to_device(sd_ctx *ctx, T **dst, const std::vector<T> &v) {
 
 extern "C" int sd_filter(sd_ctx *ctx, const sd_batch *b, const sd_params *p, const uint64_t *d_name_hash,
                          const uint32_t *h_utr_chrom, const int64_t *h_utr_start, const int64_t *h_utr_stop,
-                         const uint32_t *h_utr_name_id, uint32_t n_utr, uint8_t *d_keep, int64_t *d_stats) {
+                         const uint32_t *h_utr_name_id, uint32_t n_utr, uint8_t *d_keep, int64_t *d_stats, uint8_t *d_state) {
     if (!ctx || !b || !p || !d_keep || !d_stats) return sd_fail(ctx, SD_ERR_ARG, "sd_filter: null argument");
     if (b->tile_reads != 32) return sd_fail(ctx, SD_ERR_ARG, "tile_reads must be 32");
     const bool multimap = h_utr_chrom != nullptr;
@@ -199,6 +205,7 @@ extern "C" int sd_filter(sd_ctx *ctx, const sd_batch *b, const sd_params *p, con
     const uint64_t n_pad = (uint64_t)b->n_tiles * 32;
     SD_CUDA(ctx, cudaMemsetAsync(d_stats, 0, SD_NSTAT * sizeof(int64_t), ctx->stream));
     SD_CUDA(ctx, cudaMemsetAsync(d_keep, 0, std::max<uint64_t>(1, b->n_reads), ctx->stream));
+    if (d_state) SD_CUDA(ctx, cudaMemsetAsync(d_state, 0, std::max<uint64_t>(1, b->n_reads), ctx->stream));
     if (b->n_tiles == 0) { SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return SD_OK; }
     ReadInfo *info = nullptr;
     uint8_t *keep_pad = nullptr;
@@ -242,10 +249,14 @@ extern "C" int sd_filter(sd_ctx *ctx, const sd_batch *b, const sd_params *p, con
             return rc;
         }
         FilterTables T{d_cb, d_s, d_e, d_m, d_nm, d_bi, n_chrom};
-        filter_pass2<<<(unsigned)((n_pad + 127) / 128), 128, 0, ctx->stream>>>(info, d_name_hash, b->n_reads, T, keep_pad, st);
+        filter_pass2<<<(unsigned)((n_pad + 127) / 128), 128, 0, ctx->stream>>>(info, d_name_hash, b->n_reads, T, keep_pad, d_state, st);
         ctx->launches++;
     }
     SD_CUDA(ctx, cudaMemcpyAsync(d_keep, keep_pad, b->n_reads, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_state) {
+        export_state<<<(unsigned)((b->n_reads + 255) / 256), 256, 0, ctx->stream>>>(info, b->n_reads, d_state);
+        ctx->launches++;
+    }
     cudaError_t e1 = cudaGetLastError();
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     cudaFree(info); cudaFree(keep_pad);

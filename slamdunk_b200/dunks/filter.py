@@ -3,13 +3,14 @@ filter.Filter (slamdunk/dunks/filter.py:213-315), same signature, same log lines
 @PG header rewrite, coordinate-sorted output.
 
 Device: per-read predicates (MAPQ / identity / NM) or, when a BED file is given, the
-multimapper-retention logic (sd_filter).  Host: BAM decode (C++), and writing the surviving records
-with the plain Python BAM codec -- the native BAM writer / BAI index is the next row of the build
-plan, so `pysam.index` has no equivalent here yet and `slamdunk_b200 count` reads
-the whole file instead of using an index.
+multimapper-retention logic (sd_filter).  Host (C++, all threads): BAM decode (sd_decode_bam) and the
+sorted, BGZF-compressed output with the RD tags (sd_rewrite_bam).  No BAI index is written
+(`pysam.index`, filter.py:313): `slamdunk_b200 count` streams the whole file and joins reads to UTRs
+on the device, so nothing downstream needs one.
 """
 from __future__ import print_function
 
+import ctypes
 import os
 
 import numpy as np
@@ -24,48 +25,6 @@ from ..version import __bam_version__, __version__
 OPTIONS = {"device": 0, "threads": 0, "stats": None}
 
 
-def _rd_tags(records, bam_names, keep, state, state_hits):
-    """RD:Z text of every record written by dumpBufferToBam (filter.py:56-65): the reference's
-    `multimapList` string, including its quirk of not being reset by a unique read that finds the
-    buffer empty (filter.py:176-187)."""
-    tags = {}
-    mlist = []
-    prev = ""
-    open_retained = None
-    buffer_nonempty = False
-    for i, r in enumerate(records):
-        st = state[i]
-        if st == 0:
-            continue
-        if st == 2:
-            if r.qname != prev and prev != "":
-                if open_retained is not None:
-                    tags[open_retained] = " ".join(mlist)
-                open_retained = None
-                buffer_nonempty = False
-                mlist = []
-            mlist.append("%s:%d-%d" % (bam_names[r.ref_id], r.pos, r.reference_end))
-            prev = r.qname
-        else:
-            if buffer_nonempty:
-                if open_retained is not None:
-                    tags[open_retained] = " ".join(mlist)
-                open_retained = None
-                buffer_nonempty = False
-                mlist = []
-            prev = r.qname
-        # group bookkeeping: the device tells us which record of the group is retained; whether the
-        # buffer is non-empty equals "some alignment of the open group hit a UTR"
-        if st == 2 and state_hits[i]:
-            buffer_nonempty = True
-        if keep[i] == 2:
-            open_retained = i
-    if open_retained is not None:
-        tags[open_retained] = " ".join(mlist)
-    return tags
-
-
-
 def Filter(inputBAM, outputBAM, log, bed, MQ=2, minIdentity=0.8, NM=-1, printOnly=False, verbose=True, force=False):
     if not (printOnly or checkStep([inputBAM], [outputBAM], force)):
         print("Skipped filtering for " + inputBAM, file=log)
@@ -77,7 +36,7 @@ def Filter(inputBAM, outputBAM, log, bed, MQ=2, minIdentity=0.8, NM=-1, printOnl
         params = make_params(filter_on=True, filter_mq=MQ, filter_min_identity=minIdentity, filter_max_nm=NM)
         if bed is None:
             print("#No bed-file supplied. Running default filtering on " + inputBAM + ".", file=log)
-            keep, stats = eng.filter(db, params)
+            keep, stats, state = eng.filter(db, params)
             utr_rows = None
         else:
             print("#Bed-file supplied. Running multimap retention filtering strategy on " + inputBAM + ".", file=log)
@@ -90,7 +49,7 @@ def Filter(inputBAM, outputBAM, log, bed, MQ=2, minIdentity=0.8, NM=-1, printOnl
             ni = np.array([name_ids.setdefault(u.name, len(name_ids)) for u in utr_rows], dtype=np.uint32)
             import torch
             nh = torch.from_numpy(hb.name_hash().view(np.int64).copy()).to(eng.device)
-            keep, stats = eng.filter(db, params, nh, (ci, st, sp, ni))
+            keep, stats, state = eng.filter(db, params, nh, (ci, st, sp, ni))
             if stats[L.SD_S_SLOWPATH] > 0:
                 raise RuntimeError("multimapper group exceeds the device limits (more than 32 UTR names / hits per alignment)")
     finally:
@@ -111,39 +70,8 @@ def Filter(inputBAM, outputBAM, log, bed, MQ=2, minIdentity=0.8, NM=-1, printOnl
     OPTIONS["stats"] = dict(mapped=mapped, unmapped=unmapped, filtered=filtered, mqfiltered=mqf, idfiltered=idf,
                             nmfiltered=nmf, multimapper=multimapper)
 
-    # ---- write the output BAM (host; plain codec)
-    text, refs, records = bamio.read_bam(inputBAM)
-    assert len(records) == len(keep)
-    bam_names = [n for n, _l in refs]
-    written = []
-    rd = {}
-    if bed is not None and (keep == 2).any():
-        rec = hb.rec_array()[:len(records)]
-        flags = rec[:, 1] >> 24
-        mapq = (rec[:, 1] >> 16) & 0xFF
-        xi = rec[:, 2].view(np.float32).astype(np.float64)
-        nm = rec[:, 4] & 0xFFFF
-        surv = ((flags & L.SD_F_UNMAPPED) == 0) & ~(xi < minIdentity) & ~((NM > -1) & (nm > NM))
-        state = np.where(surv, np.where(mapq == 0, 2, 1), 0)
-        hits = np.zeros(len(records), dtype=bool)
-        by_chrom = {}
-        for u in utr_rows:
-            by_chrom.setdefault(u.chromosome, []).append((u.start, u.stop + 1))
-        for i in np.nonzero(state == 2)[0]:
-            r = records[int(i)]
-            e = r.reference_end
-            for a, b in by_chrom.get(bam_names[r.ref_id], ()):
-                if a < e and b > r.pos:
-                    hits[i] = True
-                    break
-        rd = _rd_tags(records, bam_names, keep, state, hits)
-    for i, r in enumerate(records):
-        if keep[i] == 1:
-            written.append(r)
-        elif keep[i] == 2:
-            r.set_tag("RD", rd.get(i, ""), "Z")
-            r.flag &= ~(bamio.FLAG_SECONDARY | bamio.FLAG_SUPPLEMENTARY)
-            written.append(r)
+    text = hb.header_text
+    n_records = hb.n_reads
     hb.close()
     header = bamio.parse_header_text(text)
     if "RG" in header and len(header["RG"]) > 0:                     # filter.py:276-295
@@ -164,4 +92,17 @@ def Filter(inputBAM, outputBAM, log, bed, MQ=2, minIdentity=0.8, NM=-1, printOnl
         header["RG"][0]["DS"] = str(info)
     pg = {"ID": "slamdunk", "PN": "slamdunk filter v" + __version__, "VN": __bam_version__}   # filter.py:298
     header.setdefault("PG", []).append(pg)
-    bamio.write_bam(outputBAM, bamio.header_dict_to_text(header), refs, bamio.sort_records(written))
+    # ---- write the output BAM: surviving records byte for byte, RD:Z + cleared secondary/supplementary on retained
+    # multimappers (filter.py:56-65), coordinate sorted (filter.py:304-310), BGZF-compressed on the host threads
+    keep = np.ascontiguousarray(keep, dtype=np.uint8)
+    state = np.ascontiguousarray(state, dtype=np.uint8)
+    assert len(keep) == n_records
+    lib = L.load()
+    err = ctypes.create_string_buffer(512)
+    written = ctypes.c_uint64(0)
+    rc = lib.sd_rewrite_bam(os.fsencode(inputBAM), os.fsencode(outputBAM), bamio.header_dict_to_text(header).encode(),
+                            keep.ctypes.data, state.ctypes.data, n_records, 1, 6, OPTIONS["threads"], ctypes.byref(written),
+                            err, len(err))
+    if rc != L.SD_OK:
+        raise IOError("sd_rewrite_bam: " + err.value.decode("utf-8", "replace"))
+    OPTIONS["stats"]["written"] = int(written.value)

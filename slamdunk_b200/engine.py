@@ -322,11 +322,12 @@ class CountEngine(object):
     def filter(self, dbatch: DeviceBatch, params: L.Params, name_hash: Optional[torch.Tensor] = None, utrs=None):
         """filter.Filter decisions (sd_filter).  utrs: None for the default branch, or
         (chrom_idx, start, stop, name_id) numpy arrays in BED order for multimapper retention.
-        -> (keep uint8 numpy [n_reads], stats int64 numpy [SD_NSTAT])"""
+        -> (keep uint8 numpy [n_reads], stats int64 numpy [SD_NSTAT], state uint8 numpy [n_reads] for sd_rewrite_bam)"""
         n = int(dbatch.batch.n_reads)
         with torch.cuda.stream(self.stream):
             keep = torch.zeros(max(1, n), dtype=torch.uint8, device=self.device)
             stats = torch.zeros(L.SD_NSTAT, dtype=torch.int64, device=self.device)
+            state = torch.zeros(max(1, n), dtype=torch.uint8, device=self.device)
         self.stream.synchronize()
         if utrs is None:
             args = (None, None, None, None, None, 0)
@@ -337,8 +338,8 @@ class CountEngine(object):
             ni = np.ascontiguousarray(utrs[3], dtype=np.uint32)
             args = (_t_ptr(name_hash), _np_ptr(ci), _np_ptr(st), _np_ptr(sp), _np_ptr(ni), len(ci))
         self._chk(self.lib.sd_filter(self.ctx, ctypes.byref(dbatch.batch), ctypes.byref(params), args[0], args[1], args[2],
-                                     args[3], args[4], args[5], _t_ptr(keep), _t_ptr(stats)), "sd_filter")
-        return keep.cpu().numpy()[:n], stats.cpu().numpy()
+                                     args[3], args[4], args[5], _t_ptr(keep), _t_ptr(stats), _t_ptr(state)), "sd_filter")
+        return keep.cpu().numpy()[:n], stats.cpu().numpy(), state.cpu().numpy()[:n]
 
     # -- outputs -----------------------------------------------------------------------
     def results(self):

@@ -294,3 +294,92 @@ def test_native_float_repr_equals_python_repr():
             samples.append(x)
     for x in samples:
         assert fmt(x) == repr(x), (x, fmt(x), repr(x))
+
+
+def _filter_states(records, bam_names, bed_rows, min_identity, nm):
+    """What sd_filter reports next to keep[]: survivor class (0 / 1 unique / 2 multimapper) | 4 when a multimapper overlaps a
+    UTR (filter.py:137) -- here derived on the host from the decoded records, for the writer test."""
+    state = np.zeros(len(records), dtype=np.uint8)
+    for i, r in enumerate(records):
+        if r.flag & 4:
+            continue
+        if float(np.float32(r.get_tag("XI"))) < min_identity or (nm > -1 and int(r.get_tag("NM")) > nm):
+            continue
+        state[i] = 2 if r.mapq == 0 else 1
+        if state[i] == 2:
+            for ch, start, stop, _n, _s in bed_rows:
+                if ch == bam_names[r.ref_id] and start < r.reference_end and stop + 1 > r.pos:
+                    state[i] |= 4
+                    break
+    return state
+
+
+def _rec_tuple(r):
+    return (r.qname, r.flag, r.ref_id, r.pos, r.mapq, tuple(r.cigar), r.next_ref_id, r.next_pos, r.tlen, r.seq,
+            None if r.qual is None else tuple(r.qual), tuple((t, ty, tuple(v) if isinstance(v, list) else v) for t, ty, v in r.tags))
+
+
+@pytest.mark.parametrize("seed,use_bed,nm,threads", [(501, True, -1, 3), (502, True, 4, 1), (503, False, -1, 4)])
+def test_native_bam_writer_matches_python_codec(tmp_path, seed, use_bed, nm, threads):
+    """sd_rewrite_bam (host only): kept records byte-identical, RD tags as the oracle derives them from the reference's
+    multimapList, samtools-sort order, and a BGZF stream the independent Python codec reads back."""
+    import ctypes
+    from oracle import oracle
+    c = simdata.make_filter_case(str(tmp_path), seed=seed, n_reads=3000, topn=4)
+    text, refs, records = bamio.read_bam(c.bam)
+    bam_names = [n for n, _ in refs]
+    bed_rows = oracle.read_bed(c.bed) if use_bed else None
+    keep, rd, _stats = oracle.filter_records(records, bam_names, bed_rows, 2, 0.9, nm)
+    state = _filter_states(records, bam_names, bed_rows or [], 0.9, nm)
+    if use_bed:
+        assert (keep == 2).any()
+    want = []
+    for i, r in enumerate(records):
+        if keep[i] == 1:
+            want.append(r.copy())
+        elif keep[i] == 2:
+            w = r.copy()
+            w.flag &= ~0x900
+            w.set_tag("RD", rd[i], "Z")
+            want.append(w)
+    want = bamio.sort_records(want)
+    out = str(tmp_path / "w.bam")
+    new_text = text + "@CO\trewritten\n"
+    err = ctypes.create_string_buffer(256)
+    nw = ctypes.c_uint64(0)
+    lib = L.load()
+    rc = lib.sd_rewrite_bam(c.bam.encode(), out.encode(), new_text.encode(), keep.ctypes.data, state.ctypes.data, len(records), 1, 6,
+                            threads, ctypes.byref(nw), err, len(err))
+    assert rc == 0, err.value
+    assert nw.value == len(want)
+    text2, refs2, got = bamio.read_bam(out)
+    assert text2 == new_text and refs2 == refs
+    assert [_rec_tuple(r) for r in got] == [_rec_tuple(r) for r in want]
+    # wrong decision count is refused, not silently truncated
+    rc = lib.sd_rewrite_bam(c.bam.encode(), out.encode(), new_text.encode(), keep.ctypes.data, state.ctypes.data, len(records) - 1, 1, 6,
+                            threads, ctypes.byref(nw), err, len(err))
+    assert rc != 0 and b"decisions" in err.value
+
+
+def test_native_bam_writer_replaces_existing_rd_tag_and_handles_empty(tmp_path):
+    import ctypes
+    recs = [bamio.BamRecord("m1", 0x100, 0, 10, 0, "20M", "A" * 20, [30] * 20, [("RD", "Z", "old"), ("XI", "f", 1.0), ("NM", "C", 0),
+                                                                                    ("ZB", "Bs", [1, -2, 3])]),
+            bamio.BamRecord("u1", 0, 0, 5, 60, "20M", "C" * 20, [30] * 20, [("XI", "f", 1.0)])]
+    src = str(tmp_path / "s.bam")
+    bamio.write_bam(src, "@HD\tVN:1.0\n", [("chr1", 1000)], recs)
+    lib = L.load()
+    err = ctypes.create_string_buffer(256)
+    nw = ctypes.c_uint64(0)
+    keep = np.array([2, 1], dtype=np.uint8)
+    state = np.array([2 | 4, 1], dtype=np.uint8)
+    out = str(tmp_path / "o.bam")
+    assert lib.sd_rewrite_bam(src.encode(), out.encode(), b"@HD\tVN:1.0\n", keep.ctypes.data, state.ctypes.data, 2, 1, 6, 2,
+                              ctypes.byref(nw), err, len(err)) == 0, err.value
+    _t, _r, got = bamio.read_bam(out)
+    assert [r.qname for r in got] == ["u1", "m1"]
+    assert got[1].flag == 0 and got[1].tags == [("XI", "f", 1.0), ("NM", "C", 0), ("ZB", "Bs", [1, -2, 3]), ("RD", "Z", "chr1:10-30")]
+    keep[:] = 0
+    assert lib.sd_rewrite_bam(src.encode(), out.encode(), b"@HD\tVN:1.0\n", keep.ctypes.data, None, 2, 1, 6, 2,
+                              ctypes.byref(nw), err, len(err)) == 0, err.value
+    assert nw.value == 0 and bamio.read_bam(out)[2] == []
