@@ -265,7 +265,7 @@ __device__ __forceinline__ uint32_t slow_count_t(const uint2 *rx, uint64_t ga, u
     return n;
 }
 
-__device__ __noinline__ int slow_read(const CountArgs &A, const ReadView &v, uint32_t mapq) {
+__device__ __noinline__ int slow_read(const CountArgs &A, const ReadView v, uint32_t mapq) {   // by value: the view stays in registers on the fast path
     int tc = 0;
     slow_for_each_hit(A, v, [&](int, bool) { tc++; });
     const bool is_tc = tc >= A.conv_threshold;
@@ -626,12 +626,15 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #ifndef SD_CLAIM
 #define SD_CLAIM 8   // consecutive tiles claimed per atomic
 #endif
+#ifndef SD_CTA_THREADS
+#define SD_CTA_THREADS 256
+#endif
 #ifndef SD_MIN_CTAS
 #define SD_MIN_CTAS(W) ((W) == 4 ? 4 : ((W) == 8 ? 3 : 1))   // resident 256-thread CTAs per SM the register budget is tuned for
 #endif
 
 template <int W>
-__global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __grid_constant__ CountArgs A) {
+__global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kernel(const __grid_constant__ CountArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
     const uint32_t warp_bytes = A.n_stages * stage_bytes + 128u;   // stages | barriers + tile qual offsets
@@ -672,6 +675,12 @@ __global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __g
         const uint32_t b_cig = (uint32_t)(t1.cig_off - t0.cig_off);
         const uint32_t b_mp = A.mp ? (uint32_t)(t1.mp_off - t0.mp_off) : 0u;
         s_qoff[stage] = t0.qual_off;
+#ifndef SD_NO_QUAL_PREFETCH
+        {   // pull the tile's base qualities into L2 two tiles ahead: the candidate test then pays L2, not DRAM latency
+            const uint32_t b_q = (uint32_t)(t1.qual_off - t0.qual_off) & ~15u;
+            if (b_q) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.qual + t0.qual_off), "r"(b_q) : "memory");
+        }
+#endif
         mbar_arrive_expect_tx(&full[stage], b_rec + b_seq + b_cig + b_mp);
         bulk_g2s(base, reinterpret_cast<const unsigned char *>(A.rec) + tile * b_rec, b_rec, &full[stage]);
         if (b_seq) bulk_g2s(base + A.cap_rec, reinterpret_cast<const unsigned char *>(A.seq) + t0.seq_off, b_seq, &full[stage]);
@@ -711,6 +720,14 @@ __global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __g
         // row offsets inside the tile: exclusive warp scan of the row sizes
         const uint32_t x = ((lseq + 7u) >> 3) | (ncig << 16);   // seq words | ncig << 16
         uint32_t xs = x, qs = lseq, ms = nmp;
+#ifndef SD_NO_UNIFORM_SCAN
+        int uni_pred = 0;
+        __match_all_sync(0xFFFFFFFFu, lseq | (ncig << 16), &uni_pred);
+        if (uni_pred && !A.mp) {   // every row of the tile has the same shape: offsets are lane multiples
+            xs = (lane + 1u) * x;
+            qs = (lane + 1u) * lseq;
+        } else
+#endif
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t tx = __shfl_up_sync(0xFFFFFFFFu, xs, d);
@@ -725,6 +742,8 @@ __global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __g
         xs -= x;
         qs -= lseq;
         ms -= nmp;
+        // (a tile fits one shared-memory stage, < 2^16 words per column, so the packed 16-bit sums cannot overflow)
+        const uint32_t seq_row = xs & 0xFFFFu, cig_row = xs >> 16;
 
         // @region filter
         const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu, ref = rmf & 0xFFFFu;
@@ -744,7 +763,7 @@ __global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __g
 
         // Is every read of this tile a single match block (no clips, no indels)?  Warp-uniform: the decoder and
         // the generator group such reads into their own tiles, so most warps take the lean path.
-        const uint32_t cig0 = ncig ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq)[xs >> 16] : 0u;
+        const uint32_t cig0 = ncig ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq)[cig_row] : 0u;
         const bool uni_simple = __all_sync(0xFFFFFFFFu, !go || (ncig == 1u && ((0x181u >> (cig0 & 15u)) & 1u)));
         // @region view_setup
         int tc = 0;
@@ -752,9 +771,9 @@ __global__ void __launch_bounds__(256, SD_MIN_CTAS(W)) sd_count_kernel(const __g
             const uint32_t clen = __ldg(&A.chrom_len[ref]);
             if (pos >= 0 && (uint32_t)pos < clen) {
                 ReadView v;
-                v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (xs & 0xFFFFu);
+                v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + seq_row;
                 v.qual = A.qual + s_qoff[stage] + qs;
-                v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + (xs >> 16);
+                v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + cig_row;
                 v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
                 v.lseq = lseq;
                 v.ncig = ncig;
@@ -1179,7 +1198,7 @@ static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool tim
     if (128u + warp_bytes(n_stages) > (size_t)max_smem) n_stages = 1;
     if (128u + warp_bytes(n_stages) > (size_t)max_smem)
         return sd_fail(ctx, SD_ERR_LIMIT, "a 32-read tile needs %u bytes of shared memory; reads are too long for this kernel", stage_bytes);
-    uint32_t warps = (forced_warps >= 1 && forced_warps <= 8) ? (uint32_t)forced_warps : 8u;
+    uint32_t warps = (forced_warps >= 1 && forced_warps <= SD_CTA_THREADS / 32) ? (uint32_t)forced_warps : (uint32_t)(SD_CTA_THREADS / 32);
     while (warps > 1 && 128u + warps * warp_bytes(n_stages) > (size_t)max_smem / 2) warps--;   // keep >= 2 CTAs per SM possible
     while (warps > 1 && 128u + warps * warp_bytes(n_stages) > (size_t)max_smem) warps--;
     A.n_stages = n_stages;
