@@ -81,9 +81,12 @@ typedef struct sd_tile {
 
 /*
  * Column layouts (rows of one tile are consecutive, in record order, tiles padded to 16 bytes):
- *   seq   "sliced 4-bit": for every 8 bases one 32-bit word whose byte p (p = 0..3) is bit-plane
- *         p of the BAM nibble code (bit0 A, bit1 C, bit2 G, bit3 T; N = all four, '=' = none);
- *         bit i of each byte is base 8w+i.  ceil(l_seq/8) words per read, pad bits zero.
+ *   seq   "plane-sliced 4-bit", group-major per tile: a group is 32 bases of one read as four 32-bit words, word p
+ *         (p = 0..3) being bit-plane p of the BAM nibble code (bit0 A, bit1 C, bit2 G, bit3 T; N = all four,
+ *         '=' = none), bit i of each word = base 32g+i, pad bits zero.  A tile's block holds, for g = 0 ..
+ *         G-1 (G = ceil(longest l_seq of the tile / 32)), the g-th group of each of the tile_reads row slots:
+ *         group g of row r is at byte 16 * (g * tile_reads + r) of the block (shorter reads and pad rows: zeros).
+ *         One warp reads a group of all 32 rows as one conflict-free 512-byte access.
  *   qual  l_seq bytes per read, BAM phred values as stored.
  *   cigar n_cigar 32-bit words per read, BAM encoding (len << 4 | op).
  *   mp    per stored MP entry one 32-bit word: bits 0-15 readPos-1, bits 16-31 refPos-1

@@ -4,7 +4,8 @@
 # Outputs land in gpurun_out/; the summaries kept for review are copied to profiles/ by hand.
 set -u
 ORDER=${1:-sorted}
-CMD="python bench.py --reads 10000000 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --order $ORDER"
+READS=${READS:-10000000}   # READS=50000000 for the full cfg2 launch
+CMD="python bench.py --reads $READS --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --order $ORDER"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$ORDER.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$ORDER.csv $CMD > gpurun_out/ncu_launches_$ORDER.log 2>&1

@@ -66,6 +66,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // ------------------------------------------------------------------------------------------
 // kernel parameters
 // ------------------------------------------------------------------------------------------
+#define SD_TILE_READS 32
+
 struct CountArgs {
     // batch (device pointers)
     const sd_read_rec *rec;
@@ -149,7 +151,12 @@ __device__ __forceinline__ void utr_accumulate(unsigned long long *counters, uin
     const uint32_t s_mm = __reduce_add_sync(grp, multimap);
     const uint32_t s_cov = __reduce_add_sync(grp, cov_t);
     const uint32_t s_conv = __reduce_add_sync(grp, conv_t);
-    if ((threadIdx.x & 31) == (__ffs(grp) - 1)) {
+#ifdef SD_EXP_NO_CNT
+    if (n + s_tc + s_mm + s_cov + s_conv == 0xFFFFFFFFu)
+#else
+    if ((threadIdx.x & 31) == (__ffs(grp) - 1))
+#endif
+    {
         unsigned long long *c = counters + (size_t)row * SD_NCOUNTER;
         atomicAdd(c + SD_C_READS, (unsigned long long)n);
         if (s_tc) atomicAdd(c + SD_C_TCREADS, (unsigned long long)s_tc);
@@ -159,13 +166,25 @@ __device__ __forceinline__ void utr_accumulate(unsigned long long *counters, uin
     }
 }
 
+// one base quality, streamed: the byte is used once, so it must not evict the reference / table lines from L1
+__device__ __forceinline__ int ld_qual(const uint8_t *p) {
+#if defined(SD_QUAL_SMEM)
+    return (int)*p;   // generic load: the column sits in shared memory
+#elif defined(SD_QUAL_NOALLOC)
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return (int)v;
+#else
+    return (int)__ldg(p);
+#endif
+}
+
 // @region sliced_is_base
-// read mask word -> "is X" byte for 8 bases of sliced SEQ.  inv flips the planes that must be 0.
-__device__ __forceinline__ uint32_t sliced_is_base(uint32_t w, uint32_t inv) {
-    uint32_t x = w ^ inv;
-    x &= x >> 16;
-    x &= x >> 8;
-    return x & 0xFFu;
+// Read mask of one 32-base group of the plane-sliced SEQ column (four words: bit-planes A, C, G, T of the BAM nibble):
+// bit i set where base i is exactly C (plus strand) / exactly G (minus strand).  sm = all ones on the minus strand.
+__device__ __forceinline__ uint32_t group_is_base(const uint4 p, uint32_t sm) {
+    const uint32_t f = ((p.y & ~p.z) & ~sm) | ((p.z & ~p.y) & sm);   // one LOP3: the wanted plane without the other of C/G
+    return f & ~p.x & ~p.w;                                          // one LOP3: neither A nor T
 }
 
 // @region slow_and_generic
@@ -189,7 +208,7 @@ __device__ __forceinline__ int ref_to_read(const uint32_t *cig, uint32_t ncig, i
 }
 
 struct ReadView {
-    const uint32_t *seq;   // sliced words (shared memory)
+    const uint32_t *seq;   // this read's slot of group 0 in the tile's group-major plane block (shared memory)
     const uint8_t *qual;   // bytes (shared memory)
     const uint32_t *cig;   // ops (shared memory)
     const uint32_t *mp;    // entries (shared memory) or null
@@ -223,7 +242,7 @@ __device__ __forceinline__ void slow_for_each_hit(const CountArgs &A, const Read
         return;
     }
     if (!v.has_mp) return;  // no MP tag: the reference sees no mismatches (SlamSeqFile.py:318)
-    const uint32_t inv = v.strand ? 0xFF00FFFFu : 0xFFFF00FFu;
+    const uint32_t sm = v.strand ? 0xFFFFFFFFu : 0u;
     int q = 0, r = 0;
     for (uint32_t i = 0; i < v.ncig; i++) {
         const uint32_t c = v.cig[i], op = c & 15u;
@@ -232,8 +251,8 @@ __device__ __forceinline__ void slow_for_each_hit(const CountArgs &A, const Read
             for (int j = 0; j < len; j++) {
                 const int o = r + j, qi = q + j;
                 if (o >= v.span || qi >= (int)v.lseq) break;
-                const uint32_t isx = sliced_is_base(v.seq[qi >> 3], inv);
-                if (!((isx >> (qi & 7)) & 1u)) continue;
+                const uint32_t isx = group_is_base(reinterpret_cast<const uint4 *>(v.seq)[(qi >> 5) * SD_TILE_READS], sm);
+                if (!((isx >> (qi & 31)) & 1u)) continue;
                 const uint64_t gp = (uint64_t)v.g + (uint64_t)o;
                 const uint2 x = __ldg(&rx[gp >> 5]);
                 const uint32_t bit = 1u << (gp & 31);
@@ -295,8 +314,10 @@ __device__ __noinline__ int slow_read(const CountArgs &A, const ReadView v, uint
                 const uint32_t ss = A.seg_start[s][seg], se = A.seg_end[s][seg];
                 const uint64_t off = A.seg_off[s][seg];
                 const uint32_t pa = ss > g ? ss : g, pb = se < e ? se : e;
+#if !defined(SD_EXP_NO_POS) && !defined(SD_EXP_NO_COV)
                 atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
                 atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
+#endif
                 if (tc > 0)
                     slow_for_each_hit(A, v, [&](int o, bool on_t) {
                         const uint32_t gp = g + (uint32_t)o;
@@ -411,18 +432,12 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             }
         }
     } else {
-        const uint32_t inv = s ? 0xFF00FFFFu : 0xFFFF00FFu;
-        const uint32_t nw8 = (v.lseq + 7u) >> 3;
+        const uint32_t sm = s ? 0xFFFFFFFFu : 0u;
+        const uint32_t ng = (v.lseq + 31u) >> 5;
+        const uint4 *grp = reinterpret_cast<const uint4 *>(v.seq);   // this row's slot of group 0; the tile block is group-major
         uint32_t M[W];
 #pragma unroll
-        for (int k = 0; k < W; k++) {
-            uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-            if (4u * k + 0u < nw8) b0 = sliced_is_base(v.seq[4 * k + 0], inv);
-            if (4u * k + 1u < nw8) b1 = sliced_is_base(v.seq[4 * k + 1], inv);
-            if (4u * k + 2u < nw8) b2 = sliced_is_base(v.seq[4 * k + 2], inv);
-            if (4u * k + 3u < nw8) b3 = sliced_is_base(v.seq[4 * k + 3], inv);
-            M[k] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-        }
+        for (int k = 0; k < W; k++) M[k] = ((uint32_t)k < ng) ? group_is_base(grp[k * SD_TILE_READS], sm) : 0u;
         if (SIMPLE) {
 #pragma unroll
             for (int k = 0; k < W; k++) R[k] = M[k];
@@ -522,8 +537,43 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
     } else {
 #pragma unroll
         for (int k = 0; k < W; k++) H[k] = v.has_mp ? (R[k] & T[k] & ~S[k]) : 0u;
-        // Base quality only where a candidate survived: one byte of the qual column per candidate,
-        // visited in one loop per 64 window positions.
+        // Base quality only where a candidate survived: one byte of the qual column per candidate.
+#ifndef SD_NO_FIRSTBIT
+        // The first candidate of every 32-position word is tested in straight-line code, so these quality bytes are in
+        // flight together and the common case (at most one candidate per word) needs no loop at all.
+        int qv[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            qv[k] = 255;
+            if (H[k]) {
+                const int o = 32 * k + (__ffs((int)H[k]) - 1);
+                const int qi = SIMPLE ? o : (regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o));
+                qv[k] = (qi < 0 || qi >= (int)v.lseq) ? -1 : ld_qual(v.qual + qi);
+            }
+        }
+        uint32_t C[W], more = 0u;   // C: candidates after the first of each word, still to be tested
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            C[k] = H[k] & (H[k] - 1u);
+            H[k] = (qv[k] >= A.min_qual) ? (H[k] ^ C[k]) : 0u;   // keep the lowest candidate iff its quality passes
+            more |= C[k];
+        }
+        if (more) {
+#pragma unroll
+            for (int k2 = 0; k2 < W; k2 += 2) {
+                unsigned long long rest = (unsigned long long)C[k2] | ((unsigned long long)C[k2 + 1] << 32), fail = 0ull;
+                while (rest) {
+                    const int bit = __ffsll((long long)rest) - 1;
+                    rest &= rest - 1ull;
+                    const int o = 32 * k2 + bit;
+                    const int qi = SIMPLE ? o : (regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o));
+                    if (qi < 0 || qi >= (int)v.lseq || ld_qual(v.qual + qi) < A.min_qual) fail |= 1ull << bit;
+                }
+                H[k2] |= C[k2] & ~(uint32_t)fail;
+                H[k2 + 1] |= C[k2 + 1] & ~(uint32_t)(fail >> 32);
+            }
+        }
+#else
 #pragma unroll
         for (int k2 = 0; k2 < W; k2 += 2) {
             unsigned long long rest = (unsigned long long)H[k2] | ((unsigned long long)H[k2 + 1] << 32), fail = 0ull;
@@ -532,11 +582,12 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                 rest &= rest - 1ull;
                 const int o = 32 * k2 + bit;
                 const int qi = SIMPLE ? o : (regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o));
-                if (qi < 0 || qi >= (int)v.lseq || (int)__ldg(v.qual + qi) < A.min_qual) fail |= 1ull << bit;
+                if (qi < 0 || qi >= (int)v.lseq || ld_qual(v.qual + qi) < A.min_qual) fail |= 1ull << bit;
             }
             H[k2] &= ~(uint32_t)fail;
             H[k2 + 1] &= ~(uint32_t)(fail >> 32);
         }
+#endif
 #pragma unroll
         for (int k = 0; k < W; k++) tc += __popc(H[k]);
     }
@@ -579,11 +630,35 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                 const uint32_t ss = sg.x, se = sg.y;
                 const uint64_t off = (uint64_t)sg.z | ((uint64_t)sg.w << 32);
                 const uint32_t pa = ss > g ? ss : g, pb = se < e ? se : e;
+#if !defined(SD_EXP_NO_POS) && !defined(SD_EXP_NO_COV)
                 atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
                 atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
+#endif
                 if (tc > 0) {
                     int *tcbase = A.pos_tc + ((long long)off + ((long long)g - (long long)ss));   // may point before the segment; only in-range bits are used
                     const bool whole = (pa == g && pb == e);
+#ifndef SD_NO_FIRSTBIT
+                    uint32_t more = 0u;
+#pragma unroll
+                    for (int k = 0; k < W; k++) {   // first conversion of every word without a loop
+                        uint32_t h = H[k];
+                        if (!whole) h &= prefix_word(k, (int)(pb - g)) & ~prefix_word(k, (int)(pa - g));
+                        if (h) atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                        more |= h & (h - 1u);
+                    }
+                    if (more) {
+#pragma unroll
+                        for (int k = 0; k < W; k++) {
+                            uint32_t h = H[k];
+                            if (!whole) h &= prefix_word(k, (int)(pb - g)) & ~prefix_word(k, (int)(pa - g));
+                            h &= h - 1u;
+                            while (h) {
+                                atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                                h &= h - 1u;
+                            }
+                        }
+                    }
+#else
 #pragma unroll
                     for (int k2 = 0; k2 < W; k2 += 2) {
                         uint32_t h0 = H[k2], h1 = H[k2 + 1];
@@ -595,9 +670,12 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                         while (h) {
                             const int bit = __ffsll((long long)h) - 1;
                             h &= h - 1ull;
+#if !defined(SD_EXP_NO_POS) && !defined(SD_EXP_NO_TCPOS)
                             atomicAdd(tcbase + (32 * k2 + bit), 1);
+#endif
                         }
                     }
+#endif
                 }
             }
         }
@@ -622,7 +700,6 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 // ---------------------------------------------------------------------------------------
 // @region kernel_setup
 #define SD_SMEM_STATS 8
-#define SD_TILE_READS 32
 #ifndef SD_CLAIM
 #define SD_CLAIM 8   // consecutive tiles claimed per atomic
 #endif
@@ -636,7 +713,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 template <int W>
 __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kernel(const __grid_constant__ CountArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
+    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual;
     const uint32_t warp_bytes = A.n_stages * stage_bytes + 128u;   // stages | barriers + tile qual offsets
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t nwarp = blockDim.x >> 5;
@@ -670,18 +747,29 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
     auto issue = [&](uint64_t tile, uint32_t stage) {
         unsigned char *base = stages + (size_t)stage * stage_bytes;
         const sd_tile t0 = A.tiles[tile], t1 = A.tiles[tile + 1];
+#ifdef SD_DESC_PREFETCH
+        // tile descriptors are a DRAM stream of their own, read by one lane while the warp waits: pull the one the queue
+        // reaches a few microseconds from now into L2 (every descriptor is prefetched exactly once, by tile - distance)
+        if (tile + SD_DESC_PREFETCH <= A.n_tiles) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.tiles + tile + SD_DESC_PREFETCH));
+#endif
         const uint32_t b_rec = SD_TILE_READS * (uint32_t)sizeof(sd_read_rec);
         const uint32_t b_seq = (uint32_t)(t1.seq_off - t0.seq_off);
         const uint32_t b_cig = (uint32_t)(t1.cig_off - t0.cig_off);
         const uint32_t b_mp = A.mp ? (uint32_t)(t1.mp_off - t0.mp_off) : 0u;
         s_qoff[stage] = t0.qual_off;
-#ifndef SD_NO_QUAL_PREFETCH
+#ifdef SD_QUAL_SMEM
+        const uint32_t b_qs = (uint32_t)(t1.qual_off - t0.qual_off);
+#else
+        const uint32_t b_qs = 0u;
+#endif
+#if !defined(SD_NO_QUAL_PREFETCH) && !defined(SD_QUAL_SMEM)
         {   // pull the tile's base qualities into L2 two tiles ahead: the candidate test then pays L2, not DRAM latency
             const uint32_t b_q = (uint32_t)(t1.qual_off - t0.qual_off) & ~15u;
             if (b_q) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.qual + t0.qual_off), "r"(b_q) : "memory");
         }
 #endif
-        mbar_arrive_expect_tx(&full[stage], b_rec + b_seq + b_cig + b_mp);
+        mbar_arrive_expect_tx(&full[stage], b_rec + b_seq + b_cig + b_mp + b_qs);
+        if (b_qs) bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp, A.qual + t0.qual_off, b_qs, &full[stage]);
         bulk_g2s(base, reinterpret_cast<const unsigned char *>(A.rec) + tile * b_rec, b_rec, &full[stage]);
         if (b_seq) bulk_g2s(base + A.cap_rec, reinterpret_cast<const unsigned char *>(A.seq) + t0.seq_off, b_seq, &full[stage]);
         if (b_cig)
@@ -689,6 +777,15 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
         if (b_mp)
             bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_cig, reinterpret_cast<const unsigned char *>(A.mp) + t0.mp_off, b_mp,
                      &full[stage]);
+#ifdef SD_PREFETCH_NEXT
+        if (tile + 1 < A.n_tiles) {   // the following tile's columns into L2: with a single stage the next copy then pays L2 latency only
+            const sd_tile t2 = A.tiles[tile + 2];
+            const uint32_t n_seq = (uint32_t)(t2.seq_off - t1.seq_off), n_cig = (uint32_t)(t2.cig_off - t1.cig_off);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char *>(A.rec) + (tile + 1) * b_rec), "r"(b_rec) : "memory");
+            if (n_seq) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char *>(A.seq) + t1.seq_off), "r"(n_seq) : "memory");
+            if (n_cig) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char *>(A.cigar) + t1.cig_off), "r"(n_cig) : "memory");
+        }
+#endif
     };
 
     if (lane == 0) {
@@ -718,13 +815,12 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
 
         // @region row_scan
         // row offsets inside the tile: exclusive warp scan of the row sizes
-        const uint32_t x = ((lseq + 7u) >> 3) | (ncig << 16);   // seq words | ncig << 16
-        uint32_t xs = x, qs = lseq, ms = nmp;
+        uint32_t xs = ncig, qs = lseq, ms = nmp;
 #ifndef SD_NO_UNIFORM_SCAN
         int uni_pred = 0;
         __match_all_sync(0xFFFFFFFFu, lseq | (ncig << 16), &uni_pred);
         if (uni_pred && !A.mp) {   // every row of the tile has the same shape: offsets are lane multiples
-            xs = (lane + 1u) * x;
+            xs = (lane + 1u) * ncig;
             qs = (lane + 1u) * lseq;
         } else
 #endif
@@ -739,11 +835,9 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
                 ms += tm;
             }
         }
-        xs -= x;
+        const uint32_t cig_row = xs - ncig;
         qs -= lseq;
         ms -= nmp;
-        // (a tile fits one shared-memory stage, < 2^16 words per column, so the packed 16-bit sums cannot overflow)
-        const uint32_t seq_row = xs & 0xFFFFu, cig_row = xs >> 16;
 
         // @region filter
         const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu, ref = rmf & 0xFFFFu;
@@ -771,8 +865,14 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
             const uint32_t clen = __ldg(&A.chrom_len[ref]);
             if (pos >= 0 && (uint32_t)pos < clen) {
                 ReadView v;
-                v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + seq_row;
+                v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + 4u * lane;
+#if defined(SD_EXP_QUAL_HOT)
+                v.qual = A.qual + ((s_qoff[stage] + qs) & 0xFFFFFull);   // experiment only (breaks parity): qual traffic served by L2
+#elif defined(SD_QUAL_SMEM)
+                v.qual = base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + qs;
+#else
                 v.qual = A.qual + s_qoff[stage] + qs;
+#endif
                 v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + cig_row;
                 v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
                 v.lseq = lseq;
@@ -1182,7 +1282,7 @@ static inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
 template <int W>
 static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
-    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
+    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     static int forced_stages = -1, forced_warps = -1;
@@ -1235,7 +1335,11 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     A.tiles = b->tiles; A.n_tiles = b->n_tiles; A.tile_reads = b->tile_reads;
     A.cap_rec = align16(32u * (uint32_t)sizeof(sd_read_rec));
     A.cap_seq = align16(b->max_tile_seq);
+#ifdef SD_QUAL_SMEM
+    A.cap_qual = align128(b->max_tile_qual);   // experiment: stage the whole qual column through shared memory
+#else
     A.cap_qual = 0;  // the qual column is read in place (see the kernel's header comment)
+#endif
     A.cap_cig = align16(b->max_tile_cig);
     A.cap_mp = A.mp ? align16(b->max_tile_mp) : 0;
     {   // keep every warp's region 128-byte aligned

@@ -608,16 +608,18 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         for (size_t t = 0; t < n_tiles; t++) {
             tiles[t] = cur;
             uint64_t bs = 0, bq = 0, bc = 0, bm = 0;
+            uint32_t tile_lseq = 0;
             const size_t e = std::min(n, (t + 1) * (size_t)tile_reads);
             for (size_t i = t * (size_t)tile_reads; i < e; i++) {
                 const uint32_t ls = rec[i].lseq_ncig & 0xFFFFu;
                 max_lseq = std::max(max_lseq, ls);
-                bs += 4ull * ((ls + 7u) >> 3);
+                tile_lseq = std::max(tile_lseq, ls);
                 bq += ls;
                 bc += 4ull * (rec[i].lseq_ncig >> 16);
                 bm += 4ull * (rec[i].nm_nmp >> 16);
             }
-            bs = up16(bs); bq = up16(bq); bc = up16(bc); bm = up16(bm);
+            bs = 16ull * tile_reads * ((tile_lseq + 31u) >> 5);   // group-major: every row slot of the tile, longest read's groups
+            bq = up16(bq); bc = up16(bc); bm = up16(bm);
             mt_seq = std::max<uint32_t>(mt_seq, (uint32_t)bs);
             mt_qual = std::max<uint32_t>(mt_qual, (uint32_t)bq);
             mt_cig = std::max<uint32_t>(mt_cig, (uint32_t)bc);
@@ -636,7 +638,8 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     lap("tiles+alloc");
     // ---- pass B: variable-length columns, one tile at a time
     parallel_for(n_tiles, threads, [&](size_t t) {
-        uint8_t *ps = (uint8_t *)seqc + tiles[t].seq_off;
+        uint8_t *ps = (uint8_t *)seqc + tiles[t].seq_off;   // group-major block: slot (g, row) at 16 * (g * tile_reads + row)
+        memset(ps, 0, (size_t)(tiles[t + 1].seq_off - tiles[t].seq_off));
         uint8_t *pq = qualc + tiles[t].qual_off;
         uint8_t *pc = (uint8_t *)cigc + tiles[t].cig_off;
         uint8_t *pm = mpc ? (uint8_t *)mpc + tiles[t].mp_off : nullptr;
@@ -654,18 +657,20 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
             memcpy(pq, qual, l_seq);
             pq += l_seq;
             const uint32_t nbytes = (l_seq + 1) / 2;
-            for (uint32_t w = 0; w < (l_seq + 7) / 8; w++) {
-                uint32_t v = 0;
-                for (uint32_t k = 0; k < 4; k++) {
-                    const uint32_t bi = 4 * w + k;
-                    if (bi < nbytes) {
-                        uint8_t b = seq[bi];
-                        if (2 * bi + 1 >= l_seq) b &= 0xF0;  // odd length: ignore the pad nibble
-                        v |= kSlice.v[b] << (2 * k);
-                    }
+            for (uint32_t g = 0; g < (l_seq + 31) / 32; g++) {   // one group = 32 bases = 16 packed bytes -> 4 plane words
+                uint32_t pl[4] = {0, 0, 0, 0};
+                for (uint32_t j = 0; j < 16; j++) {
+                    const uint32_t bi = 16 * g + j;
+                    if (bi >= nbytes) break;
+                    uint8_t b = seq[bi];
+                    if (2 * bi + 1 >= l_seq) b &= 0xF0;  // odd length: ignore the pad nibble
+                    const uint32_t v = kSlice.v[b];     // byte p = plane p of the two bases (bit 0 first base)
+                    pl[0] |= (v & 3u) << (2 * j);
+                    pl[1] |= ((v >> 8) & 3u) << (2 * j);
+                    pl[2] |= ((v >> 16) & 3u) << (2 * j);
+                    pl[3] |= ((v >> 24) & 3u) << (2 * j);
                 }
-                memcpy(ps, &v, 4);
-                ps += 4;
+                memcpy(ps + 16 * ((size_t)g * tile_reads + (k - t * (size_t)tile_reads)), pl, 16);
             }
             if (pm && mp_ptr[i]) {
                 mp_for_each(mp_ptr[i], (flag & 0x10) ? 2 : 16, [&](long rp, long fp) {
@@ -676,7 +681,6 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
             }
         }
         // zero the 16-byte tile padding so the columns are deterministic
-        memset(ps, 0, (size_t)(((uint8_t *)seqc + tiles[t + 1].seq_off) - ps));
         memset(pq, 0, (size_t)((qualc + tiles[t + 1].qual_off) - pq));
         memset(pc, 0, (size_t)(((uint8_t *)cigc + tiles[t + 1].cig_off) - pc));
         if (pm) memset(pm, 0, (size_t)(((uint8_t *)mpc + tiles[t + 1].mp_off) - pm));

@@ -166,8 +166,8 @@ __global__ void synth_tile_sizes_kernel(sd_synth_params P, const uint32_t *count
     unsigned long long bs = 0, bq = 0, bc = 0, bm = 0;
     if (t < n_tiles) {
         const uint64_t b = (uint64_t)t * P.tile_reads, e = min((uint64_t)P.n_reads, b + P.tile_reads);
+        bs = 16ull * P.tile_reads * ((P.read_len + 31u) >> 5);   // group-major block with all row slots
         for (uint64_t i = b; i < e; i++) {
-            bs += 4ull * ((P.read_len + 7u) >> 3);
             bq += P.read_len;
             bc += 4ull * (counts[i] & 0xFFFFu);
             bm += 4ull * (counts[i] >> 16);
@@ -193,14 +193,14 @@ __global__ void synth_pack_tiles_kernel(const unsigned long long *offs, uint32_t
 }
 
 struct FillEm {
-    uint32_t *seq;      // sliced words of this read
+    uint32_t *seq;      // this read's slot of group 0 in the tile's group-major block
     uint8_t *qv;
     uint32_t *mp;       // mp entries of this read (may be null)
     int32_t *triples;   // [1 + 3 * SD_SYNTH_MAX_TRIPLES] (may be null)
     uint32_t want, nmp, nmis, ntri;
     __device__ void base(uint32_t i, uint32_t code) {
         // BAM nibble of A,C,G,T = 1,2,4,8 -> plane `code` gets the bit
-        seq[i >> 3] |= 1u << (8u * code + (i & 7u));
+        seq[(i >> 5) * (4u * 32u) + code] |= 1u << (i & 31u);   // group-major tile block: 32 row slots of 4 words per group
     }
     __device__ void qual(uint32_t i, uint32_t q) { qv[i] = (uint8_t)q; }
     __device__ void mismatch(uint32_t conv, uint32_t rp1, uint32_t fp1) {
@@ -239,6 +239,10 @@ __global__ void synth_fill_kernel(sd_synth_params P, sd_synth_tables T, const ui
     }
     const uint32_t cig_before = cs - (c & 0xFFFFu), mp_before = ms - (c >> 16);
     sd_read_rec &o = rec[i];
+    const uint32_t groups = (P.read_len + 31u) >> 5;
+    uint32_t *my_seq = seq + tiles[tile].seq_off / 4 + (size_t)lane * 4u;   // slot (group 0, row lane); groups are 128 words apart
+    for (uint32_t g = 0; g < groups; g++)
+        *reinterpret_cast<uint4 *>(my_seq + (size_t)g * 128u) = make_uint4(0u, 0u, 0u, 0u);   // pad rows too: deterministic columns
     if (!live) {
         o.pos = 0;
         o.ref_mapq_flag = (uint32_t)SD_REF_NONE | ((uint32_t)(SD_F_PAD | SD_F_SKIP | SD_F_UNMAPPED) << 24);
@@ -249,13 +253,11 @@ __global__ void synth_fill_kernel(sd_synth_params P, sd_synth_tables T, const ui
     }
     const uint32_t k = lane;
     const sd_tile t = tiles[tile];
-    const uint32_t words = (P.read_len + 7u) >> 3;
     FillEm em;
-    em.seq = seq + t.seq_off / 4 + (size_t)k * words;
+    em.seq = my_seq;
     em.qv = qual + t.qual_off + (size_t)k * P.read_len;
     em.mp = mp ? mp + t.mp_off / 4 + mp_before : nullptr;
     em.triples = triples ? triples + i * (1 + 3 * SD_SYNTH_MAX_TRIPLES) : nullptr;
-    for (uint32_t w = 0; w < words; w++) em.seq[w] = 0u;
     Rng rng(P.seed, P.first_read + (P.order ? (uint64_t)P.order[i] : i));
     const Plan pl = make_plan(rng, P, T);
     em.want = pl.strand ? 2u : 16u;

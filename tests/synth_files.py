@@ -42,8 +42,7 @@ def write_workload_files(outdir, wl, db, triples, name="synth", sort=True):
     nt = len(tiles) - 1
     lseq_pad = (bn["rec"][:, 3] & 0xFFFF).astype(np.int64).reshape(nt, T)
     ncig_pad = (bn["rec"][:, 3] >> 16).astype(np.int64).reshape(nt, T)
-    words_pad = (lseq_pad + 7) // 8
-    seq_off = (np.cumsum(words_pad, 1) - words_pad + (tiles[:-1, 0] // 4).astype(np.int64)[:, None]).reshape(-1)[:n]
+    tile_seq = (tiles[:-1, 0] // 4).astype(np.int64)     # word offset of every tile's group-major seq block
     qual_off = (np.cumsum(lseq_pad, 1) - lseq_pad + tiles[:-1, 1].astype(np.int64)[:, None]).reshape(-1)[:n]
     cig_off = (np.cumsum(ncig_pad, 1) - ncig_pad + (tiles[:-1, 2] // 4).astype(np.int64)[:, None]).reshape(-1)[:n]
     K = (tri.shape[1] - 1) // 3
@@ -52,8 +51,9 @@ def write_workload_files(outdir, wl, db, triples, name="synth", sort=True):
         w = rec[i]
         ls, nc = int(w[3]) & 0xFFFF, int(w[3]) >> 16
         flags = int(w[1]) >> 24
-        words = seq[seq_off[i]:seq_off[i] + (ls + 7) // 8]
-        planes = np.unpackbits(words.view(np.uint8).reshape(-1, 4), axis=1, bitorder="little").reshape(-1, 4, 8)
+        gi = tile_seq[i // T] + 4 * (np.arange((ls + 31) // 32) * T + i % T)               # group g of row r at 16 * (g * T + r)
+        words = seq[(gi[:, None] + np.arange(4)[None, :]).reshape(-1)]
+        planes = np.unpackbits(words.view(np.uint8).reshape(-1, 4, 4), axis=2, bitorder="little")   # [group, plane, 32 bases]
         nib = (planes[:, 0, :] | (planes[:, 1, :] << 1) | (planes[:, 2, :] << 2) | (planes[:, 3, :] << 3)).reshape(-1)[:ls]
         s = _NIB[nib].tobytes().decode()
         cnt = int(tri[i, 0])

@@ -34,12 +34,12 @@ def _decode(path, fasta_names, want_mp=True, tile_reads=32, threads=3):
     return HostBatch(path, fasta_names, want_mp=want_mp, tile_reads=tile_reads, threads=threads)
 
 
-def _unslice(words, lseq):
+def _unslice(seq, tile_word_off, row, lseq, tile_reads=32):
+    """bases of one read from the group-major plane-sliced tile block (include/slamdunk_b200.h, sd_batch.seq)"""
     out = []
     for i in range(lseq):
-        w = int(words[i >> 3])
-        b = i & 7
-        nib = sum((((w >> (8 * p + b)) & 1) << p) for p in range(4))
+        g = tile_word_off + 4 * ((i >> 5) * tile_reads + row)
+        nib = sum((((int(seq[g + p]) >> (i & 31)) & 1) << p) for p in range(4))
         out.append(bamio.SEQ_NIBBLES[nib])
     return "".join(out)
 
@@ -86,8 +86,7 @@ def test_bam_decoder_matches_python_codec(tmp_path, tile_reads):
             prev_name = r.qname
             assert nm == r.get_tag("NM")
             assert np.float32(np.uint32(w[2]).view(np.float32)) == np.float32(r.get_tag("XI"))
-            nw = (lseq + 7) // 8
-            assert _unslice(seq[so:so + nw], lseq) == r.seq.upper()
+            assert _unslice(seq, so, k, lseq) == r.seq.upper()
             assert list(qual[qo:qo + lseq]) == r.qual
             assert [(int(x) & 15, int(x) >> 4) for x in cig[co:co + ncig]] == r.cigar
             want = []
@@ -97,7 +96,7 @@ def test_bam_decoder_matches_python_codec(tmp_path, tile_reads):
                     if conv == (2 if r.flag & 16 else 16):
                         want.append(((rp - 1) | ((fp - 1) << 16)))
             assert [int(x) for x in mp[mo:mo + nmp]] == want
-            so += nw; qo += lseq; co += ncig; mo += nmp
+            qo += lseq; co += ncig; mo += nmp
     hb.close()
 
 
@@ -241,9 +240,8 @@ def test_decoder_grouping_is_a_stable_partition(tmp_path):
             r = recs[order[slot]]
             lseq = int(rec[slot][3]) & 0xFFFF
             assert lseq == len(r.seq) and np.int32(rec[slot][0]) == r.pos
-            assert _unslice(seq[so:so + (lseq + 7) // 8], lseq) == r.seq.upper()
+            assert _unslice(seq, so, k, lseq) == r.seq.upper()
             assert list(qual[qo:qo + lseq]) == r.qual
-            so += (lseq + 7) // 8
             qo += lseq
     hb.close()
     plain = HostBatch(c.bam, names, want_mp=True, group=False)
