@@ -16,6 +16,7 @@
 //      need (tcounter.py:229-231, 246-248, 285).
 // The path is integer streaming work bound by HBM bandwidth; there is no tensor-core use.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -113,7 +114,7 @@ struct CountArgs {
     int filter_on;
     int filter_mq;
     int filter_max_nm;
-    double filter_min_identity;
+    float filter_min_identity;   // smallest float >= the double threshold: xi < this  <=>  (double)xi < threshold
     int force_slow;
 };
 
@@ -151,12 +152,7 @@ __device__ __forceinline__ void utr_accumulate(unsigned long long *counters, uin
     const uint32_t s_mm = __reduce_add_sync(grp, multimap);
     const uint32_t s_cov = __reduce_add_sync(grp, cov_t);
     const uint32_t s_conv = __reduce_add_sync(grp, conv_t);
-#ifdef SD_EXP_NO_CNT
-    if (n + s_tc + s_mm + s_cov + s_conv == 0xFFFFFFFFu)
-#else
-    if ((threadIdx.x & 31) == (__ffs(grp) - 1))
-#endif
-    {
+    if ((threadIdx.x & 31) == (__ffs(grp) - 1)) {
         unsigned long long *c = counters + (size_t)row * SD_NCOUNTER;
         atomicAdd(c + SD_C_READS, (unsigned long long)n);
         if (s_tc) atomicAdd(c + SD_C_TCREADS, (unsigned long long)s_tc);
@@ -166,18 +162,8 @@ __device__ __forceinline__ void utr_accumulate(unsigned long long *counters, uin
     }
 }
 
-// one base quality, streamed: the byte is used once, so it must not evict the reference / table lines from L1
-__device__ __forceinline__ int ld_qual(const uint8_t *p) {
-#if defined(SD_QUAL_SMEM)
-    return (int)*p;   // generic load: the column sits in shared memory
-#elif defined(SD_QUAL_NOALLOC)
-    uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
-    return (int)v;
-#else
-    return (int)__ldg(p);
-#endif
-}
+// one base quality, fetched where a candidate survived (the tile's qualities were pulled into L2 when the tile was issued)
+__device__ __forceinline__ int ld_qual(const uint8_t *p) { return (int)__ldg(p); }
 
 // @region sliced_is_base
 // Read mask of one 32-base group of the plane-sliced SEQ column (four words: bit-planes A, C, G, T of the BAM nibble):
@@ -314,10 +300,8 @@ __device__ __noinline__ int slow_read(const CountArgs &A, const ReadView v, uint
                 const uint32_t ss = A.seg_start[s][seg], se = A.seg_end[s][seg];
                 const uint64_t off = A.seg_off[s][seg];
                 const uint32_t pa = ss > g ? ss : g, pb = se < e ? se : e;
-#if !defined(SD_EXP_NO_POS) && !defined(SD_EXP_NO_COV)
                 atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
                 atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
-#endif
                 if (tc > 0)
                     slow_for_each_hit(A, v, [&](int o, bool on_t) {
                         const uint32_t gp = g + (uint32_t)o;
@@ -432,12 +416,18 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             }
         }
     } else {
-        const uint32_t sm = s ? 0xFFFFFFFFu : 0u;
+        uint32_t sm = 0u - (uint32_t)s;   // all ones on the minus strand
+        asm volatile("" : "+r"(sm));      // keep it a mask operand of the LOP3s (not a predicate with selects)
         const uint32_t ng = (v.lseq + 31u) >> 5;
         const uint4 *grp = reinterpret_cast<const uint4 *>(v.seq);   // this row's slot of group 0; the tile block is group-major
         uint32_t M[W];
 #pragma unroll
-        for (int k = 0; k < W; k++) M[k] = ((uint32_t)k < ng) ? group_is_base(grp[k * SD_TILE_READS], sm) : 0u;
+        for (int k = 0; k < W; k++) {
+            // unconditional load of an existing group (index clamped), masked afterwards: no branch per group
+            const uint32_t kc = ng ? min((uint32_t)k, ng - 1u) : 0u;
+            const uint32_t m = group_is_base(grp[kc * SD_TILE_READS], sm);
+            M[k] = ((uint32_t)k < ng) ? m : 0u;
+        }
         if (SIMPLE) {
 #pragma unroll
             for (int k = 0; k < W; k++) R[k] = M[k];
@@ -538,7 +528,6 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #pragma unroll
         for (int k = 0; k < W; k++) H[k] = v.has_mp ? (R[k] & T[k] & ~S[k]) : 0u;
         // Base quality only where a candidate survived: one byte of the qual column per candidate.
-#ifndef SD_NO_FIRSTBIT
         // The first candidate of every 32-position word is tested in straight-line code, so these quality bytes are in
         // flight together and the common case (at most one candidate per word) needs no loop at all.
         int qv[W];
@@ -573,21 +562,6 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                 H[k2 + 1] |= C[k2 + 1] & ~(uint32_t)(fail >> 32);
             }
         }
-#else
-#pragma unroll
-        for (int k2 = 0; k2 < W; k2 += 2) {
-            unsigned long long rest = (unsigned long long)H[k2] | ((unsigned long long)H[k2 + 1] << 32), fail = 0ull;
-            while (rest) {
-                const int bit = __ffsll((long long)rest) - 1;
-                rest &= rest - 1ull;
-                const int o = 32 * k2 + bit;
-                const int qi = SIMPLE ? o : (regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o));
-                if (qi < 0 || qi >= (int)v.lseq || ld_qual(v.qual + qi) < A.min_qual) fail |= 1ull << bit;
-            }
-            H[k2] &= ~(uint32_t)fail;
-            H[k2 + 1] &= ~(uint32_t)(fail >> 32);
-        }
-#endif
 #pragma unroll
         for (int k = 0; k < W; k++) tc += __popc(H[k]);
     }
@@ -630,52 +604,39 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                 const uint32_t ss = sg.x, se = sg.y;
                 const uint64_t off = (uint64_t)sg.z | ((uint64_t)sg.w << 32);
                 const uint32_t pa = ss > g ? ss : g, pb = se < e ? se : e;
-#if !defined(SD_EXP_NO_POS) && !defined(SD_EXP_NO_COV)
                 atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
                 atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
-#endif
                 if (tc > 0) {
                     int *tcbase = A.pos_tc + ((long long)off + ((long long)g - (long long)ss));   // may point before the segment; only in-range bits are used
                     const bool whole = (pa == g && pb == e);
-#ifndef SD_NO_FIRSTBIT
-                    uint32_t more = 0u;
+                    asm volatile("" : "+l"(tcbase));   // keep it a pointer: each scatter address is then one IMAD.WIDE
+                    if (whole) {
+                        uint32_t more = 0u;
 #pragma unroll
-                    for (int k = 0; k < W; k++) {   // first conversion of every word without a loop
-                        uint32_t h = H[k];
-                        if (!whole) h &= prefix_word(k, (int)(pb - g)) & ~prefix_word(k, (int)(pa - g));
-                        if (h) atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
-                        more |= h & (h - 1u);
-                    }
-                    if (more) {
+                        for (int k = 0; k < W; k++) {   // first conversion of every word without a loop
+                            const uint32_t h = H[k];
+                            if (h) atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                            more |= h & (h - 1u);
+                        }
+                        if (more) {
 #pragma unroll
+                            for (int k = 0; k < W; k++) {
+                                uint32_t h = H[k] & (H[k] - 1u);
+                                while (h) {
+                                    atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                                    h &= h - 1u;
+                                }
+                            }
+                        }
+                    } else {   // the segment holds only part of the read (rare): masked, plain loops
                         for (int k = 0; k < W; k++) {
-                            uint32_t h = H[k];
-                            if (!whole) h &= prefix_word(k, (int)(pb - g)) & ~prefix_word(k, (int)(pa - g));
-                            h &= h - 1u;
+                            uint32_t h = H[k] & prefix_word(k, (int)(pb - g)) & ~prefix_word(k, (int)(pa - g));
                             while (h) {
                                 atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
                                 h &= h - 1u;
                             }
                         }
                     }
-#else
-#pragma unroll
-                    for (int k2 = 0; k2 < W; k2 += 2) {
-                        uint32_t h0 = H[k2], h1 = H[k2 + 1];
-                        if (!whole) {
-                            h0 &= prefix_word(k2, (int)(pb - g)) & ~prefix_word(k2, (int)(pa - g));
-                            h1 &= prefix_word(k2 + 1, (int)(pb - g)) & ~prefix_word(k2 + 1, (int)(pa - g));
-                        }
-                        unsigned long long h = (unsigned long long)h0 | ((unsigned long long)h1 << 32);
-                        while (h) {
-                            const int bit = __ffsll((long long)h) - 1;
-                            h &= h - 1ull;
-#if !defined(SD_EXP_NO_POS) && !defined(SD_EXP_NO_TCPOS)
-                            atomicAdd(tcbase + (32 * k2 + bit), 1);
-#endif
-                        }
-                    }
-#endif
                 }
             }
         }
@@ -713,7 +674,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 template <int W>
 __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kernel(const __grid_constant__ CountArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual;
+    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
     const uint32_t warp_bytes = A.n_stages * stage_bytes + 128u;   // stages | barriers + tile qual offsets
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t nwarp = blockDim.x >> 5;
@@ -747,29 +708,16 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
     auto issue = [&](uint64_t tile, uint32_t stage) {
         unsigned char *base = stages + (size_t)stage * stage_bytes;
         const sd_tile t0 = A.tiles[tile], t1 = A.tiles[tile + 1];
-#ifdef SD_DESC_PREFETCH
-        // tile descriptors are a DRAM stream of their own, read by one lane while the warp waits: pull the one the queue
-        // reaches a few microseconds from now into L2 (every descriptor is prefetched exactly once, by tile - distance)
-        if (tile + SD_DESC_PREFETCH <= A.n_tiles) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.tiles + tile + SD_DESC_PREFETCH));
-#endif
         const uint32_t b_rec = SD_TILE_READS * (uint32_t)sizeof(sd_read_rec);
         const uint32_t b_seq = (uint32_t)(t1.seq_off - t0.seq_off);
         const uint32_t b_cig = (uint32_t)(t1.cig_off - t0.cig_off);
         const uint32_t b_mp = A.mp ? (uint32_t)(t1.mp_off - t0.mp_off) : 0u;
         s_qoff[stage] = t0.qual_off;
-#ifdef SD_QUAL_SMEM
-        const uint32_t b_qs = (uint32_t)(t1.qual_off - t0.qual_off);
-#else
-        const uint32_t b_qs = 0u;
-#endif
-#if !defined(SD_NO_QUAL_PREFETCH) && !defined(SD_QUAL_SMEM)
         {   // pull the tile's base qualities into L2 two tiles ahead: the candidate test then pays L2, not DRAM latency
             const uint32_t b_q = (uint32_t)(t1.qual_off - t0.qual_off) & ~15u;
             if (b_q) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.qual + t0.qual_off), "r"(b_q) : "memory");
         }
-#endif
-        mbar_arrive_expect_tx(&full[stage], b_rec + b_seq + b_cig + b_mp + b_qs);
-        if (b_qs) bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp, A.qual + t0.qual_off, b_qs, &full[stage]);
+        mbar_arrive_expect_tx(&full[stage], b_rec + b_seq + b_cig + b_mp);
         bulk_g2s(base, reinterpret_cast<const unsigned char *>(A.rec) + tile * b_rec, b_rec, &full[stage]);
         if (b_seq) bulk_g2s(base + A.cap_rec, reinterpret_cast<const unsigned char *>(A.seq) + t0.seq_off, b_seq, &full[stage]);
         if (b_cig)
@@ -777,15 +725,6 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
         if (b_mp)
             bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_cig, reinterpret_cast<const unsigned char *>(A.mp) + t0.mp_off, b_mp,
                      &full[stage]);
-#ifdef SD_PREFETCH_NEXT
-        if (tile + 1 < A.n_tiles) {   // the following tile's columns into L2: with a single stage the next copy then pays L2 latency only
-            const sd_tile t2 = A.tiles[tile + 2];
-            const uint32_t n_seq = (uint32_t)(t2.seq_off - t1.seq_off), n_cig = (uint32_t)(t2.cig_off - t1.cig_off);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char *>(A.rec) + (tile + 1) * b_rec), "r"(b_rec) : "memory");
-            if (n_seq) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char *>(A.seq) + t1.seq_off), "r"(n_seq) : "memory");
-            if (n_cig) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char *>(A.cigar) + t1.cig_off), "r"(n_cig) : "memory");
-        }
-#endif
     };
 
     if (lane == 0) {
@@ -798,8 +737,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
     __syncwarp();
 
     // @region tile_wait_rec
-    uint32_t my_counted = 0, my_slow = 0, my_disagree = 0;
-    unsigned long long my_tc_total = 0;
+    uint32_t my_counted = 0, my_tc_total = 0;   // per-lane run totals (a lane sees far fewer than 2^32 conversions per launch)
     uint32_t stage = 0, phase = 0;
     for (;;) {
         const uint64_t tile = s_tile[stage];
@@ -816,14 +754,12 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
         // @region row_scan
         // row offsets inside the tile: exclusive warp scan of the row sizes
         uint32_t xs = ncig, qs = lseq, ms = nmp;
-#ifndef SD_NO_UNIFORM_SCAN
         int uni_pred = 0;
         __match_all_sync(0xFFFFFFFFu, lseq | (ncig << 16), &uni_pred);
         if (uni_pred && !A.mp) {   // every row of the tile has the same shape: offsets are lane multiples
             xs = (lane + 1u) * ncig;
             qs = (lane + 1u) * lseq;
         } else
-#endif
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t tx = __shfl_up_sync(0xFFFFFFFFu, xs, d);
@@ -848,7 +784,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
             if (primary) atomicAdd(&s_stats[unmapped ? SD_S_UNMAPPED : SD_S_MAPPED], 1u);
             if (unmapped) go = false;
             else if ((int)mapq < A.filter_mq) { atomicAdd(&s_stats[SD_S_MQFILTERED], 1u); go = false; }
-            else if ((double)xi < A.filter_min_identity) { atomicAdd(&s_stats[SD_S_IDFILTERED], 1u); go = false; }
+            else if (xi < A.filter_min_identity) { atomicAdd(&s_stats[SD_S_IDFILTERED], 1u); go = false; }
             else if (A.filter_max_nm > -1 && (int)nm > A.filter_max_nm) { atomicAdd(&s_stats[SD_S_NMFILTERED], 1u); go = false; }
             else if (primary) atomicAdd(&s_stats[SD_S_FILTERED], 1u);
         }
@@ -866,13 +802,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
             if (pos >= 0 && (uint32_t)pos < clen) {
                 ReadView v;
                 v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + 4u * lane;
-#if defined(SD_EXP_QUAL_HOT)
-                v.qual = A.qual + ((s_qoff[stage] + qs) & 0xFFFFFull);   // experiment only (breaks parity): qual traffic served by L2
-#elif defined(SD_QUAL_SMEM)
-                v.qual = base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + qs;
-#else
                 v.qual = A.qual + s_qoff[stage] + qs;
-#endif
                 v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + cig_row;
                 v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
                 v.lseq = lseq;
@@ -904,12 +834,12 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
                 if (fits) {
                     bool bad = false;
                     tc = uni_simple ? fast_read<W, true>(A, v, B, mapq, bad) : fast_read<W, false>(A, v, B, mapq, bad);
-                    my_disagree += bad ? 1u : 0u;
+                    if (bad) atomicAdd(&A.stats[SD_S_MP_DISAGREE], 1ull);   // rare: straight to the global counter
                 } else {
-                    my_slow++;
+                    atomicAdd(&A.stats[SD_S_SLOWPATH], 1ull);
                     tc = slow_read(A, v, mapq);
                 }
-                my_tc_total += (unsigned long long)tc;
+                my_tc_total += (uint32_t)tc;
             }
         }
         if (A.read_tc) A.read_tc[tile * SD_TILE_READS + lane] = (uint8_t)(tc > 255 ? 255 : tc);
@@ -931,14 +861,11 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
     // @region kernel_tail
     // flush run-level counters
     my_counted = __reduce_add_sync(0xFFFFFFFFu, my_counted);
-    my_slow = __reduce_add_sync(0xFFFFFFFFu, my_slow);
-    my_disagree = __reduce_add_sync(0xFFFFFFFFu, my_disagree);
-    for (int d = 16; d > 0; d >>= 1) my_tc_total += __shfl_xor_sync(0xFFFFFFFFu, my_tc_total, d);
+    unsigned long long tc_total = my_tc_total;
+    for (int d = 16; d > 0; d >>= 1) tc_total += __shfl_xor_sync(0xFFFFFFFFu, tc_total, d);
     if (lane == 0) {
         if (my_counted) atomicAdd(&A.stats[SD_S_COUNTED], (unsigned long long)my_counted);
-        if (my_slow) atomicAdd(&A.stats[SD_S_SLOWPATH], (unsigned long long)my_slow);
-        if (my_disagree) atomicAdd(&A.stats[SD_S_MP_DISAGREE], (unsigned long long)my_disagree);
-        if (my_tc_total) atomicAdd(&A.stats[SD_S_TC_TOTAL], my_tc_total);
+        if (tc_total) atomicAdd(&A.stats[SD_S_TC_TOTAL], tc_total);
     }
     __syncthreads();
     if (tid < 6 && s_stats[tid]) atomicAdd(&A.stats[tid], (unsigned long long)s_stats[tid]);
@@ -1282,7 +1209,7 @@ static inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
 template <int W>
 static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
-    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual;
+    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     static int forced_stages = -1, forced_warps = -1;
@@ -1334,12 +1261,8 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     A.mp = (p->mismatch_source == SD_MISMATCH_CIGAR) ? nullptr : b->mp;
     A.tiles = b->tiles; A.n_tiles = b->n_tiles; A.tile_reads = b->tile_reads;
     A.cap_rec = align16(32u * (uint32_t)sizeof(sd_read_rec));
-    A.cap_seq = align16(b->max_tile_seq);
-#ifdef SD_QUAL_SMEM
-    A.cap_qual = align128(b->max_tile_qual);   // experiment: stage the whole qual column through shared memory
-#else
+    A.cap_seq = std::max(align16(b->max_tile_seq), 16u * SD_TILE_READS);   // at least one group per row: the kernel loads group 0 unconditionally
     A.cap_qual = 0;  // the qual column is read in place (see the kernel's header comment)
-#endif
     A.cap_cig = align16(b->max_tile_cig);
     A.cap_mp = A.mp ? align16(b->max_tile_mp) : 0;
     {   // keep every warp's region 128-byte aligned
@@ -1364,7 +1287,12 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     A.tile_counter = ctx->d_tile_counter;
     A.min_qual = p->min_qual; A.conv_threshold = p->conversion_threshold; A.mismatch_source = p->mismatch_source;
     A.filter_on = p->filter_on; A.filter_mq = p->filter_mq; A.filter_max_nm = p->filter_max_nm;
-    A.filter_min_identity = p->filter_min_identity; A.force_slow = p->force_slow_path;
+    {   // filter.py:246 compares the float32 XI tag, promoted to double, with the double threshold; the same predicate in float:
+        float f = (float)p->filter_min_identity;
+        if ((double)f < p->filter_min_identity) f = nextafterf(f, INFINITY);
+        A.filter_min_identity = f;
+    }
+    A.force_slow = p->force_slow_path;
     if (b->max_lseq <= 128) return launch_count<4>(ctx, A, stream, timed);
     if (b->max_lseq <= 256) return launch_count<8>(ctx, A, stream, timed);
     return launch_count<16>(ctx, A, stream, timed);
