@@ -82,6 +82,7 @@ struct CountArgs {
     // shared-memory stage layout (bytes, all multiples of 128)
     uint32_t cap_rec, cap_seq, cap_qual, cap_cig, cap_mp;
     uint32_t n_stages;
+    uint32_t qual_prefetch;   // L2-prefetch each tile's qual bytes when the tile is issued
     // reference
     const uint2 *refx[2];
     const uint32_t *chrom_off;
@@ -713,7 +714,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
         const uint32_t b_cig = (uint32_t)(t1.cig_off - t0.cig_off);
         const uint32_t b_mp = A.mp ? (uint32_t)(t1.mp_off - t0.mp_off) : 0u;
         s_qoff[stage] = t0.qual_off;
-        {   // pull the tile's base qualities into L2 two tiles ahead: the candidate test then pays L2, not DRAM latency
+        if (A.qual_prefetch) {   // pull the tile's base qualities into L2 ahead of use: the candidate test then pays L2, not DRAM latency
             const uint32_t b_q = (uint32_t)(t1.qual_off - t0.qual_off) & ~15u;
             if (b_q) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.qual + t0.qual_off), "r"(b_q) : "memory");
         }
@@ -1212,29 +1213,62 @@ static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool tim
     const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    static int forced_stages = -1, forced_warps = -1;
+    static int forced_stages = -1, forced_warps = -1, forced_pf = -1;
     if (forced_stages < 0) {
         const char *e = getenv("SD_STAGES");
         forced_stages = e ? atoi(e) : 0;
+        e = getenv("SD_QUAL_PF");
+        forced_pf = e ? atoi(e) : -1;
         e = getenv("SD_WARPS");
         forced_warps = e ? atoi(e) : 0;
     }
-    // per-warp ring of n_stages tiles; as many warps per CTA (<= 8) as the shared memory allows
-    uint32_t n_stages = (forced_stages >= 1 && forced_stages <= 4) ? (uint32_t)forced_stages : 2u;
+    // Per-warp ring of n_stages tiles.  Two stages hide the copy latency behind the previous tile, but shared memory is taken
+    // from the same 228 KB as the L1 that serves the reference window / annotation table lookups, and it can cost a resident
+    // CTA: the second stage is used only when it neither lowers the CTAs per SM nor leaves L1 less than 56 KB.
     auto warp_bytes = [&](uint32_t ns) { return (size_t)ns * stage_bytes + 128u; };
-    if (128u + warp_bytes(n_stages) > (size_t)max_smem) n_stages = 1;
-    if (128u + warp_bytes(n_stages) > (size_t)max_smem)
+    if (128u + warp_bytes(1) > (size_t)max_smem)
         return sd_fail(ctx, SD_ERR_LIMIT, "a 32-read tile needs %u bytes of shared memory; reads are too long for this kernel", stage_bytes);
-    uint32_t warps = (forced_warps >= 1 && forced_warps <= SD_CTA_THREADS / 32) ? (uint32_t)forced_warps : (uint32_t)(SD_CTA_THREADS / 32);
-    while (warps > 1 && 128u + warps * warp_bytes(n_stages) > (size_t)max_smem / 2) warps--;   // keep >= 2 CTAs per SM possible
-    while (warps > 1 && 128u + warps * warp_bytes(n_stages) > (size_t)max_smem) warps--;
-    A.n_stages = n_stages;
-    const size_t smem = 128u + warps * warp_bytes(n_stages);
-    const int threads = (int)warps * 32;
-    SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W>, threads, smem));
+    auto plan = [&](uint32_t ns, uint32_t &warps, size_t &smem, int &per_sm) -> int {
+        warps = (forced_warps >= 1 && forced_warps <= SD_CTA_THREADS / 32) ? (uint32_t)forced_warps : (uint32_t)(SD_CTA_THREADS / 32);
+        while (warps > 1 && 128u + warps * warp_bytes(ns) > (size_t)max_smem / 2) warps--;   // keep >= 2 CTAs per SM possible
+        while (warps > 1 && 128u + warps * warp_bytes(ns) > (size_t)max_smem) warps--;
+        smem = 128u + warps * warp_bytes(ns);
+        if (smem > (size_t)max_smem) { per_sm = 0; return SD_OK; }
+        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W>, (int)warps * 32, smem));
+        return SD_OK;
+    };
+    uint32_t n_stages = 1, warps = 0;
+    size_t smem = 0;
+    int per_sm = 0, rc = SD_OK;
+    struct Planned { uint32_t stage_bytes; int device; uint32_t n_stages, warps; size_t smem; int per_sm; };
+    static Planned last = {0, -1, 0, 0, 0, 0};   // the shape rarely changes between launches: skip the occupancy queries
+    if (last.device == ctx->device && last.stage_bytes == stage_bytes) {
+        n_stages = last.n_stages; warps = last.warps; smem = last.smem; per_sm = last.per_sm;
+    } else if ((rc = plan(1, warps, smem, per_sm)) != SD_OK) {
+        return rc;
+    } else if (forced_stages >= 1 && forced_stages <= 4) {
+        n_stages = (uint32_t)forced_stages;
+        if ((rc = plan(n_stages, warps, smem, per_sm)) != SD_OK) return rc;
+    } else {
+        uint32_t w2 = 0;
+        size_t s2 = 0;
+        int p2 = 0;
+        if ((rc = plan(2, w2, s2, p2)) != SD_OK) return rc;
+        int sm_total = 0;
+        cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device);
+        if (p2 >= 1 && (uint64_t)p2 * w2 >= (uint64_t)per_sm * warps && (size_t)p2 * s2 + 56u * 1024u <= (size_t)sm_total) {
+            n_stages = 2; warps = w2; smem = s2; per_sm = p2;
+        }
+    }
     if (per_sm < 1) return sd_fail(ctx, SD_ERR_LIMIT, "count kernel does not fit on an SM (smem %zu)", smem);
+    if (last.device != ctx->device || last.stage_bytes != stage_bytes) {
+        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        last = {stage_bytes, ctx->device, n_stages, warps, smem, per_sm};
+    }
+    A.n_stages = n_stages;
+    A.qual_prefetch = forced_pf >= 0 ? (uint32_t)forced_pf : 0u;   // off: on-demand quality bytes keep DRAM traffic at the touched sectors
+    const int threads = (int)warps * 32;
     const uint64_t want_ctas = ((uint64_t)A.n_tiles + warps - 1) / warps;
     uint32_t grid = (uint32_t)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * per_sm);
     if (grid == 0) grid = 1;
