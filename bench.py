@@ -279,7 +279,7 @@ def main():
     achieved = n_reads * bytes_per_read / (k_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": load_ncu_traffic(), "kernel": "sd_count_kernel", "kernel_ms": k_ms,
+                "traffic": load_ncu_traffic(args), "kernel": "sd_count_kernel", "kernel_ms": k_ms,
                 "algorithmic_bytes_per_read": bytes_per_read, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "kernel_share_of_step": k_ms / ms_per_step}
 
@@ -356,11 +356,15 @@ def main():
         dist.destroy_process_group()
 
 
-def load_ncu_traffic():
-    """dram bytes per launch of sd_count_kernel from the committed ncu summary (profiles/), or None."""
+def load_ncu_traffic(args):
+    """dram bytes per launch of sd_count_kernel from the committed ncu summary (profiles/); None when this run is not
+    the workload that capture was taken on (cfg2: 50 M x 100 bp per GPU, coordinate order)."""
     path = os.path.join(ROOT, "profiles", "count_kernel_dram.json")
     try:
-        return json.load(open(path)).get("dram_bytes_per_launch")
+        d = json.load(open(path))
+        if args.reads != d.get("reads_per_launch") or args.read_len != 100 or args.order != "sorted":
+            return None
+        return d.get("dram_bytes_per_launch")
     except Exception:
         return None
 
