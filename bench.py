@@ -172,7 +172,7 @@ def run_reference(args, rank, world, local_rank):
                          "sample": "first %d reads of the cfg2 read stream per step, inputs pre-decoded in RAM" % sample},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, sample_reads=None):
@@ -187,7 +187,28 @@ def workload_config(args, sample_reads=None):
     return c
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner to stdout at
+    communicator creation), so stdout is pointed at stderr for the whole run and the result line goes to the saved
+    descriptor."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -350,7 +371,7 @@ def main():
             "counted_reads_last_step": int(stats[L.SD_S_COUNTED]), "filtered_reads_last_step": int(stats[L.SD_S_FILTERED]),
             "slow_path_reads": int(stats[L.SD_S_SLOWPATH]),
         }
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -123,6 +123,8 @@ __device__ __forceinline__ bool cigar_consumes_ref(uint32_t op) { return op == 0
 __device__ __forceinline__ bool cigar_is_match(uint32_t op) { return op == 0 || op == 7 || op == 8; }
 __device__ __forceinline__ bool cigar_consumes_query(uint32_t op) { return op == 0 || op == 1 || op == 4 || op == 7 || op == 8; }
 
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
 // @region helpers
 // bits [lo, hi) of the window restricted to word k
 __device__ __forceinline__ uint32_t range_word(int k, int lo, int hi) {
@@ -375,7 +377,7 @@ __device__ __forceinline__ int block_read_index(const Blocks &B, int o) {
 // their own tiles), so the read mask needs no placement and a window position is a read index.
 template <int W, bool SIMPLE>
 __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, const Blocks &B, uint32_t mapq,
-                                         bool &mp_disagree) {
+                                         bool dense_tile, bool &mp_disagree) {
     const int s = v.strand;
     const uint32_t g = v.g, e = v.g + (uint32_t)v.span;
     const uint32_t nU = A.n_u[s];
@@ -605,8 +607,17 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                 const uint32_t ss = sg.x, se = sg.y;
                 const uint64_t off = (uint64_t)sg.z | ((uint64_t)sg.w << 32);
                 const uint32_t pa = ss > g ? ss : g, pb = se < e ? se : e;
-                atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
-                atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
+                // coverage difference: +1 at the first covered position, -1 after the last
+                if (dense_tile) {   // the tile's reads start (and end) at a handful of positions: lanes with the same address elect one to add the count
+                    const unsigned act = __activemask();
+                    const unsigned long long ia = off + (pa - ss), ib = off + (pb - ss);   // lanes may sit in different segments: match the full index
+                    const unsigned ga = __match_any_sync(act, ia), gb = __match_any_sync(act, ib);
+                    if (lane_id() == (uint32_t)__ffs((int)ga) - 1u) atomicAdd(&A.pos_cov[ia], (int)__popc(ga));
+                    if (lane_id() == (uint32_t)__ffs((int)gb) - 1u) atomicAdd(&A.pos_cov[ib], -(int)__popc(gb));
+                } else {
+                    atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
+                    atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
+                }
                 if (tc > 0) {
                     int *tcbase = A.pos_tc + ((long long)off + ((long long)g - (long long)ss));   // may point before the segment; only in-range bits are used
                     const bool whole = (pa == g && pb == e);
@@ -662,6 +673,9 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 // ---------------------------------------------------------------------------------------
 // @region kernel_setup
 #define SD_SMEM_STATS 8
+#ifndef SD_DENSE_SPAN
+#define SD_DENSE_SPAN 8   // <= 8 start positions for 32 reads: >= 4 reads per position
+#endif
 #ifndef SD_CLAIM
 #define SD_CLAIM 8   // consecutive tiles claimed per atomic
 #endif
@@ -796,6 +810,10 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
         // the generator group such reads into their own tiles, so most warps take the lean path.
         const uint32_t cig0 = ncig ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq)[cig_row] : 0u;
         const bool uni_simple = __all_sync(0xFFFFFFFFu, !go || (ncig == 1u && ((0x181u >> (cig0 & 15u)) & 1u)));
+        // Deep coverage: a coordinate-sorted tile whose 32 reads start within a few positions would send dozens of atomics to
+        // the same addresses; such tiles (warp-uniform test on the tile's first and last record) aggregate them in the warp.
+        const bool dense_tile = __shfl_sync(0xFFFFFFFFu, rmf & 0xFFFFu, 0) == __shfl_sync(0xFFFFFFFFu, rmf & 0xFFFFu, 31) &&
+                                (uint32_t)(__shfl_sync(0xFFFFFFFFu, pos, 31) - __shfl_sync(0xFFFFFFFFu, pos, 0)) <= SD_DENSE_SPAN;
         // @region view_setup
         int tc = 0;
         if (go) {
@@ -834,7 +852,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
                 my_counted++;
                 if (fits) {
                     bool bad = false;
-                    tc = uni_simple ? fast_read<W, true>(A, v, B, mapq, bad) : fast_read<W, false>(A, v, B, mapq, bad);
+                    tc = uni_simple ? fast_read<W, true>(A, v, B, mapq, dense_tile, bad) : fast_read<W, false>(A, v, B, mapq, dense_tile, bad);
                     if (bad) atomicAdd(&A.stats[SD_S_MP_DISAGREE], 1ull);   // rare: straight to the global counter
                 } else {
                     atomicAdd(&A.stats[SD_S_SLOWPATH], 1ull);
