@@ -766,6 +766,13 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
         const uint32_t lseq = rw[3] & 0xFFFFu, ncig = rw[3] >> 16;
         const uint32_t nm = rw[4] & 0xFFFFu, nmp = A.mp ? (rw[4] >> 16) : 0u;
 
+#ifndef SD_NO_DESC_L1PF
+        // lane 0 will read the next tile's descriptors when it refills the stage: start that (DRAM-latency) load now
+        if (lane == 0 && claim_next != claim_end && claim_next < A.n_tiles) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(A.tiles + claim_next));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(A.tiles + claim_next + 1));
+        }
+#endif
         // @region row_scan
         // row offsets inside the tile: exclusive warp scan of the row sizes
         uint32_t xs = ncig, qs = lseq, ms = nmp;
