@@ -223,3 +223,32 @@ def test_empty_inputs(tmp_path):
     open(nobed, "w").write("")
     tcounter.computeTconversions(c.ref, nobed, None, c.bam, 100, 27, o + "2.tsv", o + "2.p", o + "2.m", 1, io.StringIO())
     assert len(_read(o + "2.tsv").strip().split("\n")) == 3
+
+
+@pytest.mark.parametrize("mode", ["verify", "mp"])
+def test_records_without_seq_are_counted_but_convert_nothing(tmp_path, mode):
+    """Secondary alignments often carry SEQ '*': they still count as reads and coverage of their UTRs; their MP entries
+    find no base quality (read position beyond the empty quality array -> 0, SlamSeqFile.py:326-329)."""
+    from slamdunk_b200.io import bam as bamio
+    c = simdata.make_case(str(tmp_path), seed=91, n_reads=1200, n_utr=30, snp_density=0.0)
+    text, refs, recs = bamio.read_bam(c.bam)
+    n = 0
+    for i, r in enumerate(recs):
+        if i % 7 == 3 or 320 <= i < 360:        # scattered, and one stretch covering a whole tile
+            r.seq, r.qual = "", None
+            r.flag |= 0x100
+            n += 1
+    assert n > 150
+    bam2 = str(tmp_path / "noseq.bam")
+    bamio.write_bam(bam2, text, refs, recs)
+    log = io.StringIO()
+    o = str(tmp_path / "orc")
+    oracle.count_files(c.ref, c.bed, None, bam2, 100, 27, o + ".tsv", o + "_p.bg", o + "_m.bg", 1, log)
+
+    class Case:
+        ref, bed, vcf, bam = c.ref, c.bed, None, bam2
+        max_read_length, min_qual, conv_threshold = 100, 27, 1
+    out, glog, tm = _count(Case, tmp_path, mode, "gpu")
+    assert _read(out + ".tsv") == _read(o + ".tsv")
+    assert _read(out + "_plus.bedgraph") == _read(o + "_p.bg")
+    assert _read(out + "_mins.bedgraph") == _read(o + "_m.bg")

@@ -283,3 +283,24 @@ def test_full_size_cfg2_properties():
     assert int(eng.pos_cov.min()) >= 0 and int(eng.pos_tc.min()) >= 0
     assert int((eng.pos_tc > eng.pos_cov).sum()) == 0                                   # conversions only where covered
     eng.close()
+
+
+def test_deep_coverage_tiles_aggregate_their_coverage_atomics():
+    """Ten reads per annotated base: the 32 sorted reads of a tile start within a few positions, which switches the
+    kernel to warp-aggregated coverage updates (the multi-GPU region shards look like this); counts stay exact."""
+    from slamdunk_b200 import _lib as L
+    from slamdunk_b200.engine import make_params
+    eng, wl = _setup(genome_bp=400_000, n_utr=24, seed=11)
+    p = wl.params(seed=21, first_read=0, n_reads=300_000, read_len=100, frac_softclip=0.05, frac_indel=0.02,
+                  frac_antisense=0.02, frac_labelled=1.0)
+    db, triples = wl.generate(p, want_mp=True, want_triples=True, coordinate_sorted=True)
+    pos = db.tensors["rec"].cpu().numpy().view(np.int32).reshape(-1, 5)[: 300_000, 0].astype(np.int64)
+    starts = pos.reshape(-1, 32)
+    assert np.median(starts[:, -1] - starts[:, 0]) <= 8, "workload is not deep enough to reach the aggregated path"
+    eng.count(db, make_params(27, 1, 0))
+    eng.finalize()
+    res = eng.results()
+    rows, bg = _oracle(wl, db, triples, 27, 1)
+    assert res["stats"][L.SD_S_COUNTED] == 300_000
+    assert ob.compare(res, rows, bg, wl.ann, eng.pos_off, wl.chrom_off) == []
+    eng.close()
