@@ -85,6 +85,9 @@ def lib():
         L.orc_count.argtypes = [ctypes.POINTER(_CountArgs), ctypes.c_void_p,
                                 ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
         L.orc_free.argtypes = [ctypes.c_void_p]
+        L.orc_positional_chrom.argtypes = [ctypes.POINTER(_CountArgs), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_positional_chrom.restype = ctypes.c_int
         L.orc_filter_default.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_filter_multimap.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32,
@@ -358,6 +361,123 @@ def count_files(ref, bed, snps_file, bam, max_read_length, min_qual, out_csv, ou
             out = fp if e["strand"] == 0 else fm
             print(id_to_name[int(e["name_id"])], int(e["pos"]), int(e["pos"]) + 1, rate, file=out)
     return rows, bg
+
+
+def _natural_keys(text):
+    """SlamSeqBamFile.natural_keys, SlamSeqFile.py:458-464"""
+    import re
+    return [int(c) if c.isdigit() else c for c in re.split(r"(\d+)", text)]
+
+
+TRACKS = [  # (file suffix, track name suffix, description) in the order tcounter.py:349-365 opens / heads them
+    ("_TC_rates_genomewide.bedGraph", " tc-conversions", "# T->C conversions / # reads on T per position genome-wide"),
+    ("_AG_rates_genomewide.bedGraph", " ag-conversions", "# A->G conversions / # reads on A per position genome-wide"),
+    ("_coverage_plus_genomewide.bedGraph", " plus-strand coverage", "# Reads on plus strand genome-wide"),
+    ("_coverage_minus_genomewide.bedGraph", " minus-strand coverage", "# Reads on minus strand genome-wide"),
+    ("_TC_conversions_genomewide.bedGraph", " T->C conversions", "# T->C conversions on plus strand genome-wide"),
+    ("_AG_conversions_genomewide.bedGraph", " A->G conversions", "# A->G conversions on minus strand genome-wide"),
+    ("_coverage_T_genomewide.bedGraph", " T-coverage", "# Plus-strand reads on Ts genome-wide"),
+    ("_coverage_A_genomewide.bedGraph", " A-coverage", "# Minus-strand reads on As genome-wide"),
+]
+
+
+def _rle_lines(chromosome, values, fh):
+    """The reference's run-length writer (tcounter.py:417-476) for one track of one chromosome: `values` is a Python
+    list holding exactly the objects the reference compares (ints, or int 0 / floats for the rate tracks).  A line is
+    written at every position whose value differs from the running one; the run in progress at the end is never written."""
+    prev, prev_pos = 0, 0
+    for pos, v in enumerate(values):
+        if prev != v:
+            print(chromosome + "\t" + str(prev_pos + 1) + "\t" + str(pos + 1) + "\t" + str(prev), file=fh)
+            prev, prev_pos = v, pos
+
+
+def positional_files(ref, snps_file, bam, min_qual, prefix, conv_threshold, coverage_cutoff, log, out=None):
+    """File-level restatement of tcounter.genomewideConversionRates (dunks/tcounter.py:332-487): eight run-length
+    bedGraphs.  Small inputs only: the per-position part runs as plain Python."""
+    import re
+    from slamdunk_b200.io import bam as bamio
+    text, bam_refs, records = bamio.read_bam(bam)
+    fasta = bamio.read_fasta(ref)
+    genome = Genome(list(fasta.keys()), [s.encode("ascii") for s in fasta.values()])
+    msgs = []
+    snp_handle = make_snps(read_vcf_records(snps_file, msgs))
+    for m in msgs:
+        print(m)
+    bam_names = [n for n, _l in bam_refs]
+    reads = np.zeros(len(records), dtype=READ_DT)
+    quals, mps = [], []
+    qoff = moff = k = 0
+    for r in records:
+        if r.ref_id < 0 or r.reference_end is None:
+            continue
+        rec = reads[k]
+        rec["chrom"] = genome.index.get(bam_names[r.ref_id], -1)
+        rec["pos"], rec["end"] = r.pos, r.reference_end
+        q = bytes(r.qual) if r.qual is not None else b""
+        rec["l_qual"], rec["flag"], rec["mapq"], rec["qual_off"] = len(q), r.flag, r.mapq, qoff
+        quals.append(q)
+        qoff += len(q)
+        if r.has_tag("MP"):
+            mp = r.get_tag("MP").encode("ascii")
+            rec["has_mp"], rec["mp_off"], rec["mp_len"] = 1, moff, len(mp)
+            mps.append(mp)
+            moff += len(mp)
+        k += 1
+    reads = reads[:k]
+    reads = reads[reads["chrom"] >= 0]
+    order = np.lexsort((reads["pos"], reads["chrom"]))
+    reads = np.ascontiguousarray(reads[order])
+    n_chrom = len(genome.names)
+    begin = np.searchsorted(reads["chrom"], np.arange(n_chrom + 1), side="left").astype(np.int64)
+    span = np.ones(n_chrom, dtype=np.int32)
+    qual_pool = np.frombuffer(b"".join(quals), dtype=np.uint8)
+    mp_buf = ctypes.create_string_buffer(b"".join(mps), moff + 1)
+    names = (ctypes.c_char_p * n_chrom)(*[n.encode() for n in genome.names])
+    seqs = (ctypes.c_char_p * n_chrom)(*genome.seqs)
+    a = _CountArgs()
+    a.n_chrom, a.chrom_names, a.chrom_seq, a.chrom_len = n_chrom, names, seqs, genome.lengths.ctypes.data
+    a.reads, a.chrom_read_begin, a.chrom_max_span = reads.ctypes.data, begin.ctypes.data, span.ctypes.data
+    a.qual_pool = qual_pool.ctypes.data if len(qual_pool) else None
+    a.mp_text, a.mp_triples = ctypes.cast(mp_buf, ctypes.c_void_p), None
+    a.n_utr, a.utrs = 0, None
+    a.min_qual, a.conversion_threshold, a.snps = int(min_qual), int(conv_threshold), snp_handle
+
+    info = re.sub("_slamdunk_mapped.*", "", os.path.basename(prefix))       # tcounter.py:346
+    print(info, file=out)                                                    # tcounter.py:347 (stdout)
+    files = [open(prefix + suffix, "w") for suffix, _n, _d in TRACKS]
+    try:
+        for fh, (_s, name, desc) in zip(files, TRACKS):
+            print("track type=bedGraph name=\"" + info + name + "\" description=\"" + desc + "\"", file=fh)
+        f_rate_p, f_rate_m, f_cov_p, f_cov_m, f_tc, f_ag, f_t, f_a = files
+        for chromosome in sorted(genome.names, key=_natural_keys):          # getChromosomes, SlamSeqFile.py:469-472
+            c = genome.index[chromosome]
+            n = int(genome.lengths[c])
+            tc, ag, covp, covm = (np.zeros(max(1, n), dtype=np.int32) for _ in range(4))
+            rc = lib().orc_positional_chrom(ctypes.byref(a), c, 1 if chromosome in bam_names else 0,
+                                            tc.ctypes.data, ag.ctypes.data, covp.ctypes.data, covm.ctypes.data)
+            if rc != 0:
+                raise RuntimeError("orc_positional_chrom failed")
+            seq = genome.seqs[c].decode("ascii")
+            tcl, agl, cpl, cml = tc[:n].tolist(), ag[:n].tolist(), covp[:n].tolist(), covm[:n].tolist()
+            # ref.fetch(start=pos + 1, end=pos + 2): the base right of index pos; past the end the fetch is empty
+            base = [seq[p + 1].upper() if p + 1 < n else "" for p in range(n)]
+            t_cov = [cpl[p] if cpl[p] > 0 and base[p] == "T" else 0 for p in range(n)]          # tcounter.py:427-439
+            a_cov = [cml[p] if cml[p] > 0 and base[p] == "A" else 0 for p in range(n)]
+            rate_p = [float(tcl[p]) / float(cpl[p]) if cpl[p] > 0 and cpl[p] >= coverage_cutoff else 0 for p in range(n)]
+            rate_m = [float(agl[p]) / float(cml[p]) if cml[p] > 0 and cml[p] >= coverage_cutoff else 0 for p in range(n)]
+            _rle_lines(chromosome, cpl, f_cov_p)
+            _rle_lines(chromosome, cml, f_cov_m)
+            _rle_lines(chromosome, t_cov, f_t)
+            _rle_lines(chromosome, a_cov, f_a)
+            _rle_lines(chromosome, tcl, f_tc)
+            _rle_lines(chromosome, agl, f_ag)
+            _rle_lines(chromosome, rate_p, f_rate_p)
+            _rle_lines(chromosome, rate_m, f_rate_m)
+    finally:
+        for fh in files:
+            fh.close()
+        free_snps(snp_handle)
 
 
 # --------------------------------------------------------------------------

@@ -285,6 +285,61 @@ static void count_one_utr(const orc_count_args_t *a, const orc_utr_t *u, orc_row
     free(tcCountUtr); free(coverageUtr);
 }
 
+/* One chromosome of genomewideConversionRates, tcounter.py:373-398 (the array part; the run-length text is written by the
+ * Python side of the oracle).  readsInChromosome (SlamSeqFile.py:447-453) hands the iterator startPosition 1 and strand ".",
+ * so every index below is (0-based genomic position - 1) and no read is skipped for its strand.
+ * tc/ag/covp/covm: int32[chrom_len], zeroed by the caller. */
+int orc_positional_chrom(const orc_count_args_t *a, int32_t chrom, int32_t in_bam,
+                         int32_t *tc, int32_t *ag, int32_t *covp, int32_t *covm) {
+    if (chrom < 0 || chrom >= a->n_chrom) return -1;
+    if (!in_bam) return 0;                                           /* `chromosome in self._bamFile.references` else iter([]) */
+    const int64_t chrLength = a->chrom_len[chrom];
+    const char *cname = a->chrom_names[chrom];
+    const int64_t startPosition = 1;
+    mp_entry_t ents[4096];
+    for (int64_t i = a->chrom_read_begin[chrom]; i < a->chrom_read_begin[chrom + 1]; i++) {   /* fetch(reference=chromosome) */
+        const orc_read_t *r = &a->reads[i];
+        const int is_rev = (r->flag & 0x10) != 0;                    /* read.direction, SlamSeqFile.py:376-379 */
+        int tcCount = 0, n_kept = 0;
+        int32_t kept_refpos[4096]; uint8_t kept_istc[4096];
+        if (r->has_mp) {                                             /* fillMismatchesNGM, SlamSeqFile.py:313-348 */
+            int n_ent;
+            if (a->mp_text) n_ent = mp_parse(a->mp_text + r->mp_off, r->mp_len, ents, 4096);
+            else {
+                n_ent = r->mp_len;
+                for (int k = 0; k < n_ent && k < 4096; k++) {
+                    const int32_t *t = a->mp_triples + 3 * (r->mp_off + k);
+                    ents[k].conv = t[0]; ents[k].read_pos = t[1]; ents[k].ref_pos = t[2];
+                }
+            }
+            if (n_ent > 4096) n_ent = 4096;
+            for (int k = 0; k < n_ent; k++) {
+                int readPos = ents[k].read_pos - 1;
+                int readQlty = (readPos >= r->l_qual) ? 0 : a->qual_pool[r->qual_off + readPos];
+                if (readQlty >= a->min_qual) {
+                    int refPos = ents[k].ref_pos - 1;
+                    int isSnp;
+                    if (is_rev) isSnp = a->snps && snp_query(&((orc_snps_t *)a->snps)->ag, cname, (int64_t)r->pos + refPos);
+                    else        isSnp = a->snps && snp_query(&((orc_snps_t *)a->snps)->tc, cname, (int64_t)r->pos + refPos);
+                    int64_t relPos = (int64_t)r->pos - startPosition + refPos;                    /* :339 */
+                    int isTC = ((is_rev ? ents[k].conv == 2 : ents[k].conv == 16) && !isSnp);
+                    if (isTC) tcCount++;
+                    kept_refpos[n_kept] = (int32_t)relPos; kept_istc[n_kept] = (uint8_t)isTC; n_kept++;
+                }
+            }
+        }
+        if (!(tcCount >= a->conversion_threshold)) { tcCount = 0; n_kept = 0; }                  /* tcounter.py:378-382 */
+        for (int k = 0; k < n_kept; k++)                                                          /* tcounter.py:384-389 */
+            if (kept_istc[k] && kept_refpos[k] >= 0 && kept_refpos[k] < chrLength) {
+                if (is_rev) ag[kept_refpos[k]]++; else tc[kept_refpos[k]]++;
+            }
+        const int64_t startRefPos = (int64_t)r->pos - startPosition, endRefPos = (int64_t)r->end - startPosition;
+        for (int64_t p = startRefPos; p < endRefPos; p++)                                         /* tcounter.py:391-396 */
+            if (p >= 0 && p < chrLength) { if (is_rev) covm[p]++; else covp[p]++; }
+    }
+    return 0;
+}
+
 /* computeTconversions, tcounter.py:165-326, without the text formatting.
  * rows[n_utr]; bedgraph entries returned through *bg (malloc'd, free with orc_free) in the
  * dict's iteration order (first insertion keeps the slot, later assignments overwrite the value). */

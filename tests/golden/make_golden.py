@@ -13,6 +13,8 @@ case_* randomized data sets from tests/simdata.py; expected files are whatever t
        code writes for them.
 filt_* mapper-order BAMs through the reference's filter.Filter (default and multimapper-
        retention modes); expected = DS counters + the written records.
+case_*/positional   the same inputs through tcounter.genomewideConversionRates (alleyoop positional-tracks):
+       the eight run-length bedGraphs (python tests/golden/make_golden.py positional regenerates only these).
 """
 import hashlib
 import json
@@ -143,14 +145,39 @@ def make_filter_case(name, mk, fk):
     print(name, "kept", len(recs), hdr["RG"][0]["DS"])
 
 
+# case -> (min_qual, conversion threshold, coverage cutoff) of the positional-tracks run on the count case's inputs
+POSITIONAL = {"case_a": (27, 1, 1), "case_b": (20, 2, 3), "case_d": (27, 1, 2), "case_e": (0, 0, 1)}
+
+
+def make_positional(name, min_qual, conv_threshold, cutoff):
+    d = os.path.join(HERE, name)
+    out = os.path.join(d, "positional")
+    if os.path.isdir(out):
+        shutil.rmtree(out)
+    os.makedirs(out)
+    vcf = os.path.join(d, name + ".vcf")
+    prefix = os.path.join(out, name + "_slamdunk_mapped_filtered_positional_rates")
+    stdout, _log = refrun.run_positional(os.path.join(d, name + ".fa"), vcf if os.path.exists(vcf) else None,
+                                         os.path.join(d, name + ".bam"), prefix, min_qual, conv_threshold, cutoff)
+    with open(os.path.join(out, "params.json"), "w") as fh:
+        json.dump(dict(min_qual=min_qual, conv_threshold=conv_threshold, coverage_cutoff=cutoff, stdout=stdout), fh, indent=1, sort_keys=True)
+    print(name, "positional lines", sum(sum(1 for _ in open(os.path.join(out, f))) for f in os.listdir(out) if f.endswith(".bedGraph")))
+
+
 def main():
     if not refrun.available():
         sys.exit("reference tree not found; goldens can only be regenerated in the build container")
+    if sys.argv[1:] == ["positional"]:
+        for name, args in POSITIONAL.items():
+            make_positional(name, *args)
+        return
     make_cfg1(os.path.join(HERE, "cfg1"))
     for name, (mk, ck) in CASES.items():
         make_count_case(name, mk, ck)
     for name, (mk, fk) in FILTER_CASES.items():
         make_filter_case(name, mk, fk)
+    for name, args in POSITIONAL.items():
+        make_positional(name, *args)
 
 
 if __name__ == "__main__":

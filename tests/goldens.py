@@ -43,3 +43,20 @@ class FilterCase:
 
 COUNT_CASES = ["cfg1", "case_a", "case_b", "case_c", "case_d", "case_e"]
 FILTER_CASES = ["filt_default", "filt_nm", "filt_multimap", "filt_multimap_nm"]
+
+
+class PositionalCase:
+    """alleyoop positional-tracks on the inputs of a count case (tests/golden/<case>/positional)."""
+    def __init__(self, name):
+        c = CountCase(name)
+        self.name, self.ref, self.vcf, self.bam = name, c.ref, c.vcf, c.bam
+        self.dir = os.path.join(c.dir, "positional")
+        p = json.load(open(os.path.join(self.dir, "params.json")))
+        self.min_qual, self.conv_threshold, self.coverage_cutoff, self.stdout = p["min_qual"], p["conv_threshold"], p["coverage_cutoff"], p["stdout"]
+        self.prefix_name = name + "_slamdunk_mapped_filtered_positional_rates"
+
+    def expected(self, suffix):
+        return os.path.join(self.dir, self.prefix_name + suffix)
+
+
+POSITIONAL_CASES = ["case_a", "case_b", "case_d", "case_e"]

@@ -65,3 +65,14 @@ def run_filter(in_bam, out_bam, bed=None, mq=2, min_identity=0.95, nm=-1):
     log = io.StringIO()
     rfilter.Filter(in_bam, out_bam, log, bed, mq, min_identity, nm, False, False, True)
     return log.getvalue()
+
+
+def run_positional(ref, vcf, bam, out_prefix, min_qual=27, conv_threshold=1, coverage_cutoff=1):
+    """reference tcounter.genomewideConversionRates (alleyoop positional-tracks) -> (stdout text, log text);
+    the eight bedGraphs are written next to out_prefix."""
+    import contextlib
+    tcounter, _ = reference_modules()
+    log, out = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(out):
+        tcounter.genomewideConversionRates(ref, vcf, bam, min_qual, out_prefix, conv_threshold, coverage_cutoff, log)
+    return out.getvalue(), log.getvalue()

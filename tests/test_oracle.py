@@ -112,3 +112,29 @@ def test_bam_codec_roundtrip(tmp_path):
                (b.qname, b.flag, b.ref_id, b.pos, b.mapq, b.cigar, b.seq, b.qual)
         assert [(t, v if ty != "f" else round(v, 5)) for t, ty, v in a.tags] == \
                [(t, v if ty != "f" else round(v, 5)) for t, ty, v in b.tags]
+
+
+@pytest.mark.parametrize("name", goldens.POSITIONAL_CASES)
+def test_oracle_positional_tracks_match_golden(name, tmp_path):
+    """genomewideConversionRates (alleyoop positional-tracks): the oracle's eight run-length bedGraphs equal what the
+    reference wrote for the same inputs (tests/golden/<case>/positional)."""
+    c = goldens.PositionalCase(name)
+    out = io.StringIO()
+    oracle.positional_files(c.ref, c.vcf, c.bam, c.min_qual, str(tmp_path / c.prefix_name), c.conv_threshold,
+                            c.coverage_cutoff, io.StringIO(), out=out)
+    assert out.getvalue() == c.stdout
+    for suffix, _n, _d in oracle.TRACKS:
+        assert open(str(tmp_path / c.prefix_name) + suffix).read() == open(c.expected(suffix)).read(), suffix
+
+
+@pytest.mark.skipif(not refrun.available(), reason="reference tree not present")
+@pytest.mark.parametrize("seed,q,thr,cutoff", [(61, 27, 1, 1), (62, 10, 3, 4)])
+def test_oracle_vs_live_reference_positional(seed, q, thr, cutoff, tmp_path):
+    c = simdata.make_case(str(tmp_path), seed=seed, n_reads=700, n_utr=10, complexity=2.0, snp_density=0.02,
+                          chroms=(("chr10", 5000), ("chr2", 4000), ("chr1", 2500), ("chrM", 600)))
+    (tmp_path / "r").mkdir()
+    (tmp_path / "o").mkdir()
+    refrun.run_positional(c.ref, c.vcf, c.bam, str(tmp_path / "r" / "s_slamdunk_mapped_x"), q, thr, cutoff)
+    oracle.positional_files(c.ref, c.vcf, c.bam, q, str(tmp_path / "o" / "s_slamdunk_mapped_x"), thr, cutoff, io.StringIO(), out=io.StringIO())
+    for suffix, _n, _d in oracle.TRACKS:
+        assert open(str(tmp_path / "o" / "s_slamdunk_mapped_x") + suffix).read() == open(str(tmp_path / "r" / "s_slamdunk_mapped_x") + suffix).read(), suffix
