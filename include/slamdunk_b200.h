@@ -127,8 +127,12 @@ typedef struct sd_params {
     int32_t filter_max_nm;        /* NM, -1 = off */
     double filter_min_identity;   /* minIdentity */
     int32_t force_slow_path;      /* testing: run every read through the per-base path */
-    int32_t reserved;
+    int32_t flags;                /* SD_PARAM_* */
 } sd_params;
+/* SD_MISMATCH_MP only: keep every accepted MP conversion, also where the FASTA base is not T / A.  For the genome-wide
+ * tracks: genomewideConversionRates never looks at the FASTA for its conversion arrays (tcounter.py:384-389).  The
+ * per-UTR conversionsOnTs counter of `count` does (tcounter.py:279) and must not be read from a run with this flag. */
+#define SD_PARAM_MP_ANY_BASE 1
 
 /* Per-UTR integer counters, row-major [n_utr][SD_NCOUNTER], BED order. */
 #define SD_NCOUNTER 5
@@ -308,6 +312,27 @@ int sd_write_bedgraphs(const char *path_plus, const char *path_minus, uint32_t n
                        const uint64_t *row_pos_off, const uint32_t *row_pos_len, const uint64_t *row_gstart,
                        const uint32_t *isx_plus, const uint32_t *isx_minus, const int32_t *pos_cov,
                        const int32_t *pos_tc, uint64_t n_positions);
+
+/* ------------------------------------------------------------------ genome-wide per-position tracks
+ * `alleyoop positional-tracks` (dunks/tcounter.py:332-487 genomewideConversionRates).  The per-position arrays come from
+ * sd_count + sd_finalize run with one annotation row per chromosome strand starting at position 1 (the reference's
+ * iterator has startPosition 1, SlamSeqFile.py:451: array index p = 0-based genomic position p + 1).
+ * sd_track_runs compacts one track of one row into its change points on the device: d_pos[j] = index whose value
+ * differs from the previous index's (index -1 counts as 0), d_val[j] = the value from there on, d_isfloat[j] (RATE
+ * track, may be NULL otherwise) = 1 when the reference holds that value as a float (coverage >= cutoff) rather than
+ * the int 0.  track_len = length of the reference's array (the chromosome length); indices past the row's clipped
+ * length read as 0.  Call with d_pos == NULL (or capacity 0) to get the number of change points in *n_runs.
+ * sd_write_track appends the reference's run-length lines (tcounter.py:417-476) for those change points to `path`:
+ * one line per change point, "<chrom>\t<previous change + 1>\t<this change + 1>\t<value before>"; the run still
+ * open at the end of the chromosome is never written, exactly as in the reference. */
+#define SD_TRACK_COVERAGE 0         /* reads covering the position (coverage_plus / coverage_minus) */
+#define SD_TRACK_COVERAGE_ON_BASE 1 /* the same where the FASTA base is T (plus) / A (minus), else 0 */
+#define SD_TRACK_CONVERSIONS 2      /* T>C (plus) / A>G (minus) conversions at the position */
+#define SD_TRACK_RATE 3             /* conversions / coverage where coverage >= max(1, cutoff), else int 0 */
+int sd_track_runs(sd_ctx *ctx, uint32_t row, int kind, int coverage_cutoff, uint32_t track_len, uint32_t *d_pos,
+                  double *d_val, uint8_t *d_isfloat, uint64_t capacity, uint64_t *n_runs);
+int sd_write_track(const char *path, const char *chrom, int kind, uint64_t n_runs, const uint32_t *h_pos,
+                   const double *h_val, const uint8_t *h_isfloat);
 
 /* ------------------------------------------------------------------ synthetic SLAM-seq reads
  * Device-side generator of the BASELINE.json configurations (per-T Bernoulli conversions as in

@@ -13,6 +13,8 @@ SD_F_REVERSE, SD_F_UNMAPPED, SD_F_SECONDARY, SD_F_SUPPLEMENTARY = 0x01, 0x02, 0x
 SD_F_HAS_MP, SD_F_SKIP, SD_F_NEWNAME, SD_F_PAD = 0x10, 0x20, 0x40, 0x80
 SD_REF_NONE = 0xFFFF
 SD_MISMATCH_CIGAR, SD_MISMATCH_MP, SD_MISMATCH_VERIFY = 0, 1, 2
+SD_PARAM_MP_ANY_BASE = 1
+SD_TRACK_COVERAGE, SD_TRACK_COVERAGE_ON_BASE, SD_TRACK_CONVERSIONS, SD_TRACK_RATE = 0, 1, 2, 3
 SD_NCOUNTER = 5
 SD_DECODE_MP, SD_DECODE_GROUP = 1, 2
 SD_C_READS, SD_C_TCREADS, SD_C_MULTIMAP, SD_C_COV_ON_T, SD_C_CONV_ON_T = range(5)
@@ -48,7 +50,7 @@ class Params(ctypes.Structure):
     _fields_ = [("min_qual", ctypes.c_int32), ("conversion_threshold", ctypes.c_int32),
                 ("mismatch_source", ctypes.c_int32), ("filter_on", ctypes.c_int32), ("filter_mq", ctypes.c_int32),
                 ("filter_max_nm", ctypes.c_int32), ("filter_min_identity", ctypes.c_double),
-                ("force_slow_path", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("force_slow_path", ctypes.c_int32), ("flags", ctypes.c_int32)]
 
 
 class HBatch(ctypes.Structure):
@@ -116,6 +118,8 @@ PROTOTYPES = {
     "sd_format_repr": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p]),
     "sd_write_bedgraphs": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p), _VP, _VP,
                                           _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_uint64]),
+    "sd_track_runs": (ctypes.c_int, [_VP, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, _VP, _VP, _VP, ctypes.c_uint64, c_u64p]),
+    "sd_write_track": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint64, _VP, _VP, _VP]),
     "sd_synth_positions": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP, _VP]),
     "sd_synth_plan": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP, _VP, c_u64p]),
     "sd_synth_fill": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP,

@@ -117,6 +117,7 @@ struct CountArgs {
     int filter_max_nm;
     float filter_min_identity;   // smallest float >= the double threshold: xi < this  <=>  (double)xi < threshold
     int force_slow;
+    int mp_any_base;   // SD_PARAM_MP_ANY_BASE
 };
 
 __device__ __forceinline__ bool cigar_consumes_ref(uint32_t op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
@@ -308,7 +309,8 @@ __device__ __noinline__ int slow_read(const CountArgs &A, const ReadView v, uint
                 if (tc > 0)
                     slow_for_each_hit(A, v, [&](int o, bool on_t) {
                         const uint32_t gp = g + (uint32_t)o;
-                        if (on_t && gp >= pa && gp < pb) atomicAdd(&A.pos_tc[off + (gp - ss)], 1);
+                        if ((on_t || (A.mp_any_base && A.mismatch_source == SD_MISMATCH_MP)) && gp >= pa && gp < pb)
+                            atomicAdd(&A.pos_tc[off + (gp - ss)], 1);
                     });
             }
         }
@@ -525,7 +527,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
         for (int k = 0; k < W; k++) {
             const uint32_t h = R[k] & ~S[k];
             tc += __popc(h);
-            H[k] = h & T[k];
+            H[k] = A.mp_any_base ? h : (h & T[k]);
         }
     } else {
 #pragma unroll
@@ -1192,6 +1194,8 @@ extern "C" int sd_set_utrs(sd_ctx *ctx, const uint32_t *h_chrom, const int64_t *
     if ((rc = upload(ctx, &ctx->d_row_gstart, row_gs))) return rc;
     if ((rc = upload(ctx, &ctx->d_row_gend, row_ge))) return rc;
     if ((rc = upload(ctx, &ctx->d_row_strand, row_st))) return rc;
+    ctx->row_gstart = row_gs;
+    ctx->row_strand = row_st;
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->counters = nullptr;
     ctx->pos_cov = ctx->pos_tc = nullptr;
@@ -1352,6 +1356,7 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
         A.filter_min_identity = f;
     }
     A.force_slow = p->force_slow_path;
+    A.mp_any_base = (p->flags & SD_PARAM_MP_ANY_BASE) ? 1 : 0;
     if (b->max_lseq <= 128) return launch_count<4>(ctx, A, stream, timed);
     if (b->max_lseq <= 256) return launch_count<8>(ctx, A, stream, timed);
     return launch_count<16>(ctx, A, stream, timed);

@@ -48,6 +48,8 @@ struct sd_ctx {
     uint8_t *d_row_strand = nullptr;
     std::vector<uint64_t> row_pos_off;
     std::vector<uint32_t> row_pos_len;
+    std::vector<uint32_t> row_gstart;   // host copies of d_row_gstart / d_row_strand
+    std::vector<uint8_t> row_strand;
 
     // caller-owned outputs
     int64_t *counters = nullptr;

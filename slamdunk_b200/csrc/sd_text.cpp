@@ -132,3 +132,43 @@ extern "C" int sd_write_bedgraphs(const char *path_plus, const char *path_minus,
     }
     return SD_OK;
 }
+
+
+// Run-length lines of one genome-wide track of one chromosome (tcounter.py:417-476): a line is printed whenever the value
+// changes, holding the run that just ended; the first run is the implicit "0 from position 0".
+extern "C" int sd_write_track(const char *path, const char *chrom, int kind, uint64_t n_runs, const uint32_t *h_pos,
+                              const double *h_val, const uint8_t *h_isfloat) {
+    if (!path || !chrom || (n_runs && (!h_pos || !h_val))) return SD_ERR_ARG;
+    if (kind == SD_TRACK_RATE && n_runs && !h_isfloat) return SD_ERR_ARG;
+    FILE *fh = fopen(path, "ab");
+    if (!fh) return SD_ERR_IO;
+    std::string out;
+    out.reserve(1 << 20);
+    const size_t lc = strlen(chrom);
+    uint32_t prev_pos = 0;
+    double prev_val = 0.0;
+    bool prev_float = false;
+    char num[64];
+    for (uint64_t j = 0; j < n_runs; j++) {
+        out.append(chrom, lc);
+        int k = snprintf(num, sizeof num, "\t%u\t%u\t", prev_pos + 1u, h_pos[j] + 1u);
+        out.append(num, (size_t)k);
+        if (kind == SD_TRACK_RATE && prev_float) {
+            sd_format_repr(prev_val, num);
+            out.append(num);
+        } else {
+            k = snprintf(num, sizeof num, "%lld", (long long)prev_val);
+            out.append(num, (size_t)k);
+        }
+        out.push_back('\n');
+        prev_pos = h_pos[j];
+        prev_val = h_val[j];
+        prev_float = kind == SD_TRACK_RATE && h_isfloat[j];
+        if (out.size() > (1u << 20) - 256) {
+            if (fwrite(out.data(), 1, out.size(), fh) != out.size()) { fclose(fh); return SD_ERR_IO; }
+            out.clear();
+        }
+    }
+    const bool ok = fwrite(out.data(), 1, out.size(), fh) == out.size();
+    return (fclose(fh) == 0 && ok) ? SD_OK : SD_ERR_IO;
+}

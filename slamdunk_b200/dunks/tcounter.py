@@ -11,6 +11,7 @@ What happens where
 from __future__ import print_function
 
 import os
+import re
 import time
 
 import numpy as np
@@ -228,3 +229,110 @@ def _write_bedgraphs(utrs, chrom_idx, genome, res, pos_off, pos_len, counters, o
                                 ptr(pl), ptr(gstart), ptr(isx[0]), ptr(isx[1]), ptr(cov), ptr(tc), len(cov))
     if rc != L.SD_OK:
         raise L.NativeError("sd_write_bedgraphs failed with code %d" % rc)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# alleyoop positional-tracks
+# ---------------------------------------------------------------------------------------------------------------
+TRACKS = [  # (file suffix, track name suffix, description, strand, SD_TRACK_*) in the order tcounter.py:349-365 opens / heads them
+    ("_TC_rates_genomewide.bedGraph", " tc-conversions", "# T->C conversions / # reads on T per position genome-wide", 0, L.SD_TRACK_RATE),
+    ("_AG_rates_genomewide.bedGraph", " ag-conversions", "# A->G conversions / # reads on A per position genome-wide", 1, L.SD_TRACK_RATE),
+    ("_coverage_plus_genomewide.bedGraph", " plus-strand coverage", "# Reads on plus strand genome-wide", 0, L.SD_TRACK_COVERAGE),
+    ("_coverage_minus_genomewide.bedGraph", " minus-strand coverage", "# Reads on minus strand genome-wide", 1, L.SD_TRACK_COVERAGE),
+    ("_TC_conversions_genomewide.bedGraph", " T->C conversions", "# T->C conversions on plus strand genome-wide", 0, L.SD_TRACK_CONVERSIONS),
+    ("_AG_conversions_genomewide.bedGraph", " A->G conversions", "# A->G conversions on minus strand genome-wide", 1, L.SD_TRACK_CONVERSIONS),
+    ("_coverage_T_genomewide.bedGraph", " T-coverage", "# Plus-strand reads on Ts genome-wide", 0, L.SD_TRACK_COVERAGE_ON_BASE),
+    ("_coverage_A_genomewide.bedGraph", " A-coverage", "# Minus-strand reads on As genome-wide", 1, L.SD_TRACK_COVERAGE_ON_BASE),
+]
+
+
+def _natural_keys(text):
+    """SlamSeqBamFile.natural_keys (slamseq/SlamSeqFile.py:458-464): chr2 before chr10."""
+    return [int(c) if c.isdigit() else c for c in re.split(r"(\d+)", text)]
+
+
+def genomewideConversionRates(referenceFile, snpsFile, bam, minBaseQual, outputBedGraphPrefix, conversionThreshold,
+                              coverageCutoff, log):
+    """Drop-in for the reference's tcounter.genomewideConversionRates (dunks/tcounter.py:332-487, behind
+    `alleyoop positional-tracks`): eight run-length bedGraphs per BAM -- coverage, coverage on T / A, conversions and
+    conversion rates on both strands, genome-wide.
+
+    Device: the same per-read scan as `count`, with one annotation row per chromosome strand that starts at position 1
+    (the reference builds its iterator with startPosition 1, SlamSeqFile.py:451, so index p of its arrays is the 0-based
+    genomic position p + 1 and the chromosome's first base is never counted), then sd_track_runs compacts every track
+    into its change points.  Host: BAM / FASTA decode and the text of the change points (sd_write_track)."""
+    import ctypes
+    tm = CountTimings()
+    t0 = time.time()
+    genome, cached = _genome(referenceFile)
+    tm["fasta_decode_s"] = 0.0 if cached else genome.seconds
+    mode = {"cigar": L.SD_MISMATCH_CIGAR, "mp": L.SD_MISMATCH_MP, "verify": L.SD_MISMATCH_VERIFY}[OPTIONS["mismatch_source"]]
+    hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True)
+    tm["bam_inflate_s"], tm["bam_decode_s"], tm["bam_reads"] = hbatch.seconds_inflate, hbatch.seconds_decode, hbatch.n_reads
+    tc_mask, ag_mask = build_snp_masks(snpsFile, genome.names, genome.chrom_off, genome.chrom_len, genome.n_words, warn=print)
+
+    chromosomes = sorted(genome.names, key=_natural_keys)              # getChromosomes, SlamSeqFile.py:469-472
+    bedGraphInfo = re.sub("_slamdunk_mapped.*", "", os.path.basename(outputBedGraphPrefix))
+    print(bedGraphInfo)                                                # tcounter.py:347
+    paths = []
+    for suffix, name, desc, _strand, _kind in TRACKS:
+        paths.append(outputBedGraphPrefix + suffix)
+        with open(paths[-1], "w") as fh:
+            print("track type=bedGraph name=\"" + bedGraphInfo + name + "\" description=\"" + desc + "\"", file=fh)
+
+    # rows 2c (+) and 2c + 1 (-) for FASTA chromosome c: [1, chrLen + 1) clipped to the chromosome by sd_set_utrs
+    n_chrom = len(genome.names)
+    bam_names = set(hbatch.ref_names)
+    chrom_idx = np.repeat(np.arange(n_chrom, dtype=np.uint32), 2)
+    lengths = np.asarray(genome.chrom_len, dtype=np.int64)
+    start = np.ones(2 * n_chrom, dtype=np.int64)
+    stop = np.repeat(lengths + 1, 2)
+    strand = np.tile(np.array([0, 1], dtype=np.uint8), n_chrom)
+    in_bam = np.repeat(np.array([1 if nm in bam_names else 0 for nm in genome.names], dtype=np.uint8), 2)
+    tm["host_prepare_s"] = time.time() - t0 - tm["fasta_decode_s"] - tm["bam_inflate_s"] - tm["bam_decode_s"]
+
+    t1 = time.time()
+    lib = L.load()
+    eng = CountEngine(OPTIONS["device"])
+    try:
+        eng.set_reference(genome.lo, genome.hi, genome.nmask, genome.chrom_off, genome.chrom_len)
+        if tc_mask is not None:
+            eng.set_snps(tc_mask, ag_mask)
+        eng.set_utrs(chrom_idx, start, stop, strand, in_bam)
+        params = make_params(min_qual=minBaseQual, conversion_threshold=conversionThreshold, mismatch_source=mode,
+                             flags=L.SD_PARAM_MP_ANY_BASE)
+        eng.synchronize()
+        t2 = time.time()
+        eng.count_host(hbatch.batch, params)
+        stats = eng.stats.cpu().numpy()
+        if mode == L.SD_MISMATCH_VERIFY and stats[L.SD_S_MP_DISAGREE] > 0:
+            print("Warning: %d reads carry MP tags that disagree with a CIGAR walk against %s; taking the conversions from the MP tags as slamdunk does."
+                  % (int(stats[L.SD_S_MP_DISAGREE]), os.path.basename(referenceFile)), file=log)
+            eng.reset_outputs()
+            params = make_params(min_qual=minBaseQual, conversion_threshold=conversionThreshold, mismatch_source=L.SD_MISMATCH_MP,
+                                 flags=L.SD_PARAM_MP_ANY_BASE)
+            eng.count_host(hbatch.batch, params)
+        eng.finalize()
+        tm["gpu_setup_s"] = t2 - t1
+        tm["gpu_count_s"] = time.time() - t2
+        t3 = time.time()
+        n_lines = 0
+        for chromosome in chromosomes:
+            c = genome.index[chromosome]
+            for path, (_suffix, _name, _desc, s, kind) in zip(paths, TRACKS):
+                pos, val, isf = eng.track_runs(2 * c + s, kind, int(coverageCutoff), int(lengths[c]))
+                if len(pos) == 0:
+                    continue
+                rc = lib.sd_write_track(os.fsencode(path), chromosome.encode(), kind, len(pos), pos.ctypes.data, val.ctypes.data,
+                                        isf.ctypes.data)
+                if rc != L.SD_OK:
+                    raise IOError("sd_write_track failed with code %d on %s" % (rc, path))
+                n_lines += len(pos)
+        tm["tracks_s"] = time.time() - t3
+        tm["track_lines"] = n_lines
+        tm["gpu_launches"] = eng.launch_count()
+    finally:
+        eng.close()
+    tm["total_s"] = time.time() - t0
+    OPTIONS["timings"] = tm
+    hbatch.close()

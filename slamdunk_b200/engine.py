@@ -185,7 +185,7 @@ class DeviceBatch(object):
 
 
 def make_params(min_qual=27, conversion_threshold=1, mismatch_source=L.SD_MISMATCH_CIGAR, filter_on=False,
-                filter_mq=0, filter_min_identity=0.0, filter_max_nm=-1, force_slow_path=False) -> L.Params:
+                filter_mq=0, filter_min_identity=0.0, filter_max_nm=-1, force_slow_path=False, flags=0) -> L.Params:
     p = L.Params()
     p.min_qual = int(min_qual)
     p.conversion_threshold = int(conversion_threshold)
@@ -195,6 +195,7 @@ def make_params(min_qual=27, conversion_threshold=1, mismatch_source=L.SD_MISMAT
     p.filter_max_nm = int(filter_max_nm)
     p.filter_min_identity = float(filter_min_identity)
     p.force_slow_path = 1 if force_slow_path else 0
+    p.flags = int(flags)
     return p
 
 
@@ -340,6 +341,26 @@ class CountEngine(object):
         self._chk(self.lib.sd_filter(self.ctx, ctypes.byref(dbatch.batch), ctypes.byref(params), args[0], args[1], args[2],
                                      args[3], args[4], args[5], _t_ptr(keep), _t_ptr(stats), _t_ptr(state)), "sd_filter")
         return keep.cpu().numpy()[:n], stats.cpu().numpy(), state.cpu().numpy()[:n]
+
+    # -- genome-wide tracks ------------------------------------------------------------
+    def track_runs(self, row: int, kind: int, coverage_cutoff: int, track_len: int):
+        """Change points of one per-position track of annotation row `row` (sd_track_runs), after finalize().
+        -> (pos uint32[n], val float64[n], isfloat uint8[n]) host arrays."""
+        n = ctypes.c_uint64(0)
+        self._chk(self.lib.sd_track_runs(self.ctx, row, kind, coverage_cutoff, track_len, None, None, None, 0, ctypes.byref(n)),
+                  "sd_track_runs")
+        cnt = int(n.value)
+        if cnt == 0:
+            return np.zeros(0, np.uint32), np.zeros(0, np.float64), np.zeros(0, np.uint8)
+        with torch.cuda.stream(self.stream):
+            pos = torch.empty(cnt, dtype=torch.int32, device=self.device)
+            val = torch.empty(cnt, dtype=torch.float64, device=self.device)
+            isf = torch.zeros(cnt, dtype=torch.uint8, device=self.device)
+        self.stream.synchronize()
+        self._chk(self.lib.sd_track_runs(self.ctx, row, kind, coverage_cutoff, track_len, _t_ptr(pos), _t_ptr(val), _t_ptr(isf),
+                                         cnt, ctypes.byref(n)), "sd_track_runs")
+        assert int(n.value) == cnt
+        return pos.cpu().numpy().view(np.uint32), val.cpu().numpy(), isf.cpu().numpy()
 
     # -- outputs -----------------------------------------------------------------------
     def results(self):
