@@ -58,6 +58,10 @@ struct sd_ctx {
 
     unsigned int *d_tile_counter = nullptr;   // work-queue head of the count kernel
 
+    // grow-only scratch of sd_track_runs (flags | selected positions | cub temp | count)
+    void *d_track_scratch = nullptr;
+    size_t track_scratch_cap = 0;
+
     // staging for sd_count_host
     void *d_stage[2] = {nullptr, nullptr};
     size_t stage_cap = 0;

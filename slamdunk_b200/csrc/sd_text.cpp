@@ -151,14 +151,16 @@ extern "C" int sd_write_track(const char *path, const char *chrom, int kind, uin
     char num[64];
     for (uint64_t j = 0; j < n_runs; j++) {
         out.append(chrom, lc);
-        int k = snprintf(num, sizeof num, "\t%u\t%u\t", prev_pos + 1u, h_pos[j] + 1u);
-        out.append(num, (size_t)k);
+        out.push_back('\t');
+        out.append(num, (size_t)(std::to_chars(num, num + sizeof num, prev_pos + 1u).ptr - num));
+        out.push_back('\t');
+        out.append(num, (size_t)(std::to_chars(num, num + sizeof num, h_pos[j] + 1u).ptr - num));
+        out.push_back('\t');
         if (kind == SD_TRACK_RATE && prev_float) {
             sd_format_repr(prev_val, num);
             out.append(num);
         } else {
-            k = snprintf(num, sizeof num, "%lld", (long long)prev_val);
-            out.append(num, (size_t)k);
+            out.append(num, (size_t)(std::to_chars(num, num + sizeof num, (long long)prev_val).ptr - num));
         }
         out.push_back('\n');
         prev_pos = h_pos[j];

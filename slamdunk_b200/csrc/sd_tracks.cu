@@ -69,6 +69,7 @@ extern "C" int sd_track_runs(sd_ctx *ctx, uint32_t row, int kind, int coverage_c
     if (row >= ctx->n_utr) return sd_fail(ctx, SD_ERR_ARG, "sd_track_runs: row %u out of range", row);
     if (kind < SD_TRACK_COVERAGE || kind > SD_TRACK_RATE) return sd_fail(ctx, SD_ERR_ARG, "sd_track_runs: unknown track kind %d", kind);
     if (!ctx->pos_cov || !ctx->pos_tc) return sd_fail(ctx, SD_ERR_STATE, "sd_track_runs before sd_bind_outputs");
+    if (track_len > 0x7FFFFFFFu) return sd_fail(ctx, SD_ERR_LIMIT, "sd_track_runs: track longer than 2^31 - 1 positions");
     SD_CUDA(ctx, cudaSetDevice(ctx->device));
     *n_runs = 0;
     if (track_len == 0) return SD_OK;
@@ -82,58 +83,54 @@ extern "C" int sd_track_runs(sd_ctx *ctx, uint32_t row, int kind, int coverage_c
     a.track_len = track_len;
     a.kind = kind;
     a.cutoff = coverage_cutoff;
-    uint8_t *flags = nullptr;
-    uint32_t *sel = nullptr;
-    uint64_t *d_n = nullptr;
-    void *tmp = nullptr;
-    size_t tmp_bytes = 0;
-    auto done = [&](int code) {
-        cudaFree(flags); cudaFree(sel); cudaFree(d_n); cudaFree(tmp);
-        return code;
-    };
-    SD_CUDA(ctx, cudaMalloc(&flags, track_len));
-    if (cudaMalloc(&d_n, sizeof(uint64_t)) != cudaSuccess) return done(sd_fail(ctx, SD_ERR_NOMEM, "sd_track_runs: out of device memory"));
+    const bool sizing = d_pos == nullptr || capacity == 0;
+    if (!sizing && !d_val) return sd_fail(ctx, SD_ERR_ARG, "sd_track_runs: d_val is null");
+
+    // scratch (kept in the context, grow only): flags | count | selected positions | cub temp
+    cub::CountingInputIterator<uint32_t> positions(0);
+    cub::TransformInputIterator<uint64_t, cub::CastOp<uint64_t>, const uint8_t *> wide((const uint8_t *)nullptr, cub::CastOp<uint64_t>());
+    size_t tmp_select = 0, tmp_sum = 0;
+    cub::DeviceSelect::Flagged(nullptr, tmp_select, positions, (const uint8_t *)nullptr, (uint32_t *)nullptr, (uint64_t *)nullptr, (int)track_len, ctx->stream);
+    cub::DeviceReduce::Sum(nullptr, tmp_sum, wide, (uint64_t *)nullptr, (int)track_len, ctx->stream);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_flags = 0, o_count = up(track_len), o_sel = o_count + 256, o_tmp = o_sel + up((size_t)track_len * sizeof(uint32_t));
+    const size_t need = o_tmp + up(std::max(tmp_select, tmp_sum)) + 256;
+    if (need > ctx->track_scratch_cap) {
+        SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_track_scratch);
+        ctx->d_track_scratch = nullptr;
+        ctx->track_scratch_cap = 0;
+        if (cudaMalloc(&ctx->d_track_scratch, need) != cudaSuccess) return sd_fail(ctx, SD_ERR_NOMEM, "sd_track_runs: out of device memory (%zu bytes)", need);
+        ctx->track_scratch_cap = need;
+    }
+    unsigned char *base = static_cast<unsigned char *>(ctx->d_track_scratch);
+    uint8_t *flags = base + o_flags;
+    uint64_t *d_n = reinterpret_cast<uint64_t *>(base + o_count);
+    uint32_t *sel = reinterpret_cast<uint32_t *>(base + o_sel);
+    void *tmp = base + o_tmp;
+
     track_flags_kernel<<<(track_len + 255u) / 256u, 256, 0, ctx->stream>>>(a, flags);
     ctx->launches++;
-    cub::CountingInputIterator<uint32_t> positions(0);
-    if (d_pos == nullptr || capacity == 0) {   // sizing call: count the change points
-        // flags are bytes: sum them as 64-bit through a transform iterator
-        cub::TransformInputIterator<uint64_t, cub::CastOp<uint64_t>, const uint8_t *> wide(flags, cub::CastOp<uint64_t>());
-        cub::DeviceReduce::Sum(nullptr, tmp_bytes, wide, d_n, (int)track_len, ctx->stream);
-        if (cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)) != cudaSuccess) return done(sd_fail(ctx, SD_ERR_NOMEM, "sd_track_runs: out of device memory"));
-        cub::DeviceReduce::Sum(tmp, tmp_bytes, wide, d_n, (int)track_len, ctx->stream);
-        ctx->launches++;
-        uint64_t n = 0;
-        cudaError_t e = cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) return done(sd_fail(ctx, SD_ERR_CUDA, "sd_track_runs: %s", cudaGetErrorString(e)));
-        *n_runs = n;
-        return done(SD_OK);
+    if (sizing) {
+        wide = cub::TransformInputIterator<uint64_t, cub::CastOp<uint64_t>, const uint8_t *>(flags, cub::CastOp<uint64_t>());
+        cub::DeviceReduce::Sum(tmp, tmp_sum, wide, d_n, (int)track_len, ctx->stream);
+    } else {
+        cub::DeviceSelect::Flagged(tmp, tmp_select, positions, flags, sel, d_n, (int)track_len, ctx->stream);
     }
-    if (!d_val) return done(sd_fail(ctx, SD_ERR_ARG, "sd_track_runs: d_val is null"));
-    if (cudaMalloc(&sel, (size_t)track_len * sizeof(uint32_t)) != cudaSuccess) return done(sd_fail(ctx, SD_ERR_NOMEM, "sd_track_runs: out of device memory"));
-    cub::DeviceSelect::Flagged(nullptr, tmp_bytes, positions, flags, sel, d_n, (int)track_len, ctx->stream);
-    if (cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)) != cudaSuccess) return done(sd_fail(ctx, SD_ERR_NOMEM, "sd_track_runs: out of device memory"));
-    cub::DeviceSelect::Flagged(tmp, tmp_bytes, positions, flags, sel, d_n, (int)track_len, ctx->stream);
     ctx->launches++;
     uint64_t n = 0;
     {
         cudaError_t e = cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) return done(sd_fail(ctx, SD_ERR_CUDA, "sd_track_runs: %s", cudaGetErrorString(e)));
+        if (e != cudaSuccess) return sd_fail(ctx, SD_ERR_CUDA, "sd_track_runs: %s", cudaGetErrorString(e));
     }
     *n_runs = n;
-    if (n > capacity) return done(sd_fail(ctx, SD_ERR_LIMIT, "sd_track_runs: %llu change points, room for %llu", (unsigned long long)n, (unsigned long long)capacity));
-    if (n) {
-        cudaError_t e = cudaMemcpyAsync(d_pos, sel, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
-        if (e != cudaSuccess) return done(sd_fail(ctx, SD_ERR_CUDA, "sd_track_runs: %s", cudaGetErrorString(e)));
-        track_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, d_pos, n, d_val, d_isfloat);
-        ctx->launches++;
-    }
-    {
-        cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) return done(sd_fail(ctx, SD_ERR_CUDA, "sd_track_runs: %s", cudaGetErrorString(e)));
-    }
-    return done(SD_OK);
+    if (sizing || n == 0) return SD_OK;
+    if (n > capacity) return sd_fail(ctx, SD_ERR_LIMIT, "sd_track_runs: %llu change points, room for %llu", (unsigned long long)n, (unsigned long long)capacity);
+    SD_CUDA(ctx, cudaMemcpyAsync(d_pos, sel, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    track_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, d_pos, n, d_val, d_isfloat);
+    ctx->launches++;
+    SD_CUDA(ctx, cudaGetLastError());
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
 }
