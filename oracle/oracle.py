@@ -88,6 +88,8 @@ def lib():
         L.orc_positional_chrom.argtypes = [ctypes.POINTER(_CountArgs), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_positional_chrom.restype = ctypes.c_int
+        L.orc_read_tc.argtypes = [ctypes.POINTER(_CountArgs), ctypes.c_int64, ctypes.c_void_p]
+        L.orc_read_tc.restype = ctypes.c_int
         L.orc_filter_default.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_filter_multimap.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32,
@@ -478,6 +480,60 @@ def positional_files(ref, snps_file, bam, min_qual, prefix, conv_threshold, cove
         for fh in files:
             fh.close()
         free_snps(snp_handle)
+
+
+def read_separation(ref, snps_file, bam, min_qual, conv_threshold):
+    """Restatement of tcounter.genomewideReadSeparation (dunks/tcounter.py:488-527) up to the two record lists:
+    -> (records, tc_indices, background_indices) with indices into `records` (file order), as `samFile.fetch()` yields
+    them (placed records only)."""
+    from slamdunk_b200.io import bam as bamio
+    _text, bam_refs, records = bamio.read_bam(bam)
+    fasta = bamio.read_fasta(ref)
+    genome = Genome(list(fasta.keys()), [s.encode("ascii") for s in fasta.values()])
+    msgs = []
+    snp_handle = make_snps(read_vcf_records(snps_file, msgs))
+    bam_names = [n for n, _l in bam_refs]
+    idx = [i for i, r in enumerate(records) if r.ref_id >= 0 and r.reference_end is not None]
+    reads = np.zeros(len(idx), dtype=READ_DT)
+    quals, mps = [], []
+    qoff = moff = 0
+    for k, i in enumerate(idx):
+        r = records[i]
+        rec = reads[k]
+        rec["chrom"] = genome.index.get(bam_names[r.ref_id], -1)
+        rec["pos"], rec["end"] = r.pos, r.reference_end
+        q = bytes(r.qual) if r.qual is not None else b""
+        rec["l_qual"], rec["flag"], rec["mapq"], rec["qual_off"] = len(q), r.flag, r.mapq, qoff
+        quals.append(q)
+        qoff += len(q)
+        if r.has_tag("MP"):
+            mp = r.get_tag("MP").encode("ascii")
+            rec["has_mp"], rec["mp_off"], rec["mp_len"] = 1, moff, len(mp)
+            mps.append(mp)
+            moff += len(mp)
+    n_chrom = len(genome.names)
+    qual_pool = np.frombuffer(b"".join(quals), dtype=np.uint8)
+    mp_buf = ctypes.create_string_buffer(b"".join(mps), moff + 1)
+    names = (ctypes.c_char_p * n_chrom)(*[n.encode() for n in genome.names])
+    seqs = (ctypes.c_char_p * n_chrom)(*genome.seqs)
+    a = _CountArgs()
+    a.n_chrom, a.chrom_names, a.chrom_seq, a.chrom_len = n_chrom, names, seqs, genome.lengths.ctypes.data
+    a.reads = reads.ctypes.data
+    a.qual_pool = qual_pool.ctypes.data if len(qual_pool) else None
+    a.mp_text, a.mp_triples = ctypes.cast(mp_buf, ctypes.c_void_p), None
+    a.min_qual, a.conversion_threshold, a.snps = int(min_qual), int(conv_threshold), snp_handle
+    tc = np.zeros(max(1, len(idx)), dtype=np.int32)
+    try:
+        if lib().orc_read_tc(ctypes.byref(a), len(idx), tc.ctypes.data) != 0:
+            raise RuntimeError("orc_read_tc failed")
+    finally:
+        free_snps(snp_handle)
+    tc_names = set()                                                      # tcReadDict, tcounter.py:508-516
+    for k, i in enumerate(idx):
+        if tc[k] >= 0 and tc[k] >= conv_threshold:                        # isTcRead, SlamSeqFile.py:397-400
+            tc_names.add(records[i].qname)
+    placed = [i for i, r in enumerate(records) if r.ref_id >= 0]          # samFile.fetch(), tcounter.py:518
+    return records, [i for i in placed if records[i].qname in tc_names], [i for i in placed if records[i].qname not in tc_names]
 
 
 # --------------------------------------------------------------------------

@@ -340,6 +340,37 @@ int orc_positional_chrom(const orc_count_args_t *a, int32_t chrom, int32_t in_ba
     return 0;
 }
 
+/* tcCount of every read as the iterator of readsInChromosome computes it (fillMismatchesNGM, SlamSeqFile.py:313-348;
+ * used by genomewideReadSeparation, tcounter.py:510-516, through read.isTcRead = tcCount >= conversionThreshold).
+ * out[i] for a->reads[i]; reads whose chromosome is not in the FASTA (chrom < 0) are never seen: out = -1. */
+int orc_read_tc(const orc_count_args_t *a, int64_t n_reads, int32_t *out) {
+    mp_entry_t ents[4096];
+    for (int64_t i = 0; i < n_reads; i++) {
+        const orc_read_t *r = &a->reads[i];
+        if (r->chrom < 0 || r->chrom >= a->n_chrom) { out[i] = -1; continue; }
+        const char *cname = a->chrom_names[r->chrom];
+        const int is_rev = (r->flag & 0x10) != 0;
+        int tcCount = 0;
+        if (r->has_mp) {
+            int n_ent = mp_parse(a->mp_text + r->mp_off, r->mp_len, ents, 4096);
+            if (n_ent > 4096) n_ent = 4096;
+            for (int k = 0; k < n_ent; k++) {
+                int readPos = ents[k].read_pos - 1;
+                int readQlty = (readPos >= r->l_qual) ? 0 : a->qual_pool[r->qual_off + readPos];
+                if (readQlty >= a->min_qual) {
+                    int refPos = ents[k].ref_pos - 1;
+                    int isSnp;
+                    if (is_rev) isSnp = a->snps && snp_query(&((orc_snps_t *)a->snps)->ag, cname, (int64_t)r->pos + refPos);
+                    else        isSnp = a->snps && snp_query(&((orc_snps_t *)a->snps)->tc, cname, (int64_t)r->pos + refPos);
+                    if ((is_rev ? ents[k].conv == 2 : ents[k].conv == 16) && !isSnp) tcCount++;
+                }
+            }
+        }
+        out[i] = tcCount;
+    }
+    return 0;
+}
+
 /* computeTconversions, tcounter.py:165-326, without the text formatting.
  * rows[n_utr]; bedgraph entries returned through *bg (malloc'd, free with orc_free) in the
  * dict's iteration order (first insertion keeps the slot, later assignments overwrite the value). */

@@ -281,14 +281,8 @@ def genomewideConversionRates(referenceFile, snpsFile, bam, minBaseQual, outputB
             print("track type=bedGraph name=\"" + bedGraphInfo + name + "\" description=\"" + desc + "\"", file=fh)
 
     # rows 2c (+) and 2c + 1 (-) for FASTA chromosome c: [1, chrLen + 1) clipped to the chromosome by sd_set_utrs
-    n_chrom = len(genome.names)
-    bam_names = set(hbatch.ref_names)
-    chrom_idx = np.repeat(np.arange(n_chrom, dtype=np.uint32), 2)
+    chrom_idx, start, stop, strand, in_bam = _chromosome_rows(genome, hbatch)
     lengths = np.asarray(genome.chrom_len, dtype=np.int64)
-    start = np.ones(2 * n_chrom, dtype=np.int64)
-    stop = np.repeat(lengths + 1, 2)
-    strand = np.tile(np.array([0, 1], dtype=np.uint8), n_chrom)
-    in_bam = np.repeat(np.array([1 if nm in bam_names else 0 for nm in genome.names], dtype=np.uint8), 2)
     tm["host_prepare_s"] = time.time() - t0 - tm["fasta_decode_s"] - tm["bam_inflate_s"] - tm["bam_decode_s"]
 
     t1 = time.time()
@@ -336,3 +330,89 @@ def genomewideConversionRates(referenceFile, snpsFile, bam, minBaseQual, outputB
     tm["total_s"] = time.time() - t0
     OPTIONS["timings"] = tm
     hbatch.close()
+
+
+def _chromosome_rows(genome, hbatch):
+    """Annotation rows 2c (+) and 2c + 1 (-) for FASTA chromosome c, [1, chrLen + 1) as the reference's whole-chromosome
+    iterator sees it (readsInChromosome, SlamSeqFile.py:447-453)."""
+    n_chrom = len(genome.names)
+    bam_names = set(hbatch.ref_names)
+    lengths = np.asarray(genome.chrom_len, dtype=np.int64)
+    return (np.repeat(np.arange(n_chrom, dtype=np.uint32), 2), np.ones(2 * n_chrom, dtype=np.int64), np.repeat(lengths + 1, 2),
+            np.tile(np.array([0, 1], dtype=np.uint8), n_chrom),
+            np.repeat(np.array([1 if nm in bam_names else 0 for nm in genome.names], dtype=np.uint8), 2))
+
+
+def genomewideReadSeparation(referenceFile, snpsFile, bam, minBaseQual, outputBAMPrefix, conversionThreshold, log):
+    """Drop-in for the reference's tcounter.genomewideReadSeparation (dunks/tcounter.py:488-527, behind
+    `alleyoop read-separator`): <prefix>_TCReads.bam holds every placed record whose query NAME belongs to a read with at
+    least conversionThreshold T>C conversions in one of its alignments, <prefix>_backgroundReads.bam the other placed
+    records; input order and header are kept.
+
+    Device: the per-read conversion count of the count kernel (sd_count_reads).  Host: decode, the name set (64-bit name
+    hashes from the decoder) and the two BAMs (sd_rewrite_bam).  No BAI is written (pysamIndex, tcounter.py:526-527)."""
+    import ctypes
+
+    import torch
+    from ..engine import DeviceBatch
+    tm = CountTimings()
+    t0 = time.time()
+    genome, cached = _genome(referenceFile)
+    mode = {"cigar": L.SD_MISMATCH_CIGAR, "mp": L.SD_MISMATCH_MP, "verify": L.SD_MISMATCH_VERIFY}[OPTIONS["mismatch_source"]]
+    hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True)
+    tm["bam_inflate_s"], tm["bam_decode_s"], tm["bam_reads"] = hbatch.seconds_inflate, hbatch.seconds_decode, hbatch.n_reads
+    tc_mask, ag_mask = build_snp_masks(snpsFile, genome.names, genome.chrom_off, genome.chrom_len, genome.n_words, warn=print)
+    n = hbatch.n_reads
+    t1 = time.time()
+    eng = CountEngine(OPTIONS["device"])
+    try:
+        eng.set_reference(genome.lo, genome.hi, genome.nmask, genome.chrom_off, genome.chrom_len)
+        if tc_mask is not None:
+            eng.set_snps(tc_mask, ag_mask)
+        eng.set_utrs(*_chromosome_rows(genome, hbatch))
+        db = DeviceBatch.from_host(hbatch.batch, eng.device)
+        with torch.cuda.stream(eng.stream):
+            read_tc = torch.zeros(max(1, hbatch.batch.n_tiles * 32), dtype=torch.uint8, device=eng.device)
+        eng.synchronize()
+        # the threshold is applied here on the raw count (the kernel zeroes counts below its threshold, and 0 >= 0 must
+        # still make a TC read for conversionThreshold 0): ask the kernel for every conversion
+        params = make_params(min_qual=minBaseQual, conversion_threshold=0, mismatch_source=mode)
+        eng.count(db, params, read_tc)
+        stats = eng.stats.cpu().numpy()
+        if mode == L.SD_MISMATCH_VERIFY and stats[L.SD_S_MP_DISAGREE] > 0:
+            print("Warning: %d reads carry MP tags that disagree with a CIGAR walk against %s; taking the conversions from the MP tags as slamdunk does."
+                  % (int(stats[L.SD_S_MP_DISAGREE]), os.path.basename(referenceFile)), file=log)
+            eng.reset_outputs()
+            eng.count(db, make_params(min_qual=minBaseQual, conversion_threshold=0, mismatch_source=L.SD_MISMATCH_MP), read_tc)
+        eng.synchronize()
+        tc_slot = read_tc.cpu().numpy()[:n].astype(np.int64)
+        tm["gpu_s"] = time.time() - t1
+    finally:
+        eng.close()
+    rec = hbatch.rec_array()[:n]
+    flags = rec[:, 1] >> 24
+    seen = ((rec[:, 1] & 0xFFFF) != L.SD_REF_NONE) & ((flags & (L.SD_F_PAD | L.SD_F_UNMAPPED)) == 0)   # chromosome in the FASTA
+    placed_slot = rec[:, 0].view(np.int32) >= 0                                  # samFile.fetch(): records with a position
+    is_tc_slot = seen & (tc_slot >= int(conversionThreshold))                    # isTcRead, SlamSeqFile.py:397-400
+    order = hbatch.order().astype(np.int64)                                      # slot -> record index in the file
+    name_hash = hbatch.name_hash()                                               # file order
+    tc_names = np.unique(name_hash[order[is_tc_slot]])                           # tcReadDict, tcounter.py:508-516
+    placed = np.zeros(n, dtype=bool)
+    placed[order] = placed_slot
+    in_tc = np.isin(name_hash, tc_names)
+    text = hbatch.header_text
+    hbatch.close()
+    lib = L.load()
+    err = ctypes.create_string_buffer(512)
+    written = {}
+    for suffix, keep in (("_backgroundReads.bam", placed & ~in_tc), ("_TCReads.bam", placed & in_tc)):
+        k8 = np.ascontiguousarray(keep, dtype=np.uint8)
+        nw = ctypes.c_uint64(0)
+        rc = lib.sd_rewrite_bam(os.fsencode(bam), os.fsencode(outputBAMPrefix + suffix), text.encode(), k8.ctypes.data, None, n, 0, 6,
+                                OPTIONS["threads"], ctypes.byref(nw), err, len(err))
+        if rc != L.SD_OK:
+            raise IOError("sd_rewrite_bam: " + err.value.decode("utf-8", "replace"))
+        written[suffix] = int(nw.value)
+    tm["written"] = written
+    tm["total_s"] = time.time() - t0
+    OPTIONS["timings"] = tm

@@ -15,6 +15,8 @@ filt_* mapper-order BAMs through the reference's filter.Filter (default and mult
        retention modes); expected = DS counters + the written records.
 case_*/positional   the same inputs through tcounter.genomewideConversionRates (alleyoop positional-tracks):
        the eight run-length bedGraphs (python tests/golden/make_golden.py positional regenerates only these).
+case_*/readsep      tcounter.genomewideReadSeparation (alleyoop read-separator) on the case's BAM plus same-name
+       secondary copies; expected = the records of the two BAMs it writes (`... make_golden.py readsep`).
 """
 import hashlib
 import json
@@ -164,12 +166,52 @@ def make_positional(name, min_qual, conv_threshold, cutoff):
     print(name, "positional lines", sum(sum(1 for _ in open(os.path.join(out, f))) for f in os.listdir(out) if f.endswith(".bedGraph")))
 
 
+# case -> (min_qual, conversion threshold) of the read-separator run; the input is the count case's BAM plus secondary
+# copies of every 9th record under the same query name (the separation is by NAME, tcounter.py:508-522)
+READSEP = {"case_a": (27, 1), "case_b": (20, 2), "case_e": (0, 0)}
+
+
+def make_readsep(name, min_qual, conv_threshold):
+    d = os.path.join(HERE, name)
+    out = os.path.join(d, "readsep")
+    if os.path.isdir(out):
+        shutil.rmtree(out)
+    os.makedirs(out)
+    text, refs, recs = bamio.read_bam(os.path.join(d, name + ".bam"))
+    extra = []
+    for i, r in enumerate(recs):
+        if i % 9 == 4:
+            c = r.copy()
+            c.flag |= 0x100
+            c.pos = max(0, min(refs[c.ref_id][1] - 400, c.pos + 57))
+            c.tags = [t for t in c.tags if t[0] != "MP"]
+            extra.append(c)
+    bam = os.path.join(out, name + "_multi.bam")
+    bamio.write_bam(bam, text, refs, bamio.sort_records(recs + extra))
+    vcf = os.path.join(d, name + ".vcf")
+    refrun.run_read_separator(os.path.join(d, name + ".fa"), vcf if os.path.exists(vcf) else None, bam, os.path.join(out, "x"),
+                              min_qual, conv_threshold)
+    exp = {"min_qual": min_qual, "conv_threshold": conv_threshold}
+    for key, f in (("tc", "x_TCReads.bam"), ("background", "x_backgroundReads.bam")):
+        t2, _r, rr = bamio.read_bam(os.path.join(out, f))
+        assert t2 == text
+        exp[key] = [[r.qname, r.flag, r.ref_id, r.pos] for r in rr]
+        os.remove(os.path.join(out, f))
+    with open(os.path.join(out, "expected.json"), "w") as fh:
+        json.dump(exp, fh, indent=0)
+    print(name, "readsep tc", len(exp["tc"]), "background", len(exp["background"]))
+
+
 def main():
     if not refrun.available():
         sys.exit("reference tree not found; goldens can only be regenerated in the build container")
     if sys.argv[1:] == ["positional"]:
         for name, args in POSITIONAL.items():
             make_positional(name, *args)
+        return
+    if sys.argv[1:] == ["readsep"]:
+        for name, args in READSEP.items():
+            make_readsep(name, *args)
         return
     make_cfg1(os.path.join(HERE, "cfg1"))
     for name, (mk, ck) in CASES.items():
@@ -178,6 +220,8 @@ def main():
         make_filter_case(name, mk, fk)
     for name, args in POSITIONAL.items():
         make_positional(name, *args)
+    for name, args in READSEP.items():
+        make_readsep(name, *args)
 
 
 if __name__ == "__main__":

@@ -60,3 +60,17 @@ class PositionalCase:
 
 
 POSITIONAL_CASES = ["case_a", "case_b", "case_d", "case_e"]
+
+
+class ReadSepCase:
+    """alleyoop read-separator on a count case's BAM with extra same-name secondary alignments (tests/golden/<case>/readsep)."""
+    def __init__(self, name):
+        c = CountCase(name)
+        self.name, self.ref, self.vcf = name, c.ref, c.vcf
+        self.dir = os.path.join(c.dir, "readsep")
+        self.bam = os.path.join(self.dir, name + "_multi.bam")
+        self.expected = json.load(open(os.path.join(self.dir, "expected.json")))
+        self.min_qual, self.conv_threshold = self.expected["min_qual"], self.expected["conv_threshold"]
+
+
+READSEP_CASES = ["case_a", "case_b", "case_e"]

@@ -76,3 +76,12 @@ def run_positional(ref, vcf, bam, out_prefix, min_qual=27, conv_threshold=1, cov
     with contextlib.redirect_stdout(out):
         tcounter.genomewideConversionRates(ref, vcf, bam, min_qual, out_prefix, conv_threshold, coverage_cutoff, log)
     return out.getvalue(), log.getvalue()
+
+
+def run_read_separator(ref, vcf, bam, out_prefix, min_qual=27, conv_threshold=1):
+    """reference tcounter.genomewideReadSeparation (alleyoop read-separator): writes <prefix>_TCReads.bam and
+    <prefix>_backgroundReads.bam."""
+    tcounter, _ = reference_modules()
+    log = io.StringIO()
+    tcounter.genomewideReadSeparation(ref, vcf, bam, min_qual, out_prefix, conv_threshold, log)
+    return log.getvalue()

@@ -57,3 +57,58 @@ def test_alleyoop_cli_writes_the_reference_file_names(tmp_path):
     assert made == sorted(["case_a_positional_rates" + s for s, _n, _d in oracle.TRACKS] + ["case_a_positional_rates.log"])
     got = open(str(out / ("case_a_positional_rates" + oracle.TRACKS[2][0]))).read().split("\n", 1)[1]
     assert got == open(c.expected(oracle.TRACKS[2][0])).read().split("\n", 1)[1]
+
+
+def _rec_key(r):
+    return [r.qname, r.flag, r.ref_id, r.pos]
+
+
+def _full(r):
+    return (r.qname, r.flag, r.ref_id, r.pos, r.mapq, tuple(r.cigar), r.seq, None if r.qual is None else tuple(r.qual),
+            tuple((t, ty, tuple(v) if isinstance(v, list) else v) for t, ty, v in r.tags))
+
+
+@pytest.mark.parametrize("mode", ["verify", "mp"])
+@pytest.mark.parametrize("name", goldens.READSEP_CASES)
+def test_read_separator_matches_reference_golden(name, mode, tmp_path):
+    """alleyoop read-separator (tcounter.genomewideReadSeparation): separation is by query NAME, input order kept."""
+    from slamdunk_b200.dunks import tcounter
+    from slamdunk_b200.io import bam as bamio
+    c = goldens.ReadSepCase(name)
+    prefix = str(tmp_path / "x")
+    tcounter.OPTIONS["mismatch_source"] = mode
+    try:
+        tcounter.genomewideReadSeparation(c.ref, c.vcf, c.bam, c.min_qual, prefix, c.conv_threshold, io.StringIO())
+    finally:
+        tcounter.OPTIONS["mismatch_source"] = "verify"
+    text, refs, src = bamio.read_bam(c.bam)
+    by_key = {}
+    for r in src:
+        by_key.setdefault(tuple(_rec_key(r)), []).append(_full(r))
+    for key, f in (("tc", "x_TCReads.bam"), ("background", "x_backgroundReads.bam")):
+        t2, r2, recs = bamio.read_bam(str(tmp_path / f))
+        assert t2 == text and r2 == refs
+        assert [_rec_key(r) for r in recs] == c.expected[key]
+        for r in recs:                                   # records are copied whole
+            assert _full(r) in by_key[tuple(_rec_key(r))]
+
+
+@pytest.mark.parametrize("seed,q,thr", [(81, 27, 1), (82, 27, 3), (83, 10, 0)])
+def test_read_separator_matches_oracle_on_random_data(seed, q, thr, tmp_path):
+    from slamdunk_b200.dunks import tcounter
+    from slamdunk_b200.io import bam as bamio
+    c = simdata.make_case(str(tmp_path), seed=seed, n_reads=5000, n_utr=30, complexity=1.5, snp_density=0.02, p_conv=0.04,
+                          chroms=(("chr10", 30000), ("chr2", 20000), ("chr1", 9000), ("chrM", 1200)))
+    tcounter.genomewideReadSeparation(c.ref, c.vcf, c.bam, q, str(tmp_path / "g"), thr, io.StringIO())
+    recs, tci, bgi = oracle.read_separation(c.ref, c.vcf, c.bam, q, thr)
+    assert [_rec_key(r) for r in bamio.read_bam(str(tmp_path / "g_TCReads.bam"))[2]] == [_rec_key(recs[i]) for i in tci]
+    assert [_rec_key(r) for r in bamio.read_bam(str(tmp_path / "g_backgroundReads.bam"))[2]] == [_rec_key(recs[i]) for i in bgi]
+    assert len(tci) > 0 and (thr == 0 or len(bgi) > 0)
+
+
+def test_alleyoop_read_separator_cli(tmp_path):
+    from slamdunk_b200 import alleyoop
+    c = goldens.ReadSepCase("case_a")
+    out = tmp_path / "sep"
+    alleyoop.run(["read-separator", "-o", str(out), "-r", c.ref, "-v", c.vcf, c.bam])
+    assert sorted(os.listdir(out)) == ["case_a_multi_TCReads.bam", "case_a_multi_backgroundReads.bam", "case_a_multi_read_separator.log"]

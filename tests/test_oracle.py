@@ -138,3 +138,15 @@ def test_oracle_vs_live_reference_positional(seed, q, thr, cutoff, tmp_path):
     oracle.positional_files(c.ref, c.vcf, c.bam, q, str(tmp_path / "o" / "s_slamdunk_mapped_x"), thr, cutoff, io.StringIO(), out=io.StringIO())
     for suffix, _n, _d in oracle.TRACKS:
         assert open(str(tmp_path / "o" / "s_slamdunk_mapped_x") + suffix).read() == open(str(tmp_path / "r" / "s_slamdunk_mapped_x") + suffix).read(), suffix
+
+
+@pytest.mark.parametrize("name", goldens.READSEP_CASES)
+def test_oracle_read_separation_matches_golden(name):
+    """genomewideReadSeparation (alleyoop read-separator): the oracle's two record lists equal the reference's BAMs."""
+    c = goldens.ReadSepCase(name)
+    recs, tci, bgi = oracle.read_separation(c.ref, c.vcf, c.bam, c.min_qual, c.conv_threshold)
+    key = lambda r: [r.qname, r.flag, r.ref_id, r.pos]   # noqa: E731
+    assert [key(recs[i]) for i in tci] == c.expected["tc"]
+    assert [key(recs[i]) for i in bgi] == c.expected["background"]
+    names = [r.qname for r in recs]
+    assert len(set(names)) < len(names)        # the case really has several alignments per name
