@@ -110,7 +110,8 @@ typedef struct sd_batch {
     uint32_t max_tile_qual;
     uint32_t max_tile_cig;
     uint32_t max_tile_mp;
-    uint32_t reserved;
+    uint32_t max_span;      /* largest reference span (M/D/N/=/X) among alignments with span <= l_seq + 64 (spliced
+                               alignments are left out: they take the per-base path anyway); 0 = not known */
 } sd_batch;
 
 /* Where the per-read mismatch list comes from. */

@@ -43,7 +43,7 @@ class Batch(ctypes.Structure):
                 ("rec", ctypes.c_void_p), ("seq", ctypes.c_void_p), ("qual", ctypes.c_void_p),
                 ("cigar", ctypes.c_void_p), ("mp", ctypes.c_void_p), ("tiles", ctypes.c_void_p),
                 ("max_lseq", ctypes.c_uint32), ("max_tile_seq", ctypes.c_uint32), ("max_tile_qual", ctypes.c_uint32),
-                ("max_tile_cig", ctypes.c_uint32), ("max_tile_mp", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("max_tile_cig", ctypes.c_uint32), ("max_tile_mp", ctypes.c_uint32), ("max_span", ctypes.c_uint32)]
 
 
 class Params(ctypes.Structure):

@@ -685,7 +685,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #define SD_CTA_THREADS 256
 #endif
 #ifndef SD_MIN_CTAS
-#define SD_MIN_CTAS(W) ((W) == 4 ? 4 : ((W) == 8 ? 3 : 1))   // resident 256-thread CTAs per SM the register budget is tuned for
+#define SD_MIN_CTAS(W) ((W) <= 6 ? 4 : ((W) <= 10 ? 3 : 2))   // resident 256-thread CTAs per SM the register budget is tuned for
 #endif
 
 template <int W>
@@ -1358,8 +1358,16 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     }
     A.force_slow = p->force_slow_path;
     A.mp_any_base = (p->flags & SD_PARAM_MP_ANY_BASE) ? 1 : 0;
-    if (b->max_lseq <= 128) return launch_count<4>(ctx, A, stream, timed);
-    if (b->max_lseq <= 256) return launch_count<8>(ctx, A, stream, timed);
+    // Window of W 32-base words: it must hold the alignment's reference span, i.e. the read plus its deletions -- a read
+    // that does not fit takes the per-base path, two orders of magnitude slower, and stalls its whole warp (190 bp reads
+    // with 2 % short indels in a 192-base window: 9.6 instead of 15 G reads/s).  The batch says how wide its alignments
+    // are (spliced ones aside); without that, 16 bases of slack cover the usual gaps.
+    const uint32_t need = b->max_span ? std::max(b->max_lseq, b->max_span) : b->max_lseq + 16u;
+    if (need <= 128) return launch_count<4>(ctx, A, stream, timed);
+    if (need <= 192) return launch_count<6>(ctx, A, stream, timed);
+    if (need <= 256) return launch_count<8>(ctx, A, stream, timed);
+    if (need <= 320) return launch_count<10>(ctx, A, stream, timed);
+    if (need <= 384) return launch_count<12>(ctx, A, stream, timed);
     return launch_count<16>(ctx, A, stream, timed);
 }
 

@@ -487,6 +487,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     if (!rec || !name_hash || !tiles) return bail(SD_ERR_NOMEM, "out of host memory");
     std::vector<const char *> mp_ptr(n, nullptr);
     std::atomic<int> fmt_err(0), limit_err(0);
+    std::atomic<uint32_t> max_span(0);
 
     lap("alloc");
     // ---- pass A: fixed-size fields, tags, sizes
@@ -535,6 +536,17 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
                 { fmt_err = 1; return; }
             if (!range_ok || nmp > 65535) { limit_err = 1; return; }
             mp_ptr[i] = a.mp;
+        }
+        if (!(f & (SD_F_UNMAPPED | SD_F_SKIP))) {   // reference span of the alignment: sizes the count kernel's register window
+            uint32_t span = 0;
+            for (uint32_t k = 0; k < n_cig; k++) {
+                const uint32_t c = rd32(cig + 4 * (size_t)k);
+                if ((0x18Du >> (c & 15u)) & 1u) span += c >> 4;
+            }
+            if (span <= (uint32_t)l_seq + 64u) {
+                uint32_t cur = max_span.load(std::memory_order_relaxed);
+                while (span > cur && !max_span.compare_exchange_weak(cur, span, std::memory_order_relaxed)) {}
+            }
         }
         sd_read_rec &o = rec[i];
         o.pos = pos;
@@ -702,6 +714,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     hb->batch.max_tile_qual = mt_qual;
     hb->batch.max_tile_cig = mt_cig;
     hb->batch.max_tile_mp = mt_mp;
+    hb->batch.max_span = max_span.load();
     hb->name_hash = name_hash;
     hb->order = order;
     hb->seconds_inflate = t1 - t0;

@@ -381,3 +381,17 @@ def test_native_bam_writer_replaces_existing_rd_tag_and_handles_empty(tmp_path):
     assert lib.sd_rewrite_bam(src.encode(), out.encode(), b"@HD\tVN:1.0\n", keep.ctypes.data, None, 2, 1, 6, 2,
                               ctypes.byref(nw), err, len(err)) == 0, err.value
     assert nw.value == 0 and bamio.read_bam(out)[2] == []
+
+
+def test_decoder_reports_the_widest_unspliced_alignment(tmp_path):
+    """sd_batch.max_span sizes the count kernel's register window: the largest reference span, spliced alignments aside."""
+    recs = [bamio.BamRecord("a", 0, 0, 10, 60, "50M", "A" * 50, [30] * 50, [("XI", "f", 1.0)]),
+            bamio.BamRecord("b", 0, 0, 20, 60, "20M7D30M", "C" * 50, [30] * 50, [("XI", "f", 1.0)]),        # span 57
+            bamio.BamRecord("c", 0, 0, 30, 60, "5S40M5I", "G" * 50, [30] * 50, [("XI", "f", 1.0)]),          # span 40
+            bamio.BamRecord("d", 0, 0, 40, 60, "25M900N25M", "T" * 50, [30] * 50, [("XI", "f", 1.0)]),       # spliced: left out
+            bamio.BamRecord("e", 4, -1, -1, 0, "", "T" * 80, [30] * 80, [])]
+    p = str(tmp_path / "s.bam")
+    bamio.write_bam(p, "@HD\tVN:1.0\n", [("chr1", 5000)], recs)
+    hb = _decode(p, ["chr1"], want_mp=False)
+    assert hb.batch.max_lseq == 80 and hb.batch.max_span == 57
+    hb.close()
