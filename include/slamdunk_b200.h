@@ -41,7 +41,7 @@ extern "C" {
 #define SD_ERR_LIMIT (-6)
 #define SD_ERR_NOMEM (-7)
 
-#define SD_ABI_VERSION 1
+#define SD_ABI_VERSION 2
 
 typedef struct sd_ctx sd_ctx;
 

@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SLAMDUNK_B200_LIB") or os.path.join(HERE, "libslamdunk_b200.so")   # env: kernel experiments
 
 SD_OK = 0
+SD_ABI_VERSION = 2   # include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span
 SD_F_REVERSE, SD_F_UNMAPPED, SD_F_SECONDARY, SD_F_SUPPLEMENTARY = 0x01, 0x02, 0x04, 0x08
 SD_F_HAS_MP, SD_F_SKIP, SD_F_NEWNAME, SD_F_PAD = 0x10, 0x20, 0x40, 0x80
 SD_REF_NONE = 0xFFFF
@@ -153,6 +154,9 @@ def load():
         raise RuntimeError("libslamdunk_b200.so is stale, it lacks %s; rebuild with `python -m slamdunk_b200.build`"
                            % ", ".join(missing))
     assert ctypes.sizeof(ReadRec) == 20 and ctypes.sizeof(Tile) == 32
+    if L.sd_abi_version() != SD_ABI_VERSION:
+        raise RuntimeError("libslamdunk_b200.so has ABI version %d, these bindings expect %d; rebuild with `python -m slamdunk_b200.build`"
+                           % (L.sd_abi_version(), SD_ABI_VERSION))
     _lib = L
     return L
 
