@@ -27,6 +27,14 @@
 
 #include "sd_internal.h"
 
+// -DSD_DEBUG_BOUNDS: device-side asserts on every scatter / gather index (compute-sanitizer stand-in for the test suite)
+#ifdef SD_DEBUG_BOUNDS
+#include <assert.h>
+#define SD_CHECK(cond) assert(cond)
+#else
+#define SD_CHECK(cond) ((void)0)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // small PTX wrappers (mbarrier + 1-D bulk async copy; SASS: SYNCS.*, UBLKCP)
 // ------------------------------------------------------------------------------------------
@@ -118,6 +126,9 @@ struct CountArgs {
     float filter_min_identity;   // smallest float >= the double threshold: xi < this  <=>  (double)xi < threshold
     int force_slow;
     int mp_any_base;   // SD_PARAM_MP_ANY_BASE
+    // bounds (checked in SD_DEBUG_BOUNDS builds only)
+    unsigned long long n_positions, qual_bytes;
+    uint32_t n_utr;
 };
 
 __device__ __forceinline__ bool cigar_consumes_ref(uint32_t op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
@@ -168,6 +179,7 @@ __device__ __forceinline__ void utr_accumulate(unsigned long long *counters, uin
 
 // one base quality, fetched where a candidate survived (the tile's qualities were pulled into L2 when the tile was issued)
 __device__ __forceinline__ int ld_qual(const uint8_t *p) { return (int)__ldg(p); }
+#define SD_CHECK_QUAL(A, p) SD_CHECK((unsigned long long)((p) - (A).qual) < (A).qual_bytes)
 
 // @region sliced_is_base
 // Read mask of one 32-base group of the plane-sliced SEQ column (four words: bit-planes A, C, G, T of the BAM nibble):
@@ -304,13 +316,17 @@ __device__ __noinline__ int slow_read(const CountArgs &A, const ReadView v, uint
                 const uint32_t ss = A.seg_start[s][seg], se = A.seg_end[s][seg];
                 const uint64_t off = A.seg_off[s][seg];
                 const uint32_t pa = ss > g ? ss : g, pb = se < e ? se : e;
+                SD_CHECK(pb >= pa && off + (pb - ss) < A.n_positions);
                 atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
                 atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
                 if (tc > 0)
                     slow_for_each_hit(A, v, [&](int o, bool on_t) {
                         const uint32_t gp = g + (uint32_t)o;
                         if ((on_t || (A.mp_any_base && A.mismatch_source == SD_MISMATCH_MP)) && gp >= pa && gp < pb)
+                            {
+                            SD_CHECK(off + (gp - ss) < A.n_positions);
                             atomicAdd(&A.pos_tc[off + (gp - ss)], 1);
+                        }
                     });
             }
         }
@@ -542,6 +558,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             if (H[k]) {
                 const int o = 32 * k + (__ffs((int)H[k]) - 1);
                 const int qi = SIMPLE ? o : (regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o));
+                SD_CHECK_QUAL(A, v.qual + (qi < 0 || qi >= (int)v.lseq ? 0 : qi));
                 qv[k] = (qi < 0 || qi >= (int)v.lseq) ? -1 : ld_qual(v.qual + qi);
             }
         }
@@ -602,6 +619,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #pragma unroll
                 for (int k = 0; k < W; k++) conv += __popc(H[k]);
             }
+            SD_CHECK(u.z < A.n_utr);
             utr_accumulate(A.counters, u.z, tc > 0 ? 1u : 0u, mapq == 0 ? 1u : 0u, cov_t, conv);
             if (u.w != last_seg) {
                 last_seg = u.w;
@@ -613,10 +631,12 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                 if (dense_tile) {   // the tile's reads start (and end) at a handful of positions: lanes with the same address elect one to add the count
                     const unsigned act = __activemask();
                     const unsigned long long ia = off + (pa - ss), ib = off + (pb - ss);   // lanes may sit in different segments: match the full index
+                    SD_CHECK(ib >= ia && ib < A.n_positions);
                     const unsigned ga = __match_any_sync(act, ia), gb = __match_any_sync(act, ib);
                     if (lane_id() == (uint32_t)__ffs((int)ga) - 1u) atomicAdd(&A.pos_cov[ia], (int)__popc(ga));
                     if (lane_id() == (uint32_t)__ffs((int)gb) - 1u) atomicAdd(&A.pos_cov[ib], -(int)__popc(gb));
                 } else {
+                    SD_CHECK(pb >= pa && off + (pb - ss) < A.n_positions);
                     atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
                     atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
                 }
@@ -629,7 +649,10 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #pragma unroll
                         for (int k = 0; k < W; k++) {   // first conversion of every word without a loop
                             const uint32_t h = H[k];
-                            if (h) atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                            if (h) {
+                                SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
+                                atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                            }
                             more |= h & (h - 1u);
                         }
                         if (more) {
@@ -637,7 +660,10 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                             for (int k = 0; k < W; k++) {
                                 uint32_t h = H[k] & (H[k] - 1u);
                                 while (h) {
-                                    atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                                    {
+                                SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
+                                atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                            }
                                     h &= h - 1u;
                                 }
                             }
@@ -646,7 +672,10 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                         for (int k = 0; k < W; k++) {
                             uint32_t h = H[k] & prefix_word(k, (int)(pb - g)) & ~prefix_word(k, (int)(pa - g));
                             while (h) {
+                                {
+                                SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
                                 atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                            }
                                 h &= h - 1u;
                             }
                         }
@@ -1358,6 +1387,17 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     }
     A.force_slow = p->force_slow_path;
     A.mp_any_base = (p->flags & SD_PARAM_MP_ANY_BASE) ? 1 : 0;
+    A.n_positions = ctx->n_positions;
+    A.n_utr = ctx->n_utr;
+    A.qual_bytes = 0;   // set below in debug builds
+#ifdef SD_DEBUG_BOUNDS
+    {
+        sd_tile last;
+        SD_CUDA(ctx, cudaDeviceSynchronize());   // the tile table may still be in flight on the copy stream (sd_count_host)
+        SD_CUDA(ctx, cudaMemcpy(&last, b->tiles + b->n_tiles, sizeof last, cudaMemcpyDefault));
+        A.qual_bytes = last.qual_off;
+    }
+#endif
     // Window of W 32-base words: it must hold the alignment's reference span, i.e. the read plus its deletions -- a read
     // that does not fit takes the per-base path, two orders of magnitude slower, and stalls its whole warp (190 bp reads
     // with 2 % short indels in a 192-base window: 9.6 instead of 15 G reads/s).  The batch says how wide its alignments
