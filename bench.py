@@ -241,7 +241,7 @@ def main():
     import torch.distributed as dist
     from slamdunk_b200 import _lib as L
     from slamdunk_b200.engine import make_params
-    from slamdunk_b200.synth import algorithmic_bytes_per_read, batch_to_host
+    from slamdunk_b200.synth import algorithmic_bytes_per_read, batch_to_host, host_batch_bytes
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -307,8 +307,8 @@ def main():
     # end to end: pinned host buffers -> sd_count_host -> counters back on the host
     e2e = None
     if not args.no_e2e:
-        hb, keep = batch_to_host(db)
-        h2d = db.nbytes()
+        hb, keep = batch_to_host(db, eng)     # the host form sd_decode_bam produces: quality codes when the column has <= 16 values
+        h2d = host_batch_bytes(keep)
         d2h = eng.counters.numel() * 8 + eng.stats.numel() * 8
 
         def e2e_step():
@@ -333,7 +333,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": world * n_reads / dt, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt * 1e3, "h2d_gbs": h2d / dt / 1e9}
+               "ms_per_step": dt * 1e3, "h2d_gbs": h2d / dt / 1e9, "host_qual_bits": int(hb.qual_bits)}
         del hb, keep
 
     # CPU baseline + parity of the GPU counters with the oracle on a bounded sample (rank 0, N = 1)

@@ -41,7 +41,7 @@ extern "C" {
 #define SD_ERR_LIMIT (-6)
 #define SD_ERR_NOMEM (-7)
 
-#define SD_ABI_VERSION 2
+#define SD_ABI_VERSION 3
 
 typedef struct sd_ctx sd_ctx;
 
@@ -112,6 +112,13 @@ typedef struct sd_batch {
     uint32_t max_tile_mp;
     uint32_t max_span;      /* largest reference span (M/D/N/=/X) among alignments with span <= l_seq + 64 (spliced
                                alignments are left out: they take the per-base path anyway); 0 = not known */
+    uint32_t qual_bits;     /* bits per base quality in `qual`: 0 or 8 = one byte each (the only form the device entry
+                               points take); 2 or 4 = dictionary codes, four or two per byte starting at the low bits, the
+                               quality at column offset o being code (qual[o * bits / 8] >> (o * bits % 8)) & (2^bits - 1).
+                               HOST batches only: sd_decode_bam codes a file with at most 4 / 16 distinct qualities this
+                               way (Illumina's binned qualities), sd_count_host copies the codes and expands them on the
+                               device -- a quarter of the column's PCIe bytes.  Tile qual offsets are always in bases. */
+    uint8_t qual_dict[16];  /* code -> phred value */
 } sd_batch;
 
 /* Where the per-read mismatch list comes from. */
@@ -251,6 +258,7 @@ int sd_filter(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params, con
  */
 #define SD_DECODE_MP 1
 #define SD_DECODE_GROUP 2
+#define SD_DECODE_RAW_QUAL 4   /* keep one byte per base quality even when the file has <= 16 distinct values */
 
 typedef struct sd_hbatch {
     sd_batch batch;          /* host pointers */
@@ -271,7 +279,9 @@ typedef struct sd_hbatch {
  * the ref field is the BAM reference id itself (what sd_filter works in).
  * options: SD_DECODE_MP also decodes the MP tags into the mp column; SD_DECODE_GROUP orders the batch by
  * alignment shape and strand (plain single-match-block reads first, each group in file order) so that the
- * count kernel's warps are homogeneous -- use file order (no grouping) for sd_filter.  tile_reads: 32 (0 = default).
+ * count kernel's warps are homogeneous -- use file order (no grouping) for sd_filter.  Base qualities are written as
+ * 2- or 4-bit dictionary codes when the file has at most 4 / 16 distinct values (sd_batch.qual_bits) unless
+ * SD_DECODE_RAW_QUAL is given.  tile_reads: 32 (0 = default).
  * threads <= 0: hardware concurrency. */
 int sd_decode_bam(const char *path, const char *const *fasta_names, uint32_t n_fasta, int options,
                   uint32_t tile_reads, int threads, sd_hbatch **out, char *err, int errlen);
@@ -290,6 +300,14 @@ typedef struct sd_hgenome {
 
 int sd_load_fasta(const char *path, int threads, sd_hgenome **out, char *err, int errlen);
 void sd_hgenome_free(sd_hgenome *g);
+
+/* ------------------------------------------------------------------ base-quality transfer coding
+ * sd_qual_unpack: device codes -> device bytes (what sd_count_host does per chunk; also for uploading a host batch by
+ * hand).  sd_qual_pack: the reverse for a device-resident column: *bits receives 2, 4 or 8 (8: more than 16 distinct
+ * values, nothing written), dict the code table.  n_bases = length of the qual column in bases (a multiple of 16);
+ * d_packed needs n_bases * bits / 8 bytes (n_bases / 2 always suffices for a packable column). */
+int sd_qual_unpack(sd_ctx *ctx, const uint8_t *d_packed, uint64_t n_bases, uint32_t bits, const uint8_t *dict16, uint8_t *d_qual);
+int sd_qual_pack(sd_ctx *ctx, const uint8_t *d_qual, uint64_t n_bases, uint8_t *d_packed, uint32_t *bits, uint8_t *dict16);
 
 /* ------------------------------------------------------------------ filtered BAM output (host, C++ threads + zlib)
  * Replaces pysam's outfile.write / dumpBufferToBam and `samtools sort` after the decisions of sd_filter

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SLAMDUNK_B200_LIB") or os.path.join(HERE, "libslamdunk_b200.so")   # env: kernel experiments
 
 SD_OK = 0
-SD_ABI_VERSION = 2   # include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span
+SD_ABI_VERSION = 3   # include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual
 SD_F_REVERSE, SD_F_UNMAPPED, SD_F_SECONDARY, SD_F_SUPPLEMENTARY = 0x01, 0x02, 0x04, 0x08
 SD_F_HAS_MP, SD_F_SKIP, SD_F_NEWNAME, SD_F_PAD = 0x10, 0x20, 0x40, 0x80
 SD_REF_NONE = 0xFFFF
@@ -17,7 +17,7 @@ SD_MISMATCH_CIGAR, SD_MISMATCH_MP, SD_MISMATCH_VERIFY = 0, 1, 2
 SD_PARAM_MP_ANY_BASE = 1
 SD_TRACK_COVERAGE, SD_TRACK_COVERAGE_ON_BASE, SD_TRACK_CONVERSIONS, SD_TRACK_RATE = 0, 1, 2, 3
 SD_NCOUNTER = 5
-SD_DECODE_MP, SD_DECODE_GROUP = 1, 2
+SD_DECODE_MP, SD_DECODE_GROUP, SD_DECODE_RAW_QUAL = 1, 2, 4
 SD_C_READS, SD_C_TCREADS, SD_C_MULTIMAP, SD_C_COV_ON_T, SD_C_CONV_ON_T = range(5)
 SD_NSTAT = 10
 (SD_S_MAPPED, SD_S_UNMAPPED, SD_S_FILTERED, SD_S_MQFILTERED, SD_S_IDFILTERED, SD_S_NMFILTERED,
@@ -44,7 +44,8 @@ class Batch(ctypes.Structure):
                 ("rec", ctypes.c_void_p), ("seq", ctypes.c_void_p), ("qual", ctypes.c_void_p),
                 ("cigar", ctypes.c_void_p), ("mp", ctypes.c_void_p), ("tiles", ctypes.c_void_p),
                 ("max_lseq", ctypes.c_uint32), ("max_tile_seq", ctypes.c_uint32), ("max_tile_qual", ctypes.c_uint32),
-                ("max_tile_cig", ctypes.c_uint32), ("max_tile_mp", ctypes.c_uint32), ("max_span", ctypes.c_uint32)]
+                ("max_tile_cig", ctypes.c_uint32), ("max_tile_mp", ctypes.c_uint32), ("max_span", ctypes.c_uint32), ("qual_bits", ctypes.c_uint32),
+                ("qual_dict", ctypes.c_uint8 * 16)]
 
 
 class Params(ctypes.Structure):
@@ -109,6 +110,8 @@ PROTOTYPES = {
                                  ctypes.c_uint32, _VP, _VP, _VP]),
     "sd_rewrite_bam": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, _VP, _VP, ctypes.c_uint64, ctypes.c_int,
                                       ctypes.c_int, ctypes.c_int, c_u64p, ctypes.c_char_p, ctypes.c_int]),
+    "sd_qual_unpack": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64, ctypes.c_uint32, _VP, _VP]),
+    "sd_qual_pack": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64, _VP, ctypes.POINTER(ctypes.c_uint32), _VP]),
     "sd_decode_bam": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint32, ctypes.c_int,
                                      ctypes.c_uint32, ctypes.c_int, ctypes.POINTER(ctypes.POINTER(HBatch)),
                                      ctypes.c_char_p, ctypes.c_int]),

@@ -1348,6 +1348,8 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     if (b->n_tiles == 0) return SD_OK;
     if (b->tile_reads != 32) return sd_fail(ctx, SD_ERR_ARG, "tile_reads must be 32 (one tile per warp)");
     if (p->mismatch_source != SD_MISMATCH_CIGAR && !b->mp) return sd_fail(ctx, SD_ERR_ARG, "mismatch source needs the mp column");
+    if (b->qual_bits != 0 && b->qual_bits != 8)
+        return sd_fail(ctx, SD_ERR_ARG, "the qual column holds %u-bit codes: expand it with sd_qual_unpack (sd_count_host does)", b->qual_bits);
     CountArgs A;
     memset(&A, 0, sizeof A);
     A.rec = b->rec; A.seq = b->seq; A.qual = b->qual; A.cigar = b->cigar;
@@ -1444,11 +1446,15 @@ extern "C" int sd_count_host(sd_ctx *ctx, const sd_batch *hb, const sd_params *p
     const bool use_mp = params->mismatch_source != SD_MISMATCH_CIGAR;
     if (use_mp && !hb->mp) return sd_fail(ctx, SD_ERR_ARG, "mismatch source needs the mp column");
     const uint64_t target = 256ull << 20;  // bytes per chunk
+    const uint32_t qbits = hb->qual_bits ? hb->qual_bits : 8u;
+    const bool coded = qbits != 8;
+    if (coded && qbits != 2 && qbits != 4) return sd_fail(ctx, SD_ERR_ARG, "quality coding of %u bits is not supported", qbits);
     const sd_tile *T = hb->tiles;
     const uint64_t rec_tile = (uint64_t)hb->tile_reads * sizeof(sd_read_rec);
     auto chunk_bytes = [&](uint32_t t0, uint32_t t1) {
         uint64_t b = (uint64_t)(t1 - t0) * rec_tile + (T[t1].seq_off - T[t0].seq_off) + (T[t1].qual_off - T[t0].qual_off) +
-                     (T[t1].cig_off - T[t0].cig_off) + (uint64_t)(t1 - t0 + 1) * sizeof(sd_tile) + 5 * 256;
+                     (T[t1].cig_off - T[t0].cig_off) + (uint64_t)(t1 - t0 + 1) * sizeof(sd_tile) + 6 * 256;
+        if (coded) b += (T[t1].qual_off - T[t0].qual_off) * qbits / 8;   // the codes as copied, next to the expanded column
         if (use_mp) b += T[t1].mp_off - T[t0].mp_off;
         return b;
     };
@@ -1498,8 +1504,17 @@ extern "C" int sd_count_host(sd_ctx *ctx, const sd_batch *hb, const sd_params *p
         if (b_seq) SD_CUDA(ctx, cudaMemcpyAsync(d + o, (const unsigned char *)hb->seq + T[t0].seq_off, b_seq, cudaMemcpyHostToDevice, ctx->copy_stream));
         o = up256(o + b_seq);
         db.qual = (const uint8_t *)(d + o);
-        if (b_qual) SD_CUDA(ctx, cudaMemcpyAsync(d + o, hb->qual + T[t0].qual_off, b_qual, cudaMemcpyHostToDevice, ctx->copy_stream));
-        o = up256(o + b_qual);
+        db.qual_bits = 8;
+        unsigned char *d_codes = nullptr;
+        if (!coded) {
+            if (b_qual) SD_CUDA(ctx, cudaMemcpyAsync(d + o, hb->qual + T[t0].qual_off, b_qual, cudaMemcpyHostToDevice, ctx->copy_stream));
+            o = up256(o + b_qual);
+        } else {   // copy the dictionary codes; they are expanded into db.qual on the compute stream once the copy has landed
+            o = up256(o + b_qual);
+            d_codes = d + o;
+            if (b_qual) SD_CUDA(ctx, cudaMemcpyAsync(d_codes, hb->qual + T[t0].qual_off * qbits / 8, b_qual * qbits / 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            o = up256(o + b_qual * qbits / 8);
+        }
         db.cigar = (const uint32_t *)(d + o);
         if (b_cig) SD_CUDA(ctx, cudaMemcpyAsync(d + o, (const unsigned char *)hb->cigar + T[t0].cig_off, b_cig, cudaMemcpyHostToDevice, ctx->copy_stream));
         o = up256(o + b_cig);
@@ -1521,7 +1536,10 @@ extern "C" int sd_count_host(sd_ctx *ctx, const sd_batch *hb, const sd_params *p
         SD_CUDA(ctx, cudaMemcpyAsync(d + o, rl.data(), (size_t)(nt + 1) * sizeof(sd_tile), cudaMemcpyHostToDevice, ctx->copy_stream));
         SD_CUDA(ctx, cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
         SD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
-        int rc = count_on_stream(ctx, &db, params, ctx->stream, nullptr, false);
+        int rc = SD_OK;
+        if (coded && b_qual && (rc = sd_qual_unpack_on(ctx, ctx->stream, d_codes, b_qual, qbits, hb->qual_dict, const_cast<uint8_t *>(db.qual))))
+            return rc;
+        rc = count_on_stream(ctx, &db, params, ctx->stream, nullptr, false);
         if (rc) return rc;
         SD_CUDA(ctx, cudaEventRecord(ctx->ev_done[buf], ctx->stream));
     }

@@ -416,6 +416,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     if (!path || !out) return fail(err, errlen, SD_ERR_ARG, "sd_decode_bam: null argument");
     *out = nullptr;
     const bool want_mp = (options & SD_DECODE_MP) != 0, group = (options & SD_DECODE_GROUP) != 0;
+    const bool raw_qual = (options & SD_DECODE_RAW_QUAL) != 0;
     if (tile_reads != 0 && tile_reads != 32) return fail(err, errlen, SD_ERR_ARG, "tile_reads must be 32 (or 0 = default)");
     tile_reads = 32;
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -488,6 +489,8 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     std::vector<const char *> mp_ptr(n, nullptr);
     std::atomic<int> fmt_err(0), limit_err(0);
     std::atomic<uint32_t> max_span(0);
+    std::atomic<uint64_t> qual_seen[4];   // which of the 256 quality values occur (sizes the transfer coding of the column)
+    for (auto &w : qual_seen) w = 0;
 
     lap("alloc");
     // ---- pass A: fixed-size fields, tags, sizes
@@ -547,6 +550,12 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
                 uint32_t cur = max_span.load(std::memory_order_relaxed);
                 while (span > cur && !max_span.compare_exchange_weak(cur, span, std::memory_order_relaxed)) {}
             }
+        }
+        if (!raw_qual && l_seq > 0) {
+            uint64_t seen[4] = {0, 0, 0, 0};
+            for (int32_t k = 0; k < l_seq; k++) seen[qual[k] >> 6] |= 1ull << (qual[k] & 63);
+            for (int w = 0; w < 4; w++)
+                if (seen[w] & ~qual_seen[w].load(std::memory_order_relaxed)) qual_seen[w].fetch_or(seen[w], std::memory_order_relaxed);
         }
         sd_read_rec &o = rec[i];
         o.pos = pos;
@@ -642,7 +651,20 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     }
     const sd_tile tot = tiles[n_tiles];
     uint32_t *seqc = (uint32_t *)own->mem.get(tot.seq_off + 16);
-    uint8_t *qualc = (uint8_t *)own->mem.get(tot.qual_off + 16);
+    // transfer coding of the base qualities: 2- or 4-bit dictionary codes when the file has few distinct values
+    uint32_t qual_bits = 8;
+    uint8_t qual_dict[16] = {0}, qual_code[256] = {0};
+    if (!raw_qual) {
+        int distinct = 0;
+        for (int v = 0; v < 256; v++)
+            if ((qual_seen[v >> 6].load() >> (v & 63)) & 1ull) {
+                if (distinct < 16) { qual_dict[distinct] = (uint8_t)v; qual_code[v] = (uint8_t)distinct; }
+                distinct++;
+            }
+        if (distinct <= 4) qual_bits = 2;
+        else if (distinct <= 16) qual_bits = 4;
+    }
+    uint8_t *qualc = (uint8_t *)own->mem.get(tot.qual_off * qual_bits / 8 + 16);
     uint32_t *cigc = (uint32_t *)own->mem.get(tot.cig_off + 16);
     uint32_t *mpc = want_mp ? (uint32_t *)own->mem.get(tot.mp_off + 16) : nullptr;
     if (!seqc || !qualc || !cigc || (want_mp && !mpc)) return bail(SD_ERR_NOMEM, "out of host memory");
@@ -652,7 +674,8 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     parallel_for(n_tiles, threads, [&](size_t t) {
         uint8_t *ps = (uint8_t *)seqc + tiles[t].seq_off;   // group-major block: slot (g, row) at 16 * (g * tile_reads + row)
         memset(ps, 0, (size_t)(tiles[t + 1].seq_off - tiles[t].seq_off));
-        uint8_t *pq = qualc + tiles[t].qual_off;
+        uint8_t *pq = qualc + tiles[t].qual_off * qual_bits / 8;   // tile offsets are in bases, a multiple of 16: byte aligned at any coding
+        uint64_t qn = 0;                                            // bases of this tile written so far (coded form)
         uint8_t *pc = (uint8_t *)cigc + tiles[t].cig_off;
         uint8_t *pm = mpc ? (uint8_t *)mpc + tiles[t].mp_off : nullptr;
         const size_t e = std::min(n, (t + 1) * (size_t)tile_reads);
@@ -666,8 +689,20 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
             const uint8_t *qual = seq + ((size_t)l_seq + 1) / 2;
             memcpy(pc, cig, 4 * (size_t)n_cig);
             pc += 4 * (size_t)n_cig;
-            memcpy(pq, qual, l_seq);
-            pq += l_seq;
+            if (qual_bits == 8) {
+                memcpy(pq, qual, l_seq);
+                pq += l_seq;
+            } else if (qual_bits == 4) {
+                for (uint32_t j = 0; j < l_seq; j++, qn++) {
+                    if (!(qn & 1)) pq[qn >> 1] = qual_code[qual[j]];
+                    else pq[qn >> 1] |= (uint8_t)(qual_code[qual[j]] << 4);
+                }
+            } else {
+                for (uint32_t j = 0; j < l_seq; j++, qn++) {
+                    if (!(qn & 3)) pq[qn >> 2] = qual_code[qual[j]];
+                    else pq[qn >> 2] |= (uint8_t)(qual_code[qual[j]] << (2 * (qn & 3)));
+                }
+            }
             const uint32_t nbytes = (l_seq + 1) / 2;
             for (uint32_t g = 0; g < (l_seq + 31) / 32; g++) {   // one group = 32 bases = 16 packed bytes -> 4 plane words
                 uint32_t pl[4] = {0, 0, 0, 0};
@@ -693,7 +728,8 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
             }
         }
         // zero the 16-byte tile padding so the columns are deterministic
-        memset(pq, 0, (size_t)((qualc + tiles[t + 1].qual_off) - pq));
+        if (qual_bits != 8) pq += (qn * qual_bits + 7) / 8;
+        memset(pq, 0, (size_t)((qualc + tiles[t + 1].qual_off * qual_bits / 8) - pq));
         memset(pc, 0, (size_t)(((uint8_t *)cigc + tiles[t + 1].cig_off) - pc));
         if (pm) memset(pm, 0, (size_t)(((uint8_t *)mpc + tiles[t + 1].mp_off) - pm));
     });
@@ -715,6 +751,8 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     hb->batch.max_tile_cig = mt_cig;
     hb->batch.max_tile_mp = mt_mp;
     hb->batch.max_span = max_span.load();
+    hb->batch.qual_bits = qual_bits;
+    memcpy(hb->batch.qual_dict, qual_dict, 16);
     hb->name_hash = name_hash;
     hb->order = order;
     hb->seconds_inflate = t1 - t0;

@@ -1,0 +1,134 @@
+// sd_qual.cu -- transfer coding of the base-quality column.
+//
+// The count kernel reads one byte per base quality (and only at candidate positions).  Over PCIe the column is the largest
+// part of a batch, and sequencers emit few distinct values (Illumina bins qualities into 4-8 levels), so a HOST batch may
+// hold 2- or 4-bit dictionary codes instead (sd_batch.qual_bits / qual_dict): sd_count_host copies the codes and expands
+// them on the device, next to the kernel that consumes them.
+#include "sd_internal.h"
+
+namespace {
+
+// one thread per 16 output bytes (4 or 8 bytes of codes)
+__global__ void qual_unpack_kernel(const uint8_t *__restrict__ packed, uint64_t n_bases, uint32_t bits, uint4 dict_words, uint8_t *__restrict__ out) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16ull;
+    if (i >= n_bases) return;
+    const uint32_t dw[4] = {dict_words.x, dict_words.y, dict_words.z, dict_words.w};
+    auto dict = [&](uint32_t code) { return (dw[code >> 2] >> (8u * (code & 3u))) & 0xFFu; };
+    uint32_t o[4] = {0, 0, 0, 0};
+    if (bits == 2) {
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(packed + i / 4);   // 16 codes
+#pragma unroll
+        for (int k = 0; k < 16; k++) o[k >> 2] |= dict((w >> (2 * k)) & 3u) << (8 * (k & 3));
+    } else {
+        const uint2 w = *reinterpret_cast<const uint2 *>(packed + i / 2);
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k >> 2] |= dict((w.x >> (4 * k)) & 15u) << (8 * (k & 3));
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[2 + (k >> 2)] |= dict((w.y >> (4 * k)) & 15u) << (8 * (k & 3));
+    }
+    *reinterpret_cast<uint4 *>(out + i) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void qual_seen_kernel(const uint8_t *__restrict__ q, uint64_t n, unsigned int *seen /*[8] bit per value*/) {
+    __shared__ unsigned int s[8];
+    if (threadIdx.x < 8) s[threadIdx.x] = 0u;
+    __syncthreads();
+    unsigned int mine[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16ull; i < n; i += (uint64_t)gridDim.x * blockDim.x * 16ull) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(q + i);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t v = (ww[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+            mine[v >> 5] |= 1u << (v & 31u);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if (mine[k]) atomicOr(&s[k], mine[k]);
+    __syncthreads();
+    if (threadIdx.x < 8 && s[threadIdx.x]) atomicOr(&seen[threadIdx.x], s[threadIdx.x]);
+}
+
+struct CodeTable { uint8_t code[256]; };
+
+__global__ void qual_pack_kernel(const uint8_t *__restrict__ q, uint64_t n_bases, uint32_t bits, CodeTable t, uint8_t *__restrict__ packed) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16ull;
+    if (i >= n_bases) return;
+    const uint4 w = *reinterpret_cast<const uint4 *>(q + i);
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    if (bits == 2) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) o |= (uint32_t)t.code[(ww[k >> 2] >> (8 * (k & 3))) & 0xFFu] << (2 * k);
+        *reinterpret_cast<uint32_t *>(packed + i / 4) = o;
+    } else {
+        uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o0 |= (uint32_t)t.code[(ww[k >> 2] >> (8 * (k & 3))) & 0xFFu] << (4 * k);
+#pragma unroll
+        for (int k = 0; k < 8; k++) o1 |= (uint32_t)t.code[(ww[2 + (k >> 2)] >> (8 * (k & 3))) & 0xFFu] << (4 * k);
+        *reinterpret_cast<uint2 *>(packed + i / 2) = make_uint2(o0, o1);
+    }
+}
+
+}  // namespace
+
+// internal: used by sd_count_host on its own stream
+int sd_qual_unpack_on(sd_ctx *ctx, cudaStream_t stream, const uint8_t *d_packed, uint64_t n_bases, uint32_t bits, const uint8_t *dict16,
+                      uint8_t *d_qual) {
+    if (bits != 2 && bits != 4) return sd_fail(ctx, SD_ERR_ARG, "quality coding of %u bits is not supported", bits);
+    if (n_bases % 16) return sd_fail(ctx, SD_ERR_ARG, "quality column length must be a multiple of 16");
+    if (n_bases == 0) return SD_OK;
+    uint4 dw;
+    memcpy(&dw, dict16, 16);
+    const uint64_t threads = n_bases / 16;
+    qual_unpack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_packed, n_bases, bits, dw, d_qual);
+    ctx->launches++;
+    SD_CUDA(ctx, cudaGetLastError());
+    return SD_OK;
+}
+
+extern "C" int sd_qual_unpack(sd_ctx *ctx, const uint8_t *d_packed, uint64_t n_bases, uint32_t bits, const uint8_t *dict16, uint8_t *d_qual) {
+    if (!ctx || !d_packed || !dict16 || !d_qual) return sd_fail(ctx, SD_ERR_ARG, "sd_qual_unpack: null argument");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int rc = sd_qual_unpack_on(ctx, ctx->stream, d_packed, n_bases, bits, dict16, d_qual);
+    if (rc != SD_OK) return rc;
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+extern "C" int sd_qual_pack(sd_ctx *ctx, const uint8_t *d_qual, uint64_t n_bases, uint8_t *d_packed, uint32_t *bits, uint8_t *dict16) {
+    if (!ctx || !d_qual || !bits || !dict16) return sd_fail(ctx, SD_ERR_ARG, "sd_qual_pack: null argument");
+    if (n_bases % 16) return sd_fail(ctx, SD_ERR_ARG, "quality column length must be a multiple of 16");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    *bits = 8;
+    memset(dict16, 0, 16);
+    if (n_bases == 0) return SD_OK;
+    unsigned int *d_seen = nullptr, seen[8];
+    SD_CUDA(ctx, cudaMalloc(&d_seen, sizeof seen));
+    cudaMemsetAsync(d_seen, 0, sizeof seen, ctx->stream);
+    qual_seen_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(d_qual, n_bases, d_seen);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(seen, d_seen, sizeof seen, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_seen);
+    if (e != cudaSuccess) return sd_fail(ctx, SD_ERR_CUDA, "sd_qual_pack: %s", cudaGetErrorString(e));
+    CodeTable t;
+    memset(&t, 0, sizeof t);
+    int distinct = 0;
+    for (int v = 0; v < 256; v++)
+        if ((seen[v >> 5] >> (v & 31)) & 1u) {
+            if (distinct < 16) { dict16[distinct] = (uint8_t)v; t.code[v] = (uint8_t)distinct; }
+            distinct++;
+        }
+    if (distinct > 16) return SD_OK;   // not packable: *bits stays 8
+    *bits = distinct <= 4 ? 2u : 4u;
+    if (!d_packed) return sd_fail(ctx, SD_ERR_ARG, "sd_qual_pack: d_packed is null");
+    const uint64_t threads = n_bases / 16;
+    qual_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(d_qual, n_bases, *bits, t, d_packed);
+    ctx->launches++;
+    SD_CUDA(ctx, cudaGetLastError());
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}

@@ -32,7 +32,7 @@ def Filter(inputBAM, outputBAM, log, bed, MQ=2, minIdentity=0.8, NM=-1, printOnl
     hb = HostBatch(inputBAM, [], want_mp=False, threads=OPTIONS["threads"])
     eng = CountEngine(OPTIONS["device"])
     try:
-        db = DeviceBatch.from_host(hb.batch, eng.device)
+        db = DeviceBatch.from_host(hb.batch, eng.device, eng)
         params = make_params(filter_on=True, filter_mq=MQ, filter_min_identity=minIdentity, filter_max_nm=NM)
         if bed is None:
             print("#No bed-file supplied. Running default filtering on " + inputBAM + ".", file=log)

@@ -370,7 +370,7 @@ def genomewideReadSeparation(referenceFile, snpsFile, bam, minBaseQual, outputBA
         if tc_mask is not None:
             eng.set_snps(tc_mask, ag_mask)
         eng.set_utrs(*_chromosome_rows(genome, hbatch))
-        db = DeviceBatch.from_host(hbatch.batch, eng.device)
+        db = DeviceBatch.from_host(hbatch.batch, eng.device, eng)
         with torch.cuda.stream(eng.stream):
             read_tc = torch.zeros(max(1, hbatch.batch.n_tiles * 32), dtype=torch.uint8, device=eng.device)
         eng.synchronize()

@@ -72,13 +72,14 @@ class HostBatch(object):
     """A BAM file decoded into the columnar batch (sd_decode_bam); buffers are page-locked."""
 
     def __init__(self, path: str, fasta_names: Sequence[str], want_mp: bool = True, tile_reads: int = 0,
-                 threads: int = 0, group: bool = False):
+                 threads: int = 0, group: bool = False, raw_qual: bool = False):
         lib = L.load()
         err = ctypes.create_string_buffer(512)
         out = ctypes.POINTER(L.HBatch)()
         names = (ctypes.c_char_p * max(1, len(fasta_names)))(*[n.encode() for n in fasta_names])
         rc = lib.sd_decode_bam(os.fsencode(path), names, len(fasta_names),
-                               (L.SD_DECODE_MP if want_mp else 0) | (L.SD_DECODE_GROUP if group else 0), int(tile_reads),
+                               (L.SD_DECODE_MP if want_mp else 0) | (L.SD_DECODE_GROUP if group else 0) |
+                               (L.SD_DECODE_RAW_QUAL if raw_qual else 0), int(tile_reads),
                                int(threads), ctypes.byref(out), err, len(err))
         if rc != L.SD_OK:
             raise L.NativeError("sd_decode_bam(%s) failed (%d): %s" % (path, rc, err.value.decode("utf-8", "replace")))
@@ -112,6 +113,14 @@ class HostBatch(object):
         if which == "seq":
             n, addr, dt = int(t[0]) // 4, b.seq, ctypes.c_uint32
         elif which == "qual":
+            bits = int(b.qual_bits) or 8
+            if bits != 8:        # dictionary codes -> phred bytes
+                nq = int(t[1])
+                if not nq or not b.qual:
+                    return np.zeros(0, dtype=np.uint8)
+                codes = np.frombuffer((ctypes.c_uint8 * (nq * bits // 8)).from_address(b.qual), dtype=np.uint8)
+                idx = (codes[:, None] >> (np.arange(8 // bits, dtype=np.uint8) * bits)[None, :]) & ((1 << bits) - 1)
+                return np.array(list(b.qual_dict), dtype=np.uint8)[idx.reshape(-1)]
             n, addr, dt = int(t[1]), b.qual, ctypes.c_uint8
         elif which == "cigar":
             n, addr, dt = int(t[2]) // 4, b.cigar, ctypes.c_uint32
@@ -156,7 +165,9 @@ class DeviceBatch(object):
         self.tensors = tensors
 
     @staticmethod
-    def from_host(hb: L.Batch, device: torch.device) -> "DeviceBatch":
+    def from_host(hb: L.Batch, device: torch.device, eng: Optional["CountEngine"] = None) -> "DeviceBatch":
+        """Upload a host batch.  A coded quality column (hb.qual_bits 2 / 4) is expanded to bytes: on the device when an
+        engine is given (sd_qual_unpack), else with numpy before the copy."""
         def up(addr, nbytes):
             if not addr or nbytes == 0:
                 return torch.zeros(16, dtype=torch.uint8, device=device)
@@ -168,16 +179,30 @@ class DeviceBatch(object):
         T = {
             "rec": up(hb.rec, nt * hb.tile_reads * 20),
             "seq": up(hb.seq, int(tot[0])),
-            "qual": up(hb.qual, int(tot[1])),
+            "qual": None,
             "cigar": up(hb.cigar, int(tot[2])),
             "mp": up(hb.mp, int(tot[3])) if hb.mp else None,
             "tiles": up(hb.tiles, (nt + 1) * 32),
         }
+        bits, n_q = int(hb.qual_bits) or 8, int(tot[1])
+        if bits == 8 or n_q == 0:
+            T["qual"] = up(hb.qual, n_q)
+        elif eng is not None:
+            codes = up(hb.qual, n_q * bits // 8)
+            T["qual"] = torch.empty(n_q, dtype=torch.uint8, device=device)
+            dict16 = (ctypes.c_uint8 * 16)(*hb.qual_dict)
+            eng._chk(eng.lib.sd_qual_unpack(eng.ctx, _t_ptr(codes), n_q, bits, dict16, _t_ptr(T["qual"])), "sd_qual_unpack")
+        else:
+            codes = np.frombuffer((ctypes.c_uint8 * (n_q * bits // 8)).from_address(hb.qual), dtype=np.uint8)
+            per = 8 // bits
+            idx = (codes[:, None] >> (np.arange(per, dtype=np.uint8) * bits)[None, :]) & ((1 << bits) - 1)
+            T["qual"] = torch.from_numpy(np.array(list(hb.qual_dict), dtype=np.uint8)[idx.reshape(-1)]).to(device)
         b = L.Batch()
         ctypes.memmove(ctypes.byref(b), ctypes.byref(hb), ctypes.sizeof(L.Batch))
         b.rec, b.seq, b.qual, b.cigar = T["rec"].data_ptr(), T["seq"].data_ptr(), T["qual"].data_ptr(), T["cigar"].data_ptr()
         b.mp = T["mp"].data_ptr() if T["mp"] is not None else None
         b.tiles = T["tiles"].data_ptr()
+        b.qual_bits = 8
         return DeviceBatch(b, T)
 
     def nbytes(self) -> int:

@@ -211,13 +211,26 @@ def algorithmic_bytes_per_read(read_len, mean_cigar_ops):
     return 4 * ((read_len + 7) // 8) + read_len + 4.0 * mean_cigar_ops + 20
 
 
-def batch_to_host(db: DeviceBatch):
-    """Pinned host copy of a device batch -> (L.Batch with host pointers, keep-alive dict)."""
+def batch_to_host(db: DeviceBatch, eng=None):
+    """Pinned host copy of a device batch -> (L.Batch with host pointers, keep-alive dict).  With an engine the quality
+    column is stored the way sd_decode_bam stores it: as dictionary codes when it has at most 16 distinct values."""
     host = {}
+    bits = 8
+    dict16 = (ctypes.c_uint8 * 16)()
     for k, t in db.tensors.items():
         if t is None:
             host[k] = None
             continue
+        if k == "qual" and eng is not None:
+            nt = int(db.batch.n_tiles)
+            n_q = int(db.tensors["tiles"].view(torch.int64)[4 * nt + 1].item()) if nt else 0
+            if n_q:
+                codes = torch.empty(n_q // 2, dtype=torch.uint8, device=t.device)
+                cb = ctypes.c_uint32(8)
+                eng._chk(eng.lib.sd_qual_pack(eng.ctx, t.data_ptr(), n_q, codes.data_ptr(), ctypes.byref(cb), dict16), "sd_qual_pack")
+                bits = int(cb.value)
+                if bits != 8:
+                    t = codes[: n_q * bits // 8]
         h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         h.copy_(t)
         host[k] = h
@@ -226,4 +239,12 @@ def batch_to_host(db: DeviceBatch):
     b.rec, b.seq, b.qual, b.cigar = host["rec"].data_ptr(), host["seq"].data_ptr(), host["qual"].data_ptr(), host["cigar"].data_ptr()
     b.mp = host["mp"].data_ptr() if host["mp"] is not None else None
     b.tiles = host["tiles"].data_ptr()
+    b.qual_bits = bits
+    for i in range(16):
+        b.qual_dict[i] = dict16[i]
     return b, host
+
+
+def host_batch_bytes(host: dict) -> int:
+    """bytes sd_count_host copies to the device for this host batch"""
+    return sum(t.numel() * t.element_size() for t in host.values() if t is not None)

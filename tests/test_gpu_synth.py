@@ -110,12 +110,17 @@ def test_count_host_equals_count_device():
     eng.count(db, params)
     eng.synchronize()
     want = (eng.counters.clone(), eng.pos_cov.clone(), eng.pos_tc.clone(), eng.stats.clone())
-    hb, keep = batch_to_host(db)
-    eng.reset_outputs()
-    eng.count_host(hb, params)
-    got = (eng.counters, eng.pos_cov, eng.pos_tc, eng.stats)
-    for w, g in zip(want, got):
-        assert torch.equal(w, g)
+    for coded in (False, True):       # one byte per quality / the dictionary codes sd_decode_bam writes for binned qualities
+        hb, keep = batch_to_host(db, eng if coded else None)
+        assert hb.qual_bits == (2 if coded else 8)       # the generator draws from three quality values
+        eng.reset_outputs()
+        eng.count_host(hb, params)
+        got = (eng.counters, eng.pos_cov, eng.pos_tc, eng.stats)
+        for w, g in zip(want, got):
+            assert torch.equal(w, g)
+    with pytest.raises(Exception, match="codes"):         # device entry points take bytes only
+        import ctypes
+        eng._chk(eng.lib.sd_count(eng.ctx, ctypes.byref(hb), ctypes.byref(params)), "sd_count")
     eng.close()
 
 

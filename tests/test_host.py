@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "library does not export " + name
     assert declared == set(L.PROTOTYPES.keys())
-    assert lib.sd_abi_version() == L.SD_ABI_VERSION == 2
+    assert lib.sd_abi_version() == L.SD_ABI_VERSION == 3
 
 
 def _decode(path, fasta_names, want_mp=True, tile_reads=32, threads=3):
@@ -395,3 +395,32 @@ def test_decoder_reports_the_widest_unspliced_alignment(tmp_path):
     hb = _decode(p, ["chr1"], want_mp=False)
     assert hb.batch.max_lseq == 80 and hb.batch.max_span == 57
     hb.close()
+
+
+def test_decoder_codes_binned_qualities(tmp_path):
+    """<= 4 distinct quality values -> 2-bit codes, <= 16 -> 4-bit, more -> bytes; column("qual") gives the phred bytes back."""
+    import random
+    rnd = random.Random(5)
+    for levels, bits in (([2, 12, 23, 37], 2), (list(range(10, 40, 3)), 4), (list(range(2, 42)), 8)):
+        recs = []
+        for i in range(150):
+            n = rnd.randint(20, 90)
+            recs.append(bamio.BamRecord("r%d" % i, 0, 0, 10 + 3 * i, 60, "%dM" % n, "".join(rnd.choice("ACGT") for _ in range(n)),
+                                        [rnd.choice(levels) for _ in range(n)], [("XI", "f", 1.0)]))
+        p = str(tmp_path / ("q%d.bam" % bits))
+        bamio.write_bam(p, "@HD\tVN:1.0\n", [("chr1", 5000)], recs)
+        for raw in (False, True):
+            from slamdunk_b200.engine import HostBatch
+            hb = HostBatch(p, ["chr1"], want_mp=False, tile_reads=32, threads=2, raw_qual=raw)
+            assert hb.batch.qual_bits == (8 if raw else bits)
+            qual, tiles = hb.column("qual"), hb.tiles_array()
+            for t in range(hb.batch.n_tiles):
+                qo = int(tiles[t][1])
+                for k in range(32):
+                    i = t * 32 + k
+                    if i >= len(recs):
+                        break
+                    n = len(recs[i].qual)
+                    assert list(qual[qo:qo + n]) == recs[i].qual
+                    qo += n
+            hb.close()
