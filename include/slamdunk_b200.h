@@ -41,7 +41,7 @@ extern "C" {
 #define SD_ERR_LIMIT (-6)
 #define SD_ERR_NOMEM (-7)
 
-#define SD_ABI_VERSION 3
+#define SD_ABI_VERSION 4
 
 typedef struct sd_ctx sd_ctx;
 
@@ -318,6 +318,12 @@ int sd_qual_pack(sd_ctx *ctx, const uint8_t *d_qual, uint64_t n_bases, uint8_t *
 int sd_rewrite_bam(const char *in_path, const char *out_path, const char *header_text, const uint8_t *keep,
                    const uint8_t *state, uint64_t n_records, int sort, int level, int threads, uint64_t *n_written,
                    char *err, int errlen);
+/* The same, and a BAI index of the output next to it (pysam.index, filter.py:313 / tcounter.py:526-527): binning index,
+ * 16 kb linear index and htslib's metadata pseudo-bin, over the virtual offsets of the BGZF blocks just written.  The
+ * output must come out coordinate sorted (sort != 0, or a sorted input); bai_path NULL = no index. */
+int sd_rewrite_bam_indexed(const char *in_path, const char *out_path, const char *bai_path, const char *header_text,
+                           const uint8_t *keep, const uint8_t *state, uint64_t n_records, int sort, int level, int threads,
+                           uint64_t *n_written, char *err, int errlen);
 
 /* ------------------------------------------------------------------ host text output
  * sd_format_repr: x printed like Python's repr(float) (what the reference's print() of a rate produces); buf >= 32 bytes.

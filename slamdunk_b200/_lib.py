@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SLAMDUNK_B200_LIB") or os.path.join(HERE, "libslamdunk_b200.so")   # env: kernel experiments
 
 SD_OK = 0
-SD_ABI_VERSION = 3   # include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual
+SD_ABI_VERSION = 4   # include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual; 4 = BAI writer
 SD_F_REVERSE, SD_F_UNMAPPED, SD_F_SECONDARY, SD_F_SUPPLEMENTARY = 0x01, 0x02, 0x04, 0x08
 SD_F_HAS_MP, SD_F_SKIP, SD_F_NEWNAME, SD_F_PAD = 0x10, 0x20, 0x40, 0x80
 SD_REF_NONE = 0xFFFF
@@ -112,6 +112,8 @@ PROTOTYPES = {
                                       ctypes.c_int, ctypes.c_int, c_u64p, ctypes.c_char_p, ctypes.c_int]),
     "sd_qual_unpack": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64, ctypes.c_uint32, _VP, _VP]),
     "sd_qual_pack": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64, _VP, ctypes.POINTER(ctypes.c_uint32), _VP]),
+    "sd_rewrite_bam_indexed": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, _VP, _VP, ctypes.c_uint64,
+                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, c_u64p, ctypes.c_char_p, ctypes.c_int]),
     "sd_decode_bam": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint32, ctypes.c_int,
                                      ctypes.c_uint32, ctypes.c_int, ctypes.POINTER(ctypes.POINTER(HBatch)),
                                      ctypes.c_char_p, ctypes.c_int]),

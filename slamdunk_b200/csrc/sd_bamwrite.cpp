@@ -10,6 +10,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <map>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -85,9 +86,36 @@ struct Span { const uint8_t *p; size_t n; };
 
 }  // namespace
 
-extern "C" int sd_rewrite_bam(const char *in_path, const char *out_path, const char *header_text, const uint8_t *keep,
-                              const uint8_t *state, uint64_t n_records, int sort, int level, int threads, uint64_t *n_written,
-                              char *err, int errlen) {
+namespace {
+
+// ---- BAI (SAM spec 5.2): binning index + 16 kb linear index over virtual offsets (compressed block start << 16 | offset)
+inline uint32_t reg2bin(int64_t beg, int64_t end) {
+    --end;
+    if (beg >> 14 == end >> 14) return (uint32_t)(((1 << 15) - 1) / 7 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (uint32_t)(((1 << 12) - 1) / 7 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (uint32_t)(((1 << 9) - 1) / 7 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (uint32_t)(((1 << 6) - 1) / 7 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (uint32_t)(((1 << 3) - 1) / 7 + (beg >> 26));
+    return 0;
+}
+
+struct BaiRef {
+    std::map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins;   // bin -> chunks (begin, end)
+    uint32_t last_bin = 0;
+    bool has_last = false;
+    std::vector<uint64_t> linear;
+    uint64_t off_beg = 0, off_end = 0, n_mapped = 0, n_unmapped = 0;
+    bool used = false;
+};
+
+void put32(std::vector<uint8_t> &o, uint32_t v) { for (int k = 0; k < 4; k++) o.push_back((uint8_t)(v >> (8 * k))); }
+void put64(std::vector<uint8_t> &o, uint64_t v) { for (int k = 0; k < 8; k++) o.push_back((uint8_t)(v >> (8 * k))); }
+
+}  // namespace
+
+extern "C" int sd_rewrite_bam_indexed(const char *in_path, const char *out_path, const char *bai_path, const char *header_text,
+                                      const uint8_t *keep, const uint8_t *state, uint64_t n_records, int sort, int level, int threads,
+                                      uint64_t *n_written, char *err, int errlen) {
     if (!in_path || !out_path || !header_text || !keep) return wfail(err, errlen, SD_ERR_ARG, "sd_rewrite_bam: null argument");
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     if (level < 1 || level > 9) level = 6;
@@ -276,6 +304,73 @@ extern "C" int sd_rewrite_bam(const char *in_path, const char *out_path, const c
         out.resize(bsize);
     });
     if (bad) return wfail(err, errlen, SD_ERR_LIMIT, "BGZF compression failed (block does not fit 64 KiB)");
+    if (bai_path) {
+        // compressed start of every block (one more: the EOF block) -> virtual offset of a position in the record stream
+        std::vector<uint64_t> coff(n_blocks + 1, 0);
+        for (size_t b = 0; b < n_blocks; b++) coff[b + 1] = coff[b] + blocks[b].size();
+        auto voff = [&](size_t u) { return (coff[u / payload] << 16) | (uint64_t)(u % payload); };
+        std::vector<BaiRef> refs(names.size());
+        uint64_t n_no_coor = 0;
+        int32_t last_ref = -1;
+        int64_t last_pos = -1;
+        for (size_t k = 0; k < order.size(); k++) {
+            const Span &sp = spans[k + 1];              // spans[0] is the header
+            const uint8_t *r = sp.p + 4;
+            const int32_t ref_id = (int32_t)g32(r), pos = (int32_t)g32(r + 4);
+            const uint32_t flag = g16(r + 14);
+            if (ref_id < 0 || (size_t)ref_id >= refs.size()) { n_no_coor++; continue; }
+            if (n_no_coor || ref_id < last_ref || (ref_id == last_ref && pos < last_pos))
+                return wfail(err, errlen, SD_ERR_ARG, "%s: records are not coordinate sorted, cannot index", out_path);
+            last_ref = ref_id;
+            last_pos = pos;
+            const uint32_t l_name = r[8], n_cig = g16(r + 12);
+            int64_t reflen = 0;
+            if (!(flag & 4))
+                for (uint32_t c = 0; c < n_cig; c++) {
+                    const uint32_t op = g32(r + 32 + l_name + 4 * c);
+                    if ((0x18Du >> (op & 15u)) & 1u) reflen += op >> 4;
+                }
+            const int64_t beg = pos < 0 ? 0 : pos, end = beg + (reflen > 0 ? reflen : 1);
+            const uint64_t v0 = voff(start[k + 1]), v1 = voff(start[k + 2]);
+            BaiRef &R2 = refs[(size_t)ref_id];
+            if (!R2.used) { R2.used = true; R2.off_beg = v0; }
+            R2.off_end = v1;
+            if (flag & 4) R2.n_unmapped++; else R2.n_mapped++;
+            const uint32_t bin = reg2bin(beg, end);
+            if (R2.has_last && R2.last_bin == bin) R2.bins[bin].back().second = v1;   // consecutive records of one bin: one chunk
+            else R2.bins[bin].push_back({v0, v1});
+            R2.has_last = true;
+            R2.last_bin = bin;
+            const size_t w0 = (size_t)(beg >> 14), w1 = (size_t)((end - 1) >> 14);
+            if (R2.linear.size() < w1 + 1) R2.linear.resize(w1 + 1, UINT64_MAX);
+            for (size_t w = w0; w <= w1; w++)
+                if (R2.linear[w] == UINT64_MAX) R2.linear[w] = v0;
+        }
+        std::vector<uint8_t> bai = {'B', 'A', 'I', 1};
+        put32(bai, (uint32_t)refs.size());
+        for (BaiRef &R2 : refs) {
+            if (!R2.used) { put32(bai, 0); put32(bai, 0); continue; }
+            put32(bai, (uint32_t)R2.bins.size() + 1);
+            for (auto &bn : R2.bins) {
+                put32(bai, bn.first);
+                put32(bai, (uint32_t)bn.second.size());
+                for (auto &ch : bn.second) { put64(bai, ch.first); put64(bai, ch.second); }
+            }
+            put32(bai, 37450);                          // htslib's metadata pseudo-bin
+            put32(bai, 2);
+            put64(bai, R2.off_beg); put64(bai, R2.off_end);
+            put64(bai, R2.n_mapped); put64(bai, R2.n_unmapped);
+            for (size_t w = R2.linear.size(); w-- > 0;)  // windows without a record start where the next one does
+                if (R2.linear[w] == UINT64_MAX) R2.linear[w] = (w + 1 < R2.linear.size()) ? R2.linear[w + 1] : 0;
+            put32(bai, (uint32_t)R2.linear.size());
+            for (uint64_t v : R2.linear) put64(bai, v);
+        }
+        put64(bai, n_no_coor);
+        FILE *fb = fopen(bai_path, "wb");
+        if (!fb) return wfail(err, errlen, SD_ERR_IO, "cannot create %s", bai_path);
+        const bool ok = fwrite(bai.data(), 1, bai.size(), fb) == bai.size();
+        if (fclose(fb) != 0 || !ok) return wfail(err, errlen, SD_ERR_IO, "short write on %s", bai_path);
+    }
     FILE *fh = fopen(out_path, "wb");
     if (!fh) return wfail(err, errlen, SD_ERR_IO, "cannot create %s", out_path);
     for (auto &b : blocks)
@@ -285,4 +380,11 @@ extern "C" int sd_rewrite_bam(const char *in_path, const char *out_path, const c
     fclose(fh);
     if (n_written) *n_written = order.size();
     return SD_OK;
+}
+
+extern "C" int sd_rewrite_bam(const char *in_path, const char *out_path, const char *header_text, const uint8_t *keep,
+                              const uint8_t *state, uint64_t n_records, int sort, int level, int threads, uint64_t *n_written,
+                              char *err, int errlen) {
+    return sd_rewrite_bam_indexed(in_path, out_path, nullptr, header_text, keep, state, n_records, sort, level, threads, n_written, err,
+                                  errlen);
 }

@@ -281,7 +281,7 @@ int sd_bam_inflate_file(const char *path, int threads, RawBuf &raw, size_t *comp
     if (bad) return fail(err, errlen, SD_ERR_FORMAT, "%s: corrupt BGZF block", path);
     const size_t compressed = file.size();
     file.release();
-    if (compressed_bytes) *compressed_bytes = file.size();
+    if (compressed_bytes) *compressed_bytes = compressed;
     return SD_OK;
 }
 

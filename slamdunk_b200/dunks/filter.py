@@ -4,9 +4,8 @@ filter.Filter (slamdunk/dunks/filter.py:213-315), same signature, same log lines
 
 Device: per-read predicates (MAPQ / identity / NM) or, when a BED file is given, the
 multimapper-retention logic (sd_filter).  Host (C++, all threads): BAM decode (sd_decode_bam) and the
-sorted, BGZF-compressed output with the RD tags (sd_rewrite_bam).  No BAI index is written
-(`pysam.index`, filter.py:313): `slamdunk_b200 count` streams the whole file and joins reads to UTRs
-on the device, so nothing downstream needs one.
+sorted, BGZF-compressed output with the RD tags and its BAI index (sd_rewrite_bam_indexed; `pysam.index`,
+filter.py:313).
 """
 from __future__ import print_function
 
@@ -100,9 +99,9 @@ def Filter(inputBAM, outputBAM, log, bed, MQ=2, minIdentity=0.8, NM=-1, printOnl
     lib = L.load()
     err = ctypes.create_string_buffer(512)
     written = ctypes.c_uint64(0)
-    rc = lib.sd_rewrite_bam(os.fsencode(inputBAM), os.fsencode(outputBAM), bamio.header_dict_to_text(header).encode(),
-                            keep.ctypes.data, state.ctypes.data, n_records, 1, 6, OPTIONS["threads"], ctypes.byref(written),
-                            err, len(err))
+    rc = lib.sd_rewrite_bam_indexed(os.fsencode(inputBAM), os.fsencode(outputBAM), os.fsencode(outputBAM + ".bai"),
+                                    bamio.header_dict_to_text(header).encode(), keep.ctypes.data, state.ctypes.data, n_records,
+                                    1, 6, OPTIONS["threads"], ctypes.byref(written), err, len(err))
     if rc != L.SD_OK:
-        raise IOError("sd_rewrite_bam: " + err.value.decode("utf-8", "replace"))
+        raise IOError("sd_rewrite_bam_indexed: " + err.value.decode("utf-8", "replace"))
     OPTIONS["stats"]["written"] = int(written.value)

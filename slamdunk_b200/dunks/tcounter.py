@@ -350,7 +350,7 @@ def genomewideReadSeparation(referenceFile, snpsFile, bam, minBaseQual, outputBA
     records; input order and header are kept.
 
     Device: the per-read conversion count of the count kernel (sd_count_reads).  Host: decode, the name set (64-bit name
-    hashes from the decoder) and the two BAMs (sd_rewrite_bam).  No BAI is written (pysamIndex, tcounter.py:526-527)."""
+    hashes from the decoder), the two BAMs and their BAI indexes (sd_rewrite_bam_indexed; pysamIndex, tcounter.py:526-527)."""
     import ctypes
 
     import torch
@@ -408,10 +408,11 @@ def genomewideReadSeparation(referenceFile, snpsFile, bam, minBaseQual, outputBA
     for suffix, keep in (("_backgroundReads.bam", placed & ~in_tc), ("_TCReads.bam", placed & in_tc)):
         k8 = np.ascontiguousarray(keep, dtype=np.uint8)
         nw = ctypes.c_uint64(0)
-        rc = lib.sd_rewrite_bam(os.fsencode(bam), os.fsencode(outputBAMPrefix + suffix), text.encode(), k8.ctypes.data, None, n, 0, 6,
+        rc = lib.sd_rewrite_bam_indexed(os.fsencode(bam), os.fsencode(outputBAMPrefix + suffix), os.fsencode(outputBAMPrefix + suffix + ".bai"),
+                                        text.encode(), k8.ctypes.data, None, n, 0, 6,
                                 OPTIONS["threads"], ctypes.byref(nw), err, len(err))
         if rc != L.SD_OK:
-            raise IOError("sd_rewrite_bam: " + err.value.decode("utf-8", "replace"))
+            raise IOError("sd_rewrite_bam_indexed: " + err.value.decode("utf-8", "replace"))
         written[suffix] = int(nw.value)
     tm["written"] = written
     tm["total_s"] = time.time() - t0

@@ -19,6 +19,13 @@ def _run(bam, bed, mq, mi, nm, tmp_path, tag="out"):
     log = io.StringIO()
     gfilter.Filter(bam, out, log, bed, mq, mi, nm, False, False, True)
     text, refs, recs = bamio.read_bam(out)
+    import baiquery                                   # the filtered BAM comes with an index that answers region queries
+    idx, _n = baiquery.read_bai(out + ".bai")
+    assert len(idx) == len(refs)
+    if recs:
+        mid = recs[len(recs) // 2]
+        lo, hi = max(0, mid.pos - 300), mid.pos + 300
+        assert baiquery.fetch(out, idx, mid.ref_id, lo, hi) == baiquery.scan(out, mid.ref_id, lo, hi)
     hdr = bamio.parse_header_text(text)
     got = [[r.qname, r.flag, r.ref_id, r.pos, r.get_tag("RD") if r.has_tag("RD") else None] for r in recs]
     return hdr, got, log.getvalue()

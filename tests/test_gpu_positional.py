@@ -111,4 +111,5 @@ def test_alleyoop_read_separator_cli(tmp_path):
     c = goldens.ReadSepCase("case_a")
     out = tmp_path / "sep"
     alleyoop.run(["read-separator", "-o", str(out), "-r", c.ref, "-v", c.vcf, c.bam])
-    assert sorted(os.listdir(out)) == ["case_a_multi_TCReads.bam", "case_a_multi_backgroundReads.bam", "case_a_multi_read_separator.log"]
+    assert sorted(os.listdir(out)) == ["case_a_multi_TCReads.bam", "case_a_multi_TCReads.bam.bai", "case_a_multi_backgroundReads.bam",
+                                       "case_a_multi_backgroundReads.bam.bai", "case_a_multi_read_separator.log"]

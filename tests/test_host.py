@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "library does not export " + name
     assert declared == set(L.PROTOTYPES.keys())
-    assert lib.sd_abi_version() == L.SD_ABI_VERSION == 3
+    assert lib.sd_abi_version() == L.SD_ABI_VERSION == 4
 
 
 def _decode(path, fasta_names, want_mp=True, tile_reads=32, threads=3):
@@ -424,3 +424,43 @@ def test_decoder_codes_binned_qualities(tmp_path):
                     assert list(qual[qo:qo + n]) == recs[i].qual
                     qo += n
             hb.close()
+
+
+def test_native_bai_index_answers_region_queries(tmp_path):
+    """sd_rewrite_bam_indexed: fetching regions through the BAI (independent reader, tests/baiquery.py) equals a scan."""
+    import ctypes
+    import random
+    import baiquery
+    c = simdata.make_case(str(tmp_path), seed=611, n_reads=9000, n_utr=60, read_len=(30, 120), complexity=2.0,
+                          chroms=(("chr1", 400000), ("chr2", 70000), ("chr3", 20000), ("chrEmpty", 5000)))
+    text, refs, records = bamio.read_bam(c.bam)
+    rnd = random.Random(3)
+    keep = np.array([1 if rnd.random() < 0.8 else 0 for _ in records], dtype=np.uint8)
+    out, bai = str(tmp_path / "o.bam"), str(tmp_path / "o.bam.bai")
+    err = ctypes.create_string_buffer(256)
+    nw = ctypes.c_uint64(0)
+    lib = L.load()
+    rc = lib.sd_rewrite_bam_indexed(c.bam.encode(), out.encode(), bai.encode(), text.encode(), keep.ctypes.data, None, len(records), 1, 6,
+                                    3, ctypes.byref(nw), err, len(err))
+    assert rc == 0, err.value
+    idx, n_no_coor = baiquery.read_bai(bai)
+    assert len(idx) == len(refs) and n_no_coor == 0
+    kept = [r for r, k in zip(records, keep) if k]
+    for rid in range(len(refs)):
+        meta = idx[rid][0].get(37450)
+        on_ref = [r for r in kept if r.ref_id == rid]
+        if on_ref:
+            assert meta is not None and meta[1] == (sum(1 for r in on_ref if not r.flag & 4), sum(1 for r in on_ref if r.flag & 4))
+        else:
+            assert idx[rid] == ({}, [])
+    for _ in range(60):
+        rid = rnd.randrange(3)
+        ln = refs[rid][1]
+        beg = rnd.randrange(ln)
+        end = min(ln, beg + rnd.choice([1, 50, 2000, 40000, 300000]))
+        assert baiquery.fetch(out, idx, rid, beg, end) == baiquery.scan(out, rid, beg, end), (rid, beg, end)
+    # an unsorted output cannot be indexed
+    rc = lib.sd_rewrite_bam_indexed(c.bam.encode(), out.encode(), bai.encode(), text.encode(), keep.ctypes.data, None, len(records), 0, 6,
+                                    3, ctypes.byref(nw), err, len(err))
+    srt = all((a.ref_id, a.pos) <= (b.ref_id, b.pos) for a, b in zip(kept, kept[1:]))
+    assert (rc == 0) == srt
