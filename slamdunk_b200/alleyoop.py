@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""`alleyoop` sub-commands that ride on the GPU count path: `positional-tracks` and `read-separator` (same options,
+"""`alleyoop` sub-commands that ride on the GPU count path: `positional-tracks`, `read-separator` and the table tool
+`collapse` (same options,
 defaults and output names as the reference, slamdunk/alleyoop.py:115-144, 312-333, 450-481); the other alleyoop tools
 are plots and table utilities outside the accelerated path.
 
@@ -52,6 +53,17 @@ def runReadSeparator(tid, bam, ref, minQual, conversionThreshold, outputDirector
     stepFinished()
 
 
+def runCollapse(tid, tcount, outputDirectory):
+    """alleyoop.py:94-100"""
+    from .dunks import tcounter
+    outputTCOUNT = os.path.join(outputDirectory, replaceExtension(basename(tcount), ".csv", "_collapsed"))
+    outputLOG = os.path.join(outputDirectory, replaceExtension(basename(tcount), ".log", "_collapsed"))
+    log = getLogFile(outputLOG)
+    tcounter.collapse(tcount, outputTCOUNT, log)
+    log.close()
+    stepFinished()
+
+
 def build_parser():
     parser = ArgumentParser(description="alleyoop (GPU subset) v" + __version__, prog="alleyoop", formatter_class=ArgumentDefaultsHelpFormatter)
     parser.add_argument("--version", action="version", version="%(prog)s " + __version__)
@@ -69,6 +81,10 @@ def build_parser():
     p.add_argument("-q", "--min-base-qual", type=int, default=27, required=False, dest="minQual", help="Min base quality for T -> C conversions (default: %(default)d)")
     p.add_argument("-t", "--threads", type=int, required=False, default=1, dest="threads", help="Thread number (default: %(default)d)")
     p.add_argument("--device", type=int, default=0, help="CUDA device")
+    p = sub.add_parser("collapse", help="Collapse UTRs", formatter_class=ArgumentDefaultsHelpFormatter)
+    p.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", default=SUPPRESS, help="Output directory for mapped BAM files.")
+    p.add_argument("-t", "--threads", type=int, required=False, default=1, dest="threads", help="Thread number")
+    p.add_argument("tcount", action="store", help="Tcount file(s)", nargs="+")
     p = sub.add_parser("read-separator", help="Separate TC-reads from background reads genome-wide", formatter_class=ArgumentDefaultsHelpFormatter)
     p.add_argument("bam", action="store", help="Bam file(s)", nargs="+")
     p.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", default=SUPPRESS, help="Output directory for bam files.")
@@ -86,9 +102,16 @@ def build_parser():
 def run(argv=None):
     parser = build_parser()
     args = parser.parse_args(argv)
-    if args.command not in ("positional-tracks", "read-separator"):
+    if args.command not in ("positional-tracks", "read-separator", "collapse"):
         parser.print_help()
         sys.exit(0)
+    if args.command == "collapse":
+        createDir(args.outputDir)
+        message("Running alleyoop collapse for " + str(len(args.tcount)) + " files (" + str(args.threads) + " threads)")
+        for tid in range(0, len(args.tcount)):
+            runCollapse(tid, args.tcount[tid], args.outputDir)
+        dunkFinished()
+        return
     from .dunks import tcounter
     tcounter.OPTIONS["device"] = args.device
     tcounter.OPTIONS["threads"] = args.threads if args.threads > 1 else 0

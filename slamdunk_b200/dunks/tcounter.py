@@ -417,3 +417,38 @@ def genomewideReadSeparation(referenceFile, snpsFile, bam, minBaseQual, outputBA
     tm["written"] = written
     tm["total_s"] = time.time() - t0
     OPTIONS["timings"] = tm
+
+
+def collapse(expandedCSV, collapsedCSV, log):
+    """Drop-in for the reference's tcounter.collapse (dunks/tcounter.py:39-111, `alleyoop collapse`): sum the tcount rows
+    of every gene name (column 4) and recompute CPM and conversion rate.  Host-side table work on the count path's output;
+    same column order, same float text (readsCPM is readCount / total reads * 1e6 as three float operations)."""
+    genes = {}
+    readNumber = 0
+    with open(expandedCSV, "r") as f:
+        for line in f:
+            if line.startswith("#") or line.startswith("Chromosome"):
+                continue
+            fields = line.rstrip().split("\t")
+            if len(fields) < 14:                                        # tcounter.py:86-87
+                print("Error in TC file format - unexpected number of fields (" + str(len(fields)) + ") in the following line:\n" + line,
+                      file=log)
+                continue
+            vals = [max(int(fields[k]), 0) for k in (4, 8, 9, 10, 11, 12, 13)]   # length, Tcontent, cov, conv, reads, tcReads, multimap
+            acc = genes.get(fields[3])
+            if acc is None:
+                genes[fields[3]] = vals
+            else:
+                for k in range(7):
+                    acc[k] += vals[k]
+            readNumber += int(fields[11])                               # not clamped (tcounter.py:84)
+    with open(collapsedCSV, "w") as out:
+        print("gene_name", "length", "readsCPM", "conversionRate", "Tcontent", "coverageOnTs", "conversionsOnTs", "readCount",
+              "tcReadCount", "multimapCount", sep="\t", file=out)
+        for gene in sorted(genes.keys()):
+            length, tcontent, cov, conv, reads, tcreads, multimap = genes[gene]
+            conversionRate = 0
+            if cov > 0:
+                conversionRate = float(conv) / cov
+            print(gene, length, float(reads) / float(readNumber) * 1000000, conversionRate, tcontent, cov, conv, reads, tcreads,
+                  multimap, sep="\t", file=out)

@@ -60,3 +60,34 @@ def test_count_cli_end_to_end(tmp_path):
     assert open(base + "_tcount_plus.bedgraph").read() == open(c.plus).read()
     assert open(base + "_tcount_mins.bedgraph").read() == ""
     assert open(base + "_tcount.log").read().startswith("Using 100 as maximum read length.")
+
+
+def test_collapse_matches_reference(tmp_path):
+    """alleyoop collapse (tcounter.collapse, tcounter.py:39-111): rows of one gene name summed; against the reference when present,
+    against a hand-made expectation otherwise."""
+    import io
+    import refrun
+    from slamdunk_b200.dunks import tcounter
+    hdr = "Chromosome\tStart\tEnd\tName\tLength\tStrand\tConversionRate\tReadsCPM\tTcontent\tCoverageOnTs\tConversionsOnTs\tReadCount\tTcReadCount\tmultimapCount\tConversionRateLower\tConversionRateUpper\n"
+    rows = ["chr1\t10\t210\tgeneB\t200\t+\t0.02\t100.0\t50\t1000\t20\t30\t12\t1\t-1.0\t-1.0\n",
+            "chr1\t900\t1000\tgeneA\t100\t-\t0\t0\t20\t0\t0\t0\t0\t0\t-1.0\t-1.0\n",
+            "chr2\t10\t310\tgeneB\t300\t+\t0.5\t7.5\t70\t33\t7\t9\t3\t2\t-1.0\t-1.0\n",
+            "chr2\tbroken\n"]
+    src = tmp_path / "x_tcount.tsv"
+    src.write_text("#slamdunk v0.4.3\t3\n#annotation:\ta.bed\tabc\n" + hdr + "".join(rows))
+    log = io.StringIO()
+    tcounter.collapse(str(src), str(tmp_path / "mine.csv"), log)
+    got = (tmp_path / "mine.csv").read_text()
+    assert "unexpected number of fields (2)" in log.getvalue()
+    lines = got.split("\n")
+    assert lines[0].split("\t")[:4] == ["gene_name", "length", "readsCPM", "conversionRate"]
+    assert lines[1] == "geneA\t100\t0.0\t0\t20\t0\t0\t0\t0\t0"
+    assert lines[2] == "geneB\t500\t1000000.0\t" + repr(27.0 / 1033) + "\t120\t1033\t27\t39\t15\t3"
+    if refrun.available():
+        ref_tc, _f = refrun.reference_modules()
+        rlog = io.StringIO()
+        ref_tc.collapse(str(src), str(tmp_path / "ref.csv"), rlog)
+        assert got == (tmp_path / "ref.csv").read_text() and log.getvalue() == rlog.getvalue()
+    from slamdunk_b200 import alleyoop
+    alleyoop.run(["collapse", "-o", str(tmp_path / "c"), str(src)])
+    assert (tmp_path / "c" / "x_tcount_collapsed.csv").read_text() == got
