@@ -14,6 +14,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -40,20 +41,89 @@ int fail(char *err, int errlen, int code, const char *fmt, ...) {
 
 // Page-locked when a CUDA device is present (async H2D), plain aligned memory otherwise
 // (CPU-only decode tests).
+// Page-locked host memory for the decoded columns.  Pinning pages is slow (a few GB/s, single threaded), about as long as
+// inflating the file on all cores, so one arena sized from the file is pinned on a helper thread WHILE the BGZF blocks are
+// inflated; the columns are then carved out of it (anything that does not fit gets its own allocation).  A freed arena is
+// parked in a one-slot process-wide cache: `count` decodes one BAM after the other (12 samples in cfg3), and every file
+// after the first gets its pinned memory for nothing.
+struct ArenaCache {
+    std::mutex mu;
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    int dev = -1;
+    bool take(size_t want, int device, uint8_t **out, size_t *out_cap) {
+        std::lock_guard<std::mutex> g(mu);
+        if (!p || cap < want || dev != device) return false;
+        *out = p;
+        *out_cap = cap;
+        p = nullptr;
+        cap = 0;
+        return true;
+    }
+    void give(uint8_t *q, size_t qcap, int device) {
+        uint8_t *drop = q;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (!p || qcap > cap) {
+                drop = p;
+                p = q;
+                cap = qcap;
+                dev = device;
+            }
+        }
+        if (drop) cudaFreeHost(drop);
+    }
+};
+static ArenaCache &arena_cache() {
+    static ArenaCache *c = new ArenaCache();   // never destroyed: the CUDA context may be gone at exit
+    return *c;
+}
+
 struct HostAlloc {
     std::vector<std::pair<void *, bool>> blocks;
-    void *get(size_t bytes) {
-        if (bytes == 0) bytes = 16;
-        bytes = (bytes + 255) & ~(size_t)255;
-        void *p = nullptr;
-        bool pinned = false;
+    uint8_t *arena = nullptr;
+    size_t arena_cap = 0, arena_used = 0;
+    int arena_dev = 0;
+    std::thread arena_thread;
+
+    static bool have_device() {
         static int have_dev = -1;
         if (have_dev < 0) {
             int n = 0;
             have_dev = (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0;
             cudaGetLastError();
         }
-        if (have_dev && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) pinned = true;
+        return have_dev == 1;
+    }
+    void reserve_async(size_t bytes) {
+        if (!have_device() || bytes == 0 || arena_thread.joinable() || arena) return;
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+        const size_t cap = (bytes + 4095) & ~(size_t)4095;
+        arena_dev = dev;
+        if (arena_cache().take(cap, dev, &arena, &arena_cap)) return;
+        arena_thread = std::thread([this, dev, cap]() {
+            void *p = nullptr;
+            if (cudaSetDevice(dev) == cudaSuccess && cudaHostAlloc(&p, cap, cudaHostAllocDefault) == cudaSuccess) {
+                arena = static_cast<uint8_t *>(p);
+                arena_cap = cap;
+            } else {
+                cudaGetLastError();
+            }
+        });
+    }
+    void *get(size_t bytes) {
+        if (arena_thread.joinable()) arena_thread.join();
+        if (bytes == 0) bytes = 16;
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (arena && arena_used + bytes <= arena_cap) {
+            void *p = arena + arena_used;
+            arena_used += bytes;
+            return p;
+        }
+        void *p = nullptr;
+        bool pinned = false;
+        if (have_device() && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) pinned = true;
         else {
             cudaGetLastError();
             if (posix_memalign(&p, 256, bytes) != 0) return nullptr;
@@ -62,6 +132,8 @@ struct HostAlloc {
         return p;
     }
     ~HostAlloc() {
+        if (arena_thread.joinable()) arena_thread.join();
+        if (arena) arena_cache().give(arena, arena_cap, arena_dev);
         for (auto &b : blocks) {
             if (b.second) cudaFreeHost(b.first);
             else free(b.first);
@@ -430,20 +502,29 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         tp = t;
     };
 
+    Owner *own = new Owner();
+    sd_hbatch *hb = new sd_hbatch();
+    memset(hb, 0, sizeof *hb);
+    hb->opaque = own;
+    {   // pin the column arena while the file inflates: the columns take about as much room as three times the file
+        FILE *probe = fopen(path, "rb");
+        if (probe) {
+            fseek(probe, 0, SEEK_END);
+            const long fsz = ftell(probe);
+            fclose(probe);
+            if (fsz > 0) own->mem.reserve_async(3 * (size_t)fsz + (1u << 20));
+        }
+    }
     RawBuf raw;
     size_t compressed = 0;
     {
         const int rc = sd_bam_inflate_file(path, threads, raw, &compressed, err, errlen);
-        if (rc != SD_OK) return rc;
+        if (rc != SD_OK) { sd_hbatch_free(hb); return rc; }
     }
     const double t1 = now_s();
     lap("inflate");
 
     // ---- BAM header
-    Owner *own = new Owner();
-    sd_hbatch *hb = new sd_hbatch();
-    memset(hb, 0, sizeof *hb);
-    hb->opaque = own;
     auto bail = [&](int code, const char *msg) {
         sd_hbatch_free(hb);
         return fail(err, errlen, code, "%s: %s", path, msg);
