@@ -41,7 +41,7 @@ extern "C" {
 #define SD_ERR_LIMIT (-6)
 #define SD_ERR_NOMEM (-7)
 
-#define SD_ABI_VERSION 4
+#define SD_ABI_VERSION 5
 
 typedef struct sd_ctx sd_ctx;
 
@@ -192,7 +192,8 @@ int sd_set_snps(sd_ctx *ctx, const uint32_t *d_tc_mask, const uint32_t *d_ag_mas
  * Replaces BedIterator + the per-UTR indexed fetch (tcounter.py:165, SlamSeqFile.py:441).
  * Host arrays in BED order.  chrom[i] = FASTA chromosome index or SD_REF_NONE; start/stop as in
  * the BED file (stop is clipped to the chromosome length internally, SlamSeqFile.py:441);
- * strand 0 '+', 1 '-'.  in_bam[i] = 0 suppresses reads for rows whose chromosome is not in the
+ * strand 0 '+', 1 '-' (2: no strand -- the row then takes reads of both strands as the reference's iterator does for
+ * strand "."; sd_read_stats only, `count` refuses such rows).  in_bam[i] = 0 suppresses reads for rows whose chromosome is not in the
  * BAM header (SlamSeqFile.py:440-445).
  */
 int sd_set_utrs(sd_ctx *ctx, const uint32_t *h_chrom, const int64_t *h_start, const int64_t *h_stop,
@@ -259,6 +260,8 @@ int sd_filter(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params, con
 #define SD_DECODE_MP 1
 #define SD_DECODE_GROUP 2
 #define SD_DECODE_RAW_QUAL 4   /* keep one byte per base quality even when the file has <= 16 distinct values */
+#define SD_DECODE_MP_ALL 8     /* mp column holds EVERY MP entry, two words each: {readPos-1 | refPos-1 << 16, conv (0..24)} --
+                                  the form sd_read_stats takes (sd_count cannot read it); implies SD_DECODE_MP */
 
 typedef struct sd_hbatch {
     sd_batch batch;          /* host pointers */
@@ -358,6 +361,49 @@ int sd_track_runs(sd_ctx *ctx, uint32_t row, int kind, int coverage_cutoff, uint
                   double *d_val, uint8_t *d_isfloat, uint64_t capacity, uint64_t *n_runs);
 int sd_write_track(const char *path, const char *chrom, int kind, uint64_t n_runs, const uint32_t *h_pos,
                    const double *h_val, const uint8_t *h_isfloat);
+
+/* ------------------------------------------------------------------ conversion statistics over the same per-read scan
+ * `alleyoop rates / tcperreadpos / utrrates / tcperutrpos / snpeval` (dunks/stats.py:85-131, 591-657, 331-528, 659-772,
+ * 774-849) and the per-read lists of computeTconversions(mle=True) (dunks/tcounter.py:233-243) all iterate
+ * SlamSeqBamIterator (slamseq/SlamSeqFile.py:364-402) and look at the COMPLETE mismatch list of every read -- all 25
+ * conversion types of the MP tag that pass the base-quality test -- plus the read's 5 x 5 conversion matrix
+ * (computeRatesForRead, SlamSeqFile.py:231-249).  sd_read_stats does that scan for one device-resident batch decoded
+ * with SD_DECODE_MP_ALL: one thread per read, per-UTR quantities through the interval join of sd_set_utrs (strand
+ * specific, SlamSeqFile.py:369), genome-wide ones over every placed record (readsInChromosome, strand ".").  SNP masking
+ * follows sd_set_snps (none set = snps None).  Every output is optional (NULL = not wanted), caller-owned device memory,
+ * ACCUMULATED into (zero it first); all integers.  Asynchronous.
+ */
+typedef struct sd_read_pair {  /* one (read, BED row) incidence for the mle per-read lists */
+    uint32_t row;              /* BED row */
+    uint32_t read;             /* index of the record in the file (d_order[slot]; the slot itself without d_order) */
+    uint32_t t_count;          /* testN: T (A on reverse reads) in the read sequence + in-UTR mismatches on a T/A reference base, tcounter.py:233-238 */
+    uint32_t tc_count;         /* testk: in-UTR T>C / A>G conversions of the read, tcounter.py:239-240 */
+} sd_read_pair;
+
+#define SD_NRATE 25            /* conv = 5 * refBase + readBase over A,C,G,T,N (SlamSeqFile.py:251-257) */
+typedef struct sd_stats_args {
+    int32_t min_qual;              /* minQual / minBaseQual: an MP entry counts when its base quality >= this (SlamSeqFile.py:330) */
+    int32_t conversion_threshold;  /* isTcRead = tcCount >= this (SlamSeqFile.py:397); the stats use the iterator's default 1 */
+    int32_t strict;                /* what happens to reads that are not isTcRead: utr_snp and pairs see an empty mismatch list
+                                      (stats.py:806-810 with -m; tcounter.py:210-214 always); utr_rates skips them when
+                                      tcCount > 0 (stats.py:376 with -m) */
+    uint32_t max_read_length;      /* readpos: reads longer than this are left out (stats.py:621) */
+    uint32_t utr_norm;             /* utrpos: utrNormFactor, 250 (stats.py:35) */
+    const uint32_t *d_order;       /* optional device uint32[n_reads]: batch slot -> record index in the file */
+    int64_t *d_rates;              /* [2][25] summed conversion matrices of forward / reverse reads (stats.py:112-117) */
+    int64_t *d_readpos;            /* [6][max_read_length + 1]: per read position (reverse reads counted from their end,
+                                      SlamSeqFile.py:335) other mismatches fwd, rev; T>C fwd, A>G rev; then reads covering
+                                      the position fwd, rev in DIFFERENCE form (+1 at 0, -1 at the read length) */
+    int64_t *d_utr_rates;          /* [n_utr][26]: summed matrices of the row's reads, then their number (stats.py:369-384) */
+    int64_t *d_utr_snp;            /* [n_utr][3]: readCount, unmaskedTCCount, maskedTCCount (stats.py:799-835) */
+    int64_t *d_utrpos;             /* [6][utr_norm + 1] over the last utr_norm positions of '+' rows / the first of '-' rows
+                                      (stats.py:693-747): other mismatches fwd, rev; T>C fwd, A>G rev; coverage fwd, rev in
+                                      DIFFERENCE form; the reverse arrays in the reference's own (unreversed) index */
+    sd_read_pair *d_pairs;         /* [pair_capacity] */
+    uint64_t pair_capacity;
+    unsigned long long *d_n_pairs; /* number of pairs found (may exceed the capacity: then only the first are stored) */
+} sd_stats_args;
+int sd_read_stats(sd_ctx *ctx, const sd_batch *d_batch, const sd_stats_args *args);
 
 /* ------------------------------------------------------------------ synthetic SLAM-seq reads
  * Device-side generator of the BASELINE.json configurations (per-T Bernoulli conversions as in

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SLAMDUNK_B200_LIB") or os.path.join(HERE, "libslamdunk_b200.so")   # env: kernel experiments
 
 SD_OK = 0
-SD_ABI_VERSION = 4   # include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual; 4 = BAI writer
+SD_ABI_VERSION = 5   # include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual; 4 = BAI writer; 5 = sd_read_stats
 SD_F_REVERSE, SD_F_UNMAPPED, SD_F_SECONDARY, SD_F_SUPPLEMENTARY = 0x01, 0x02, 0x04, 0x08
 SD_F_HAS_MP, SD_F_SKIP, SD_F_NEWNAME, SD_F_PAD = 0x10, 0x20, 0x40, 0x80
 SD_REF_NONE = 0xFFFF
@@ -17,7 +17,8 @@ SD_MISMATCH_CIGAR, SD_MISMATCH_MP, SD_MISMATCH_VERIFY = 0, 1, 2
 SD_PARAM_MP_ANY_BASE = 1
 SD_TRACK_COVERAGE, SD_TRACK_COVERAGE_ON_BASE, SD_TRACK_CONVERSIONS, SD_TRACK_RATE = 0, 1, 2, 3
 SD_NCOUNTER = 5
-SD_DECODE_MP, SD_DECODE_GROUP, SD_DECODE_RAW_QUAL = 1, 2, 4
+SD_DECODE_MP, SD_DECODE_GROUP, SD_DECODE_RAW_QUAL, SD_DECODE_MP_ALL = 1, 2, 4, 8
+SD_NRATE = 25
 SD_C_READS, SD_C_TCREADS, SD_C_MULTIMAP, SD_C_COV_ON_T, SD_C_CONV_ON_T = range(5)
 SD_NSTAT = 10
 (SD_S_MAPPED, SD_S_UNMAPPED, SD_S_FILTERED, SD_S_MQFILTERED, SD_S_IDFILTERED, SD_S_NMFILTERED,
@@ -83,6 +84,14 @@ class SynthTables(ctypes.Structure):
                 ("utr_end", ctypes.c_void_p), ("utr_strand", ctypes.c_void_p), ("utr_cum_weight", ctypes.c_void_p)]
 
 
+class StatsArgs(ctypes.Structure):
+    _fields_ = [("min_qual", ctypes.c_int32), ("conversion_threshold", ctypes.c_int32), ("strict", ctypes.c_int32),
+                ("max_read_length", ctypes.c_uint32), ("utr_norm", ctypes.c_uint32), ("d_order", ctypes.c_void_p),
+                ("d_rates", ctypes.c_void_p), ("d_readpos", ctypes.c_void_p), ("d_utr_rates", ctypes.c_void_p),
+                ("d_utr_snp", ctypes.c_void_p), ("d_utrpos", ctypes.c_void_p), ("d_pairs", ctypes.c_void_p),
+                ("pair_capacity", ctypes.c_uint64), ("d_n_pairs", ctypes.c_void_p)]
+
+
 SD_SYNTH_MAX_TRIPLES = 40
 
 # name -> (restype, argtypes); every symbol declared in include/slamdunk_b200.h
@@ -126,6 +135,7 @@ PROTOTYPES = {
                                           _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_uint64]),
     "sd_track_runs": (ctypes.c_int, [_VP, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, _VP, _VP, _VP, ctypes.c_uint64, c_u64p]),
     "sd_write_track": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint64, _VP, _VP, _VP]),
+    "sd_read_stats": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(StatsArgs)]),
     "sd_synth_positions": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP, _VP]),
     "sd_synth_plan": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP, _VP, c_u64p]),
     "sd_synth_fill": (ctypes.c_int, [_VP, ctypes.POINTER(SynthParams), ctypes.POINTER(SynthTables), _VP,

@@ -1053,8 +1053,8 @@ static void free_utr_tables(sd_ctx *ctx) {
         ctx->d_seg_start[s] = ctx->d_seg_end[s] = nullptr;
         ctx->d_seg_off[s] = nullptr;
     }
-    cudaFree(ctx->d_row_gstart); cudaFree(ctx->d_row_gend); cudaFree(ctx->d_row_strand);
-    ctx->d_row_gstart = ctx->d_row_gend = nullptr;
+    cudaFree(ctx->d_row_gstart); cudaFree(ctx->d_row_gend); cudaFree(ctx->d_row_strand); cudaFree(ctx->d_row_blen);
+    ctx->d_row_gstart = ctx->d_row_gend = ctx->d_row_blen = nullptr;
     ctx->d_row_strand = nullptr;
 }
 
@@ -1147,11 +1147,13 @@ extern "C" int sd_set_utrs(sd_ctx *ctx, const uint32_t *h_chrom, const int64_t *
     ctx->row_pos_len.assign(n_utr, 0);
     std::vector<uint32_t> row_gs(n_utr, 0), row_ge(n_utr, 0);
     std::vector<uint8_t> row_st(n_utr, 0);
+    std::vector<uint32_t> row_bl(n_utr, 0);
     struct Ent { uint32_t gs, ge, row; };
     std::vector<Ent> ent[2];
     for (uint32_t i = 0; i < n_utr; i++) {
-        const int s = h_strand[i] ? 1 : 0;
-        row_st[i] = (uint8_t)s;
+        const int s = h_strand[i] == 1 ? 1 : 0;
+        row_st[i] = h_strand[i] > 1 ? (uint8_t)2 : (uint8_t)s;   // 2: unstranded row, joins reads of both strands (sd_read_stats only)
+        row_bl[i] = h_stop[i] > h_start[i] ? (uint32_t)std::min<int64_t>(h_stop[i] - h_start[i], 0xFFFFFFFFll) : 0u;
         if (h_chrom[i] >= ctx->n_chrom) continue;
         const int64_t clen = ctx->chrom_len[h_chrom[i]];
         int64_t a = h_start[i] < 0 ? 0 : h_start[i];
@@ -1163,6 +1165,7 @@ extern "C" int sd_set_utrs(sd_ctx *ctx, const uint32_t *h_chrom, const int64_t *
         ctx->row_pos_len[i] = (uint32_t)(b - a);
         if (h_in_bam && !h_in_bam[i]) continue;
         ent[s].push_back({row_gs[i], row_ge[i], i});
+        if (h_strand[i] > 1) ent[1].push_back({row_gs[i], row_ge[i], i});
     }
     const uint64_t total_bits = ctx->n_words * 32ull;
     ctx->n_bins = (uint32_t)((total_bits >> SD_BIN_SHIFT) + 2);
@@ -1224,6 +1227,7 @@ extern "C" int sd_set_utrs(sd_ctx *ctx, const uint32_t *h_chrom, const int64_t *
     if ((rc = upload(ctx, &ctx->d_row_gstart, row_gs))) return rc;
     if ((rc = upload(ctx, &ctx->d_row_gend, row_ge))) return rc;
     if ((rc = upload(ctx, &ctx->d_row_strand, row_st))) return rc;
+    if ((rc = upload(ctx, &ctx->d_row_blen, row_bl))) return rc;
     ctx->row_gstart = row_gs;
     ctx->row_strand = row_st;
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

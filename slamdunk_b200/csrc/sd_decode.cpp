@@ -268,6 +268,28 @@ bool mp_for_each(const char *s, int want, F f) {
     return true;
 }
 
+// Every entry: f(conv, readPos-1, refPos-1).
+template <class F>
+bool mp_for_all(const char *s, F f) {
+    while (*s) {
+        long v[3];
+        for (int k = 0; k < 3; k++) {
+            char *e;
+            v[k] = strtol(s, &e, 10);
+            if (e == s) return false;
+            s = e;
+            if (k < 2) {
+                if (*s != ':') return false;
+                s++;
+            }
+        }
+        f(v[0], v[1] - 1, v[2] - 1);
+        if (*s == ',') s++;
+        else if (*s) return false;
+    }
+    return true;
+}
+
 struct SliceLut {
     uint32_t v[256];
     SliceLut() {
@@ -487,7 +509,9 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
                              uint32_t tile_reads, int threads, sd_hbatch **out, char *err, int errlen) {
     if (!path || !out) return fail(err, errlen, SD_ERR_ARG, "sd_decode_bam: null argument");
     *out = nullptr;
-    const bool want_mp = (options & SD_DECODE_MP) != 0, group = (options & SD_DECODE_GROUP) != 0;
+    const bool mp_all = (options & SD_DECODE_MP_ALL) != 0;   // every MP entry, two words each (sd_read_stats)
+    const bool want_mp = (options & SD_DECODE_MP) != 0 || mp_all, group = (options & SD_DECODE_GROUP) != 0;
+    const uint64_t mp_entry_bytes = mp_all ? 8 : 4;
     const bool raw_qual = (options & SD_DECODE_RAW_QUAL) != 0;
     if (tile_reads != 0 && tile_reads != 32) return fail(err, errlen, SD_ERR_ARG, "tile_reads must be 32 (or 0 = default)");
     tile_reads = 32;
@@ -612,12 +636,18 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         if (newname) f |= SD_F_NEWNAME;
         uint32_t nmp = 0;
         if (want_mp && a.has_mp) {
-            bool range_ok = true;
-            if (!mp_for_each(a.mp, (flag & 0x10) ? 2 : 16, [&](long rp, long fp) {
+            bool range_ok = true, ok;
+            if (mp_all)
+                ok = mp_for_all(a.mp, [&](long conv, long rp, long fp) {
+                    nmp++;
+                    if (rp < 0 || rp > 65535 || fp < 0 || fp > 65535 || conv < 0 || conv > 24) range_ok = false;
+                });
+            else
+                ok = mp_for_each(a.mp, (flag & 0x10) ? 2 : 16, [&](long rp, long fp) {
                     nmp++;
                     if (rp < 0 || rp > 65535 || fp < 0 || fp > 65535) range_ok = false;
-                }))
-                { fmt_err = 1; return; }
+                });
+            if (!ok) { fmt_err = 1; return; }
             if (!range_ok || nmp > 65535) { limit_err = 1; return; }
             mp_ptr[i] = a.mp;
         }
@@ -718,7 +748,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
                 tile_lseq = std::max(tile_lseq, ls);
                 bq += ls;
                 bc += 4ull * (rec[i].lseq_ncig >> 16);
-                bm += 4ull * (rec[i].nm_nmp >> 16);
+                bm += mp_entry_bytes * (rec[i].nm_nmp >> 16);
             }
             bs = 16ull * tile_reads * ((tile_lseq + 31u) >> 5);   // group-major: every row slot of the tile, longest read's groups
             bq = up16(bq); bc = up16(bc); bm = up16(bm);
@@ -800,7 +830,13 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
                 }
                 memcpy(ps + 16 * ((size_t)g * tile_reads + (k - t * (size_t)tile_reads)), pl, 16);
             }
-            if (pm && mp_ptr[i]) {
+            if (pm && mp_ptr[i] && mp_all) {
+                mp_for_all(mp_ptr[i], [&](long conv, long rp, long fp) {
+                    const uint32_t v[2] = {(uint32_t)rp | ((uint32_t)fp << 16), (uint32_t)conv};
+                    memcpy(pm, v, 8);
+                    pm += 8;
+                });
+            } else if (pm && mp_ptr[i]) {
                 mp_for_each(mp_ptr[i], (flag & 0x10) ? 2 : 16, [&](long rp, long fp) {
                     const uint32_t v = (uint32_t)rp | ((uint32_t)fp << 16);
                     memcpy(pm, &v, 4);

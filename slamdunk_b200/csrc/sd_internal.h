@@ -46,6 +46,7 @@ struct sd_ctx {
     // all BED rows (for Tcontent and host layout)
     uint32_t *d_row_gstart = nullptr, *d_row_gend = nullptr;
     uint8_t *d_row_strand = nullptr;
+    uint32_t *d_row_blen = nullptr;     // BED stop - start per row, not clipped (utr.getLength(); sd_read_stats)
     std::vector<uint64_t> row_pos_off;
     std::vector<uint32_t> row_pos_len;
     std::vector<uint32_t> row_gstart;   // host copies of d_row_gstart / d_row_strand

@@ -21,7 +21,7 @@ from .. import parallel
 from ..engine import CountEngine, HostBatch, HostGenome, make_params
 from ..utils.bed import BedIterator
 from ..utils.snpmask import build_snp_masks
-from ..utils.samheader import SlamSeqInfo, getSampleInfo, md5, parse_sam_header
+from ..utils.samheader import SlamSeqInfo, getSampleInfo, md5, parse_sam_header, replaceExtension
 from ..version import __bam_version__, __count_version__, __version__
 
 HEADER = "\t".join(["Chromosome", "Start", "End", "Name", "Length", "Strand", "ConversionRate", "ReadsCPM", "Tcontent",
@@ -72,8 +72,6 @@ def _genome(ref):
 
 def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputCSV, outputBedgraphPlus,
                         outputBedgraphMinus, conversionThreshold, log, mle=False):
-    if mle:
-        raise NotImplementedError("mle=True (per-read output + R MLE fit) is not part of the GPU count path")
     tm = CountTimings()
     t0 = time.time()
     # multi-GPU: when the caller joined a process group (parallel.init / torchrun), every rank counts a slice of
@@ -103,6 +101,13 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
           sampleInfo.Type, sampleInfo.Time, sep="\t", file=fileCSV)
     print("#annotation:", os.path.basename(bed), bedMD5, sep="\t", file=fileCSV)
     print(HEADER, file=fileCSV)
+    fileTest = None
+    if mle:                                                  # tcounter.py:137-143
+        fileTest = open(os.devnull if rank != 0 else replaceExtension(outputCSV, ".tsv", "_perread"), "w")
+        print("#slamdunk v" + __version__, __count_version__, "sample info:", sampleInfo.Name, sampleInfo.ID,
+              sampleInfo.Type, sampleInfo.Time, sep="\t", file=fileTest)
+        print("#annotation:", os.path.basename(bed), bedMD5, sep="\t", file=fileTest)
+        print(HEADER, file=fileTest)
 
     tc_mask, ag_mask = build_snp_masks(snpsFile, genome.names, genome.chrom_off, genome.chrom_len, genome.n_words,
                                        warn=print)          # SNPtools.py:40-51
@@ -179,6 +184,20 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
     t3 = time.time()
     counters = res["counters"]
     tcontent = res["tcontent"]
+    pair_lo = pair_hi = pairs = None
+    if mle:
+        # the tInReads / tcInRead lists (tcounter.py:233-243) need every mismatch of a read, not only its conversions:
+        # a second scan (sd_read_stats) over the BAM decoded with all MP entries, one (read, UTR) pair per list element
+        from . import stats as _stats
+        rs = _stats.ReadStats(ref, bam, snpsFile=snpsFile, bed=None)
+        rs.utrs, rs.has_bed = utrs, True
+        try:
+            pairs = rs.run(minQual, conversion_threshold=conversionThreshold, strict=True, want=("pairs",),
+                           pair_capacity=2 * hbatch.n_reads + 1024)["pairs"]
+        finally:
+            rs.close()
+        pair_lo = np.searchsorted(pairs["row"], np.arange(n), side="left")
+        pair_hi = np.searchsorted(pairs["row"], np.arange(n), side="right")
     for i, utr in enumerate(utrs):
         readCount = int(counters[i, L.SD_C_READS])
         Tcontent = int(tcontent[i])
@@ -193,13 +212,24 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
                 conversionRate = float(conversionsOnTs) / float(coverageOnTs)
             print(_row(utr, conversionRate, readsCPM, Tcontent, coverageOnTs, conversionsOnTs, readCount,
                        int(counters[i, L.SD_C_TCREADS]), int(counters[i, L.SD_C_MULTIMAP])), file=fileCSV)
+            if mle:                                          # tcounter.py:305: the two lists in the ReadCount / TcReadCount columns
+                p = pairs[pair_lo[i]:pair_hi[i]]
+                print(_row(utr, conversionRate, readsCPM, Tcontent, coverageOnTs, conversionsOnTs,
+                           ",".join(str(int(x)) for x in p["t_count"]), ",".join(str(int(x)) for x in p["tc_count"]),
+                           int(counters[i, L.SD_C_MULTIMAP])), file=fileTest)
         else:
             print(_row(utr, 0, 0, Tcontent, 0, 0, 0, 0, 0), file=fileCSV)
+            if mle:                                          # tcounter.py:168: the default MLE row never gets its Tcontent
+                print(_row(utr, 0, 0, 0, 0, 0, 0, 0, 0), file=fileTest)
     fileCSV.close()
+    if mle:
+        fileTest.close()
     if pending_error is not None:
         raise pending_error
 
     _write_bedgraphs(utrs, chrom_idx, genome, res, pos_off, pos_len, counters, outputBedgraphPlus, outputBedgraphMinus)
+    if mle:                                                  # tcounter.py:328-330 shells out to an R script that is not part of this package
+        print("R plotters are not part of slamdunk_b200: the MLE fit over " + replaceExtension(outputCSV, ".tsv", "_perread") + " was not run.", file=log)
     tm["write_s"] = time.time() - t3
     tm["total_s"] = time.time() - t0
     OPTIONS["timings"] = tm

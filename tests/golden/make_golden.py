@@ -15,6 +15,8 @@ filt_* mapper-order BAMs through the reference's filter.Filter (default and mult
        retention modes); expected = DS counters + the written records.
 case_*/positional   the same inputs through tcounter.genomewideConversionRates (alleyoop positional-tracks):
        the eight run-length bedGraphs (python tests/golden/make_golden.py positional regenerates only these).
+case_*/stats        dunks/stats.py's iterator-based tools (alleyoop rates, utrrates, tcperreadpos, tcperutrpos, snpeval; the two
+       with -m also as *_strict) and the _perread.tsv of computeTconversions(mle=True) (`... make_golden.py stats`).
 case_*/readsep      tcounter.genomewideReadSeparation (alleyoop read-separator) on the case's BAM plus same-name
        secondary copies; expected = the records of the two BAMs it writes (`... make_golden.py readsep`).
 """
@@ -202,9 +204,41 @@ def make_readsep(name, min_qual, conv_threshold):
     print(name, "readsep tc", len(exp["tc"]), "background", len(exp["background"]))
 
 
+# the iterator-based alleyoop statistics (dunks/stats.py) and the mle per-read lists of `count` on the count cases' inputs,
+# with each case's own min_qual / max_read_length / conversion threshold (tests/goldens.py StatsCase)
+STATS = ["case_a", "case_b", "case_d", "case_e"]
+STATS_RUNS = [("rates", False), ("utrrates", False), ("utrrates", True), ("tcperreadpos", False), ("tcperutrpos", False),
+              ("snpeval", False), ("snpeval", True)]
+
+
+def make_stats(name):
+    d = os.path.join(HERE, name)
+    out = os.path.join(d, "stats")
+    if os.path.isdir(out):
+        shutil.rmtree(out)
+    os.makedirs(out)
+    p = json.load(open(os.path.join(d, "params.json")))["count"]
+    ref, bam, bed = os.path.join(d, name + ".fa"), os.path.join(d, name + ".bam"), os.path.join(d, name + ".bed")
+    vcf = os.path.join(d, name + ".vcf") if p["vcf"] else None
+    for tool, strict in STATS_RUNS:
+        csv = os.path.join(out, tool + ("_strict" if strict else "") + ".csv")
+        refrun.run_stats(tool, csv, ref, bam, bed=bed, vcf=vcf, min_qual=p["min_qual"], max_read_length=p["max_read_length"], strict=strict)
+    tmp = os.path.join(out, "tmp")
+    perread = refrun.run_count_mle(ref, bed, vcf, bam, tmp, p["max_read_length"], p["min_qual"], p["conv_threshold"])
+    os.rename(perread, os.path.join(out, "tcount_perread.tsv"))
+    for f in os.listdir(out):
+        if f.startswith("tmp"):
+            os.remove(os.path.join(out, f))
+    print(name, "stats files", sorted(os.listdir(out)))
+
+
 def main():
     if not refrun.available():
         sys.exit("reference tree not found; goldens can only be regenerated in the build container")
+    if sys.argv[1:] == ["stats"]:
+        for name in STATS:
+            make_stats(name)
+        return
     if sys.argv[1:] == ["positional"]:
         for name, args in POSITIONAL.items():
             make_positional(name, *args)
@@ -222,6 +256,8 @@ def main():
         make_positional(name, *args)
     for name, args in READSEP.items():
         make_readsep(name, *args)
+    for name in STATS:
+        make_stats(name)
 
 
 if __name__ == "__main__":

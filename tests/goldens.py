@@ -74,3 +74,26 @@ class ReadSepCase:
 
 
 READSEP_CASES = ["case_a", "case_b", "case_e"]
+
+
+class StatsCase:
+    """alleyoop rates / utrrates / tcperreadpos / tcperutrpos / snpeval and the mle per-read lists on a count case's inputs
+    (tests/golden/<case>/stats, written by the unmodified reference)."""
+    RUNS = [("rates", False), ("utrrates", False), ("utrrates", True), ("tcperreadpos", False), ("tcperutrpos", False),
+            ("snpeval", False), ("snpeval", True)]
+
+    def __init__(self, name):
+        c = CountCase(name)
+        self.name, self.ref, self.vcf, self.bam, self.bed = name, c.ref, c.vcf, c.bam, c.bed
+        self.max_read_length, self.min_qual, self.conv_threshold = c.max_read_length, c.min_qual, c.conv_threshold
+        self.dir = os.path.join(c.dir, "stats")
+
+    def expected(self, tool, strict=False):
+        return os.path.join(self.dir, tool + ("_strict" if strict else "") + ".csv")
+
+    @property
+    def perread(self):
+        return os.path.join(self.dir, "tcount_perread.tsv")
+
+
+STATS_CASES = ["case_a", "case_b", "case_d", "case_e"]

@@ -85,3 +85,52 @@ def run_read_separator(ref, vcf, bam, out_prefix, min_qual=27, conv_threshold=1)
     log = io.StringIO()
     tcounter.genomewideReadSeparation(ref, vcf, bam, min_qual, out_prefix, conv_threshold, log)
     return log.getvalue()
+
+
+def stats_module():
+    """the reference's dunks/stats.py, imported verbatim; its R plot calls (callR) are switched off -- no Rscript here,
+    and the plots are not arithmetic."""
+    if not available():
+        raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
+    _prepare()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from slamdunk.dunks import stats
+    stats.callR = lambda *a, **k: None
+    return stats
+
+
+def run_stats(tool, out_csv, ref, bam, bed=None, vcf=None, min_qual=27, max_read_length=100, strict=False):
+    """One of the reference's iterator-based alleyoop statistics -> log text; the CSV is written to out_csv.
+    tool: rates | utrrates | tcperreadpos | tcperutrpos | snpeval"""
+    import warnings
+    stats = stats_module()
+    log = io.StringIO()
+    pdf = out_csv + ".pdf"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if tool == "rates":
+            stats.statsComputeOverallRates(ref, bam, min_qual, out_csv, pdf, log)
+        elif tool == "utrrates":
+            stats.statsComputeOverallRatesPerUTR(ref, bam, min_qual, strict, out_csv, pdf, bed, max_read_length, log)
+        elif tool == "tcperreadpos":
+            stats.tcPerReadPos(ref, bam, min_qual, max_read_length, out_csv, pdf, vcf, log)
+        elif tool == "tcperutrpos":
+            stats.tcPerUtr(ref, bed, bam, min_qual, max_read_length, out_csv, pdf, vcf, log, False, True, True)
+        elif tool == "snpeval":
+            stats.computeSNPMaskedRates(ref, bed, vcf, bam, max_read_length, min_qual, 10, 0.8, out_csv, pdf, strict, log)
+        else:
+            raise KeyError(tool)
+    return log.getvalue()
+
+
+def run_count_mle(ref, bed, vcf, bam, out_prefix, max_read_length=100, min_qual=27, conv_threshold=1):
+    """reference computeTconversions(mle=True) with the R fit switched off -> path of the _perread.tsv it wrote"""
+    tcounter, _ = reference_modules()
+    tcounter.callR = lambda *a, **k: None
+    tsv = out_prefix + "_tcount.tsv"
+    log = io.StringIO()
+    tcounter.computeTconversions(ref, bed, vcf, bam, max_read_length, min_qual, tsv, out_prefix + "_plus.bedgraph",
+                                 out_prefix + "_mins.bedgraph", conv_threshold, log, True)
+    return out_prefix + "_tcount_perread.tsv"

@@ -1,0 +1,106 @@
+"""The iterator-based alleyoop statistics (rates, utrrates, tcperreadpos, tcperutrpos, snpeval) and the mle per-read
+lists of `count` on the GPU (slamdunk_b200/dunks/stats.py over sd_read_stats) against the reference's outputs
+(tests/golden/<case>/stats) and the oracle restatement (oracle/stats_oracle.py).  Everything is integer: byte-identical
+files."""
+import io
+import os
+
+import pytest
+
+import goldens
+import simdata
+import statsrun
+from oracle import stats_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _read(p):
+    with open(p) as fh:
+        return fh.read()
+
+
+@pytest.mark.parametrize("name", goldens.STATS_CASES)
+def test_stats_match_reference_golden(name, tmp_path):
+    c = goldens.StatsCase(name)
+    for tool, strict in goldens.StatsCase.RUNS:
+        out = str(tmp_path / (tool + str(strict) + ".csv"))
+        log = statsrun.run_gpu(tool, out, c.ref, c.bam, c.bed, c.vcf, c.min_qual, c.max_read_length, strict)
+        assert _read(out) == _read(c.expected(tool, strict)), (tool, strict)
+        assert "not written" in log and not os.path.exists(out + ".pdf")
+
+
+@pytest.mark.parametrize("name", goldens.STATS_CASES)
+def test_mle_perread_lists_match_reference_golden(name, tmp_path):
+    """computeTconversions(mle=True): the _perread.tsv next to the tcount file (tcounter.py:137-143, 233-243, 305-309)"""
+    from slamdunk_b200.dunks import tcounter
+    c = goldens.StatsCase(name)
+    cc = goldens.CountCase(name)
+    out = str(tmp_path / "x_tcount.tsv")
+    tcounter.computeTconversions(c.ref, c.bed, c.vcf, c.bam, c.max_read_length, c.min_qual, out, str(tmp_path / "p"), str(tmp_path / "m"),
+                                 c.conv_threshold, io.StringIO(), True)
+    assert _read(out) == _read(cc.tsv)
+    assert _read(str(tmp_path / "x_tcount_perread.tsv")) == _read(c.perread)
+
+
+@pytest.mark.parametrize("seed,q,maxlen,read_len,n_reads", [(95, 27, 100, (40, 100), 6000), (96, 0, 60, (30, 80), 4000),
+                                                            (97, 20, 300, (200, 300), 3000)])
+def test_stats_match_oracle_on_random_data(seed, q, maxlen, read_len, n_reads, tmp_path):
+    """rows without a strand, UTRs past the chromosome end / on chromosomes missing from FASTA or BAM, reads longer than
+    maxReadLength, SNPs incl. key collisions, several tiles"""
+    c = simdata.make_case(str(tmp_path), seed=seed, n_reads=n_reads, n_utr=40, complexity=2.0, snp_density=0.02, read_len=read_len)
+    bed = str(tmp_path / "mixed.bed")
+    statsrun.unstrand_some_rows(c.bed, bed)
+    for tool, strict in goldens.StatsCase.RUNS:
+        use_bed = c.bed if tool == "snpeval" else bed
+        g, o = str(tmp_path / (tool + str(strict) + "_g.csv")), str(tmp_path / (tool + str(strict) + "_o.csv"))
+        statsrun.run_gpu(tool, g, c.ref, c.bam, use_bed, c.vcf, q, maxlen, strict)
+        statsrun.run_oracle(tool, o, c.ref, c.bam, use_bed, c.vcf, q, maxlen, strict)
+        assert _read(g) == _read(o), (tool, strict)
+
+
+@pytest.mark.parametrize("thr", [1, 2])
+def test_mle_perread_lists_match_oracle_on_random_data(thr, tmp_path):
+    from slamdunk_b200.dunks import tcounter
+    c = simdata.make_case(str(tmp_path), seed=98, n_reads=5000, n_utr=40, complexity=2.0, snp_density=0.02, p_conv=0.05)
+    out = str(tmp_path / "x_tcount.tsv")
+    tcounter.computeTconversions(c.ref, c.bed, c.vcf, c.bam, 100, 27, out, str(tmp_path / "p"), str(tmp_path / "m"), thr, io.StringIO(), True)
+    lists = stats_oracle.perread_lists(c.ref, c.bed, c.vcf, c.bam, 100, 27, thr)
+    cols = statsrun.perread_columns(str(tmp_path / "x_tcount_perread.tsv"))
+    assert len(cols) == len(lists) > 0
+    for (n_txt, k_txt), (n_list, k_list) in zip(cols, lists):
+        if n_list:
+            assert n_txt == ",".join(map(str, n_list)) and k_txt == ",".join(map(str, k_list))
+        else:
+            assert (n_txt, k_txt) == ("0", "0")
+
+
+def test_snpeval_stops_at_a_row_without_strand(tmp_path):
+    """stats.py:791-792: rows before the bad one are written, then RuntimeError"""
+    c = simdata.make_case(str(tmp_path), seed=99, n_reads=800, n_utr=12)
+    bed = str(tmp_path / "mixed.bed")
+    statsrun.unstrand_some_rows(c.bed, bed, every=6)     # row 1 loses its strand
+    out = str(tmp_path / "s.csv")
+    with pytest.raises(RuntimeError, match="stranded"):
+        statsrun.run_gpu("snpeval", out, c.ref, c.bam, bed, c.vcf, 27, 100, False)
+    assert len(_read(out).splitlines()) == 1
+
+
+def test_stats_cli(tmp_path):
+    """python -m slamdunk_b200.alleyoop rates / tcperreadpos / utrrates / tcperutrpos / snpeval: file names of alleyoop.py:147-262"""
+    from slamdunk_b200 import alleyoop
+    c = goldens.StatsCase("case_a")
+    out = str(tmp_path / "out")
+    snpdir = str(tmp_path / "snp")
+    os.makedirs(snpdir)
+    base = os.path.splitext(os.path.basename(c.bam))[0]
+    os.symlink(c.vcf, os.path.join(snpdir, base + "_snp.vcf"))
+    q, L = str(c.min_qual), str(c.max_read_length)
+    alleyoop.run(["rates", "-o", out, "-r", c.ref, "-mq", q, c.bam])
+    alleyoop.run(["tcperreadpos", "-o", out, "-r", c.ref, "-s", snpdir, "-l", L, "-mq", q, c.bam])
+    alleyoop.run(["utrrates", "-o", out, "-r", c.ref, "-b", c.bed, "-l", L, "-mq", q, c.bam])
+    alleyoop.run(["tcperutrpos", "-o", out, "-r", c.ref, "-b", c.bed, "-s", snpdir, "-l", L, "-mq", q, c.bam])
+    alleyoop.run(["snpeval", "-o", out, "-r", c.ref, "-b", c.bed, "-s", snpdir, "-l", L, "-q", q, c.bam])
+    for suffix, tool in (("_overallrates", "rates"), ("_tcperreadpos", "tcperreadpos"), ("_mutationrates_utr", "utrrates"),
+                         ("_tcperutr", "tcperutrpos"), ("_SNPeval", "snpeval")):
+        assert _read(os.path.join(out, base + suffix + ".csv")) == _read(c.expected(tool)), tool

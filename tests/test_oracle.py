@@ -150,3 +150,45 @@ def test_oracle_read_separation_matches_golden(name):
     assert [key(recs[i]) for i in bgi] == c.expected["background"]
     names = [r.qname for r in recs]
     assert len(set(names)) < len(names)        # the case really has several alignments per name
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# iterator-based alleyoop statistics + mle per-read lists (oracle/stats_oracle.py)
+# ---------------------------------------------------------------------------------------------------------------
+import statsrun  # noqa: E402
+from oracle import stats_oracle  # noqa: E402
+
+
+@pytest.mark.parametrize("name", goldens.STATS_CASES)
+def test_stats_oracle_matches_reference_golden(name, tmp_path):
+    c = goldens.StatsCase(name)
+    for tool, strict in goldens.StatsCase.RUNS:
+        out = str(tmp_path / (tool + str(strict) + ".csv"))
+        statsrun.run_oracle(tool, out, c.ref, c.bam, c.bed, c.vcf, c.min_qual, c.max_read_length, strict)
+        assert _read(out) == _read(c.expected(tool, strict)), (tool, strict)
+    lists = stats_oracle.perread_lists(c.ref, c.bed, c.vcf, c.bam, c.max_read_length, c.min_qual, c.conv_threshold)
+    cols = statsrun.perread_columns(c.perread)
+    assert len(cols) == len(lists)
+    for (n_txt, k_txt), (n_list, k_list) in zip(cols, lists):
+        if n_list:
+            assert n_txt == ",".join(map(str, n_list)) and k_txt == ",".join(map(str, k_list))
+        else:
+            assert (n_txt, k_txt) in (("0", "0"), ("", ""))     # default row / a row whose reads are all antisense
+
+
+@pytest.mark.skipif(not refrun.available(), reason="reference tree not present")
+@pytest.mark.parametrize("seed,q,maxlen,read_len", [(91, 27, 100, (40, 100)), (92, 0, 60, (30, 80))])
+def test_stats_oracle_matches_live_reference(seed, q, maxlen, read_len, tmp_path):
+    """fresh seed, rows without a strand (both read strands join them), reads longer than maxReadLength"""
+    c = simdata.make_case(str(tmp_path), seed=seed, n_reads=1500, n_utr=30, complexity=2.0, snp_density=0.02, read_len=read_len)
+    bed = str(tmp_path / "mixed.bed")
+    statsrun.unstrand_some_rows(c.bed, bed)
+    for tool, strict in goldens.StatsCase.RUNS:
+        use_bed = c.bed if tool == "snpeval" else bed          # snpeval refuses rows without strand
+        r, o = str(tmp_path / "r.csv"), str(tmp_path / "o.csv")
+        for f in (r, o):
+            if os.path.exists(f):
+                os.remove(f)
+        refrun.run_stats(tool, r, c.ref, c.bam, bed=use_bed, vcf=c.vcf, min_qual=q, max_read_length=maxlen, strict=strict)
+        statsrun.run_oracle(tool, o, c.ref, c.bam, use_bed, c.vcf, q, maxlen, strict)
+        assert _read(r) == _read(o), (tool, strict)
