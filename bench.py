@@ -180,8 +180,8 @@ def workload_config(args, sample_reads=None):
                      "2.5%% T>C per reference T" % (args.reads, args.read_len, args.utrs, args.genome_bp / 1e6),
          "reads_per_gpu": args.reads, "read_len": args.read_len, "n_utr": args.utrs,
          "filter": "MQ>=2, identity>=0.95 (slamdunk defaults)", "min_base_qual": MIN_QUAL, "conversion_threshold": CONV_THRESHOLD,
-         "mismatch_source": "cigar_walk", "read_order": args.order, "sharding": "utr_owner_regions" if args.gpus > 1 else "none",
-         "l2_policy": "inputs (~%.1f GB per GPU) far exceed the 126 MB L2; no explicit flush" % (args.reads * 176.3 / 1e9)}
+         "mismatch_source": "cigar_walk", "read_order": args.order, "seq_bits": getattr(args, "seq_bits", 2), "sharding": "utr_owner_regions" if args.gpus > 1 else "none",
+         "l2_policy": "inputs (~%.1f GB per GPU) far exceed the 126 MB L2; no explicit flush" % (args.reads * (getattr(args, "seq_bits", 2) * 4 * ((args.read_len + 31) // 32) + args.read_len + 24.4) / 1e9)}
     if sample_reads is not None:
         c["sample_reads"] = sample_reads
     return c
@@ -222,6 +222,9 @@ def main():
     ap.add_argument("--order", default="sorted", choices=["sorted", "mapper"],
                     help="read order inside the batch: coordinate-sorted (what `slamdunk count` reads: the sorted BAM "
                          "written by `slamdunk filter`) or mapper order (random placement, the filter's input)")
+    ap.add_argument("--seq-bits", type=int, default=2, choices=[2, 4], dest="seq_bits",
+                    help="form of the SEQ column: 2 = 2-bit base codes, what sd_decode_bam hands the count path (default); "
+                         "4 = the four BAM-nibble bit-planes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -241,7 +244,7 @@ def main():
     import torch.distributed as dist
     from slamdunk_b200 import _lib as L
     from slamdunk_b200.engine import make_params
-    from slamdunk_b200.synth import algorithmic_bytes_per_read, batch_to_host, host_batch_bytes
+    from slamdunk_b200.synth import algorithmic_bytes_per_read, batch_to_host, host_batch_bytes, layout_bytes_per_read, to_seq2
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -251,6 +254,12 @@ def main():
                                     coordinate_sorted=(args.order == "sorted"))
     params = make_params(MIN_QUAL, CONV_THRESHOLD, L.SD_MISMATCH_CIGAR, **FILTER)
     n_reads = args.reads
+    if args.seq_bits == 2:
+        db4 = db
+        db = to_seq2(db4, eng)
+        db4.tensors["seq"] = None      # free the 4-plane column
+        del db4
+        torch.cuda.empty_cache()
 
     def step():
         eng.reset_outputs()
@@ -296,12 +305,15 @@ def main():
     tiles = db.tensors["tiles"].cpu().numpy().view(np.uint64).reshape(-1, 4)
     mean_cig = float(tiles[-1, 2]) / 4.0 / n_reads
     bytes_per_read = algorithmic_bytes_per_read(args.read_len, mean_cig)
+    layout_bytes = layout_bytes_per_read(args.read_len, mean_cig, args.seq_bits)
     k_ms = float(np.mean(kernel_ms))
     achieved = n_reads * bytes_per_read / (k_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_ncu_traffic(args), "kernel": "sd_count_kernel", "kernel_ms": k_ms,
-                "algorithmic_bytes_per_read": bytes_per_read, "peak_source": peak_src,
+                "algorithmic_bytes_per_read": bytes_per_read, "algorithmic_bytes_source": "SURVEY.md 8(d): ceil(L/2) + L + 4c + 17",
+                "layout_bytes_per_read": layout_bytes, "achieved_layout_bytes": n_reads * layout_bytes / (k_ms * 1e-3) / 1e9,
+                "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "kernel_share_of_step": k_ms / ms_per_step}
 
     # end to end: pinned host buffers -> sd_count_host -> counters back on the host
@@ -333,7 +345,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": world * n_reads / dt, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt * 1e3, "h2d_gbs": h2d / dt / 1e9, "host_qual_bits": int(hb.qual_bits)}
+               "ms_per_step": dt * 1e3, "h2d_gbs": h2d / dt / 1e9, "host_qual_bits": int(hb.qual_bits),
+               "host_seq_bits": int(hb.seq_bits) or 4}
         del hb, keep
 
     # CPU baseline + parity of the GPU counters with the oracle on a bounded sample (rank 0, N = 1)
@@ -383,7 +396,7 @@ def load_ncu_traffic(args):
     path = os.path.join(ROOT, "profiles", "count_kernel_dram.json")
     try:
         d = json.load(open(path))
-        if args.reads != d.get("reads_per_launch") or args.read_len != 100 or args.order != "sorted":
+        if args.reads != d.get("reads_per_launch") or args.read_len != 100 or args.order != "sorted" or args.seq_bits != d.get("seq_bits", 4):
             return None
         return d.get("dram_bytes_per_launch")
     except Exception:

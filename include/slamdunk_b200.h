@@ -119,6 +119,15 @@ typedef struct sd_batch {
                                way (Illumina's binned qualities), sd_count_host copies the codes and expands them on the
                                device -- a quarter of the column's PCIe bytes.  Tile qual offsets are always in bases. */
     uint8_t qual_dict[16];  /* code -> phred value */
+    uint32_t seq_bits;      /* form of the `seq` column: 0 or 4 = the four bit-planes described above (16 bytes per group);
+                               2 = two words per group, bit i of word 0 / word 1 = low / high bit of base 32g+i coded A=0 C=1
+                               G=2 T=3, group g of row r at byte 8 * (g * tile_reads + r) of the tile block.  A base that is
+                               not exactly one of A, C, G, T (N, IUPAC codes, '=') is coded A, and so are the pad bits: the
+                               count path only ever asks "is this base C" / "is it G" (SlamSeqFile.py:137-141), for which the
+                               2-bit form is lossless -- half the SEQ bytes in HBM and on PCIe.  Tile seq offsets are byte
+                               offsets into the column as stored.  sd_count* / sd_count_host take both forms;
+                               sd_read_stats (exact base counts) needs the 4-plane form. */
+    uint32_t reserved0;
 } sd_batch;
 
 /* Where the per-read mismatch list comes from. */
@@ -260,6 +269,7 @@ int sd_filter(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params, con
 #define SD_DECODE_MP 1
 #define SD_DECODE_GROUP 2
 #define SD_DECODE_RAW_QUAL 4   /* keep one byte per base quality even when the file has <= 16 distinct values */
+#define SD_DECODE_SEQ2 16      /* write the SEQ column in the 2-bit form (sd_batch.seq_bits = 2) -- for sd_count* only */
 #define SD_DECODE_MP_ALL 8     /* mp column holds EVERY MP entry, two words each: {readPos-1 | refPos-1 << 16, conv (0..24)} --
                                   the form sd_read_stats takes (sd_count cannot read it); implies SD_DECODE_MP */
 
@@ -311,6 +321,10 @@ void sd_hgenome_free(sd_hgenome *g);
  * d_packed needs n_bases * bits / 8 bytes (n_bases / 2 always suffices for a packable column). */
 int sd_qual_unpack(sd_ctx *ctx, const uint8_t *d_packed, uint64_t n_bases, uint32_t bits, const uint8_t *dict16, uint8_t *d_qual);
 int sd_qual_pack(sd_ctx *ctx, const uint8_t *d_qual, uint64_t n_bases, uint8_t *d_packed, uint32_t *bits, uint8_t *dict16);
+/* sd_seq_pack: the 2-bit form (sd_batch.seq_bits = 2) of a device-resident 4-plane SEQ column: d_seq2 receives half the
+ * column's bytes, d_tiles2 [n_tiles + 1] the tile table with the seq offsets of the new column (other offsets copied).
+ * What sd_decode_bam does with SD_DECODE_SEQ2, for batches that were made on the device.  Asynchronous. */
+int sd_seq_pack(sd_ctx *ctx, const sd_batch *d_batch, uint32_t *d_seq2, sd_tile *d_tiles2);
 
 /* ------------------------------------------------------------------ filtered BAM output (host, C++ threads + zlib)
  * Replaces pysam's outfile.write / dumpBufferToBam and `samtools sort` after the decisions of sd_filter

@@ -17,7 +17,7 @@ SD_MISMATCH_CIGAR, SD_MISMATCH_MP, SD_MISMATCH_VERIFY = 0, 1, 2
 SD_PARAM_MP_ANY_BASE = 1
 SD_TRACK_COVERAGE, SD_TRACK_COVERAGE_ON_BASE, SD_TRACK_CONVERSIONS, SD_TRACK_RATE = 0, 1, 2, 3
 SD_NCOUNTER = 5
-SD_DECODE_MP, SD_DECODE_GROUP, SD_DECODE_RAW_QUAL, SD_DECODE_MP_ALL = 1, 2, 4, 8
+SD_DECODE_MP, SD_DECODE_GROUP, SD_DECODE_RAW_QUAL, SD_DECODE_MP_ALL, SD_DECODE_SEQ2 = 1, 2, 4, 8, 16
 SD_NRATE = 25
 SD_C_READS, SD_C_TCREADS, SD_C_MULTIMAP, SD_C_COV_ON_T, SD_C_CONV_ON_T = range(5)
 SD_NSTAT = 10
@@ -46,7 +46,7 @@ class Batch(ctypes.Structure):
                 ("cigar", ctypes.c_void_p), ("mp", ctypes.c_void_p), ("tiles", ctypes.c_void_p),
                 ("max_lseq", ctypes.c_uint32), ("max_tile_seq", ctypes.c_uint32), ("max_tile_qual", ctypes.c_uint32),
                 ("max_tile_cig", ctypes.c_uint32), ("max_tile_mp", ctypes.c_uint32), ("max_span", ctypes.c_uint32), ("qual_bits", ctypes.c_uint32),
-                ("qual_dict", ctypes.c_uint8 * 16)]
+                ("qual_dict", ctypes.c_uint8 * 16), ("seq_bits", ctypes.c_uint32), ("reserved0", ctypes.c_uint32)]
 
 
 class Params(ctypes.Structure):
@@ -121,6 +121,7 @@ PROTOTYPES = {
                                       ctypes.c_int, ctypes.c_int, c_u64p, ctypes.c_char_p, ctypes.c_int]),
     "sd_qual_unpack": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64, ctypes.c_uint32, _VP, _VP]),
     "sd_qual_pack": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64, _VP, ctypes.POINTER(ctypes.c_uint32), _VP]),
+    "sd_seq_pack": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), _VP, _VP]),
     "sd_rewrite_bam_indexed": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, _VP, _VP, ctypes.c_uint64,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, c_u64p, ctypes.c_char_p, ctypes.c_int]),
     "sd_decode_bam": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint32, ctypes.c_int,
@@ -168,7 +169,7 @@ def load():
     if missing:
         raise RuntimeError("libslamdunk_b200.so is stale, it lacks %s; rebuild with `python -m slamdunk_b200.build`"
                            % ", ".join(missing))
-    assert ctypes.sizeof(ReadRec) == 20 and ctypes.sizeof(Tile) == 32
+    assert ctypes.sizeof(ReadRec) == 20 and ctypes.sizeof(Tile) == 32 and ctypes.sizeof(Batch) == 120
     if L.sd_abi_version() != SD_ABI_VERSION:
         raise RuntimeError("libslamdunk_b200.so has ABI version %d, these bindings expect %d; rebuild with `python -m slamdunk_b200.build`"
                            % (L.sd_abi_version(), SD_ABI_VERSION))

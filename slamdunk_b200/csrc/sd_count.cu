@@ -87,6 +87,7 @@ struct CountArgs {
     const sd_tile *tiles;
     uint32_t n_tiles;
     uint32_t tile_reads;
+    uint32_t seq2;            // the SEQ column holds 2-bit base codes (sd_batch.seq_bits == 2): two words per group
     // shared-memory stage layout (bytes, all multiples of 128)
     uint32_t cap_rec, cap_seq, cap_qual, cap_cig, cap_mp;
     uint32_t n_stages;
@@ -189,6 +190,18 @@ __device__ __forceinline__ uint32_t group_is_base(const uint4 p, uint32_t sm) {
     return f & ~p.x & ~p.w;                                          // one LOP3: neither A nor T
 }
 
+// The same for the 2-bit SEQ column (two words per group: low / high bit of the base code A=0 C=1 G=2 T=3): C is
+// lo & ~hi, G is hi & ~lo -- one LOP3.  Bases that are not one of ACGT are coded A there, pad bits too: never C or G.
+__device__ __forceinline__ uint32_t group_is_base2(const uint2 p, uint32_t sm) {
+    return ((p.x & ~p.y) & ~sm) | ((p.y & ~p.x) & sm);
+}
+// group g of the row whose slot of group 0 is `row` (group-major tile block in shared memory)
+template <int SB>
+__device__ __forceinline__ uint32_t row_group_is_base(const uint32_t *row, uint32_t g, uint32_t sm) {
+    if (SB == 2) return group_is_base2(reinterpret_cast<const uint2 *>(row)[g * SD_TILE_READS], sm);
+    return group_is_base(reinterpret_cast<const uint4 *>(row)[g * SD_TILE_READS], sm);
+}
+
 // @region slow_and_generic
 // Map a reference offset (relative to the alignment start) to the read index aligned to it.
 __device__ __forceinline__ int ref_to_read(const uint32_t *cig, uint32_t ncig, int o) {
@@ -253,7 +266,7 @@ __device__ __forceinline__ void slow_for_each_hit(const CountArgs &A, const Read
             for (int j = 0; j < len; j++) {
                 const int o = r + j, qi = q + j;
                 if (o >= v.span || qi >= (int)v.lseq) break;
-                const uint32_t isx = group_is_base(reinterpret_cast<const uint4 *>(v.seq)[(qi >> 5) * SD_TILE_READS], sm);
+                const uint32_t isx = A.seq2 ? row_group_is_base<2>(v.seq, (uint32_t)qi >> 5, sm) : row_group_is_base<4>(v.seq, (uint32_t)qi >> 5, sm);
                 if (!((isx >> (qi & 31)) & 1u)) continue;
                 const uint64_t gp = (uint64_t)v.g + (uint64_t)o;
                 const uint2 x = __ldg(&rx[gp >> 5]);
@@ -393,7 +406,7 @@ __device__ __forceinline__ int block_read_index(const Blocks &B, int o) {
 
 // SIMPLE: every read of the tile is one match block without clips (the decoder groups such reads into
 // their own tiles), so the read mask needs no placement and a window position is a read index.
-template <int W, bool SIMPLE>
+template <int W, bool SIMPLE, int SB>
 __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, const Blocks &B, uint32_t mapq,
                                          bool dense_tile, bool &mp_disagree) {
     const int s = v.strand;
@@ -440,13 +453,12 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
         uint32_t sm = 0u - (uint32_t)s;   // all ones on the minus strand
         asm volatile("" : "+r"(sm));      // keep it a mask operand of the LOP3s (not a predicate with selects)
         const uint32_t ng = (v.lseq + 31u) >> 5;
-        const uint4 *grp = reinterpret_cast<const uint4 *>(v.seq);   // this row's slot of group 0; the tile block is group-major
         uint32_t M[W];
 #pragma unroll
         for (int k = 0; k < W; k++) {
             // unconditional load of an existing group (index clamped), masked afterwards: no branch per group
             const uint32_t kc = ng ? min((uint32_t)k, ng - 1u) : 0u;
-            const uint32_t m = group_is_base(grp[kc * SD_TILE_READS], sm);
+            const uint32_t m = row_group_is_base<SB>(v.seq, kc, sm);   // this row's slot of group kc; the tile block is group-major
             M[k] = ((uint32_t)k < ng) ? m : 0u;
         }
         if (SIMPLE) {
@@ -717,7 +729,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #define SD_MIN_CTAS(W) ((W) <= 6 ? 4 : ((W) <= 10 ? 3 : 2))   // resident 256-thread CTAs per SM the register budget is tuned for
 #endif
 
-template <int W>
+template <int W, int SB>
 __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kernel(const __grid_constant__ CountArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
@@ -858,7 +870,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
             const uint32_t clen = __ldg(&A.chrom_len[ref]);
             if (pos >= 0 && (uint32_t)pos < clen) {
                 ReadView v;
-                v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + 4u * lane;
+                v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (SB == 2 ? 2u : 4u) * lane;
                 v.qual = A.qual + s_qoff[stage] + qs;
                 v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + cig_row;
                 v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
@@ -890,7 +902,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
                 my_counted++;
                 if (fits) {
                     bool bad = false;
-                    tc = uni_simple ? fast_read<W, true>(A, v, B, mapq, dense_tile, bad) : fast_read<W, false>(A, v, B, mapq, dense_tile, bad);
+                    tc = uni_simple ? fast_read<W, true, SB>(A, v, B, mapq, dense_tile, bad) : fast_read<W, false, SB>(A, v, B, mapq, dense_tile, bad);
                     if (bad) atomicAdd(&A.stats[SD_S_MP_DISAGREE], 1ull);   // rare: straight to the global counter
                 } else {
                     atomicAdd(&A.stats[SD_S_SLOWPATH], 1ull);
@@ -1271,7 +1283,7 @@ extern "C" int sd_bind_outputs(sd_ctx *ctx, int64_t *d_counters, int32_t *d_pos_
 static inline uint32_t align128(uint32_t x) { return (x + 127u) & ~127u; }
 static inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
-template <int W>
+template <int W, int SB>
 static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
     const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
     int max_smem = 0;
@@ -1297,8 +1309,8 @@ static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool tim
         while (warps > 1 && 128u + warps * warp_bytes(ns) > (size_t)max_smem) warps--;
         smem = 128u + warps * warp_bytes(ns);
         if (smem > (size_t)max_smem) { per_sm = 0; return SD_OK; }
-        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W>, (int)warps * 32, smem));
+        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W, SB>, (int)warps * 32, smem));
         return SD_OK;
     };
     uint32_t n_stages = 1, warps = 0;
@@ -1326,7 +1338,7 @@ static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool tim
     }
     if (per_sm < 1) return sd_fail(ctx, SD_ERR_LIMIT, "count kernel does not fit on an SM (smem %zu)", smem);
     if (last.device != ctx->device || last.stage_bytes != stage_bytes) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         last = {stage_bytes, ctx->device, n_stages, warps, smem, per_sm};
     }
     A.n_stages = n_stages;
@@ -1336,7 +1348,7 @@ static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool tim
     uint32_t grid = (uint32_t)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * per_sm);
     if (grid == 0) grid = 1;
     if (timed) SD_CUDA(ctx, cudaEventRecord(ctx->ev_k0, stream));
-    sd_count_kernel<W><<<grid, threads, smem, stream>>>(A);
+    sd_count_kernel<W, SB><<<grid, threads, smem, stream>>>(A);
     if (timed) {
         SD_CUDA(ctx, cudaEventRecord(ctx->ev_k1, stream));
         ctx->have_kernel_time = true;
@@ -1360,7 +1372,9 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     A.mp = (p->mismatch_source == SD_MISMATCH_CIGAR) ? nullptr : b->mp;
     A.tiles = b->tiles; A.n_tiles = b->n_tiles; A.tile_reads = b->tile_reads;
     A.cap_rec = align16(32u * (uint32_t)sizeof(sd_read_rec));
-    A.cap_seq = std::max(align16(b->max_tile_seq), 16u * SD_TILE_READS);   // at least one group per row: the kernel loads group 0 unconditionally
+    if (b->seq_bits != 0 && b->seq_bits != 4 && b->seq_bits != 2) return sd_fail(ctx, SD_ERR_ARG, "seq_bits must be 4 (or 0) or 2");
+    A.seq2 = b->seq_bits == 2 ? 1u : 0u;
+    A.cap_seq = std::max(align16(b->max_tile_seq), (A.seq2 ? 8u : 16u) * SD_TILE_READS);   // at least one group per row: the kernel loads group 0 unconditionally
     A.cap_qual = 0;  // the qual column is read in place (see the kernel's header comment)
     A.cap_cig = align16(b->max_tile_cig);
     A.cap_mp = A.mp ? align16(b->max_tile_mp) : 0;
@@ -1409,12 +1423,20 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     // with 2 % short indels in a 192-base window: 9.6 instead of 15 G reads/s).  The batch says how wide its alignments
     // are (spliced ones aside); without that, 16 bases of slack cover the usual gaps.
     const uint32_t need = b->max_span ? std::max(b->max_lseq, b->max_span) : b->max_lseq + 16u;
-    if (need <= 128) return launch_count<4>(ctx, A, stream, timed);
-    if (need <= 192) return launch_count<6>(ctx, A, stream, timed);
-    if (need <= 256) return launch_count<8>(ctx, A, stream, timed);
-    if (need <= 320) return launch_count<10>(ctx, A, stream, timed);
-    if (need <= 384) return launch_count<12>(ctx, A, stream, timed);
-    return launch_count<16>(ctx, A, stream, timed);
+    if (A.seq2) {
+        if (need <= 128) return launch_count<4, 2>(ctx, A, stream, timed);
+        if (need <= 192) return launch_count<6, 2>(ctx, A, stream, timed);
+        if (need <= 256) return launch_count<8, 2>(ctx, A, stream, timed);
+        if (need <= 320) return launch_count<10, 2>(ctx, A, stream, timed);
+        if (need <= 384) return launch_count<12, 2>(ctx, A, stream, timed);
+        return launch_count<16, 2>(ctx, A, stream, timed);
+    }
+    if (need <= 128) return launch_count<4, 4>(ctx, A, stream, timed);
+    if (need <= 192) return launch_count<6, 4>(ctx, A, stream, timed);
+    if (need <= 256) return launch_count<8, 4>(ctx, A, stream, timed);
+    if (need <= 320) return launch_count<10, 4>(ctx, A, stream, timed);
+    if (need <= 384) return launch_count<12, 4>(ctx, A, stream, timed);
+    return launch_count<16, 4>(ctx, A, stream, timed);
 }
 
 extern "C" int sd_count(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params) {

@@ -512,6 +512,9 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     const bool mp_all = (options & SD_DECODE_MP_ALL) != 0;   // every MP entry, two words each (sd_read_stats)
     const bool want_mp = (options & SD_DECODE_MP) != 0 || mp_all, group = (options & SD_DECODE_GROUP) != 0;
     const uint64_t mp_entry_bytes = mp_all ? 8 : 4;
+    const bool seq2 = (options & SD_DECODE_SEQ2) != 0;      // 2-bit SEQ column (count path only)
+    if (seq2 && mp_all) return fail(err, errlen, SD_ERR_ARG, "SD_DECODE_SEQ2 and SD_DECODE_MP_ALL exclude each other (sd_read_stats needs the 4-plane SEQ column)");
+    const uint64_t group_bytes = seq2 ? 8 : 16;
     const bool raw_qual = (options & SD_DECODE_RAW_QUAL) != 0;
     if (tile_reads != 0 && tile_reads != 32) return fail(err, errlen, SD_ERR_ARG, "tile_reads must be 32 (or 0 = default)");
     tile_reads = 32;
@@ -750,7 +753,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
                 bc += 4ull * (rec[i].lseq_ncig >> 16);
                 bm += mp_entry_bytes * (rec[i].nm_nmp >> 16);
             }
-            bs = 16ull * tile_reads * ((tile_lseq + 31u) >> 5);   // group-major: every row slot of the tile, longest read's groups
+            bs = group_bytes * tile_reads * ((tile_lseq + 31u) >> 5);   // group-major: every row slot of the tile, longest read's groups
             bq = up16(bq); bc = up16(bc); bm = up16(bm);
             mt_seq = std::max<uint32_t>(mt_seq, (uint32_t)bs);
             mt_qual = std::max<uint32_t>(mt_qual, (uint32_t)bq);
@@ -828,7 +831,13 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
                     pl[2] |= ((v >> 16) & 3u) << (2 * j);
                     pl[3] |= ((v >> 24) & 3u) << (2 * j);
                 }
-                memcpy(ps + 16 * ((size_t)g * tile_reads + (k - t * (size_t)tile_reads)), pl, 16);
+                if (seq2) {   // A=0 C=1 G=2 T=3, anything else A
+                    const uint32_t onlyC = ~pl[0] & pl[1] & ~pl[2] & ~pl[3], onlyG = ~pl[0] & ~pl[1] & pl[2] & ~pl[3],
+                                   onlyT = ~pl[0] & ~pl[1] & ~pl[2] & pl[3];
+                    const uint32_t two[2] = {onlyC | onlyT, onlyG | onlyT};
+                    memcpy(ps + 8 * ((size_t)g * tile_reads + (k - t * (size_t)tile_reads)), two, 8);
+                } else
+                    memcpy(ps + 16 * ((size_t)g * tile_reads + (k - t * (size_t)tile_reads)), pl, 16);
             }
             if (pm && mp_ptr[i] && mp_all) {
                 mp_for_all(mp_ptr[i], [&](long conv, long rp, long fp) {
@@ -869,6 +878,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     hb->batch.max_tile_mp = mt_mp;
     hb->batch.max_span = max_span.load();
     hb->batch.qual_bits = qual_bits;
+    hb->batch.seq_bits = seq2 ? 2 : 4;
     memcpy(hb->batch.qual_dict, qual_dict, 16);
     hb->name_hash = name_hash;
     hb->order = order;

@@ -132,3 +132,42 @@ extern "C" int sd_qual_pack(sd_ctx *ctx, const uint8_t *d_qual, uint64_t n_bases
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SD_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2-bit form of the SEQ column (sd_batch.seq_bits = 2): the count path only asks "is this base C / G", so A=0 C=1 G=2 T=3
+// with everything else coded A is lossless for it and halves the column.
+namespace {
+__global__ void seq_pack_kernel(const uint4 *seq4, uint64_t n_groups, uint2 *seq2) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_groups) return;
+    const uint4 p = seq4[i];
+    const uint32_t onlyC = ~p.x & p.y & ~p.z & ~p.w, onlyG = ~p.x & ~p.y & p.z & ~p.w, onlyT = ~p.x & ~p.y & ~p.z & p.w;
+    seq2[i] = make_uint2(onlyC | onlyT, onlyG | onlyT);
+}
+__global__ void tiles_seq2_kernel(const sd_tile *in, uint32_t n, sd_tile *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sd_tile t = in[i];
+    t.seq_off >>= 1;
+    out[i] = t;
+}
+}  // namespace
+
+extern "C" int sd_seq_pack(sd_ctx *ctx, const sd_batch *b, uint32_t *d_seq2, sd_tile *d_tiles2) {
+    if (!ctx || !b || !d_seq2 || !d_tiles2) return sd_fail(ctx, SD_ERR_ARG, "sd_seq_pack: null argument");
+    if (b->seq_bits != 0 && b->seq_bits != 4) return sd_fail(ctx, SD_ERR_ARG, "sd_seq_pack: the column is not in the 4-plane form");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    sd_tile last;
+    SD_CUDA(ctx, cudaMemcpyAsync(&last, b->tiles + b->n_tiles, sizeof last, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t n_groups = last.seq_off / 16;
+    if (n_groups) {
+        seq_pack_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(b->seq), n_groups,
+                                                                                   reinterpret_cast<uint2 *>(d_seq2));
+        ctx->launches++;
+    }
+    tiles_seq2_kernel<<<(b->n_tiles + 1 + 255) / 256, 256, 0, ctx->stream>>>(b->tiles, b->n_tiles + 1, d_tiles2);
+    ctx->launches++;
+    SD_CUDA(ctx, cudaGetLastError());
+    return SD_OK;
+}

@@ -291,6 +291,7 @@ extern "C" int sd_read_stats(sd_ctx *ctx, const sd_batch *b, const sd_stats_args
     if (want_utr && !ctx->d_row_blen) return sd_fail(ctx, SD_ERR_STATE, "sd_read_stats: per-UTR outputs need sd_set_utrs");
     if (a->d_pairs && !a->d_n_pairs) return sd_fail(ctx, SD_ERR_ARG, "sd_read_stats: d_pairs without d_n_pairs");
     if (a->d_readpos && a->max_read_length == 0) return sd_fail(ctx, SD_ERR_ARG, "sd_read_stats: max_read_length 0");
+    if (b->seq_bits == 2) return sd_fail(ctx, SD_ERR_ARG, "sd_read_stats needs the 4-plane SEQ column (exact base counts), not the 2-bit form");
     if (b->n_tiles == 0) return SD_OK;
     if (!b->mp && b->max_tile_mp) return sd_fail(ctx, SD_ERR_ARG, "sd_read_stats: batch without the MP column (decode with SD_DECODE_MP_ALL)");
     SD_CUDA(ctx, cudaSetDevice(ctx->device));

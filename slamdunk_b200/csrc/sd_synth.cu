@@ -389,6 +389,7 @@ extern "C" int sd_synth_fill(sd_ctx *ctx, const sd_synth_params *p, const sd_syn
     out->tile_reads = p->tile_reads;
     out->max_lseq = p->read_len;
     out->qual_bits = 8;
+    out->seq_bits = 4;
     out->max_span = p->read_len + 3;   // at most one deletion of up to three bases per read (make_plan)
     out->max_tile_seq = ms; out->max_tile_qual = mq; out->max_tile_cig = mc; out->max_tile_mp = mm;
     return SD_OK;

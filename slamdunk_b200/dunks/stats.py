@@ -36,6 +36,8 @@ utrNormFactor = 250                               # stats.py:35
 baseNumber = 5
 toBase = ["A", "C", "G", "T", "N"]
 
+TIMINGS = {}                                      # last sd_read_stats run: kernel_ms, reads, device_bytes, decode seconds
+
 PAIR_DT = np.dtype([("row", np.uint32), ("read", np.uint32), ("t_count", np.uint32), ("tc_count", np.uint32)])
 
 
@@ -114,8 +116,13 @@ class ReadStats(object):
             a.d_rates, a.d_readpos = _ptr(out.get("rates")), _ptr(out.get("readpos"))
             a.d_utr_rates, a.d_utr_snp, a.d_utrpos = _ptr(out.get("utr_rates")), _ptr(out.get("utr_snp")), _ptr(out.get("utrpos"))
             a.d_pairs, a.pair_capacity, a.d_n_pairs = _ptr(pairs), int(pair_capacity), _ptr(n_pairs)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(eng.stream)
             eng._chk(eng.lib.sd_read_stats(eng.ctx, ctypes.byref(dbatch.batch), ctypes.byref(a)), "sd_read_stats")
+            ev1.record(eng.stream)
             eng.synchronize()
+            TIMINGS.update(kernel_ms=ev0.elapsed_time(ev1), reads=hb.n_reads, device_bytes=dbatch.nbytes(),
+                           bam_inflate_s=hb.seconds_inflate, bam_decode_s=hb.seconds_decode)
             res = dict((k, v.cpu().numpy()) for k, v in out.items())
             if pairs is not None:
                 found = int(n_pairs.item())

@@ -50,6 +50,7 @@ OPTIONS = {
     "device": 0,
     "threads": 0,                       # host decode threads (0 = all cores)
     "mismatch_source": "verify",        # "cigar" | "mp" | "verify" (CIGAR walk cross-checked against MP)
+    "seq_bits": 2,                      # SEQ column handed to sd_count: 2 = 2-bit base codes (half the bytes), 4 = BAM nibble planes
     "timings": None,                    # last run's CountTimings
 }
 
@@ -83,7 +84,8 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
     genome, cached = _genome(ref)
     tm["fasta_decode_s"] = 0.0 if cached else genome.seconds
     mode = {"cigar": L.SD_MISMATCH_CIGAR, "mp": L.SD_MISMATCH_MP, "verify": L.SD_MISMATCH_VERIFY}[OPTIONS["mismatch_source"]]
-    hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True)
+    hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True,
+                       seq2=OPTIONS["seq_bits"] == 2)
     tm["bam_inflate_s"] = hbatch.seconds_inflate
     tm["bam_decode_s"] = hbatch.seconds_decode
     tm["bam_reads"] = hbatch.n_reads

@@ -72,14 +72,14 @@ class HostBatch(object):
     """A BAM file decoded into the columnar batch (sd_decode_bam); buffers are page-locked."""
 
     def __init__(self, path: str, fasta_names: Sequence[str], want_mp: bool = True, tile_reads: int = 0,
-                 threads: int = 0, group: bool = False, raw_qual: bool = False, mp_all: bool = False):
+                 threads: int = 0, group: bool = False, raw_qual: bool = False, mp_all: bool = False, seq2: bool = False):
         lib = L.load()
         err = ctypes.create_string_buffer(512)
         out = ctypes.POINTER(L.HBatch)()
         names = (ctypes.c_char_p * max(1, len(fasta_names)))(*[n.encode() for n in fasta_names])
         rc = lib.sd_decode_bam(os.fsencode(path), names, len(fasta_names),
                                (L.SD_DECODE_MP if want_mp else 0) | (L.SD_DECODE_GROUP if group else 0) |
-                               (L.SD_DECODE_RAW_QUAL if raw_qual else 0) | (L.SD_DECODE_MP_ALL if mp_all else 0), int(tile_reads),
+                               (L.SD_DECODE_RAW_QUAL if raw_qual else 0) | (L.SD_DECODE_MP_ALL if mp_all else 0) | (L.SD_DECODE_SEQ2 if seq2 else 0), int(tile_reads),
                                int(threads), ctypes.byref(out), err, len(err))
         if rc != L.SD_OK:
             raise L.NativeError("sd_decode_bam(%s) failed (%d): %s" % (path, rc, err.value.decode("utf-8", "replace")))

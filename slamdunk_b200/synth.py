@@ -206,9 +206,37 @@ class SynthWorkload(object):
 
 
 def algorithmic_bytes_per_read(read_len, mean_cigar_ops):
-    """Compulsory bytes per read of the columnar layout, each touched once by the count kernel
-    (DESIGN.md): sliced 4-bit SEQ rounded to 8 bases, QUAL, CIGAR ops, the 20-byte record."""
-    return 4 * ((read_len + 7) // 8) + read_len + 4.0 * mean_cigar_ops + 20
+    """compulsory bytes per read of the path's INPUT, each touched once, independent of how the
+    columns are coded in HBM -- ceil(L/2) (SEQ as BAM stores it, 4 bits per base) + L (QUAL) + 4 c (CIGAR ops) +
+    12 (pos, ref_id + flag + mapq + n_cigar, XI) + 4 (NM + pad) + 1 (per-read tc output): 171 B at L = 100, c = 1."""
+    return (read_len + 1) // 2 + read_len + 4.0 * mean_cigar_ops + 17
+
+
+def layout_bytes_per_read(read_len, mean_cigar_ops, seq_bits=4):
+    """Bytes per read of the columns as THIS layout holds them in HBM: SEQ in 32-base groups of
+    seq_bits planes, QUAL bytes, CIGAR ops, the 20-byte record.  (The count kernel touches fewer: QUAL only at candidates.)"""
+    return seq_bits * 4 * ((read_len + 31) // 32) + read_len + 4.0 * mean_cigar_ops + 20
+
+
+def to_seq2(db: DeviceBatch, eng) -> DeviceBatch:
+    """The same device batch with its SEQ column in the 2-bit form (sd_seq_pack), the form sd_decode_bam hands the
+    count path (SD_DECODE_SEQ2).  The other columns are shared with `db`."""
+    nt = int(db.batch.n_tiles)
+    n_seq = int(db.tensors["tiles"].view(torch.int64)[4 * nt].item()) if nt else 0
+    with torch.cuda.stream(eng.stream):
+        seq2 = torch.zeros(max(16, n_seq // 2), dtype=torch.uint8, device=db.tensors["seq"].device)
+        tiles2 = torch.empty_like(db.tensors["tiles"])
+    eng.stream.synchronize()
+    eng._chk(eng.lib.sd_seq_pack(eng.ctx, ctypes.byref(db.batch), seq2.data_ptr(), tiles2.data_ptr()), "sd_seq_pack")
+    eng.synchronize()
+    tens = dict(db.tensors)
+    tens["seq"], tens["tiles"] = seq2, tiles2
+    b = L.Batch()
+    ctypes.memmove(ctypes.byref(b), ctypes.byref(db.batch), ctypes.sizeof(L.Batch))
+    b.seq, b.tiles = seq2.data_ptr(), tiles2.data_ptr()
+    b.seq_bits = 2
+    b.max_tile_seq = int(db.batch.max_tile_seq) // 2
+    return DeviceBatch(b, tens)
 
 
 def batch_to_host(db: DeviceBatch, eng=None):

@@ -46,6 +46,21 @@ def test_count_matches_reference_golden(name, mode, tmp_path):
     assert tm["gpu_launches"] >= 4
 
 
+@pytest.mark.parametrize("name", goldens.COUNT_CASES)
+def test_count_matches_reference_golden_with_the_plane_seq_column(name, tmp_path):
+    """the default hands sd_count the 2-bit SEQ column (OPTIONS["seq_bits"] = 2); the four-plane form gives the same files"""
+    from slamdunk_b200.dunks import tcounter
+    c = goldens.CountCase(name)
+    tcounter.OPTIONS["seq_bits"] = 4
+    try:
+        out, _log, _tm = _count(c, tmp_path)
+    finally:
+        tcounter.OPTIONS["seq_bits"] = 2
+    assert _read(out + ".tsv") == _read(c.tsv)
+    assert _read(out + "_plus.bedgraph") == _read(c.plus)
+    assert _read(out + "_mins.bedgraph") == _read(c.minus)
+
+
 def _engine_run(case_files, min_qual, thr, mode, force_slow=False, tile_reads=32, want_read_tc=False, snps=True):
     """Engine-level run -> results dict (+ per-read tc)."""
     import torch

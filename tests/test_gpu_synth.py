@@ -309,3 +309,43 @@ def test_deep_coverage_tiles_aggregate_their_coverage_atomics():
     assert res["stats"][L.SD_S_COUNTED] == 300_000
     assert ob.compare(res, rows, bg, wl.ann, eng.pos_off, wl.chrom_off) == []
     eng.close()
+
+
+@pytest.mark.parametrize("read_len,n_reads,mode,slow", [(100, 150_000, "cigar", False), (150, 80_000, "verify", False), (250, 40_000, "mp", False),
+                                                        (36, 30_000, "cigar", False), (400, 8_000, "cigar", False), (100, 20_000, "cigar", True)])
+def test_two_bit_seq_column_counts_like_the_plane_form(read_len, n_reads, mode, slow):
+    """sd_batch.seq_bits = 2 (sd_seq_pack; what sd_decode_bam hands the count path): every output identical to the run on
+    the four-plane column, on all window sizes, the per-base path, from the device and through sd_count_host."""
+    import torch
+    from slamdunk_b200 import _lib as L
+    from slamdunk_b200.engine import make_params
+    from slamdunk_b200.synth import batch_to_host, to_seq2
+    eng, wl = _setup()
+    p = wl.params(seed=21, first_read=0, n_reads=n_reads, read_len=read_len, frac_softclip=0.1, frac_indel=0.08,
+                  frac_antisense=0.05, frac_labelled=0.8)
+    db, _ = wl.generate(p, want_mp=True)
+    params = make_params(27, 1, {"cigar": 0, "mp": 1, "verify": 2}[mode], force_slow_path=slow)
+    read_tc4 = torch.zeros(int(db.batch.n_tiles) * 32, dtype=torch.uint8, device=eng.device)
+    eng.count(db, params, read_tc=read_tc4)
+    eng.finalize()
+    want = eng.results()
+    db2 = to_seq2(db, eng)
+    assert db2.batch.seq_bits == 2 and db2.tensors["seq"].numel() * 2 == db.tensors["seq"].numel()
+    eng.reset_outputs()
+    read_tc2 = torch.zeros_like(read_tc4)
+    eng.count(db2, params, read_tc=read_tc2)
+    eng.finalize()
+    got = eng.results()
+    assert want["stats"][L.SD_S_COUNTED] == n_reads and want["counters"][:, L.SD_C_CONV_ON_T].sum() > 0
+    for k in ("counters", "stats", "pos_cov", "pos_tc", "tcontent"):
+        assert np.array_equal(want[k], got[k]), k
+    assert torch.equal(read_tc4, read_tc2)
+    hb, keep = batch_to_host(db2, eng)
+    assert hb.seq_bits == 2
+    eng.reset_outputs()
+    eng.count_host(hb, params)
+    eng.finalize()
+    got = eng.results()
+    for k in ("counters", "stats", "pos_cov", "pos_tc"):
+        assert np.array_equal(want[k], got[k]), "host " + k
+    eng.close()

@@ -464,3 +464,57 @@ def test_native_bai_index_answers_region_queries(tmp_path):
                                     3, ctypes.byref(nw), err, len(err))
     srt = all((a.ref_id, a.pos) <= (b.ref_id, b.pos) for a, b in zip(kept, kept[1:]))
     assert (rc == 0) == srt
+
+
+def test_bam_decoder_two_bit_seq_and_full_mp_columns(tmp_path):
+    """SD_DECODE_SEQ2: 2-bit base codes (A=0 C=1 G=2 T=3, everything else A), half the plane column's bytes, same tile
+    geometry; SD_DECODE_MP_ALL: every MP entry as {readPos-1 | refPos-1 << 16, conv}.  The two exclude each other."""
+    from slamdunk_b200.engine import HostBatch
+    c = simdata.make_case(str(tmp_path), seed=78, n_reads=500, complexity=2.0)
+    text, refs, recs = bamio.read_bam(c.bam)
+    recs[3].seq = "N" + recs[3].seq[1:-1] + "R"       # non-ACGT bases in a read
+    recs[7].seq = "=" * len(recs[7].seq)
+    path = str(tmp_path / "n.bam")
+    bamio.write_bam(path, text, refs, recs)
+    names = list(c.genome.keys())
+    h4 = HostBatch(path, names, threads=3)
+    h2 = HostBatch(path, names, threads=3, seq2=True)
+    assert (h4.batch.seq_bits or 4) == 4 and h2.batch.seq_bits == 2
+    t4, t2 = h4.tiles_array(), h2.tiles_array()
+    assert (t2[:, 0] * 2 == t4[:, 0]).all() and (t2[:, 1:] == t4[:, 1:]).all()
+    assert h2.batch.max_tile_seq * 2 == h4.batch.max_tile_seq
+    s4, s2 = h4.column("seq"), h2.column("seq")
+    assert len(s2) * 2 == len(s4)
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    rec = h4.rec_array()
+    for i, r in enumerate(recs):
+        t, k = divmod(i, 32)
+        base2 = int(t2[t, 0]) // 4
+        for j, ch in enumerate(r.seq.upper()):
+            g = base2 + 2 * ((j >> 5) * 32 + k)
+            got = ((int(s2[g]) >> (j & 31)) & 1) | (((int(s2[g + 1]) >> (j & 31)) & 1) << 1)
+            assert got == code.get(ch, 0), (i, j, ch)
+        lseq = int(rec[i, 3]) & 0xFFFF
+        if lseq % 32:      # pad bits of the last group are zero
+            g = base2 + 2 * ((lseq >> 5) * 32 + k)
+            assert (int(s2[g]) | int(s2[g + 1])) >> (lseq & 31) == 0
+    hm = HostBatch(path, names, threads=3, mp_all=True)
+    mp, tm, recm = hm.column("mp"), hm.tiles_array(), hm.rec_array()
+    for t in range(hm.batch.n_tiles):
+        mo = int(tm[t, 3]) // 4
+        for k in range(32):
+            i = t * 32 + k
+            if i >= len(recs):
+                break
+            nmp = int(recm[i, 4]) >> 16
+            want = []
+            if recs[i].has_tag("MP"):
+                for ent in recs[i].get_tag("MP").split(","):
+                    conv, rp, fp = (int(x) for x in ent.split(":"))
+                    want += [(rp - 1) | ((fp - 1) << 16), conv]
+            assert [int(x) for x in mp[mo:mo + 2 * nmp]] == want
+            mo += 2 * nmp
+    with pytest.raises(L.NativeError, match="exclude"):
+        HostBatch(path, names, threads=3, mp_all=True, seq2=True)
+    for h in (h4, h2, hm):
+        h.close()
