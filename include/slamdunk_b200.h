@@ -454,6 +454,8 @@ typedef struct sd_synth_tables {
     const uint32_t *utr_end;
     const uint8_t *utr_strand;
     const double *utr_cum_weight;    /* inclusive cumulative expression weight */
+    const float *utr_label_frac;     /* optional: per-UTR fraction of labelled reads, overriding sd_synth_params.frac_labelled --
+                                        a 4sU time point, 1 - exp(-ln2 t / halflife(u)) (dunks/simulator.py:291-302) */
 } sd_synth_tables;
 
 #define SD_SYNTH_MAX_TRIPLES 40

@@ -81,7 +81,8 @@ class SynthTables(ctypes.Structure):
     _fields_ = [("lo", ctypes.c_void_p), ("hi", ctypes.c_void_p), ("nmask", ctypes.c_void_p),
                 ("chrom_off", ctypes.c_void_p), ("chrom_len", ctypes.c_void_p), ("n_chrom", ctypes.c_uint32),
                 ("n_utr", ctypes.c_uint32), ("utr_chrom", ctypes.c_void_p), ("utr_start", ctypes.c_void_p),
-                ("utr_end", ctypes.c_void_p), ("utr_strand", ctypes.c_void_p), ("utr_cum_weight", ctypes.c_void_p)]
+                ("utr_end", ctypes.c_void_p), ("utr_strand", ctypes.c_void_p), ("utr_cum_weight", ctypes.c_void_p),
+                ("utr_label_frac", ctypes.c_void_p)]
 
 
 class StatsArgs(ctypes.Structure):

@@ -89,7 +89,7 @@ __device__ Plan make_plan(Rng &rng, const sd_synth_params &P, const sd_synth_tab
     pl.strand = T.utr_strand[u];
     if (rng.uniform() < P.frac_antisense) pl.strand ^= 1u;
     pl.mapq = (rng.uniform() < P.frac_multimap) ? 0u : 60u;
-    pl.labelled = rng.uniform() < P.frac_labelled;
+    pl.labelled = rng.uniform() < (T.utr_label_frac ? T.utr_label_frac[u] : P.frac_labelled);
     return pl;
 }
 

@@ -118,6 +118,22 @@ class SynthWorkload(object):
         t.utr_strand, t.utr_cum_weight = self.d_utr_strand.data_ptr(), self.d_cum.data_ptr()
         self.tables = t
 
+    def set_time_point(self, minutes=None, halflife_seed=7):
+        """4sU time course (BASELINE.json config 3): every UTR gets a half-life drawn uniformly from [30, 720] min
+        (splash.py:126-127) and, at labelling time `minutes`, the labelled-read fraction 1 - exp(-ln2 t / halflife)
+        (simulator.py:291-302); None goes back to the global frac_labelled of params()."""
+        if minutes is None:
+            self.d_label_frac = None
+            self.tables.utr_label_frac = None
+            return None
+        hl = np.random.default_rng(halflife_seed).uniform(30.0, 720.0, len(self.ann))
+        frac = (1.0 - np.exp(-np.log(2.0) * float(minutes) / hl)).astype(np.float32)
+        with torch.cuda.stream(self.eng.stream):
+            self.d_label_frac = torch.from_numpy(frac).to(self.eng.device)
+        self.eng.stream.synchronize()
+        self.tables.utr_label_frac = self.d_label_frac.data_ptr()
+        return frac
+
     def install(self):
         """Hand genome and annotation to the engine (sd_set_reference / sd_set_utrs)."""
         self.eng.set_reference(self.lo, self.hi, self.nmask, self.chrom_off, self.chrom_len)

@@ -349,3 +349,30 @@ def test_two_bit_seq_column_counts_like_the_plane_form(read_len, n_reads, mode, 
     for k in ("counters", "stats", "pos_cov", "pos_tc"):
         assert np.array_equal(want[k], got[k]), "host " + k
     eng.close()
+
+
+def test_time_course_samples_counted_in_one_batched_run():
+    """BASELINE.json config 3 in miniature: samples of a 4sU time course (labelled-read fraction 1 - exp(-ln2 t / halflife)
+    per UTR, 150 bp reads) counted one after the other by one engine on one genome / annotation; every sample equals the
+    oracle, and the conversion-carrying reads grow with the labelling time."""
+    from slamdunk_b200 import _lib as L
+    from slamdunk_b200.engine import make_params
+    from slamdunk_b200.synth import to_seq2
+    eng, wl = _setup()
+    params = make_params(27, 1, 0)
+    tc_reads = []
+    for k, minutes in enumerate([0, 30, 120, 720]):
+        frac = wl.set_time_point(minutes)
+        assert frac.min() >= 0.0 and (minutes == 0 or 0.02 < frac.mean() < 1.0)
+        p = wl.params(seed=10 + k, first_read=0, n_reads=40_000, read_len=150)
+        db, triples = wl.generate(p, want_triples=True)
+        eng.reset_outputs()
+        eng.count(to_seq2(db, eng), params)
+        eng.finalize()
+        res = eng.results()
+        rows, bg = _oracle(wl, db, triples, 27, 1)
+        assert ob.compare(res, rows, bg, wl.ann, eng.pos_off, wl.chrom_off) == []
+        tc_reads.append(int(res["counters"][:, L.SD_C_TCREADS].sum()))
+    wl.set_time_point(None)
+    assert tc_reads[0] < tc_reads[1] < tc_reads[2] < tc_reads[3]
+    eng.close()
