@@ -47,7 +47,8 @@ def main():
             eng.count(s, params)
             eng.finalize()
             kms.append(None)
-            counters.append(eng.counters.clone())
+            with torch.cuda.stream(eng.stream):          # the outputs live on the engine's stream
+                counters.append(eng.counters.clone())
         return kms
 
     for _ in range(2):
