@@ -180,7 +180,8 @@ def workload_config(args, sample_reads=None):
                      "2.5%% T>C per reference T" % (args.reads, args.read_len, args.utrs, args.genome_bp / 1e6),
          "reads_per_gpu": args.reads, "read_len": args.read_len, "n_utr": args.utrs,
          "filter": "MQ>=2, identity>=0.95 (slamdunk defaults)", "min_base_qual": MIN_QUAL, "conversion_threshold": CONV_THRESHOLD,
-         "mismatch_source": "cigar_walk", "read_order": args.order, "seq_bits": getattr(args, "seq_bits", 2), "sharding": "utr_owner_regions" if args.gpus > 1 else "none",
+         "mismatch_source": "cigar_walk", "read_order": args.order, "seq_bits": getattr(args, "seq_bits", 2),
+         "qual_form": getattr(args, "qual_form", "planes") if getattr(args, "seq_bits", 2) == 2 else "bytes", "sharding": "utr_owner_regions" if args.gpus > 1 else "none",
          "l2_policy": "inputs (~%.1f GB per GPU) far exceed the 126 MB L2; no explicit flush" % (args.reads * (getattr(args, "seq_bits", 2) * 4 * ((args.read_len + 31) // 32) + args.read_len + 24.4) / 1e9)}
     if sample_reads is not None:
         c["sample_reads"] = sample_reads
@@ -225,6 +226,10 @@ def main():
     ap.add_argument("--seq-bits", type=int, default=2, choices=[2, 4], dest="seq_bits",
                     help="form of the SEQ column: 2 = 2-bit base codes, what sd_decode_bam hands the count path (default); "
                          "4 = the four BAM-nibble bit-planes")
+    ap.add_argument("--qual-form", default="planes", choices=["planes", "bytes"], dest="qual_form",
+                    help="device form of the base qualities: planes = bit-planes of the dictionary code staged with the tile "
+                         "(what sd_count_host gives the kernel when the file has <= 16 distinct qualities and the SEQ column is "
+                         "2-bit; default), bytes = one byte per base fetched at candidates")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -244,7 +249,8 @@ def main():
     import torch.distributed as dist
     from slamdunk_b200 import _lib as L
     from slamdunk_b200.engine import make_params
-    from slamdunk_b200.synth import algorithmic_bytes_per_read, batch_to_host, host_batch_bytes, layout_bytes_per_read, to_seq2
+    from slamdunk_b200.synth import (algorithmic_bytes_per_read, batch_to_host, host_batch_bytes, layout_bytes_per_read,
+                                     to_qual_planes, to_seq2)
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -260,6 +266,12 @@ def main():
         db4.tensors["seq"] = None      # free the 4-plane column
         del db4
         torch.cuda.empty_cache()
+    db_rows = db                       # qualities as one byte per base: what the host batch of the e2e leg is made from
+    qual_planes = 0
+    if args.seq_bits == 2 and args.qual_form == "planes":
+        dbq = to_qual_planes(db_rows, eng)
+        if dbq is not None:
+            db, qual_planes = dbq, int(dbq.batch.qual_bits)
 
     def step():
         eng.reset_outputs()
@@ -305,7 +317,7 @@ def main():
     tiles = db.tensors["tiles"].cpu().numpy().view(np.uint64).reshape(-1, 4)
     mean_cig = float(tiles[-1, 2]) / 4.0 / n_reads
     bytes_per_read = algorithmic_bytes_per_read(args.read_len, mean_cig)
-    layout_bytes = layout_bytes_per_read(args.read_len, mean_cig, args.seq_bits)
+    layout_bytes = layout_bytes_per_read(args.read_len, mean_cig, args.seq_bits, qual_planes)
     k_ms = float(np.mean(kernel_ms))
     achieved = n_reads * bytes_per_read / (k_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
@@ -319,7 +331,7 @@ def main():
     # end to end: pinned host buffers -> sd_count_host -> counters back on the host
     e2e = None
     if not args.no_e2e:
-        hb, keep = batch_to_host(db, eng)     # the host form sd_decode_bam produces: quality codes when the column has <= 16 values
+        hb, keep = batch_to_host(db_rows, eng)     # the host form sd_decode_bam produces: quality codes when the column has <= 16 values
         h2d = host_batch_bytes(keep)
         d2h = eng.counters.numel() * 8 + eng.stats.numel() * 8
 
@@ -396,7 +408,7 @@ def load_ncu_traffic(args):
     path = os.path.join(ROOT, "profiles", "count_kernel_dram.json")
     try:
         d = json.load(open(path))
-        if args.reads != d.get("reads_per_launch") or args.read_len != 100 or args.order != "sorted" or args.seq_bits != d.get("seq_bits", 4):
+        if args.reads != d.get("reads_per_launch") or args.read_len != 100 or args.order != "sorted" or args.seq_bits != d.get("seq_bits", 4) or args.qual_form != d.get("qual_form", "bytes"):
             return None
         return d.get("dram_bytes_per_launch")
     except Exception:

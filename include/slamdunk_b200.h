@@ -127,7 +127,14 @@ typedef struct sd_batch {
                                2-bit form is lossless -- half the SEQ bytes in HBM and on PCIe.  Tile seq offsets are byte
                                offsets into the column as stored.  sd_count* / sd_count_host take both forms;
                                sd_read_stats (exact base counts) needs the 4-plane form. */
-    uint32_t reserved0;
+    uint32_t qual_form;     /* 0: `qual` holds one row of l_seq qualities per read (bytes, or codes on a host batch, see qual_bits);
+                               1: DEVICE batches, group-major bit-planes of the dictionary code, like the 2-bit SEQ column:
+                               qual_bits (2 or 4) words per 32-base group, word b = bit b of the codes of bases 32g .. 32g+31,
+                               group g of row r at byte 4 * qual_bits * (g * tile_reads + r) of the tile block; pad bits zero;
+                               qual_dict ascends (sd_decode_bam / sd_qual_dict), so `quality >= minQual` is a bit-sliced
+                               `code >= c` on 32 bases at once and the block travels with the tile instead of being fetched
+                               byte by byte.  Tile qual offsets are then byte offsets into the column as stored, max_tile_qual
+                               the largest block.  Made by sd_qual_to_planes; needs seq_bits == 2; sd_count* only. */
 } sd_batch;
 
 /* Where the per-read mismatch list comes from. */
@@ -325,6 +332,15 @@ int sd_qual_pack(sd_ctx *ctx, const uint8_t *d_qual, uint64_t n_bases, uint8_t *
  * column's bytes, d_tiles2 [n_tiles + 1] the tile table with the seq offsets of the new column (other offsets copied).
  * What sd_decode_bam does with SD_DECODE_SEQ2, for batches that were made on the device.  Asynchronous. */
 int sd_seq_pack(sd_ctx *ctx, const sd_batch *d_batch, uint32_t *d_seq2, sd_tile *d_tiles2);
+/* sd_qual_dict: the distinct values of a device-resident byte qual column: *bits = 2 / 4 when there are at most 4 / 16 of
+ * them (dict16 = the values in ascending order, code = index), else 8.  Synchronous.
+ * sd_qual_to_planes: the plane form (sd_batch.qual_form = 1) of a device batch whose qual column holds bytes: d_planes
+ * receives 4 * bits bytes per (group, row slot) of the batch's SEQ blocks, d_tiles_out [n_tiles + 1]
+ * the tile table with the qual offsets of the new column (other offsets copied).  Values missing from dict16 get code 0.
+ * Asynchronous. */
+int sd_qual_dict(sd_ctx *ctx, const uint8_t *d_qual, uint64_t n_bases, uint32_t *bits, uint8_t *dict16);
+int sd_qual_to_planes(sd_ctx *ctx, const sd_batch *d_batch, uint32_t bits, const uint8_t *dict16, uint32_t *d_planes,
+                      sd_tile *d_tiles_out);
 
 /* ------------------------------------------------------------------ filtered BAM output (host, C++ threads + zlib)
  * Replaces pysam's outfile.write / dumpBufferToBam and `samtools sort` after the decisions of sd_filter

@@ -46,7 +46,7 @@ class Batch(ctypes.Structure):
                 ("cigar", ctypes.c_void_p), ("mp", ctypes.c_void_p), ("tiles", ctypes.c_void_p),
                 ("max_lseq", ctypes.c_uint32), ("max_tile_seq", ctypes.c_uint32), ("max_tile_qual", ctypes.c_uint32),
                 ("max_tile_cig", ctypes.c_uint32), ("max_tile_mp", ctypes.c_uint32), ("max_span", ctypes.c_uint32), ("qual_bits", ctypes.c_uint32),
-                ("qual_dict", ctypes.c_uint8 * 16), ("seq_bits", ctypes.c_uint32), ("reserved0", ctypes.c_uint32)]
+                ("qual_dict", ctypes.c_uint8 * 16), ("seq_bits", ctypes.c_uint32), ("qual_form", ctypes.c_uint32)]
 
 
 class Params(ctypes.Structure):
@@ -122,6 +122,8 @@ PROTOTYPES = {
                                       ctypes.c_int, ctypes.c_int, c_u64p, ctypes.c_char_p, ctypes.c_int]),
     "sd_qual_unpack": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64, ctypes.c_uint32, _VP, _VP]),
     "sd_qual_pack": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64, _VP, ctypes.POINTER(ctypes.c_uint32), _VP]),
+    "sd_qual_dict": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32), _VP]),
+    "sd_qual_to_planes": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.c_uint32, _VP, _VP, _VP]),
     "sd_seq_pack": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), _VP, _VP]),
     "sd_rewrite_bam_indexed": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, _VP, _VP, ctypes.c_uint64,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, c_u64p, ctypes.c_char_p, ctypes.c_int]),

@@ -88,6 +88,9 @@ struct CountArgs {
     uint32_t n_tiles;
     uint32_t tile_reads;
     uint32_t seq2;            // the SEQ column holds 2-bit base codes (sd_batch.seq_bits == 2): two words per group
+    uint32_t qual_planes;     // 0: qual column = bytes, read in place; 2 / 4: group-major bit-planes of the dictionary code
+                              // (sd_batch.qual_form == 1), staged with the tile
+    uint32_t q_cmin;          // plane form: quality >= min_qual  <=>  code >= q_cmin (codes ascend with quality); 2^planes: none
     // shared-memory stage layout (bytes, all multiples of 128)
     uint32_t cap_rec, cap_seq, cap_qual, cap_cig, cap_mp;
     uint32_t n_stages;
@@ -202,6 +205,44 @@ __device__ __forceinline__ uint32_t row_group_is_base(const uint32_t *row, uint3
     return group_is_base(reinterpret_cast<const uint4 *>(row)[g * SD_TILE_READS], sm);
 }
 
+// Bit-plane quality column (sd_batch.qual_form == 1): QB words per 32-base group, bit-plane b of the base's dictionary
+// code.  sd_decode_bam / sd_qual_dict assign codes in ascending quality order, so the reference's test
+// `readQlty >= minQual` (SlamSeqFile.py:330) is the bit-sliced comparison code >= q_cmin: 2 LOP3 per plane for 32 bases.
+template <int QB>
+__device__ __forceinline__ uint32_t planes_ge(const uint32_t (&p)[QB], uint32_t cmin) {
+    uint32_t gt = 0u, eq = 0xFFFFFFFFu;
+#pragma unroll
+    for (int b = QB - 1; b >= 0; b--) {
+        const uint32_t cb = 0u - ((cmin >> b) & 1u);
+        gt |= eq & p[b] & ~cb;
+        eq &= ~(p[b] ^ cb);
+    }
+    return (cmin >> QB) ? 0u : (gt | eq);
+}
+template <int QB>
+__device__ __forceinline__ uint32_t row_group_qual_ok(const uint32_t *row, uint32_t g, uint32_t cmin) {
+    uint32_t p[QB];
+    if (QB == 2) {
+        const uint2 x = reinterpret_cast<const uint2 *>(row)[g * SD_TILE_READS];
+        p[0] = x.x; p[1] = x.y;
+    } else {
+        const uint4 x = reinterpret_cast<const uint4 *>(row)[g * SD_TILE_READS];
+        p[0] = x.x; p[1] = x.y; p[QB > 2 ? 2 : 0] = x.z; p[QB > 2 ? 3 : 1] = x.w;
+    }
+    return planes_ge<QB>(p, cmin);
+}
+// "Quality" of read base qi (0 <= qi < l_seq) for a `>= A.min_qual` test: the byte itself, or on the plane form 255 / -1
+// for pass / fail (min_qual <= 0 makes q_cmin 0: everything passes there too).
+template <int QB>
+__device__ __forceinline__ int qual_for_test(const CountArgs &A, const uint8_t *qual, int qi) {
+    if (QB == 0) return (int)__ldg(qual + qi);
+    const uint32_t ok = row_group_qual_ok<(QB ? QB : 2)>(reinterpret_cast<const uint32_t *>(qual), (uint32_t)qi >> 5, A.q_cmin);
+    return ((ok >> (qi & 31)) & 1u) ? 255 : -1;
+}
+__device__ __forceinline__ int qual_for_test_rt(const CountArgs &A, const uint8_t *qual, int qi) {   // per-base path: form known at run time
+    return A.qual_planes == 0 ? qual_for_test<0>(A, qual, qi) : (A.qual_planes == 2 ? qual_for_test<2>(A, qual, qi) : qual_for_test<4>(A, qual, qi));
+}
+
 // @region slow_and_generic
 // Map a reference offset (relative to the alignment start) to the read index aligned to it.
 __device__ __forceinline__ int ref_to_read(const uint32_t *cig, uint32_t ncig, int o) {
@@ -224,7 +265,8 @@ __device__ __forceinline__ int ref_to_read(const uint32_t *cig, uint32_t ncig, i
 
 struct ReadView {
     const uint32_t *seq;   // this read's slot of group 0 in the tile's group-major plane block (shared memory)
-    const uint8_t *qual;   // bytes (shared memory)
+    const uint8_t *qual;   // the read's quality bytes in the global qual column, or (plane form) its slot of group 0 in the tile's
+                           // group-major plane block in shared memory
     const uint32_t *cig;   // ops (shared memory)
     const uint32_t *mp;    // entries (shared memory) or null
     uint32_t lseq, ncig, nmp;
@@ -247,7 +289,7 @@ __device__ __forceinline__ void slow_for_each_hit(const CountArgs &A, const Read
         for (uint32_t i = 0; i < v.nmp; i++) {
             const uint32_t e = v.mp[i];
             const int rp = (int)(e & 0xFFFFu), o = (int)(e >> 16);
-            const int q = (rp >= (int)v.lseq) ? 0 : (int)v.qual[rp];
+            const int q = (rp >= (int)v.lseq) ? 0 : qual_for_test_rt(A, v.qual, rp);
             if (q < A.min_qual) continue;
             const uint64_t gp = (uint64_t)v.g + (uint64_t)o;
             const uint2 x = __ldg(&rx[gp >> 5]);
@@ -272,7 +314,7 @@ __device__ __forceinline__ void slow_for_each_hit(const CountArgs &A, const Read
                 const uint2 x = __ldg(&rx[gp >> 5]);
                 const uint32_t bit = 1u << (gp & 31);
                 if (!(x.x & bit) || (x.y & bit)) continue;
-                if ((int)v.qual[qi] < A.min_qual) continue;
+                if (qual_for_test_rt(A, v.qual, qi) < A.min_qual) continue;
                 f(o, true);
             }
             q += len;
@@ -406,7 +448,7 @@ __device__ __forceinline__ int block_read_index(const Blocks &B, int o) {
 
 // SIMPLE: every read of the tile is one match block without clips (the decoder groups such reads into
 // their own tiles), so the read mask needs no placement and a window position is a read index.
-template <int W, bool SIMPLE, int SB>
+template <int W, bool SIMPLE, int SB, int QB>
 __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, const Blocks &B, uint32_t mapq,
                                          bool dense_tile, bool &mp_disagree) {
     const int s = v.strand;
@@ -441,7 +483,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             for (uint32_t i = 0; i < v.nmp; i++) {
                 const uint32_t e = v.mp[i];
                 const int rp = (int)(e & 0xFFFFu), o = (int)(e >> 16);
-                const int q = (rp >= (int)v.lseq) ? 0 : (int)v.qual[rp];
+                const int q = (rp >= (int)v.lseq) ? 0 : qual_for_test<QB>(A, v.qual, rp);
                 if (q >= A.min_qual) {
 #pragma unroll
                     for (int k = 0; k < W; k++)
@@ -458,7 +500,10 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
         for (int k = 0; k < W; k++) {
             // unconditional load of an existing group (index clamped), masked afterwards: no branch per group
             const uint32_t kc = ng ? min((uint32_t)k, ng - 1u) : 0u;
-            const uint32_t m = row_group_is_base<SB>(v.seq, kc, sm);   // this row's slot of group kc; the tile block is group-major
+            uint32_t m = row_group_is_base<SB>(v.seq, kc, sm);   // this row's slot of group kc; the tile block is group-major
+            // plane-form qualities, plain CIGAR walk: the quality test is one more mask on the read side, for 32 bases at once
+            if (QB > 0 && A.mismatch_source == SD_MISMATCH_CIGAR)
+                m &= row_group_qual_ok<(QB ? QB : 2)>(reinterpret_cast<const uint32_t *>(v.qual), kc, A.q_cmin);
             M[k] = ((uint32_t)k < ng) ? m : 0u;
         }
         if (SIMPLE) {
@@ -557,6 +602,13 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             tc += __popc(h);
             H[k] = A.mp_any_base ? h : (h & T[k]);
         }
+    } else if (QB > 0 && A.mismatch_source == SD_MISMATCH_CIGAR) {
+        // the read mask already carries the quality test (plane-form qual column)
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            H[k] = v.has_mp ? (R[k] & T[k] & ~S[k]) : 0u;
+            tc += __popc(H[k]);
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < W; k++) H[k] = v.has_mp ? (R[k] & T[k] & ~S[k]) : 0u;
@@ -570,8 +622,8 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             if (H[k]) {
                 const int o = 32 * k + (__ffs((int)H[k]) - 1);
                 const int qi = SIMPLE ? o : (regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o));
-                SD_CHECK_QUAL(A, v.qual + (qi < 0 || qi >= (int)v.lseq ? 0 : qi));
-                qv[k] = (qi < 0 || qi >= (int)v.lseq) ? -1 : ld_qual(v.qual + qi);
+                if (QB == 0) SD_CHECK_QUAL(A, v.qual + (qi < 0 || qi >= (int)v.lseq ? 0 : qi));
+                qv[k] = (qi < 0 || qi >= (int)v.lseq) ? -1 : qual_for_test<QB>(A, v.qual, qi);
             }
         }
         uint32_t C[W], more = 0u;   // C: candidates after the first of each word, still to be tested
@@ -590,7 +642,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                     rest &= rest - 1ull;
                     const int o = 32 * k2 + bit;
                     const int qi = SIMPLE ? o : (regs ? block_read_index(B, o) : ref_to_read(v.cig, v.ncig, o));
-                    if (qi < 0 || qi >= (int)v.lseq || ld_qual(v.qual + qi) < A.min_qual) fail |= 1ull << bit;
+                    if (qi < 0 || qi >= (int)v.lseq || qual_for_test<QB>(A, v.qual, qi) < A.min_qual) fail |= 1ull << bit;
                 }
                 H[k2] |= C[k2] & ~(uint32_t)fail;
                 H[k2 + 1] |= C[k2 + 1] & ~(uint32_t)(fail >> 32);
@@ -729,10 +781,10 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #define SD_MIN_CTAS(W) ((W) <= 6 ? 4 : ((W) <= 10 ? 3 : 2))   // resident 256-thread CTAs per SM the register budget is tuned for
 #endif
 
-template <int W, int SB>
+template <int W, int SB, int QB>
 __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kernel(const __grid_constant__ CountArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
+    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual;
     const uint32_t warp_bytes = A.n_stages * stage_bytes + 128u;   // stages | barriers + tile qual offsets
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t nwarp = blockDim.x >> 5;
@@ -775,7 +827,10 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
             const uint32_t b_q = (uint32_t)(t1.qual_off - t0.qual_off) & ~15u;
             if (b_q) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.qual + t0.qual_off), "r"(b_q) : "memory");
         }
-        mbar_arrive_expect_tx(&full[stage], b_rec + b_seq + b_cig + b_mp);
+        const uint32_t b_qpl = QB > 0 ? (uint32_t)(t1.qual_off - t0.qual_off) : 0u;   // plane-form qualities travel with the tile
+        mbar_arrive_expect_tx(&full[stage], b_rec + b_seq + b_cig + b_mp + b_qpl);
+        if (QB > 0 && b_qpl)
+            bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp, A.qual + t0.qual_off, b_qpl, &full[stage]);
         bulk_g2s(base, reinterpret_cast<const unsigned char *>(A.rec) + tile * b_rec, b_rec, &full[stage]);
         if (b_seq) bulk_g2s(base + A.cap_rec, reinterpret_cast<const unsigned char *>(A.seq) + t0.seq_off, b_seq, &full[stage]);
         if (b_cig)
@@ -871,7 +926,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
             if (pos >= 0 && (uint32_t)pos < clen) {
                 ReadView v;
                 v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (SB == 2 ? 2u : 4u) * lane;
-                v.qual = A.qual + s_qoff[stage] + qs;
+                v.qual = QB > 0 ? base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + 4u * QB * lane : A.qual + s_qoff[stage] + qs;
                 v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + cig_row;
                 v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
                 v.lseq = lseq;
@@ -902,7 +957,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
                 my_counted++;
                 if (fits) {
                     bool bad = false;
-                    tc = uni_simple ? fast_read<W, true, SB>(A, v, B, mapq, dense_tile, bad) : fast_read<W, false, SB>(A, v, B, mapq, dense_tile, bad);
+                    tc = uni_simple ? fast_read<W, true, SB, QB>(A, v, B, mapq, dense_tile, bad) : fast_read<W, false, SB, QB>(A, v, B, mapq, dense_tile, bad);
                     if (bad) atomicAdd(&A.stats[SD_S_MP_DISAGREE], 1ull);   // rare: straight to the global counter
                 } else {
                     atomicAdd(&A.stats[SD_S_SLOWPATH], 1ull);
@@ -1283,9 +1338,9 @@ extern "C" int sd_bind_outputs(sd_ctx *ctx, int64_t *d_counters, int32_t *d_pos_
 static inline uint32_t align128(uint32_t x) { return (x + 127u) & ~127u; }
 static inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
-template <int W, int SB>
+template <int W, int SB, int QB>
 static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
-    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
+    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     static int forced_stages = -1, forced_warps = -1, forced_pf = -1;
@@ -1309,8 +1364,8 @@ static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool tim
         while (warps > 1 && 128u + warps * warp_bytes(ns) > (size_t)max_smem) warps--;
         smem = 128u + warps * warp_bytes(ns);
         if (smem > (size_t)max_smem) { per_sm = 0; return SD_OK; }
-        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W, SB>, (int)warps * 32, smem));
+        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W, SB, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W, SB, QB>, (int)warps * 32, smem));
         return SD_OK;
     };
     uint32_t n_stages = 1, warps = 0;
@@ -1338,7 +1393,7 @@ static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool tim
     }
     if (per_sm < 1) return sd_fail(ctx, SD_ERR_LIMIT, "count kernel does not fit on an SM (smem %zu)", smem);
     if (last.device != ctx->device || last.stage_bytes != stage_bytes) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W, SB, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         last = {stage_bytes, ctx->device, n_stages, warps, smem, per_sm};
     }
     A.n_stages = n_stages;
@@ -1348,7 +1403,7 @@ static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool tim
     uint32_t grid = (uint32_t)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * per_sm);
     if (grid == 0) grid = 1;
     if (timed) SD_CUDA(ctx, cudaEventRecord(ctx->ev_k0, stream));
-    sd_count_kernel<W, SB><<<grid, threads, smem, stream>>>(A);
+    sd_count_kernel<W, SB, QB><<<grid, threads, smem, stream>>>(A);
     if (timed) {
         SD_CUDA(ctx, cudaEventRecord(ctx->ev_k1, stream));
         ctx->have_kernel_time = true;
@@ -1364,8 +1419,12 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     if (b->n_tiles == 0) return SD_OK;
     if (b->tile_reads != 32) return sd_fail(ctx, SD_ERR_ARG, "tile_reads must be 32 (one tile per warp)");
     if (p->mismatch_source != SD_MISMATCH_CIGAR && !b->mp) return sd_fail(ctx, SD_ERR_ARG, "mismatch source needs the mp column");
-    if (b->qual_bits != 0 && b->qual_bits != 8)
+    const bool qplanes = b->qual_form == 1;
+    if (!qplanes && b->qual_bits != 0 && b->qual_bits != 8)
         return sd_fail(ctx, SD_ERR_ARG, "the qual column holds %u-bit codes: expand it with sd_qual_unpack (sd_count_host does)", b->qual_bits);
+    if (qplanes && ((b->qual_bits != 2 && b->qual_bits != 4) || b->seq_bits != 2))
+        return sd_fail(ctx, SD_ERR_ARG, "a plane-form qual column needs 2 or 4 planes and the 2-bit SEQ column");
+    if (b->qual_form > 1) return sd_fail(ctx, SD_ERR_ARG, "unknown qual_form %u", b->qual_form);
     CountArgs A;
     memset(&A, 0, sizeof A);
     A.rec = b->rec; A.seq = b->seq; A.qual = b->qual; A.cigar = b->cigar;
@@ -1375,12 +1434,23 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     if (b->seq_bits != 0 && b->seq_bits != 4 && b->seq_bits != 2) return sd_fail(ctx, SD_ERR_ARG, "seq_bits must be 4 (or 0) or 2");
     A.seq2 = b->seq_bits == 2 ? 1u : 0u;
     A.cap_seq = std::max(align16(b->max_tile_seq), (A.seq2 ? 8u : 16u) * SD_TILE_READS);   // at least one group per row: the kernel loads group 0 unconditionally
-    A.cap_qual = 0;  // the qual column is read in place (see the kernel's header comment)
+    A.cap_qual = 0;  // byte form: the qual column is read in place (see the kernel's header comment)
     A.cap_cig = align16(b->max_tile_cig);
     A.cap_mp = A.mp ? align16(b->max_tile_mp) : 0;
     {   // keep every warp's region 128-byte aligned
         const uint32_t sum = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp;
         A.cap_cig += align128(sum) - sum;
+    }
+    if (qplanes) {   // plane form: the tile's block is staged behind the other columns
+        A.qual_planes = b->qual_bits;
+        A.cap_qual = align128(std::max(b->max_tile_qual, 4u * b->qual_bits * SD_TILE_READS));
+        // codes ascend with quality (sd_decode_bam, sd_qual_dict): quality >= min_qual  <=>  code >= q_cmin
+        uint32_t used = 1;
+        for (uint32_t c = 1; c < (1u << b->qual_bits); c++)
+            if (b->qual_dict[c] > b->qual_dict[c - 1]) used = c + 1;
+        uint32_t cmin = 0;
+        while (cmin < used && (int)b->qual_dict[cmin] < p->min_qual) cmin++;
+        A.q_cmin = cmin < used ? cmin : (1u << b->qual_bits);
     }
     for (int s = 0; s < 2; s++) {
         A.refx[s] = ctx->refx[s];
@@ -1423,20 +1493,20 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     // with 2 % short indels in a 192-base window: 9.6 instead of 15 G reads/s).  The batch says how wide its alignments
     // are (spliced ones aside); without that, 16 bases of slack cover the usual gaps.
     const uint32_t need = b->max_span ? std::max(b->max_lseq, b->max_span) : b->max_lseq + 16u;
-    if (A.seq2) {
-        if (need <= 128) return launch_count<4, 2>(ctx, A, stream, timed);
-        if (need <= 192) return launch_count<6, 2>(ctx, A, stream, timed);
-        if (need <= 256) return launch_count<8, 2>(ctx, A, stream, timed);
-        if (need <= 320) return launch_count<10, 2>(ctx, A, stream, timed);
-        if (need <= 384) return launch_count<12, 2>(ctx, A, stream, timed);
-        return launch_count<16, 2>(ctx, A, stream, timed);
-    }
-    if (need <= 128) return launch_count<4, 4>(ctx, A, stream, timed);
-    if (need <= 192) return launch_count<6, 4>(ctx, A, stream, timed);
-    if (need <= 256) return launch_count<8, 4>(ctx, A, stream, timed);
-    if (need <= 320) return launch_count<10, 4>(ctx, A, stream, timed);
-    if (need <= 384) return launch_count<12, 4>(ctx, A, stream, timed);
-    return launch_count<16, 4>(ctx, A, stream, timed);
+#define SD_DISPATCH_W(SB, QB)                                                        \
+    do {                                                                             \
+        if (need <= 128) return launch_count<4, SB, QB>(ctx, A, stream, timed);      \
+        if (need <= 192) return launch_count<6, SB, QB>(ctx, A, stream, timed);      \
+        if (need <= 256) return launch_count<8, SB, QB>(ctx, A, stream, timed);      \
+        if (need <= 320) return launch_count<10, SB, QB>(ctx, A, stream, timed);     \
+        if (need <= 384) return launch_count<12, SB, QB>(ctx, A, stream, timed);     \
+        return launch_count<16, SB, QB>(ctx, A, stream, timed);                      \
+    } while (0)
+    if (A.qual_planes == 2) SD_DISPATCH_W(2, 2);
+    if (A.qual_planes == 4) SD_DISPATCH_W(2, 4);
+    if (A.seq2) SD_DISPATCH_W(2, 0);
+    SD_DISPATCH_W(4, 0);
+#undef SD_DISPATCH_W
 }
 
 extern "C" int sd_count(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params) {
@@ -1475,12 +1545,17 @@ extern "C" int sd_count_host(sd_ctx *ctx, const sd_batch *hb, const sd_params *p
     const uint32_t qbits = hb->qual_bits ? hb->qual_bits : 8u;
     const bool coded = qbits != 8;
     if (coded && qbits != 2 && qbits != 4) return sd_fail(ctx, SD_ERR_ARG, "quality coding of %u bits is not supported", qbits);
+    // coded qualities next to the 2-bit SEQ column: the count kernel takes them as bit-planes (sd_batch.qual_form = 1)
+    static int planes_env = -1;
+    if (planes_env < 0) { const char *e = getenv("SD_QUAL_PLANES"); planes_env = e ? atoi(e) : 1; }
+    const bool to_planes = coded && hb->seq_bits == 2 && planes_env != 0;
     const sd_tile *T = hb->tiles;
     const uint64_t rec_tile = (uint64_t)hb->tile_reads * sizeof(sd_read_rec);
     auto chunk_bytes = [&](uint32_t t0, uint32_t t1) {
         uint64_t b = (uint64_t)(t1 - t0) * rec_tile + (T[t1].seq_off - T[t0].seq_off) + (T[t1].qual_off - T[t0].qual_off) +
                      (T[t1].cig_off - T[t0].cig_off) + (uint64_t)(t1 - t0 + 1) * sizeof(sd_tile) + 6 * 256;
         if (coded) b += (T[t1].qual_off - T[t0].qual_off) * qbits / 8;   // the codes as copied, next to the expanded column
+        if (to_planes) b += (T[t1].seq_off - T[t0].seq_off) * qbits / 2 + (uint64_t)(t1 - t0 + 1) * sizeof(sd_tile) + 4 * 256;
         if (use_mp) b += T[t1].mp_off - T[t0].mp_off;
         return b;
     };
@@ -1562,9 +1637,21 @@ extern "C" int sd_count_host(sd_ctx *ctx, const sd_batch *hb, const sd_params *p
         SD_CUDA(ctx, cudaMemcpyAsync(d + o, rl.data(), (size_t)(nt + 1) * sizeof(sd_tile), cudaMemcpyHostToDevice, ctx->copy_stream));
         SD_CUDA(ctx, cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
         SD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
+        o = up256(o + (size_t)(nt + 1) * sizeof(sd_tile));
         int rc = SD_OK;
         if (coded && b_qual && (rc = sd_qual_unpack_on(ctx, ctx->stream, d_codes, b_qual, qbits, hb->qual_dict, const_cast<uint8_t *>(db.qual))))
             return rc;
+        if (to_planes) {   // bytes -> bit-planes in the SEQ geometry; the kernel then stages them with the tile
+            uint32_t *d_planes = (uint32_t *)(d + o);
+            o = up256(o + b_seq * qbits / 2);
+            sd_tile *d_tiles2 = (sd_tile *)(d + o);
+            if ((rc = sd_qual_to_planes_on(ctx, ctx->stream, &db, qbits, hb->qual_dict, d_planes, d_tiles2))) return rc;
+            db.qual = (const uint8_t *)d_planes;
+            db.tiles = d_tiles2;
+            db.qual_bits = qbits;
+            db.qual_form = 1;
+            db.max_tile_qual = hb->max_tile_seq / 8u * 4u * qbits;
+        }
         rc = count_on_stream(ctx, &db, params, ctx->stream, nullptr, false);
         if (rc) return rc;
         SD_CUDA(ctx, cudaEventRecord(ctx->ev_done[buf], ctx->stream));

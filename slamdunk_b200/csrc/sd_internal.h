@@ -71,6 +71,8 @@ struct sd_ctx {
 int sd_fail(sd_ctx *ctx, int code, const char *fmt, ...);
 int sd_qual_unpack_on(sd_ctx *ctx, cudaStream_t stream, const uint8_t *d_packed, uint64_t n_bases, uint32_t bits,
                       const uint8_t *dict16, uint8_t *d_qual);   // sd_qual.cu
+int sd_qual_to_planes_on(sd_ctx *ctx, cudaStream_t stream, const sd_batch *b, uint32_t bits, const uint8_t *dict16, uint32_t *d_planes,
+                         sd_tile *d_tiles_out);   // sd_qual.cu
 #define SD_CUDA(ctx, call)                                                                        \
     do {                                                                                          \
         cudaError_t e__ = (call);                                                                 \

@@ -4,6 +4,8 @@
 // part of a batch, and sequencers emit few distinct values (Illumina bins qualities into 4-8 levels), so a HOST batch may
 // hold 2- or 4-bit dictionary codes instead (sd_batch.qual_bits / qual_dict): sd_count_host copies the codes and expands
 // them on the device, next to the kernel that consumes them.
+#include <algorithm>
+
 #include "sd_internal.h"
 
 namespace {
@@ -170,4 +172,111 @@ extern "C" int sd_seq_pack(sd_ctx *ctx, const sd_batch *b, uint32_t *d_seq2, sd_
     ctx->launches++;
     SD_CUDA(ctx, cudaGetLastError());
     return SD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Plane form of the quality column (sd_batch.qual_form = 1): bit-planes of the dictionary code per 32-base group, in the
+// group-major tile geometry of the SEQ column, so that the count kernel stages a tile's qualities with the tile and tests
+// 32 bases per LOP3 pair instead of fetching one byte per candidate.
+extern "C" int sd_qual_dict(sd_ctx *ctx, const uint8_t *d_qual, uint64_t n_bases, uint32_t *bits, uint8_t *dict16) {
+    if (!ctx || !d_qual || !bits || !dict16) return sd_fail(ctx, SD_ERR_ARG, "sd_qual_dict: null argument");
+    if (n_bases % 16) return sd_fail(ctx, SD_ERR_ARG, "quality column length must be a multiple of 16");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    *bits = 8;
+    memset(dict16, 0, 16);
+    if (n_bases == 0) { *bits = 2; return SD_OK; }
+    unsigned int *d_seen = nullptr, seen[8];
+    SD_CUDA(ctx, cudaMalloc(&d_seen, sizeof seen));
+    cudaMemsetAsync(d_seen, 0, sizeof seen, ctx->stream);
+    qual_seen_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(d_qual, n_bases, d_seen);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(seen, d_seen, sizeof seen, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_seen);
+    if (e != cudaSuccess) return sd_fail(ctx, SD_ERR_CUDA, "sd_qual_dict: %s", cudaGetErrorString(e));
+    int distinct = 0;
+    for (int v = 0; v < 256; v++)
+        if ((seen[v >> 5] >> (v & 31)) & 1u) {
+            if (distinct < 16) dict16[distinct] = (uint8_t)v;
+            distinct++;
+        }
+    if (distinct <= 16) *bits = distinct <= 4 ? 2u : 4u;
+    return SD_OK;
+}
+
+namespace {
+// one warp per tile, lane = row slot; every (group, row) slot of the tile's block is written (zeros past the read's end)
+template <int QB>
+__global__ void qual_planes_kernel(const sd_read_rec *rec, const uint8_t *qual, const sd_tile *tiles, uint32_t n_tiles,
+                                   uint32_t seq_group_bytes, CodeTable t, uint32_t *planes) {
+    __shared__ uint8_t lut[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = t.code[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t tile = warp; tile < n_tiles; tile += n_warps) {
+        const uint32_t lseq = rec[(size_t)tile * 32 + lane].lseq_ncig & 0xFFFFu;
+        uint32_t off = lseq;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, off, d);
+            if ((int)lane >= d) off += y;
+        }
+        off -= lseq;
+        const sd_tile t0 = tiles[tile], t1 = tiles[tile + 1];
+        const uint64_t group0 = t0.seq_off / seq_group_bytes;                                  // (group, row) slots before this tile
+        const uint32_t n_grp = (uint32_t)((t1.seq_off - t0.seq_off) / seq_group_bytes) / 32u;  // groups per row slot
+        const uint8_t *q = qual + t0.qual_off + off;
+        for (uint32_t g = 0; g < n_grp; g++) {
+            uint32_t p[QB];
+#pragma unroll
+            for (int b = 0; b < QB; b++) p[b] = 0u;
+            const uint32_t lo = 32u * g, hi = min(lseq, lo + 32u);
+            for (uint32_t j = lo; j < hi; j++) {
+                const uint32_t c = lut[q[j]];
+#pragma unroll
+                for (int b = 0; b < QB; b++) p[b] |= ((c >> b) & 1u) << (j - lo);
+            }
+            uint32_t *dst = planes + (group0 + (uint64_t)g * 32u + lane) * QB;
+#pragma unroll
+            for (int b = 0; b < QB; b++) dst[b] = p[b];
+        }
+    }
+}
+__global__ void tiles_qual_planes_kernel(const sd_tile *in, uint32_t n, uint32_t seq_group_bytes, uint32_t plane_group_bytes, sd_tile *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sd_tile t = in[i];
+    t.qual_off = t.seq_off / seq_group_bytes * plane_group_bytes;
+    out[i] = t;
+}
+}  // namespace
+
+int sd_qual_to_planes_on(sd_ctx *ctx, cudaStream_t stream, const sd_batch *b, uint32_t bits, const uint8_t *dict16, uint32_t *d_planes,
+                         sd_tile *d_tiles_out) {
+    if (bits != 2 && bits != 4) return sd_fail(ctx, SD_ERR_ARG, "sd_qual_to_planes: 2 or 4 planes");
+    if (b->tile_reads != 32) return sd_fail(ctx, SD_ERR_ARG, "sd_qual_to_planes: tile_reads must be 32");
+    if (b->qual_form != 0 || (b->qual_bits != 0 && b->qual_bits != 8)) return sd_fail(ctx, SD_ERR_ARG, "sd_qual_to_planes: the qual column must hold bytes");
+    CodeTable t;
+    memset(&t, 0, sizeof t);
+    for (uint32_t c = 0; c < (1u << bits); c++)
+        if (c == 0 || dict16[c] > dict16[c - 1]) t.code[dict16[c]] = (uint8_t)c;   // entries past the used ones are zero
+    const uint32_t sgb = b->seq_bits == 2 ? 8u : 16u;
+    if (b->n_tiles) {
+        const uint32_t blocks = std::min<uint32_t>((b->n_tiles + 7u) / 8u, (uint32_t)ctx->num_sms * 8u);
+        if (bits == 2) qual_planes_kernel<2><<<blocks, 256, 0, stream>>>(b->rec, b->qual, b->tiles, b->n_tiles, sgb, t, d_planes);
+        else qual_planes_kernel<4><<<blocks, 256, 0, stream>>>(b->rec, b->qual, b->tiles, b->n_tiles, sgb, t, d_planes);
+        ctx->launches++;
+    }
+    tiles_qual_planes_kernel<<<(b->n_tiles + 1 + 255) / 256, 256, 0, stream>>>(b->tiles, b->n_tiles + 1, sgb, 4u * bits, d_tiles_out);
+    ctx->launches++;
+    SD_CUDA(ctx, cudaGetLastError());
+    return SD_OK;
+}
+
+extern "C" int sd_qual_to_planes(sd_ctx *ctx, const sd_batch *b, uint32_t bits, const uint8_t *dict16, uint32_t *d_planes,
+                                 sd_tile *d_tiles_out) {
+    if (!ctx || !b || !dict16 || !d_planes || !d_tiles_out) return sd_fail(ctx, SD_ERR_ARG, "sd_qual_to_planes: null argument");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sd_qual_to_planes_on(ctx, ctx->stream, b, bits, dict16, d_planes, d_tiles_out);
 }

@@ -228,10 +228,45 @@ def algorithmic_bytes_per_read(read_len, mean_cigar_ops):
     return (read_len + 1) // 2 + read_len + 4.0 * mean_cigar_ops + 17
 
 
-def layout_bytes_per_read(read_len, mean_cigar_ops, seq_bits=4):
+def layout_bytes_per_read(read_len, mean_cigar_ops, seq_bits=4, qual_planes=0):
     """Bytes per read of the columns as THIS layout holds them in HBM: SEQ in 32-base groups of
-    seq_bits planes, QUAL bytes, CIGAR ops, the 20-byte record.  (The count kernel touches fewer: QUAL only at candidates.)"""
-    return seq_bits * 4 * ((read_len + 31) // 32) + read_len + 4.0 * mean_cigar_ops + 20
+    seq_bits planes, QUAL as bytes (of which the count kernel touches only those at candidates) or as qual_planes
+    bit-planes per group, CIGAR ops, the 20-byte record."""
+    groups = (read_len + 31) // 32
+    return seq_bits * 4 * groups + (qual_planes * 4 * groups if qual_planes else read_len) + 4.0 * mean_cigar_ops + 20
+
+
+def to_qual_planes(db: DeviceBatch, eng):
+    """The same device batch (2-bit SEQ form) with its quality column as bit-planes of the dictionary code (sd_qual_dict +
+    sd_qual_to_planes, sd_batch.qual_form = 1) -- what sd_count_host hands the kernel for a file with at most 16 distinct
+    qualities.  Returns None when the column has more distinct values than that (the byte column stays)."""
+    nt = int(db.batch.n_tiles)
+    tl = db.tensors["tiles"].view(torch.int64)
+    n_q = int(tl[4 * nt + 1].item()) if nt else 0
+    n_seq = int(tl[4 * nt].item()) if nt else 0
+    bits = ctypes.c_uint32(8)
+    dict16 = (ctypes.c_uint8 * 16)()
+    eng._chk(eng.lib.sd_qual_dict(eng.ctx, db.tensors["qual"].data_ptr(), n_q, ctypes.byref(bits), dict16), "sd_qual_dict")
+    if bits.value == 8:
+        return None
+    assert int(db.batch.seq_bits) == 2
+    with torch.cuda.stream(eng.stream):
+        planes = torch.zeros(max(16, n_seq * bits.value // 2), dtype=torch.uint8, device=db.tensors["seq"].device)
+        tiles2 = torch.empty_like(db.tensors["tiles"])
+    eng.stream.synchronize()
+    eng._chk(eng.lib.sd_qual_to_planes(eng.ctx, ctypes.byref(db.batch), bits.value, dict16, planes.data_ptr(), tiles2.data_ptr()),
+             "sd_qual_to_planes")
+    eng.synchronize()
+    tens = dict(db.tensors)
+    tens["qual"], tens["tiles"] = planes, tiles2
+    b = L.Batch()
+    ctypes.memmove(ctypes.byref(b), ctypes.byref(db.batch), ctypes.sizeof(L.Batch))
+    b.qual, b.tiles = planes.data_ptr(), tiles2.data_ptr()
+    b.qual_bits, b.qual_form = bits.value, 1
+    for i in range(16):
+        b.qual_dict[i] = dict16[i]
+    b.max_tile_qual = int(db.batch.max_tile_seq) // 8 * 4 * bits.value
+    return DeviceBatch(b, tens)
 
 
 def to_seq2(db: DeviceBatch, eng) -> DeviceBatch:

@@ -376,3 +376,60 @@ def test_time_course_samples_counted_in_one_batched_run():
     wl.set_time_point(None)
     assert tc_reads[0] < tc_reads[1] < tc_reads[2] < tc_reads[3]
     eng.close()
+
+
+@pytest.mark.parametrize("read_len,n_reads,mode,slow,min_qual,n_qual", [
+    (100, 150_000, "cigar", False, 27, 3), (100, 60_000, "cigar", False, 31, 3), (100, 60_000, "cigar", False, 0, 3), (100, 60_000, "cigar", False, 50, 3),
+    (150, 80_000, "verify", False, 27, 3), (250, 40_000, "mp", False, 27, 3), (36, 30_000, "cigar", False, 20, 3), (400, 8_000, "cigar", False, 27, 3),
+    (100, 20_000, "cigar", True, 27, 3), (100, 60_000, "cigar", False, 27, 11), (150, 40_000, "verify", False, 24, 11), (100, 30_000, "cigar", False, 27, 40)])
+def test_plane_form_qualities_count_like_the_byte_column(read_len, n_reads, mode, slow, min_qual, n_qual):
+    """sd_batch.qual_form = 1 (sd_qual_dict + sd_qual_to_planes): every output identical to the run on the byte column -- 2 and 4
+    planes, thresholds below / between / above the dictionary values, all mismatch sources, the per-base path, from the device
+    and through sd_count_host (which builds the planes itself); more than 16 distinct qualities: no plane form."""
+    import torch
+    from slamdunk_b200 import _lib as L
+    from slamdunk_b200.engine import make_params
+    from slamdunk_b200.synth import batch_to_host, to_qual_planes, to_seq2
+    eng, wl = _setup()
+    p = wl.params(seed=31, first_read=0, n_reads=n_reads, read_len=read_len, frac_softclip=0.1, frac_indel=0.08,
+                  frac_antisense=0.05, frac_labelled=0.8)
+    db, _ = wl.generate(p, want_mp=True)
+    if n_qual != 3:      # spread the three generated values over n_qual distinct ones (pad bytes between tiles stay 0)
+        q = db.tensors["qual"]
+        idx = torch.arange(q.numel(), device=q.device, dtype=torch.int64)
+        spread = (q.to(torch.int64) - 19 + (idx * 7919) % (n_qual // 3 + 1) * 3).clamp(2, 93).to(torch.uint8)
+        q.copy_(torch.where(q > 0, spread, q))
+    db2 = to_seq2(db, eng)
+    params = make_params(min_qual, 1, {"cigar": 0, "mp": 1, "verify": 2}[mode], force_slow_path=slow)
+    read_tc_b = torch.zeros(int(db.batch.n_tiles) * 32, dtype=torch.uint8, device=eng.device)
+    eng.count(db2, params, read_tc=read_tc_b)
+    eng.finalize()
+    want = eng.results()
+    dbq = to_qual_planes(db2, eng)
+    if n_qual > 16:
+        assert dbq is None
+        eng.close()
+        return
+    assert dbq.batch.qual_form == 1 and dbq.batch.qual_bits == (2 if n_qual <= 4 else 4)
+    eng.reset_outputs()
+    read_tc_p = torch.zeros_like(read_tc_b)
+    eng.count(dbq, params, read_tc=read_tc_p)
+    eng.finalize()
+    got = eng.results()
+    assert want["stats"][L.SD_S_COUNTED] == n_reads
+    if min_qual < 40:
+        assert want["counters"][:, L.SD_C_CONV_ON_T].sum() > 0
+    else:
+        assert want["counters"][:, L.SD_C_CONV_ON_T].sum() == 0
+    for k in ("counters", "stats", "pos_cov", "pos_tc", "tcontent"):
+        assert np.array_equal(want[k], got[k]), k
+    assert torch.equal(read_tc_b, read_tc_p)
+    hb, keep = batch_to_host(db2, eng)
+    assert hb.seq_bits == 2 and hb.qual_bits in (2, 4)
+    eng.reset_outputs()
+    eng.count_host(hb, params)
+    eng.finalize()
+    got = eng.results()
+    for k in ("counters", "stats", "pos_cov", "pos_tc"):
+        assert np.array_equal(want[k], got[k]), "host " + k
+    eng.close()
