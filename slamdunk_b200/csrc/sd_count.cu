@@ -91,6 +91,8 @@ struct CountArgs {
     uint32_t qual_planes;     // 0: qual column = bytes, read in place; 2 / 4: group-major bit-planes of the dictionary code
                               // (sd_batch.qual_form == 1), staged with the tile
     uint32_t q_cmin;          // plane form: quality >= min_qual  <=>  code >= q_cmin (codes ascend with quality); 2^planes: none
+    uint32_t q_m[4];          // the same test as all-ones / all-zeros masks (constant-bank operands of the LOP3s):
+                              // 2 planes: ok = (((p1 & (p0 | m0)) | (p0 & m1)) | m2) & m3;  4 planes: m[b] = bit b of q_cmin
     // shared-memory stage layout (bytes, all multiples of 128)
     uint32_t cap_rec, cap_seq, cap_qual, cap_cig, cap_mp;
     uint32_t n_stages;
@@ -208,19 +210,25 @@ __device__ __forceinline__ uint32_t row_group_is_base(const uint32_t *row, uint3
 // Bit-plane quality column (sd_batch.qual_form == 1): QB words per 32-base group, bit-plane b of the base's dictionary
 // code.  sd_decode_bam / sd_qual_dict assign codes in ascending quality order, so the reference's test
 // `readQlty >= minQual` (SlamSeqFile.py:330) is the bit-sliced comparison code >= q_cmin: 2 LOP3 per plane for 32 bases.
-template <int QB>
-__device__ __forceinline__ uint32_t planes_ge(const uint32_t (&p)[QB], uint32_t cmin) {
+// CM: take the comparison constant as ready-made masks from the parameter block (A.q_m) instead of deriving them from
+// A.q_cmin.  Same result; which form the compiler schedules better depends on the window size (measured: the derived
+// form at W = 4, 1.675 vs 1.75 ms at 100 bp; the mask form from W = 6 on, 1.82 vs 2.31 ms at 150 bp).
+template <int QB, bool CM>
+__device__ __forceinline__ uint32_t planes_ge(const uint32_t (&p)[QB], const CountArgs &A) {
+    if (CM && QB == 2)   // code >= c over two planes: c = 3: p1 & p0; 2: p1; 1: p1 | p0; 0: all; 4: none
+        return (((p[1] & (p[0] | A.q_m[0])) | (p[0] & A.q_m[1])) | A.q_m[2]) & A.q_m[3];
+    const uint32_t cmin = A.q_cmin;
     uint32_t gt = 0u, eq = 0xFFFFFFFFu;
 #pragma unroll
     for (int b = QB - 1; b >= 0; b--) {
-        const uint32_t cb = 0u - ((cmin >> b) & 1u);
+        const uint32_t cb = CM ? A.q_m[b] : 0u - ((cmin >> b) & 1u);
         gt |= eq & p[b] & ~cb;
         eq &= ~(p[b] ^ cb);
     }
     return (cmin >> QB) ? 0u : (gt | eq);
 }
-template <int QB>
-__device__ __forceinline__ uint32_t row_group_qual_ok(const uint32_t *row, uint32_t g, uint32_t cmin) {
+template <int QB, bool CM = false>
+__device__ __forceinline__ uint32_t row_group_qual_ok(const uint32_t *row, uint32_t g, const CountArgs &A) {
     uint32_t p[QB];
     if (QB == 2) {
         const uint2 x = reinterpret_cast<const uint2 *>(row)[g * SD_TILE_READS];
@@ -229,14 +237,14 @@ __device__ __forceinline__ uint32_t row_group_qual_ok(const uint32_t *row, uint3
         const uint4 x = reinterpret_cast<const uint4 *>(row)[g * SD_TILE_READS];
         p[0] = x.x; p[1] = x.y; p[QB > 2 ? 2 : 0] = x.z; p[QB > 2 ? 3 : 1] = x.w;
     }
-    return planes_ge<QB>(p, cmin);
+    return planes_ge<QB, CM>(p, A);
 }
 // "Quality" of read base qi (0 <= qi < l_seq) for a `>= A.min_qual` test: the byte itself, or on the plane form 255 / -1
 // for pass / fail (min_qual <= 0 makes q_cmin 0: everything passes there too).
 template <int QB>
 __device__ __forceinline__ int qual_for_test(const CountArgs &A, const uint8_t *qual, int qi) {
     if (QB == 0) return (int)__ldg(qual + qi);
-    const uint32_t ok = row_group_qual_ok<(QB ? QB : 2)>(reinterpret_cast<const uint32_t *>(qual), (uint32_t)qi >> 5, A.q_cmin);
+    const uint32_t ok = row_group_qual_ok<(QB ? QB : 2)>(reinterpret_cast<const uint32_t *>(qual), (uint32_t)qi >> 5, A);
     return ((ok >> (qi & 31)) & 1u) ? 255 : -1;
 }
 __device__ __forceinline__ int qual_for_test_rt(const CountArgs &A, const uint8_t *qual, int qi) {   // per-base path: form known at run time
@@ -503,7 +511,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             uint32_t m = row_group_is_base<SB>(v.seq, kc, sm);   // this row's slot of group kc; the tile block is group-major
             // plane-form qualities, plain CIGAR walk: the quality test is one more mask on the read side, for 32 bases at once
             if (QB > 0 && A.mismatch_source == SD_MISMATCH_CIGAR)
-                m &= row_group_qual_ok<(QB ? QB : 2)>(reinterpret_cast<const uint32_t *>(v.qual), kc, A.q_cmin);
+                m &= row_group_qual_ok<(QB ? QB : 2), (W > 4)>(reinterpret_cast<const uint32_t *>(v.qual), kc, A);
             M[k] = ((uint32_t)k < ng) ? m : 0u;
         }
         if (SIMPLE) {
@@ -785,7 +793,7 @@ template <int W, int SB, int QB>
 __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kernel(const __grid_constant__ CountArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual;
-    const uint32_t warp_bytes = A.n_stages * stage_bytes + 128u;   // stages | barriers + tile qual offsets
+    const uint32_t warp_bytes = A.n_stages * stage_bytes + 256u;   // stages | barriers + tile qual offsets | per-lane copy descriptors
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t nwarp = blockDim.x >> 5;
     uint32_t *s_stats = reinterpret_cast<uint32_t *>(smem);                 // [SD_SMEM_STATS], first 128 bytes
@@ -815,37 +823,56 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
         return t < A.n_tiles ? t : 0xFFFFFFFFu;
     };
     // @region tma_issue
-    auto issue = [&](uint64_t tile, uint32_t stage) {
+    // A tile is one bulk copy per column.  Lanes 0..4 issue them side by side -- lane c owns column c (records, SEQ, CIGAR,
+    // MP, quality planes) -- so the address arithmetic runs once for all columns instead of once per column on lane 0, which
+    // the other lanes wait for.  The per-lane descriptors live in the warp's shared-memory region (one LDS.128 per tile
+    // instead of five registers per thread).
+    uint4 *s_col = reinterpret_cast<uint4 *>(mine + (size_t)A.n_stages * stage_bytes + 128u);   // [5] {src lo, src hi, stage offset, field | travels << 8}
+    if (lane < 5u) {
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(A.rec);
+        uint32_t dst = 0u, fld = 0u, col = 1u;   // col: does this lane's column travel with the tile at all
+        if (lane == 1) { src = reinterpret_cast<const unsigned char *>(A.seq); dst = A.cap_rec; fld = 0u; }
+        if (lane == 2) { src = reinterpret_cast<const unsigned char *>(A.cigar); dst = A.cap_rec + A.cap_seq; fld = 2u; }
+        if (lane == 3) { src = reinterpret_cast<const unsigned char *>(A.mp); dst = A.cap_rec + A.cap_seq + A.cap_cig; fld = 3u; col = A.mp != nullptr; }
+        if (lane == 4) { src = A.qual; dst = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp; fld = 1u; col = QB > 0; }
+        const unsigned long long a = reinterpret_cast<unsigned long long>(src);
+        s_col[lane] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), dst, fld | (col << 8));
+    }
+    __syncwarp();
+    auto issue = [&](uint64_t tile, uint32_t stage) {   // lanes 0..4 together
         unsigned char *base = stages + (size_t)stage * stage_bytes;
-        const sd_tile t0 = A.tiles[tile], t1 = A.tiles[tile + 1];
-        const uint32_t b_rec = SD_TILE_READS * (uint32_t)sizeof(sd_read_rec);
-        const uint32_t b_seq = (uint32_t)(t1.seq_off - t0.seq_off);
-        const uint32_t b_cig = (uint32_t)(t1.cig_off - t0.cig_off);
-        const uint32_t b_mp = A.mp ? (uint32_t)(t1.mp_off - t0.mp_off) : 0u;
-        s_qoff[stage] = t0.qual_off;
-        if (A.qual_prefetch) {   // pull the tile's base qualities into L2 ahead of use: the candidate test then pays L2, not DRAM latency
-            const uint32_t b_q = (uint32_t)(t1.qual_off - t0.qual_off) & ~15u;
-            if (b_q) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.qual + t0.qual_off), "r"(b_q) : "memory");
+        const uint4 cd = s_col[lane];
+        const unsigned char *my_src = reinterpret_cast<const unsigned char *>((unsigned long long)cd.x | ((unsigned long long)cd.y << 32));
+        const uint32_t my_dst = cd.z, my_fld = cd.w & 0xFFu;
+        const bool my_col = (cd.w >> 8) != 0u;
+        const unsigned long long *tp = reinterpret_cast<const unsigned long long *>(A.tiles + tile);
+        unsigned long long off0 = tp[my_fld], off1 = tp[4u + my_fld];
+        if (lane == 0) {
+            off0 = tile * (SD_TILE_READS * (unsigned long long)sizeof(sd_read_rec));
+            off1 = off0 + SD_TILE_READS * (unsigned long long)sizeof(sd_read_rec);
         }
-        const uint32_t b_qpl = QB > 0 ? (uint32_t)(t1.qual_off - t0.qual_off) : 0u;   // plane-form qualities travel with the tile
-        mbar_arrive_expect_tx(&full[stage], b_rec + b_seq + b_cig + b_mp + b_qpl);
-        if (QB > 0 && b_qpl)
-            bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp, A.qual + t0.qual_off, b_qpl, &full[stage]);
-        bulk_g2s(base, reinterpret_cast<const unsigned char *>(A.rec) + tile * b_rec, b_rec, &full[stage]);
-        if (b_seq) bulk_g2s(base + A.cap_rec, reinterpret_cast<const unsigned char *>(A.seq) + t0.seq_off, b_seq, &full[stage]);
-        if (b_cig)
-            bulk_g2s(base + A.cap_rec + A.cap_seq, reinterpret_cast<const unsigned char *>(A.cigar) + t0.cig_off, b_cig, &full[stage]);
-        if (b_mp)
-            bulk_g2s(base + A.cap_rec + A.cap_seq + A.cap_cig, reinterpret_cast<const unsigned char *>(A.mp) + t0.mp_off, b_mp,
-                     &full[stage]);
+        if (lane == 4) {
+            s_qoff[stage] = off0;
+            if (QB == 0 && A.qual_prefetch) {   // byte form: pull the tile's base qualities into L2 ahead of use
+                const uint32_t b_q = (uint32_t)(off1 - off0) & ~15u;
+                if (b_q) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.qual + off0), "r"(b_q) : "memory");
+            }
+        }
+        const uint32_t bytes = my_col ? (uint32_t)(off1 - off0) : 0u;
+        const uint32_t total = __reduce_add_sync(0x1Fu, bytes);
+        if (lane == 0) mbar_arrive_expect_tx(&full[stage], total);
+        __syncwarp(0x1Fu);
+        if (bytes) bulk_g2s(base + my_dst, my_src + off0, bytes, &full[stage]);
     };
 
-    if (lane == 0) {
-        for (uint32_t s = 0; s < A.n_stages; s++) {
-            const uint32_t t = claim();
+    for (uint32_t s = 0; s < A.n_stages; s++) {
+        uint32_t t = 0u;
+        if (lane == 0) {
+            t = claim();
             s_tile[s] = t;
-            if (t != 0xFFFFFFFFu) issue(t, s);
         }
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (lane < 5u && t != 0xFFFFFFFFu) issue(t, s);
     }
     __syncwarp();
 
@@ -970,11 +997,13 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
 
         // @region tile_end
         __syncwarp();   // every lane is done with this stage
+        uint32_t next = 0u;
         if (lane == 0) {
-            const uint32_t next = claim();
+            next = claim();
             s_tile[stage] = next;
-            if (next != 0xFFFFFFFFu) issue(next, stage);
         }
+        next = __shfl_sync(0xFFFFFFFFu, next, 0);
+        if (lane < 5u && next != 0xFFFFFFFFu) issue(next, stage);
         __syncwarp();
         if (++stage == A.n_stages) {
             stage = 0;
@@ -1355,7 +1384,7 @@ static int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool tim
     // Per-warp ring of n_stages tiles.  Two stages hide the copy latency behind the previous tile, but shared memory is taken
     // from the same 228 KB as the L1 that serves the reference window / annotation table lookups, and it can cost a resident
     // CTA: the second stage is used only when it neither lowers the CTAs per SM nor leaves L1 less than 56 KB.
-    auto warp_bytes = [&](uint32_t ns) { return (size_t)ns * stage_bytes + 128u; };
+    auto warp_bytes = [&](uint32_t ns) { return (size_t)ns * stage_bytes + 256u; };
     if (128u + warp_bytes(1) > (size_t)max_smem)
         return sd_fail(ctx, SD_ERR_LIMIT, "a 32-read tile needs %u bytes of shared memory; reads are too long for this kernel", stage_bytes);
     auto plan = [&](uint32_t ns, uint32_t &warps, size_t &smem, int &per_sm) -> int {
@@ -1451,6 +1480,14 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
         uint32_t cmin = 0;
         while (cmin < used && (int)b->qual_dict[cmin] < p->min_qual) cmin++;
         A.q_cmin = cmin < used ? cmin : (1u << b->qual_bits);
+        if (b->qual_bits == 2) {
+            const uint32_t c = A.q_cmin, ones = 0xFFFFFFFFu;
+            A.q_m[0] = (c == 1 || c == 2) ? ones : 0u;   // p1 alone suffices
+            A.q_m[1] = c == 1 ? ones : 0u;               // p0 alone suffices
+            A.q_m[2] = c == 0 ? ones : 0u;               // everything passes
+            A.q_m[3] = c >= 4 ? 0u : ones;               // nothing passes
+        } else
+            for (int k = 0; k < 4; k++) A.q_m[k] = 0u - ((A.q_cmin >> k) & 1u);
     }
     for (int s = 0; s < 2; s++) {
         A.refx[s] = ctx->refx[s];
