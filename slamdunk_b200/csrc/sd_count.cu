@@ -769,10 +769,13 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 // issues the TMA bulk copies (records, sliced SEQ, CIGAR ops and, when needed, MP entries of one
 // tile per stage) two tiles ahead, all lanes wait on the stage's mbarrier, each lane handles one
 // read, and the lane re-arms the stage.  No warp ever waits for another warp, there is no block
-// barrier in the loop and no producer thread spinning.  The QUAL column is not staged: a base
-// quality is needed only where the read shows a C over a reference T (about one base per read),
-// so it is fetched from global memory right there -- this keeps the shared-memory footprint per
-// warp small enough for high occupancy and leaves most of the qual column's DRAM sectors untouched.
+// barrier in the loop and no producer thread spinning.  Base qualities come in one of two forms.
+// Plane form (QB = 2 / 4, files with at most 4 / 16 distinct qualities): bit-planes of the dictionary
+// code in the SEQ column's geometry, staged with the tile (8 / 16 bytes per 32 bases); the test
+// `quality >= minQual` is a bit-sliced compare ANDed into the read mask.  Byte form (QB = 0): the column
+// is NOT staged -- a quality is needed only where the read shows a C over a reference T (about one base
+// per read), so it is fetched from global memory right there, which keeps the shared-memory footprint
+// small and leaves most of the column's DRAM sectors untouched.
 // ---------------------------------------------------------------------------------------
 // @region kernel_setup
 #define SD_SMEM_STATS 8

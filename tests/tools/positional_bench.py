@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """`alleyoop positional-tracks` end to end on a synthetic coordinate-sorted BAM (needs a GPU): where the time goes
-(host decode, device scan, device run-length compaction + text) and, beside it, the oracle restatement of the reference
-on a small sample of the same kind.   python tools/positional_bench.py [n_reads] [genome_bp]"""
+(host decode, device scan, device run-length compaction + text) and, beside it, the oracle restatement of the reference (test infrastructure: that is why this script lives under tests/)
+on a small sample of the same kind.   python tests/tools/positional_bench.py [n_reads] [genome_bp]"""
 import io
 import json
 import os
@@ -9,7 +9,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

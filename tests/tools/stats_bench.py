@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """The iterator-based alleyoop statistics end to end on a synthetic coordinate-sorted BAM (needs a GPU): wall time per
-tool, the sd_read_stats kernel inside it, and beside them the oracle restatement of the reference on a small sample of
-the same kind.   python tools/stats_bench.py [n_reads] [genome_bp]"""
+tool, the sd_read_stats kernel inside it, and beside them the oracle restatement of the reference (test infrastructure: that is why this script lives under tests/) on a small sample of
+the same kind.   python tests/tools/stats_bench.py [n_reads] [genome_bp]"""
 import json
 import os
 import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
