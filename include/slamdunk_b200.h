@@ -393,8 +393,8 @@ int sd_write_track(const char *path, const char *chrom, int kind, uint64_t n_run
                    const double *h_val, const uint8_t *h_isfloat);
 
 /* ------------------------------------------------------------------ conversion statistics over the same per-read scan
- * `alleyoop rates / tcperreadpos / utrrates / tcperutrpos / snpeval` (dunks/stats.py:85-131, 591-657, 331-528, 659-772,
- * 774-849) and the per-read lists of computeTconversions(mle=True) (dunks/tcounter.py:233-243) all iterate
+ * `alleyoop rates / tcperreadpos / utrrates / tcperutrpos / snpeval / tccontext` (dunks/stats.py:85-131, 591-657, 331-528,
+ * 659-772, 774-849, 226-330) and the per-read lists of computeTconversions(mle=True) (dunks/tcounter.py:233-243) all iterate
  * SlamSeqBamIterator (slamseq/SlamSeqFile.py:364-402) and look at the COMPLETE mismatch list of every read -- all 25
  * conversion types of the MP tag that pass the base-quality test -- plus the read's 5 x 5 conversion matrix
  * (computeRatesForRead, SlamSeqFile.py:231-249).  sd_read_stats does that scan for one device-resident batch decoded
@@ -429,6 +429,11 @@ typedef struct sd_stats_args {
     int64_t *d_utrpos;             /* [6][utr_norm + 1] over the last utr_norm positions of '+' rows / the first of '-' rows
                                       (stats.py:693-747): other mismatches fwd, rev; T>C fwd, A>G rev; coverage fwd, rev in
                                       DIFFERENCE form; the reverse arrays in the reference's own (unreversed) index */
+    int64_t *d_context;            /* [2][2][5] `alleyoop tccontext` (stats.py:226-330): bases next to every T of a forward read / every A
+                                      of a reverse read in the READ sequence -- [0] 5' neighbour, [1] 3' neighbour (of the T strand:
+                                      reverse reads are complemented and their sides swapped), [.][0] forward / [.][1] reverse reads,
+                                      [.][.][A, C, G, T, N].  Over every record placed on a FASTA chromosome, unmapped ones included
+                                      (bamFile.fetch(region=chromosome), no iterator) */
     sd_read_pair *d_pairs;         /* [pair_capacity] */
     uint64_t pair_capacity;
     unsigned long long *d_n_pairs; /* number of pairs found (may exceed the capacity: then only the first are stored) */

@@ -5,6 +5,7 @@ path's read iterator.  TEST INFRASTRUCTURE O
 Pure Python, loop for loop after the reference (paths relative to /root/reference/slamdunk):
     SlamSeqBamIterator / fillMismatchesNGM / computeRatesForRead   slamseq/SlamSeqFile.py:231-249, 313-402
     statsComputeOverallRates        dunks/stats.py:85-131      (alleyoop rates)
+    statsComputeTCContext           dunks/stats.py:226-330     (alleyoop tccontext)
     statsComputeOverallRatesPerUTR  dunks/stats.py:331-528     (alleyoop utrrates)
     tcPerReadPos                    dunks/stats.py:591-657     (alleyoop tcperreadpos)
     tcPerUtr                        dunks/stats.py:659-772     (alleyoop tcperutrpos)
@@ -202,6 +203,44 @@ def rates_file(referenceFile, bam, minBaseQual, outputCSV):
             for j in range(5):
                 print(str(fwd[i * 5 + j]) + "\t" + str(rev[i * 5 + j]) + "\t", end="", file=fo)
             print(file=fo)
+
+
+def tccontext_file(referenceFile, bam, outputCSV):
+    """statsComputeTCContext, stats.py:226-330: no iterator, no quality test -- the raw read sequences of every record
+    placed on a FASTA chromosome"""
+    front, back = ["AT", "CT", "GT", "TT", "NT"], ["TA", "TC", "TG", "TT", "TN"]
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}                  # utils/misc.py:276-280
+    counts = {"5": {"fwd": dict((c, 0) for c in front), "rev": dict((c, 0) for c in front)},
+              "3": {"fwd": dict((c, 0) for c in back), "rev": dict((c, 0) for c in back)}}
+    _text, bam_refs, records = bamio.read_bam(bam)
+    bam_names = [n for n, _l in bam_refs]
+    fasta = bamio.read_fasta(referenceFile)
+    for chromosome in fasta:
+        if chromosome not in bam_names:
+            raise ValueError("invalid contig `%s`" % chromosome)
+        rid = bam_names.index(chromosome)
+        for r in records:
+            if r.ref_id != rid:
+                continue
+            seq, rev = r.seq, bool(r.flag & 0x10)
+            for i in range(len(seq)):
+                if seq[i] == "T" and not rev:
+                    if i > 0:
+                        counts["5"]["fwd"][seq[i - 1] + "T"] += 1
+                    if i < len(seq) - 1:
+                        counts["3"]["fwd"]["T" + seq[i + 1]] += 1
+                if seq[i] == "A" and rev:
+                    if i < len(seq) - 1:
+                        counts["5"]["rev"][comp[seq[i + 1]] + "T"] += 1
+                    if i > 0:
+                        counts["3"]["rev"]["T" + comp[seq[i - 1]]] += 1
+    with open(outputCSV, "w") as fo:
+        print("\t".join(front), file=fo)
+        print("\t".join(str(counts["5"]["fwd"][c]) for c in front), file=fo)
+        print("\t".join(str(counts["5"]["rev"][c]) for c in front), file=fo)
+        print("\t".join(back), file=fo)
+        print("\t".join(str(counts["3"]["fwd"][c]) for c in back), file=fo)
+        print("\t".join(str(counts["3"]["rev"][c]) for c in back), file=fo)
 
 
 PLOT_CONVERSIONS = ["A>T", "A>G", "A>C", "C>A", "C>G", "C>T", "G>A", "G>C", "G>T", "T>A", "T>G", "T>C"]   # stats.py:349-353

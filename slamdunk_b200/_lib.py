@@ -89,7 +89,7 @@ class StatsArgs(ctypes.Structure):
     _fields_ = [("min_qual", ctypes.c_int32), ("conversion_threshold", ctypes.c_int32), ("strict", ctypes.c_int32),
                 ("max_read_length", ctypes.c_uint32), ("utr_norm", ctypes.c_uint32), ("d_order", ctypes.c_void_p),
                 ("d_rates", ctypes.c_void_p), ("d_readpos", ctypes.c_void_p), ("d_utr_rates", ctypes.c_void_p),
-                ("d_utr_snp", ctypes.c_void_p), ("d_utrpos", ctypes.c_void_p), ("d_pairs", ctypes.c_void_p),
+                ("d_utr_snp", ctypes.c_void_p), ("d_utrpos", ctypes.c_void_p), ("d_context", ctypes.c_void_p), ("d_pairs", ctypes.c_void_p),
                 ("pair_capacity", ctypes.c_uint64), ("d_n_pairs", ctypes.c_void_p)]
 
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """`alleyoop` sub-commands that ride on the GPU count path: `positional-tracks`, `read-separator`, the iterator-based
-statistics `rates`, `utrrates`, `tcperreadpos`, `tcperutrpos`, `snpeval` (CSV output; the R plots are not part of this
+statistics `rates`, `tccontext`, `utrrates`, `tcperreadpos`, `tcperutrpos`, `snpeval` (CSV output; the R plots are not part of this
 package) and the table tool `collapse` (same options, defaults and output names as the reference,
 slamdunk/alleyoop.py:115-262, 312-413, 450-575); the other alleyoop tools are plots and table utilities outside the
 accelerated path.
@@ -98,6 +98,16 @@ def runStatsRates(tid, bam, referenceFile, minMQ, outputDirectory):
     stepFinished()
 
 
+def runStatsTCContext(tid, bam, referenceFile, minMQ, outputDirectory):
+    """alleyoop.py:156-163"""
+    from .dunks import stats
+    outputCSV, outputPDF, outputLOG = _stats_files(bam, outputDirectory, "_tccontext")
+    log = getLogFile(outputLOG)
+    stats.statsComputeTCContext(referenceFile, bam, minMQ, outputCSV, outputPDF, log)
+    log.close()
+    stepFinished()
+
+
 def runStatsRatesUTR(tid, bam, referenceFile, minMQ, strictTCs, outputDirectory, utrFile, maxReadLength):
     """alleyoop.py:165-182"""
     from .dunks import stats
@@ -153,7 +163,7 @@ def runTcPerUtr(tid, bam, referenceFile, bed, minMQ, maxReadLength, outputDirect
     stepFinished()
 
 
-STATS_COMMANDS = ("rates", "utrrates", "snpeval", "tcperreadpos", "tcperutrpos")
+STATS_COMMANDS = ("rates", "tccontext", "utrrates", "snpeval", "tcperreadpos", "tcperutrpos")
 
 
 def build_parser():
@@ -194,6 +204,12 @@ def build_parser():
     p.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", default=SUPPRESS, help="Output directory for mapped BAM files.")
     p.add_argument("-r", "--reference", type=str, required=True, dest="referenceFile", default=SUPPRESS, help="Reference fasta file")
     p.add_argument("-mq", "--min-basequality", type=int, required=False, default=27, dest="mq", help="Minimal base quality for SNPs")
+    p.add_argument("-t", "--threads", type=int, required=False, default=1, dest="threads", help="Thread number")
+    p = sub.add_parser("tccontext", help="Calculate T->C conversion context on SLAM-seq datasets", formatter_class=ArgumentDefaultsHelpFormatter)
+    p.add_argument("bam", action="store", help="Bam file(s)", nargs="+")
+    p.add_argument("-o", "--outputDir", type=str, required=True, dest="outputDir", default=SUPPRESS, help="Output directory for mapped BAM files.")
+    p.add_argument("-r", "--reference", type=str, required=True, dest="referenceFile", default=SUPPRESS, help="Reference fasta file")
+    p.add_argument("-mq", "--min-basequality", type=int, required=False, default=0, dest="mq", help="Minimal base quality for SNPs")
     p.add_argument("-t", "--threads", type=int, required=False, default=1, dest="threads", help="Thread number")
     p = sub.add_parser("utrrates", help="Calculate conversion rates per UTR on SLAM-seq datasets")
     p.add_argument("bam", action="store", help="Bam file(s)", nargs="+")
@@ -243,7 +259,7 @@ def _run_stats(args):
     createDir(outputDirectory)
     n = args.threads
     command = args.command
-    label = {"rates": "rates", "snpeval": "SNPeval"}.get(command, command)
+    label = {"rates": "rates", "snpeval": "SNPeval", "tccontext": "TC context"}.get(command, command)
     message("Running alleyoop " + label + " for " + str(len(args.bam)) + " files (" + str(n) + " threads)")
     snpDirectory = getattr(args, "snpDir", None)
     vcfFile = getattr(args, "vcfFile", None)
@@ -251,6 +267,8 @@ def _run_stats(args):
         bam = args.bam[tid]
         if command == "rates":
             runStatsRates(tid, bam, args.referenceFile, args.mq, outputDirectory)
+        elif command == "tccontext":
+            runStatsTCContext(tid, bam, args.referenceFile, args.mq, outputDirectory)
         elif command == "utrrates":
             runStatsRatesUTR(tid, bam, args.referenceFile, args.mq, args.strictTCs, outputDirectory, args.bed, args.maxLength)
         elif command == "snpeval":

@@ -33,7 +33,7 @@ struct StatsArgs {
     const uint8_t *row_strand;  // 0 '+', 1 '-', 2 none
     int min_qual, conv_threshold, strict;
     uint32_t max_read_length, utr_norm;
-    unsigned long long *rates, *readpos, *utr_rates, *utr_snp, *utrpos;
+    unsigned long long *rates, *readpos, *utr_rates, *utr_snp, *utrpos, *context;
     sd_read_pair *pairs;
     unsigned long long pair_capacity;
     unsigned long long *n_pairs;
@@ -161,6 +161,53 @@ __global__ void __launch_bounds__(256) sd_stats_kernel(const StatsArgs A) {
             });
         }
         const bool is_tc_read = tc_count >= A.conv_threshold;               // SlamSeqFile.py:397-400
+
+        // ---- alleyoop tccontext (stats.py:256-287): neighbours of every T (forward reads) / A (reverse reads) of the read sequence
+        if (A.context) {
+            const bool in = !(flags & SD_F_PAD) && chrom != SD_REF_NONE;      // bamFile.fetch(region=chromosome): flag-unmapped records too
+            int c5[5] = {0, 0, 0, 0, 0}, c3[5] = {0, 0, 0, 0, 0};            // by the printed neighbour: A, C, G, T, N
+            if (in) {
+                const uint4 *blk = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(A.seq) + tile.seq_off);
+                const int n_grp = (int)((l_seq + 31u) >> 5);
+                uint32_t prev[5] = {0u, 0u, 0u, 0u, 0u};                         // exact-base masks of the previous group
+                uint4 p = n_grp ? __ldg(&blk[lane]) : make_uint4(0u, 0u, 0u, 0u);
+                for (int g = 0; g < n_grp; g++) {
+                    const uint4 nx = g + 1 < n_grp ? __ldg(&blk[(size_t)(g + 1) * 32 + lane]) : make_uint4(0u, 0u, 0u, 0u);
+                    const uint32_t cur[5] = {p.x & ~p.y & ~p.z & ~p.w, ~p.x & p.y & ~p.z & ~p.w, ~p.x & ~p.y & p.z & ~p.w,
+                                             ~p.x & ~p.y & ~p.z & p.w, p.x & p.y & p.z & p.w};
+                    const uint32_t nxt[5] = {nx.x & ~nx.y & ~nx.z & ~nx.w, ~nx.x & nx.y & ~nx.z & ~nx.w, ~nx.x & ~nx.y & nx.z & ~nx.w,
+                                             ~nx.x & ~nx.y & ~nx.z & nx.w, nx.x & nx.y & nx.z & nx.w};
+                    const uint32_t centre = strand ? cur[0] : cur[3];            // A on reverse reads, T on forward reads
+#pragma unroll
+                    for (int x = 0; x < 5; x++) {
+                        const uint32_t left = (cur[x] << 1) | (prev[x] >> 31);   // bit i: base i-1 is x
+                        const uint32_t right = (cur[x] >> 1) | (nxt[x] << 31);   // bit i: base i+1 is x
+                        const int cx = x == 4 ? 4 : 3 - x;                       // complement (misc.py:276-280)
+                        if (!strand) {
+                            c5[x] += __popc(centre & left);
+                            c3[x] += __popc(centre & right);
+                        } else {                                                 // front = next base, back = previous base, both complemented
+                            c5[cx] += __popc(centre & right);
+                            c3[cx] += __popc(centre & left);
+                        }
+                    }
+#pragma unroll
+                    for (int x = 0; x < 5; x++) prev[x] = cur[x];
+                    p = nx;
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < 5; x++) {
+                const int f5 = __reduce_add_sync(0xFFFFFFFFu, strand ? 0 : c5[x]), r5 = __reduce_add_sync(0xFFFFFFFFu, strand ? c5[x] : 0);
+                const int f3 = __reduce_add_sync(0xFFFFFFFFu, strand ? 0 : c3[x]), r3 = __reduce_add_sync(0xFFFFFFFFu, strand ? c3[x] : 0);
+                if (lane == 0) {
+                    add64(&A.context[0 + x], f5);
+                    add64(&A.context[5 + x], r5);
+                    add64(&A.context[10 + x], f3);
+                    add64(&A.context[15 + x], r3);
+                }
+            }
+        }
 
         // ---- genome-wide outputs (readsInChromosome: strand ".", every placed record)
         if (A.rates) {
@@ -314,6 +361,7 @@ extern "C" int sd_read_stats(sd_ctx *ctx, const sd_batch *b, const sd_stats_args
     A.rates = (unsigned long long *)a->d_rates; A.readpos = (unsigned long long *)a->d_readpos;
     A.utr_rates = (unsigned long long *)a->d_utr_rates; A.utr_snp = (unsigned long long *)a->d_utr_snp;
     A.utrpos = (unsigned long long *)a->d_utrpos;
+    A.context = (unsigned long long *)a->d_context;
     A.pairs = a->d_pairs; A.pair_capacity = a->pair_capacity; A.n_pairs = a->d_n_pairs;
     const uint32_t warps_per_block = 8;
     uint32_t blocks = (b->n_tiles + warps_per_block - 1) / warps_per_block;

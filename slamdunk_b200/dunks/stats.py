@@ -1,7 +1,8 @@
-"""`alleyoop rates / utrrates / tcperreadpos / tcperutrpos / snpeval` on the GPU: drop-ins for the reference's
+"""`alleyoop rates / tccontext / utrrates / tcperreadpos / tcperutrpos / snpeval` on the GPU: drop-ins for the reference's
 dunks/stats.py functions that iterate SlamSeqBamIterator, same signatures, same CSV files.
 
     statsComputeOverallRates        stats.py:85-131
+    statsComputeTCContext           stats.py:226-330
     statsComputeOverallRatesPerUTR  stats.py:331-528
     tcPerReadPos                    stats.py:591-657
     tcPerUtr                        stats.py:659-772
@@ -83,7 +84,7 @@ class ReadStats(object):
 
     def run(self, min_qual, conversion_threshold=1, strict=False, want=(), max_read_length=0, utr_norm=utrNormFactor,
             pair_capacity=0):
-        """want: subset of {"rates", "readpos", "utr_rates", "utr_snp", "utrpos", "pairs"} -> dict of numpy arrays"""
+        """want: subset of {"rates", "readpos", "utr_rates", "utr_snp", "utrpos", "context", "pairs"} -> dict of numpy arrays"""
         g, hb, utrs = self.genome, self.hbatch, self.utrs
         n = len(utrs)
         eng = CountEngine(_tc.OPTIONS["device"])
@@ -101,7 +102,7 @@ class ReadStats(object):
             with torch.cuda.stream(eng.stream):
                 dbatch = DeviceBatch.from_host(hb.batch, dev, eng)
                 order = torch.from_numpy(hb.order().astype(np.int32)).to(dev) if hb.n_reads else None
-                shapes = {"rates": 2 * L.SD_NRATE, "readpos": 6 * (max_read_length + 1), "utr_rates": max(1, n) * (L.SD_NRATE + 1),
+                shapes = {"context": 20, "rates": 2 * L.SD_NRATE, "readpos": 6 * (max_read_length + 1), "utr_rates": max(1, n) * (L.SD_NRATE + 1),
                           "utr_snp": max(1, n) * 3, "utrpos": 6 * (utr_norm + 1)}
                 out = dict((k, torch.zeros(shapes[k], dtype=torch.int64, device=dev)) for k in shapes if k in want)
                 pairs = n_pairs = None
@@ -115,6 +116,7 @@ class ReadStats(object):
             a.d_order = order.data_ptr() if order is not None else None
             a.d_rates, a.d_readpos = _ptr(out.get("rates")), _ptr(out.get("readpos"))
             a.d_utr_rates, a.d_utr_snp, a.d_utrpos = _ptr(out.get("utr_rates")), _ptr(out.get("utr_snp")), _ptr(out.get("utrpos"))
+            a.d_context = _ptr(out.get("context"))
             a.d_pairs, a.pair_capacity, a.d_n_pairs = _ptr(pairs), int(pair_capacity), _ptr(n_pairs)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(eng.stream)
@@ -174,6 +176,35 @@ def statsComputeOverallRates(referenceFile, bam, minBaseQual, outputCSV, outputP
         print("Skipped computing overall rate pdfs for file " + bam, file=log)
     else:
         _no_plot("overall rates", outputPDF, log)
+
+
+def statsComputeTCContext(referenceFile, bam, minQual, outputCSV, outputPDF, log, printOnly=False, verbose=True, force=False):
+    """stats.py:226-330 (alleyoop tccontext): the bases next to every T of the forward reads / every A of the reverse reads."""
+    if not checkStep([bam, referenceFile], [outputCSV], force):
+        print("Skipped computing overall rates for file " + bam, file=log)
+    else:
+        frontCombinations = ["AT", "CT", "GT", "TT", "NT"]
+        backCombinations = ["TA", "TC", "TG", "TT", "TN"]
+        rs = ReadStats(referenceFile, bam)
+        try:
+            for chromosome in rs.genome.names:          # bamFile.fetch(region=chromosome) for every FASTA chromosome (stats.py:259)
+                if chromosome not in rs.hbatch.ref_names:
+                    raise ValueError("invalid contig `%s`" % chromosome)
+            c = rs.run(minQual, want=("context",))["context"].reshape(2, 2, 5)
+        finally:
+            rs.close()
+        fo = open(outputCSV, "w")
+        print("\t".join(frontCombinations), file=fo)
+        print("\t".join(str(int(x)) for x in c[0, 0]), file=fo)
+        print("\t".join(str(int(x)) for x in c[0, 1]), file=fo)
+        print("\t".join(backCombinations), file=fo)
+        print("\t".join(str(int(x)) for x in c[1, 0]), file=fo)
+        print("\t".join(str(int(x)) for x in c[1, 1]), file=fo)
+        fo.close()
+    if not checkStep([bam, referenceFile], [outputPDF], force):
+        print("Skipped computing overall rate pdfs for file " + bam, file=log)
+    else:
+        _no_plot("T->C context", outputPDF, log)
 
 
 PLOT_CONVERSIONS = ["A>T", "A>G", "A>C", "C>A", "C>G", "C>T", "G>A", "G>C", "G>T", "T>A", "T>G", "T>C"]   # stats.py:349-353

@@ -207,7 +207,7 @@ def make_readsep(name, min_qual, conv_threshold):
 # the iterator-based alleyoop statistics (dunks/stats.py) and the mle per-read lists of `count` on the count cases' inputs,
 # with each case's own min_qual / max_read_length / conversion threshold (tests/goldens.py StatsCase)
 STATS = ["case_a", "case_b", "case_d", "case_e"]
-STATS_RUNS = [("rates", False), ("utrrates", False), ("utrrates", True), ("tcperreadpos", False), ("tcperutrpos", False),
+STATS_RUNS = [("rates", False), ("tccontext", False), ("utrrates", False), ("utrrates", True), ("tcperreadpos", False), ("tcperutrpos", False),
               ("snpeval", False), ("snpeval", True)]
 
 
@@ -220,9 +220,11 @@ def make_stats(name):
     p = json.load(open(os.path.join(d, "params.json")))["count"]
     ref, bam, bed = os.path.join(d, name + ".fa"), os.path.join(d, name + ".bam"), os.path.join(d, name + ".bed")
     vcf = os.path.join(d, name + ".vcf") if p["vcf"] else None
+    import statsrun
+    ref_in_bam = statsrun.fasta_in_bam(ref, bam, os.path.join(out, "tmp_in_bam.fa"))   # tccontext needs every FASTA chromosome in the BAM
     for tool, strict in STATS_RUNS:
         csv = os.path.join(out, tool + ("_strict" if strict else "") + ".csv")
-        refrun.run_stats(tool, csv, ref, bam, bed=bed, vcf=vcf, min_qual=p["min_qual"], max_read_length=p["max_read_length"], strict=strict)
+        refrun.run_stats(tool, csv, ref_in_bam if tool == "tccontext" else ref, bam, bed=bed, vcf=vcf, min_qual=p["min_qual"], max_read_length=p["max_read_length"], strict=strict)
     tmp = os.path.join(out, "tmp")
     perread = refrun.run_count_mle(ref, bed, vcf, bam, tmp, p["max_read_length"], p["min_qual"], p["conv_threshold"])
     os.rename(perread, os.path.join(out, "tcount_perread.tsv"))

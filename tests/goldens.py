@@ -79,7 +79,7 @@ READSEP_CASES = ["case_a", "case_b", "case_e"]
 class StatsCase:
     """alleyoop rates / utrrates / tcperreadpos / tcperutrpos / snpeval and the mle per-read lists on a count case's inputs
     (tests/golden/<case>/stats, written by the unmodified reference)."""
-    RUNS = [("rates", False), ("utrrates", False), ("utrrates", True), ("tcperreadpos", False), ("tcperutrpos", False),
+    RUNS = [("rates", False), ("tccontext", False), ("utrrates", False), ("utrrates", True), ("tcperreadpos", False), ("tcperutrpos", False),
             ("snpeval", False), ("snpeval", True)]
 
     def __init__(self, name):

@@ -103,7 +103,7 @@ def stats_module():
 
 def run_stats(tool, out_csv, ref, bam, bed=None, vcf=None, min_qual=27, max_read_length=100, strict=False):
     """One of the reference's iterator-based alleyoop statistics -> log text; the CSV is written to out_csv.
-    tool: rates | utrrates | tcperreadpos | tcperutrpos | snpeval"""
+    tool: rates | tccontext | utrrates | tcperreadpos | tcperutrpos | snpeval"""
     import warnings
     stats = stats_module()
     log = io.StringIO()
@@ -112,6 +112,8 @@ def run_stats(tool, out_csv, ref, bam, bed=None, vcf=None, min_qual=27, max_read
         warnings.simplefilter("ignore")
         if tool == "rates":
             stats.statsComputeOverallRates(ref, bam, min_qual, out_csv, pdf, log)
+        elif tool == "tccontext":
+            stats.statsComputeTCContext(ref, bam, min_qual, out_csv, pdf, log)
         elif tool == "utrrates":
             stats.statsComputeOverallRatesPerUTR(ref, bam, min_qual, strict, out_csv, pdf, bed, max_read_length, log)
         elif tool == "tcperreadpos":

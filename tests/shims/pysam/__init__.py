@@ -130,6 +130,13 @@ class AlignmentFile(object):
     def fetch(self, reference=None, start=None, end=None, region=None, until_eof=False, contig=None):
         if reference is None and contig is not None:
             reference = contig
+        if reference is None and region is not None:       # "chr" or "chr:start-end" (1-based, inclusive), as samtools writes regions
+            reference = region
+            if ":" in region and region not in self.references:
+                reference, span = region.rsplit(":", 1)
+                a, _, b = span.replace(",", "").partition("-")
+                start = int(a) - 1
+                end = int(b) if b else None
         if reference is None:
             return iter([AlignedSegment(r, self) for r in self._records])
         if reference not in self.references:

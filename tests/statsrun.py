@@ -7,6 +7,8 @@ def run_oracle(tool, out_csv, ref, bam, bed, vcf, min_qual, max_read_length, str
     from oracle import stats_oracle as so
     if tool == "rates":
         so.rates_file(ref, bam, min_qual, out_csv)
+    elif tool == "tccontext":
+        so.tccontext_file(ref, bam, out_csv)
     elif tool == "utrrates":
         so.utrrates_file(ref, bam, min_qual, strict, out_csv, bed, max_read_length)
     elif tool == "tcperreadpos":
@@ -25,6 +27,8 @@ def run_gpu(tool, out_csv, ref, bam, bed, vcf, min_qual, max_read_length, strict
     pdf = out_csv + ".pdf"
     if tool == "rates":
         stats.statsComputeOverallRates(ref, bam, min_qual, out_csv, pdf, log)
+    elif tool == "tccontext":
+        stats.statsComputeTCContext(ref, bam, min_qual, out_csv, pdf, log)
     elif tool == "utrrates":
         stats.statsComputeOverallRatesPerUTR(ref, bam, min_qual, strict, out_csv, pdf, bed, max_read_length, log)
     elif tool == "tcperreadpos":
@@ -52,3 +56,13 @@ def unstrand_some_rows(bed_in, bed_out, every=4):
             if i % every == 1 and len(f) > 5:
                 f[5] = "."
             fo.write("\t".join(f) + "\n")
+
+
+def fasta_in_bam(ref, bam, out_fa):
+    """copy of a FASTA without the chromosomes missing from the BAM header: `alleyoop tccontext` fetches every FASTA
+    chromosome from the BAM without asking whether it is there (stats.py:259) and dies on the first missing one"""
+    from slamdunk_b200.io import bam as bamio
+    names = set(n for n, _l in bamio.read_bam(bam)[1])
+    seqs = bamio.read_fasta(ref)
+    bamio.write_fasta(out_fa, dict((k, v) for k, v in seqs.items() if k in names))
+    return out_fa

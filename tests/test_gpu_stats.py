@@ -23,9 +23,10 @@ def _read(p):
 @pytest.mark.parametrize("name", goldens.STATS_CASES)
 def test_stats_match_reference_golden(name, tmp_path):
     c = goldens.StatsCase(name)
+    ref_in_bam = statsrun.fasta_in_bam(c.ref, c.bam, str(tmp_path / "in_bam.fa"))
     for tool, strict in goldens.StatsCase.RUNS:
         out = str(tmp_path / (tool + str(strict) + ".csv"))
-        log = statsrun.run_gpu(tool, out, c.ref, c.bam, c.bed, c.vcf, c.min_qual, c.max_read_length, strict)
+        log = statsrun.run_gpu(tool, out, ref_in_bam if tool == "tccontext" else c.ref, c.bam, c.bed, c.vcf, c.min_qual, c.max_read_length, strict)
         assert _read(out) == _read(c.expected(tool, strict)), (tool, strict)
         assert "not written" in log and not os.path.exists(out + ".pdf")
 
@@ -51,12 +52,16 @@ def test_stats_match_oracle_on_random_data(seed, q, maxlen, read_len, n_reads, t
     c = simdata.make_case(str(tmp_path), seed=seed, n_reads=n_reads, n_utr=40, complexity=2.0, snp_density=0.02, read_len=read_len)
     bed = str(tmp_path / "mixed.bed")
     statsrun.unstrand_some_rows(c.bed, bed)
+    ref_in_bam = statsrun.fasta_in_bam(c.ref, c.bam, str(tmp_path / "in_bam.fa"))
     for tool, strict in goldens.StatsCase.RUNS:
         use_bed = c.bed if tool == "snpeval" else bed
+        use_ref = ref_in_bam if tool == "tccontext" else c.ref
         g, o = str(tmp_path / (tool + str(strict) + "_g.csv")), str(tmp_path / (tool + str(strict) + "_o.csv"))
-        statsrun.run_gpu(tool, g, c.ref, c.bam, use_bed, c.vcf, q, maxlen, strict)
-        statsrun.run_oracle(tool, o, c.ref, c.bam, use_bed, c.vcf, q, maxlen, strict)
+        statsrun.run_gpu(tool, g, use_ref, c.bam, use_bed, c.vcf, q, maxlen, strict)
+        statsrun.run_oracle(tool, o, use_ref, c.bam, use_bed, c.vcf, q, maxlen, strict)
         assert _read(g) == _read(o), (tool, strict)
+    with pytest.raises(ValueError, match="invalid contig"):      # a FASTA chromosome the BAM does not know (stats.py:259)
+        statsrun.run_gpu("tccontext", str(tmp_path / "x.csv"), c.ref, c.bam, None, None, q, maxlen, False)
 
 
 @pytest.mark.parametrize("thr", [1, 2])
@@ -97,10 +102,11 @@ def test_stats_cli(tmp_path):
     os.symlink(c.vcf, os.path.join(snpdir, base + "_snp.vcf"))
     q, L = str(c.min_qual), str(c.max_read_length)
     alleyoop.run(["rates", "-o", out, "-r", c.ref, "-mq", q, c.bam])
+    alleyoop.run(["tccontext", "-o", out, "-r", statsrun.fasta_in_bam(c.ref, c.bam, str(tmp_path / "in_bam.fa")), c.bam])
     alleyoop.run(["tcperreadpos", "-o", out, "-r", c.ref, "-s", snpdir, "-l", L, "-mq", q, c.bam])
     alleyoop.run(["utrrates", "-o", out, "-r", c.ref, "-b", c.bed, "-l", L, "-mq", q, c.bam])
     alleyoop.run(["tcperutrpos", "-o", out, "-r", c.ref, "-b", c.bed, "-s", snpdir, "-l", L, "-mq", q, c.bam])
     alleyoop.run(["snpeval", "-o", out, "-r", c.ref, "-b", c.bed, "-s", snpdir, "-l", L, "-q", q, c.bam])
-    for suffix, tool in (("_overallrates", "rates"), ("_tcperreadpos", "tcperreadpos"), ("_mutationrates_utr", "utrrates"),
+    for suffix, tool in (("_overallrates", "rates"), ("_tccontext", "tccontext"), ("_tcperreadpos", "tcperreadpos"), ("_mutationrates_utr", "utrrates"),
                          ("_tcperutr", "tcperutrpos"), ("_SNPeval", "snpeval")):
         assert _read(os.path.join(out, base + suffix + ".csv")) == _read(c.expected(tool)), tool

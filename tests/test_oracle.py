@@ -162,9 +162,10 @@ from oracle import stats_oracle  # noqa: E402
 @pytest.mark.parametrize("name", goldens.STATS_CASES)
 def test_stats_oracle_matches_reference_golden(name, tmp_path):
     c = goldens.StatsCase(name)
+    ref_in_bam = statsrun.fasta_in_bam(c.ref, c.bam, str(tmp_path / "in_bam.fa"))
     for tool, strict in goldens.StatsCase.RUNS:
         out = str(tmp_path / (tool + str(strict) + ".csv"))
-        statsrun.run_oracle(tool, out, c.ref, c.bam, c.bed, c.vcf, c.min_qual, c.max_read_length, strict)
+        statsrun.run_oracle(tool, out, ref_in_bam if tool == "tccontext" else c.ref, c.bam, c.bed, c.vcf, c.min_qual, c.max_read_length, strict)
         assert _read(out) == _read(c.expected(tool, strict)), (tool, strict)
     lists = stats_oracle.perread_lists(c.ref, c.bed, c.vcf, c.bam, c.max_read_length, c.min_qual, c.conv_threshold)
     cols = statsrun.perread_columns(c.perread)
@@ -183,12 +184,19 @@ def test_stats_oracle_matches_live_reference(seed, q, maxlen, read_len, tmp_path
     c = simdata.make_case(str(tmp_path), seed=seed, n_reads=1500, n_utr=30, complexity=2.0, snp_density=0.02, read_len=read_len)
     bed = str(tmp_path / "mixed.bed")
     statsrun.unstrand_some_rows(c.bed, bed)
+    ref_in_bam = statsrun.fasta_in_bam(c.ref, c.bam, str(tmp_path / "in_bam.fa"))
     for tool, strict in goldens.StatsCase.RUNS:
         use_bed = c.bed if tool == "snpeval" else bed          # snpeval refuses rows without strand
+        use_ref = ref_in_bam if tool == "tccontext" else c.ref
         r, o = str(tmp_path / "r.csv"), str(tmp_path / "o.csv")
         for f in (r, o):
             if os.path.exists(f):
                 os.remove(f)
-        refrun.run_stats(tool, r, c.ref, c.bam, bed=use_bed, vcf=c.vcf, min_qual=q, max_read_length=maxlen, strict=strict)
-        statsrun.run_oracle(tool, o, c.ref, c.bam, use_bed, c.vcf, q, maxlen, strict)
+        refrun.run_stats(tool, r, use_ref, c.bam, bed=use_bed, vcf=c.vcf, min_qual=q, max_read_length=maxlen, strict=strict)
+        statsrun.run_oracle(tool, o, use_ref, c.bam, use_bed, c.vcf, q, maxlen, strict)
         assert _read(r) == _read(o), (tool, strict)
+    # a FASTA chromosome that the BAM does not know: tccontext dies in pysam's fetch (stats.py:259)
+    for run in (lambda: refrun.run_stats("tccontext", str(tmp_path / "x.csv"), c.ref, c.bam),
+                lambda: statsrun.run_oracle("tccontext", str(tmp_path / "y.csv"), c.ref, c.bam, None, None, q, maxlen, False)):
+        with pytest.raises(ValueError, match="invalid contig"):
+            run()
