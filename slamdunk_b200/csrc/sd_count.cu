@@ -211,8 +211,7 @@ __device__ __forceinline__ uint32_t row_group_is_base(const uint32_t *row, uint3
 // code.  sd_decode_bam / sd_qual_dict assign codes in ascending quality order, so the reference's test
 // `readQlty >= minQual` (SlamSeqFile.py:330) is the bit-sliced comparison code >= q_cmin: 2 LOP3 per plane for 32 bases.
 // CM: take the comparison constant as ready-made masks from the parameter block (A.q_m) instead of deriving them from
-// A.q_cmin.  Same result; which form the compiler schedules better depends on the window size (measured: the derived
-// form at W = 4, 1.675 vs 1.75 ms at 100 bp; the mask form from W = 6 on, 1.82 vs 2.31 ms at 150 bp).
+// A.q_cmin.  Same result; the count kernel uses the mask form (150 bp: 1.83 vs 2.31 ms), the per-base lookups the other.
 template <int QB, bool CM>
 __device__ __forceinline__ uint32_t planes_ge(const uint32_t (&p)[QB], const CountArgs &A) {
     if (CM && QB == 2)   // code >= c over two planes: c = 3: p1 & p0; 2: p1; 1: p1 | p0; 0: all; 4: none
@@ -511,7 +510,7 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
             uint32_t m = row_group_is_base<SB>(v.seq, kc, sm);   // this row's slot of group kc; the tile block is group-major
             // plane-form qualities, plain CIGAR walk: the quality test is one more mask on the read side, for 32 bases at once
             if (QB > 0 && A.mismatch_source == SD_MISMATCH_CIGAR)
-                m &= row_group_qual_ok<(QB ? QB : 2), (W > 4)>(reinterpret_cast<const uint32_t *>(v.qual), kc, A);
+                m &= row_group_qual_ok<(QB ? QB : 2), true>(reinterpret_cast<const uint32_t *>(v.qual), kc, A);
             M[k] = ((uint32_t)k < ng) ? m : 0u;
         }
         if (SIMPLE) {
@@ -928,7 +927,11 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
         // @region filter
         const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu, ref = rmf & 0xFFFFu;
         bool go = !(flags & SD_F_PAD);
-        if (go && A.filter_on) {
+        // Two forms of the same filter step, chosen per window size by measurement (the kernel is bound by instruction issue,
+        // and which form schedules better differs: votes at W = 4, 1.604 vs 1.671 ms at 100 bp; per-read atomics from W = 6
+        // on, 1.83 vs 2.01 ms at 150 bp).
+        constexpr bool VOTE_COUNTERS = (W <= 4);
+        if (!VOTE_COUNTERS && go && A.filter_on) {
             const bool primary = !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
             const bool unmapped = (flags & SD_F_UNMAPPED) != 0;
             if (primary) atomicAdd(&s_stats[unmapped ? SD_S_UNMAPPED : SD_S_MAPPED], 1u);
@@ -937,6 +940,29 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
             else if (xi < A.filter_min_identity) { atomicAdd(&s_stats[SD_S_IDFILTERED], 1u); go = false; }
             else if (A.filter_max_nm > -1 && (int)nm > A.filter_max_nm) { atomicAdd(&s_stats[SD_S_NMFILTERED], 1u); go = false; }
             else if (primary) atomicAdd(&s_stats[SD_S_FILTERED], 1u);
+        }
+        if (VOTE_COUNTERS && A.filter_on) {
+            // filter.py:235-256 as predicates; the run counters are warp totals (one vote each, added by lane 0) instead of
+            // one shared-memory atomic per read and counter
+            const bool primary = go && !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
+            const bool mapped = go && !(flags & SD_F_UNMAPPED);
+            const bool f_mq = mapped && (int)mapq < A.filter_mq;
+            const bool f_id = mapped && !f_mq && xi < A.filter_min_identity;
+            const bool f_nm = mapped && !f_mq && !f_id && A.filter_max_nm > -1 && (int)nm > A.filter_max_nm;
+            go = mapped && !f_mq && !f_id && !f_nm;
+            const uint32_t b_map = __ballot_sync(0xFFFFFFFFu, primary && mapped), b_unm = __ballot_sync(0xFFFFFFFFu, primary && !mapped);
+            const uint32_t b_mq = __ballot_sync(0xFFFFFFFFu, f_mq), b_id = __ballot_sync(0xFFFFFFFFu, f_id);
+            const uint32_t b_nm = __ballot_sync(0xFFFFFFFFu, f_nm), b_ok = __ballot_sync(0xFFFFFFFFu, go && primary);
+            if (lane == 0) {   // one conflict-free shared atomic per non-zero counter and tile
+                if (b_map) atomicAdd(&s_stats[SD_S_MAPPED], (uint32_t)__popc(b_map));
+                if (b_ok) atomicAdd(&s_stats[SD_S_FILTERED], (uint32_t)__popc(b_ok));
+                if (b_unm | b_mq | b_id | b_nm) {
+                    if (b_unm) atomicAdd(&s_stats[SD_S_UNMAPPED], (uint32_t)__popc(b_unm));
+                    if (b_mq) atomicAdd(&s_stats[SD_S_MQFILTERED], (uint32_t)__popc(b_mq));
+                    if (b_id) atomicAdd(&s_stats[SD_S_IDFILTERED], (uint32_t)__popc(b_id));
+                    if (b_nm) atomicAdd(&s_stats[SD_S_NMFILTERED], (uint32_t)__popc(b_nm));
+                }
+            }
         }
         if (flags & (SD_F_UNMAPPED | SD_F_SKIP)) go = false;
         if (ref >= A.n_chrom) go = false;
