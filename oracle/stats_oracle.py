@@ -20,7 +20,6 @@ Meant for small cases (seconds for a few thousand reads).
 from __future__ import print_function
 
 import ast
-import os
 import re
 
 import numpy as np

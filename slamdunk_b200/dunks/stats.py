@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from ..engine import CountEngine, DeviceBatch, HostBatch, _t_ptr
+from ..engine import CountEngine, DeviceBatch, HostBatch
 from ..utils.bed import BedIterator
 from ..utils.samheader import SlamSeqInfo, getSampleInfo, parse_sam_header
 from ..utils.snpmask import build_snp_masks
