@@ -145,6 +145,30 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+def read_stats_on_device(eng, dbatch, n_utr, min_qual, want, conversion_threshold=1, strict=False, max_read_length=0,
+                         utr_norm=utrNormFactor, repeat=1):
+    """sd_read_stats on a batch that is already in HBM (MP column in the SD_DECODE_MP_ALL form; reference, SNPs and
+    annotation installed in `eng`) -> (dict of host numpy arrays, kernel ms of the last of `repeat` runs)."""
+    dev = eng.device
+    shapes = {"context": 20, "rates": 2 * L.SD_NRATE, "readpos": 6 * (max_read_length + 1), "utr_rates": max(1, n_utr) * (L.SD_NRATE + 1),
+              "utr_snp": max(1, n_utr) * 3, "utrpos": 6 * (utr_norm + 1)}
+    a = L.StatsArgs()
+    a.min_qual, a.conversion_threshold, a.strict = int(min_qual), int(conversion_threshold), 1 if strict else 0
+    a.max_read_length, a.utr_norm = int(max_read_length), int(utr_norm)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(repeat):
+        with torch.cuda.stream(eng.stream):
+            out = dict((k, torch.zeros(shapes[k], dtype=torch.int64, device=dev)) for k in shapes if k in want)
+        a.d_rates, a.d_readpos = _ptr(out.get("rates")), _ptr(out.get("readpos"))
+        a.d_utr_rates, a.d_utr_snp, a.d_utrpos = _ptr(out.get("utr_rates")), _ptr(out.get("utr_snp")), _ptr(out.get("utrpos"))
+        a.d_context = _ptr(out.get("context"))
+        ev0.record(eng.stream)
+        eng._chk(eng.lib.sd_read_stats(eng.ctx, ctypes.byref(dbatch.batch), ctypes.byref(a)), "sd_read_stats")
+        ev1.record(eng.stream)
+        eng.synchronize()
+    return dict((k, v.cpu().numpy()) for k, v in out.items()), ev0.elapsed_time(ev1)
+
+
 def printRates(ratesFwd, ratesRev, f):
     """stats.py:74-83"""
     print("\t", end="", file=f)

@@ -236,6 +236,55 @@ def layout_bytes_per_read(read_len, mean_cigar_ops, seq_bits=4, qual_planes=0):
     return seq_bits * 4 * groups + (qual_planes * 4 * groups if qual_planes else read_len) + 4.0 * mean_cigar_ops + 20
 
 
+def to_mp_all(db: DeviceBatch, triples: torch.Tensor, eng) -> DeviceBatch:
+    """The same device batch with the COMPLETE MP column sd_read_stats takes (what sd_decode_bam writes with
+    SD_DECODE_MP_ALL: per entry {readPos-1 | refPos-1 << 16, conv}), built from the generator's own record of the
+    mismatching columns (`triples`, batch order; 1-based positions as NextGenMap lists them).  A read that carries an MP
+    tag but no mismatch gets the entry 24:1:1 that tests/synth_files.py writes into its BAM, so that both routes agree."""
+    dev = db.tensors["rec"].device
+    nt, T, n = int(db.batch.n_tiles), int(db.batch.tile_reads), int(db.batch.n_reads)
+    with torch.cuda.stream(eng.stream):
+        rec = db.tensors["rec"].clone().view(torch.int32).view(-1, 5)
+        has_mp = ((rec[:n, 1] >> 24) & L.SD_F_HAS_MP) != 0
+        cnt = torch.where(has_mp, triples[:, 0].clamp(min=1), torch.zeros_like(triples[:, 0])).to(torch.int64)
+        dummy = has_mp & (triples[:, 0] == 0)
+        slots = torch.zeros(nt * T, dtype=torch.int64, device=dev)
+        slots[:n] = cnt
+        per_tile = slots.view(nt, T).sum(1)
+        tile_bytes = (per_tile * 8 + 15) // 16 * 16
+        mp_off = torch.zeros(nt + 1, dtype=torch.int64, device=dev)
+        mp_off[1:] = torch.cumsum(tile_bytes, 0)
+        within = torch.cumsum(slots.view(nt, T), 1) - slots.view(nt, T)
+        first = (mp_off[:nt, None] // 8 + within).view(-1)[:n]                 # entry index of every read's first entry
+        total = int(cnt.sum().item())
+        col = torch.zeros(max(4, int(mp_off[-1].item()) // 4), dtype=torch.int32, device=dev)
+        if total:
+            read_of = torch.repeat_interleave(torch.arange(n, device=dev), cnt)
+            k = torch.arange(total, device=dev) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+            conv = triples[read_of, 1 + 3 * k].to(torch.int64)
+            rp = triples[read_of, 2 + 3 * k].to(torch.int64) - 1
+            fp = triples[read_of, 3 + 3 * k].to(torch.int64) - 1
+            d = dummy[read_of]
+            conv = torch.where(d, torch.full_like(conv, 24), conv)
+            rp = torch.where(d, torch.zeros_like(rp), rp)
+            fp = torch.where(d, torch.zeros_like(fp), fp)
+            pos = first[read_of] + k
+            col[2 * pos] = (rp | (fp << 16)).to(torch.int32)
+            col[2 * pos + 1] = conv.to(torch.int32)
+        rec[:n, 4] = (rec[:n, 4] & 0xFFFF) | (cnt << 16).to(torch.int32)
+        tiles = db.tensors["tiles"].clone().view(torch.int64).view(-1, 4)
+        tiles[:, 3] = mp_off
+        max_tile_mp = int(tile_bytes.max().item()) if nt else 0
+    eng.stream.synchronize()
+    tens = dict(db.tensors)
+    tens["rec"], tens["mp"], tens["tiles"] = rec.view(-1).view(torch.uint8), col.view(torch.uint8), tiles.view(-1).view(torch.uint8)
+    b = L.Batch()
+    ctypes.memmove(ctypes.byref(b), ctypes.byref(db.batch), ctypes.sizeof(L.Batch))
+    b.rec, b.mp, b.tiles = tens["rec"].data_ptr(), tens["mp"].data_ptr(), tens["tiles"].data_ptr()
+    b.max_tile_mp = max_tile_mp
+    return DeviceBatch(b, tens)
+
+
 def to_qual_planes(db: DeviceBatch, eng):
     """The same device batch (2-bit SEQ form) with its quality column as bit-planes of the dictionary code (sd_qual_dict +
     sd_qual_to_planes, sd_batch.qual_form = 1) -- what sd_count_host hands the kernel for a file with at most 16 distinct

@@ -110,3 +110,32 @@ def test_stats_cli(tmp_path):
     for suffix, tool in (("_overallrates", "rates"), ("_tccontext", "tccontext"), ("_tcperreadpos", "tcperreadpos"), ("_mutationrates_utr", "utrrates"),
                          ("_tcperutr", "tcperutrpos"), ("_SNPeval", "snpeval")):
         assert _read(os.path.join(out, base + suffix + ".csv")) == _read(c.expected(tool)), tool
+
+
+def test_device_built_mp_column_gives_the_file_route_results(tmp_path):
+    """synth.to_mp_all (the complete MP column built on the device from the generator's triples, used by
+    tools/stats_kernel_bench.py) against the route every other test takes: the same reads written to a BAM, decoded with
+    SD_DECODE_MP_ALL and scanned -- all six output sets identical."""
+    import numpy as np
+    import synth_files
+    from slamdunk_b200.dunks import stats
+    from slamdunk_b200.engine import CountEngine
+    from slamdunk_b200.synth import SynthWorkload, to_mp_all
+    eng = CountEngine(0)
+    wl = SynthWorkload(eng, seed=5, genome_bp=3_000_000, n_utr=600, n_frac=0.01)
+    wl.install()
+    p = wl.params(seed=41, first_read=0, n_reads=30_000, frac_softclip=0.1, frac_indel=0.08, frac_antisense=0.05, frac_labelled=0.8)
+    db, triples = wl.generate(p, want_triples=True, coordinate_sorted=True, group=False)
+    want = ("rates", "context", "readpos", "utr_rates", "utrpos", "utr_snp")
+    dev_res, ms = stats.read_stats_on_device(eng, to_mp_all(db, triples, eng), len(wl.ann), 27, want, max_read_length=100)
+    assert ms > 0
+    ref, bed, bam, n = synth_files.write_workload_files(str(tmp_path), wl, db, triples)
+    eng.close()
+    rs = stats.ReadStats(ref, bam, bed=bed)
+    try:
+        file_res = rs.run(27, want=want, max_read_length=100)
+    finally:
+        rs.close()
+    for k in want:
+        assert np.array_equal(dev_res[k], file_res[k]), k
+    assert dev_res["rates"].sum() > 0 and dev_res["utr_snp"].reshape(-1, 3)[:, 0].sum() > 20_000
