@@ -33,6 +33,7 @@ struct StatsArgs {
     const uint8_t *row_strand;  // 0 '+', 1 '-', 2 none
     int min_qual, conv_threshold, strict;
     uint32_t max_read_length, utr_norm;
+    uint32_t hist_smem;         // the read-position and UTR-position histograms are accumulated per CTA in shared memory
     unsigned long long *rates, *readpos, *utr_rates, *utr_snp, *utrpos, *context;
     sd_read_pair *pairs;
     unsigned long long pair_capacity;
@@ -87,10 +88,24 @@ __device__ __forceinline__ void for_each_kept(const ReadCtx &r, F f) {
     }
 }
 
+// Accumulation.  The genome-wide outputs are a few hundred counters that every read adds to, so nothing goes straight to
+// global memory: the matrix diagonals (base counts) and the tccontext counts run in per-thread registers over all of a
+// thread's reads and are warp-reduced once at the end; the off-diagonal cells (one or two per mismatch) and the read- /
+// UTR-position histograms are shared-memory atomics on per-CTA copies, flushed with one 64-bit atomic per non-zero cell.
+// RATES / CONTEXT: compile the register accumulators of those two outputs in only when they are wanted (30 registers).
+template <bool RATES, bool CONTEXT>
 __global__ void __launch_bounds__(256) sd_stats_kernel(const StatsArgs A) {
+    extern __shared__ int s_hist[];   // [2 * 25] matrices fwd / rev | [6 * (max_read_length + 1)] | [6 * (utr_norm + 1)]
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const bool want_utr = A.utr_rates || A.utr_snp || A.utrpos || A.pairs;
+    const uint32_t n_rp = (A.readpos && A.hist_smem) ? 6u * (A.max_read_length + 1u) : 0u;
+    const uint32_t n_up = (A.utrpos && A.hist_smem) ? 6u * (A.utr_norm + 1u) : 0u;
+    int *s_rates = s_hist, *s_readpos = s_hist + 2 * SD_NRATE, *s_utrpos = s_readpos + n_rp;
+    for (uint32_t i = threadIdx.x; i < 2u * SD_NRATE + n_rp + n_up; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    int dF[5] = {0, 0, 0, 0, 0}, dR[5] = {0, 0, 0, 0, 0};                   // diagonal of the fwd / rev matrix: exact base counts
+    int c5F[5] = {0, 0, 0, 0, 0}, c5R[5] = {0, 0, 0, 0, 0}, c3F[5] = {0, 0, 0, 0, 0}, c3R[5] = {0, 0, 0, 0, 0};   // tccontext
     for (uint32_t t = warp; t < A.n_tiles; t += n_warps) {
         const sd_read_rec rec = A.rec[(size_t)t * 32 + lane];
         const uint32_t flags = rec.ref_mapq_flag >> 24, chrom = rec.ref_mapq_flag & 0xFFFFu;
@@ -100,9 +115,12 @@ __global__ void __launch_bounds__(256) sd_stats_kernel(const StatsArgs A) {
         const bool valid = !(flags & (SD_F_PAD | SD_F_SKIP | SD_F_UNMAPPED)) && chrom != SD_REF_NONE;
         const int strand = (flags & SD_F_REVERSE) ? 1 : 0;
 
-        int m[SD_NRATE];
+        int m[SD_NRATE];                       // the read's own matrix: only the per-UTR sums need it (dynamically indexed: local memory)
+        const bool want_m = A.utr_rates != nullptr;
+        if (want_m) {
 #pragma unroll
-        for (int c = 0; c < SD_NRATE; c++) m[c] = 0;
+            for (int c = 0; c < SD_NRATE; c++) m[c] = 0;
+        }
         int tc_count = 0;
         uint32_t span = 0, t_in_read = 0;
         ReadCtx R;
@@ -144,28 +162,34 @@ __global__ void __launch_bounds__(256) sd_stats_kernel(const StatsArgs A) {
                 const uint32_t onlyA = p.x & ~p.y & ~p.z & ~p.w, onlyC = ~p.x & p.y & ~p.z & ~p.w;
                 const uint32_t onlyG = ~p.x & ~p.y & p.z & ~p.w, onlyT = ~p.x & ~p.y & ~p.z & p.w;
                 const uint32_t isN = p.x & p.y & p.z & p.w;
-                m[0] += __popc(onlyA & in);
-                m[6] += __popc(onlyC & in);
-                m[12] += __popc(onlyG & in);
-                m[18] += __popc(onlyT & in);
-                m[24] += __popc(isN & in);
+                const int nA = __popc(onlyA & in), nC = __popc(onlyC & in), nG = __popc(onlyG & in), nT = __popc(onlyT & in), nN = __popc(isN & in);
+                if (want_m) { m[0] += nA; m[6] += nC; m[12] += nG; m[18] += nT; m[24] += nN; }
+                if (RATES) {
+                    if (!strand) { dF[0] += nA; dF[1] += nC; dF[2] += nG; dF[3] += nT; dF[4] += nN; }
+                    else { dR[0] += nA; dR[1] += nC; dR[2] += nG; dR[3] += nT; dR[4] += nN; }
+                }
                 t_in_read += __popc((strand ? onlyA : onlyT) & all);   // SlamSeqRead.getTcount, SlamSeqFile.py:181-185
             }
             const uint32_t tc_conv = strand ? 2u : 16u;
             for_each_kept(R, [&](uint32_t conv, uint32_t, uint32_t, bool snp) {
                 const uint32_t rb = conv / 5u, qb = conv % 5u;
-                if (!snp) m[conv]++;                    // SlamSeqFile.py:241-243
-                else m[6 * rb]++;                       // :245
-                m[6 * qb]--;
+                if (want_m) {
+                    if (!snp) m[conv]++;                // SlamSeqFile.py:241-243
+                    else m[6 * rb]++;                   // :245
+                    m[6 * qb]--;
+                }
+                if (RATES) {
+                    atomicAdd(&s_rates[strand * SD_NRATE + (snp ? 6 * rb : conv)], 1);
+                    atomicAdd(&s_rates[strand * SD_NRATE + 6 * qb], -1);
+                }
                 if (conv == tc_conv && !snp) tc_count++;   // isTCMismatch, :137-141
             });
         }
         const bool is_tc_read = tc_count >= A.conv_threshold;               // SlamSeqFile.py:397-400
 
         // ---- alleyoop tccontext (stats.py:256-287): neighbours of every T (forward reads) / A (reverse reads) of the read sequence
-        if (A.context) {
+        if (CONTEXT) {
             const bool in = !(flags & SD_F_PAD) && chrom != SD_REF_NONE;      // bamFile.fetch(region=chromosome): flag-unmapped records too
-            int c5[5] = {0, 0, 0, 0, 0}, c3[5] = {0, 0, 0, 0, 0};            // by the printed neighbour: A, C, G, T, N
             if (in) {
                 const uint4 *blk = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(A.seq) + tile.seq_off);
                 const int n_grp = (int)((l_seq + 31u) >> 5);
@@ -183,12 +207,13 @@ __global__ void __launch_bounds__(256) sd_stats_kernel(const StatsArgs A) {
                         const uint32_t left = (cur[x] << 1) | (prev[x] >> 31);   // bit i: base i-1 is x
                         const uint32_t right = (cur[x] >> 1) | (nxt[x] << 31);   // bit i: base i+1 is x
                         const int cx = x == 4 ? 4 : 3 - x;                       // complement (misc.py:276-280)
-                        if (!strand) {
-                            c5[x] += __popc(centre & left);
-                            c3[x] += __popc(centre & right);
+                        const int nl = __popc(centre & left), nr = __popc(centre & right);
+                        if (!strand) {                                           // by the printed neighbour: A, C, G, T, N
+                            c5F[x] += nl;
+                            c3F[x] += nr;
                         } else {                                                 // front = next base, back = previous base, both complemented
-                            c5[cx] += __popc(centre & right);
-                            c3[cx] += __popc(centre & left);
+                            c5R[cx] += nr;
+                            c3R[cx] += nl;
                         }
                     }
 #pragma unroll
@@ -196,40 +221,23 @@ __global__ void __launch_bounds__(256) sd_stats_kernel(const StatsArgs A) {
                     p = nx;
                 }
             }
-#pragma unroll
-            for (int x = 0; x < 5; x++) {
-                const int f5 = __reduce_add_sync(0xFFFFFFFFu, strand ? 0 : c5[x]), r5 = __reduce_add_sync(0xFFFFFFFFu, strand ? c5[x] : 0);
-                const int f3 = __reduce_add_sync(0xFFFFFFFFu, strand ? 0 : c3[x]), r3 = __reduce_add_sync(0xFFFFFFFFu, strand ? c3[x] : 0);
-                if (lane == 0) {
-                    add64(&A.context[0 + x], f5);
-                    add64(&A.context[5 + x], r5);
-                    add64(&A.context[10 + x], f3);
-                    add64(&A.context[15 + x], r3);
-                }
-            }
         }
 
         // ---- genome-wide outputs (readsInChromosome: strand ".", every placed record)
-        if (A.rates) {
-#pragma unroll
-            for (int c = 0; c < SD_NRATE; c++) {
-                const int f = __reduce_add_sync(0xFFFFFFFFu, (valid && !strand) ? m[c] : 0);
-                const int r = __reduce_add_sync(0xFFFFFFFFu, (valid && strand) ? m[c] : 0);
-                if (lane == 0) {
-                    add64(&A.rates[c], f);
-                    add64(&A.rates[SD_NRATE + c], r);
-                }
-            }
-        }
         if (A.readpos) {
             const uint32_t W = A.max_read_length, ld = W + 1;
             const bool in = valid && l_seq <= W;                              // stats.py:621
             const uint32_t key = in ? ((uint32_t)strand << 16 | l_seq) : 0xFFFFFFFFu;
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
             if (in && lane == (uint32_t)(__ffs(peers) - 1)) {
-                const long long n = __popc(peers);
-                add64(&A.readpos[(4 + strand) * (size_t)ld + 0], n);
-                add64(&A.readpos[(4 + strand) * (size_t)ld + l_seq], -n);
+                const int n = __popc(peers);
+                if (A.hist_smem) {
+                    atomicAdd(&s_readpos[(4 + strand) * ld + 0], n);
+                    atomicAdd(&s_readpos[(4 + strand) * ld + l_seq], -n);
+                } else {
+                    add64(&A.readpos[(4 + strand) * (size_t)ld + 0], n);
+                    add64(&A.readpos[(4 + strand) * (size_t)ld + l_seq], -n);
+                }
             }
             if (in) {
                 const uint32_t tc_conv = strand ? 2u : 16u;
@@ -238,7 +246,8 @@ __global__ void __launch_bounds__(256) sd_stats_kernel(const StatsArgs A) {
                     if (p < 0) p += W;                       // a Python list index below zero counts from the end
                     if (p < 0 || p >= (long long)W) return;  // (the reference raises IndexError here)
                     const bool is_tc = conv == tc_conv && !snp;
-                    atomicAdd(&A.readpos[((is_tc ? 2 : 0) + strand) * (size_t)ld + (size_t)p], 1ull);
+                    if (A.hist_smem) atomicAdd(&s_readpos[((is_tc ? 2 : 0) + strand) * ld + (uint32_t)p], 1);
+                    else atomicAdd(&A.readpos[((is_tc ? 2 : 0) + strand) * (size_t)ld + (size_t)p], 1ull);
                 });
             }
         }
@@ -291,7 +300,8 @@ __global__ void __launch_bounds__(256) sd_stats_kernel(const StatsArgs A) {
                         } else if (rel >= 0 && rel < min(L, norm)) idx = rel;           // stats.py:714
                         if (idx < 0) return;
                         const bool is_tc = conv == tc_conv && !snp;
-                        atomicAdd(&A.utrpos[((is_tc ? 2 : 0) + s) * ld + (size_t)idx], 1ull);
+                        if (A.hist_smem) atomicAdd(&s_utrpos[((is_tc ? 2 : 0) + s) * ld + (size_t)idx], 1);
+                        else atomicAdd(&A.utrpos[((is_tc ? 2 : 0) + s) * ld + (size_t)idx], 1ull);
                     });
                     long long a, b;
                     if (s) {                                                            // stats.py:725-726
@@ -303,8 +313,13 @@ __global__ void __launch_bounds__(256) sd_stats_kernel(const StatsArgs A) {
                         b = min(L, max(L - norm, end_ref)) + norm - L;
                     }
                     if (b > a) {
-                        atomicAdd(&A.utrpos[(4 + s) * ld + (size_t)a], 1ull);
-                        add64(&A.utrpos[(4 + s) * ld + (size_t)b], -1);
+                        if (A.hist_smem) {
+                            atomicAdd(&s_utrpos[(4 + s) * ld + (size_t)a], 1);
+                            atomicAdd(&s_utrpos[(4 + s) * ld + (size_t)b], -1);
+                        } else {
+                            atomicAdd(&A.utrpos[(4 + s) * ld + (size_t)a], 1ull);
+                            add64(&A.utrpos[(4 + s) * ld + (size_t)b], -1);
+                        }
                     }
                 }
                 if (A.pairs) {
@@ -325,6 +340,35 @@ __global__ void __launch_bounds__(256) sd_stats_kernel(const StatsArgs A) {
             }
         }
     }
+    // ---- flush: register accumulators -> warp totals -> the CTA's shared copy (matrix diagonals) or global (tccontext)
+    if (RATES) {
+#pragma unroll
+        for (int x = 0; x < 5; x++) {
+            const int f = __reduce_add_sync(0xFFFFFFFFu, dF[x]), r = __reduce_add_sync(0xFFFFFFFFu, dR[x]);
+            if (lane == 0) {
+                if (f) atomicAdd(&s_rates[6 * x], f);
+                if (r) atomicAdd(&s_rates[SD_NRATE + 6 * x], r);
+            }
+        }
+    }
+    if (CONTEXT) {
+#pragma unroll
+        for (int x = 0; x < 5; x++) {
+            const int f5 = __reduce_add_sync(0xFFFFFFFFu, c5F[x]), r5 = __reduce_add_sync(0xFFFFFFFFu, c5R[x]);
+            const int f3 = __reduce_add_sync(0xFFFFFFFFu, c3F[x]), r3 = __reduce_add_sync(0xFFFFFFFFu, c3R[x]);
+            if (lane == 0) {
+                add64(&A.context[0 + x], f5);
+                add64(&A.context[5 + x], r5);
+                add64(&A.context[10 + x], f3);
+                add64(&A.context[15 + x], r3);
+            }
+        }
+    }
+    __syncthreads();
+    if (RATES)
+        for (uint32_t i = threadIdx.x; i < 2u * SD_NRATE; i += blockDim.x) add64(&A.rates[i], s_rates[i]);
+    for (uint32_t i = threadIdx.x; i < n_rp; i += blockDim.x) add64(&A.readpos[i], s_readpos[i]);
+    for (uint32_t i = threadIdx.x; i < n_up; i += blockDim.x) add64(&A.utrpos[i], s_utrpos[i]);
 }
 
 }  // namespace
@@ -367,7 +411,15 @@ extern "C" int sd_read_stats(sd_ctx *ctx, const sd_batch *b, const sd_stats_args
     uint32_t blocks = (b->n_tiles + warps_per_block - 1) / warps_per_block;
     const uint32_t cap = (uint32_t)ctx->num_sms * 8u;    // grid-stride over tiles: a multiple of the SM count
     if (blocks > cap) blocks = cap;
-    sd_stats_kernel<<<blocks, warps_per_block * 32, 0, ctx->stream>>>(A);
+    // per-CTA shared copies of the read-position / UTR-position histograms when they fit (else global atomics)
+    size_t hist = (size_t)(a->d_readpos ? 6u * ((size_t)a->max_read_length + 1u) : 0u) + (size_t)(a->d_utrpos ? 6u * ((size_t)a->utr_norm + 1u) : 0u);
+    A.hist_smem = hist * sizeof(int) <= 40u * 1024u ? 1u : 0u;
+    const size_t smem = (2u * SD_NRATE + (A.hist_smem ? hist : 0u)) * sizeof(int);
+    const unsigned threads = warps_per_block * 32;
+    if (a->d_rates && a->d_context) sd_stats_kernel<true, true><<<blocks, threads, smem, ctx->stream>>>(A);
+    else if (a->d_rates) sd_stats_kernel<true, false><<<blocks, threads, smem, ctx->stream>>>(A);
+    else if (a->d_context) sd_stats_kernel<false, true><<<blocks, threads, smem, ctx->stream>>>(A);
+    else sd_stats_kernel<false, false><<<blocks, threads, smem, ctx->stream>>>(A);
     ctx->launches++;
     SD_CUDA(ctx, cudaGetLastError());
     return SD_OK;
