@@ -1188,6 +1188,7 @@ extern "C" void sd_destroy(sd_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_track_scratch);
+    cudaFree(ctx->d_filter_scratch);
     free_utr_tables(ctx);
     cudaFree(ctx->refx[0]); cudaFree(ctx->refx[1]);
     cudaFree(ctx->d_chrom_off); cudaFree(ctx->d_chrom_len);

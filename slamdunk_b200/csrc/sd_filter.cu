@@ -41,10 +41,17 @@ struct ReadInfo {      // per record, written by pass 1
 
 __global__ void filter_pass1(const sd_read_rec *rec, const uint32_t *cigar, const sd_tile *tiles, uint32_t n_tiles,
                              int multimap_mode, int mq, double min_identity, int max_nm, uint8_t *keep, ReadInfo *info,
-                             unsigned long long *stats) {
+                             uint8_t *state_out, uint64_t n_reads, unsigned long long *stats) {
+    // grid-stride over tiles; the six run counters stay in per-lane registers over all of a warp's tiles and reach global
+    // memory as one atomic per counter and CTA (one per counter and WARP serialised ~2 M same-address atomics at 50 M reads:
+    // 3.2 of the kernel's 3.6 ms)
+    __shared__ unsigned int s_cnt[6];
+    if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t tile = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (tile >= n_tiles) return;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t a_mapped = 0, a_unmapped = 0, a_filtered = 0, a_mq = 0, a_id = 0, a_nm = 0;
+    for (uint64_t tile = warp0; tile < n_tiles; tile += n_warps) {
     const uint64_t i = tile * 32 + lane;
     const sd_read_rec r = rec[i];
     const uint32_t flags = r.ref_mapq_flag >> 24, mapq = (r.ref_mapq_flag >> 16) & 0xFFu;
@@ -55,11 +62,13 @@ __global__ void filter_pass1(const sd_read_rec *rec, const uint32_t *cigar, cons
         const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, cs, d);
         if (lane >= (uint32_t)d) cs += t;
     }
-    const uint32_t *cg = cigar + tiles[tile].cig_off / 4 + (cs - ncig);
     uint32_t reflen = 0;
-    for (uint32_t k = 0; k < ncig; k++) {
-        const uint32_t c = cg[k];
-        if ((0x18Du >> (c & 15u)) & 1u) reflen += c >> 4;
+    if (multimap_mode) {            // the alignment's reference interval is only needed by the UTR lookups of pass 2
+        const uint32_t *cg = cigar + tiles[tile].cig_off / 4 + (cs - ncig);
+        for (uint32_t k = 0; k < ncig; k++) {
+            const uint32_t c = cg[k];
+            if ((0x18Du >> (c & 15u)) & 1u) reflen += c >> 4;
+        }
     }
     if (reflen == 0) reflen = 1;
     const bool pad = (flags & SD_F_PAD) != 0;
@@ -79,26 +88,32 @@ __global__ void filter_pass1(const sd_read_rec *rec, const uint32_t *cigar, cons
         }
         keep[i] = state == 1 ? 1 : 0;
     }
-    ReadInfo o;
-    o.pos = r.pos;
-    o.end = r.pos + (int32_t)reflen;
-    o.chrom = r.ref_mapq_flag & 0xFFFFu;
-    o.state = pad ? 3u : state;     // 3: padding, ends every scan
-    info[i] = o;
-    c_mapped = __reduce_add_sync(0xFFFFFFFFu, c_mapped);
-    c_unmapped = __reduce_add_sync(0xFFFFFFFFu, c_unmapped);
-    c_filtered = __reduce_add_sync(0xFFFFFFFFu, c_filtered);
-    c_mq = __reduce_add_sync(0xFFFFFFFFu, c_mq);
-    c_id = __reduce_add_sync(0xFFFFFFFFu, c_id);
-    c_nm = __reduce_add_sync(0xFFFFFFFFu, c_nm);
-    if (lane == 0) {
-        if (c_mapped) atomicAdd(&stats[SD_S_MAPPED], (unsigned long long)c_mapped);
-        if (c_unmapped) atomicAdd(&stats[SD_S_UNMAPPED], (unsigned long long)c_unmapped);
-        if (c_filtered) atomicAdd(&stats[SD_S_FILTERED], (unsigned long long)c_filtered);
-        if (c_mq) atomicAdd(&stats[SD_S_MQFILTERED], (unsigned long long)c_mq);
-        if (c_id) atomicAdd(&stats[SD_S_IDFILTERED], (unsigned long long)c_id);
-        if (c_nm) atomicAdd(&stats[SD_S_NMFILTERED], (unsigned long long)c_nm);
+    if (multimap_mode) {            // pass 2 replays the groups from these
+        ReadInfo o;
+        o.pos = r.pos;
+        o.end = r.pos + (int32_t)reflen;
+        o.chrom = r.ref_mapq_flag & 0xFFFFu;
+        o.state = pad ? 3u : state; // 3: padding, ends every scan
+        info[i] = o;
+    } else if (state_out && i < n_reads) state_out[i] = (uint8_t)state;   // default branch: the survivor class is all there is
+    a_mapped += c_mapped; a_unmapped += c_unmapped; a_filtered += c_filtered; a_mq += c_mq; a_id += c_id; a_nm += c_nm;
     }
+    a_mapped = __reduce_add_sync(0xFFFFFFFFu, a_mapped);
+    a_unmapped = __reduce_add_sync(0xFFFFFFFFu, a_unmapped);
+    a_filtered = __reduce_add_sync(0xFFFFFFFFu, a_filtered);
+    a_mq = __reduce_add_sync(0xFFFFFFFFu, a_mq);
+    a_id = __reduce_add_sync(0xFFFFFFFFu, a_id);
+    a_nm = __reduce_add_sync(0xFFFFFFFFu, a_nm);
+    if (lane == 0) {
+        if (a_mapped) atomicAdd(&s_cnt[SD_S_MAPPED], a_mapped);
+        if (a_unmapped) atomicAdd(&s_cnt[SD_S_UNMAPPED], a_unmapped);
+        if (a_filtered) atomicAdd(&s_cnt[SD_S_FILTERED], a_filtered);
+        if (a_mq) atomicAdd(&s_cnt[SD_S_MQFILTERED], a_mq);
+        if (a_id) atomicAdd(&s_cnt[SD_S_IDFILTERED], a_id);
+        if (a_nm) atomicAdd(&s_cnt[SD_S_NMFILTERED], a_nm);
+    }
+    __syncthreads();
+    if (threadIdx.x < 6 && s_cnt[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
 
 // UTR rows hit by [pos, end) on `chrom`, as (bed_index, name_id) sorted by bed_index.  Returns the count
@@ -131,12 +146,15 @@ __device__ int utr_hits(const FilterTables &T, uint32_t chrom, int64_t pos, int6
 
 __global__ void filter_pass2(const ReadInfo *info, const uint64_t *name_hash, uint64_t n, FilterTables T, uint8_t *keep,
                              uint8_t *utr_hit, unsigned long long *stats) {
+    // every thread stays to the end: the retained groups are counted per CTA (one global atomic per CTA, not per group)
+    __shared__ unsigned int s_kept;
+    if (threadIdx.x == 0) s_kept = 0u;
+    __syncthreads();
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || info[i].state != 2) return;
+    bool head = i < n && info[i].state == 2;
     // group head?  the previous survivor must be unique or carry another name (filter.py:115,173)
-    {
+    if (head) {
         uint64_t j = i;
-        bool head = true;
         while (j > 0) {
             j--;
             const uint32_t st = info[j].state;
@@ -144,8 +162,9 @@ __global__ void filter_pass2(const ReadInfo *info, const uint64_t *name_hash, ui
             head = (st != 2) || (name_hash[j] != name_hash[i]);
             break;
         }
-        if (!head) return;
     }
+    bool retained = false;
+    if (head) {
     uint32_t keys[SD_FILTER_MAX_KEYS];
     uint64_t last[SD_FILTER_MAX_KEYS];
     int n_keys = 0;
@@ -175,8 +194,13 @@ __global__ void filter_pass2(const ReadInfo *info, const uint64_t *name_hash, ui
     if (overflow) atomicAdd(&stats[SD_S_SLOWPATH], 1ull);             // host treats this as an error
     if (dump && n_keys > 0) {                                         // filter.py:118-120,178-180,197-199
         keep[last[n_keys - 1]] = 2;
-        atomicAdd(&stats[SD_S_FILTERED], 1ull);
+        retained = true;
     }
+    }
+    const unsigned int kept = __popc(__ballot_sync(0xFFFFFFFFu, retained));
+    if ((threadIdx.x & 31u) == 0 && kept) atomicAdd(&s_kept, kept);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_kept) atomicAdd(&stats[SD_S_FILTERED], (unsigned long long)s_kept);
 }
 
 __global__ void export_state(const ReadInfo *info, uint64_t n, uint8_t *state) {   // state[] arrives holding the UTR-hit bits
@@ -207,15 +231,24 @@ extern "C" int sd_filter(sd_ctx *ctx, const sd_batch *b, const sd_params *p, con
     SD_CUDA(ctx, cudaMemsetAsync(d_keep, 0, std::max<uint64_t>(1, b->n_reads), ctx->stream));
     if (d_state) SD_CUDA(ctx, cudaMemsetAsync(d_state, 0, std::max<uint64_t>(1, b->n_reads), ctx->stream));
     if (b->n_tiles == 0) { SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return SD_OK; }
-    ReadInfo *info = nullptr;
-    uint8_t *keep_pad = nullptr;
-    SD_CUDA(ctx, cudaMalloc(&info, n_pad * sizeof(ReadInfo)));
-    SD_CUDA(ctx, cudaMalloc(&keep_pad, n_pad));
+    // per-record scratch (16-byte info + padded keep flags) lives in a grow-only buffer of the context: `slamdunk filter`
+    // runs one BAM after the other, and allocating ~17 bytes per read on every call cost more than the kernels
+    const size_t need = (size_t)n_pad * sizeof(ReadInfo) + (size_t)n_pad;
+    if (need > ctx->filter_scratch_cap) {
+        cudaFree(ctx->d_filter_scratch);
+        ctx->d_filter_scratch = nullptr;
+        ctx->filter_scratch_cap = 0;
+        SD_CUDA(ctx, cudaMalloc(&ctx->d_filter_scratch, need));
+        ctx->filter_scratch_cap = need;
+    }
+    ReadInfo *info = reinterpret_cast<ReadInfo *>(ctx->d_filter_scratch);
+    uint8_t *keep_pad = reinterpret_cast<uint8_t *>(ctx->d_filter_scratch) + (size_t)n_pad * sizeof(ReadInfo);
     SD_CUDA(ctx, cudaMemsetAsync(keep_pad, 0, n_pad, ctx->stream));
     unsigned long long *st = reinterpret_cast<unsigned long long *>(d_stats);
-    filter_pass1<<<(unsigned)((n_pad + 255) / 256), 256, 0, ctx->stream>>>(b->rec, b->cigar, b->tiles, b->n_tiles, multimap ? 1 : 0,
+    const unsigned p1_blocks = (unsigned)std::min<uint64_t>((n_pad + 255) / 256, (uint64_t)ctx->num_sms * 16u);
+    filter_pass1<<<p1_blocks, 256, 0, ctx->stream>>>(b->rec, b->cigar, b->tiles, b->n_tiles, multimap ? 1 : 0,
                                                                           p->filter_mq, p->filter_min_identity, p->filter_max_nm,
-                                                                          keep_pad, info, st);
+                                                                          keep_pad, info, d_state, b->n_reads, st);
     ctx->launches++;
     int rc = SD_OK;
     uint32_t *d_cb = nullptr, *d_nm = nullptr, *d_bi = nullptr;
@@ -245,7 +278,6 @@ extern "C" int sd_filter(sd_ctx *ctx, const sd_batch *b, const sd_params *p, con
             for (uint32_t k = cb[c]; k < cb[c + 1]; k++) m[k] = (k == cb[c]) ? e[k] : std::max(m[k - 1], e[k]);
         if ((rc = to_device(ctx, &d_cb, cb)) || (rc = to_device(ctx, &d_s, s)) || (rc = to_device(ctx, &d_e, e)) ||
             (rc = to_device(ctx, &d_m, m)) || (rc = to_device(ctx, &d_nm, nm)) || (rc = to_device(ctx, &d_bi, bi))) {
-            cudaFree(info); cudaFree(keep_pad);
             return rc;
         }
         FilterTables T{d_cb, d_s, d_e, d_m, d_nm, d_bi, n_chrom};
@@ -253,13 +285,12 @@ extern "C" int sd_filter(sd_ctx *ctx, const sd_batch *b, const sd_params *p, con
         ctx->launches++;
     }
     SD_CUDA(ctx, cudaMemcpyAsync(d_keep, keep_pad, b->n_reads, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (d_state) {
+    if (d_state && multimap) {
         export_state<<<(unsigned)((b->n_reads + 255) / 256), 256, 0, ctx->stream>>>(info, b->n_reads, d_state);
         ctx->launches++;
     }
     cudaError_t e1 = cudaGetLastError();
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(info); cudaFree(keep_pad);
     cudaFree(d_cb); cudaFree(d_s); cudaFree(d_e); cudaFree(d_m); cudaFree(d_nm); cudaFree(d_bi);
     if (e1 != cudaSuccess || e2 != cudaSuccess)
         return sd_fail(ctx, SD_ERR_CUDA, "sd_filter: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));

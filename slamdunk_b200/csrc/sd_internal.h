@@ -63,6 +63,10 @@ struct sd_ctx {
     void *d_track_scratch = nullptr;
     size_t track_scratch_cap = 0;
 
+    // grow-only scratch of sd_filter (per-record info | padded keep flags)
+    void *d_filter_scratch = nullptr;
+    size_t filter_scratch_cap = 0;
+
     // staging for sd_count_host
     void *d_stage[2] = {nullptr, nullptr};
     size_t stage_cap = 0;
