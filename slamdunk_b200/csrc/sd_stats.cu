@@ -268,11 +268,20 @@ __global__ void __launch_bounds__(256) sd_stats_kernel(const StatsArgs A) {
                 const long long L = __ldg(&A.row_blen[row]);
                 const bool plus_row = __ldg(&A.row_strand[row]) == 0;   // `if utr.strand == "+"` (a row without strand takes the else branch)
                 const long long start_ref = (long long)g - (long long)ent.x, end_ref = (long long)e - (long long)ent.x;
-                if (A.utr_rates && !(!is_tc_read && A.strict && tc_count > 0)) {      // stats.py:376
+                if (A.utr_rates) {
+                    // lanes of a sorted tile mostly sit in the same UTR: the lanes that are here together and hit the same row
+                    // sum their matrices in the warp and one of them adds (26 same-address atomics per lane otherwise)
+                    const bool take = !(!is_tc_read && A.strict && tc_count > 0);       // stats.py:376
+                    const unsigned grp = __match_any_sync(__activemask(), row);
+                    const bool leader = lane == (uint32_t)(__ffs((int)grp) - 1);
                     unsigned long long *dst = A.utr_rates + (size_t)row * (SD_NRATE + 1);
 #pragma unroll
-                    for (int c = 0; c < SD_NRATE; c++) add64(&dst[c], m[c]);
-                    atomicAdd(&dst[SD_NRATE], 1ull);
+                    for (int c = 0; c < SD_NRATE; c++) {
+                        const int sum = __reduce_add_sync(grp, take ? m[c] : 0);
+                        if (leader) add64(&dst[c], sum);
+                    }
+                    const int n_take = __reduce_add_sync(grp, take ? 1 : 0);
+                    if (leader) add64(&dst[SD_NRATE], n_take);
                 }
                 const bool no_list = !is_tc_read && A.strict;                           // stats.py:806-810, tcounter.py:210-214
                 if (A.utr_snp) {
@@ -286,9 +295,13 @@ __global__ void __launch_bounds__(256) sd_stats_kernel(const StatsArgs A) {
                             }
                         });
                     unsigned long long *dst = A.utr_snp + (size_t)row * 3;
-                    atomicAdd(&dst[0], 1ull);
-                    if (is_tc) atomicAdd(&dst[1], 1ull);
-                    if (is_true_tc) atomicAdd(&dst[2], 1ull);
+                    const unsigned grp = __match_any_sync(__activemask(), row);       // same-row lanes add once, as above
+                    const int n_reads = __popc(grp), n_tc = __reduce_add_sync(grp, is_tc ? 1 : 0), n_true = __reduce_add_sync(grp, is_true_tc ? 1 : 0);
+                    if (lane == (uint32_t)(__ffs((int)grp) - 1)) {
+                        add64(&dst[0], n_reads);
+                        add64(&dst[1], n_tc);
+                        add64(&dst[2], n_true);
+                    }
                 }
                 if (A.utrpos) {
                     const size_t ld = (size_t)norm + 1;
