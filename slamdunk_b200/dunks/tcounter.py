@@ -299,7 +299,8 @@ def genomewideConversionRates(referenceFile, snpsFile, bam, minBaseQual, outputB
     genome, cached = _genome(referenceFile)
     tm["fasta_decode_s"] = 0.0 if cached else genome.seconds
     mode = {"cigar": L.SD_MISMATCH_CIGAR, "mp": L.SD_MISMATCH_MP, "verify": L.SD_MISMATCH_VERIFY}[OPTIONS["mismatch_source"]]
-    hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True)
+    hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True,
+                       seq2=OPTIONS["seq_bits"] == 2)
     tm["bam_inflate_s"], tm["bam_decode_s"], tm["bam_reads"] = hbatch.seconds_inflate, hbatch.seconds_decode, hbatch.n_reads
     tc_mask, ag_mask = build_snp_masks(snpsFile, genome.names, genome.chrom_off, genome.chrom_len, genome.n_words, warn=print)
 
@@ -391,7 +392,8 @@ def genomewideReadSeparation(referenceFile, snpsFile, bam, minBaseQual, outputBA
     t0 = time.time()
     genome, cached = _genome(referenceFile)
     mode = {"cigar": L.SD_MISMATCH_CIGAR, "mp": L.SD_MISMATCH_MP, "verify": L.SD_MISMATCH_VERIFY}[OPTIONS["mismatch_source"]]
-    hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True)
+    hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True,
+                       seq2=OPTIONS["seq_bits"] == 2)
     tm["bam_inflate_s"], tm["bam_decode_s"], tm["bam_reads"] = hbatch.seconds_inflate, hbatch.seconds_decode, hbatch.n_reads
     tc_mask, ag_mask = build_snp_masks(snpsFile, genome.names, genome.chrom_off, genome.chrom_len, genome.n_words, warn=print)
     n = hbatch.n_reads
