@@ -139,3 +139,29 @@ def test_device_built_mp_column_gives_the_file_route_results(tmp_path):
     for k in want:
         assert np.array_equal(dev_res[k], file_res[k]), k
     assert dev_res["rates"].sum() > 0 and dev_res["utr_snp"].reshape(-1, 3)[:, 0].sum() > 20_000
+
+
+@pytest.mark.parametrize("q,maxlen", [(0, 60), (27, 60), (36, 35)])
+def test_stats_match_oracle_on_edge_cases(q, maxlen, tmp_path):
+    """statsrun.make_edge_case (pinned against the live reference in tests/test_oracle.py): MP entries past the read end
+    (quality 0; negative mirrored positions on reverse reads), N bases, soft / hard clips, entries outside the UTR, a read
+    over the chromosome end, SNPs under conversions, reads without MP tag, all through the GPU tools and the mle lists."""
+    from slamdunk_b200.dunks import tcounter
+    ref, bed, vcf, bam = statsrun.make_edge_case(str(tmp_path))
+    for tool, strict in goldens.StatsCase.RUNS:
+        g, o = str(tmp_path / (tool + str(strict) + "_g.csv")), str(tmp_path / (tool + str(strict) + "_o.csv"))
+        statsrun.run_gpu(tool, g, ref, bam, bed, vcf, q, maxlen, strict)
+        statsrun.run_oracle(tool, o, ref, bam, bed, vcf, q, maxlen, strict)
+        assert _read(g) == _read(o), (tool, strict)
+    out = str(tmp_path / "x_tcount.tsv")
+    tcounter.OPTIONS["mismatch_source"] = "mp"        # the hand-made MP tags do not describe SEQ / CIGAR: count as slamdunk does
+    try:
+        tcounter.computeTconversions(ref, bed, vcf, bam, maxlen, q, out, str(tmp_path / "p"), str(tmp_path / "m"), 1, io.StringIO(), True)
+    finally:
+        tcounter.OPTIONS["mismatch_source"] = "verify"
+    lists = stats_oracle.perread_lists(ref, bed, vcf, bam, maxlen, q, 1)
+    cols = statsrun.perread_columns(str(tmp_path / "x_tcount_perread.tsv"))
+    assert len(cols) == len(lists)
+    for (n_txt, k_txt), (n_list, k_list) in zip(cols, lists):
+        if n_list:
+            assert n_txt == ",".join(map(str, n_list)) and k_txt == ",".join(map(str, k_list))

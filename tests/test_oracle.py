@@ -200,3 +200,25 @@ def test_stats_oracle_matches_live_reference(seed, q, maxlen, read_len, tmp_path
                 lambda: statsrun.run_oracle("tccontext", str(tmp_path / "y.csv"), c.ref, c.bam, None, None, q, maxlen, False)):
         with pytest.raises(ValueError, match="invalid contig"):
             run()
+
+
+@pytest.mark.skipif(not refrun.available(), reason="reference tree not present")
+@pytest.mark.parametrize("q,maxlen", [(0, 60), (27, 60), (36, 35)])
+def test_stats_oracle_matches_live_reference_on_edge_cases(q, maxlen, tmp_path):
+    """statsrun.make_edge_case: MP entries past the read end (quality 0, negative mirrored positions), N bases, clips,
+    entries outside the UTR, a read over the chromosome end, SNPs under conversions ..."""
+    ref, bed, vcf, bam = statsrun.make_edge_case(str(tmp_path))
+    for tool, strict in goldens.StatsCase.RUNS:
+        r, o = str(tmp_path / "r.csv"), str(tmp_path / "o.csv")
+        for f in (r, o):
+            if os.path.exists(f):
+                os.remove(f)
+        refrun.run_stats(tool, r, ref, bam, bed=bed, vcf=vcf, min_qual=q, max_read_length=maxlen, strict=strict)
+        statsrun.run_oracle(tool, o, ref, bam, bed, vcf, q, maxlen, strict)
+        assert _read(r) == _read(o), (tool, strict)
+    perread = refrun.run_count_mle(ref, bed, vcf, bam, str(tmp_path / "m"), maxlen, q, 1)
+    lists = stats_oracle.perread_lists(ref, bed, vcf, bam, maxlen, q, 1)
+    cols = statsrun.perread_columns(perread)
+    for (n_txt, k_txt), (n_list, k_list) in zip(cols, lists):
+        if n_list:
+            assert n_txt == ",".join(map(str, n_list)) and k_txt == ",".join(map(str, k_list))
