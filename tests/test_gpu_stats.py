@@ -165,3 +165,7 @@ def test_stats_match_oracle_on_edge_cases(q, maxlen, tmp_path):
     for (n_txt, k_txt), (n_list, k_list) in zip(cols, lists):
         if n_list:
             assert n_txt == ",".join(map(str, n_list)) and k_txt == ",".join(map(str, k_list))
+    from oracle import oracle
+    oo = str(tmp_path / "o_tcount.tsv")
+    oracle.count_files(ref, bed, vcf, bam, maxlen, q, oo, str(tmp_path / "op"), str(tmp_path / "om"), 1, io.StringIO())
+    assert _read(out) == _read(oo) and _read(str(tmp_path / "p")) == _read(str(tmp_path / "op")) and _read(str(tmp_path / "m")) == _read(str(tmp_path / "om"))
