@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Instruction / stall-sample share per source region of sd_count.cu.  Regions are delimited by
+"""Instruction / stall-sample share per source region of sd_count_kernel.cuh (the count kernel's device code).  Regions are delimited by
 comment markers `// @region <name>` in the source; input is an
 `ncu --page source --csv --print-source cuda,sass` dump."""
 import csv
@@ -8,7 +8,7 @@ import sys
 from collections import defaultdict
 
 rows = list(csv.reader(open(sys.argv[1])))
-src = open(sys.argv[2] if len(sys.argv) > 2 else "slamdunk_b200/csrc/sd_count.cu").read().split("\n")
+src = open(sys.argv[2] if len(sys.argv) > 2 else "slamdunk_b200/csrc/sd_count_kernel.cuh").read().split("\n")
 region_of = {}
 cur = "preamble"
 for i, line in enumerate(src, 1):
@@ -40,7 +40,7 @@ for r in rows:
         ii, si, ti = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
         if r[ii] == "":
             continue
-        key = region_of.get(ln, "?") if curfile == "sd_count.cu" else "hdr:" + curfile
+        key = region_of.get(ln, "?") if curfile in ("sd_count_kernel.cuh", "sd_count.cu") else "hdr:" + curfile
         inst[key] += int(r[ii])
         smp[key] += int(r[si] or 0)
         thr[key] += int(r[ti] or 0)

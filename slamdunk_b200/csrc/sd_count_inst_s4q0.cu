@@ -1,0 +1,9 @@
+// one column form of the count kernel: SEQ form 4, quality planes 0 (0 = bytes); see sd_count_kernel.cuh
+#include "sd_count_kernel.cuh"
+
+template int launch_count<4, 4, 0>(sd_ctx *, CountArgs &, cudaStream_t, bool);
+template int launch_count<6, 4, 0>(sd_ctx *, CountArgs &, cudaStream_t, bool);
+template int launch_count<8, 4, 0>(sd_ctx *, CountArgs &, cudaStream_t, bool);
+template int launch_count<10, 4, 0>(sd_ctx *, CountArgs &, cudaStream_t, bool);
+template int launch_count<12, 4, 0>(sd_ctx *, CountArgs &, cudaStream_t, bool);
+template int launch_count<16, 4, 0>(sd_ctx *, CountArgs &, cudaStream_t, bool);
