@@ -518,3 +518,33 @@ def test_bam_decoder_two_bit_seq_and_full_mp_columns(tmp_path):
         HostBatch(path, names, threads=3, mp_all=True, seq2=True)
     for h in (h4, h2, hm):
         h.close()
+
+
+def test_utrrates_percentages_and_checkstep_host_logic(tmp_path):
+    """host side of `alleyoop utrrates` (stats.py:386-486: the strand swap, the `conversionSum =+` quirk, division guards)
+    against the oracle restatement on random matrices; checkStep's date rules (utils/misc.py:147-164)."""
+    import random
+    import time
+    from oracle import stats_oracle
+    from slamdunk_b200.dunks import stats
+    rng = random.Random(7)
+    seen_none = seen_some = 0
+    for _ in range(400):
+        m = [rng.choice([0, 0, 1, 3, 50, 1000]) for _ in range(25)]
+        if rng.random() < 0.3:
+            m[18] = 0                                   # T_T = 0: the row adds nothing, whatever else it holds
+        for strand in ("+", "-", "."):
+            a, b = stats._utr_percentages(m, strand), stats_oracle.utr_percentages(m, strand)
+            assert a == b
+            seen_none += a is None
+            seen_some += a is not None
+    assert seen_none and seen_some
+    src, out = str(tmp_path / "in.txt"), str(tmp_path / "out.txt")
+    open(src, "w").write("x")
+    assert stats.checkStep([src], [out]) is True                       # output missing: run
+    time.sleep(0.05)
+    open(out, "w").write("y")
+    assert stats.checkStep([src], [out]) is False                      # output newer: skip ...
+    assert stats.checkStep([src], [out], force=True) is True           # ... unless forced
+    with pytest.raises(RuntimeError, match="don't exist"):
+        stats.checkStep([src, str(tmp_path / "missing")], [out])
