@@ -182,7 +182,8 @@ def workload_config(args, sample_reads=None):
          "filter": "MQ>=2, identity>=0.95 (slamdunk defaults)", "min_base_qual": MIN_QUAL, "conversion_threshold": CONV_THRESHOLD,
          "mismatch_source": "cigar_walk", "read_order": args.order, "seq_bits": getattr(args, "seq_bits", 2),
          "qual_form": getattr(args, "qual_form", "planes") if getattr(args, "seq_bits", 2) == 2 else "bytes", "sharding": "utr_owner_regions" if args.gpus > 1 else "none",
-         "l2_policy": "inputs (~%.1f GB per GPU) far exceed the 126 MB L2; no explicit flush" % (args.reads * (getattr(args, "seq_bits", 2) * 4 * ((args.read_len + 31) // 32) + args.read_len + 24.4) / 1e9)}
+         "l2_policy": "inputs (~%.1f GB per GPU) far exceed the 126 MB L2; no explicit flush" % (args.reads * (getattr(args, "seq_bits", 2) * 4 * ((args.read_len + 31) // 32) +
+                                                                                                         (8 * ((args.read_len + 31) // 32) if getattr(args, "seq_bits", 2) == 2 and getattr(args, "qual_form", "planes") == "planes" else args.read_len) + 24.4) / 1e9)}
     if sample_reads is not None:
         c["sample_reads"] = sample_reads
     return c
