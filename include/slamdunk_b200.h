@@ -41,7 +41,7 @@ extern "C" {
 #define SD_ERR_LIMIT (-6)
 #define SD_ERR_NOMEM (-7)
 
-#define SD_ABI_VERSION 5
+#define SD_ABI_VERSION 6
 
 typedef struct sd_ctx sd_ctx;
 
@@ -292,6 +292,8 @@ typedef struct sd_hbatch {
     double seconds_decode;
     uint64_t compressed_bytes;
     uint64_t inflated_bytes;
+    uint64_t n_mapped_no_xi; /* mapped records without an XI tag (their sd_read_rec.xi is NaN) / without an NM tag (nm = 0): */
+    uint64_t n_mapped_no_nm; /* read.get_tag() raises KeyError for them in the reference (filter.py:246,249) */
     void *opaque;
 } sd_hbatch;
 

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SLAMDUNK_B200_LIB") or os.path.join(HERE, "libslamdunk_b200.so")   # env: kernel experiments
 
 SD_OK = 0
-SD_ABI_VERSION = 5   # include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual; 4 = BAI writer; 5 = sd_read_stats
+SD_ABI_VERSION = 6   # 6 = sd_hbatch.n_mapped_no_xi/nm, wire form; include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual; 4 = BAI writer; 5 = sd_read_stats
 SD_F_REVERSE, SD_F_UNMAPPED, SD_F_SECONDARY, SD_F_SUPPLEMENTARY = 0x01, 0x02, 0x04, 0x08
 SD_F_HAS_MP, SD_F_SKIP, SD_F_NEWNAME, SD_F_PAD = 0x10, 0x20, 0x40, 0x80
 SD_REF_NONE = 0xFFFF
@@ -60,7 +60,8 @@ class HBatch(ctypes.Structure):
     _fields_ = [("batch", Batch), ("name_hash", c_u64p), ("order", c_u32p), ("header_text", ctypes.c_char_p), ("n_ref", ctypes.c_uint32),
                 ("ref_names", ctypes.POINTER(ctypes.c_char_p)), ("ref_lengths", c_u32p),
                 ("seconds_inflate", ctypes.c_double), ("seconds_decode", ctypes.c_double),
-                ("compressed_bytes", ctypes.c_uint64), ("inflated_bytes", ctypes.c_uint64), ("opaque", ctypes.c_void_p)]
+                ("compressed_bytes", ctypes.c_uint64), ("inflated_bytes", ctypes.c_uint64),
+                ("n_mapped_no_xi", ctypes.c_uint64), ("n_mapped_no_nm", ctypes.c_uint64), ("opaque", ctypes.c_void_p)]
 
 
 class HGenome(ctypes.Structure):

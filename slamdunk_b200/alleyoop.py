@@ -247,7 +247,25 @@ def build_parser():
         p.add_argument("-t", "--threads", type=int, required=False, dest="threads", default=1, help="Thread number (default: %(default)s)")
     for name in STATS_COMMANDS:
         sub.choices[name].add_argument("--device", type=int, default=0, help="CUDA device")
+    # host-only table tools (alleyoop.py:379-390)
+    p = sub.add_parser("summary", help="Display summary information and statistics on read numbers")
+    p.add_argument("bam", action="store", help="Filtered BAM files (produced by slamdunk filter or all)", nargs="+")
+    p.add_argument("-o", "--output", type=str, required=True, dest="outputFile", help="Output file")
+    p.add_argument("-t", "--tcountDir", type=str, required=False, dest="countDirectory", help="Folder containing tcount files")
+    p = sub.add_parser("merge", help="Merge T->C rates from multiple sample in one TSV file", formatter_class=ArgumentDefaultsHelpFormatter)
+    p.add_argument("countFiles", action="store", help="tCount files", nargs="+")
+    p.add_argument("-o", "--output", type=str, required=True, dest="outputFile", default=SUPPRESS, help="Output file")
+    p.add_argument("-c", "--column", dest="column", type=str, required=False, default="TcReadCount / ReadCount", help="Column or expression used to summarize files.")
+    p.add_argument("-n", "--columnname", dest="columnName", type=int, required=False, default=2, help="Index of meta data field to use as column name.")
+    # tools of the reference that are NOT provided: registered so that the failure says why instead of "invalid choice"
+    for name, what in UNSUPPORTED.items():
+        p = sub.add_parser(name, help=what + " (not provided by slamdunk_b200)")
+        p.add_argument("rest", nargs="*")
     return parser
+
+
+UNSUPPORTED = {"dedup": "Deduplicate SLAM-seq aligned data", "dump": "Print all info available for slamdunk reads",
+               "half-lifes": "Compute half-lifes"}
 
 
 def _run_stats(args):
@@ -283,10 +301,31 @@ def _run_stats(args):
 
 def run(argv=None):
     parser = build_parser()
+    if argv is None:
+        argv = sys.argv[1:]
+    if argv and argv[0] in UNSUPPORTED:
+        sys.exit("alleyoop " + argv[0] + " is not provided by slamdunk_b200 (it is outside the accelerated count path); "
+                 "use the reference's alleyoop for it.")
     args = parser.parse_args(argv)
-    if args.command not in ("positional-tracks", "read-separator", "collapse") + STATS_COMMANDS:
+    if args.command not in ("positional-tracks", "read-separator", "collapse", "summary", "merge") + STATS_COMMANDS:
         parser.print_help()
         sys.exit(0)
+    if args.command == "summary":                        # alleyoop.py:533-536
+        from .dunks import tables
+        message("Running alleyoop summary for " + str(len(args.bam)) + " files")
+        log = getLogFile(replaceExtension(args.outputFile, ".log"))
+        tables.readSummary(args.bam, args.countDirectory, args.outputFile, log)
+        log.close()
+        dunkFinished()
+        return
+    if args.command == "merge":                          # alleyoop.py:538-542
+        from .dunks import tables
+        message("Running alleyoop merge for " + str(len(args.countFiles)) + " files")
+        log = getLogFile(replaceExtension(args.outputFile, ".log"))
+        tables.mergeRates(",".join(args.countFiles), args.outputFile, args.column, args.columnName, log)
+        log.close()
+        dunkFinished()
+        return
     if args.command in STATS_COMMANDS:
         _run_stats(args)
         return

@@ -171,6 +171,7 @@ struct AuxInfo {
     uint32_t nm;
     const char *mp;  // MP:Z payload or null
     bool has_mp;
+    bool has_xi, has_nm;
 };
 
 // Walk the BAM optional fields once.
@@ -179,6 +180,7 @@ bool parse_aux(const uint8_t *p, const uint8_t *end, AuxInfo &a) {
     a.nm = 0;
     a.mp = nullptr;
     a.has_mp = false;
+    a.has_xi = a.has_nm = false;
     while (p + 3 <= end) {
         const uint8_t t0 = p[0], t1 = p[1], ty = p[2];
         p += 3;
@@ -210,7 +212,7 @@ bool parse_aux(const uint8_t *p, const uint8_t *end, AuxInfo &a) {
                 if (p + 4 > end) return false;
                 float f;
                 memcpy(&f, p, 4);
-                if (t0 == 'X' && t1 == 'I') a.xi = f;
+                if (t0 == 'X' && t1 == 'I') { a.xi = f; a.has_xi = true; }
                 num = f;
                 p += 4;
                 break;
@@ -238,8 +240,8 @@ bool parse_aux(const uint8_t *p, const uint8_t *end, AuxInfo &a) {
                 return false;
         }
         if (is_num) {
-            if (t0 == 'N' && t1 == 'M') a.nm = num < 0 ? 0u : (num > 65535.0 ? 65535u : (uint32_t)num);
-            if (t0 == 'X' && t1 == 'I') a.xi = (float)num;
+            if (t0 == 'N' && t1 == 'M') { a.nm = num < 0 ? 0u : (num > 65535.0 ? 65535u : (uint32_t)num); a.has_nm = true; }
+            if (t0 == 'X' && t1 == 'I') { a.xi = (float)num; a.has_xi = true; }
         }
     }
     return true;
@@ -597,6 +599,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     std::vector<const char *> mp_ptr(n, nullptr);
     std::atomic<int> fmt_err(0), limit_err(0);
     std::atomic<uint32_t> max_span(0);
+    std::atomic<uint64_t> no_xi(0), no_nm(0);   // mapped records without the tag: read.get_tag raises KeyError there (filter.py:246,249)
     std::atomic<uint64_t> qual_seen[4];   // which of the 256 quality values occur (sizes the transfer coding of the column)
     for (auto &w : qual_seen) w = 0;
 
@@ -624,6 +627,10 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         if (flag & 0x100) f |= SD_F_SECONDARY;
         if (flag & 0x800) f |= SD_F_SUPPLEMENTARY;
         if (a.has_mp) f |= SD_F_HAS_MP;
+        if (!(f & SD_F_UNMAPPED)) {
+            if (!a.has_xi) no_xi.fetch_add(1, std::memory_order_relaxed);
+            if (!a.has_nm) no_nm.fetch_add(1, std::memory_order_relaxed);
+        }
         uint32_t ref = SD_REF_NONE;
         if (ref_id >= 0 && ref_id < n_ref) ref = ref_map[(size_t)ref_id];
         if (ref == SD_REF_NONE) f |= SD_F_SKIP;
@@ -886,6 +893,8 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     hb->seconds_decode = t2 - t1;
     hb->compressed_bytes = compressed;
     hb->inflated_bytes = raw.size();
+    hb->n_mapped_no_xi = no_xi.load();
+    hb->n_mapped_no_nm = no_nm.load();
     *out = hb;
     return SD_OK;
 }

@@ -29,6 +29,19 @@ def Filter(inputBAM, outputBAM, log, bed, MQ=2, minIdentity=0.8, NM=-1, printOnl
         print("Skipped filtering for " + inputBAM, file=log)
         return
     hb = HostBatch(inputBAM, [], want_mp=False, threads=OPTIONS["threads"])
+    # read.get_tag("XI") / get_tag("NM") raise KeyError on a record without the tag (filter.py:246,249; :130,133 in the
+    # retention branch, which has no MQ test before them): a BAM that NextGenMap did not write must not pass silently
+    if hb.n_mapped_no_xi:
+        rec = hb.rec_array()[:hb.n_reads]
+        reached = ((rec[:, 1] >> 24) & L.SD_F_UNMAPPED) == 0
+        if bed is None:
+            reached &= ((rec[:, 1] >> 16) & 0xFF) >= MQ
+        if np.any(reached & np.isnan(rec[:, 2].view(np.float32))):
+            hb.close()
+            raise KeyError("tag 'XI' not present")
+    if NM > -1 and hb.n_mapped_no_nm:
+        hb.close()
+        raise KeyError("tag 'NM' not present")
     eng = CountEngine(OPTIONS["device"])
     try:
         db = DeviceBatch.from_host(hb.batch, eng.device, eng)

@@ -162,6 +162,7 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
         eng.count_host(my_batch, params)
         if world > 1:
             parallel.reduce_engine_outputs(eng, positions=True)
+        eng.synchronize()              # the all-reduce runs on eng.stream: every rank must branch on the REDUCED counter
         stats = eng.stats.cpu().numpy()
         if mode == L.SD_MISMATCH_VERIFY and stats[L.SD_S_MP_DISAGREE] > 0:
             # the BAM's MP tags do not describe the same mismatches as SEQ/CIGAR vs this FASTA: the reference
@@ -412,6 +413,7 @@ def genomewideReadSeparation(referenceFile, snpsFile, bam, minBaseQual, outputBA
         # still make a TC read for conversionThreshold 0): ask the kernel for every conversion
         params = make_params(min_qual=minBaseQual, conversion_threshold=0, mismatch_source=mode)
         eng.count(db, params, read_tc)
+        eng.synchronize()              # sd_count_reads only queues the kernel on eng.stream; .cpu() copies on another stream
         stats = eng.stats.cpu().numpy()
         if mode == L.SD_MISMATCH_VERIFY and stats[L.SD_S_MP_DISAGREE] > 0:
             print("Warning: %d reads carry MP tags that disagree with a CIGAR walk against %s; taking the conversions from the MP tags as slamdunk does."

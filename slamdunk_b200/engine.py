@@ -94,6 +94,8 @@ class HostBatch(object):
         self.seconds_decode = float(h.seconds_decode)
         self.compressed_bytes = int(h.compressed_bytes)
         self.inflated_bytes = int(h.inflated_bytes)
+        self.n_mapped_no_xi = int(h.n_mapped_no_xi)
+        self.n_mapped_no_nm = int(h.n_mapped_no_nm)
 
     # numpy views (tests, diagnostics)
     def rec_array(self) -> np.ndarray:

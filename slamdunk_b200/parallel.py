@@ -73,9 +73,11 @@ def allreduce_sum_(tensors, group=None):
 
 def reduce_engine_outputs(eng, positions=True, group=None):
     """All-reduce an engine's outputs on its stream: counters + stats, and the per-position arrays
-    when the reads (not the UTRs) were partitioned.  Call before eng.finalize()."""
+    when the reads (not the UTRs) were partitioned.  Call before eng.finalize().  Returns after the reduction has
+    completed, so that a decision taken from the reduced values is the same on every rank."""
     with torch.cuda.stream(eng.stream):
         ts = [eng.counters, eng.stats]
         if positions and eng.n_positions:
             ts += [eng.pos_cov, eng.pos_tc]
         allreduce_sum_(ts, group)
+    eng.synchronize()      # callers read eng.stats / eng.counters next, from other streams

@@ -20,7 +20,14 @@ def read_vcf_records(path, warn=None):
         if warn is not None:
             warn("Warning: SNP file " + path + " not found.")
         return
-    with open(path, "r") as fh:
+    with open(path, "rb") as probe:                  # pybedtools reads gzip / bgzip VCFs transparently (SNPtools.py:43)
+        gz = probe.read(2) == b"\x1f\x8b"
+    if gz:
+        import gzip
+        fh = gzip.open(path, "rt")
+    else:
+        fh = open(path, "r")
+    with fh:
         for line in fh:
             if not line or line[0] == "#" or not line.strip():
                 continue

@@ -6,6 +6,8 @@ import pytest
 
 import goldens
 
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
 
 def _ns(argv):
     from slamdunk_b200.cli import build_parser
@@ -91,3 +93,59 @@ def test_collapse_matches_reference(tmp_path):
     from slamdunk_b200 import alleyoop
     alleyoop.run(["collapse", "-o", str(tmp_path / "c"), str(src)])
     assert (tmp_path / "c" / "x_tcount_collapsed.csv").read_text() == got
+
+
+def test_summary_and_merge(tmp_path):
+    """alleyoop summary (stats.readSummary, stats.py:531-589) and merge (plot/merge_rate_files.R): host-only table tools on
+    the BAM header's DS field and tcount files.  summary is compared with the unmodified reference where it is present."""
+    import io
+    import refrun
+    from slamdunk_b200 import alleyoop
+    from slamdunk_b200.dunks import tables
+    bam = os.path.join(GOLD, "cfg1", "reads_slamdunk_mapped_filtered.bam")
+    tdir = tmp_path / "count"
+    tdir.mkdir()
+    body = open(os.path.join(GOLD, "cfg1", "expected_tcount.tsv")).read()
+    (tdir / "reads_slamdunk_mapped_filtered_tcount.tsv").write_text(body)
+    out = tmp_path / "summary.tsv"
+    alleyoop.run(["summary", "-o", str(out), "-t", str(tdir), bam])
+    lines = out.read_text().split("\n")
+    assert lines[0].startswith("# slamdunk summary v")
+    assert lines[1].split("\t")[-2:] == ["Counted", "Annotation"]
+    row = lines[2].split("\t")
+    assert row[0] == bam and int(row[12]) == tables.sumCounts(str(tdir / "reads_slamdunk_mapped_filtered_tcount.tsv"))
+    alleyoop.run(["summary", "-o", str(tmp_path / "s2.tsv"), bam])
+    assert (tmp_path / "s2.tsv").read_text().split("\n")[1].split("\t")[-2:] == ["Retained", "Annotation"]
+    if refrun.available():
+        refrun.reference_modules()
+        from slamdunk.dunks import stats as rstats
+        rstats.readSummary([bam], None, str(tmp_path / "ref.tsv"), io.StringIO())
+        assert (tmp_path / "ref.tsv").read_text().split("\n")[1:] == (tmp_path / "s2.tsv").read_text().split("\n")[1:]
+    # merge: two samples, second with doubled counts and a lower sample ID -> its column comes first
+    hdr = body.split("\n")[:3]
+    rows = [ln for ln in body.split("\n")[3:] if ln]
+    a = tmp_path / "a_tcount.tsv"
+    b = tmp_path / "b_tcount.tsv"
+    h1 = hdr[0].split("\t")
+    assert len(h1) == 7, h1
+    a.write_text("\n".join(["\t".join(h1[:3] + ["sampleA", "2"] + h1[5:]), hdr[1], hdr[2]] + rows) + "\n")
+
+    def doubled(r):
+        f = r.split("\t")
+        for k in (7, 9, 10, 11, 12, 13):
+            f[k] = str(float(f[k]) * 2 if k == 7 else int(f[k]) * 2)
+        return "\t".join(f)
+    b.write_text("\n".join(["\t".join(h1[:3] + ["sampleB", "1"] + h1[5:]), hdr[1], hdr[2]] + [doubled(r) for r in rows]) + "\n")
+    alleyoop.run(["merge", "-o", str(tmp_path / "m.tsv"), str(a), str(b)])
+    m = (tmp_path / "m.tsv").read_text().split("\n")
+    assert m[2] == "#Expression:\tTcReadCount / ReadCount"
+    assert m[3].split("\t")[6:] == ["avgReadsCPM", "avgMultimapper", "avgTcontent", "avgCoverageOnTs", "sampleB", "sampleA"]
+    f0, r0 = m[4].split("\t"), rows[0].split("\t")
+    assert f0[:6] == r0[:6]
+    assert abs(float(f0[9]) - 1.5 * int(r0[9])) < 1e-9
+    want = int(r0[12]) / int(r0[11]) if int(r0[11]) else 0.0
+    assert abs(float(f0[10]) - want) < 1e-12 and abs(float(f0[11]) - want) < 1e-12
+    import pytest
+    with pytest.raises(SystemExit) as e:
+        alleyoop.run(["dedup", "-o", "x", "y.bam"])
+    assert "not provided" in str(e.value)
