@@ -135,7 +135,23 @@ typedef struct sd_batch {
                                `code >= c` on 32 bases at once and the block travels with the tile instead of being fetched
                                byte by byte.  Tile qual offsets are then byte offsets into the column as stored, max_tile_qual
                                the largest block.  Made by sd_qual_to_planes; needs seq_bits == 2; sd_count* only. */
+    const void *spans;      /* optional, DEVICE batches: one sd_tile_span per tile, made by sd_tile_spans for the reference and
+                               annotation the context holds; NULL = none.  With them sd_count stages each tile's reference
+                               window and the annotation entries its reads can overlap together with the tile's columns
+                               (two more bulk copies per tile) instead of one lookup chain per read. */
+    uint32_t spans_epoch;   /* set by sd_tile_spans; descriptors made before a later sd_set_reference / sd_set_utrs are ignored */
 } sd_batch;
+
+/* Stretch of the linear genome (sd_set_reference's bit space) covered by the countable reads of one tile -- mapped, on a
+ * FASTA chromosome, position inside it -- and the run of annotation entries (both strands, sorted by start) that can overlap
+ * it.  A tile with reads all over the genome (unsorted input) is still described; sd_count then falls back to per-read
+ * lookups for it. */
+typedef struct sd_tile_span {
+    uint32_t g_min;         /* first linear position covered */
+    uint32_t g_end;         /* one past the last */
+    uint32_t ent_first;     /* library-internal index of the first candidate entry */
+    uint32_t n_ent_flags;   /* bits 0-15 number of candidate entries, bit 16 descriptor valid */
+} sd_tile_span;
 
 /* Where the per-read mismatch list comes from. */
 #define SD_MISMATCH_CIGAR 0 /* walk the CIGAR, compare SEQ with the reference planes (north star) */
@@ -237,6 +253,11 @@ int sd_bind_outputs(sd_ctx *ctx, int64_t *d_counters, int32_t *d_pos_cov, int32_
  * + per-position scatter, for one device-resident batch.  Asynchronous.
  */
 int sd_count(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params);
+/* Fill d_spans (device, n_tiles * sizeof(sd_tile_span)) for a device-resident batch and attach it (d_batch->spans,
+ * d_batch->spans_epoch).  Call after sd_set_reference and sd_set_utrs; part of building the batch, like its tile table.
+ * A tile whose CIGAR block is empty (tiles[t + 1].cig_off == tiles[t].cig_off) is read as: every record with one CIGAR op
+ * is a single M block of l_seq bases -- plain-match tiles need not carry the column.  Asynchronous. */
+int sd_tile_spans(sd_ctx *ctx, sd_batch *d_batch, void *d_spans);
 /* sd_count that also writes every record's tcCount (after the conversionThreshold rule, saturated at
  * 255; 0 for records that were not counted) to d_read_tc[n_tiles * tile_reads] -- the per-read
  * quantity SlamSeqBamIterator yields (SlamSeqFile.py:386,397); tests and read separation use it. */

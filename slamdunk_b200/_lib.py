@@ -46,7 +46,8 @@ class Batch(ctypes.Structure):
                 ("cigar", ctypes.c_void_p), ("mp", ctypes.c_void_p), ("tiles", ctypes.c_void_p),
                 ("max_lseq", ctypes.c_uint32), ("max_tile_seq", ctypes.c_uint32), ("max_tile_qual", ctypes.c_uint32),
                 ("max_tile_cig", ctypes.c_uint32), ("max_tile_mp", ctypes.c_uint32), ("max_span", ctypes.c_uint32), ("qual_bits", ctypes.c_uint32),
-                ("qual_dict", ctypes.c_uint8 * 16), ("seq_bits", ctypes.c_uint32), ("qual_form", ctypes.c_uint32)]
+                ("qual_dict", ctypes.c_uint8 * 16), ("seq_bits", ctypes.c_uint32), ("qual_form", ctypes.c_uint32),
+                ("spans", ctypes.c_void_p), ("spans_epoch", ctypes.c_uint32)]
 
 
 class Params(ctypes.Structure):
@@ -111,6 +112,7 @@ PROTOTYPES = {
     "sd_utr_layout": (ctypes.c_int, [_VP, _VP, _VP]),
     "sd_bind_outputs": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "sd_count": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params)]),
+    "sd_tile_spans": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), _VP]),
     "sd_count_reads": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params), _VP]),
     "sd_count_host": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params)]),
     "sd_finalize": (ctypes.c_int, [_VP]),
@@ -173,7 +175,7 @@ def load():
     if missing:
         raise RuntimeError("libslamdunk_b200.so is stale, it lacks %s; rebuild with `python -m slamdunk_b200.build`"
                            % ", ".join(missing))
-    assert ctypes.sizeof(ReadRec) == 20 and ctypes.sizeof(Tile) == 32 and ctypes.sizeof(Batch) == 120
+    assert ctypes.sizeof(ReadRec) == 20 and ctypes.sizeof(Tile) == 32 and ctypes.sizeof(Batch) == 136
     if L.sd_abi_version() != SD_ABI_VERSION:
         raise RuntimeError("libslamdunk_b200.so has ABI version %d, these bindings expect %d; rebuild with `python -m slamdunk_b200.build`"
                            % (L.sd_abi_version(), SD_ABI_VERSION))

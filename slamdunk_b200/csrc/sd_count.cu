@@ -17,6 +17,8 @@
 // The path is integer streaming work bound by HBM bandwidth; there is no tensor-core use.
 #include "sd_count_kernel.cuh"
 
+#include <atomic>
+
 // the launcher is instantiated in sd_count_inst_*.cu
 #define SD_EXTERN_W(SB, QB)                                                                  \
     extern template int launch_count<4, SB, QB>(sd_ctx *, CountArgs &, cudaStream_t, bool);  \
@@ -35,7 +37,7 @@ SD_EXTERN_W(2, 4)
 // small kernels: reference planes, finalize scan, Tcontent
 // ---------------------------------------------------------------------------------------
 __global__ void sd_refx_kernel(const uint32_t *lo, const uint32_t *hi, const uint32_t *nm, uint64_t n_words,
-                               uint2 *rx_plus, uint2 *rx_minus) {
+                               uint2 *rx_plus, uint2 *rx_minus, uint4 *rm) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_words + SD_REF_PAD_WORDS) return;
     uint32_t t = 0, a = 0;
@@ -46,13 +48,17 @@ __global__ void sd_refx_kernel(const uint32_t *lo, const uint32_t *hi, const uin
     }
     rx_plus[i] = make_uint2(t, 0u);
     rx_minus[i] = make_uint2(a, 0u);
+    rm[i] = make_uint4(t, 0u, a, 0u);
 }
 
-__global__ void sd_snp_kernel(const uint32_t *tc, const uint32_t *ag, uint64_t n_words, uint2 *rx_plus, uint2 *rx_minus) {
+__global__ void sd_snp_kernel(const uint32_t *tc, const uint32_t *ag, uint64_t n_words, uint2 *rx_plus, uint2 *rx_minus, uint4 *rm) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_words) return;
-    rx_plus[i].y = tc ? tc[i] : 0u;
-    rx_minus[i].y = ag ? ag[i] : 0u;
+    const uint32_t t = tc ? tc[i] : 0u, a = ag ? ag[i] : 0u;
+    rx_plus[i].y = t;
+    rx_minus[i].y = a;
+    rm[i].y = t;
+    rm[i].w = a;
 }
 
 // segment-local inclusive prefix sum of the coverage differences; one warp per segment
@@ -105,6 +111,69 @@ __global__ void sd_tcontent_kernel(const uint2 *rx_plus, const uint2 *rx_minus, 
     if (lane == 0) out[wid] = (long long)cnt;
 }
 
+// Span descriptor of every tile (sd_batch.spans): the stretch of the linear genome its countable reads cover and the
+// run of strand-merged annotation entries that can overlap it.  One warp per tile, one lane per read.
+struct SpanArgs {
+    const sd_read_rec *rec;
+    const uint32_t *cigar;
+    const sd_tile *tiles;
+    uint32_t n_tiles;
+    const uint32_t *chrom_off, *chrom_len;
+    uint32_t n_chrom;
+    const uint4 *ment;
+    const uint32_t *bin_first_m;
+    uint32_t n_ment;
+    uint4 *out;
+};
+
+__global__ void sd_tile_spans_kernel(const SpanArgs A) {
+    const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (tile >= A.n_tiles) return;
+    const sd_read_rec r = A.rec[(size_t)tile * 32u + lane];
+    const uint32_t flags = r.ref_mapq_flag >> 24, ref = r.ref_mapq_flag & 0xFFFFu;
+    const uint32_t lseq = r.lseq_ncig & 0xFFFFu, ncig = r.lseq_ncig >> 16;
+    const unsigned long long c0 = A.tiles[tile].cig_off, c1 = A.tiles[tile + 1].cig_off;
+    const bool nocig = c1 == c0;
+    uint32_t xs = ncig;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xs, d);
+        if (lane >= (uint32_t)d) xs += t;
+    }
+    bool countable = !(flags & (SD_F_PAD | SD_F_UNMAPPED | SD_F_SKIP)) && ref < A.n_chrom && !(nocig && ncig > 1u);
+    uint32_t clen = 0, g = 0xFFFFFFFFu, e = 0u;
+    if (countable) {
+        clen = A.chrom_len[ref];
+        countable = r.pos >= 0 && (uint32_t)r.pos < clen;
+    }
+    if (countable) {
+        uint32_t reflen = 0;
+        if (nocig) reflen = ncig ? lseq : 0u;
+        else {
+            const uint32_t *cg = A.cigar + c0 / 4u + (xs - ncig);
+            for (uint32_t i = 0; i < ncig; i++) {
+                const uint32_t c = cg[i];
+                if ((0x18Du >> (c & 15u)) & 1u) reflen += c >> 4;
+            }
+        }
+        if (reflen == 0) reflen = 1;
+        if ((uint64_t)r.pos + reflen > clen) reflen = clen - (uint32_t)r.pos;
+        g = A.chrom_off[ref] + (uint32_t)r.pos;
+        e = g + reflen;
+    }
+    const uint32_t gmin = __reduce_min_sync(0xFFFFFFFFu, g), gend = __reduce_max_sync(0xFFFFFFFFu, e);
+    uint4 out = make_uint4(0u, 0u, 0u, SD_SPAN_VALID << 16);   // no countable read: nothing to stage
+    if (gend != 0u) {
+        const uint32_t i0 = A.bin_first_m[gmin >> SD_BIN_SHIFT];
+        const uint32_t i = i0 + lane;
+        const bool can = i < A.n_ment && __ldg(&A.ment[2 * (size_t)i]).x < gend;   // sorted by start: a prefix of the lanes
+        const unsigned b = __ballot_sync(0xFFFFFFFFu, can);
+        out = (b == 0xFFFFFFFFu) ? make_uint4(gmin, gend, 0u, 0u)               // more candidates than a stage could hold
+                                 : make_uint4(gmin, gend, i0, (uint32_t)__popc(b) | (SD_SPAN_VALID << 16));
+    }
+    if (lane == 0) A.out[tile] = out;
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -119,6 +188,12 @@ int sd_fail(sd_ctx *ctx, int code, const char *fmt, ...) {
 }
 
 extern "C" int sd_abi_version(void) { return SD_ABI_VERSION; }
+
+// identifies one (reference layout, annotation) state across all contexts of the process: span descriptors are valid for one
+static uint32_t next_epoch() {
+    static std::atomic<uint32_t> epoch(0);
+    return ++epoch;
+}
 
 extern "C" const char *sd_last_error(const sd_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
@@ -156,6 +231,10 @@ static void free_utr_tables(sd_ctx *ctx) {
         ctx->d_seg_start[s] = ctx->d_seg_end[s] = nullptr;
         ctx->d_seg_off[s] = nullptr;
     }
+    cudaFree(ctx->d_ment); cudaFree(ctx->d_bin_first_m);
+    ctx->d_ment = nullptr;
+    ctx->d_bin_first_m = nullptr;
+    ctx->n_ment = 0;
     cudaFree(ctx->d_row_gstart); cudaFree(ctx->d_row_gend); cudaFree(ctx->d_row_strand); cudaFree(ctx->d_row_blen);
     ctx->d_row_gstart = ctx->d_row_gend = ctx->d_row_blen = nullptr;
     ctx->d_row_strand = nullptr;
@@ -168,10 +247,11 @@ extern "C" void sd_destroy(sd_ctx *ctx) {
     cudaFree(ctx->d_track_scratch);
     cudaFree(ctx->d_filter_scratch);
     free_utr_tables(ctx);
-    cudaFree(ctx->refx[0]); cudaFree(ctx->refx[1]);
+    cudaFree(ctx->refx[0]); cudaFree(ctx->refx[1]); cudaFree(ctx->refm);
     cudaFree(ctx->d_chrom_off); cudaFree(ctx->d_chrom_len);
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
     cudaFree(ctx->d_tile_counter);
+    cudaFree(ctx->d_leftover);
     cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_copy[i]); cudaEventDestroy(ctx->ev_done[i]); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -198,8 +278,10 @@ extern "C" int sd_set_reference(sd_ctx *ctx, const uint32_t *d_lo, const uint32_
             return sd_fail(ctx, SD_ERR_ARG, "chromosomes %u and %u need >= 32 pad positions between them", c, c + 1);
     }
     SD_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaFree(ctx->refx[0]); cudaFree(ctx->refx[1]); cudaFree(ctx->d_chrom_off); cudaFree(ctx->d_chrom_len);
+    cudaFree(ctx->refx[0]); cudaFree(ctx->refx[1]); cudaFree(ctx->refm); cudaFree(ctx->d_chrom_off); cudaFree(ctx->d_chrom_len);
     ctx->refx[0] = ctx->refx[1] = nullptr;
+    ctx->refm = nullptr;
+    ctx->ann_epoch = next_epoch();
     ctx->n_words = n_words;
     ctx->n_chrom = n_chrom;
     ctx->chrom_off.assign(h_chrom_off, h_chrom_off + n_chrom);
@@ -207,12 +289,13 @@ extern "C" int sd_set_reference(sd_ctx *ctx, const uint32_t *d_lo, const uint32_
     const uint64_t tot = n_words + SD_REF_PAD_WORDS;
     SD_CUDA(ctx, cudaMalloc(&ctx->refx[0], tot * sizeof(uint2)));
     SD_CUDA(ctx, cudaMalloc(&ctx->refx[1], tot * sizeof(uint2)));
+    SD_CUDA(ctx, cudaMalloc(&ctx->refm, tot * sizeof(uint4)));
     SD_CUDA(ctx, cudaMalloc(&ctx->d_chrom_off, n_chrom * sizeof(uint32_t)));
     SD_CUDA(ctx, cudaMalloc(&ctx->d_chrom_len, n_chrom * sizeof(uint32_t)));
     SD_CUDA(ctx, cudaMemcpyAsync(ctx->d_chrom_off, h_chrom_off, n_chrom * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     SD_CUDA(ctx, cudaMemcpyAsync(ctx->d_chrom_len, h_chrom_len, n_chrom * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     const unsigned blocks = (unsigned)((tot + 255) / 256);
-    sd_refx_kernel<<<blocks, 256, 0, ctx->stream>>>(d_lo, d_hi, d_nmask, n_words, ctx->refx[0], ctx->refx[1]);
+    sd_refx_kernel<<<blocks, 256, 0, ctx->stream>>>(d_lo, d_hi, d_nmask, n_words, ctx->refx[0], ctx->refx[1], ctx->refm);
     ctx->launches++;
     SD_CUDA(ctx, cudaGetLastError());
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -224,7 +307,7 @@ extern "C" int sd_set_snps(sd_ctx *ctx, const uint32_t *d_tc_mask, const uint32_
     if (!ctx->refx[0]) return sd_fail(ctx, SD_ERR_STATE, "sd_set_snps before sd_set_reference");
     SD_CUDA(ctx, cudaSetDevice(ctx->device));
     const unsigned blocks = (unsigned)((ctx->n_words + 255) / 256);
-    sd_snp_kernel<<<blocks, 256, 0, ctx->stream>>>(d_tc_mask, d_ag_mask, ctx->n_words, ctx->refx[0], ctx->refx[1]);
+    sd_snp_kernel<<<blocks, 256, 0, ctx->stream>>>(d_tc_mask, d_ag_mask, ctx->n_words, ctx->refx[0], ctx->refx[1], ctx->refm);
     ctx->launches++;
     SD_CUDA(ctx, cudaGetLastError());
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -274,6 +357,8 @@ extern "C" int sd_set_utrs(sd_ctx *ctx, const uint32_t *h_chrom, const int64_t *
     const uint64_t total_bits = ctx->n_words * 32ull;
     ctx->n_bins = (uint32_t)((total_bits >> SD_BIN_SHIFT) + 2);
     uint64_t pos_total = 0;
+    struct MEnt { uint32_t gs, ge, rowst, seg, ss, se; uint64_t posbase; };
+    std::vector<MEnt> merged;
     for (int s = 0; s < 2; s++) {
         auto &E = ent[s];
         std::stable_sort(E.begin(), E.end(), [](const Ent &x, const Ent &y) { return x.gs < y.gs || (x.gs == y.gs && x.ge < y.ge); });
@@ -300,6 +385,8 @@ extern "C" int sd_set_utrs(sd_ctx *ctx, const uint32_t *h_chrom, const int64_t *
             pos_total += (uint64_t)(send[m] - sstart[m]) + 1ull;
         }
         for (uint32_t i = 0; i < n; i++) ctx->row_pos_off[ur[i]] = soff[useg[i]] + (us[i] - sstart[useg[i]]);
+        for (uint32_t i = 0; i < n; i++)
+            merged.push_back({us[i], ue[i], ur[i] | ((uint32_t)s << 31), useg[i], sstart[useg[i]], send[useg[i]], soff[useg[i]] - sstart[useg[i]]});
         // bin -> first table index that can still overlap a window starting in the bin
         std::vector<uint32_t> bins(ctx->n_bins);
         uint32_t j = 0;
@@ -328,6 +415,32 @@ extern "C" int sd_set_utrs(sd_ctx *ctx, const uint32_t *h_chrom, const int64_t *
     }
     ctx->n_positions = pos_total;
     int rc;
+    {   // strand-merged table for the staged join (same order rule, so each strand's entries keep their relative order)
+        if (n_utr >= 0x80000000u) return sd_fail(ctx, SD_ERR_LIMIT, "too many annotation rows");
+        std::stable_sort(merged.begin(), merged.end(), [](const MEnt &x, const MEnt &y) { return x.gs < y.gs || (x.gs == y.gs && x.ge < y.ge); });
+        const uint32_t n = (uint32_t)merged.size();
+        std::vector<uint4> tab(2 * (size_t)n);
+        std::vector<uint32_t> bins(ctx->n_bins);
+        uint32_t maxend = 0, j = 0;
+        std::vector<uint32_t> pm(n);
+        for (uint32_t i = 0; i < n; i++) {
+            const MEnt &m = merged[i];
+            tab[2 * (size_t)i] = make_uint4(m.gs, m.ge, m.rowst, m.seg);
+            tab[2 * (size_t)i + 1] = make_uint4(m.ss, m.se, (uint32_t)(m.posbase & 0xFFFFFFFFull), (uint32_t)(m.posbase >> 32));
+            maxend = std::max(maxend, m.ge);
+            pm[i] = maxend;
+        }
+        for (uint32_t b = 0; b < ctx->n_bins; b++) {
+            const uint64_t bstart = (uint64_t)b << SD_BIN_SHIFT;
+            while (j < n && (uint64_t)pm[j] <= bstart) j++;
+            bins[b] = j;
+        }
+        ctx->n_ment = n;
+        if ((rc = upload(ctx, &ctx->d_ment, tab))) return rc;
+        if ((rc = upload(ctx, &ctx->d_bin_first_m, bins))) return rc;
+        SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->ann_epoch = next_epoch();
     if ((rc = upload(ctx, &ctx->d_row_gstart, row_gs))) return rc;
     if ((rc = upload(ctx, &ctx->d_row_gend, row_ge))) return rc;
     if ((rc = upload(ctx, &ctx->d_row_strand, row_st))) return rc;
@@ -419,6 +532,15 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
         } else
             for (int k = 0; k < 4; k++) A.q_m[k] = 0u - ((A.q_cmin >> k) & 1u);
     }
+    // span descriptors made for this reference layout and annotation: the kernel stages each tile's reference window and
+    // annotation entries with the tile (otherwise every lane fetches its own from global memory)
+    static int spans_env = -1;
+    if (spans_env < 0) { const char *e = getenv("SD_SPANS"); spans_env = e ? atoi(e) : 1; }
+    A.spans = (b->spans && b->spans_epoch == ctx->ann_epoch && spans_env) ? reinterpret_cast<const uint4 *>(b->spans) : nullptr;
+    A.refm = ctx->refm;
+    A.ment = ctx->d_ment;
+    A.n_ment = ctx->n_ment;
+    A.n_refm = (uint32_t)std::min<uint64_t>(ctx->n_words + SD_REF_PAD_WORDS, 0xFFFFFFFFull);
     for (int s = 0; s < 2; s++) {
         A.refx[s] = ctx->refx[s];
         A.ustart[s] = ctx->d_ustart[s]; A.uend[s] = ctx->d_uend[s]; A.urow[s] = ctx->d_urow[s]; A.useg[s] = ctx->d_useg[s];
@@ -432,9 +554,20 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     A.pos_cov = ctx->pos_cov; A.pos_tc = ctx->pos_tc;
     A.stats = reinterpret_cast<unsigned long long *>(ctx->stats);
     A.read_tc = read_tc;
-    if (!ctx->d_tile_counter) SD_CUDA(ctx, cudaMalloc(&ctx->d_tile_counter, sizeof(unsigned int)));
-    SD_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned int), stream));
+    if (!ctx->d_tile_counter) SD_CUDA(ctx, cudaMalloc(&ctx->d_tile_counter, 4 * sizeof(unsigned int)));
+    SD_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_counter, 0, 4 * sizeof(unsigned int), stream));
     A.tile_counter = ctx->d_tile_counter;
+    if (A.spans) {   // tiles the staged kernel hands on to the plain one
+        if (ctx->leftover_cap < b->n_tiles) {
+            SD_CUDA(ctx, cudaStreamSynchronize(stream));
+            cudaFree(ctx->d_leftover);
+            ctx->d_leftover = nullptr;
+            ctx->leftover_cap = 0;
+            SD_CUDA(ctx, cudaMalloc(&ctx->d_leftover, (size_t)b->n_tiles * sizeof(uint32_t)));
+            ctx->leftover_cap = b->n_tiles;
+        }
+        A.leftover = ctx->d_leftover;
+    }
     A.min_qual = p->min_qual; A.conv_threshold = p->conversion_threshold; A.mismatch_source = p->mismatch_source;
     A.filter_on = p->filter_on; A.filter_mq = p->filter_mq; A.filter_max_nm = p->filter_max_nm;
     {   // filter.py:246 compares the float32 XI tag, promoted to double, with the double threshold; the same predicate in float:
@@ -460,6 +593,11 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     // with 2 % short indels in a 192-base window: 9.6 instead of 15 G reads/s).  The batch says how wide its alignments
     // are (spliced ones aside); without that, 16 bases of slack cover the usual gaps.
     const uint32_t need = b->max_span ? std::max(b->max_lseq, b->max_span) : b->max_lseq + 16u;
+    if (A.spans) {   // room for the staged window (the reads' words, a few more for the spread of their starts, W behind the last) and 8 entries
+        const uint32_t Wn = need <= 128 ? 4 : need <= 192 ? 6 : need <= 256 ? 8 : need <= 320 ? 10 : need <= 384 ? 12 : 16;
+        A.cap_win = align128(16u * (3u * Wn + 4u));
+        A.cap_ent = 256u;
+    }
 #define SD_DISPATCH_W(SB, QB)                                                        \
     do {                                                                             \
         if (need <= 128) return launch_count<4, SB, QB>(ctx, A, stream, timed);      \
@@ -474,6 +612,32 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     if (A.seq2) SD_DISPATCH_W(2, 0);
     SD_DISPATCH_W(4, 0);
 #undef SD_DISPATCH_W
+}
+
+static int tile_spans_on(sd_ctx *ctx, cudaStream_t stream, const sd_batch *b, void *d_spans) {
+    if (b->n_tiles == 0) return SD_OK;
+    SpanArgs S;
+    S.rec = b->rec; S.cigar = b->cigar; S.tiles = b->tiles; S.n_tiles = b->n_tiles;
+    S.chrom_off = ctx->d_chrom_off; S.chrom_len = ctx->d_chrom_len; S.n_chrom = ctx->n_chrom;
+    S.ment = ctx->d_ment; S.bin_first_m = ctx->d_bin_first_m; S.n_ment = ctx->n_ment;
+    S.out = reinterpret_cast<uint4 *>(d_spans);
+    const unsigned blocks = (unsigned)(((uint64_t)b->n_tiles * 32u + 255u) / 256u);
+    sd_tile_spans_kernel<<<blocks, 256, 0, stream>>>(S);
+    ctx->launches++;
+    SD_CUDA(ctx, cudaGetLastError());
+    return SD_OK;
+}
+
+extern "C" int sd_tile_spans(sd_ctx *ctx, sd_batch *d_batch, void *d_spans) {
+    if (!ctx || !d_batch || (d_batch->n_tiles && !d_spans)) return sd_fail(ctx, SD_ERR_ARG, "sd_tile_spans: null argument");
+    if (!ctx->refx[0] || !ctx->d_ment) return sd_fail(ctx, SD_ERR_STATE, "sd_tile_spans before sd_set_reference / sd_set_utrs");
+    if (d_batch->tile_reads != 32) return sd_fail(ctx, SD_ERR_ARG, "tile_reads must be 32");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int rc = tile_spans_on(ctx, ctx->stream, d_batch, d_spans);
+    if (rc) return rc;
+    d_batch->spans = d_spans;
+    d_batch->spans_epoch = ctx->ann_epoch;
+    return SD_OK;
 }
 
 extern "C" int sd_count(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params) {
@@ -524,6 +688,7 @@ extern "C" int sd_count_host(sd_ctx *ctx, const sd_batch *hb, const sd_params *p
         if (coded) b += (T[t1].qual_off - T[t0].qual_off) * qbits / 8;   // the codes as copied, next to the expanded column
         if (to_planes) b += (T[t1].seq_off - T[t0].seq_off) * qbits / 2 + (uint64_t)(t1 - t0 + 1) * sizeof(sd_tile) + 4 * 256;
         if (use_mp) b += T[t1].mp_off - T[t0].mp_off;
+        b += (uint64_t)(t1 - t0) * sizeof(sd_tile_span) + 256;
         return b;
     };
     // chunk boundaries
@@ -618,6 +783,14 @@ extern "C" int sd_count_host(sd_ctx *ctx, const sd_batch *hb, const sd_params *p
             db.qual_bits = qbits;
             db.qual_form = 1;
             db.max_tile_qual = hb->max_tile_seq / 8u * 4u * qbits;
+        }
+        db.spans = nullptr;
+        if (ctx->d_ment) {   // span descriptors of the chunk's tiles (the staged count kernel)
+            void *d_spans = d + o;
+            o = up256(o + (size_t)nt * sizeof(sd_tile_span));
+            if ((rc = tile_spans_on(ctx, ctx->stream, &db, d_spans))) return rc;
+            db.spans = d_spans;
+            db.spans_epoch = ctx->ann_epoch;
         }
         rc = count_on_stream(ctx, &db, params, ctx->stream, nullptr, false);
         if (rc) return rc;

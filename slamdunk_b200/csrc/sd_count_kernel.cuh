@@ -99,8 +99,14 @@ struct CountArgs {
                               // 2 planes: ok = (((p1 & (p0 | m0)) | (p0 & m1)) | m2) & m3;  4 planes: m[b] = bit b of q_cmin
     // shared-memory stage layout (bytes, all multiples of 128)
     uint32_t cap_rec, cap_seq, cap_qual, cap_cig, cap_mp;
+    uint32_t cap_win, cap_ent;   // staged reference window / annotation entries (0: the batch has no span descriptors)
     uint32_t n_stages;
     uint32_t qual_prefetch;   // L2-prefetch each tile's qual bytes when the tile is issued
+    // per-tile span descriptors (sd_batch.spans) and what they index: the strand-merged reference and annotation tables
+    const uint4 *spans;       // {g_min, g_end, first entry, n entries | SD_SPAN_VALID << 16} or null
+    const uint4 *refm;        // per 32 bp {isT, T>C SNPs, isA, A>G SNPs}
+    const uint4 *ment;        // two uint4 per entry, see StageView
+    uint32_t n_ment, n_refm;  // entries in ment, words in refm (bounds of what a descriptor may ask for)
     // reference
     const uint2 *refx[2];
     const uint32_t *chrom_off;
@@ -126,6 +132,14 @@ struct CountArgs {
     unsigned long long *stats;
     uint8_t *read_tc;  // optional per-read tcCount (saturated), may be null
     unsigned int *tile_counter;   // work queue head: warps claim chunks of consecutive tiles
+    // The batch's tiles are counted by two launches when it carries span descriptors: the STAGED kernel takes every tile whose
+    // reference window and annotation entries fit a stage and appends the others (reads spread over the genome) to `leftover`;
+    // the plain kernel then counts that list (tile_list / n_list) with per-read lookups.  Without descriptors the plain kernel
+    // runs over all tiles (tile_list null).
+    uint32_t *leftover;
+    unsigned int *n_leftover;
+    const uint32_t *tile_list;
+    const unsigned int *n_list;
     // parameters
     int min_qual;
     int conv_threshold;
@@ -459,34 +473,16 @@ __device__ __forceinline__ int block_read_index(const Blocks &B, int o) {
 
 // SIMPLE: every read of the tile is one match block without clips (the decoder groups such reads into
 // their own tiles), so the read mask needs no placement and a window position is a read index.
+//
+// The per-read scan is the same whether the tile's reference window and annotation entries were staged in shared
+// memory with the tile (staged_read, the common case for coordinate-sorted input) or are fetched from global memory
+// lane by lane (fast_read, the fallback): read_side() builds the candidate mask, reference_side() applies it.
+
+// @region read_mask
+// --- read-side candidate mask R in window coordinates
 template <int W, bool SIMPLE, int SB, int QB>
-__device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, const Blocks &B, uint32_t mapq,
-                                         bool dense_tile, bool &mp_disagree) {
+__device__ __forceinline__ void read_side(const CountArgs &A, const ReadView &v, const Blocks &B, bool regs, uint32_t (&R)[W]) {
     const int s = v.strand;
-    const uint32_t g = v.g, e = v.g + (uint32_t)v.span;
-    const uint32_t nU = A.n_u[s];
-    const uint4 *ut = A.utab[s];
-    // the interval-join entry point is fetched up front so that its latency overlaps the bit work below
-    uint32_t i = __ldg(&A.bin_first[s][g >> SD_BIN_SHIFT]);
-    // @region window
-    // --- reference window: isX (T or A) and SNP planes, shifted so that bit j = position g + j
-    uint32_t T[W], S[W];
-    {
-        const uint2 *rx = A.refx[s] + (v.g >> 5);
-        const uint32_t sh = v.g & 31u;
-        uint2 x[W + 1];
-#pragma unroll
-        for (int k = 0; k <= W; k++) x[k] = __ldg(rx + k);
-#pragma unroll
-        for (int k = 0; k < W; k++) {
-            T[k] = __funnelshift_r(x[k].x, x[k + 1].x, sh) & prefix_word(k, v.span);
-            S[k] = __funnelshift_r(x[k].y, x[k + 1].y, sh);
-        }
-    }
-    // @region read_mask
-    // --- read-side candidate mask in window coordinates
-    uint32_t R[W];
-    const bool regs = SIMPLE || B.regs_ok;
     if (A.mismatch_source == SD_MISMATCH_MP) {
 #pragma unroll
         for (int k = 0; k < W; k++) R[k] = 0u;
@@ -502,79 +498,87 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
                 }
             }
         }
-    } else {
-        uint32_t sm = 0u - (uint32_t)s;   // all ones on the minus strand
-        asm volatile("" : "+r"(sm));      // keep it a mask operand of the LOP3s (not a predicate with selects)
-        const uint32_t ng = (v.lseq + 31u) >> 5;
-        uint32_t M[W];
+        return;
+    }
+    uint32_t sm = 0u - (uint32_t)s;   // all ones on the minus strand
+    asm volatile("" : "+r"(sm));      // keep it a mask operand of the LOP3s (not a predicate with selects)
+    const uint32_t ng = (v.lseq + 31u) >> 5;
+    uint32_t M[W];
 #pragma unroll
-        for (int k = 0; k < W; k++) {
-            // unconditional load of an existing group (index clamped), masked afterwards: no branch per group
-            const uint32_t kc = ng ? min((uint32_t)k, ng - 1u) : 0u;
-            uint32_t m = row_group_is_base<SB>(v.seq, kc, sm);   // this row's slot of group kc; the tile block is group-major
-            // plane-form qualities, plain CIGAR walk: the quality test is one more mask on the read side, for 32 bases at once
-            if (QB > 0 && A.mismatch_source == SD_MISMATCH_CIGAR)
-                m &= row_group_qual_ok<(QB ? QB : 2), true>(reinterpret_cast<const uint32_t *>(v.qual), kc, A);
-            M[k] = ((uint32_t)k < ng) ? m : 0u;
-        }
-        if (SIMPLE) {
+    for (int k = 0; k < W; k++) {
+        // unconditional load of an existing group (index clamped), masked afterwards: no branch per group
+        const uint32_t kc = ng ? min((uint32_t)k, ng - 1u) : 0u;
+        uint32_t m = row_group_is_base<SB>(v.seq, kc, sm);   // this row's slot of group kc; the tile block is group-major
+        // plane-form qualities, plain CIGAR walk: the quality test is one more mask on the read side, for 32 bases at once
+        if (QB > 0 && A.mismatch_source == SD_MISMATCH_CIGAR)
+            m &= row_group_qual_ok<(QB ? QB : 2), true>(reinterpret_cast<const uint32_t *>(v.qual), kc, A);
+        M[k] = ((uint32_t)k < ng) ? m : 0u;
+    }
+    if (SIMPLE) {
 #pragma unroll
-            for (int k = 0; k < W; k++) R[k] = M[k];
-        } else if (regs) {
-            if (B.n <= 1) {
-                // one block: bits past its end are cleared by T (masked to the span) later on
-                if (B.sha == 0) {
+        for (int k = 0; k < W; k++) R[k] = M[k];
+    } else if (regs) {
+        if (B.n <= 1) {
+            // one block: bits past its end are cleared by T (masked to the span) later on
+            if (B.sha == 0) {
 #pragma unroll
-                    for (int k = 0; k < W; k++) R[k] = M[k];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < W; k++) R[k] = shifted_word<W>(M, k, B.sha) & range_word(k, B.r0a, B.r1a);
-                }
+                for (int k = 0; k < W; k++) R[k] = M[k];
             } else {
 #pragma unroll
-                for (int k = 0; k < W; k++) {
-                    uint32_t r = shifted_word<W>(M, k, B.sha) & range_word(k, B.r0a, B.r1a);
-                    r |= shifted_word<W>(M, k, B.shb) & range_word(k, B.r0b, B.r1b);
-                    if (B.n > 2) r |= shifted_word<W>(M, k, B.shc) & range_word(k, B.r0c, B.r1c);
-                    R[k] = r;
-                }
+                for (int k = 0; k < W; k++) R[k] = shifted_word<W>(M, k, B.sha) & range_word(k, B.r0a, B.r1a);
             }
         } else {
-            // generic placement through a scratch copy of the read mask (dynamically indexed, so it lives in
-            // local memory; only alignments with > 3 match blocks or shifts >= 32 come here)
-            uint32_t scratch[W + 1];
 #pragma unroll
             for (int k = 0; k < W; k++) {
-                R[k] = 0u;
-                scratch[k] = M[k];
+                uint32_t r = shifted_word<W>(M, k, B.sha) & range_word(k, B.r0a, B.r1a);
+                r |= shifted_word<W>(M, k, B.shb) & range_word(k, B.r0b, B.r1b);
+                if (B.n > 2) r |= shifted_word<W>(M, k, B.shc) & range_word(k, B.r0c, B.r1c);
+                R[k] = r;
             }
-            scratch[W] = 0u;
-            int q = 0, r = 0;
-            for (uint32_t i = 0; i < v.ncig; i++) {
-                const uint32_t c = v.cig[i], op = c & 15u;
-                const int len = (int)(c >> 4);
-                if (cigar_is_match(op)) {
+        }
+    } else {
+        // generic placement through a scratch copy of the read mask (dynamically indexed, so it lives in
+        // local memory; only alignments with > 3 match blocks or shifts >= 32 come here)
+        uint32_t scratch[W + 1];
 #pragma unroll
-                    for (int k = 0; k < W; k++) {
-                        const uint32_t m = range_word(k, r, r + len);
-                        if (m) {
-                            const int b = q - r + 32 * k;  // read-mask bit aligned to window bit 32k
-                            const int idx = b >> 5;        // arithmetic shift: floor
-                            const uint32_t lo = (idx >= 0 && idx <= W) ? scratch[idx] : 0u;
-                            const uint32_t hi = (idx + 1 >= 0 && idx + 1 <= W) ? scratch[idx + 1] : 0u;
-                            R[k] |= __funnelshift_r(lo, hi, (uint32_t)(b & 31)) & m;
-                        }
+        for (int k = 0; k < W; k++) {
+            R[k] = 0u;
+            scratch[k] = M[k];
+        }
+        scratch[W] = 0u;
+        int q = 0, r = 0;
+        for (uint32_t i = 0; i < v.ncig; i++) {
+            const uint32_t c = v.cig[i], op = c & 15u;
+            const int len = (int)(c >> 4);
+            if (cigar_is_match(op)) {
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    const uint32_t m = range_word(k, r, r + len);
+                    if (m) {
+                        const int b = q - r + 32 * k;  // read-mask bit aligned to window bit 32k
+                        const int idx = b >> 5;        // arithmetic shift: floor
+                        const uint32_t lo = (idx >= 0 && idx <= W) ? scratch[idx] : 0u;
+                        const uint32_t hi = (idx + 1 >= 0 && idx + 1 <= W) ? scratch[idx + 1] : 0u;
+                        R[k] |= __funnelshift_r(lo, hi, (uint32_t)(b & 31)) & m;
                     }
-                    q += len;
-                    r += len;
-                } else if (op == 1 || op == 4) {
-                    q += len;
-                } else if (op == 2 || op == 3) {
-                    r += len;
                 }
+                q += len;
+                r += len;
+            } else if (op == 1 || op == 4) {
+                q += len;
+            } else if (op == 2 || op == 3) {
+                r += len;
             }
         }
     }
+}
+
+// --- R against the reference planes T (is T / A, masked to the span) and S (SNPs): MP cross-check, candidates H
+// (quality-tested, threshold applied), the read's tcCount and its T coverage.
+template <int W, bool SIMPLE, int SB, int QB>
+__device__ __forceinline__ int reference_side(const CountArgs &A, const ReadView &v, const Blocks &B, bool regs, const uint32_t (&R)[W],
+                                              const uint32_t (&T)[W], const uint32_t (&S)[W], uint32_t (&H)[W], uint32_t &pop_t,
+                                              bool &mp_disagree) {
     // @region verify
     // --- cross-check against NextGenMap's MP list (before quality / SNP masking)
     if (A.mismatch_source == SD_MISMATCH_VERIFY && v.has_mp && v.mp != nullptr) {
@@ -598,11 +602,8 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
         for (int k = 0; k < W; k++) bad |= (D[k] != 0u);
         mp_disagree = bad;
     }
-    uint4 u = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);   // first table entry {start, end, row, seg}, in flight during the quality test
-    if (i < nU) u = __ldg(&ut[i]);
     // @region candidates_qual
     // --- candidates: reference is T (A), read is C (G), not a SNP
-    uint32_t H[W];
     int tc = 0;
     if (A.mismatch_source == SD_MISMATCH_MP) {
         // the reference counts tcCount from the MP entry alone (SlamSeqFile.py:343); the FASTA base is
@@ -668,98 +669,209 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #pragma unroll
         for (int k = 0; k < W; k++) H[k] = 0u;
     }
-    uint32_t pop_t = 0;
+    pop_t = 0;
 #pragma unroll
     for (int k = 0; k < W; k++) pop_t += __popc(T[k]);
+    return tc;
+}
+
+// @region scatter
+// Per-position outputs of one (read, merged segment) incidence: the coverage difference (+1 at the first covered position,
+// -1 after the last) and one add per surviving conversion.  [ss, se) is the segment, posbase = its offset in the
+// per-position arrays minus ss, so that position p lives at index posbase + p.
+template <int W>
+__device__ __forceinline__ void scatter_segment(const CountArgs &A, const uint32_t (&H)[W], int tc, uint32_t g, uint32_t e,
+                                                uint32_t ss, uint32_t se, unsigned long long posbase, bool dense_tile) {
+    const uint32_t pa = ss > g ? ss : g, pb = se < e ? se : e;
+    const unsigned long long ia = posbase + pa, ib = posbase + pb;
+    SD_CHECK(pb >= pa && ib < A.n_positions);
+    if (dense_tile) {   // the tile's reads start (and end) at a handful of positions: lanes with the same address elect one to add the count
+        const unsigned act = __activemask();
+        const unsigned ga = __match_any_sync(act, ia), gb = __match_any_sync(act, ib);   // lanes may sit in different segments: match the full index
+        if (lane_id() == (uint32_t)__ffs((int)ga) - 1u) atomicAdd(&A.pos_cov[ia], (int)__popc(ga));
+        if (lane_id() == (uint32_t)__ffs((int)gb) - 1u) atomicAdd(&A.pos_cov[ib], -(int)__popc(gb));
+    } else {
+        atomicAdd(&A.pos_cov[ia], 1);
+        atomicAdd(&A.pos_cov[ib], -1);
+    }
+    if (tc > 0) {
+        int *tcbase = A.pos_tc + (long long)(posbase + g);   // may point before the segment; only in-range bits are used
+        const bool whole = (pa == g && pb == e);
+        asm volatile("" : "+l"(tcbase));   // keep it a pointer: each scatter address is then one IMAD.WIDE
+        if (whole) {
+            uint32_t more = 0u;
+#pragma unroll
+            for (int k = 0; k < W; k++) {   // first conversion of every word without a loop
+                const uint32_t h = H[k];
+                if (h) {
+                    SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
+                    atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                }
+                more |= h & (h - 1u);
+            }
+            if (more) {
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    uint32_t h = H[k] & (H[k] - 1u);
+                    while (h) {
+                        SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
+                        atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                        h &= h - 1u;
+                    }
+                }
+            }
+        } else {   // the segment holds only part of the read (rare): masked, plain loops
+            for (int k = 0; k < W; k++) {
+                uint32_t h = H[k] & prefix_word(k, (int)(pb - g)) & ~prefix_word(k, (int)(pa - g));
+                while (h) {
+                    SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
+                    atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                    h &= h - 1u;
+                }
+            }
+        }
+    }
+}
+
+// T coverage and conversions of the read inside one UTR [us, ue)
+template <int W>
+__device__ __forceinline__ void utr_part(const CountArgs &A, const uint32_t (&T)[W], const uint32_t (&H)[W], uint32_t g, uint32_t e, int span,
+                                         uint32_t us, uint32_t ue, uint32_t pop_t, int tc, uint32_t &cov_t, uint32_t &conv) {
+    cov_t = pop_t;
+    conv = (uint32_t)tc;
+    if (us > g || ue < e) {  // the UTR covers only part of the read
+        const int lo = us > g ? (int)(us - g) : 0;
+        const int hi = ue < e ? (int)(ue - g) : span;
+        cov_t = 0;
+        conv = 0;
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            const uint32_t m = prefix_word(k, hi) & ~prefix_word(k, lo);
+            cov_t += __popc(T[k] & m);
+            conv += __popc(H[k] & m);
+        }
+    } else if (A.mismatch_source == SD_MISMATCH_MP) {
+        conv = 0;
+#pragma unroll
+        for (int k = 0; k < W; k++) conv += __popc(H[k]);
+    }
+}
+
+// Fallback: reference window and annotation entries come from global memory, lane by lane (tiles without a span
+// descriptor, or whose reads are spread over more of the genome than a stage holds: unsorted input).
+template <int W, bool SIMPLE, int SB, int QB>
+__device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, const Blocks &B, uint32_t mapq,
+                                         bool dense_tile, bool &mp_disagree) {
+    const int s = v.strand;
+    const uint32_t g = v.g, e = v.g + (uint32_t)v.span;
+    const uint32_t nU = A.n_u[s];
+    const uint4 *ut = A.utab[s];
+    // the interval-join entry point is fetched up front so that its latency overlaps the bit work below
+    uint32_t i = __ldg(&A.bin_first[s][g >> SD_BIN_SHIFT]);
+    // @region window
+    // --- reference window: isX (T or A) and SNP planes, shifted so that bit j = position g + j
+    uint32_t T[W], S[W];
+    {
+        const uint2 *rx = A.refx[s] + (v.g >> 5);
+        const uint32_t sh = v.g & 31u;
+        uint2 x[W + 1];
+#pragma unroll
+        for (int k = 0; k <= W; k++) x[k] = __ldg(rx + k);
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            T[k] = __funnelshift_r(x[k].x, x[k + 1].x, sh) & prefix_word(k, v.span);
+            S[k] = __funnelshift_r(x[k].y, x[k + 1].y, sh);
+        }
+    }
+    uint32_t R[W], H[W], pop_t;
+    const bool regs = SIMPLE || B.regs_ok;
+    read_side<W, SIMPLE, SB, QB>(A, v, B, regs, R);
+    uint4 u = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);   // first table entry {start, end, row, seg}, in flight during the quality test
+    if (i < nU) u = __ldg(&ut[i]);
+    int tc = reference_side<W, SIMPLE, SB, QB>(A, v, B, regs, R, T, S, H, pop_t, mp_disagree);
     // @region utr_join
     // --- interval join + per-UTR reduction + per-position scatter
     uint32_t last_seg = 0xFFFFFFFFu;
     while (i < nU) {
         if (u.x >= e) break;
         if (u.y > g) {
-            uint32_t cov_t = pop_t, conv = (uint32_t)tc;
-            if (u.x > g || u.y < e) {  // the UTR covers only part of the read
-                const int lo = u.x > g ? (int)(u.x - g) : 0;
-                const int hi = u.y < e ? (int)(u.y - g) : v.span;
-                cov_t = 0;
-                conv = 0;
-#pragma unroll
-                for (int k = 0; k < W; k++) {
-                    const uint32_t m = prefix_word(k, hi) & ~prefix_word(k, lo);
-                    cov_t += __popc(T[k] & m);
-                    conv += __popc(H[k] & m);
-                }
-            } else if (A.mismatch_source == SD_MISMATCH_MP) {
-                conv = 0;
-#pragma unroll
-                for (int k = 0; k < W; k++) conv += __popc(H[k]);
-            }
+            uint32_t cov_t, conv;
+            utr_part<W>(A, T, H, g, e, v.span, u.x, u.y, pop_t, tc, cov_t, conv);
             SD_CHECK(u.z < A.n_utr);
             utr_accumulate(A.counters, u.z, tc > 0 ? 1u : 0u, mapq == 0 ? 1u : 0u, cov_t, conv);
             if (u.w != last_seg) {
                 last_seg = u.w;
                 const uint4 sg = __ldg(&A.stab[s][u.w]);   // {start, end, off_lo, off_hi}
-                const uint32_t ss = sg.x, se = sg.y;
-                const uint64_t off = (uint64_t)sg.z | ((uint64_t)sg.w << 32);
-                const uint32_t pa = ss > g ? ss : g, pb = se < e ? se : e;
-                // coverage difference: +1 at the first covered position, -1 after the last
-                if (dense_tile) {   // the tile's reads start (and end) at a handful of positions: lanes with the same address elect one to add the count
-                    const unsigned act = __activemask();
-                    const unsigned long long ia = off + (pa - ss), ib = off + (pb - ss);   // lanes may sit in different segments: match the full index
-                    SD_CHECK(ib >= ia && ib < A.n_positions);
-                    const unsigned ga = __match_any_sync(act, ia), gb = __match_any_sync(act, ib);
-                    if (lane_id() == (uint32_t)__ffs((int)ga) - 1u) atomicAdd(&A.pos_cov[ia], (int)__popc(ga));
-                    if (lane_id() == (uint32_t)__ffs((int)gb) - 1u) atomicAdd(&A.pos_cov[ib], -(int)__popc(gb));
-                } else {
-                    SD_CHECK(pb >= pa && off + (pb - ss) < A.n_positions);
-                    atomicAdd(&A.pos_cov[off + (pa - ss)], 1);
-                    atomicAdd(&A.pos_cov[off + (pb - ss)], -1);
-                }
-                if (tc > 0) {
-                    int *tcbase = A.pos_tc + ((long long)off + ((long long)g - (long long)ss));   // may point before the segment; only in-range bits are used
-                    const bool whole = (pa == g && pb == e);
-                    asm volatile("" : "+l"(tcbase));   // keep it a pointer: each scatter address is then one IMAD.WIDE
-                    if (whole) {
-                        uint32_t more = 0u;
-#pragma unroll
-                        for (int k = 0; k < W; k++) {   // first conversion of every word without a loop
-                            const uint32_t h = H[k];
-                            if (h) {
-                                SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
-                                atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
-                            }
-                            more |= h & (h - 1u);
-                        }
-                        if (more) {
-#pragma unroll
-                            for (int k = 0; k < W; k++) {
-                                uint32_t h = H[k] & (H[k] - 1u);
-                                while (h) {
-                                    {
-                                SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
-                                atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
-                            }
-                                    h &= h - 1u;
-                                }
-                            }
-                        }
-                    } else {   // the segment holds only part of the read (rare): masked, plain loops
-                        for (int k = 0; k < W; k++) {
-                            uint32_t h = H[k] & prefix_word(k, (int)(pb - g)) & ~prefix_word(k, (int)(pa - g));
-                            while (h) {
-                                {
-                                SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
-                                atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
-                            }
-                                h &= h - 1u;
-                            }
-                        }
-                    }
-                }
+                const unsigned long long off = (unsigned long long)sg.z | ((unsigned long long)sg.w << 32);
+                scatter_segment<W>(A, H, tc, g, e, sg.x, sg.y, off - sg.x, dense_tile);
             }
         }
         i++;
         if (i < nU) u = __ldg(&ut[i]);
+    }
+    return tc;
+}
+
+// What a stage holds besides the tile's columns (see the kernel): the reference window of the tile's reads, both strands
+// side by side, and the annotation entries that can overlap them.
+struct StageView {
+    const uint4 *win;     // word w0 + i: {isT, T>C SNPs, isA, A>G SNPs} of linear positions 32 (w0 + i) ..
+    const uint4 *ent;     // entry j: ent[2j] = {start, end, row | strand << 31, segment}, ent[2j + 1] = {segment start, end, posbase lo, hi}
+    uint32_t w0, n_ent;
+};
+
+// Staged tile: EVERY lane of the warp comes here (live = this lane has a read to count), so the loop over the tile's
+// annotation entries is warp-uniform and a UTR's counters are one set of warp votes / reductions and at most five atomics.
+template <int W, bool SIMPLE, int SB, int QB>
+__device__ __forceinline__ int staged_read(const CountArgs &A, const ReadView &v, const Blocks &B, uint32_t mapq, bool dense_tile,
+                                           bool live, const StageView &sv, bool &mp_disagree) {
+    const int s = v.strand;
+    const uint32_t g = v.g, e = v.g + (uint32_t)v.span;
+    // @region window
+    uint32_t T[W], S[W];
+    {
+        const uint32_t d = live ? (v.g >> 5) - sv.w0 : 0u;
+        const uint2 *wp = reinterpret_cast<const uint2 *>(sv.win + d) + s;   // this strand's half of each 16-byte word
+        const uint32_t sh = v.g & 31u;
+        uint2 x[W + 1];
+#pragma unroll
+        for (int k = 0; k <= W; k++) x[k] = wp[2 * k];
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            T[k] = __funnelshift_r(x[k].x, x[k + 1].x, sh) & prefix_word(k, v.span);
+            S[k] = __funnelshift_r(x[k].y, x[k + 1].y, sh);
+        }
+    }
+    uint32_t R[W], H[W], pop_t;
+    const bool regs = SIMPLE || B.regs_ok;
+    read_side<W, SIMPLE, SB, QB>(A, v, B, regs, R);
+    int tc = reference_side<W, SIMPLE, SB, QB>(A, v, B, regs, R, T, S, H, pop_t, mp_disagree);
+    // @region utr_join
+    uint32_t last_seg = 0xFFFFFFFFu;
+    for (uint32_t j = 0; j < sv.n_ent; j++) {   // warp-uniform trip count
+        const uint4 u = sv.ent[2 * j];          // broadcast
+        const bool hit = live && (u.z >> 31) == (uint32_t)s && u.x < e && u.y > g;
+        const unsigned hm = __ballot_sync(0xFFFFFFFFu, hit);
+        if (hm == 0u) continue;
+        uint32_t cov_t = 0u, conv = 0u;
+        if (hit) utr_part<W>(A, T, H, g, e, v.span, u.x, u.y, pop_t, tc, cov_t, conv);
+        const unsigned b_tc = __ballot_sync(0xFFFFFFFFu, hit && tc > 0), b_mm = __ballot_sync(0xFFFFFFFFu, hit && mapq == 0u);
+        const uint32_t s_cov = __reduce_add_sync(0xFFFFFFFFu, cov_t), s_conv = __reduce_add_sync(0xFFFFFFFFu, conv);
+        if (lane_id() == 0u) {
+            const uint32_t row = u.z & 0x7FFFFFFFu;
+            SD_CHECK(row < A.n_utr);
+            unsigned long long *c = A.counters + (size_t)row * SD_NCOUNTER;
+            atomicAdd(c + SD_C_READS, (unsigned long long)__popc(hm));
+            if (b_tc) atomicAdd(c + SD_C_TCREADS, (unsigned long long)__popc(b_tc));
+            if (b_mm) atomicAdd(c + SD_C_MULTIMAP, (unsigned long long)__popc(b_mm));
+            if (s_cov) atomicAdd(c + SD_C_COV_ON_T, (unsigned long long)s_cov);
+            if (s_conv) atomicAdd(c + SD_C_CONV_ON_T, (unsigned long long)s_conv);
+        }
+        if (hit && u.w != last_seg) {
+            last_seg = u.w;
+            const uint4 sg = sv.ent[2 * j + 1];
+            scatter_segment<W>(A, H, tc, g, e, sg.x, sg.y, (unsigned long long)sg.z | ((unsigned long long)sg.w << 32), dense_tile);
+        }
     }
     return tc;
 }
@@ -791,15 +903,17 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 #ifndef SD_CTA_THREADS
 #define SD_CTA_THREADS 256
 #endif
+#define SD_WARP_TRAILER 384u   // per-warp bookkeeping behind the stages
+#define SD_SPAN_VALID 1u       // sd_tile_span flag: g_min / g_end / entries describe every countable read of the tile
 #ifndef SD_MIN_CTAS
 #define SD_MIN_CTAS(W) ((W) <= 6 ? 4 : ((W) <= 10 ? 3 : 2))   // resident 256-thread CTAs per SM the register budget is tuned for
 #endif
 
-template <int W, int SB, int QB>
+template <int W, int SB, int QB, bool STAGED>
 __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kernel(const __grid_constant__ CountArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual;
-    const uint32_t warp_bytes = A.n_stages * stage_bytes + 256u;   // stages | barriers + tile qual offsets | per-lane copy descriptors
+    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual + A.cap_win + A.cap_ent;
+    const uint32_t warp_bytes = A.n_stages * stage_bytes + SD_WARP_TRAILER;   // stages | barriers + tile qual offsets | per-lane copy descriptors | span info
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t nwarp = blockDim.x >> 5;
     uint32_t *s_stats = reinterpret_cast<uint32_t *>(smem);                 // [SD_SMEM_STATS], first 128 bytes
@@ -820,54 +934,85 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
     // windows and table rows in L1.
     uint32_t *s_tile = reinterpret_cast<uint32_t *>(mine + (size_t)A.n_stages * stage_bytes + 96u);   // [n_stages] tile held by each stage
     uint32_t claim_next = 0, claim_end = 0;   // lane 0 only
+    const uint32_t n_queue = (!STAGED && A.tile_list) ? *A.n_list : A.n_tiles;
     auto claim = [&]() -> uint32_t {          // next tile for this warp, or 0xFFFFFFFF when the queue is empty
         if (claim_next == claim_end) {
             claim_next = atomicAdd(A.tile_counter, (unsigned int)SD_CLAIM);
             claim_end = claim_next + SD_CLAIM;
         }
         const uint32_t t = claim_next++;
-        return t < A.n_tiles ? t : 0xFFFFFFFFu;
+        if (!STAGED && A.tile_list) return t < n_queue ? A.tile_list[t] : 0xFFFFFFFFu;
+        return t < n_queue ? t : 0xFFFFFFFFu;
     };
     // @region tma_issue
     // A tile is one bulk copy per column.  Lanes 0..4 issue them side by side -- lane c owns column c (records, SEQ, CIGAR,
     // MP, quality planes) -- so the address arithmetic runs once for all columns instead of once per column on lane 0, which
     // the other lanes wait for.  The per-lane descriptors live in the warp's shared-memory region (one LDS.128 per tile
     // instead of five registers per thread).
-    uint4 *s_col = reinterpret_cast<uint4 *>(mine + (size_t)A.n_stages * stage_bytes + 128u);   // [5] {src lo, src hi, stage offset, field | travels << 8}
-    if (lane < 5u) {
+    uint4 *s_col = reinterpret_cast<uint4 *>(mine + (size_t)A.n_stages * stage_bytes + 128u);   // [7] {src lo, src hi, stage offset, field | travels << 8}
+    uint32_t *s_nocig = reinterpret_cast<uint32_t *>(mine + (size_t)A.n_stages * stage_bytes + 112u);   // [n_stages] the tile has no CIGAR block
+    uint4 *s_info = reinterpret_cast<uint4 *>(mine + (size_t)A.n_stages * stage_bytes + 256u);   // [n_stages] {g_min, g_end, n entries, staged}
+    if (lane < 7u) {
         const unsigned char *src = reinterpret_cast<const unsigned char *>(A.rec);
         uint32_t dst = 0u, fld = 0u, col = 1u;   // col: does this lane's column travel with the tile at all
         if (lane == 1) { src = reinterpret_cast<const unsigned char *>(A.seq); dst = A.cap_rec; fld = 0u; }
         if (lane == 2) { src = reinterpret_cast<const unsigned char *>(A.cigar); dst = A.cap_rec + A.cap_seq; fld = 2u; }
         if (lane == 3) { src = reinterpret_cast<const unsigned char *>(A.mp); dst = A.cap_rec + A.cap_seq + A.cap_cig; fld = 3u; col = A.mp != nullptr; }
         if (lane == 4) { src = A.qual; dst = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp; fld = 1u; col = QB > 0; }
+        if (lane == 5) { src = reinterpret_cast<const unsigned char *>(A.refm); dst = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual; col = A.spans != nullptr; }
+        if (lane == 6) { src = reinterpret_cast<const unsigned char *>(A.ment); dst = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual + A.cap_win; col = A.spans != nullptr; }
         const unsigned long long a = reinterpret_cast<unsigned long long>(src);
         s_col[lane] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), dst, fld | (col << 8));
     }
     __syncwarp();
-    auto issue = [&](uint64_t tile, uint32_t stage) {   // lanes 0..4 together
+    auto issue = [&](uint64_t tile, uint32_t stage) {   // lanes 0..6 together
         unsigned char *base = stages + (size_t)stage * stage_bytes;
         const uint4 cd = s_col[lane];
         const unsigned char *my_src = reinterpret_cast<const unsigned char *>((unsigned long long)cd.x | ((unsigned long long)cd.y << 32));
         const uint32_t my_dst = cd.z, my_fld = cd.w & 0xFFu;
         const bool my_col = (cd.w >> 8) != 0u;
-        const unsigned long long *tp = reinterpret_cast<const unsigned long long *>(A.tiles + tile);
-        unsigned long long off0 = tp[my_fld], off1 = tp[4u + my_fld];
-        if (lane == 0) {
-            off0 = tile * (SD_TILE_READS * (unsigned long long)sizeof(sd_read_rec));
-            off1 = off0 + SD_TILE_READS * (unsigned long long)sizeof(sd_read_rec);
-        }
-        if (lane == 4) {
-            s_qoff[stage] = off0;
-            if (QB == 0 && A.qual_prefetch) {   // byte form: pull the tile's base qualities into L2 ahead of use
-                const uint32_t b_q = (uint32_t)(off1 - off0) & ~15u;
-                if (b_q) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.qual + off0), "r"(b_q) : "memory");
+        unsigned long long off0, off1;
+        if (lane < 5u) {
+            const unsigned long long *tp = reinterpret_cast<const unsigned long long *>(A.tiles + tile);
+            off0 = tp[my_fld];
+            off1 = tp[4u + my_fld];
+            if (lane == 0) {
+                off0 = tile * (SD_TILE_READS * (unsigned long long)sizeof(sd_read_rec));
+                off1 = off0 + SD_TILE_READS * (unsigned long long)sizeof(sd_read_rec);
             }
+            if (lane == 2) s_nocig[stage] = (off1 == off0) ? 1u : 0u;
+            if (lane == 4) {
+                s_qoff[stage] = off0;
+                if (QB == 0 && A.qual_prefetch) {   // byte form: pull the tile's base qualities into L2 ahead of use
+                    const uint32_t b_q = (uint32_t)(off1 - off0) & ~15u;
+                    if (b_q) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.qual + off0), "r"(b_q) : "memory");
+                }
+            }
+        } else {
+            // the tile's reference window (both strands side by side) and the annotation entries that can overlap its reads,
+            // located by the span descriptor the batch carries for it: two more bulk copies, no dependent lookup
+            off0 = off1 = 0ull;
+            if (my_col) {
+                const uint4 sp = __ldg(A.spans + tile);
+                const uint32_t w0 = sp.x >> 5, n_ent = sp.w & 0xFFFFu;
+                // words w0 .. word of (g_end - 1), plus the W words a read starting there still loads
+                const uint32_t nw = sp.y > sp.x ? ((sp.y - 1u) >> 5) - w0 + 1u + (uint32_t)W : 0u;
+                const bool ok = ((sp.w >> 16) & SD_SPAN_VALID) && nw * 16u <= A.cap_win && n_ent * 32u <= A.cap_ent &&
+                                (unsigned long long)w0 + nw <= A.n_refm && (unsigned long long)sp.z + n_ent <= A.n_ment;
+                if (lane == 5) {
+                    s_info[stage] = make_uint4(sp.x, sp.y, n_ent, ok ? 1u : 0u);
+                    off0 = (unsigned long long)w0 * 16ull;
+                    off1 = off0 + (ok ? nw * 16u : 0u);
+                } else {
+                    off0 = (unsigned long long)sp.z * 32ull;
+                    off1 = off0 + (ok ? n_ent * 32u : 0u);
+                }
+            } else if (lane == 5) s_info[stage] = make_uint4(0u, 0u, 0u, 0u);
         }
         const uint32_t bytes = my_col ? (uint32_t)(off1 - off0) : 0u;
-        const uint32_t total = __reduce_add_sync(0x1Fu, bytes);
+        const uint32_t total = __reduce_add_sync(0x7Fu, bytes);
         if (lane == 0) mbar_arrive_expect_tx(&full[stage], total);
-        __syncwarp(0x1Fu);
+        __syncwarp(0x7Fu);
         if (bytes) bulk_g2s(base + my_dst, my_src + off0, bytes, &full[stage]);
     };
 
@@ -878,7 +1023,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
             s_tile[s] = t;
         }
         t = __shfl_sync(0xFFFFFFFFu, t, 0);
-        if (lane < 5u && t != 0xFFFFFFFFu) issue(t, s);
+        if (lane < 7u && t != 0xFFFFFFFFu) issue(t, s);
     }
     __syncwarp();
 
@@ -889,6 +1034,12 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
         const uint64_t tile = s_tile[stage];
         if (tile == 0xFFFFFFFFull) break;   // the queue ran dry (claims are monotonic: later stages are empty too)
         mbar_wait(&full[stage], phase);
+        const uint4 info = STAGED ? s_info[stage] : make_uint4(0u, 0u, 0u, 0u);   // {g_min, g_end, n entries, staged}
+        if (STAGED && info.w == 0u) {
+            // The tile's reads are spread over more of the genome than a stage holds (unsorted input, a tile that crosses
+            // chromosomes): leave it to the plain kernel that follows this launch.
+            if (lane == 0) A.leftover[atomicAdd(A.n_leftover, 1u)] = (uint32_t)tile;
+        } else {
         const unsigned char *base = stages + (size_t)stage * stage_bytes;
         const uint32_t *rw = reinterpret_cast<const uint32_t *>(base) + 5u * lane;
         const int32_t pos = (int32_t)rw[0];
@@ -930,103 +1081,168 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
 
         // @region filter
         const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu, ref = rmf & 0xFFFFu;
-        bool go = !(flags & SD_F_PAD);
-        // Two forms of the same filter step, chosen per window size by measurement (the kernel is bound by instruction issue,
-        // and which form schedules better differs: votes at W = 4, 1.604 vs 1.671 ms at 100 bp; per-read atomics from W = 6
-        // on, 1.83 vs 2.01 ms at 150 bp).
-        constexpr bool VOTE_COUNTERS = (W <= 4);
-        if (!VOTE_COUNTERS && go && A.filter_on) {
-            const bool primary = !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
-            const bool unmapped = (flags & SD_F_UNMAPPED) != 0;
-            if (primary) atomicAdd(&s_stats[unmapped ? SD_S_UNMAPPED : SD_S_MAPPED], 1u);
-            if (unmapped) go = false;
-            else if ((int)mapq < A.filter_mq) { atomicAdd(&s_stats[SD_S_MQFILTERED], 1u); go = false; }
-            else if (xi < A.filter_min_identity) { atomicAdd(&s_stats[SD_S_IDFILTERED], 1u); go = false; }
-            else if (A.filter_max_nm > -1 && (int)nm > A.filter_max_nm) { atomicAdd(&s_stats[SD_S_NMFILTERED], 1u); go = false; }
-            else if (primary) atomicAdd(&s_stats[SD_S_FILTERED], 1u);
-        }
-        if (VOTE_COUNTERS && A.filter_on) {
-            // filter.py:235-256 as predicates; the run counters are warp totals (one vote each, added by lane 0) instead of
-            // one shared-memory atomic per read and counter
-            const bool primary = go && !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
-            const bool mapped = go && !(flags & SD_F_UNMAPPED);
-            const bool f_mq = mapped && (int)mapq < A.filter_mq;
-            const bool f_id = mapped && !f_mq && xi < A.filter_min_identity;
-            const bool f_nm = mapped && !f_mq && !f_id && A.filter_max_nm > -1 && (int)nm > A.filter_max_nm;
-            go = mapped && !f_mq && !f_id && !f_nm;
-            const uint32_t b_map = __ballot_sync(0xFFFFFFFFu, primary && mapped), b_unm = __ballot_sync(0xFFFFFFFFu, primary && !mapped);
-            const uint32_t b_mq = __ballot_sync(0xFFFFFFFFu, f_mq), b_id = __ballot_sync(0xFFFFFFFFu, f_id);
-            const uint32_t b_nm = __ballot_sync(0xFFFFFFFFu, f_nm), b_ok = __ballot_sync(0xFFFFFFFFu, go && primary);
-            if (lane == 0) {   // one conflict-free shared atomic per non-zero counter and tile
-                if (b_map) atomicAdd(&s_stats[SD_S_MAPPED], (uint32_t)__popc(b_map));
-                if (b_ok) atomicAdd(&s_stats[SD_S_FILTERED], (uint32_t)__popc(b_ok));
-                if (b_unm | b_mq | b_id | b_nm) {
-                    if (b_unm) atomicAdd(&s_stats[SD_S_UNMAPPED], (uint32_t)__popc(b_unm));
-                    if (b_mq) atomicAdd(&s_stats[SD_S_MQFILTERED], (uint32_t)__popc(b_mq));
-                    if (b_id) atomicAdd(&s_stats[SD_S_IDFILTERED], (uint32_t)__popc(b_id));
-                    if (b_nm) atomicAdd(&s_stats[SD_S_NMFILTERED], (uint32_t)__popc(b_nm));
+        // filter.py:235-256 on a record that is not tile padding -> does it go on to be counted; the run counters are added here
+        auto filter_step = [&](bool go) -> bool {
+            // Two forms of the same step, chosen per window size by measurement (the kernel is bound by instruction issue, and
+            // which form schedules better differs: votes at W = 4, 1.604 vs 1.671 ms at 100 bp; per-read atomics from W = 6
+            // on, 1.83 vs 2.01 ms at 150 bp).
+            constexpr bool VOTE_COUNTERS = (W <= 4);
+            if (!VOTE_COUNTERS && go && A.filter_on) {
+                const bool primary = !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
+                const bool unmapped = (flags & SD_F_UNMAPPED) != 0;
+                if (primary) atomicAdd(&s_stats[unmapped ? SD_S_UNMAPPED : SD_S_MAPPED], 1u);
+                if (unmapped) go = false;
+                else if ((int)mapq < A.filter_mq) { atomicAdd(&s_stats[SD_S_MQFILTERED], 1u); go = false; }
+                else if (xi < A.filter_min_identity) { atomicAdd(&s_stats[SD_S_IDFILTERED], 1u); go = false; }
+                else if (A.filter_max_nm > -1 && (int)nm > A.filter_max_nm) { atomicAdd(&s_stats[SD_S_NMFILTERED], 1u); go = false; }
+                else if (primary) atomicAdd(&s_stats[SD_S_FILTERED], 1u);
+            }
+            if (VOTE_COUNTERS && A.filter_on) {
+                // the run counters are warp totals (one vote each, added by lane 0) instead of one shared-memory atomic per
+                // read and counter
+                const bool primary = go && !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
+                const bool mapped = go && !(flags & SD_F_UNMAPPED);
+                const bool f_mq = mapped && (int)mapq < A.filter_mq;
+                const bool f_id = mapped && !f_mq && xi < A.filter_min_identity;
+                const bool f_nm = mapped && !f_mq && !f_id && A.filter_max_nm > -1 && (int)nm > A.filter_max_nm;
+                go = mapped && !f_mq && !f_id && !f_nm;
+                const uint32_t b_map = __ballot_sync(0xFFFFFFFFu, primary && mapped), b_unm = __ballot_sync(0xFFFFFFFFu, primary && !mapped);
+                const uint32_t b_mq = __ballot_sync(0xFFFFFFFFu, f_mq), b_id = __ballot_sync(0xFFFFFFFFu, f_id);
+                const uint32_t b_nm = __ballot_sync(0xFFFFFFFFu, f_nm), b_ok = __ballot_sync(0xFFFFFFFFu, go && primary);
+                if (lane == 0) {   // one conflict-free shared atomic per non-zero counter and tile
+                    if (b_map) atomicAdd(&s_stats[SD_S_MAPPED], (uint32_t)__popc(b_map));
+                    if (b_ok) atomicAdd(&s_stats[SD_S_FILTERED], (uint32_t)__popc(b_ok));
+                    if (b_unm | b_mq | b_id | b_nm) {
+                        if (b_unm) atomicAdd(&s_stats[SD_S_UNMAPPED], (uint32_t)__popc(b_unm));
+                        if (b_mq) atomicAdd(&s_stats[SD_S_MQFILTERED], (uint32_t)__popc(b_mq));
+                        if (b_id) atomicAdd(&s_stats[SD_S_IDFILTERED], (uint32_t)__popc(b_id));
+                        if (b_nm) atomicAdd(&s_stats[SD_S_NMFILTERED], (uint32_t)__popc(b_nm));
+                    }
                 }
             }
-        }
-        if (flags & (SD_F_UNMAPPED | SD_F_SKIP)) go = false;
-        if (ref >= A.n_chrom) go = false;
-
-        // Is every read of this tile a single match block (no clips, no indels)?  Warp-uniform: the decoder and
-        // the generator group such reads into their own tiles, so most warps take the lean path.
-        const uint32_t cig0 = ncig ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq)[cig_row] : 0u;
-        const bool uni_simple = __all_sync(0xFFFFFFFFu, !go || (ncig == 1u && ((0x181u >> (cig0 & 15u)) & 1u)));
+            return go;
+        };
+        // A tile without a CIGAR block: every record with one op is one M block of l_seq bases (sd_batch: plain-match tiles
+        // need not carry the column at all)
+        const bool nocig = s_nocig[stage] != 0u;
+        // could this record be counted at all, whatever the filter says
+        const bool cand = !(flags & (SD_F_PAD | SD_F_UNMAPPED | SD_F_SKIP)) && ref < A.n_chrom && !(nocig && ncig > 1u);
+        const uint32_t cig0 = nocig ? (lseq << 4) : (ncig ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq)[cig_row] : 0u);
         // Deep coverage: a coordinate-sorted tile whose 32 reads start within a few positions would send dozens of atomics to
         // the same addresses; such tiles (warp-uniform test on the tile's first and last record) aggregate them in the warp.
         const bool dense_tile = __shfl_sync(0xFFFFFFFFu, rmf & 0xFFFFu, 0) == __shfl_sync(0xFFFFFFFFu, rmf & 0xFFFFu, 31) &&
                                 (uint32_t)(__shfl_sync(0xFFFFFFFFu, pos, 31) - __shfl_sync(0xFFFFFFFFu, pos, 0)) <= SD_DENSE_SPAN;
-        // @region view_setup
         int tc = 0;
-        if (go) {
-            const uint32_t clen = __ldg(&A.chrom_len[ref]);
-            if (pos >= 0 && (uint32_t)pos < clen) {
-                ReadView v;
-                v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (SB == 2 ? 2u : 4u) * lane;
-                v.qual = QB > 0 ? base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + 4u * QB * lane : A.qual + s_qoff[stage] + qs;
-                v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + cig_row;
-                v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
-                v.lseq = lseq;
-                v.ncig = ncig;
-                v.nmp = nmp;
-                v.g = __ldg(&A.chrom_off[ref]) + (uint32_t)pos;
-                v.strand = (flags & SD_F_REVERSE) ? 1 : 0;
-                v.has_mp = (flags & SD_F_HAS_MP) != 0;
-                Blocks B;
-                uint32_t reflen;
-                if (uni_simple) {   // one match block starting at window position 0
-                    B.n = 1;
-                    B.r0a = 0;
-                    B.r1a = (int)(cig0 >> 4);
-                    B.r0b = B.r1b = B.r0c = B.r1c = 0;
-                    B.sha = B.shb = B.shc = 0;
-                    B.regs_ok = true;
-                    reflen = cig0 >> 4;
-                } else reflen = (uint32_t)parse_cigar(v.cig, ncig, B);
-                if (reflen == 0) reflen = 1;  // htslib bam_endpos
-                if ((uint64_t)pos + reflen > clen) reflen = clen - (uint32_t)pos;
-                v.span = (int)reflen;
-                bool fits = !A.force_slow && reflen <= 32u * W && lseq <= 32u * W;
-                if (fits && A.mismatch_source == SD_MISMATCH_MP && v.mp) {
-                    for (uint32_t i = 0; i < nmp; i++)
-                        if ((v.mp[i] >> 16) >= 32u * W) fits = false;
+        bool bad = false;
+        if (STAGED) {
+            // Is every read of this tile a single match block (no clips, no indels)?  Warp-uniform: the decoder and
+            // the generator group such reads into their own tiles, so most warps take the lean path.
+            const bool uni_simple = __all_sync(0xFFFFFFFFu, !cand || (ncig == 1u && ((0x181u >> (cig0 & 15u)) & 1u)));
+            // @region view_setup
+            // Every lane builds its view; a lane without a countable read gets an empty one (no bases, no span), so that the
+            // whole warp runs through the same code and a UTR's counters are warp-wide votes.
+            const uint32_t refc = cand ? ref : 0u;
+            const uint32_t clen = __ldg(&A.chrom_len[refc]);
+            const bool placed = cand && pos >= 0 && (uint32_t)pos < clen;
+            ReadView v;
+            v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (SB == 2 ? 2u : 4u) * lane;
+            v.qual = QB > 0 ? base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + 4u * QB * lane : A.qual + s_qoff[stage] + qs;
+            v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + cig_row;
+            v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
+            v.ncig = placed ? ncig : 0u;
+            v.g = __ldg(&A.chrom_off[refc]) + (placed ? (uint32_t)pos : 0u);
+            v.strand = (flags & SD_F_REVERSE) ? 1 : 0;
+            v.has_mp = (flags & SD_F_HAS_MP) != 0;
+            Blocks B;
+            uint32_t reflen;
+            if (uni_simple) {   // one match block starting at window position 0
+                B.n = 1;
+                B.r0a = 0;
+                B.r1a = (int)(cig0 >> 4);
+                B.r0b = B.r1b = B.r0c = B.r1c = 0;
+                B.sha = B.shb = B.shc = 0;
+                B.regs_ok = true;
+                reflen = cig0 >> 4;
+            } else reflen = (uint32_t)parse_cigar(v.cig, v.ncig, B);
+            if (reflen == 0) reflen = 1;  // htslib bam_endpos
+            if (placed && (uint64_t)pos + reflen > clen) reflen = clen - (uint32_t)pos;
+            bool fits = !A.force_slow && reflen <= 32u * W && lseq <= 32u * W;
+            if (placed && fits && A.mismatch_source == SD_MISMATCH_MP && v.mp) {
+                for (uint32_t i = 0; i < nmp; i++)
+                    if ((v.mp[i] >> 16) >= 32u * W) fits = false;
+            }
+            // A read that needs the per-base path (wider than the register window), or lies outside the span its tile declared
+            // (honest spans contain every read), sends the whole tile to the plain kernel -- before anything was counted.
+            if (__any_sync(0xFFFFFFFFu, placed && !(fits && v.g >= info.x && v.g + reflen <= info.y))) {
+                if (lane == 0) A.leftover[atomicAdd(A.n_leftover, 1u)] = (uint32_t)tile;
+            } else {
+                const bool live = filter_step(!(flags & SD_F_PAD)) && placed;
+                if (live) my_counted++;
+                v.lseq = live ? lseq : 0u;
+                v.nmp = live ? nmp : 0u;
+                v.span = live ? (int)reflen : 0;
+                StageView sv;
+                sv.win = reinterpret_cast<const uint4 *>(base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual);
+                sv.ent = reinterpret_cast<const uint4 *>(base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual + A.cap_win);
+                sv.w0 = info.x >> 5;
+                sv.n_ent = info.z;
+                tc = uni_simple ? staged_read<W, true, SB, QB>(A, v, B, mapq, dense_tile, live, sv, bad)
+                                : staged_read<W, false, SB, QB>(A, v, B, mapq, dense_tile, live, sv, bad);
+                if (!live) tc = 0;
+            }
+        } else {
+            const bool go = filter_step(!(flags & SD_F_PAD)) && cand;
+            const bool uni_simple = __all_sync(0xFFFFFFFFu, !go || (ncig == 1u && ((0x181u >> (cig0 & 15u)) & 1u)));
+            // @region view_setup
+            if (go) {
+                const uint32_t clen = __ldg(&A.chrom_len[ref]);
+                if (pos >= 0 && (uint32_t)pos < clen) {
+                    ReadView v;
+                    v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (SB == 2 ? 2u : 4u) * lane;
+                    v.qual = QB > 0 ? base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + 4u * QB * lane : A.qual + s_qoff[stage] + qs;
+                    v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + cig_row;
+                    v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
+                    v.lseq = lseq;
+                    v.ncig = ncig;
+                    v.nmp = nmp;
+                    v.g = __ldg(&A.chrom_off[ref]) + (uint32_t)pos;
+                    v.strand = (flags & SD_F_REVERSE) ? 1 : 0;
+                    v.has_mp = (flags & SD_F_HAS_MP) != 0;
+                    Blocks B;
+                    uint32_t reflen;
+                    if (uni_simple) {   // one match block starting at window position 0
+                        B.n = 1;
+                        B.r0a = 0;
+                        B.r1a = (int)(cig0 >> 4);
+                        B.r0b = B.r1b = B.r0c = B.r1c = 0;
+                        B.sha = B.shb = B.shc = 0;
+                        B.regs_ok = true;
+                        reflen = cig0 >> 4;
+                    } else reflen = (uint32_t)parse_cigar(v.cig, ncig, B);
+                    if (reflen == 0) reflen = 1;  // htslib bam_endpos
+                    if ((uint64_t)pos + reflen > clen) reflen = clen - (uint32_t)pos;
+                    v.span = (int)reflen;
+                    bool fits = !A.force_slow && reflen <= 32u * W && lseq <= 32u * W;
+                    if (fits && A.mismatch_source == SD_MISMATCH_MP && v.mp) {
+                        for (uint32_t i = 0; i < nmp; i++)
+                            if ((v.mp[i] >> 16) >= 32u * W) fits = false;
+                    }
+                    my_counted++;
+                    if (fits) {
+                        tc = uni_simple ? fast_read<W, true, SB, QB>(A, v, B, mapq, dense_tile, bad) : fast_read<W, false, SB, QB>(A, v, B, mapq, dense_tile, bad);
+                    } else {
+                        uint32_t cigw = lseq << 4;   // a tile without a CIGAR block: the per-base path wants the op spelled out
+                        if (nocig) v.cig = &cigw;
+                        atomicAdd(&A.stats[SD_S_SLOWPATH], 1ull);
+                        tc = slow_read(A, v, mapq);
+                    }
                 }
-                my_counted++;
-                if (fits) {
-                    bool bad = false;
-                    tc = uni_simple ? fast_read<W, true, SB, QB>(A, v, B, mapq, dense_tile, bad) : fast_read<W, false, SB, QB>(A, v, B, mapq, dense_tile, bad);
-                    if (bad) atomicAdd(&A.stats[SD_S_MP_DISAGREE], 1ull);   // rare: straight to the global counter
-                } else {
-                    atomicAdd(&A.stats[SD_S_SLOWPATH], 1ull);
-                    tc = slow_read(A, v, mapq);
-                }
-                my_tc_total += (uint32_t)tc;
             }
         }
+        if (bad) atomicAdd(&A.stats[SD_S_MP_DISAGREE], 1ull);   // rare: straight to the global counter
+        my_tc_total += (uint32_t)tc;
         if (A.read_tc) A.read_tc[tile * SD_TILE_READS + lane] = (uint8_t)(tc > 255 ? 255 : tc);
+        }
 
         // @region tile_end
         __syncwarp();   // every lane is done with this stage
@@ -1036,7 +1252,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
             s_tile[stage] = next;
         }
         next = __shfl_sync(0xFFFFFFFFu, next, 0);
-        if (lane < 5u && next != 0xFFFFFFFFu) issue(next, stage);
+        if (lane < 7u && next != 0xFFFFFFFFu) issue(next, stage);
         __syncwarp();
         if (++stage == A.n_stages) {
             stage = 0;
@@ -1064,9 +1280,9 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
 inline uint32_t align128(uint32_t x) { return (x + 127u) & ~127u; }
 inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
-template <int W, int SB, int QB>
-int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
-    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual;
+template <int W, int SB, int QB, bool STAGED>
+static int launch_one(sd_ctx *ctx, CountArgs &A, cudaStream_t stream) {
+    const uint32_t stage_bytes = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual + A.cap_win + A.cap_ent;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     static int forced_stages = -1, forced_warps = -1, forced_pf = -1;
@@ -1080,8 +1296,9 @@ int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
     }
     // Per-warp ring of n_stages tiles.  Two stages hide the copy latency behind the previous tile, but shared memory is taken
     // from the same 228 KB as the L1 that serves the reference window / annotation table lookups, and it can cost a resident
-    // CTA: the second stage is used only when it neither lowers the CTAs per SM nor leaves L1 less than 56 KB.
-    auto warp_bytes = [&](uint32_t ns) { return (size_t)ns * stage_bytes + 256u; };
+    // CTA: the second stage is used only when it neither lowers the CTAs per SM nor leaves L1 less than 56 KB (24 KB for the
+    // staged kernel, whose reference window and annotation entries arrive with the tile instead of through L1).
+    auto warp_bytes = [&](uint32_t ns) { return (size_t)ns * stage_bytes + SD_WARP_TRAILER; };
     if (128u + warp_bytes(1) > (size_t)max_smem)
         return sd_fail(ctx, SD_ERR_LIMIT, "a 32-read tile needs %u bytes of shared memory; reads are too long for this kernel", stage_bytes);
     auto plan = [&](uint32_t ns, uint32_t &warps, size_t &smem, int &per_sm) -> int {
@@ -1090,8 +1307,8 @@ int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
         while (warps > 1 && 128u + warps * warp_bytes(ns) > (size_t)max_smem) warps--;
         smem = 128u + warps * warp_bytes(ns);
         if (smem > (size_t)max_smem) { per_sm = 0; return SD_OK; }
-        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W, SB, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W, SB, QB>, (int)warps * 32, smem));
+        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W, SB, QB, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_count_kernel<W, SB, QB, STAGED>, (int)warps * 32, smem));
         return SD_OK;
     };
     uint32_t n_stages = 1, warps = 0;
@@ -1113,13 +1330,14 @@ int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
         if ((rc = plan(2, w2, s2, p2)) != SD_OK) return rc;
         int sm_total = 0;
         cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device);
-        if (p2 >= 1 && (uint64_t)p2 * w2 >= (uint64_t)per_sm * warps && (size_t)p2 * s2 + 56u * 1024u <= (size_t)sm_total) {
+        const size_t l1_keep = (STAGED ? 24u : 56u) * 1024u;
+        if (p2 >= 1 && (uint64_t)p2 * w2 >= (uint64_t)per_sm * warps && (size_t)p2 * s2 + l1_keep <= (size_t)sm_total) {
             n_stages = 2; warps = w2; smem = s2; per_sm = p2;
         }
     }
     if (per_sm < 1) return sd_fail(ctx, SD_ERR_LIMIT, "count kernel does not fit on an SM (smem %zu)", smem);
     if (last.device != ctx->device || last.stage_bytes != stage_bytes) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W, SB, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SD_CUDA(ctx, cudaFuncSetAttribute(sd_count_kernel<W, SB, QB, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         last = {stage_bytes, ctx->device, n_stages, warps, smem, per_sm};
     }
     A.n_stages = n_stages;
@@ -1128,14 +1346,31 @@ int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
     const uint64_t want_ctas = ((uint64_t)A.n_tiles + warps - 1) / warps;
     uint32_t grid = (uint32_t)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * per_sm);
     if (grid == 0) grid = 1;
-    if (timed) SD_CUDA(ctx, cudaEventRecord(ctx->ev_k0, stream));
-    sd_count_kernel<W, SB, QB><<<grid, threads, smem, stream>>>(A);
-    if (timed) {
-        SD_CUDA(ctx, cudaEventRecord(ctx->ev_k1, stream));
-        ctx->have_kernel_time = true;
-    }
+    sd_count_kernel<W, SB, QB, STAGED><<<grid, threads, smem, stream>>>(A);
     ctx->launches++;
     SD_CUDA(ctx, cudaGetLastError());
     return SD_OK;
 }
 
+// A.tile_counter points at three zeroed words: the two launches' queue heads and the number of tiles the first left over.
+template <int W, int SB, int QB>
+int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
+    if (timed) SD_CUDA(ctx, cudaEventRecord(ctx->ev_k0, stream));
+    unsigned int *words = A.tile_counter;
+    int rc = SD_OK;
+    if (A.spans) {
+        A.n_leftover = words + 2;
+        if ((rc = launch_one<W, SB, QB, true>(ctx, A, stream)) != SD_OK) return rc;
+        A.tile_list = A.leftover;
+        A.n_list = words + 2;
+        A.tile_counter = words + 1;
+        A.spans = nullptr;
+        A.cap_win = A.cap_ent = 0;
+    }
+    if ((rc = launch_one<W, SB, QB, false>(ctx, A, stream)) != SD_OK) return rc;
+    if (timed) {
+        SD_CUDA(ctx, cudaEventRecord(ctx->ev_k1, stream));
+        ctx->have_kernel_time = true;
+    }
+    return SD_OK;
+}

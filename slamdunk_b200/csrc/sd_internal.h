@@ -25,6 +25,7 @@ struct sd_ctx {
 
     // reference: per strand {isX, snpX} per 32 bp; strand 0: X = T / T>C SNPs, strand 1: X = A / A>G SNPs
     uint2 *refx[2] = {nullptr, nullptr};
+    uint4 *refm = nullptr;   // both strands side by side {isT, T>C SNPs, isA, A>G SNPs}: what a tile's staged reference window is copied from
     uint64_t n_words = 0;
     std::vector<uint32_t> chrom_off, chrom_len;
     uint32_t *d_chrom_off = nullptr, *d_chrom_len = nullptr;
@@ -43,6 +44,13 @@ struct sd_ctx {
     uint32_t *d_seg_start[2] = {nullptr, nullptr}, *d_seg_end[2] = {nullptr, nullptr};
     uint64_t *d_seg_off[2] = {nullptr, nullptr};
     uint64_t n_positions = 0;
+    // strand-merged annotation for the staged join: entries of both strands sorted by start, two uint4 each
+    // ({start, end, row | strand << 31, segment}, {segment start, segment end, posbase lo, hi}; posbase = segment offset - start),
+    // and per bin the first entry that can still overlap a window starting in it
+    uint4 *d_ment = nullptr;
+    uint32_t *d_bin_first_m = nullptr;
+    uint32_t n_ment = 0;
+    uint32_t ann_epoch = 0;   // bumped by sd_set_reference / sd_set_utrs: span descriptors made before are ignored
     // all BED rows (for Tcontent and host layout)
     uint32_t *d_row_gstart = nullptr, *d_row_gend = nullptr;
     uint8_t *d_row_strand = nullptr;
@@ -57,7 +65,9 @@ struct sd_ctx {
     int32_t *pos_cov = nullptr, *pos_tc = nullptr;
     int64_t *stats = nullptr;
 
-    unsigned int *d_tile_counter = nullptr;   // work-queue head of the count kernel
+    unsigned int *d_tile_counter = nullptr;   // work-queue heads of the count kernel's launches + number of left-over tiles
+    uint32_t *d_leftover = nullptr;           // tiles the staged count kernel leaves to the plain one
+    uint32_t leftover_cap = 0;
 
     // grow-only scratch of sd_track_runs (flags | selected positions | cub temp | count)
     void *d_track_scratch = nullptr;

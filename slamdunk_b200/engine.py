@@ -249,6 +249,8 @@ class CountEngine(object):
         L.check(self.lib.sd_create(device, ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(ctx)), None, "sd_create")
         self.ctx = ctx
         self.n_utr = 0
+        self.n_utr_set = False
+        self._epoch = 0
         self.n_positions = 0
         self.counters = self.pos_cov = self.pos_tc = self.stats = self.tcontent = None
         self._keep = {}
@@ -286,6 +288,7 @@ class CountEngine(object):
         self._chk(self.lib.sd_set_reference(self.ctx, _t_ptr(d_lo), _t_ptr(d_hi), _t_ptr(d_n), self.n_words,
                                             _np_ptr(co), _np_ptr(cl), len(co)), "sd_set_reference")
         self.chrom_off, self.chrom_len = co, cl
+        self._epoch += 1
 
     def set_snps(self, tc_mask, ag_mask):
         def dev(x):
@@ -307,6 +310,8 @@ class CountEngine(object):
         self._chk(self.lib.sd_set_utrs(self.ctx, _np_ptr(ci), _np_ptr(st), _np_ptr(sp), _np_ptr(sd),
                                        _np_ptr(ib) if ib is not None else None, n), "sd_set_utrs")
         self.n_utr = n
+        self.n_utr_set = True
+        self._epoch += 1
         npos = ctypes.c_uint64()
         self._chk(self.lib.sd_position_space(self.ctx, ctypes.byref(npos)), "sd_position_space")
         self.n_positions = int(npos.value)
@@ -326,7 +331,24 @@ class CountEngine(object):
                                            _t_ptr(self.stats)), "sd_bind_outputs")
 
     # -- the hot path ------------------------------------------------------------------
-    def count(self, dbatch: DeviceBatch, params: L.Params, read_tc: Optional[torch.Tensor] = None):
+    def attach_spans(self, dbatch: DeviceBatch):
+        """Per-tile span descriptors (sd_tile_spans) for the reference and annotation this engine holds: with them the count
+        kernel stages each tile's reference window and annotation entries together with the tile.  Part of building a
+        device batch; redo after set_reference / set_utrs (stale descriptors are ignored by the library, not misused)."""
+        nt = int(dbatch.batch.n_tiles)
+        with torch.cuda.stream(self.stream):
+            spans = torch.empty(max(1, nt) * 16, dtype=torch.uint8, device=self.device)
+        self._chk(self.lib.sd_tile_spans(self.ctx, ctypes.byref(dbatch.batch), _t_ptr(spans)), "sd_tile_spans")
+        dbatch.spans_tensor = spans      # owned by this DeviceBatch object (the tensors dict may be shared between views)
+        dbatch.spans_key = (self.ctx.value, self._epoch)
+        return dbatch
+
+    def count(self, dbatch: DeviceBatch, params: L.Params, read_tc: Optional[torch.Tensor] = None, spans: bool = True):
+        if spans and int(dbatch.batch.n_tiles) and self.n_utr_set and getattr(dbatch, "spans_key", None) != (self.ctx.value, self._epoch):
+            self.attach_spans(dbatch)
+        if not spans and dbatch.batch.spans:          # tests: the plain kernel on a batch that has descriptors
+            dbatch.batch.spans = None
+            dbatch.spans_key = None
         if read_tc is not None:
             self._chk(self.lib.sd_count_reads(self.ctx, ctypes.byref(dbatch.batch), ctypes.byref(params), _t_ptr(read_tc)),
                       "sd_count_reads")

@@ -433,3 +433,69 @@ def test_plane_form_qualities_count_like_the_byte_column(read_len, n_reads, mode
     for k in ("counters", "stats", "pos_cov", "pos_tc"):
         assert np.array_equal(want[k], got[k]), "host " + k
     eng.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("sorted_", [True, False])
+def test_staged_and_plain_kernels_agree(mode, sorted_):
+    """The count kernel that stages each tile's reference window and annotation entries with the tile (batches with span
+    descriptors, sd_tile_spans) gives the outputs of the kernel that looks them up per read -- on coordinate-sorted reads
+    (nearly every tile staged) and in mapper order (most tiles handed on to the plain kernel), in every mismatch mode, with
+    the filter predicates fused, and per read."""
+    import torch
+    from slamdunk_b200.engine import make_params
+    from slamdunk_b200.synth import to_qual_planes, to_seq2
+    eng, wl = _setup(genome_bp=2_000_000, n_utr=900, seed=11)
+    p = wl.params(seed=4, first_read=0, n_reads=150_000, read_len=100, frac_softclip=0.1, frac_indel=0.08, frac_antisense=0.1)
+    db, _ = wl.generate(p, want_mp=True, coordinate_sorted=sorted_)
+    params = make_params(27, 1, mode, filter_on=True, filter_mq=2, filter_min_identity=0.95, filter_max_nm=-1)
+    forms = [db, to_seq2(db, eng)]
+    qp = to_qual_planes(forms[1], eng)
+    if qp is not None:
+        forms.append(qp)
+    for form in forms:
+        outs = []
+        for spans in (False, True):
+            eng.reset_outputs()
+            rtc = torch.zeros(form.batch.n_tiles * 32, dtype=torch.uint8, device=eng.device)
+            eng.count(form, params, rtc, spans=spans)
+            eng.finalize()
+            eng.synchronize()
+            assert bool(form.batch.spans) == spans
+            outs.append((eng.counters.clone(), eng.pos_cov.clone(), eng.pos_tc.clone(), eng.stats.clone(), rtc))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+        assert int(outs[0][3][6]) > 100_000
+    eng.close()
+
+
+def test_stale_span_descriptors_are_ignored():
+    """Descriptors made for another annotation must not be used: after sd_set_utrs the library ignores them (epoch), and the
+    engine attaches fresh ones."""
+    import torch
+    from slamdunk_b200.engine import make_params
+    eng, wl = _setup(genome_bp=1_000_000, n_utr=300, seed=3)
+    db, _ = wl.generate(wl.params(seed=2, first_read=0, n_reads=40_000), coordinate_sorted=True)
+    params = make_params(27, 1, 0)
+    eng.count(db, params)
+    a = wl.ann
+    keep = np.arange(len(a)) % 2 == 0                       # another annotation: every second UTR
+    eng.set_utrs(a.chrom[keep], a.start[keep], a.stop[keep], a.strand[keep], None)
+    stale_key = db.spans_key
+    db.spans_key = (eng.ctx.value, eng._epoch)               # pretend they are current: the library must still refuse them
+    eng.count(db, params)
+    eng.finalize()
+    eng.synchronize()
+    got = eng.counters.clone()
+    db.spans_key = stale_key
+    eng.reset_outputs()
+    eng.count(db, params)                                    # fresh descriptors
+    eng.finalize()
+    eng.synchronize()
+    assert torch.equal(got, eng.counters)
+    eng.reset_outputs()
+    eng.count(db, params, spans=False)
+    eng.finalize()
+    eng.synchronize()
+    assert torch.equal(got, eng.counters)
+    eng.close()
