@@ -250,8 +250,7 @@ def main():
     import torch.distributed as dist
     from slamdunk_b200 import _lib as L
     from slamdunk_b200.engine import make_params
-    from slamdunk_b200.synth import (algorithmic_bytes_per_read, batch_to_host, host_batch_bytes, layout_bytes_per_read,
-                                     to_qual_planes, to_seq2)
+    from slamdunk_b200.synth import (algorithmic_bytes_per_read, batch_to_wire, layout_bytes_per_read, to_qual_planes, to_seq2)
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -337,13 +336,13 @@ def main():
     # end to end: pinned host buffers -> sd_count_host -> counters back on the host
     e2e = None
     if not args.no_e2e:
-        hb, keep = batch_to_host(db_rows, eng)     # the host form sd_decode_bam produces: quality codes when the column has <= 16 values
-        h2d = host_batch_bytes(keep)
+        hw = batch_to_wire(db_rows, eng)           # the packed host form sd_decode_bam produces for `count` (sd_wire)
+        h2d = hw.h2d_bytes(params)
         d2h = eng.counters.numel() * 8 + eng.stats.numel() * 8
 
         def e2e_step():
             eng.reset_outputs()
-            eng.count_host(hb, params)
+            eng.count_wire(hw.wire, params)
             eng.finalize()
             if world > 1:
                 with torch.cuda.stream(eng.stream):
@@ -363,9 +362,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": world * n_reads / dt, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt * 1e3, "h2d_gbs": h2d / dt / 1e9, "host_qual_bits": int(hb.qual_bits),
-               "host_seq_bits": int(hb.seq_bits) or 4}
-        del hb, keep
+               "ms_per_step": dt * 1e3, "h2d_gbs": h2d / dt / 1e9, "h2d_bytes_per_read": h2d / n_reads,
+               "host_form": "sd_wire: per-field columns, 2-bit SEQ codes, %d-bit quality codes, plain-match tiles without l_seq / CIGAR" % int(hw.wire.qual_bits),
+               "counted_reads": int(out[1][L.SD_S_COUNTED])}
+        del hw
 
     # CPU baseline + parity of the GPU counters with the oracle on a bounded sample (rank 0, N = 1)
     cpu = None

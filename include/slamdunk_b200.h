@@ -142,15 +142,14 @@ typedef struct sd_batch {
     uint32_t spans_epoch;   /* set by sd_tile_spans; descriptors made before a later sd_set_reference / sd_set_utrs are ignored */
 } sd_batch;
 
-/* Stretch of the linear genome (sd_set_reference's bit space) covered by the countable reads of one tile -- mapped, on a
- * FASTA chromosome, position inside it -- and the run of annotation entries (both strands, sorted by start) that can overlap
- * it.  A tile with reads all over the genome (unsorted input) is still described; sd_count then falls back to per-read
- * lookups for it. */
+/* What the staged count kernel copies for one tile besides its columns, as [begin, end) byte offsets into two
+ * library-internal tables: the strand-merged reference planes (16 bytes per 32 linear positions) over the stretch of the
+ * genome the tile's countable reads cover -- mapped, on a FASTA chromosome, position inside it -- and the run of
+ * annotation entries (both strands, sorted by start) that can overlap that stretch.  A tile with reads all over the genome
+ * (unsorted input) is described by an impossible size; sd_count then counts it with per-read lookups. */
 typedef struct sd_tile_span {
-    uint32_t g_min;         /* first linear position covered */
-    uint32_t g_end;         /* one past the last */
-    uint32_t ent_first;     /* library-internal index of the first candidate entry */
-    uint32_t n_ent_flags;   /* bits 0-15 number of candidate entries, bit 16 descriptor valid */
+    uint64_t win_begin, win_end;
+    uint64_t ent_begin, ent_end;
 } sd_tile_span;
 
 /* Where the per-read mismatch list comes from. */
@@ -276,6 +275,77 @@ int64_t sd_launch_count(const sd_ctx *ctx);
 /* Duration of the most recent sd_count kernel on its stream (CUDA events), ms; <0 if none. */
 float sd_last_kernel_ms(sd_ctx *ctx);
 
+/* ------------------------------------------------------------------ packed host batch ("wire" form)
+ * What travels over PCIe for `count`: the same records as an sd_batch, with every field in its own column and nothing
+ * padded or repeated, so that sd_count_wire copies only what the call needs (no XI when the filter is off, no NM unless
+ * the NM filter is on, no MP entries for a plain CIGAR walk) and expands the rest on the device, next to the kernel that
+ * consumes it.  At 100 bp: 2-bit SEQ codes 25 B + 2-bit quality codes 25 B + pos / mapq+flags / XI code 6 B per read, plus
+ * a 32-byte header per 32-read tile; plain-match tiles carry neither l_seq nor CIGAR (58 B per read against the 82 B of
+ * the sd_batch host form).  Made by sd_decode_bam (SD_DECODE_WIRE) or, from a device batch, by sd_wire_plan + sd_wire_fill.
+ *
+ * Per-read columns [n_tiles * 32], slot order as in sd_batch.rec:
+ *   pos16   pos - tile.base_pos (tiles without SD_WT_POS32)
+ *   mqf     MAPQ | SD_F_* << 8
+ *   xi16    index into xi_dict (files with at most 65536 distinct XI values), else xi32 holds the floats
+ *   nm16    NM tag, saturated
+ *   nmp16   number of MP entries of the record (only with mp)
+ * Per-base columns, rows back to back at base granularity, a tile's first base at tiles[t].base_off (a multiple of 64):
+ *   seq     2-bit base codes A=0 C=1 G=2 T=3 (anything else A, see sd_batch.seq_bits), base i of the column at bits
+ *           2 (i % 4) of byte i / 4
+ *   qual    qual_bits-bit dictionary codes (2 or 4, low bits first), or bytes (8)
+ * var: per tile one block of 32-bit words at tiles[t].var_off (a multiple of 4 words), made of, in this order and each
+ * only when the tile's flag is set: int32 pos[32] (SD_WT_POS32: positions that do not fit base_pos + 16 bits), uint16
+ * ref[32] (SD_WT_REFS: the tile's records are not all on tiles[t].ref), uint32 l_seq | n_cigar << 16 [32] followed by
+ * the CIGAR ops of the 32 rows back to back (SD_WT_SHAPE; a tile without it holds records that are one M block of
+ * tiles[t].lseq bases each -- padding records, flagged SD_F_PAD in mqf, have no bases).
+ * mp: as sd_batch.mp, tile blocks at tiles[t].mp_off (words, multiple of 4).
+ */
+#define SD_WT_POS32 1u
+#define SD_WT_REFS 2u
+#define SD_WT_SHAPE 4u
+typedef struct sd_wire_tile {
+    uint64_t base_off;      /* bases */
+    uint32_t var_off;       /* 32-bit words */
+    uint32_t mp_off;        /* 32-bit words */
+    int32_t base_pos;
+    uint16_t ref;
+    uint16_t flags;         /* SD_WT_* */
+    uint16_t lseq;
+    uint16_t reserved0;
+    uint32_t reserved1;
+} sd_wire_tile;
+
+typedef struct sd_wire {
+    uint64_t n_reads;
+    uint32_t n_tiles;
+    uint32_t tile_reads;           /* 32 */
+    const sd_wire_tile *tiles;     /* [n_tiles + 1]; the last entry holds the column totals */
+    const uint16_t *pos16, *mqf, *xi16, *nm16, *nmp16;
+    const float *xi32;             /* used when xi16 is NULL */
+    const uint8_t *seq, *qual;
+    const uint32_t *var, *mp;      /* mp may be NULL */
+    const float *xi_dict;          /* [n_xi_dict] */
+    uint32_t n_xi_dict;
+    uint32_t qual_bits;            /* 2, 4 or 8 */
+    uint8_t qual_dict[16];         /* code -> phred value, ascending */
+    uint32_t max_lseq, max_span;   /* as in sd_batch */
+    uint32_t max_tile_cig;         /* largest CIGAR block of a tile in bytes (rounded up to 16), 0 when no tile has SD_WT_SHAPE */
+    uint32_t max_tile_mp;          /* largest MP block of a tile in bytes */
+} sd_wire;
+
+/* sd_count_host for the wire form: copies the columns this call needs to the device in chunks of whole tiles (copy
+ * stream overlapped with the kernels), expands each chunk into an sd_batch with 2-bit SEQ, quality bit-planes and span
+ * descriptors, and counts it.  Host pointers (page-locked for full speed).  Synchronous. */
+int sd_count_wire(sd_ctx *ctx, const sd_wire *h_wire, const sd_params *params);
+/* Wire form of a device-resident batch (2-bit SEQ column, byte qualities): pass 1 fills d_tiles [n_tiles + 1] and reports
+ * h_totals = {bases, var words, mp words, largest CIGAR block in bytes}; pass 2 writes the columns into caller-allocated
+ * DEVICE buffers of those sizes (out->seq / out->qual zero-filled by the caller; out->xi16 / xi_dict / nmp16 / mp may be
+ * NULL; d_xi_code: optional uint16 [n_tiles * 32] dictionary code of every record's XI, copied to out->xi16; out->tiles =
+ * d_tiles of pass 1; qual_bits and qual_dict from sd_qual_dict).  Both synchronous.  Copy the buffers to the host to get
+ * what sd_decode_bam would have produced for the same records. */
+int sd_wire_plan(sd_ctx *ctx, const sd_batch *d_batch, sd_wire_tile *d_tiles, uint64_t h_totals[4]);
+int sd_wire_fill(sd_ctx *ctx, const sd_batch *d_batch, const uint16_t *d_xi_code, sd_wire *out);
+
 /* ------------------------------------------------------------------ read filter
  * filter.Filter decision logic (dunks/filter.py:225-271) for one device-resident batch in FILE
  * order.  keep: device uint8[n_reads], 0 drop / 1 write / 2 write with secondary+supplementary
@@ -298,6 +368,7 @@ int sd_filter(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params, con
 #define SD_DECODE_GROUP 2
 #define SD_DECODE_RAW_QUAL 4   /* keep one byte per base quality even when the file has <= 16 distinct values */
 #define SD_DECODE_SEQ2 16      /* write the SEQ column in the 2-bit form (sd_batch.seq_bits = 2) -- for sd_count* only */
+#define SD_DECODE_WIRE 32      /* also build the wire form of the batch (sd_hbatch.wire): what `count` sends over PCIe */
 #define SD_DECODE_MP_ALL 8     /* mp column holds EVERY MP entry, two words each: {readPos-1 | refPos-1 << 16, conv (0..24)} --
                                   the form sd_read_stats takes (sd_count cannot read it); implies SD_DECODE_MP */
 
@@ -315,6 +386,7 @@ typedef struct sd_hbatch {
     uint64_t inflated_bytes;
     uint64_t n_mapped_no_xi; /* mapped records without an XI tag (their sd_read_rec.xi is NaN) / without an NM tag (nm = 0): */
     uint64_t n_mapped_no_nm; /* read.get_tag() raises KeyError for them in the reference (filter.py:246,249) */
+    sd_wire wire;            /* SD_DECODE_WIRE: host pointers; n_tiles = 0 otherwise */
     void *opaque;
 } sd_hbatch;
 

@@ -50,6 +50,25 @@ class Batch(ctypes.Structure):
                 ("spans", ctypes.c_void_p), ("spans_epoch", ctypes.c_uint32)]
 
 
+class WireTile(ctypes.Structure):
+    _fields_ = [("base_off", ctypes.c_uint64), ("var_off", ctypes.c_uint32), ("mp_off", ctypes.c_uint32), ("base_pos", ctypes.c_int32),
+                ("ref", ctypes.c_uint16), ("flags", ctypes.c_uint16), ("lseq", ctypes.c_uint16), ("reserved0", ctypes.c_uint16),
+                ("reserved1", ctypes.c_uint32)]
+
+
+class Wire(ctypes.Structure):
+    _fields_ = [("n_reads", ctypes.c_uint64), ("n_tiles", ctypes.c_uint32), ("tile_reads", ctypes.c_uint32), ("tiles", ctypes.c_void_p),
+                ("pos16", ctypes.c_void_p), ("mqf", ctypes.c_void_p), ("xi16", ctypes.c_void_p), ("nm16", ctypes.c_void_p),
+                ("nmp16", ctypes.c_void_p), ("xi32", ctypes.c_void_p), ("seq", ctypes.c_void_p), ("qual", ctypes.c_void_p),
+                ("var", ctypes.c_void_p), ("mp", ctypes.c_void_p), ("xi_dict", ctypes.c_void_p), ("n_xi_dict", ctypes.c_uint32),
+                ("qual_bits", ctypes.c_uint32), ("qual_dict", ctypes.c_uint8 * 16), ("max_lseq", ctypes.c_uint32),
+                ("max_span", ctypes.c_uint32), ("max_tile_cig", ctypes.c_uint32), ("max_tile_mp", ctypes.c_uint32)]
+
+
+SD_WT_POS32, SD_WT_REFS, SD_WT_SHAPE = 1, 2, 4
+SD_DECODE_WIRE = 32
+
+
 class Params(ctypes.Structure):
     _fields_ = [("min_qual", ctypes.c_int32), ("conversion_threshold", ctypes.c_int32),
                 ("mismatch_source", ctypes.c_int32), ("filter_on", ctypes.c_int32), ("filter_mq", ctypes.c_int32),
@@ -62,7 +81,7 @@ class HBatch(ctypes.Structure):
                 ("ref_names", ctypes.POINTER(ctypes.c_char_p)), ("ref_lengths", c_u32p),
                 ("seconds_inflate", ctypes.c_double), ("seconds_decode", ctypes.c_double),
                 ("compressed_bytes", ctypes.c_uint64), ("inflated_bytes", ctypes.c_uint64),
-                ("n_mapped_no_xi", ctypes.c_uint64), ("n_mapped_no_nm", ctypes.c_uint64), ("opaque", ctypes.c_void_p)]
+                ("n_mapped_no_xi", ctypes.c_uint64), ("n_mapped_no_nm", ctypes.c_uint64), ("wire", Wire), ("opaque", ctypes.c_void_p)]
 
 
 class HGenome(ctypes.Structure):
@@ -113,6 +132,9 @@ PROTOTYPES = {
     "sd_bind_outputs": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "sd_count": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params)]),
     "sd_tile_spans": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), _VP]),
+    "sd_count_wire": (ctypes.c_int, [_VP, ctypes.POINTER(Wire), ctypes.POINTER(Params)]),
+    "sd_wire_plan": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), _VP, ctypes.POINTER(ctypes.c_uint64)]),
+    "sd_wire_fill": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), _VP, ctypes.POINTER(Wire)]),
     "sd_count_reads": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params), _VP]),
     "sd_count_host": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params)]),
     "sd_finalize": (ctypes.c_int, [_VP]),

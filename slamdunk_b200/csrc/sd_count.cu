@@ -123,7 +123,8 @@ struct SpanArgs {
     const uint4 *ment;
     const uint32_t *bin_first_m;
     uint32_t n_ment;
-    uint4 *out;
+    ulonglong4 *out;
+    uint64_t n_refm;
 };
 
 __global__ void sd_tile_spans_kernel(const SpanArgs A) {
@@ -162,14 +163,19 @@ __global__ void sd_tile_spans_kernel(const SpanArgs A) {
         e = g + reflen;
     }
     const uint32_t gmin = __reduce_min_sync(0xFFFFFFFFu, g), gend = __reduce_max_sync(0xFFFFFFFFu, e);
-    uint4 out = make_uint4(0u, 0u, 0u, SD_SPAN_VALID << 16);   // no countable read: nothing to stage
+    // {window begin, end, entries begin, end} as byte offsets into the strand-merged reference and annotation tables
+    ulonglong4 out = make_ulonglong4(0ull, 0ull, 0ull, 0ull);   // no countable read: nothing to stage
     if (gend != 0u) {
         const uint32_t i0 = A.bin_first_m[gmin >> SD_BIN_SHIFT];
         const uint32_t i = i0 + lane;
         const bool can = i < A.n_ment && __ldg(&A.ment[2 * (size_t)i]).x < gend;   // sorted by start: a prefix of the lanes
         const unsigned b = __ballot_sync(0xFFFFFFFFu, can);
-        out = (b == 0xFFFFFFFFu) ? make_uint4(gmin, gend, 0u, 0u)               // more candidates than a stage could hold
-                                 : make_uint4(gmin, gend, i0, (uint32_t)__popc(b) | (SD_SPAN_VALID << 16));
+        const unsigned long long w0 = gmin >> 5, w1 = ((unsigned long long)(gend - 1u) >> 5) + 1ull;
+        out.x = w0 * 16ull;
+        out.y = w1 * 16ull;
+        out.z = (unsigned long long)i0 * 32ull;
+        out.w = out.z + (unsigned long long)__popc(b) * 32ull;
+        if (b == 0xFFFFFFFFu || w1 + 32ull > A.n_refm) out.y = out.x + (1ull << 40);   // too many candidate entries: never staged
     }
     if (lane == 0) A.out[tile] = out;
 }
@@ -252,6 +258,7 @@ extern "C" void sd_destroy(sd_ctx *ctx) {
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
     cudaFree(ctx->d_tile_counter);
     cudaFree(ctx->d_leftover);
+    cudaFree(ctx->d_xi_dict);
     cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_copy[i]); cudaEventDestroy(ctx->ev_done[i]); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -485,7 +492,7 @@ extern "C" int sd_bind_outputs(sd_ctx *ctx, int64_t *d_counters, int32_t *d_pos_
     return SD_OK;
 }
 
-static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, cudaStream_t stream, uint8_t *read_tc, bool timed) {
+int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, cudaStream_t stream, uint8_t *read_tc, bool timed) {
     if (!ctx->refx[0]) return sd_fail(ctx, SD_ERR_STATE, "sd_count before sd_set_reference");
     if (!ctx->counters) return sd_fail(ctx, SD_ERR_STATE, "sd_count before sd_bind_outputs");
     if (b->n_tiles == 0) return SD_OK;
@@ -536,11 +543,9 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     // annotation entries with the tile (otherwise every lane fetches its own from global memory)
     static int spans_env = -1;
     if (spans_env < 0) { const char *e = getenv("SD_SPANS"); spans_env = e ? atoi(e) : 1; }
-    A.spans = (b->spans && b->spans_epoch == ctx->ann_epoch && spans_env) ? reinterpret_cast<const uint4 *>(b->spans) : nullptr;
+    A.spans = (b->spans && b->spans_epoch == ctx->ann_epoch && spans_env) ? b->spans : nullptr;
     A.refm = ctx->refm;
     A.ment = ctx->d_ment;
-    A.n_ment = ctx->n_ment;
-    A.n_refm = (uint32_t)std::min<uint64_t>(ctx->n_words + SD_REF_PAD_WORDS, 0xFFFFFFFFull);
     for (int s = 0; s < 2; s++) {
         A.refx[s] = ctx->refx[s];
         A.ustart[s] = ctx->d_ustart[s]; A.uend[s] = ctx->d_uend[s]; A.urow[s] = ctx->d_urow[s]; A.useg[s] = ctx->d_useg[s];
@@ -561,6 +566,7 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
         if (ctx->leftover_cap < b->n_tiles) {
             SD_CUDA(ctx, cudaStreamSynchronize(stream));
             cudaFree(ctx->d_leftover);
+    cudaFree(ctx->d_xi_dict);
             ctx->d_leftover = nullptr;
             ctx->leftover_cap = 0;
             SD_CUDA(ctx, cudaMalloc(&ctx->d_leftover, (size_t)b->n_tiles * sizeof(uint32_t)));
@@ -595,7 +601,7 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
     const uint32_t need = b->max_span ? std::max(b->max_lseq, b->max_span) : b->max_lseq + 16u;
     if (A.spans) {   // room for the staged window (the reads' words, a few more for the spread of their starts, W behind the last) and 8 entries
         const uint32_t Wn = need <= 128 ? 4 : need <= 192 ? 6 : need <= 256 ? 8 : need <= 320 ? 10 : need <= 384 ? 12 : 16;
-        A.cap_win = align128(16u * (3u * Wn + 4u));
+        A.cap_win = align128(16u * (6u * Wn + 8u));   // 864 bp of tile at W = 4: the thinly populated classes of a grouped batch (clipped / indel reads) fit too
         A.cap_ent = 256u;
     }
 #define SD_DISPATCH_W(SB, QB)                                                        \
@@ -614,13 +620,14 @@ static int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, c
 #undef SD_DISPATCH_W
 }
 
-static int tile_spans_on(sd_ctx *ctx, cudaStream_t stream, const sd_batch *b, void *d_spans) {
+int tile_spans_on(sd_ctx *ctx, cudaStream_t stream, const sd_batch *b, void *d_spans) {
     if (b->n_tiles == 0) return SD_OK;
     SpanArgs S;
     S.rec = b->rec; S.cigar = b->cigar; S.tiles = b->tiles; S.n_tiles = b->n_tiles;
     S.chrom_off = ctx->d_chrom_off; S.chrom_len = ctx->d_chrom_len; S.n_chrom = ctx->n_chrom;
     S.ment = ctx->d_ment; S.bin_first_m = ctx->d_bin_first_m; S.n_ment = ctx->n_ment;
-    S.out = reinterpret_cast<uint4 *>(d_spans);
+    S.out = reinterpret_cast<ulonglong4 *>(d_spans);
+    S.n_refm = ctx->n_words + SD_REF_PAD_WORDS;
     const unsigned blocks = (unsigned)(((uint64_t)b->n_tiles * 32u + 255u) / 256u);
     sd_tile_spans_kernel<<<blocks, 256, 0, stream>>>(S);
     ctx->launches++;
@@ -777,6 +784,7 @@ extern "C" int sd_count_host(sd_ctx *ctx, const sd_batch *hb, const sd_params *p
             uint32_t *d_planes = (uint32_t *)(d + o);
             o = up256(o + b_seq * qbits / 2);
             sd_tile *d_tiles2 = (sd_tile *)(d + o);
+            o = up256(o + (size_t)(nt + 1) * sizeof(sd_tile));
             if ((rc = sd_qual_to_planes_on(ctx, ctx->stream, &db, qbits, hb->qual_dict, d_planes, d_tiles2))) return rc;
             db.qual = (const uint8_t *)d_planes;
             db.tiles = d_tiles2;

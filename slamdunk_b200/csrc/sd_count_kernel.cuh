@@ -103,10 +103,9 @@ struct CountArgs {
     uint32_t n_stages;
     uint32_t qual_prefetch;   // L2-prefetch each tile's qual bytes when the tile is issued
     // per-tile span descriptors (sd_batch.spans) and what they index: the strand-merged reference and annotation tables
-    const uint4 *spans;       // {g_min, g_end, first entry, n entries | SD_SPAN_VALID << 16} or null
+    const void *spans;        // sd_tile_span per tile (four 64-bit byte offsets) or null
     const uint4 *refm;        // per 32 bp {isT, T>C SNPs, isA, A>G SNPs}
     const uint4 *ment;        // two uint4 per entry, see StageView
-    uint32_t n_ment, n_refm;  // entries in ment, words in refm (bounds of what a descriptor may ask for)
     // reference
     const uint2 *refx[2];
     const uint32_t *chrom_off;
@@ -815,9 +814,9 @@ __device__ __forceinline__ int fast_read(const CountArgs &A, const ReadView &v, 
 // What a stage holds besides the tile's columns (see the kernel): the reference window of the tile's reads, both strands
 // side by side, and the annotation entries that can overlap them.
 struct StageView {
-    const uint4 *win;     // word w0 + i: {isT, T>C SNPs, isA, A>G SNPs} of linear positions 32 (w0 + i) ..
+    const uint4 *win;     // staged words: {isT, T>C SNPs, isA, A>G SNPs} per 32 linear positions
     const uint4 *ent;     // entry j: ent[2j] = {start, end, row | strand << 31, segment}, ent[2j + 1] = {segment start, end, posbase lo, hi}
-    uint32_t w0, n_ent;
+    uint32_t d, n_ent;    // first window word of this lane's read among the staged ones; entries staged
 };
 
 // Staged tile: EVERY lane of the warp comes here (live = this lane has a read to count), so the loop over the tile's
@@ -830,8 +829,7 @@ __device__ __forceinline__ int staged_read(const CountArgs &A, const ReadView &v
     // @region window
     uint32_t T[W], S[W];
     {
-        const uint32_t d = live ? (v.g >> 5) - sv.w0 : 0u;
-        const uint2 *wp = reinterpret_cast<const uint2 *>(sv.win + d) + s;   // this strand's half of each 16-byte word
+        const uint2 *wp = reinterpret_cast<const uint2 *>(sv.win + sv.d) + s;   // this strand's half of each 16-byte word
         const uint32_t sh = v.g & 31u;
         uint2 x[W + 1];
 #pragma unroll
@@ -867,10 +865,53 @@ __device__ __forceinline__ int staged_read(const CountArgs &A, const ReadView &v
             if (s_cov) atomicAdd(c + SD_C_COV_ON_T, (unsigned long long)s_cov);
             if (s_conv) atomicAdd(c + SD_C_CONV_ON_T, (unsigned long long)s_conv);
         }
-        if (hit && u.w != last_seg) {
-            last_seg = u.w;
-            const uint4 sg = sv.ent[2 * j + 1];
-            scatter_segment<W>(A, H, tc, g, e, sg.x, sg.y, (unsigned long long)sg.z | ((unsigned long long)sg.w << 32), dense_tile);
+        // per-position outputs, once per (read, merged segment).  Still the whole warp: the reads of a sorted tile start and
+        // end at few distinct positions in lane order, so equal addresses sit in runs of neighbouring lanes -- the first lane of
+        // a run adds the run's length (one shuffle and two votes per address instead of a match over the warp)
+        const bool part = hit && u.w != last_seg;
+        const unsigned pm = __ballot_sync(0xFFFFFFFFu, part);
+        if (pm == 0u) continue;
+        if (part) last_seg = u.w;
+        const uint4 sg = sv.ent[2 * j + 1];   // {segment start, end, posbase lo, hi}: position p lives at index posbase + p
+        const unsigned long long posbase = (unsigned long long)sg.z | ((unsigned long long)sg.w << 32);
+        const uint32_t pa = sg.x > g ? sg.x : g, pb = sg.y < e ? sg.y : e;
+        const uint32_t lane = lane_id();
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const uint32_t p = side ? pb : pa;   // all participants share the segment: equal positions <=> equal addresses
+            const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, p, 1);
+            const bool lead = part && !(lane > 0u && ((pm >> (lane - 1u)) & 1u) && prev == p);
+            const unsigned lm = __ballot_sync(0xFFFFFFFFu, lead);
+            if (lead) {
+                const unsigned stop = (~pm | lm) & ~((2u << lane) - 1u);   // first lane after this one that is not in its run
+                const int run = (stop ? __ffs((int)stop) - 1 : 32) - (int)lane;
+                SD_CHECK(pb >= pa && posbase + p < A.n_positions);
+                atomicAdd(&A.pos_cov[posbase + p], side ? -run : run);
+            }
+        }
+        if (part && tc > 0) {
+            int *tcbase = A.pos_tc + (long long)(posbase + g);   // may point before the segment; only in-range bits are used
+            asm volatile("" : "+l"(tcbase));   // keep it a pointer: each scatter address is then one IMAD.WIDE
+            if (pa == g && pb == e) {
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    uint32_t h = H[k];
+                    while (h) {
+                        SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
+                        atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                        h &= h - 1u;
+                    }
+                }
+            } else {   // the segment holds only part of the read (rare)
+                for (int k = 0; k < W; k++) {
+                    uint32_t h = H[k] & prefix_word(k, (int)(pb - g)) & ~prefix_word(k, (int)(pa - g));
+                    while (h) {
+                        SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
+                        atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                        h &= h - 1u;
+                    }
+                }
+            }
         }
     }
     return tc;
@@ -903,8 +944,7 @@ __device__ __forceinline__ int staged_read(const CountArgs &A, const ReadView &v
 #ifndef SD_CTA_THREADS
 #define SD_CTA_THREADS 256
 #endif
-#define SD_WARP_TRAILER 384u   // per-warp bookkeeping behind the stages
-#define SD_SPAN_VALID 1u       // sd_tile_span flag: g_min / g_end / entries describe every countable read of the tile
+#define SD_WARP_TRAILER 512u   // per-warp bookkeeping behind the stages (at most two stages)
 #ifndef SD_MIN_CTAS
 #define SD_MIN_CTAS(W) ((W) <= 6 ? 4 : ((W) <= 10 ? 3 : 2))   // resident 256-thread CTAs per SM the register budget is tuned for
 #endif
@@ -920,7 +960,6 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
     unsigned char *mine = smem + 128u + (size_t)warp * warp_bytes;
     unsigned char *stages = mine;
     uint64_t *full = reinterpret_cast<uint64_t *>(mine + (size_t)A.n_stages * stage_bytes);   // [n_stages]
-    unsigned long long *s_qoff = reinterpret_cast<unsigned long long *>(mine + (size_t)A.n_stages * stage_bytes + 64u);  // [n_stages]
 
     if (tid < SD_SMEM_STATS) s_stats[tid] = 0u;
     if (lane == 0) {
@@ -932,7 +971,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
     // Tiles are handed out dynamically in chunks of SD_CLAIM consecutive tiles (one atomic per chunk): warps that hit
     // expensive tiles simply claim fewer, so the grid drains evenly, and a warp's consecutive tiles share reference
     // windows and table rows in L1.
-    uint32_t *s_tile = reinterpret_cast<uint32_t *>(mine + (size_t)A.n_stages * stage_bytes + 96u);   // [n_stages] tile held by each stage
+    uint32_t *s_tile = reinterpret_cast<uint32_t *>(mine + (size_t)A.n_stages * stage_bytes + 16u);   // [n_stages] tile held by each stage
     uint32_t claim_next = 0, claim_end = 0;   // lane 0 only
     const uint32_t n_queue = (!STAGED && A.tile_list) ? *A.n_list : A.n_tiles;
     auto claim = [&]() -> uint32_t {          // next tile for this warp, or 0xFFFFFFFF when the queue is empty
@@ -945,75 +984,61 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
         return t < n_queue ? t : 0xFFFFFFFFu;
     };
     // @region tma_issue
-    // A tile is one bulk copy per column.  Lanes 0..4 issue them side by side -- lane c owns column c (records, SEQ, CIGAR,
-    // MP, quality planes) -- so the address arithmetic runs once for all columns instead of once per column on lane 0, which
-    // the other lanes wait for.  The per-lane descriptors live in the warp's shared-memory region (one LDS.128 per tile
-    // instead of five registers per thread).
-    uint4 *s_col = reinterpret_cast<uint4 *>(mine + (size_t)A.n_stages * stage_bytes + 128u);   // [7] {src lo, src hi, stage offset, field | travels << 8}
-    uint32_t *s_nocig = reinterpret_cast<uint32_t *>(mine + (size_t)A.n_stages * stage_bytes + 112u);   // [n_stages] the tile has no CIGAR block
-    uint4 *s_info = reinterpret_cast<uint4 *>(mine + (size_t)A.n_stages * stage_bytes + 256u);   // [n_stages] {g_min, g_end, n entries, staged}
+    // A tile is one bulk copy per column, issued by lanes 0..6 side by side -- lane c owns column c: records, SEQ, CIGAR, MP,
+    // quality planes and, in the staged kernel, the tile's reference window and its annotation entries.  Every lane runs the
+    // same few instructions: two 64-bit loads from a per-tile table (the batch's tile table, or its span table) give the
+    // column's [begin, end) in bytes.  The per-lane constants live in the warp's shared-memory region, and so does what the
+    // lanes found out about the tile (s_meta), which the consumers read after the wait.
+    uint4 *s_col = reinterpret_cast<uint4 *>(mine + (size_t)A.n_stages * stage_bytes + 64u);     // [7][2] {src lo, src hi, table lo, table hi}, {stage offset, end - begin words apart, extra bytes, most bytes}
+    uint4 *s_meta = reinterpret_cast<uint4 *>(mine + (size_t)A.n_stages * stage_bytes + 288u);   // [n_stages][7] {begin lo, begin hi, bytes, copied}
     if (lane < 7u) {
         const unsigned char *src = reinterpret_cast<const unsigned char *>(A.rec);
-        uint32_t dst = 0u, fld = 0u, col = 1u;   // col: does this lane's column travel with the tile at all
-        if (lane == 1) { src = reinterpret_cast<const unsigned char *>(A.seq); dst = A.cap_rec; fld = 0u; }
-        if (lane == 2) { src = reinterpret_cast<const unsigned char *>(A.cigar); dst = A.cap_rec + A.cap_seq; fld = 2u; }
-        if (lane == 3) { src = reinterpret_cast<const unsigned char *>(A.mp); dst = A.cap_rec + A.cap_seq + A.cap_cig; fld = 3u; col = A.mp != nullptr; }
-        if (lane == 4) { src = A.qual; dst = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp; fld = 1u; col = QB > 0; }
-        if (lane == 5) { src = reinterpret_cast<const unsigned char *>(A.refm); dst = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual; col = A.spans != nullptr; }
-        if (lane == 6) { src = reinterpret_cast<const unsigned char *>(A.ment); dst = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual + A.cap_win; col = A.spans != nullptr; }
-        const unsigned long long a = reinterpret_cast<unsigned long long>(src);
-        s_col[lane] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), dst, fld | (col << 8));
+        const unsigned long long *tbl = reinterpret_cast<const unsigned long long *>(A.tiles);   // begin of tile t at tbl[4 t], end `apart` words on
+        uint32_t dst = 0u, apart = 4u, extra = 0u, most = 0xFFFFFFFFu;
+        bool col = true;   // does this lane's column travel with the tile at all
+        if (lane == 1) { src = reinterpret_cast<const unsigned char *>(A.seq); dst = A.cap_rec; }
+        if (lane == 2) { src = reinterpret_cast<const unsigned char *>(A.cigar); dst = A.cap_rec + A.cap_seq; tbl += 2; }
+        if (lane == 3) { src = reinterpret_cast<const unsigned char *>(A.mp); dst = A.cap_rec + A.cap_seq + A.cap_cig; tbl += 3; col = A.mp != nullptr; }
+        if (lane == 4) { src = A.qual; dst = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp; tbl += 1; col = QB > 0; }
+        if (lane >= 5) {
+            col = STAGED;
+            tbl = reinterpret_cast<const unsigned long long *>(STAGED ? (const void *)A.spans : (const void *)A.tiles);
+            apart = 1u;
+        }
+        if (lane == 5) { src = reinterpret_cast<const unsigned char *>(A.refm); dst = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual; extra = 16u * W; most = A.cap_win; }
+        if (lane == 6) { src = reinterpret_cast<const unsigned char *>(A.ment); dst = A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual + A.cap_win; tbl += 2; most = A.cap_ent; }
+        if (!col) most = 0u;
+        const unsigned long long a = reinterpret_cast<unsigned long long>(src), t = reinterpret_cast<unsigned long long>(tbl);
+        s_col[2 * lane] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)t, (uint32_t)(t >> 32));
+        s_col[2 * lane + 1] = make_uint4(dst, apart, extra, most);
     }
     __syncwarp();
     auto issue = [&](uint64_t tile, uint32_t stage) {   // lanes 0..6 together
         unsigned char *base = stages + (size_t)stage * stage_bytes;
-        const uint4 cd = s_col[lane];
-        const unsigned char *my_src = reinterpret_cast<const unsigned char *>((unsigned long long)cd.x | ((unsigned long long)cd.y << 32));
-        const uint32_t my_dst = cd.z, my_fld = cd.w & 0xFFu;
-        const bool my_col = (cd.w >> 8) != 0u;
-        unsigned long long off0, off1;
-        if (lane < 5u) {
-            const unsigned long long *tp = reinterpret_cast<const unsigned long long *>(A.tiles + tile);
-            off0 = tp[my_fld];
-            off1 = tp[4u + my_fld];
-            if (lane == 0) {
-                off0 = tile * (SD_TILE_READS * (unsigned long long)sizeof(sd_read_rec));
-                off1 = off0 + SD_TILE_READS * (unsigned long long)sizeof(sd_read_rec);
-            }
-            if (lane == 2) s_nocig[stage] = (off1 == off0) ? 1u : 0u;
-            if (lane == 4) {
-                s_qoff[stage] = off0;
-                if (QB == 0 && A.qual_prefetch) {   // byte form: pull the tile's base qualities into L2 ahead of use
-                    const uint32_t b_q = (uint32_t)(off1 - off0) & ~15u;
-                    if (b_q) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.qual + off0), "r"(b_q) : "memory");
-                }
-            }
-        } else {
-            // the tile's reference window (both strands side by side) and the annotation entries that can overlap its reads,
-            // located by the span descriptor the batch carries for it: two more bulk copies, no dependent lookup
-            off0 = off1 = 0ull;
-            if (my_col) {
-                const uint4 sp = __ldg(A.spans + tile);
-                const uint32_t w0 = sp.x >> 5, n_ent = sp.w & 0xFFFFu;
-                // words w0 .. word of (g_end - 1), plus the W words a read starting there still loads
-                const uint32_t nw = sp.y > sp.x ? ((sp.y - 1u) >> 5) - w0 + 1u + (uint32_t)W : 0u;
-                const bool ok = ((sp.w >> 16) & SD_SPAN_VALID) && nw * 16u <= A.cap_win && n_ent * 32u <= A.cap_ent &&
-                                (unsigned long long)w0 + nw <= A.n_refm && (unsigned long long)sp.z + n_ent <= A.n_ment;
-                if (lane == 5) {
-                    s_info[stage] = make_uint4(sp.x, sp.y, n_ent, ok ? 1u : 0u);
-                    off0 = (unsigned long long)w0 * 16ull;
-                    off1 = off0 + (ok ? nw * 16u : 0u);
-                } else {
-                    off0 = (unsigned long long)sp.z * 32ull;
-                    off1 = off0 + (ok ? n_ent * 32u : 0u);
-                }
-            } else if (lane == 5) s_info[stage] = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 c0 = s_col[2 * lane], c1 = s_col[2 * lane + 1];
+        const unsigned char *my_src = reinterpret_cast<const unsigned char *>((unsigned long long)c0.x | ((unsigned long long)c0.y << 32));
+        const unsigned long long *tp = reinterpret_cast<const unsigned long long *>((unsigned long long)c0.z | ((unsigned long long)c0.w << 32)) + 4ull * tile;
+        unsigned long long off0 = __ldg(tp), off1 = __ldg(tp + c1.y);
+        if (lane == 0) {
+            off0 = tile * (SD_TILE_READS * (unsigned long long)sizeof(sd_read_rec));
+            off1 = off0 + SD_TILE_READS * (unsigned long long)sizeof(sd_read_rec);
         }
-        const uint32_t bytes = my_col ? (uint32_t)(off1 - off0) : 0u;
+        // an empty column stays empty; the reference window gets the W words a read starting in its last word still loads
+        unsigned long long want = off1 > off0 ? off1 - off0 + c1.z : 0ull;
+        // the span table marks a tile whose reads are spread too widely with an impossible size; then neither of the two
+        // span-driven copies is made and the consumers see `copied` = 0 for them
+        const unsigned fit = __ballot_sync(0x7Fu, want <= (unsigned long long)c1.w);
+        const bool copied = (fit >> lane) & 1u & ((lane < 5u) | ((fit >> 5) & (fit >> 6) & 1u));
+        const uint32_t bytes = copied ? (uint32_t)want : 0u;
+        s_meta[7u * stage + lane] = make_uint4((uint32_t)off0, (uint32_t)(off0 >> 32), bytes, copied ? 1u : 0u);
+        if (QB == 0 && A.qual_prefetch && lane == 4) {   // byte form: pull the tile's base qualities into L2 ahead of use
+            const uint32_t b_q = (uint32_t)(off1 - off0) & ~15u;
+            if (b_q) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.qual + off0), "r"(b_q) : "memory");
+        }
         const uint32_t total = __reduce_add_sync(0x7Fu, bytes);
         if (lane == 0) mbar_arrive_expect_tx(&full[stage], total);
         __syncwarp(0x7Fu);
-        if (bytes) bulk_g2s(base + my_dst, my_src + off0, bytes, &full[stage]);
+        if (bytes) bulk_g2s(base + c1.x, my_src + off0, bytes, &full[stage]);
     };
 
     for (uint32_t s = 0; s < A.n_stages; s++) {
@@ -1028,14 +1053,25 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
     __syncwarp();
 
     // @region tile_wait_rec
-    uint32_t my_counted = 0, my_tc_total = 0;   // per-lane run totals (a lane sees far fewer than 2^32 conversions per launch)
+    uint32_t my_tc_total = 0;   // per-lane run total (a lane sees far fewer than 2^32 conversions per launch)
+    uint32_t cnt_a = 0, cnt_b = 0, cnt_tiles = 0;   // packed per-lane run counters, see filter_step
+    auto flush_counts = [&]() {
+        const uint32_t f[6] = {cnt_a & 1023u, (cnt_a >> 10) & 1023u, cnt_a >> 20, cnt_b & 1023u, (cnt_b >> 10) & 1023u, cnt_b >> 20};
+        const int slot[6] = {SD_S_MAPPED, SD_S_FILTERED, SD_S_COUNTED, SD_S_UNMAPPED, SD_S_MQFILTERED, SD_S_IDFILTERED};
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, f[k]);
+            if (lane == 0 && t) atomicAdd(&s_stats[slot[k]], t);
+        }
+        cnt_a = cnt_b = cnt_tiles = 0u;
+    };
     uint32_t stage = 0, phase = 0;
     for (;;) {
         const uint64_t tile = s_tile[stage];
         if (tile == 0xFFFFFFFFull) break;   // the queue ran dry (claims are monotonic: later stages are empty too)
         mbar_wait(&full[stage], phase);
-        const uint4 info = STAGED ? s_info[stage] : make_uint4(0u, 0u, 0u, 0u);   // {g_min, g_end, n entries, staged}
-        if (STAGED && info.w == 0u) {
+        const uint4 m_win = STAGED ? s_meta[7u * stage + 5u] : make_uint4(0u, 0u, 0u, 0u);   // {begin lo, begin hi, bytes, copied}
+        if (STAGED && m_win.w == 0u) {
             // The tile's reads are spread over more of the genome than a stage holds (unsorted input, a tile that crosses
             // chromosomes): leave it to the plain kernel that follows this launch.
             if (lane == 0) A.leftover[atomicAdd(A.n_leftover, 1u)] = (uint32_t)tile;
@@ -1081,56 +1117,33 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
 
         // @region filter
         const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu, ref = rmf & 0xFFFFu;
-        // filter.py:235-256 on a record that is not tile padding -> does it go on to be counted; the run counters are added here
+        // filter.py:235-256 on a record that is not tile padding -> does it go on to be counted.  The run counters are kept per
+        // lane as 10-bit fields of two registers (cnt_a: mapped | kept | counted, cnt_b: unmapped | MQ | identity) and added up
+        // by flush_counts() before a field can overflow -- a handful of integer instructions per read instead of six warp
+        // votes and as many shared-memory atomics per tile.
         auto filter_step = [&](bool go) -> bool {
-            // Two forms of the same step, chosen per window size by measurement (the kernel is bound by instruction issue, and
-            // which form schedules better differs: votes at W = 4, 1.604 vs 1.671 ms at 100 bp; per-read atomics from W = 6
-            // on, 1.83 vs 2.01 ms at 150 bp).
-            constexpr bool VOTE_COUNTERS = (W <= 4);
-            if (!VOTE_COUNTERS && go && A.filter_on) {
-                const bool primary = !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
-                const bool unmapped = (flags & SD_F_UNMAPPED) != 0;
-                if (primary) atomicAdd(&s_stats[unmapped ? SD_S_UNMAPPED : SD_S_MAPPED], 1u);
-                if (unmapped) go = false;
-                else if ((int)mapq < A.filter_mq) { atomicAdd(&s_stats[SD_S_MQFILTERED], 1u); go = false; }
-                else if (xi < A.filter_min_identity) { atomicAdd(&s_stats[SD_S_IDFILTERED], 1u); go = false; }
-                else if (A.filter_max_nm > -1 && (int)nm > A.filter_max_nm) { atomicAdd(&s_stats[SD_S_NMFILTERED], 1u); go = false; }
-                else if (primary) atomicAdd(&s_stats[SD_S_FILTERED], 1u);
-            }
-            if (VOTE_COUNTERS && A.filter_on) {
-                // the run counters are warp totals (one vote each, added by lane 0) instead of one shared-memory atomic per
-                // read and counter
+            if (A.filter_on) {
                 const bool primary = go && !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
                 const bool mapped = go && !(flags & SD_F_UNMAPPED);
                 const bool f_mq = mapped && (int)mapq < A.filter_mq;
                 const bool f_id = mapped && !f_mq && xi < A.filter_min_identity;
                 const bool f_nm = mapped && !f_mq && !f_id && A.filter_max_nm > -1 && (int)nm > A.filter_max_nm;
                 go = mapped && !f_mq && !f_id && !f_nm;
-                const uint32_t b_map = __ballot_sync(0xFFFFFFFFu, primary && mapped), b_unm = __ballot_sync(0xFFFFFFFFu, primary && !mapped);
-                const uint32_t b_mq = __ballot_sync(0xFFFFFFFFu, f_mq), b_id = __ballot_sync(0xFFFFFFFFu, f_id);
-                const uint32_t b_nm = __ballot_sync(0xFFFFFFFFu, f_nm), b_ok = __ballot_sync(0xFFFFFFFFu, go && primary);
-                if (lane == 0) {   // one conflict-free shared atomic per non-zero counter and tile
-                    if (b_map) atomicAdd(&s_stats[SD_S_MAPPED], (uint32_t)__popc(b_map));
-                    if (b_ok) atomicAdd(&s_stats[SD_S_FILTERED], (uint32_t)__popc(b_ok));
-                    if (b_unm | b_mq | b_id | b_nm) {
-                        if (b_unm) atomicAdd(&s_stats[SD_S_UNMAPPED], (uint32_t)__popc(b_unm));
-                        if (b_mq) atomicAdd(&s_stats[SD_S_MQFILTERED], (uint32_t)__popc(b_mq));
-                        if (b_id) atomicAdd(&s_stats[SD_S_IDFILTERED], (uint32_t)__popc(b_id));
-                        if (b_nm) atomicAdd(&s_stats[SD_S_NMFILTERED], (uint32_t)__popc(b_nm));
-                    }
-                }
+                cnt_a += (uint32_t)(primary && mapped) | ((uint32_t)(go && primary) << 10);
+                cnt_b += (uint32_t)(primary && !mapped) | ((uint32_t)f_mq << 10) | ((uint32_t)f_id << 20);
+                if (f_nm) atomicAdd(&s_stats[SD_S_NMFILTERED], 1u);   // off by default
             }
             return go;
         };
         // A tile without a CIGAR block: every record with one op is one M block of l_seq bases (sd_batch: plain-match tiles
         // need not carry the column at all)
-        const bool nocig = s_nocig[stage] != 0u;
+        const bool nocig = s_meta[7u * stage + 2u].z == 0u;
         // could this record be counted at all, whatever the filter says
         const bool cand = !(flags & (SD_F_PAD | SD_F_UNMAPPED | SD_F_SKIP)) && ref < A.n_chrom && !(nocig && ncig > 1u);
         const uint32_t cig0 = nocig ? (lseq << 4) : (ncig ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq)[cig_row] : 0u);
         // Deep coverage: a coordinate-sorted tile whose 32 reads start within a few positions would send dozens of atomics to
         // the same addresses; such tiles (warp-uniform test on the tile's first and last record) aggregate them in the warp.
-        const bool dense_tile = __shfl_sync(0xFFFFFFFFu, rmf & 0xFFFFu, 0) == __shfl_sync(0xFFFFFFFFu, rmf & 0xFFFFu, 31) &&
+        const bool dense_tile = !STAGED && __shfl_sync(0xFFFFFFFFu, rmf & 0xFFFFu, 0) == __shfl_sync(0xFFFFFFFFu, rmf & 0xFFFFu, 31) &&
                                 (uint32_t)(__shfl_sync(0xFFFFFFFFu, pos, 31) - __shfl_sync(0xFFFFFFFFu, pos, 0)) <= SD_DENSE_SPAN;
         int tc = 0;
         bool bad = false;
@@ -1146,7 +1159,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
             const bool placed = cand && pos >= 0 && (uint32_t)pos < clen;
             ReadView v;
             v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (SB == 2 ? 2u : 4u) * lane;
-            v.qual = QB > 0 ? base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + 4u * QB * lane : A.qual + s_qoff[stage] + qs;
+            v.qual = QB > 0 ? base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + 4u * QB * lane : A.qual + ((unsigned long long)s_meta[7u * stage + 4u].x | ((unsigned long long)s_meta[7u * stage + 4u].y << 32)) + qs;
             v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + cig_row;
             v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
             v.ncig = placed ? ncig : 0u;
@@ -1171,21 +1184,25 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
                 for (uint32_t i = 0; i < nmp; i++)
                     if ((v.mp[i] >> 16) >= 32u * W) fits = false;
             }
-            // A read that needs the per-base path (wider than the register window), or lies outside the span its tile declared
-            // (honest spans contain every read), sends the whole tile to the plain kernel -- before anything was counted.
-            if (__any_sync(0xFFFFFFFFu, placed && !(fits && v.g >= info.x && v.g + reflen <= info.y))) {
+            // First window word of this read among the staged ones.  The span table is made for this batch (sd_tile_spans), so
+            // the read lies inside; a table that lies gets a wrong count but no wild access (or the tile is left over).
+            const uint32_t w0 = (uint32_t)(((unsigned long long)m_win.x | ((unsigned long long)m_win.y << 32)) >> 4);
+            const uint32_t dword = (v.g >> 5) - w0;
+            // A read that needs the per-base path (wider than the register window) sends the whole tile to the plain kernel --
+            // before anything was counted.
+            if (__any_sync(0xFFFFFFFFu, placed && !(fits && dword < (m_win.z >> 4) && dword + (uint32_t)W < (m_win.z >> 4)))) {
                 if (lane == 0) A.leftover[atomicAdd(A.n_leftover, 1u)] = (uint32_t)tile;
             } else {
                 const bool live = filter_step(!(flags & SD_F_PAD)) && placed;
-                if (live) my_counted++;
+                cnt_a += (uint32_t)live << 20;
                 v.lseq = live ? lseq : 0u;
                 v.nmp = live ? nmp : 0u;
                 v.span = live ? (int)reflen : 0;
                 StageView sv;
                 sv.win = reinterpret_cast<const uint4 *>(base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual);
                 sv.ent = reinterpret_cast<const uint4 *>(base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + A.cap_qual + A.cap_win);
-                sv.w0 = info.x >> 5;
-                sv.n_ent = info.z;
+                sv.d = live ? dword : 0u;
+                sv.n_ent = s_meta[7u * stage + 6u].z >> 5;
                 tc = uni_simple ? staged_read<W, true, SB, QB>(A, v, B, mapq, dense_tile, live, sv, bad)
                                 : staged_read<W, false, SB, QB>(A, v, B, mapq, dense_tile, live, sv, bad);
                 if (!live) tc = 0;
@@ -1199,7 +1216,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
                 if (pos >= 0 && (uint32_t)pos < clen) {
                     ReadView v;
                     v.seq = reinterpret_cast<const uint32_t *>(base + A.cap_rec) + (SB == 2 ? 2u : 4u) * lane;
-                    v.qual = QB > 0 ? base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + 4u * QB * lane : A.qual + s_qoff[stage] + qs;
+                    v.qual = QB > 0 ? base + A.cap_rec + A.cap_seq + A.cap_cig + A.cap_mp + 4u * QB * lane : A.qual + ((unsigned long long)s_meta[7u * stage + 4u].x | ((unsigned long long)s_meta[7u * stage + 4u].y << 32)) + qs;
                     v.cig = reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq) + cig_row;
                     v.mp = A.mp ? reinterpret_cast<const uint32_t *>(base + A.cap_rec + A.cap_seq + A.cap_cig) + ms : nullptr;
                     v.lseq = lseq;
@@ -1227,7 +1244,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
                         for (uint32_t i = 0; i < nmp; i++)
                             if ((v.mp[i] >> 16) >= 32u * W) fits = false;
                     }
-                    my_counted++;
+                    cnt_a += 1u << 20;
                     if (fits) {
                         tc = uni_simple ? fast_read<W, true, SB, QB>(A, v, B, mapq, dense_tile, bad) : fast_read<W, false, SB, QB>(A, v, B, mapq, dense_tile, bad);
                     } else {
@@ -1241,6 +1258,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
         }
         if (bad) atomicAdd(&A.stats[SD_S_MP_DISAGREE], 1ull);   // rare: straight to the global counter
         my_tc_total += (uint32_t)tc;
+        if (++cnt_tiles == 1000u) flush_counts();
         if (A.read_tc) A.read_tc[tile * SD_TILE_READS + lane] = (uint8_t)(tc > 255 ? 255 : tc);
         }
 
@@ -1262,15 +1280,12 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
 
     // @region kernel_tail
     // flush run-level counters
-    my_counted = __reduce_add_sync(0xFFFFFFFFu, my_counted);
+    flush_counts();
     unsigned long long tc_total = my_tc_total;
     for (int d = 16; d > 0; d >>= 1) tc_total += __shfl_xor_sync(0xFFFFFFFFu, tc_total, d);
-    if (lane == 0) {
-        if (my_counted) atomicAdd(&A.stats[SD_S_COUNTED], (unsigned long long)my_counted);
-        if (tc_total) atomicAdd(&A.stats[SD_S_TC_TOTAL], tc_total);
-    }
+    if (lane == 0 && tc_total) atomicAdd(&A.stats[SD_S_TC_TOTAL], tc_total);
     __syncthreads();
-    if (tid < 6 && s_stats[tid]) atomicAdd(&A.stats[tid], (unsigned long long)s_stats[tid]);
+    if (tid < 7 && s_stats[tid]) atomicAdd(&A.stats[tid], (unsigned long long)s_stats[tid]);
 }
 
 
@@ -1320,7 +1335,7 @@ static int launch_one(sd_ctx *ctx, CountArgs &A, cudaStream_t stream) {
         n_stages = last.n_stages; warps = last.warps; smem = last.smem; per_sm = last.per_sm;
     } else if ((rc = plan(1, warps, smem, per_sm)) != SD_OK) {
         return rc;
-    } else if (forced_stages >= 1 && forced_stages <= 4) {
+    } else if (forced_stages >= 1 && forced_stages <= 2) {
         n_stages = (uint32_t)forced_stages;
         if ((rc = plan(n_stages, warps, smem, per_sm)) != SD_OK) return rc;
     } else {

@@ -77,7 +77,11 @@ struct sd_ctx {
     void *d_filter_scratch = nullptr;
     size_t filter_scratch_cap = 0;
 
-    // staging for sd_count_host
+    // XI dictionary of the wire batch being counted (sd_count_wire)
+    float *d_xi_dict = nullptr;
+    uint32_t xi_dict_cap = 0;
+
+    // staging for sd_count_host / sd_count_wire
     void *d_stage[2] = {nullptr, nullptr};
     size_t stage_cap = 0;
 };

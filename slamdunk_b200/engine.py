@@ -337,7 +337,7 @@ class CountEngine(object):
         device batch; redo after set_reference / set_utrs (stale descriptors are ignored by the library, not misused)."""
         nt = int(dbatch.batch.n_tiles)
         with torch.cuda.stream(self.stream):
-            spans = torch.empty(max(1, nt) * 16, dtype=torch.uint8, device=self.device)
+            spans = torch.empty(max(1, nt) * 32, dtype=torch.uint8, device=self.device)
         self._chk(self.lib.sd_tile_spans(self.ctx, ctypes.byref(dbatch.batch), _t_ptr(spans)), "sd_tile_spans")
         dbatch.spans_tensor = spans      # owned by this DeviceBatch object (the tensors dict may be shared between views)
         dbatch.spans_key = (self.ctx.value, self._epoch)
@@ -357,6 +357,10 @@ class CountEngine(object):
 
     def count_host(self, hbatch: L.Batch, params: L.Params):
         self._chk(self.lib.sd_count_host(self.ctx, ctypes.byref(hbatch), ctypes.byref(params)), "sd_count_host")
+
+    def count_wire(self, wire: L.Wire, params: L.Params):
+        """sd_count_wire: a packed host batch (sd_wire) -> chunked copy, expansion on the device, count.  Synchronous."""
+        self._chk(self.lib.sd_count_wire(self.ctx, ctypes.byref(wire), ctypes.byref(params)), "sd_count_wire")
 
     def finalize(self):
         self._chk(self.lib.sd_finalize(self.ctx), "sd_finalize")

@@ -376,3 +376,92 @@ def batch_to_host(db: DeviceBatch, eng=None):
 def host_batch_bytes(host: dict) -> int:
     """bytes sd_count_host copies to the device for this host batch"""
     return sum(t.numel() * t.element_size() for t in host.values() if t is not None)
+
+
+class HostWire(object):
+    """Pinned host copy of a batch in the wire form (sd_wire): what sd_decode_bam hands `count` and sd_count_wire sends over
+    PCIe.  `wire` holds the host pointers, `host` keeps the buffers alive."""
+
+    def __init__(self, wire: L.Wire, host: dict):
+        self.wire = wire
+        self.host = host
+
+    def h2d_bytes(self, params: L.Params) -> int:
+        """bytes sd_count_wire copies to the device for a call with these parameters"""
+        h = self.host
+        use_mp = params.mismatch_source != L.SD_MISMATCH_CIGAR
+        cols = ["tiles", "pos16", "mqf", "seq", "qual", "var"]
+        if params.filter_on:
+            cols.append("xi16" if h.get("xi16") is not None else "xi32")
+            if params.filter_max_nm > -1:
+                cols.append("nm16")
+        if use_mp:
+            cols += ["nmp16", "mp"]
+        n = sum(h[c].numel() * h[c].element_size() for c in cols if h.get(c) is not None)
+        if params.filter_on and h.get("xi16") is not None:
+            n += h["xi_dict"].numel() * 4
+        return int(n)
+
+
+def batch_to_wire(db: DeviceBatch, eng) -> HostWire:
+    """Wire form of a device batch whose SEQ column is 2-bit (to_seq2) and whose qualities are bytes: packed on the device
+    (sd_wire_plan / sd_wire_fill; XI dictionary with torch.unique), then copied to page-locked host memory."""
+    dev = db.tensors["rec"].device
+    nt = int(db.batch.n_tiles)
+    tl = db.tensors["tiles"].view(torch.int64)
+    n_q = int(tl[4 * nt + 1].item()) if nt else 0
+    bits = ctypes.c_uint32(8)
+    dict16 = (ctypes.c_uint8 * 16)()
+    eng._chk(eng.lib.sd_qual_dict(eng.ctx, db.tensors["qual"].data_ptr(), n_q, ctypes.byref(bits), dict16), "sd_qual_dict")
+    qb = int(bits.value)
+    with torch.cuda.stream(eng.stream):
+        wt = torch.zeros((nt + 1) * 32, dtype=torch.uint8, device=dev)
+    eng.stream.synchronize()
+    totals = (ctypes.c_uint64 * 4)()
+    eng._chk(eng.lib.sd_wire_plan(eng.ctx, ctypes.byref(db.batch), wt.data_ptr(), totals), "sd_wire_plan")
+    n_bases, n_var, n_mp, max_cig = (int(x) for x in totals)
+    has_mp = bool(db.batch.mp)
+    with torch.cuda.stream(eng.stream):
+        xi_bits = db.tensors["rec"].view(torch.int32).view(-1, 5)[:, 2].contiguous()
+        xdict, inv = torch.unique(xi_bits, return_inverse=True)
+        small = xdict.numel() <= 65536
+        dv = {
+            "tiles": wt,
+            "pos16": torch.zeros(nt * 32, dtype=torch.int16, device=dev),
+            "mqf": torch.zeros(nt * 32, dtype=torch.int16, device=dev),
+            "xi16": inv.to(torch.int16) if small else None,        # codes 0..65535 wrap into int16 bit patterns
+            "xi32": None if small else torch.zeros(nt * 32, dtype=torch.int32, device=dev),
+            "nm16": torch.zeros(nt * 32, dtype=torch.int16, device=dev),
+            "nmp16": torch.zeros(nt * 32, dtype=torch.int16, device=dev) if has_mp else None,
+            "seq": torch.zeros(n_bases // 4 + 16, dtype=torch.uint8, device=dev),
+            "qual": torch.zeros(n_bases * qb // 8 + 16, dtype=torch.uint8, device=dev),
+            "var": torch.zeros(n_var + 4, dtype=torch.int32, device=dev),
+            "mp": torch.zeros(n_mp + 4, dtype=torch.int32, device=dev) if has_mp else None,
+            "xi_dict": xdict.contiguous() if small else None,
+        }
+        if small and xdict.numel() > 32768:
+            dv["xi16"] = (inv & 0xFFFF).to(torch.int32).to(torch.int16)
+    eng.stream.synchronize()
+    w = L.Wire()
+    ptr = lambda t: t.data_ptr() if t is not None else None      # noqa: E731
+    w.tiles, w.pos16, w.mqf, w.xi16, w.nm16, w.nmp16 = ptr(dv["tiles"]), ptr(dv["pos16"]), ptr(dv["mqf"]), ptr(dv["xi16"]), ptr(dv["nm16"]), ptr(dv["nmp16"])
+    w.xi32, w.seq, w.qual, w.var, w.mp = ptr(dv["xi32"]), ptr(dv["seq"]), ptr(dv["qual"]), ptr(dv["var"]), ptr(dv["mp"])
+    w.qual_bits = qb
+    for i in range(16):
+        w.qual_dict[i] = dict16[i]
+    eng._chk(eng.lib.sd_wire_fill(eng.ctx, ctypes.byref(db.batch), ptr(dv["xi16"]), ctypes.byref(w)), "sd_wire_fill")
+    w.max_tile_cig = max_cig
+    host = {}
+    for k, t in dv.items():
+        if t is None:
+            host[k] = None
+            continue
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        host[k] = h
+    hp = lambda k: host[k].data_ptr() if host[k] is not None else None      # noqa: E731
+    w.tiles, w.pos16, w.mqf, w.xi16, w.nm16, w.nmp16 = hp("tiles"), hp("pos16"), hp("mqf"), hp("xi16"), hp("nm16"), hp("nmp16")
+    w.xi32, w.seq, w.qual, w.var, w.mp = hp("xi32"), hp("seq"), hp("qual"), hp("var"), hp("mp")
+    w.xi_dict = hp("xi_dict")
+    w.n_xi_dict = int(host["xi_dict"].numel()) if host["xi_dict"] is not None else 0
+    return HostWire(w, host)

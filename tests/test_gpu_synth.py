@@ -499,3 +499,40 @@ def test_stale_span_descriptors_are_ignored():
     eng.synchronize()
     assert torch.equal(got, eng.counters)
     eng.close()
+
+
+@pytest.mark.parametrize("mode,sorted_,qvals", [(0, True, 3), (2, True, 3), (1, False, 3), (0, False, 11), (2, True, 40)])
+def test_wire_form_counts_like_the_device_batch(mode, sorted_, qvals):
+    """sd_wire_plan / sd_wire_fill pack a device batch into the wire form, sd_count_wire expands it on the device and counts it:
+    same outputs as counting the device batch directly -- plain-match tiles without l_seq / CIGAR, mixed tiles, tiles whose
+    positions need 32 bits or that cross chromosomes (mapper order), 2-bit / 4-bit / byte qualities, with and without the
+    filter columns and the MP column."""
+    import torch
+    from slamdunk_b200.engine import make_params
+    from slamdunk_b200.synth import batch_to_wire, to_seq2
+    eng, wl = _setup(genome_bp=2_000_000, n_utr=900, seed=21)
+    p = wl.params(seed=8, first_read=0, n_reads=120_000 - 7, read_len=100 if qvals == 3 else 77, frac_softclip=0.1, frac_indel=0.08,
+                  frac_antisense=0.1)
+    db, _ = wl.generate(p, want_mp=True, coordinate_sorted=sorted_)
+    if qvals != 3:      # more distinct qualities than the generator makes: 4-bit codes / plain bytes on the wire
+        g = torch.Generator(device=eng.device).manual_seed(5)
+        db.tensors["qual"].copy_(torch.randint(0, qvals, db.tensors["qual"].shape, generator=g, device=eng.device, dtype=torch.uint8) + 10)
+    db2 = to_seq2(db, eng)
+    hw = batch_to_wire(db2, eng)
+    assert hw.wire.qual_bits == {3: 2, 11: 4, 40: 8}[qvals]
+    for filt in (False, True):
+        params = make_params(27, 1, mode, filter_on=filt, filter_mq=2, filter_min_identity=0.95, filter_max_nm=3 if filt else -1)
+        eng.reset_outputs()
+        eng.count(db2, params)
+        eng.finalize()
+        eng.synchronize()
+        want = (eng.counters.clone(), eng.pos_cov.clone(), eng.pos_tc.clone(), eng.stats.clone())
+        eng.reset_outputs()
+        eng.count_wire(hw.wire, params)
+        eng.finalize()
+        eng.synchronize()
+        for a, b in zip(want, (eng.counters, eng.pos_cov, eng.pos_tc, eng.stats)):
+            assert torch.equal(a, b)
+        assert int(want[3][6]) > 50_000
+        assert hw.h2d_bytes(params) < 0.8 * sum(t.numel() * t.element_size() for t in db2.tensors.values() if t is not None)
+    eng.close()
