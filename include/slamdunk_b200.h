@@ -272,6 +272,8 @@ int sd_finalize(sd_ctx *ctx);
 int sd_tcontent(sd_ctx *ctx, int64_t *d_tcontent);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t sd_launch_count(const sd_ctx *ctx);
+/* Tiles of the most recent sd_count that the staged kernel handed on to the plain one (diagnostic; waits for the stream). */
+int64_t sd_last_leftover_tiles(sd_ctx *ctx);
 /* Duration of the most recent sd_count kernel on its stream (CUDA events), ms; <0 if none. */
 float sd_last_kernel_ms(sd_ctx *ctx);
 

@@ -140,6 +140,7 @@ PROTOTYPES = {
     "sd_finalize": (ctypes.c_int, [_VP]),
     "sd_tcontent": (ctypes.c_int, [_VP, _VP]),
     "sd_launch_count": (ctypes.c_int64, [_VP]),
+    "sd_last_leftover_tiles": (ctypes.c_int64, [_VP]),
     "sd_last_kernel_ms": (ctypes.c_float, [_VP]),
     "sd_filter": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params), _VP, _VP, _VP, _VP, _VP,
                                  ctypes.c_uint32, _VP, _VP, _VP]),

@@ -671,6 +671,15 @@ extern "C" float sd_last_kernel_ms(sd_ctx *ctx) {
 
 extern "C" int64_t sd_launch_count(const sd_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int64_t sd_last_leftover_tiles(sd_ctx *ctx) {
+    if (!ctx || !ctx->d_tile_counter) return -1;
+    cudaSetDevice(ctx->device);
+    unsigned int n = 0;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(&n, ctx->d_tile_counter + 2, sizeof n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)n;
+}
+
 // Host batch -> device in chunks of whole tiles, double buffered: the copy of chunk i+1 overlaps the
 // kernel of chunk i.  One staging allocation per buffer holds rec | seq | qual | cigar | mp | tiles.
 extern "C" int sd_count_host(sd_ctx *ctx, const sd_batch *hb, const sd_params *params) {

@@ -330,6 +330,21 @@ class CountEngine(object):
         self._chk(self.lib.sd_bind_outputs(self.ctx, _t_ptr(self.counters), _t_ptr(self.pos_cov), _t_ptr(self.pos_tc),
                                            _t_ptr(self.stats)), "sd_bind_outputs")
 
+    def new_output_set(self):
+        """A second (third ...) set of output tensors for the current annotation: (counters, pos_cov, pos_tc, stats, tcontent).
+        bind_output_set() makes one of them the target of the next counts (and zero-fills it)."""
+        with torch.cuda.stream(self.stream):
+            return (torch.empty(max(1, self.n_utr) * L.SD_NCOUNTER, dtype=torch.int64, device=self.device),
+                    torch.empty(max(1, self.n_positions), dtype=torch.int32, device=self.device),
+                    torch.empty(max(1, self.n_positions), dtype=torch.int32, device=self.device),
+                    torch.empty(L.SD_NSTAT, dtype=torch.int64, device=self.device),
+                    torch.zeros(max(1, self.n_utr), dtype=torch.int64, device=self.device))
+
+    def bind_output_set(self, outs):
+        self.counters, self.pos_cov, self.pos_tc, self.stats, self.tcontent = outs
+        self._chk(self.lib.sd_bind_outputs(self.ctx, _t_ptr(self.counters), _t_ptr(self.pos_cov), _t_ptr(self.pos_tc),
+                                           _t_ptr(self.stats)), "sd_bind_outputs")
+
     # -- the hot path ------------------------------------------------------------------
     def attach_spans(self, dbatch: DeviceBatch):
         """Per-tile span descriptors (sd_tile_spans) for the reference and annotation this engine holds: with them the count
@@ -368,6 +383,9 @@ class CountEngine(object):
 
     def last_kernel_ms(self) -> float:
         return float(self.lib.sd_last_kernel_ms(self.ctx))
+
+    def leftover_tiles(self) -> int:
+        return int(self.lib.sd_last_leftover_tiles(self.ctx))
 
     def launch_count(self) -> int:
         return int(self.lib.sd_launch_count(self.ctx))
