@@ -1,30 +1,43 @@
 #!/usr/bin/env python
 """bench.py -- reads/s of the `slamdunk count` hot path (filter + T>C scan + UTR reduce) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--reads R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload cfg2|cfg3|cfg4|cfg5]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-Workload: BASELINE.json configs[1] ("cfg2"): synthetic 50 M single-end 100 bp SLAM-seq reads over
-20 000 UTRs on a ~100 Mb, 21-contig genome, 2.5 % T>C per reference T,
-generated on the device from a counter-based RNG.  A step = one pass of the hot path over the
-whole batch: zero the outputs, sd_count (filter predicates + conversion scan + interval join +
-per-UTR / per-position reduction), sd_finalize (coverage scan) + sd_tcontent and, for N > 1, one
-NCCL all-reduce of the int64 per-UTR counter table.  Multi-GPU runs are weak-scaling: every rank
-owns a contiguous genome region (UTR-owner sharding) and counts R reads placed there.
+Workloads (BASELINE.json `configs`, recipes in SURVEY.md section 8d), all generated on the device from a
+counter-based RNG keyed by (seed, read index):
 
-One JSON line on stdout (rank 0).  `value` is device-resident throughput, `e2e` is the same work
-through sd_count_host from pinned HOST buffers (H2D inside the timed region, counters read back),
-`roofline` relates the count kernel's algorithmic bytes to the measured HBM copy peak, and
-`cpu_baseline` is the oracle port of the reference's algorithm timed on this box's host cores
-on a bounded sample of the same workload.
+  cfg2 (default; the configuration the metric is quoted on): 50 M single-end 100 bp SLAM-seq reads per GPU over 20 000
+        UTRs on a ~100 Mb, 21-contig genome, 2.5 % T>C per reference T.  N > 1: weak scaling, every rank owns a
+        contiguous genome region (UTR-owner sharding) and counts 50 M reads placed there; one NCCL all-reduce of the
+        int64 per-UTR counter table per step.
+  cfg3  4sU time course: 12 samples x 30 M x 150 bp counted in one batched run (one genome / annotation, 12 output
+        sets).  N > 1: the samples are dealt out over the ranks (sample sharding, no collective); strong scaling.
+  cfg4  5 M x 250 bp, the sample's own SNPs every 500 bp (reads carry the alternative allele at 90 % of the sites) masked
+        through a VarScan-style VCF incl. the reference's chrom+pos key collisions, 15 % mapq-0 reads retained
+        (multimapper branch of the filter: no MAPQ threshold), maxReadLength 250.
+  cfg5  1 B-read atlas: ONE read stream of 10^9 reads sharded by chromosome region over the ranks (each rank keeps the
+        reads whose alignment starts in its region; any N gives the same reads), one NCCL all-reduce of the per-UTR
+        counters per step; strong scaling.  N = 1 is the unsharded run.
+
+A step = one pass of the hot path over everything resident on the rank: zero the outputs, sd_count per batch (filter
+predicates + conversion scan + interval join + per-UTR / per-position reduction), sd_finalize (coverage scan) +
+sd_tcontent and, where the path shards by region, the all-reduce.
+
+One JSON line on stdout (rank 0).  `value` is device-resident throughput, `e2e` is the same work through sd_count_wire
+from pinned HOST buffers (H2D inside the timed region, counters read back), `roofline` relates the count kernel's
+algorithmic bytes to the measured HBM copy peak, `cpu_baseline` is the oracle port of the reference's algorithm timed on
+this box's host cores on a bounded sample of the same workload, `parity` says what was compared in this very run: the
+GPU path on the benchmarked column form against the oracle (N = 1), and the sharded run against the unsharded one on a
+10 M-read subsample of the same read stream (N > 1).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -34,8 +47,24 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-FILTER = dict(filter_on=True, filter_mq=2, filter_min_identity=0.95, filter_max_nm=-1)   # slamdunk.py:371-373 defaults
 MIN_QUAL, CONV_THRESHOLD = 27, 1                                                         # slamdunk.py:395,397 defaults
+TIME_POINTS = [0, 15, 30, 45, 60, 90, 120, 180, 240, 360, 480, 720]                      # cfg3, minutes of labelling
+
+WORKLOADS = {
+    # reads: per GPU (cfg2), per sample (cfg3), in total (cfg4, cfg5)
+    "cfg2": dict(reads=50_000_000, read_len=100, scaling="weak", frac_multimap=0.03, filter_mq=2),
+    "cfg3": dict(reads=30_000_000, read_len=150, scaling="strong", frac_multimap=0.03, filter_mq=2),
+    "cfg4": dict(reads=5_000_000, read_len=250, scaling="weak", frac_multimap=0.15, filter_mq=0),
+    "cfg5": dict(reads=1_000_000_000, read_len=100, scaling="strong", frac_multimap=0.03, filter_mq=2),
+}
+PART_READS = 50_000_000        # cfg5: reads per resident batch (a rank's share is a list of batches)
+SHARD_CHECK_READS = 10_000_000  # N > 1: sharded == unsharded on this many reads of the same stream
+
+
+def filter_params(args):
+    """slamdunk.py:371-373 defaults; cfg4 counts a BAM written by the multimapper-retention branch of the filter, which has
+    no MAPQ threshold (filter.py:105-112), so mapq-0 reads reach the counters (multimapCount)."""
+    return dict(filter_on=True, filter_mq=WORKLOADS[args.workload]["filter_mq"], filter_min_identity=0.95, filter_max_nm=-1)
 
 
 def measured_peaks():
@@ -100,18 +129,157 @@ class ClockSampler(object):
         return out
 
 
-def build_workload(local_rank, rank, world, n_reads, read_len, genome_bp, n_utr, want_triples=False, first_read=None,
-                   want_mp=False, coordinate_sorted=True):
-    from slamdunk_b200.engine import CountEngine
-    from slamdunk_b200.synth import SynthWorkload
-    eng = CountEngine(local_rank)
-    wl = SynthWorkload(eng, seed=1, genome_bp=genome_bp, n_utr=n_utr)
-    wl.install()
-    first, count = (0, 0) if world == 1 else wl.region_split(world)[rank]
-    fr = rank * n_reads if first_read is None else first_read
-    p = wl.params(seed=3, first_read=fr, n_reads=n_reads, read_len=read_len, utr_first=first, utr_count=count)
-    db, triples = wl.generate(p, want_mp=want_mp, want_triples=want_triples, coordinate_sorted=coordinate_sorted)
-    return eng, wl, db, triples
+# ------------------------------------------------------------------------------------------------------------------
+# workload construction
+# ------------------------------------------------------------------------------------------------------------------
+class Bench(object):
+    """Genome + annotation + (cfg4) SNP mask on one GPU, and the list of resident batches this rank counts."""
+
+    def __init__(self, args, rank, world, local_rank):
+        from slamdunk_b200 import _lib as L
+        from slamdunk_b200.engine import CountEngine, make_params
+        from slamdunk_b200.synth import SynthWorkload
+        self.args, self.rank, self.world = args, rank, world
+        self.L = L
+        self.eng = CountEngine(local_rank)
+        self.wl = SynthWorkload(self.eng, seed=1, genome_bp=args.genome_bp, n_utr=args.utrs)
+        self.wl.install()
+        self.snp_records = None
+        if args.workload == "cfg4":
+            from slamdunk_b200.utils.snpmask import SNPMasks
+            self.snp_records = self.wl.set_sample_snps(spacing=500, seed=30, p_allele=0.9)
+            sm = SNPMasks(self.wl.names, self.wl.chrom_off, self.wl.chrom_len, self.wl.n_words)
+            for r in self.snp_records:
+                sm.add(*r)
+            self.eng.set_snps(*sm.masks())
+        src = {"cigar": L.SD_MISMATCH_CIGAR, "mp": L.SD_MISMATCH_MP, "verify": L.SD_MISMATCH_VERIFY}[args.mismatch]
+        self.want_mp = src != L.SD_MISMATCH_CIGAR
+        self.params = make_params(MIN_QUAL, CONV_THRESHOLD, src, **filter_params(args))
+        self.sorted = args.order == "sorted"
+        self.parts = []          # [{"db": coded DeviceBatch, "n": reads, "spec": how to make it again, "sample": index or None}]
+        self.qual_planes = 0
+        self.region = None
+
+    # -- how a batch is (re)made: a spec is (time point or None, SynthParams kwargs, gpos_range or None)
+    def specs(self):
+        a, wl, rank, world = self.args, self.wl, self.rank, self.world
+        common = dict(read_len=a.read_len, frac_multimap=WORKLOADS[a.workload]["frac_multimap"])
+        if a.workload in ("cfg2", "cfg4"):
+            first, count = (0, 0) if world == 1 else wl.region_split(world)[rank]
+            return [dict(minutes=None, sample=None, gpos_range=None,
+                         kw=dict(seed=3 if a.workload == "cfg2" else 30, first_read=rank * a.reads, n_reads=a.reads, utr_first=first,
+                                 utr_count=count, **common))]
+        if a.workload == "cfg3":
+            mine = [k for k in range(len(TIME_POINTS)) if k % world == rank]
+            return [dict(minutes=TIME_POINTS[k], sample=k, gpos_range=None, kw=dict(seed=10 + k, first_read=0, n_reads=a.reads, **common))
+                    for k in mine]
+        # cfg5: the stream [0, reads) is scanned in index chunks; this rank keeps what starts inside its region
+        self.region = self.region_bounds(world)[rank]
+        chunk = min(a.reads, PART_READS * world)
+        return [dict(minutes=None, sample=None, gpos_range=self.region,
+                     kw=dict(seed=3, first_read=f, n_reads=min(chunk, a.reads - f), **common)) for f in range(0, a.reads, chunk)]
+
+    def region_bounds(self, n_parts):
+        """Cut the linear genome into n_parts stretches with about equal expected read counts (region_split), each cut a
+        little before a UTR that no earlier UTR of its chromosome reaches: a read belongs to the stretch its alignment starts
+        in, so every read has exactly one owner, and no read of one stretch touches a UTR of another -- a rank fills only its
+        own rows of the counter table and its own slice of the per-position arrays (partitioning A)."""
+        wl = self.wl
+        a = wl.ann
+        margin = self.args.read_len + 8         # a read starts at most read_len + 3 before the UTR it was placed on
+        reach = np.zeros(len(a), dtype=np.int64)        # furthest stop among the earlier UTRs of the same chromosome
+        far, chrom = -1, -1
+        for u in range(len(a)):
+            if int(a.chrom[u]) != chrom:
+                chrom, far = int(a.chrom[u]), -1
+            reach[u] = far
+            far = max(far, int(a.stop[u]))
+        cuts = [0]
+        for first, _ in wl.region_split(n_parts)[1:]:
+            u = first
+            while u < len(a) - 1 and reach[u] + margin > int(a.start[u]) - margin:
+                u += 1
+            c = int(a.chrom[u])
+            cuts.append(max(cuts[-1], int(wl.chrom_off[c]) + max(0, int(a.start[u]) - margin)))
+        cuts.append(1 << 33)
+        return [(cuts[k], cuts[k + 1]) for k in range(n_parts)]
+
+    def generate(self, spec, want_triples=False, n_reads=None):
+        """-> (byte-quality DeviceBatch with 2-bit SEQ, triples) for a spec (None, None when a region holds no read)"""
+        import torch
+        from slamdunk_b200.synth import to_seq2
+        wl = self.wl
+        wl.set_time_point(spec["minutes"])
+        kw = dict(spec["kw"])
+        if n_reads is not None:
+            kw["n_reads"] = n_reads
+        p = wl.params(**kw)
+        db4, triples = wl.generate(p, want_mp=self.want_mp, want_triples=want_triples, coordinate_sorted=self.sorted,
+                                   gpos_range=spec["gpos_range"])
+        wl.set_time_point(None)
+        if db4 is None:
+            return None, None
+        if self.args.seq_bits == 4:
+            return db4, triples
+        rows = to_seq2(db4, self.eng)
+        db4.tensors["seq"] = None
+        del db4
+        torch.cuda.empty_cache()
+        return rows, triples
+
+    def code(self, rows):
+        """the column form the kernel is benchmarked on: quality bit-planes when the file has <= 16 distinct qualities"""
+        from slamdunk_b200.synth import to_qual_planes
+        if self.args.seq_bits == 2 and self.args.qual_form == "planes":
+            dbq = to_qual_planes(rows, self.eng)
+            if dbq is not None:
+                self.qual_planes = int(dbq.batch.qual_bits)
+                return dbq
+        return rows
+
+    def build(self):
+        import torch
+        keep_rows = None
+        specs = self.specs()
+        for spec in specs:
+            rows, _ = self.generate(spec)
+            if rows is None:
+                continue
+            db = self.code(rows)
+            if len(specs) == 1 and not self.args.no_e2e:
+                keep_rows = rows          # one batch: the e2e leg packs its wire form from these rows
+            elif db is not rows:
+                rows.tensors["qual"] = None
+            del rows
+            torch.cuda.empty_cache()
+            self.parts.append({"db": db, "n": int(db.batch.n_reads), "spec": spec, "sample": spec["sample"], "outs": None})
+        self.rows = keep_rows
+        self.per_sample = self.args.workload == "cfg3"
+        self.reduce = self.world > 1 and self.args.workload in ("cfg2", "cfg4", "cfg5")
+        return self
+
+    @property
+    def n_reads(self):
+        return sum(p["n"] for p in self.parts)
+
+    def step(self):
+        import torch
+        import torch.distributed as dist
+        eng = self.eng
+        if self.per_sample:
+            for part in self.parts:
+                eng.reset_outputs()
+                eng.count(part["db"], self.params)
+                eng.finalize()
+                part["outs"] = (eng.counters, eng.stats)
+            return
+        eng.reset_outputs()
+        for part in self.parts:
+            eng.count(part["db"], self.params)
+        eng.finalize()
+        if self.reduce:
+            with torch.cuda.stream(eng.stream):
+                dist.all_reduce(eng.counters)
 
 
 def oracle_inputs(wl, db, triples):
@@ -123,8 +291,9 @@ def oracle_inputs(wl, db, triples):
     return g, bn, reads, qual, mp, ob.annotation_to_oracle(wl.ann, len(wl.names))
 
 
-def oracle_pass(g, bn, reads, qual, mp, utrs, threads):
-    """The reference's algorithm (oracle port): filter.Filter default branch, then computeTconversions."""
+def oracle_pass(g, bn, reads, qual, mp, utrs, threads, fp, snps=None):
+    """The reference's algorithm (oracle port): filter.Filter's predicates, then computeTconversions.
+    -> (seconds, rows, bedgraph entries, filter stats, {stage: seconds})"""
     from oracle import oracle
     from slamdunk_b200 import _lib as L
     n = bn["n_reads"]
@@ -138,27 +307,44 @@ def oracle_pass(g, bn, reads, qual, mp, utrs, threads):
     keep = np.zeros(n, dtype=np.uint8)
     stats = np.zeros(7, dtype=np.int64)
     t0 = time.perf_counter()
-    oracle.lib().orc_filter_default(fr.ctypes.data, n, FILTER["filter_mq"], FILTER["filter_min_identity"],
-                                    FILTER["filter_max_nm"], keep.ctypes.data, stats.ctypes.data)
+    oracle.lib().orc_filter_default_mt(fr.ctypes.data, n, fp["filter_mq"], fp["filter_min_identity"], fp["filter_max_nm"],
+                                       keep.ctypes.data, stats.ctypes.data, threads)
+    t1 = time.perf_counter()
     kept = reads[keep.astype(bool)]
-    rows, bg = oracle.count_arrays(g, kept, qual, utrs, MIN_QUAL, CONV_THRESHOLD, None, mp_triples=mp, threads=threads)
-    return time.perf_counter() - t0, rows, bg, stats
+    t2 = time.perf_counter()
+    rows, bg = oracle.count_arrays(g, kept, qual, utrs, MIN_QUAL, CONV_THRESHOLD, snps, mp_triples=mp, threads=threads)
+    t3 = time.perf_counter()
+    return t3 - t0, rows, bg, stats, {"filter_s": t1 - t0, "select_kept_s": t2 - t1, "sort_and_count_s": t3 - t2}
+
+
+def cpu_sample_spec(bench, sample):
+    """The bounded sample of the workload the CPU arm counts: the first `sample` reads of the read stream, unsharded
+    (cfg3: of the 120-minute sample, which has labelled and unlabelled reads in comparable numbers)."""
+    a = bench.args
+    k = 6
+    return dict(minutes=TIME_POINTS[k] if a.workload == "cfg3" else None, sample=None, gpos_range=None,
+                kw=dict(seed={"cfg2": 3, "cfg3": 10 + k, "cfg4": 30, "cfg5": 3}[a.workload], first_read=0, n_reads=sample,
+                        read_len=a.read_len, frac_multimap=WORKLOADS[a.workload]["frac_multimap"]))
 
 
 def run_reference(args, rank, world, local_rank):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference cannot travel
-    to the GPU box) on the host cores, each step a bounded sample of the same workload."""
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference cannot travel to the GPU box) on
+    all host threads of the box, each step a bounded sample of the same workload.  Under torchrun rank 0 alone runs."""
     if rank != 0:
         return
     from oracle import oracle
     threads = oracle.max_threads()
     sample = min(args.reads, args.cpu_sample)
-    eng, wl, db, triples = build_workload(local_rank, 0, 1, sample, args.read_len, args.genome_bp, args.utrs, want_triples=True)
-    inp = oracle_inputs(wl, db, triples)
-    eng.close()
-    times = []
+    bench = Bench(args, 0, 1, local_rank)
+    bench.want_mp = False
+    rows, triples = bench.generate(cpu_sample_spec(bench, sample), want_triples=True)
+    inp = oracle_inputs(bench.wl, rows, triples)
+    snps = oracle.make_snps(bench.snp_records) if bench.snp_records else None
+    bench.eng.close()
+    times, stages = [], {}
+    fp = filter_params(args)
     for i in range(args.warmup + args.steps):
-        dt, _rows, _bg, _st = oracle_pass(*inp, threads=threads)
+        dt, _rows, _bg, _st, stages = oracle_pass(*inp, threads=threads, fp=fp, snps=snps)
         if i >= args.warmup:
             times.append(dt)
     t = float(np.mean(times))
@@ -166,24 +352,50 @@ def run_reference(args, rank, world, local_rank):
     line = {
         "impl": "reference", "metric": "reads/sec counted (filter+T>C scan+UTR reduce)", "value": v, "unit": "reads/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
+        "scaling": WORKLOADS[args.workload]["scaling"], "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
         "config": workload_config(args, sample_reads=sample),
         "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "port",
-                         "sample": "first %d reads of the cfg2 read stream per step, inputs pre-decoded in RAM" % sample},
+                         "sample": "first %d reads of the %s read stream per step, inputs pre-decoded in RAM" % (sample, args.workload),
+                         "stages_last_step": stages,
+                         "note": "OpenMP over BED rows (count) and over records (filter); the coordinate sort that stands in for the "
+                                 "indexed BAM (numpy lexsort) and the selection of kept reads are single-threaded"},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
 def workload_config(args, sample_reads=None):
-    c = {"workload": "cfg2: synthetic %d x %d bp single-end SLAM-seq reads per GPU, %d UTRs, %.0f Mb genome on 21 contigs, "
-                     "2.5%% T>C per reference T" % (args.reads, args.read_len, args.utrs, args.genome_bp / 1e6),
-         "reads_per_gpu": args.reads, "read_len": args.read_len, "n_utr": args.utrs,
-         "filter": "MQ>=2, identity>=0.95 (slamdunk defaults)", "min_base_qual": MIN_QUAL, "conversion_threshold": CONV_THRESHOLD,
-         "mismatch_source": "cigar_walk", "read_order": args.order, "seq_bits": getattr(args, "seq_bits", 2),
-         "qual_form": getattr(args, "qual_form", "planes") if getattr(args, "seq_bits", 2) == 2 else "bytes", "sharding": "utr_owner_regions" if args.gpus > 1 else "none",
-         "l2_policy": "inputs (~%.1f GB per GPU) far exceed the 126 MB L2; no explicit flush" % (args.reads * (getattr(args, "seq_bits", 2) * 4 * ((args.read_len + 31) // 32) +
-                                                                                                         (8 * ((args.read_len + 31) // 32) if getattr(args, "seq_bits", 2) == 2 and getattr(args, "qual_form", "planes") == "planes" else args.read_len) + 24.4) / 1e9)}
+    w = args.workload
+    groups = (args.read_len + 31) // 32
+    per_read = args.seq_bits * 4 * groups + (8 * groups if args.seq_bits == 2 and args.qual_form == "planes" else args.read_len) + 24.4
+    names = {
+        "cfg2": "cfg2: synthetic %d x %d bp single-end SLAM-seq reads per GPU, %d UTRs, %.0f Mb genome on 21 contigs, 2.5%% T>C per reference T"
+                % (args.reads, args.read_len, args.utrs, args.genome_bp / 1e6),
+        "cfg3": "cfg3: 4sU time course, %d samples x %d x %d bp reads counted in one batched run, %d UTRs, %.0f Mb genome; "
+                "labelled-read fraction 1 - exp(-ln2 t / halflife) per UTR" % (len(TIME_POINTS), args.reads, args.read_len, args.utrs, args.genome_bp / 1e6),
+        "cfg4": "cfg4: %d x %d bp reads per GPU, sample SNPs 1 / 500 bp (90%% allele frequency in the reads) masked through the VCF, "
+                "15%% mapq-0 reads retained, maxReadLength 250" % (args.reads, args.read_len),
+        "cfg5": "cfg5: one %d-read x %d bp atlas stream sharded by chromosome region over the GPUs, %d UTRs, %.0f Mb genome"
+                % (args.reads, args.read_len, args.utrs, args.genome_bp / 1e6),
+    }
+    resident = {"cfg2": args.reads, "cfg3": args.reads * -(-len(TIME_POINTS) // args.gpus), "cfg4": args.reads,
+                "cfg5": args.reads / args.gpus}[w]
+    fp = filter_params(args)
+    c = {"workload": names[w], "read_len": args.read_len, "n_utr": args.utrs,
+         "filter": "MQ>=%d, identity>=0.95%s" % (fp["filter_mq"], " (slamdunk defaults)" if fp["filter_mq"] == 2 else " (multimapper-retained input: no MAPQ threshold)"),
+         "min_base_qual": MIN_QUAL, "conversion_threshold": CONV_THRESHOLD,
+         "mismatch_source": {"cigar": "cigar_walk", "mp": "mp_tags", "verify": "cigar_walk_verified_against_mp_tags"}[args.mismatch],
+         "read_order": args.order, "seq_bits": args.seq_bits,
+         "qual_form": args.qual_form if args.seq_bits == 2 else "bytes",
+         "sharding": {"cfg2": "utr_owner_regions" if args.gpus > 1 else "none", "cfg3": "samples over ranks, no collective" if args.gpus > 1 else "none",
+                      "cfg4": "utr_owner_regions" if args.gpus > 1 else "none", "cfg5": "chromosome regions of one read stream" if args.gpus > 1 else "none (unsharded stream)"}[w],
+         "l2_policy": "inputs (~%.1f GB per GPU) far exceed the 126 MB L2; no explicit flush" % (resident * per_read / 1e9)}
+    if w == "cfg2":
+        c["reads_per_gpu"] = args.reads
+    elif w == "cfg3":
+        c["samples"], c["reads_per_sample"] = len(TIME_POINTS), args.reads
+    else:
+        c["reads_total" if w == "cfg5" else "reads_per_gpu"] = args.reads
     if sample_reads is not None:
         c["sample_reads"] = sample_reads
     return c
@@ -209,6 +421,172 @@ def emit(line):
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# the legs of a native run
+# ------------------------------------------------------------------------------------------------------------------
+def e2e_leg(bench, barrier, reps):
+    """The same pass through the reference-facing call with HOST buffers: every batch in its wire form (sd_wire, what
+    sd_decode_bam hands `count`) in page-locked memory, sd_count_wire (chunked H2D overlapped with the expansion and count
+    kernels), sd_finalize, all-reduce where the path has one, counters and run statistics read back.
+    One resident batch: the wire is built once and `reps` whole steps are timed.  Several batches (cfg3 / cfg5: up to
+    58 GB of wire): the wires are staged one at a time -- each batch's calls are timed `reps` times in a row and the per-step
+    time is the sum over the batches (the calls are synchronous, nothing overlaps between batches anyway)."""
+    import torch
+    import torch.distributed as dist
+    from slamdunk_b200.synth import batch_to_wire
+    eng, L, world = bench.eng, bench.L, bench.world
+    d2h = eng.counters.numel() * 8 + eng.stats.numel() * 8
+
+    def readback():
+        eng.synchronize()
+        return eng.counters.cpu(), eng.stats.cpu()
+
+    def reduce_():
+        if bench.reduce:
+            with torch.cuda.stream(eng.stream):
+                dist.all_reduce(eng.counters)
+
+    h2d, counted, qbits = 0, 0, 0
+    if bench.rows is not None:
+        hw = batch_to_wire(bench.rows, eng)
+        h2d, qbits = hw.h2d_bytes(bench.params), int(hw.wire.qual_bits)
+
+        def e2e_step():
+            eng.reset_outputs()
+            eng.count_wire(hw.wire, bench.params)
+            eng.finalize()
+            reduce_()
+            return readback()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / reps
+        counted = int(out[1][L.SD_S_COUNTED])
+        del hw
+        mode = "one wire, whole steps timed"
+    else:
+        barrier()
+        dt = 0.0
+        for part in bench.parts:
+            rows, _ = bench.generate(part["spec"])
+            hw = batch_to_wire(rows, eng)
+            del rows
+            torch.cuda.empty_cache()
+            h2d += hw.h2d_bytes(bench.params)
+            qbits = int(hw.wire.qual_bits)
+            eng.reset_outputs()
+            eng.count_wire(hw.wire, bench.params)      # warm
+            eng.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                if bench.per_sample:
+                    eng.reset_outputs()
+                eng.count_wire(hw.wire, bench.params)
+                if bench.per_sample:
+                    eng.finalize()
+                    out = readback()
+            dt += (time.perf_counter() - t0) / reps
+            if bench.per_sample:
+                counted += int(out[1][L.SD_S_COUNTED])
+            del hw
+        if not bench.per_sample:
+            eng.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                eng.reset_outputs()
+                eng.finalize()
+                reduce_()
+                out = readback()
+            dt += (time.perf_counter() - t0) / reps
+            d2h_n = 1
+        else:
+            d2h_n = len(bench.parts)
+        d2h *= d2h_n
+        mode = "wires staged one batch at a time, per-step time = sum over %d batches" % len(bench.parts)
+    return dt, h2d, d2h, counted, qbits, mode
+
+
+def shard_check(bench, n_check):
+    """N > 1: the first n_check reads of ONE read stream, (a) sharded by chromosome region over the ranks -- each rank counts
+    the reads that start in its stretch of the genome against the whole annotation, counters / per-position arrays / run
+    statistics are all-reduced, then the coverage scan -- and (b) counted unsharded on rank 0.  Everything must be identical."""
+    import torch
+    import torch.distributed as dist
+    eng, wl, a = bench.eng, bench.wl, bench.args
+    kw = dict(seed=3, first_read=0, n_reads=n_check, read_len=a.read_len, frac_multimap=WORKLOADS[a.workload]["frac_multimap"])
+    mine = dict(minutes=None, sample=None, gpos_range=bench.region_bounds(bench.world)[bench.rank], kw=kw)
+    rows, _ = bench.generate(mine)
+    eng.reset_outputs()
+    n_mine = 0
+    if rows is not None:
+        eng.count(bench.code(rows), bench.params)
+        n_mine = int(rows.batch.n_reads)
+    with torch.cuda.stream(eng.stream):
+        for t in (eng.counters, eng.pos_cov, eng.pos_tc, eng.stats):
+            dist.all_reduce(t)
+    eng.finalize()
+    eng.synchronize()
+    tot = torch.tensor([n_mine], dtype=torch.int64, device=eng.device)
+    dist.all_reduce(tot)
+    got = eng.results()
+    del rows
+    torch.cuda.empty_cache()
+    if bench.rank != 0:
+        return None
+    rows, _ = bench.generate(dict(minutes=None, sample=None, gpos_range=None, kw=kw))
+    eng.reset_outputs()
+    eng.count(bench.code(rows), bench.params)
+    eng.finalize()
+    want = eng.results()
+    bad = [k for k in ("counters", "pos_cov", "pos_tc", "tcontent") if not np.array_equal(want[k], got[k])]
+    L = bench.L
+    ws, gs = want["stats"], got["stats"]
+    if any(int(ws[k]) != int(gs[k]) for k in range(L.SD_NSTAT) if k != L.SD_S_SLOWPATH):
+        bad.append("stats")
+    if int(tot.item()) != n_check:
+        bad.append("shards hold %d reads" % int(tot.item()))
+    if bad:
+        return "MISMATCH sharded vs unsharded: " + ", ".join(bad)
+    return ("sharded over %d GPUs by chromosome region == unsharded on the first %d reads of the stream: per-UTR counters, "
+            "per-position arrays, run statistics identical (%d reads counted)" % (bench.world, n_check, int(ws[L.SD_S_COUNTED])))
+
+
+def oracle_check(bench, sample):
+    """N = 1: the GPU path on the benchmarked column form against the oracle port on a bounded sample, and the port's time."""
+    from oracle import oracle
+    import oracle_bridge as ob
+    eng, wl = bench.eng, bench.wl
+    rows, triples = bench.generate(cpu_sample_spec(bench, sample), want_triples=True)
+    inp = oracle_inputs(wl, rows, triples)
+    threads = oracle.max_threads()
+    snps = oracle.make_snps(bench.snp_records) if bench.snp_records else None
+    try:
+        dt, orows, bg, ostats, stages = oracle_pass(*inp, threads=threads, fp=filter_params(bench.args), snps=snps)
+    finally:
+        oracle.free_snps(snps)
+    db = bench.code(rows)
+    eng.reset_outputs()
+    eng.count(db, bench.params)
+    eng.finalize()
+    res = eng.results()
+    problems = ob.compare(res, orows, bg, wl.ann, eng.pos_off, wl.chrom_off)
+    if res["stats"][:6].tolist() != ostats[:6].tolist():
+        problems.append("filter stats differ")
+    if bench.params.mismatch_source == bench.L.SD_MISMATCH_VERIFY and int(res["stats"][bench.L.SD_S_MP_DISAGREE]) != 0:
+        problems.append("CIGAR walk disagrees with the MP tags on %d reads" % int(res["stats"][bench.L.SD_S_MP_DISAGREE]))
+    form = "2-bit SEQ + %d quality bit-planes" % int(db.batch.qual_bits) if int(db.batch.qual_form) == 1 else \
+        ("%d-bit SEQ + byte qualities" % (int(db.batch.seq_bits) or 4))
+    parity = ("bit-exact vs oracle on %d reads (%s, %s)" % (sample, form, bench.args.mismatch)) if not problems else "MISMATCH: " + "; ".join(problems)
+    cpu = {"value": sample / dt, "unit": "reads/s", "cores": threads, "kind": "port",
+           "sample": "first %d reads of the same read stream, inputs pre-decoded in RAM, filter + count" % sample,
+           "seconds": dt, "stages": stages}
+    return parity, cpu
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -216,11 +594,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--reads", type=int, default=50_000_000, help="reads per GPU")
-    ap.add_argument("--read-len", type=int, default=100, dest="read_len")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=None, help="reads per GPU (cfg2, cfg4), per sample (cfg3), in total (cfg5)")
+    ap.add_argument("--read-len", type=int, default=None, dest="read_len")
     ap.add_argument("--utrs", type=int, default=20000)
     ap.add_argument("--genome-bp", type=int, default=100_000_000, dest="genome_bp")
     ap.add_argument("--cpu-sample", type=int, default=4_000_000, dest="cpu_sample")
+    ap.add_argument("--mismatch", default="cigar", choices=["cigar", "mp", "verify"],
+                    help="where the per-read mismatch list comes from: the CIGAR walk (north star; default), NextGenMap's MP tags, or "
+                         "the walk cross-checked against the tags read by read (computeTconversions' default mode)")
     ap.add_argument("--order", default="sorted", choices=["sorted", "mapper"],
                     help="read order inside the batch: coordinate-sorted (what `slamdunk count` reads: the sorted BAM "
                          "written by `slamdunk filter`) or mapper order (random placement, the filter's input)")
@@ -233,8 +615,15 @@ def main():
                          "2-bit; default), bytes = one byte per base fetched at candidates")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-shard-check", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.reads is None:
+        args.reads = WORKLOADS[args.workload]["reads"]
+    if args.read_len is None:
+        args.read_len = WORKLOADS[args.workload]["read_len"]
+    if args.seq_bits == 4:
+        args.no_e2e = True      # the wire form is made from the 2-bit column
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -248,159 +637,127 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from slamdunk_b200 import _lib as L
-    from slamdunk_b200.engine import make_params
-    from slamdunk_b200.synth import (algorithmic_bytes_per_read, batch_to_wire, layout_bytes_per_read, to_qual_planes, to_seq2)
+    from slamdunk_b200.synth import algorithmic_bytes_per_read, layout_bytes_per_read
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    eng, wl, db, _ = build_workload(local_rank, rank, world, args.reads, args.read_len, args.genome_bp, args.utrs,
-                                    coordinate_sorted=(args.order == "sorted"))
-    params = make_params(MIN_QUAL, CONV_THRESHOLD, L.SD_MISMATCH_CIGAR, **FILTER)
-    n_reads = args.reads
-    if args.seq_bits == 2:
-        db4 = db
-        db = to_seq2(db4, eng)
-        db4.tensors["seq"] = None      # free the 4-plane column
-        del db4
-        torch.cuda.empty_cache()
-    db_rows = db                       # qualities as one byte per base: what the host batch of the e2e leg is made from
-    qual_planes = 0
-    if args.seq_bits == 2 and args.qual_form == "planes":
-        dbq = to_qual_planes(db_rows, eng)
-        if dbq is not None:
-            db, qual_planes = dbq, int(dbq.batch.qual_bits)
-
-    def step():
-        eng.reset_outputs()
-        eng.count(db, params)
-        eng.finalize()
-        if world > 1:
-            with torch.cuda.stream(eng.stream):
-                dist.all_reduce(eng.counters)
+    bench = Bench(args, rank, world, local_rank).build()
+    eng, L = bench.eng, bench.L
+    n_mine = bench.n_reads
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_sum(x):
+        if world == 1:
+            return int(x)
+        t = torch.tensor([int(x)], dtype=torch.int64, device=eng.device)
+        dist.all_reduce(t)
+        return int(t.item())
+
+    def all_max(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n_total = all_sum(n_mine)
     for _ in range(args.warmup):
-        step()
+        bench.step()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
     barrier()
     ev0.record(eng.stream)
     for _ in range(args.steps):
-        step()
-        kernel_ms.append(eng.last_kernel_ms())      # CUDA events around the count kernel, on its stream
+        bench.step()
     ev1.record(eng.stream)
     barrier()
-    total_ms = ev0.elapsed_time(ev1)
+    total_ms = all_max(ev0.elapsed_time(ev1))
     launches = eng.launch_count() - launches0
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=eng.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
-    value = world * n_reads / (ms_per_step * 1e-3)
-    stats = eng.stats.cpu().numpy()
+    value = n_total / (ms_per_step * 1e-3)
+    if bench.per_sample:
+        counted = sum(int(p["outs"][1].cpu()[L.SD_S_COUNTED]) for p in bench.parts)
+        filtered = sum(int(p["outs"][1].cpu()[L.SD_S_FILTERED]) for p in bench.parts)
+        slow = sum(int(p["outs"][1].cpu()[L.SD_S_SLOWPATH]) for p in bench.parts)
+    else:
+        stats = eng.stats.cpu().numpy()
+        counted, filtered, slow = int(stats[L.SD_S_COUNTED]), int(stats[L.SD_S_FILTERED]), int(stats[L.SD_S_SLOWPATH])
 
-    # roofline of the dominant kernel (sd_count_kernel)
-    tiles = db.tensors["tiles"].cpu().numpy().view(np.uint64).reshape(-1, 4)
-    mean_cig = float(tiles[-1, 2]) / 4.0 / n_reads
+    # count-kernel time per step: CUDA events the library records around the kernel(s) of every sd_count on its stream, read
+    # in a separate pass of the same step (reading an event's time waits for it, which would serialise the timed loop)
+    k_ms = 0.0
+    k_reps = min(args.steps, 5)
+    for _ in range(k_reps):
+        for part in bench.parts:
+            eng.reset_outputs()
+            eng.count(part["db"], bench.params)
+            k_ms += eng.last_kernel_ms()
+    k_ms /= k_reps
+    mean_cig = 0.0
+    for part in bench.parts:
+        tiles = part["db"].tensors["tiles"].view(torch.int64).view(-1, 4)
+        mean_cig += float(tiles[-1, 2].item()) / 4.0
+    mean_cig /= max(1, n_mine)
     bytes_per_read = algorithmic_bytes_per_read(args.read_len, mean_cig)
-    layout_bytes = layout_bytes_per_read(args.read_len, mean_cig, args.seq_bits, qual_planes)
-    k_ms = float(np.mean(kernel_ms))
-    achieved = n_reads * bytes_per_read / (k_ms * 1e-3) / 1e9
+    layout_bytes = layout_bytes_per_read(args.read_len, mean_cig, args.seq_bits, bench.qual_planes)
+    achieved = n_mine * bytes_per_read / (k_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_ncu_traffic(args), "kernel": "sd_count_kernel", "kernel_ms": k_ms,
                 "algorithmic_bytes_per_read": bytes_per_read, "algorithmic_bytes_source": "SURVEY.md 8(d): ceil(L/2) + L + 4c + 17",
-                "layout_bytes_per_read": layout_bytes, "achieved_layout_bytes": n_reads * layout_bytes / (k_ms * 1e-3) / 1e9,
-                "frac_layout_bytes": n_reads * layout_bytes / (k_ms * 1e-3) / 1e9 / peak,
-                "note": "achieved / frac follow the contract: SURVEY 8(d)'s bytes of the path's INPUT per read over the kernel time. "
+                "layout_bytes_per_read": layout_bytes, "achieved_layout_bytes": n_mine * layout_bytes / (k_ms * 1e-3) / 1e9,
+                "frac_layout_bytes": n_mine * layout_bytes / (k_ms * 1e-3) / 1e9 / peak,
+                "note": "achieved / frac follow the contract: SURVEY 8(d)'s bytes of the path's INPUT per read over the kernel time "
+                        "(rank 0's reads and kernels; the staged kernel plus the plain one that takes its left-over tiles). "
                         "The columns are held coded (2-bit SEQ, quality bit-planes), so the kernel moves fewer bytes "
-                        "(layout_bytes_per_read; traffic = ncu DRAM bytes per launch) and at this point is bound by instruction "
-                        "issue (about 70 % of the issue slots, profiles/), not by HBM: frac can exceed 1 at longer reads.",
+                        "(layout_bytes_per_read; traffic = ncu DRAM bytes per launch) and is bound by instruction issue together "
+                        "with DRAM (profiles/): frac can exceed 1 at longer reads.",
                 "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "kernel_share_of_step": k_ms / ms_per_step}
 
-    # end to end: pinned host buffers -> sd_count_host -> counters back on the host
     e2e = None
     if not args.no_e2e:
-        hw = batch_to_wire(db_rows, eng)           # the packed host form sd_decode_bam produces for `count` (sd_wire)
-        h2d = hw.h2d_bytes(params)
-        d2h = eng.counters.numel() * 8 + eng.stats.numel() * 8
+        dt, h2d, d2h, e2e_counted, qbits, mode = e2e_leg(bench, barrier, args.steps if bench.rows is not None else min(args.steps, 3))
+        dt = all_max(dt)
+        e2e = {"value": n_total / dt, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt * 1e3, "h2d_gbs": h2d / dt / 1e9, "h2d_bytes_per_read": h2d / max(1, n_mine),
+               "host_form": "sd_wire: per-field columns, 2-bit SEQ codes, %d-bit quality codes, plain-match tiles without l_seq / CIGAR" % qbits,
+               "mode": mode, "counted_reads": int(e2e_counted), "bytes_are": "rank 0's"}
 
-        def e2e_step():
-            eng.reset_outputs()
-            eng.count_wire(hw.wire, params)
-            eng.finalize()
-            if world > 1:
-                with torch.cuda.stream(eng.stream):
-                    dist.all_reduce(eng.counters)
-            eng.synchronize()
-            return eng.counters.cpu(), eng.stats.cpu()
-
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            out = e2e_step()
-        barrier()
-        dt = (time.perf_counter() - t0) / args.steps
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=eng.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * n_reads / dt, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt * 1e3, "h2d_gbs": h2d / dt / 1e9, "h2d_bytes_per_read": h2d / n_reads,
-               "host_form": "sd_wire: per-field columns, 2-bit SEQ codes, %d-bit quality codes, plain-match tiles without l_seq / CIGAR" % int(hw.wire.qual_bits),
-               "counted_reads": int(out[1][L.SD_S_COUNTED])}
-        del hw
-
-    # CPU baseline + parity of the GPU counters with the oracle on a bounded sample (rank 0, N = 1)
     cpu = None
-    parity = None
+    parity = {}
+    if world > 1 and not args.no_shard_check and args.workload != "cfg3":
+        msg = shard_check(bench, min(SHARD_CHECK_READS, args.reads * (world if args.workload != "cfg5" else 1)))
+        if rank == 0:
+            parity["sharding"] = msg
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle
-        import oracle_bridge as ob
-        sample = min(n_reads, args.cpu_sample)
-        p = wl.params(seed=3, first_read=0, n_reads=sample, read_len=args.read_len)
-        sdb, triples = wl.generate(p, want_triples=True, coordinate_sorted=(args.order == "sorted"))
-        inp = oracle_inputs(wl, sdb, triples)
-        threads = oracle.max_threads()
-        dt, rows, bg, ostats = oracle_pass(*inp, threads=threads)
-        eng.reset_outputs()
-        eng.count(sdb, params)
-        eng.finalize()
-        res = eng.results()
-        problems = ob.compare(res, rows, bg, wl.ann, eng.pos_off, wl.chrom_off)
-        if res["stats"][:6].tolist() != ostats[:6].tolist():
-            problems.append("filter stats differ")
-        parity = "bit-exact vs oracle on %d reads" % sample if not problems else "MISMATCH: " + "; ".join(problems)
-        cpu = {"value": sample / dt, "unit": "reads/s", "cores": threads, "kind": "port",
-               "sample": "first %d reads of the same read stream, inputs pre-decoded in RAM, filter + count" % sample,
-               "seconds": dt}
+        parity["oracle"], cpu = oracle_check(bench, min(args.reads, args.cpu_sample))
+    if world > 1:
+        barrier()
 
     if rank == 0:
         line = {
             "metric": "reads/sec counted (filter+T>C scan+UTR reduce)", "value": value, "unit": "reads/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64 (integer bit ops)",
+            "higher_is_better": True, "scaling": WORKLOADS[args.workload]["scaling"], "vs_baseline": None,
+            "dtype": "u8/int64 (integer bit ops)",
             "data": "synthetic", "config": workload_config(args),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "parity": parity,
-            "counted_reads_last_step": int(stats[L.SD_S_COUNTED]), "filtered_reads_last_step": int(stats[L.SD_S_FILTERED]),
-            "slow_path_reads": int(stats[L.SD_S_SLOWPATH]),
+            "parity": parity or None,
+            "reads_per_step": n_total, "reads_rank0": n_mine, "batches_rank0": len(bench.parts),
+            "counted_reads_last_step": counted, "filtered_reads_last_step": filtered,
+            "slow_path_reads": slow,
         }
         emit(line)
     eng.close()
@@ -414,7 +771,8 @@ def load_ncu_traffic(args):
     path = os.path.join(ROOT, "profiles", "count_kernel_dram.json")
     try:
         d = json.load(open(path))
-        if args.reads != d.get("reads_per_launch") or args.read_len != 100 or args.order != "sorted" or args.seq_bits != d.get("seq_bits", 4) or args.qual_form != d.get("qual_form", "bytes"):
+        if (args.workload != "cfg2" or args.reads != d.get("reads_per_launch") or args.read_len != 100 or args.order != "sorted"
+                or args.seq_bits != d.get("seq_bits", 4) or args.qual_form != d.get("qual_form", "bytes") or args.mismatch != "cigar"):
             return None
         return d.get("dram_bytes_per_launch")
     except Exception:

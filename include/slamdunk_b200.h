@@ -41,7 +41,7 @@ extern "C" {
 #define SD_ERR_LIMIT (-6)
 #define SD_ERR_NOMEM (-7)
 
-#define SD_ABI_VERSION 6
+#define SD_ABI_VERSION 7
 
 typedef struct sd_ctx sd_ctx;
 
@@ -574,6 +574,11 @@ typedef struct sd_synth_tables {
     const double *utr_cum_weight;    /* inclusive cumulative expression weight */
     const float *utr_label_frac;     /* optional: per-UTR fraction of labelled reads, overriding sd_synth_params.frac_labelled --
                                         a 4sU time point, 1 - exp(-ln2 t / halflife(u)) (dunks/simulator.py:291-302) */
+    const uint32_t *snp_tc, *snp_ag, *snp_other; /* optional bit planes over the linear genome (like nmask): true SNP sites of the
+                                        sample -- reference T with alternative allele C, reference A with alternative G, any
+                                        other substitution (the read then shows the next base code: A>C, C>G, G>T, T>A) */
+    float p_snp_allele;              /* probability that a read covering a SNP site carries the alternative allele (BASELINE.json
+                                        config 4: 0.9); reads of both strands, labelled or not */
 } sd_synth_tables;
 
 #define SD_SYNTH_MAX_TRIPLES 40

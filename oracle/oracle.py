@@ -92,6 +92,8 @@ def lib():
         L.orc_read_tc.restype = ctypes.c_int
         L.orc_filter_default.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_filter_default_mt.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
+                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.orc_filter_multimap.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32,
                                           ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
@@ -103,7 +105,12 @@ def lib():
 
 
 def max_threads() -> int:
-    return int(lib().orc_max_threads())
+    """Host threads available to this process: the scheduler's affinity mask, NOT OpenMP's default -- torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which is a launcher setting and not a property of the box."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return max(1, os.cpu_count() or 1)
 
 
 # --------------------------------------------------------------------------

@@ -379,7 +379,7 @@ int orc_count(const orc_count_args_t *a, orc_row_t *rows, orc_bg_t **bg, int64_t
     int64_t *nlist = (int64_t *)calloc((size_t)a->n_utr, sizeof(*nlist));
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
-#pragma omp parallel for schedule(dynamic, 8)
+#pragma omp parallel for schedule(dynamic, 1)
 #endif
     for (int32_t i = 0; i < a->n_utr; i++)
         count_one_utr(a, &a->utrs[i], &rows[i], &lists[i], &nlist[i]);
@@ -432,9 +432,14 @@ typedef struct { int32_t chrom_id, start, stop, name_id; } orc_futr_t;  /* name_
 
 /* Default branch, filter.py:233-256.  keep[i] = 1 when the record is written.
  * stats = mapped, unmapped, filtered, mqFiltered, idFiltered, nmFiltered, multimapper */
-int orc_filter_default(const orc_fread_t *r, int64_t n, int mq, double min_identity, int nm,
-                       uint8_t *keep, int64_t stats[7]) {
+int orc_filter_default_mt(const orc_fread_t *r, int64_t n, int mq, double min_identity, int nm,
+                          uint8_t *keep, int64_t stats[7], int threads) {
     int64_t mapped = 0, unmapped = 0, filtered = 0, mqf = 0, idf = 0, nmf = 0;
+    /* every record is decided on its own (the counters are plain sums), so the file-order loop splits over threads */
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(static) reduction(+ : mapped, unmapped, filtered, mqf, idf, nmf)
+#endif
     for (int64_t i = 0; i < n; i++) {
         keep[i] = 0;
         int primary = !(r[i].flag & 0x100) && !(r[i].flag & 0x800);
@@ -449,6 +454,10 @@ int orc_filter_default(const orc_fread_t *r, int64_t n, int mq, double min_ident
     }
     stats[0] = mapped; stats[1] = unmapped; stats[2] = filtered; stats[3] = mqf; stats[4] = idf; stats[5] = nmf; stats[6] = 0;
     return 0;
+}
+int orc_filter_default(const orc_fread_t *r, int64_t n, int mq, double min_identity, int nm,
+                       uint8_t *keep, int64_t stats[7]) {
+    return orc_filter_default_mt(r, n, mq, min_identity, nm, keep, stats, 1);
 }
 
 /* multimapUTRRetainment, filter.py:72-210 (+ dumpBufferToBam :56-65).

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SLAMDUNK_B200_LIB") or os.path.join(HERE, "libslamdunk_b200.so")   # env: kernel experiments
 
 SD_OK = 0
-SD_ABI_VERSION = 6   # 6 = sd_hbatch.n_mapped_no_xi/nm, wire form; include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual; 4 = BAI writer; 5 = sd_read_stats
+SD_ABI_VERSION = 7   # 7 = SNP alleles in the generator (sd_synth_tables); 6 = sd_hbatch.n_mapped_no_xi/nm, wire form; include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual; 4 = BAI writer; 5 = sd_read_stats
 SD_F_REVERSE, SD_F_UNMAPPED, SD_F_SECONDARY, SD_F_SUPPLEMENTARY = 0x01, 0x02, 0x04, 0x08
 SD_F_HAS_MP, SD_F_SKIP, SD_F_NEWNAME, SD_F_PAD = 0x10, 0x20, 0x40, 0x80
 SD_REF_NONE = 0xFFFF
@@ -103,7 +103,8 @@ class SynthTables(ctypes.Structure):
                 ("chrom_off", ctypes.c_void_p), ("chrom_len", ctypes.c_void_p), ("n_chrom", ctypes.c_uint32),
                 ("n_utr", ctypes.c_uint32), ("utr_chrom", ctypes.c_void_p), ("utr_start", ctypes.c_void_p),
                 ("utr_end", ctypes.c_void_p), ("utr_strand", ctypes.c_void_p), ("utr_cum_weight", ctypes.c_void_p),
-                ("utr_label_frac", ctypes.c_void_p)]
+                ("utr_label_frac", ctypes.c_void_p), ("snp_tc", ctypes.c_void_p), ("snp_ag", ctypes.c_void_p),
+                ("snp_other", ctypes.c_void_p), ("p_snp_allele", ctypes.c_float)]
 
 
 class StatsArgs(ctypes.Structure):

@@ -111,6 +111,12 @@ __device__ void simulate(Rng &rng, const sd_synth_params &P, const sd_synth_tabl
             for (uint32_t j = 0; j < len; j++) {
                 const uint32_t rc = ref_code(T, g0 + r);
                 uint32_t b = rc < 4 ? rc : rng.below(4);
+                if (T.snp_tc && rc < 4) {   // the sample's own SNPs: the read carries the alternative allele
+                    const uint64_t g = g0 + r;
+                    const uint32_t w = (uint32_t)(g >> 5), bit = 1u << (g & 31);
+                    const uint32_t alt = (T.snp_tc[w] & bit) ? 1u : ((T.snp_ag[w] & bit) ? 2u : ((T.snp_other && (T.snp_other[w] & bit)) ? ((rc + 1u) & 3u) : rc));
+                    if (alt != rc && rng.uniform() < T.p_snp_allele) b = alt;
+                }
                 if (rc == conv_from && pl.labelled && rng.uniform() < P.p_conv) b = conv_to;
                 if (rng.uniform() < P.p_err) b = (b + 1 + rng.below(3)) & 3u;
                 em.base(q, b);

@@ -134,6 +134,50 @@ class SynthWorkload(object):
         self.tables.utr_label_frac = self.d_label_frac.data_ptr()
         return frac
 
+    def set_sample_snps(self, spacing=500, seed=30, p_allele=0.9, tc_ag_share=0.5, multi_allelic=0.02):
+        """BASELINE.json config 4: the sample's own SNPs, one per `spacing` bp genome-wide.  `tc_ag_share` of them are T>C /
+        A>G (placed on a reference T / A), the rest other substitutions; `multi_allelic` of the T>C / A>G ones are written
+        with a second alternative allele ("C,G"), which the reference's SNPDictionary never matches (SNPtools.py:33-37).
+        Reads of the generator then carry the alternative allele with probability p_allele.
+        -> VCF records [(CHROM, POS text, REF, ALT)] as VarScan would list them, for utils.snpmask.SNPMasks / the oracle."""
+        rng = np.random.default_rng(seed)
+        lo, hi, nm = (t.cpu().numpy().view(np.uint32) for t in (self.lo, self.hi, self.nmask))
+        tc = np.zeros(self.n_words, dtype=np.uint32)
+        ag = np.zeros(self.n_words, dtype=np.uint32)
+        other = np.zeros(self.n_words, dtype=np.uint32)
+        records = []
+        letters = "ACGT"
+        for c, name in enumerate(self.names):
+            clen, off = int(self.chrom_len[c]), int(self.chrom_off[c])
+            k = clen // spacing
+            if k == 0:
+                continue
+            pos = np.unique(rng.integers(0, clen, size=k))
+            g = off + pos
+            w, b = g >> 5, (g & 31).astype(np.uint32)
+            code = ((lo[w] >> b) & 1) | (((hi[w] >> b) & 1) << 1)
+            isn = ((nm[w] >> b) & 1).astype(bool)
+            want_conv = rng.random(len(pos)) < tc_ag_share
+            multi = rng.random(len(pos)) < multi_allelic
+            for j in range(len(pos)):
+                if isn[j]:
+                    continue
+                cj = int(code[j])
+                bit = np.uint32(1) << b[j]
+                if want_conv[j] and cj in (0, 3):
+                    alt = "G" if cj == 0 else "C"
+                    (ag if cj == 0 else tc)[w[j]] |= bit
+                    records.append((name, str(int(pos[j]) + 1), letters[cj], alt + (",T" if multi[j] and cj == 0 else (",G" if multi[j] else ""))))
+                else:
+                    other[w[j]] |= bit
+                    records.append((name, str(int(pos[j]) + 1), letters[cj], letters[(cj + 1) & 3]))
+        with torch.cuda.stream(self.eng.stream):
+            self.d_snp = [torch.from_numpy(x.view(np.int32)).to(self.eng.device) for x in (tc, ag, other)]
+        self.eng.stream.synchronize()
+        self.tables.snp_tc, self.tables.snp_ag, self.tables.snp_other = (t.data_ptr() for t in self.d_snp)
+        self.tables.p_snp_allele = float(p_allele)
+        return records
+
     def install(self):
         """Hand genome and annotation to the engine (sd_set_reference / sd_set_utrs)."""
         self.eng.set_reference(self.lo, self.hi, self.nmask, self.chrom_off, self.chrom_len)
@@ -164,19 +208,28 @@ class SynthWorkload(object):
         p.utr_first, p.utr_count = int(utr_first), int(utr_count)
         return p
 
-    def generate(self, p: L.SynthParams, want_mp=False, want_triples=False, coordinate_sorted=False, group=None):
+    @staticmethod
+    def _copy_params(p: L.SynthParams) -> L.SynthParams:
+        q = L.SynthParams()
+        ctypes.memmove(ctypes.byref(q), ctypes.byref(p), ctypes.sizeof(L.SynthParams))
+        return q
+
+    def generate(self, p: L.SynthParams, want_mp=False, want_triples=False, coordinate_sorted=False, group=None, gpos_range=None):
         """-> (DeviceBatch, triples tensor or None).
         coordinate_sorted: order the reads by alignment start like the sorted BAM `slamdunk count` reads;
         group (default: same as coordinate_sorted): additionally order them by alignment shape and strand the way
-        sd_decode_bam's SD_DECODE_GROUP does (plain match blocks first).  Triples follow the batch order."""
+        sd_decode_bam's SD_DECODE_GROUP does (plain match blocks first).  Triples follow the batch order.
+        gpos_range = (lo, hi): keep only the reads of the index range [first_read, first_read + n_reads) whose alignment
+        starts at a linear genome position in [lo, hi) -- one rank's share of a read stream sharded by chromosome region
+        (BASELINE.json config 5); returns (None, None) when no read falls there.  The reads themselves depend only on
+        (seed, read index), so the shards of any split add up to the unsharded stream."""
         eng, dev = self.eng, self.eng.device
         n = int(p.n_reads)
         T = int(p.tile_reads)
-        n_tiles = (n + T - 1) // T
         order = None
         if group is None:
             group = coordinate_sorted
-        if coordinate_sorted or group:
+        if coordinate_sorted or group or gpos_range is not None:
             with torch.cuda.stream(eng.stream):
                 gpos = torch.empty(n, dtype=torch.int32, device=dev)
                 cls = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -185,13 +238,26 @@ class SynthWorkload(object):
             eng._chk(self.lib.sd_synth_positions(eng.ctx, ctypes.byref(p), ctypes.byref(self.tables), gpos.data_ptr(),
                                                  cls.data_ptr()), "sd_synth_positions")
             with torch.cuda.stream(eng.stream):
-                key = (gpos.to(torch.int64) & 0xFFFFFFFF) if coordinate_sorted else torch.arange(n, device=dev, dtype=torch.int64)
+                g64 = gpos.to(torch.int64) & 0xFFFFFFFF
+                key = g64 if coordinate_sorted else torch.arange(n, device=dev, dtype=torch.int64)
                 if group:
                     key = key | (cls.to(torch.int64) << 40)
-                order = torch.argsort(key, stable=True).to(torch.int32)
-                del gpos, cls, key
+                if gpos_range is not None:
+                    sel = torch.nonzero((g64 >= int(gpos_range[0])) & (g64 < int(gpos_range[1]))).view(-1)
+                    order = sel[torch.argsort(key[sel], stable=True)].to(torch.int32)
+                    del sel
+                else:
+                    order = torch.argsort(key, stable=True).to(torch.int32)
+                del gpos, cls, key, g64
             eng.stream.synchronize()
+            if gpos_range is not None:
+                n = int(order.numel())
+                if n == 0:
+                    return None, None
+                p = self._copy_params(p)
+                p.n_reads = n
             p.order = order.data_ptr()
+        n_tiles = (n + T - 1) // T
         with torch.cuda.stream(eng.stream):
             counts = torch.empty(n, dtype=torch.int32, device=dev)
             tiles = torch.empty((n_tiles + 1) * 4, dtype=torch.int64, device=dev)
