@@ -704,6 +704,7 @@ def main():
             eng.count(part["db"], bench.params)
             k_ms += eng.last_kernel_ms()
     k_ms /= k_reps
+    k_split, k_left = eng.last_kernel_split()      # of the last batch counted
     mean_cig = 0.0
     for part in bench.parts:
         tiles = part["db"].tensors["tiles"].view(torch.int64).view(-1, 4)
@@ -714,7 +715,9 @@ def main():
     achieved = n_mine * bytes_per_read / (k_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": load_ncu_traffic(args), "kernel": "sd_count_kernel", "kernel_ms": k_ms,
+                "traffic": load_ncu_traffic(args), "kernel": "sd_lean_kernel + sd_count_kernel (staged, plain) on the tiles it leaves", "kernel_ms": k_ms,
+                "kernel_split_last_batch": {"lean_ms": k_split[0], "staged_ms": k_split[1], "plain_ms": k_split[2], "tiles": int(bench.parts[-1]["db"].batch.n_tiles),
+                                            "tiles_left_to_staged": k_left[0], "tiles_left_to_plain": k_left[1]},
                 "algorithmic_bytes_per_read": bytes_per_read, "algorithmic_bytes_source": "SURVEY.md 8(d): ceil(L/2) + L + 4c + 17",
                 "layout_bytes_per_read": layout_bytes, "achieved_layout_bytes": n_mine * layout_bytes / (k_ms * 1e-3) / 1e9,
                 "frac_layout_bytes": n_mine * layout_bytes / (k_ms * 1e-3) / 1e9 / peak,

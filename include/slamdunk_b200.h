@@ -41,7 +41,7 @@ extern "C" {
 #define SD_ERR_LIMIT (-6)
 #define SD_ERR_NOMEM (-7)
 
-#define SD_ABI_VERSION 7
+#define SD_ABI_VERSION 8
 
 typedef struct sd_ctx sd_ctx;
 
@@ -142,14 +142,21 @@ typedef struct sd_batch {
     uint32_t spans_epoch;   /* set by sd_tile_spans; descriptors made before a later sd_set_reference / sd_set_utrs are ignored */
 } sd_batch;
 
-/* What the staged count kernel copies for one tile besides its columns, as [begin, end) byte offsets into two
+/* What the staged count kernels copy for one tile besides its columns, as [begin, end) byte offsets into two
  * library-internal tables: the strand-merged reference planes (16 bytes per 32 linear positions) over the stretch of the
  * genome the tile's countable reads cover -- mapped, on a FASTA chromosome, position inside it -- and the run of
  * annotation entries (both strands, sorted by start) that can overlap that stretch.  A tile with reads all over the genome
- * (unsorted input) is described by an impossible size; sd_count then counts it with per-read lookups. */
+ * (unsorted input) is described by an impossible size; sd_count then counts it with per-read lookups.
+ * The second half describes the tile for the LEAN kernel, which only takes tiles whose countable reads are all alike:
+ * one match block (M / = / X) of the same l_seq bases, on one chromosome, fully inside it, with a window and an entry run
+ * that fit the kernel's stage.  win / ent then hold (byte offset << 16 | bytes to copy) and `lean` the common l_seq
+ * (0 = not such a tile), g0 the linear-genome offset of the tile's chromosome (linear position = g0 + pos). */
 typedef struct sd_tile_span {
     uint64_t win_begin, win_end;
     uint64_t ent_begin, ent_end;
+    uint64_t win, ent;
+    uint32_t lean, g0;
+    uint64_t reserved;
 } sd_tile_span;
 
 /* Where the per-read mismatch list comes from. */
@@ -274,6 +281,11 @@ int sd_tcontent(sd_ctx *ctx, int64_t *d_tcontent);
 int64_t sd_launch_count(const sd_ctx *ctx);
 /* Tiles of the most recent sd_count that the staged kernel handed on to the plain one (diagnostic; waits for the stream). */
 int64_t sd_last_leftover_tiles(sd_ctx *ctx);
+/* The same split over the launches a batch with span descriptors takes -- ms[0] lean kernel (tiles whose reads are all one match
+ * block of the same length), ms[1] staged kernel (the other tiles), ms[2] plain kernel (tiles spread too widely to stage) -- and the
+ * number of tiles handed from the first to the second (left[0]) and from the second to the third launch (left[1]).  Diagnostic;
+ * waits for the stream. */
+int sd_last_kernel_split(sd_ctx *ctx, float ms[3], int64_t left[2]);
 /* Duration of the most recent sd_count kernel on its stream (CUDA events), ms; <0 if none. */
 float sd_last_kernel_ms(sd_ctx *ctx);
 

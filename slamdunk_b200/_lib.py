@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SLAMDUNK_B200_LIB") or os.path.join(HERE, "libslamdunk_b200.so")   # env: kernel experiments
 
 SD_OK = 0
-SD_ABI_VERSION = 7   # 7 = SNP alleles in the generator (sd_synth_tables); 6 = sd_hbatch.n_mapped_no_xi/nm, wire form; include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual; 4 = BAI writer; 5 = sd_read_stats
+SD_ABI_VERSION = 8   # 8 = 64-byte sd_tile_span (lean-kernel tile description); 7 = SNP alleles in the generator (sd_synth_tables); 6 = sd_hbatch.n_mapped_no_xi/nm, wire form; include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual; 4 = BAI writer; 5 = sd_read_stats
 SD_F_REVERSE, SD_F_UNMAPPED, SD_F_SECONDARY, SD_F_SUPPLEMENTARY = 0x01, 0x02, 0x04, 0x08
 SD_F_HAS_MP, SD_F_SKIP, SD_F_NEWNAME, SD_F_PAD = 0x10, 0x20, 0x40, 0x80
 SD_REF_NONE = 0xFFFF
@@ -143,6 +143,7 @@ PROTOTYPES = {
     "sd_launch_count": (ctypes.c_int64, [_VP]),
     "sd_last_leftover_tiles": (ctypes.c_int64, [_VP]),
     "sd_last_kernel_ms": (ctypes.c_float, [_VP]),
+    "sd_last_kernel_split": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int64)]),
     "sd_filter": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(Params), _VP, _VP, _VP, _VP, _VP,
                                  ctypes.c_uint32, _VP, _VP, _VP]),
     "sd_rewrite_bam": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, _VP, _VP, ctypes.c_uint64, ctypes.c_int,

@@ -123,8 +123,9 @@ struct SpanArgs {
     const uint4 *ment;
     const uint32_t *bin_first_m;
     uint32_t n_ment;
-    ulonglong4 *out;
+    sd_tile_span *out;
     uint64_t n_refm;
+    uint32_t W, cap_win, cap_ent;   // the count kernels' window words and stage room for this batch (span_caps)
 };
 
 __global__ void sd_tile_spans_kernel(const SpanArgs A) {
@@ -141,12 +142,19 @@ __global__ void sd_tile_spans_kernel(const SpanArgs A) {
         const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xs, d);
         if (lane >= (uint32_t)d) xs += t;
     }
-    bool countable = !(flags & (SD_F_PAD | SD_F_UNMAPPED | SD_F_SKIP)) && ref < A.n_chrom && !(nocig && ncig > 1u);
+    const bool cand = !(flags & (SD_F_PAD | SD_F_UNMAPPED | SD_F_SKIP)) && ref < A.n_chrom;   // what the lean kernel takes for a countable record
+    bool countable = cand && !(nocig && ncig > 1u);
     uint32_t clen = 0, g = 0xFFFFFFFFu, e = 0u;
-    if (countable) {
+    bool alike = true;   // lean: one match block of l_seq bases, inside the chromosome
+    if (cand) {
         clen = A.chrom_len[ref];
-        countable = r.pos >= 0 && (uint32_t)r.pos < clen;
+        alike = ncig == 1u && lseq >= 1u && r.pos >= 0 && (uint64_t)r.pos + lseq <= clen;
+        if (alike && !nocig) {
+            const uint32_t c = A.cigar[c0 / 4u + (xs - ncig)];
+            alike = ((0x181u >> (c & 15u)) & 1u) && (c >> 4) == lseq;
+        }
     }
+    if (countable) countable = r.pos >= 0 && (uint32_t)r.pos < clen;
     if (countable) {
         uint32_t reflen = 0;
         if (nocig) reflen = ncig ? lseq : 0u;
@@ -164,18 +172,33 @@ __global__ void sd_tile_spans_kernel(const SpanArgs A) {
     }
     const uint32_t gmin = __reduce_min_sync(0xFFFFFFFFu, g), gend = __reduce_max_sync(0xFFFFFFFFu, e);
     // {window begin, end, entries begin, end} as byte offsets into the strand-merged reference and annotation tables
-    ulonglong4 out = make_ulonglong4(0ull, 0ull, 0ull, 0ull);   // no countable read: nothing to stage
+    sd_tile_span out;
+    memset(&out, 0, sizeof out);   // no countable read: nothing to stage
+    const unsigned cm = __ballot_sync(0xFFFFFFFFu, cand);
+    const int first = cm ? __ffs((int)cm) - 1 : 0;
+    const uint32_t ref0 = __shfl_sync(0xFFFFFFFFu, ref, first), lseq0 = __shfl_sync(0xFFFFFFFFu, lseq, first);
+    bool lean = cm != 0u && __all_sync(0xFFFFFFFFu, !cand || (alike && ref == ref0 && lseq == lseq0)) && lseq0 <= 32u * A.W;
     if (gend != 0u) {
         const uint32_t i0 = A.bin_first_m[gmin >> SD_BIN_SHIFT];
         const uint32_t i = i0 + lane;
         const bool can = i < A.n_ment && __ldg(&A.ment[2 * (size_t)i]).x < gend;   // sorted by start: a prefix of the lanes
         const unsigned b = __ballot_sync(0xFFFFFFFFu, can);
         const unsigned long long w0 = gmin >> 5, w1 = ((unsigned long long)(gend - 1u) >> 5) + 1ull;
-        out.x = w0 * 16ull;
-        out.y = w1 * 16ull;
-        out.z = (unsigned long long)i0 * 32ull;
-        out.w = out.z + (unsigned long long)__popc(b) * 32ull;
-        if (b == 0xFFFFFFFFu || w1 + 32ull > A.n_refm) out.y = out.x + (1ull << 40);   // too many candidate entries: never staged
+        out.win_begin = w0 * 16ull;
+        out.win_end = w1 * 16ull;
+        out.ent_begin = (unsigned long long)i0 * 32ull;
+        out.ent_end = out.ent_begin + (unsigned long long)__popc(b) * 32ull;
+        const unsigned long long win_bytes = (w1 - w0 + A.W) * 16ull, ent_bytes = (unsigned long long)__popc(b) * 32ull;
+        if (b == 0xFFFFFFFFu || w1 + 32ull > A.n_refm) {   // too many candidate entries: never staged
+            out.win_end = out.win_begin + (1ull << 40);
+            lean = false;
+        }
+        if (lean && win_bytes <= A.cap_win && ent_bytes <= A.cap_ent) {
+            out.win = (out.win_begin << 16) | win_bytes;
+            out.ent = (out.ent_begin << 16) | ent_bytes;
+            out.lean = lseq0;
+            out.g0 = A.chrom_off[ref0];
+        }
     }
     if (lane == 0) A.out[tile] = out;
 }
@@ -219,6 +242,8 @@ extern "C" int sd_create(int device, void *stream, sd_ctx **out) {
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     cudaEventCreate(&ctx->ev_k0);
     cudaEventCreate(&ctx->ev_k1);
+    cudaEventCreate(&ctx->ev_split[0]);
+    cudaEventCreate(&ctx->ev_split[1]);
     for (int i = 0; i < 2; i++) {
         cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
@@ -260,6 +285,7 @@ extern "C" void sd_destroy(sd_ctx *ctx) {
     cudaFree(ctx->d_leftover);
     cudaFree(ctx->d_xi_dict);
     cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1);
+    cudaEventDestroy(ctx->ev_split[0]); cudaEventDestroy(ctx->ev_split[1]);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_copy[i]); cudaEventDestroy(ctx->ev_done[i]); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -492,6 +518,20 @@ extern "C" int sd_bind_outputs(sd_ctx *ctx, int64_t *d_counters, int32_t *d_pos_
     return SD_OK;
 }
 
+// Window words of the count kernels for a batch, and the room a stage gives a tile's reference window and annotation entries.
+// The window must hold the alignment's reference span, i.e. the read plus its deletions -- a read that does not fit takes the
+// per-base path, two orders of magnitude slower, and stalls its whole warp (190 bp reads with 2 % short indels in a 192-base
+// window: 9.6 instead of 15 G reads/s).  The batch says how wide its alignments are (spliced ones aside); without that, 16
+// bases of slack cover the usual gaps.
+static void span_caps(const sd_batch *b, uint32_t &need, uint32_t &Wn, uint32_t &cap_win, uint32_t &cap_ent) {
+    need = b->max_span ? std::max(b->max_lseq, b->max_span) : b->max_lseq + 16u;
+    Wn = need <= 128 ? 4 : need <= 192 ? 6 : need <= 256 ? 8 : need <= 320 ? 10 : need <= 384 ? 12 : 16;
+    // the reads' words, a few more for the spread of their starts, W behind the last: 864 bp of tile at W = 4 -- the thinly
+    // populated classes of a grouped batch (clipped / indel reads) fit too; 8 entries
+    cap_win = align128(16u * (6u * Wn + 8u));
+    cap_ent = 256u;
+}
+
 int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, cudaStream_t stream, uint8_t *read_tc, bool timed) {
     if (!ctx->refx[0]) return sd_fail(ctx, SD_ERR_STATE, "sd_count before sd_set_reference");
     if (!ctx->counters) return sd_fail(ctx, SD_ERR_STATE, "sd_count before sd_bind_outputs");
@@ -559,17 +599,16 @@ int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, cudaStre
     A.pos_cov = ctx->pos_cov; A.pos_tc = ctx->pos_tc;
     A.stats = reinterpret_cast<unsigned long long *>(ctx->stats);
     A.read_tc = read_tc;
-    if (!ctx->d_tile_counter) SD_CUDA(ctx, cudaMalloc(&ctx->d_tile_counter, 4 * sizeof(unsigned int)));
-    SD_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_counter, 0, 4 * sizeof(unsigned int), stream));
+    if (!ctx->d_tile_counter) SD_CUDA(ctx, cudaMalloc(&ctx->d_tile_counter, 8 * sizeof(unsigned int)));
+    SD_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_counter, 0, 8 * sizeof(unsigned int), stream));
     A.tile_counter = ctx->d_tile_counter;
-    if (A.spans) {   // tiles the staged kernel hands on to the plain one
+    if (A.spans) {   // two lists: tiles the lean kernel hands on to the staged one, and the staged one to the plain one
         if (ctx->leftover_cap < b->n_tiles) {
             SD_CUDA(ctx, cudaStreamSynchronize(stream));
             cudaFree(ctx->d_leftover);
-    cudaFree(ctx->d_xi_dict);
             ctx->d_leftover = nullptr;
             ctx->leftover_cap = 0;
-            SD_CUDA(ctx, cudaMalloc(&ctx->d_leftover, (size_t)b->n_tiles * sizeof(uint32_t)));
+            SD_CUDA(ctx, cudaMalloc(&ctx->d_leftover, 2 * (size_t)b->n_tiles * sizeof(uint32_t)));
             ctx->leftover_cap = b->n_tiles;
         }
         A.leftover = ctx->d_leftover;
@@ -594,15 +633,11 @@ int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, cudaStre
         A.qual_bytes = last.qual_off;
     }
 #endif
-    // Window of W 32-base words: it must hold the alignment's reference span, i.e. the read plus its deletions -- a read
-    // that does not fit takes the per-base path, two orders of magnitude slower, and stalls its whole warp (190 bp reads
-    // with 2 % short indels in a 192-base window: 9.6 instead of 15 G reads/s).  The batch says how wide its alignments
-    // are (spliced ones aside); without that, 16 bases of slack cover the usual gaps.
-    const uint32_t need = b->max_span ? std::max(b->max_lseq, b->max_span) : b->max_lseq + 16u;
-    if (A.spans) {   // room for the staged window (the reads' words, a few more for the spread of their starts, W behind the last) and 8 entries
-        const uint32_t Wn = need <= 128 ? 4 : need <= 192 ? 6 : need <= 256 ? 8 : need <= 320 ? 10 : need <= 384 ? 12 : 16;
-        A.cap_win = align128(16u * (6u * Wn + 8u));   // 864 bp of tile at W = 4: the thinly populated classes of a grouped batch (clipped / indel reads) fit too
-        A.cap_ent = 256u;
+    uint32_t need, Wn, cap_win, cap_ent;
+    span_caps(b, need, Wn, cap_win, cap_ent);
+    if (A.spans) {
+        A.cap_win = cap_win;
+        A.cap_ent = cap_ent;
     }
 #define SD_DISPATCH_W(SB, QB)                                                        \
     do {                                                                             \
@@ -626,8 +661,10 @@ int tile_spans_on(sd_ctx *ctx, cudaStream_t stream, const sd_batch *b, void *d_s
     S.rec = b->rec; S.cigar = b->cigar; S.tiles = b->tiles; S.n_tiles = b->n_tiles;
     S.chrom_off = ctx->d_chrom_off; S.chrom_len = ctx->d_chrom_len; S.n_chrom = ctx->n_chrom;
     S.ment = ctx->d_ment; S.bin_first_m = ctx->d_bin_first_m; S.n_ment = ctx->n_ment;
-    S.out = reinterpret_cast<ulonglong4 *>(d_spans);
+    S.out = reinterpret_cast<sd_tile_span *>(d_spans);
     S.n_refm = ctx->n_words + SD_REF_PAD_WORDS;
+    uint32_t need;
+    span_caps(b, need, S.W, S.cap_win, S.cap_ent);
     const unsigned blocks = (unsigned)(((uint64_t)b->n_tiles * 32u + 255u) / 256u);
     sd_tile_spans_kernel<<<blocks, 256, 0, stream>>>(S);
     ctx->launches++;
@@ -669,6 +706,27 @@ extern "C" float sd_last_kernel_ms(sd_ctx *ctx) {
     return ms;
 }
 
+extern "C" int sd_last_kernel_split(sd_ctx *ctx, float ms[3], int64_t left[2]) {
+    if (!ctx || !ms || !left) return SD_ERR_ARG;
+    ms[0] = ms[1] = ms[2] = 0.f;
+    left[0] = left[1] = 0;
+    if (!ctx->have_kernel_time || !ctx->d_tile_counter) return sd_fail(ctx, SD_ERR_STATE, "no timed sd_count yet");
+    SD_CUDA(ctx, cudaSetDevice(ctx->device));
+    SD_CUDA(ctx, cudaEventSynchronize(ctx->ev_k1));
+    cudaEvent_t marks[4] = {ctx->ev_k0, ctx->ev_split[0], ctx->ev_split[1], ctx->ev_k1};
+    if (ctx->split_marks == 2) {
+        for (int i = 0; i < 3; i++) SD_CUDA(ctx, cudaEventElapsedTime(&ms[i], marks[i], marks[i + 1]));
+    } else if (ctx->split_marks == 1) {   // no lean launch
+        SD_CUDA(ctx, cudaEventElapsedTime(&ms[1], ctx->ev_k0, ctx->ev_split[1]));
+        SD_CUDA(ctx, cudaEventElapsedTime(&ms[2], ctx->ev_split[1], ctx->ev_k1));
+    } else SD_CUDA(ctx, cudaEventElapsedTime(&ms[2], ctx->ev_k0, ctx->ev_k1));
+    unsigned int n[2] = {0, 0};
+    SD_CUDA(ctx, cudaMemcpy(n, ctx->d_tile_counter + 3, sizeof n, cudaMemcpyDeviceToHost));
+    left[0] = n[0];
+    left[1] = n[1];
+    return SD_OK;
+}
+
 extern "C" int64_t sd_launch_count(const sd_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int64_t sd_last_leftover_tiles(sd_ctx *ctx) {
@@ -676,7 +734,7 @@ extern "C" int64_t sd_last_leftover_tiles(sd_ctx *ctx) {
     cudaSetDevice(ctx->device);
     unsigned int n = 0;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
-    if (cudaMemcpy(&n, ctx->d_tile_counter + 2, sizeof n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (cudaMemcpy(&n, ctx->d_tile_counter + 4, sizeof n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return (int64_t)n;
 }
 

@@ -1,5 +1,5 @@
 // one column form of the count kernel: SEQ form 2, quality planes 4 (0 = bytes); see sd_count_kernel.cuh
-#include "sd_count_kernel.cuh"
+#include "sd_count_lean.cuh"
 
 template int launch_count<4, 2, 4>(sd_ctx *, CountArgs &, cudaStream_t, bool);
 template int launch_count<6, 2, 4>(sd_ctx *, CountArgs &, cudaStream_t, bool);

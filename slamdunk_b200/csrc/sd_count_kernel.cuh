@@ -172,11 +172,12 @@ __device__ __forceinline__ uint32_t range_word(int k, int lo, int hi) {
 }
 
 // @region helpers
-// bits [0, hi) of the window restricted to word k
+// bits [0, hi) of the window restricted to word k: the low max(0, min(32, hi - 32 k)) bits, as one add-and-clamp and one
+// clamped funnel shift (the high word of 0x00000000FFFFFFFF << n)
 __device__ __forceinline__ uint32_t prefix_word(int k, int hi) {
     int b = hi - 32 * k;
-    b = b < 0 ? 0 : (b > 32 ? 32 : b);
-    return (uint32_t)((1ull << b) - 1ull);
+    b = b < 0 ? 0 : b;
+    return __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)b);
 }
 
 // @region utr_accumulate
@@ -229,8 +230,8 @@ __device__ __forceinline__ uint32_t row_group_is_base(const uint32_t *row, uint3
 // `readQlty >= minQual` (SlamSeqFile.py:330) is the bit-sliced comparison code >= q_cmin: 2 LOP3 per plane for 32 bases.
 // CM: take the comparison constant as ready-made masks from the parameter block (A.q_m) instead of deriving them from
 // A.q_cmin.  Same result; the count kernel uses the mask form (150 bp: 1.83 vs 2.31 ms), the per-base lookups the other.
-template <int QB, bool CM>
-__device__ __forceinline__ uint32_t planes_ge(const uint32_t (&p)[QB], const CountArgs &A) {
+template <int QB, bool CM, class AR>
+__device__ __forceinline__ uint32_t planes_ge(const uint32_t (&p)[QB], const AR &A) {
     if (CM && QB == 2)   // code >= c over two planes: c = 3: p1 & p0; 2: p1; 1: p1 | p0; 0: all; 4: none
         return (((p[1] & (p[0] | A.q_m[0])) | (p[0] & A.q_m[1])) | A.q_m[2]) & A.q_m[3];
     const uint32_t cmin = A.q_cmin;
@@ -243,8 +244,8 @@ __device__ __forceinline__ uint32_t planes_ge(const uint32_t (&p)[QB], const Cou
     }
     return (cmin >> QB) ? 0u : (gt | eq);
 }
-template <int QB, bool CM = false>
-__device__ __forceinline__ uint32_t row_group_qual_ok(const uint32_t *row, uint32_t g, const CountArgs &A) {
+template <int QB, bool CM = false, class AR = CountArgs>
+__device__ __forceinline__ uint32_t row_group_qual_ok(const uint32_t *row, uint32_t g, const AR &A) {
     uint32_t p[QB];
     if (QB == 2) {
         const uint2 x = reinterpret_cast<const uint2 *>(row)[g * SD_TILE_READS];
@@ -973,14 +974,15 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
     // windows and table rows in L1.
     uint32_t *s_tile = reinterpret_cast<uint32_t *>(mine + (size_t)A.n_stages * stage_bytes + 16u);   // [n_stages] tile held by each stage
     uint32_t claim_next = 0, claim_end = 0;   // lane 0 only
-    const uint32_t n_queue = (!STAGED && A.tile_list) ? *A.n_list : A.n_tiles;
+    const uint32_t n_queue = A.tile_list ? *A.n_list : A.n_tiles;
     auto claim = [&]() -> uint32_t {          // next tile for this warp, or 0xFFFFFFFF when the queue is empty
         if (claim_next == claim_end) {
-            claim_next = atomicAdd(A.tile_counter, (unsigned int)SD_CLAIM);
-            claim_end = claim_next + SD_CLAIM;
+            const unsigned int chunk = (unsigned int)SD_CLAIM;
+            claim_next = atomicAdd(A.tile_counter, chunk);
+            claim_end = claim_next + chunk;
         }
         const uint32_t t = claim_next++;
-        if (!STAGED && A.tile_list) return t < n_queue ? A.tile_list[t] : 0xFFFFFFFFu;
+        if (A.tile_list) return t < n_queue ? A.tile_list[t] : 0xFFFFFFFFu;
         return t < n_queue ? t : 0xFFFFFFFFu;
     };
     // @region tma_issue
@@ -1017,7 +1019,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
         unsigned char *base = stages + (size_t)stage * stage_bytes;
         const uint4 c0 = s_col[2 * lane], c1 = s_col[2 * lane + 1];
         const unsigned char *my_src = reinterpret_cast<const unsigned char *>((unsigned long long)c0.x | ((unsigned long long)c0.y << 32));
-        const unsigned long long *tp = reinterpret_cast<const unsigned long long *>((unsigned long long)c0.z | ((unsigned long long)c0.w << 32)) + 4ull * tile;
+        const unsigned long long *tp = reinterpret_cast<const unsigned long long *>((unsigned long long)c0.z | ((unsigned long long)c0.w << 32)) + ((STAGED && lane >= 5u) ? 8ull : 4ull) * tile;   // sd_tile is 4 words, sd_tile_span 8
         unsigned long long off0 = __ldg(tp), off1 = __ldg(tp + c1.y);
         if (lane == 0) {
             off0 = tile * (SD_TILE_READS * (unsigned long long)sizeof(sd_read_rec));
@@ -1086,7 +1088,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_MIN_CTAS(W)) sd_count_kerne
 
 #ifndef SD_NO_DESC_L1PF
         // lane 0 will read the next tile's descriptors when it refills the stage: start that (DRAM-latency) load now
-        if (lane == 0 && claim_next != claim_end && claim_next < A.n_tiles) {
+        if (lane == 0 && !A.tile_list && claim_next != claim_end && claim_next < A.n_tiles) {
             asm volatile("prefetch.global.L1 [%0];" ::"l"(A.tiles + claim_next));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(A.tiles + claim_next + 1));
         }
@@ -1367,18 +1369,39 @@ static int launch_one(sd_ctx *ctx, CountArgs &A, cudaStream_t stream) {
     return SD_OK;
 }
 
-// A.tile_counter points at three zeroed words: the two launches' queue heads and the number of tiles the first left over.
+// Up to three launches count a batch that carries span descriptors: the LEAN kernel (sd_count_lean.cuh) takes the tiles whose reads
+// are all alike and appends the others to a list; the STAGED kernel counts that list and appends the tiles whose reads are spread
+// too widely for a stage to a second list; the plain kernel counts that one with per-read lookups.
+// A.tile_counter points at eight zeroed words: the three queue heads (0..2) and the lengths of the two lists (3, 4).
+template <int W, int QB, bool VERIFY>
+int launch_lean(sd_ctx *ctx, const CountArgs &A, cudaStream_t stream, uint32_t *list_out, unsigned int *n_out);
+
 template <int W, int SB, int QB>
 int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
     if (timed) SD_CUDA(ctx, cudaEventRecord(ctx->ev_k0, stream));
     unsigned int *words = A.tile_counter;
     int rc = SD_OK;
+    int marks = 0;
     if (A.spans) {
-        A.n_leftover = words + 2;
-        if ((rc = launch_one<W, SB, QB, true>(ctx, A, stream)) != SD_OK) return rc;
-        A.tile_list = A.leftover;
-        A.n_list = words + 2;
+        static int lean_env = -1;
+        if (lean_env < 0) { const char *e = getenv("SD_LEAN"); lean_env = e ? atoi(e) : 1; }
+        uint32_t *list1 = A.leftover, *list2 = A.leftover + A.n_tiles;
+        if constexpr (SB == 2 && QB > 0) if (lean_env && !A.force_slow && (A.mismatch_source == SD_MISMATCH_CIGAR || A.mismatch_source == SD_MISMATCH_VERIFY)) {
+            if (A.mismatch_source == SD_MISMATCH_CIGAR) rc = launch_lean<W, (QB > 0 ? QB : 2), false>(ctx, A, stream, list1, words + 3);
+            else rc = launch_lean<W, (QB > 0 ? QB : 2), true>(ctx, A, stream, list1, words + 3);
+            if (rc != SD_OK) return rc;
+            A.tile_list = list1;
+            A.n_list = words + 3;
+            if (timed) { SD_CUDA(ctx, cudaEventRecord(ctx->ev_split[0], stream)); marks = 2; }
+        }
         A.tile_counter = words + 1;
+        A.leftover = list2;
+        A.n_leftover = words + 4;
+        if ((rc = launch_one<W, SB, QB, true>(ctx, A, stream)) != SD_OK) return rc;
+        if (timed) { SD_CUDA(ctx, cudaEventRecord(ctx->ev_split[1], stream)); if (!marks) marks = 1; }
+        A.tile_list = list2;
+        A.n_list = words + 4;
+        A.tile_counter = words + 2;
         A.spans = nullptr;
         A.cap_win = A.cap_ent = 0;
     }
@@ -1386,6 +1409,7 @@ int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
     if (timed) {
         SD_CUDA(ctx, cudaEventRecord(ctx->ev_k1, stream));
         ctx->have_kernel_time = true;
+        ctx->split_marks = marks;
     }
     return SD_OK;
 }

@@ -17,6 +17,8 @@ struct sd_ctx {
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_split[2] = {nullptr, nullptr};   // between the lean, staged and plain launches of a timed sd_count
+    int split_marks = 0;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     bool have_kernel_time = false;
     std::string err;

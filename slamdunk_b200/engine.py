@@ -352,7 +352,7 @@ class CountEngine(object):
         device batch; redo after set_reference / set_utrs (stale descriptors are ignored by the library, not misused)."""
         nt = int(dbatch.batch.n_tiles)
         with torch.cuda.stream(self.stream):
-            spans = torch.empty(max(1, nt) * 32, dtype=torch.uint8, device=self.device)
+            spans = torch.empty(max(1, nt) * 64, dtype=torch.uint8, device=self.device)      # sizeof(sd_tile_span)
         self._chk(self.lib.sd_tile_spans(self.ctx, ctypes.byref(dbatch.batch), _t_ptr(spans)), "sd_tile_spans")
         dbatch.spans_tensor = spans      # owned by this DeviceBatch object (the tensors dict may be shared between views)
         dbatch.spans_key = (self.ctx.value, self._epoch)
@@ -383,6 +383,13 @@ class CountEngine(object):
 
     def last_kernel_ms(self) -> float:
         return float(self.lib.sd_last_kernel_ms(self.ctx))
+
+    def last_kernel_split(self):
+        """-> ([lean ms, staged ms, plain ms], [tiles lean -> staged, tiles staged -> plain]) of the most recent count"""
+        ms = (ctypes.c_float * 3)()
+        left = (ctypes.c_int64 * 2)()
+        self._chk(self.lib.sd_last_kernel_split(self.ctx, ms, left), "sd_last_kernel_split")
+        return [float(x) for x in ms], [int(x) for x in left]
 
     def leftover_tiles(self) -> int:
         return int(self.lib.sd_last_leftover_tiles(self.ctx))
