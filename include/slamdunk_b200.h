@@ -148,9 +148,10 @@ typedef struct sd_batch {
  * annotation entries (both strands, sorted by start) that can overlap that stretch.  A tile with reads all over the genome
  * (unsorted input) is described by an impossible size; sd_count then counts it with per-read lookups.
  * The second half describes the tile for the LEAN kernel, which only takes tiles whose countable reads are all alike:
- * one match block (M / = / X) of the same l_seq bases, on one chromosome, fully inside it, with a window and an entry run
- * that fit the kernel's stage.  win / ent then hold (byte offset << 16 | bytes to copy) and `lean` the common l_seq
- * (0 = not such a tile), g0 the linear-genome offset of the tile's chromosome (linear position = g0 + pos). */
+ * one match block (M / = / X) of the same l_seq bases, on one chromosome, fully inside it, with at most 16 annotation
+ * entries in reach.  `lean` then holds the common l_seq (0 = not such a tile), g0 the linear-genome offset of the tile's
+ * chromosome (linear position = g0 + pos), ent = byte offset of the tile's first entry << 16 | bytes of its entries, win the
+ * same for the reference window (informative). */
 typedef struct sd_tile_span {
     uint64_t win_begin, win_end;
     uint64_t ent_begin, ent_end;

@@ -193,8 +193,8 @@ __global__ void sd_tile_spans_kernel(const SpanArgs A) {
             out.win_end = out.win_begin + (1ull << 40);
             lean = false;
         }
-        if (lean && win_bytes <= A.cap_win && ent_bytes <= A.cap_ent) {
-            out.win = (out.win_begin << 16) | win_bytes;
+        if (lean && ent_bytes <= 16u * 32u) {   // the lean kernel walks the entries in a warp-uniform loop: at most 16
+            out.win = (out.win_begin << 16) | (win_bytes & 0xFFFFull);
             out.ent = (out.ent_begin << 16) | ent_bytes;
             out.lean = lseq0;
             out.g0 = A.chrom_off[ref0];

@@ -5,12 +5,19 @@
 // and plane-form qualities only.  Tiles that are not of that kind go, untouched, to the general kernels that follow
 // (sd_count_kernel<..., true> staged, then <..., false> plain).  Same outputs, bit for bit.
 //
-// Per warp: a ring of two shared-memory stages filled by TMA bulk copies (records, SEQ codes, quality planes, the tile's
-// reference window and annotation entries -- one copy per lane 0..4), one thread per read:
+// The columns are read straight from global memory into registers: in the group-major layout the 32 rows of one 32-base
+// group are 256 (SEQ, 2 quality planes) or 512 consecutive bytes, so "lane r loads group g of row r" is one fully coalesced
+// warp access -- no shared-memory stage and no bulk copy.  (A first version staged every tile with five cp.async.bulk copies
+// like the general kernel does.  It ran at exactly one bulk copy per 46 cycles per SM whatever else changed in the kernel:
+// the copy engine's request rate, not instruction issue or DRAM, was the limit -- 7.1 M copies of 64 B .. 1 KB for 50 M reads.
+// profiles/r2_lean_tma_*.)  The tile's reference window and annotation entries come through L1: without the stages almost
+// all of the SM's 228 KB is cache, and consecutive tiles of a sorted batch look at the same few lines.
+// One thread per read:
 //   filter predicates (dunks/filter.py:235-256)  ->  read mask "is C / is G and quality >= minQual" (SlamSeqFile.py:137-141, 330)
 //   AND reference planes "is T / is A, not a SNP" of the read's window (SlamSeqFile.py:333-344)  ->  tcCount, T coverage
-//   ->  warp-uniform walk over the tile's annotation entries: per-UTR counters as warp votes / reductions and at most five
-//   atomics (tcounter.py:216-248, 277-283), per-position coverage differences and conversions (tcounter.py:229-231, 246-248).
+//   ->  warp-uniform walk over the tile's annotation entries: per-UTR counters as warp votes / reductions, kept in registers
+//   while consecutive tiles stay in the same UTR (tcounter.py:216-248, 277-283), per-position coverage differences and
+//   conversions (tcounter.py:229-231, 246-248).
 #pragma once
 #include "sd_count_kernel.cuh"
 
@@ -19,9 +26,9 @@ struct LeanArgs {
     const unsigned char *seq, *qual, *mp;   // 2-bit SEQ column, plane-form qualities, MP entries (VERIFY) or null
     const sd_tile *tiles;
     const sd_tile_span *spans;
-    const unsigned char *refm, *ment;
+    const uint4 *refm, *ment;
     uint32_t n_tiles, n_chrom;
-    uint32_t cap_seq, cap_qual, cap_win, cap_ent, cap_mp;   // stage layout: rec | seq | qual | win | ent | mp, multiples of 128
+    uint32_t claim;               // consecutive tiles per queue access
     uint32_t q_cmin, q_m[4];
     int conv_threshold, filter_on, filter_mq, filter_max_nm;
     float filter_min_identity;
@@ -36,107 +43,59 @@ struct LeanArgs {
     uint32_t n_utr;
 };
 
-#define SD_LEAN_STAGES 2
+#ifndef SD_LEAN_DIAG
+#define SD_LEAN_DIAG 0   // timing experiments only (wrong results): 1 no conversion scatter, 2 no coverage adds, 4 no annotation walk, 8 no window loads
+#endif
+#ifndef SD_LEAN_CLAIM
+#define SD_LEAN_CLAIM 32   // most consecutive tiles per claim: a warp stays in one stretch of the genome (window and entry lines in L1, one
+                           // UTR's sums in registers) -- 1.05 instead of 1.16 ms per 50 M reads against chunks of 8.  Small batches get
+                           // smaller chunks, at least eight per warp, so that the grid drains evenly
+#endif
 #ifndef SD_LEAN_MIN_CTAS
 #define SD_LEAN_MIN_CTAS(W) SD_MIN_CTAS(W)
 #endif
-#define SD_LEAN_REC_BYTES (SD_TILE_READS * 20u)
 
 template <int W, int QB, bool VERIFY>
 __global__ void __launch_bounds__(SD_CTA_THREADS, SD_LEAN_MIN_CTAS(W)) sd_lean_kernel(const __grid_constant__ LeanArgs A) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t off_seq = SD_LEAN_REC_BYTES, off_qual = off_seq + A.cap_seq, off_win = off_qual + A.cap_qual, off_ent = off_win + A.cap_win,
-                   off_mp = off_ent + A.cap_ent;
-    const uint32_t stage_bytes = off_mp + A.cap_mp;
-    uint32_t *s_stats = reinterpret_cast<uint32_t *>(smem);   // [SD_SMEM_STATS]
-    unsigned char *mine = smem + 128u + (size_t)warp * (SD_LEAN_STAGES * stage_bytes + 128u);
-    uint64_t *full = reinterpret_cast<uint64_t *>(mine + SD_LEAN_STAGES * stage_bytes);   // [2]
-    uint4 *s_info = reinterpret_cast<uint4 *>(mine + SD_LEAN_STAGES * stage_bytes + 32u);   // [2][2] {lean, g0, win lo, win hi}, {ent lo, ent hi, tile, 0} of the tile in each stage
+    __shared__ uint32_t s_stats[SD_SMEM_STATS];
+    const uint32_t lane = threadIdx.x & 31u;
     if (threadIdx.x < SD_SMEM_STATS) s_stats[threadIdx.x] = 0u;
-    if (lane == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        mbar_fence_init();
-    }
     __syncthreads();
 
-    // --- per-lane copy constants: lane c < 5 (6 with VERIFY) moves column c of a tile into the stage
-    const unsigned char *my_src = reinterpret_cast<const unsigned char *>(A.rec);
-    uint32_t my_dst = 0u;
-    if (lane == 1) { my_src = A.seq; my_dst = off_seq; }
-    if (lane == 2) { my_src = A.qual; my_dst = off_qual; }
-    if (lane == 3) { my_src = A.refm; my_dst = off_win; }
-    if (lane == 4) { my_src = A.ment; my_dst = off_ent; }
-    if (lane == 5) { my_src = A.mp; my_dst = off_mp; }
-    constexpr uint32_t NCOPY = VERIFY ? 6u : 5u;
-    constexpr unsigned COPY_MASK = (1u << NCOPY) - 1u;
-
-    // tile queue: chunks of SD_CLAIM consecutive tiles per atomic.  Every lane keeps the chunk's bounds (warp-uniform); the atomic for
+    // tile queue: chunks of SD_LEAN_CLAIM consecutive tiles per atomic.  Every lane keeps the chunk's bounds (warp-uniform); the atomic for
     // the chunk AFTER the current one is already in flight (lane 0's `pend`), so taking a new chunk never waits for the queue head.
     uint32_t claim_next, claim_end, pend = 0u;
     {
         uint32_t c = 0u;
-        if (lane == 0) c = atomicAdd(A.tile_counter, (unsigned int)SD_CLAIM);
+        if (lane == 0) c = atomicAdd(A.tile_counter, A.claim);
         claim_next = __shfl_sync(0xFFFFFFFFu, c, 0);
-        claim_end = claim_next + SD_CLAIM;
-        if (lane == 0) pend = atomicAdd(A.tile_counter, (unsigned int)SD_CLAIM);
+        claim_end = claim_next + A.claim;
+        if (lane == 0) pend = atomicAdd(A.tile_counter, A.claim);
     }
     auto claim = [&]() -> uint32_t {
         if (claim_next == claim_end) {   // warp-uniform
             claim_next = __shfl_sync(0xFFFFFFFFu, pend, 0);
-            claim_end = claim_next + SD_CLAIM;
-            if (lane == 0 && claim_next < A.n_tiles) pend = atomicAdd(A.tile_counter, (unsigned int)SD_CLAIM);
+            claim_end = claim_next + A.claim;
+            if (lane == 0 && claim_next < A.n_tiles) pend = atomicAdd(A.tile_counter, A.claim);
         }
         const uint32_t t = claim_next++;
         return t < A.n_tiles ? t : 0xFFFFFFFFu;
     };
-    // A tile's description is five (six / seven with VERIFY) 64-bit words in two tables; lane c fetches word c as soon as the tile is
-    // claimed -- one tile ahead of the copies that need it -- and keeps it in a register:
-    //   0 spans[t].{lean, g0}   1 tiles[t].seq_off   2 tiles[t].qual_off   3 spans[t].win   4 spans[t].ent   5, 6 tiles[t], tiles[t + 1].mp_off
+    // A tile's description is four (five with VERIFY) 64-bit words in two tables; lane c fetches word c as soon as the tile is
+    // claimed -- one tile ahead of its use -- and keeps it in a register:
+    //   0 spans[t].{lean, g0}   1 tiles[t].seq_off   2 tiles[t].qual_off   3 spans[t].ent   4 tiles[t].mp_off
     auto fetch_desc = [&](uint32_t tile) -> unsigned long long {
-        if (tile == 0xFFFFFFFFu || lane >= NCOPY + (VERIFY ? 1u : 0u)) return 0ull;
-        const bool in_tiles = lane == 1u || lane == 2u || lane >= 5u;
+        if (tile == 0xFFFFFFFFu || lane >= (VERIFY ? 5u : 4u)) return 0ull;
+        const bool in_tiles = lane == 1u || lane == 2u || lane == 4u;
         const unsigned char *base = in_tiles ? reinterpret_cast<const unsigned char *>(A.tiles) : reinterpret_cast<const unsigned char *>(A.spans);
-        //                      lane:     6    5    4    3    2    1    0
-        const uint32_t field = (uint32_t)((0x38182820080030ull >> (8u * lane)) & 0xFFull);   // byte offset of the word in its table entry
+        //                      lane:   4    3    2    1    0
+        const uint32_t field = (uint32_t)((0x1828080030ull >> (8u * lane)) & 0xFFull);   // byte offset of the word in its table entry
         return __ldg(reinterpret_cast<const unsigned long long *>(base + (size_t)tile * (in_tiles ? sizeof(sd_tile) : sizeof(sd_tile_span)) + field));
     };
-    // Issue the copies of `tile` (description words `x`, one per lane, from fetch_desc) into `stage`.  Returns lq = l_seq of a lean
-    // tile, 0 for any other -- no copies are made and the consumer hands the tile on without waiting.  The description -- {lean, g0},
-    // win, ent, the tile index -- waits in s_info[stage] for the consumer.
-    auto issue = [&](uint32_t tile, uint32_t stage, unsigned long long x) -> uint32_t {
-        const uint32_t lseq = __shfl_sync(0xFFFFFFFFu, (uint32_t)x, 0);
-        unsigned long long *info = reinterpret_cast<unsigned long long *>(&s_info[2u * stage]);
-        if (lane == 0u) info[3] = tile;
-        if (lseq == 0u) { __syncwarp(); return 0u; }   // warp-uniform
-        if (lane == 0u || lane == 3u || lane == 4u) info[lane == 0u ? 0 : lane - 2u] = x;   // {lean, g0} | win | ent
-        // every lane goes through the same instructions (lanes without a column copy nothing): the warp stays converged for the reduction
-        const uint32_t G = (lseq + 31u) >> 5;
-        unsigned long long off = x;
-        uint32_t bytes = 0u;
-        if (lane == 0) { off = (unsigned long long)tile * SD_LEAN_REC_BYTES; bytes = SD_LEAN_REC_BYTES; }
-        if (lane == 1) bytes = G * (8u * SD_TILE_READS);
-        if (lane == 2) bytes = G * (4u * QB * SD_TILE_READS);
-        if (lane == 3 || lane == 4) { off = x >> 16; bytes = (uint32_t)x & 0xFFFFu; }
-        if (VERIFY) {
-            const unsigned long long mp_end = __shfl_sync(0xFFFFFFFFu, x, 6);
-            if (lane == 5) bytes = (uint32_t)(mp_end - x);
-        }
-        const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, bytes);
-        if (lane == 0) mbar_arrive_expect_tx(&full[stage], total);
-        __syncwarp();
-        if (bytes) bulk_g2s(mine + stage * stage_bytes + my_dst, my_src + off, bytes, &full[stage]);
-        return lseq;
+    auto bcast64 = [&](unsigned long long x, int src) -> unsigned long long {
+        const uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)x, src), hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(x >> 32), src);
+        return (unsigned long long)lo | ((unsigned long long)hi << 32);
     };
-
-    // two tiles in flight; lq_[st] = l_seq of the (lean) tile in stage st, 0 = not a lean tile, 0xFFFFFFFF = the queue ran dry
-    uint32_t lq_[2];
-#pragma unroll
-    for (int st = 0; st < 2; st++) {
-        const uint32_t t = claim();
-        lq_[st] = t != 0xFFFFFFFFu ? issue(t, (uint32_t)st, fetch_desc(t)) : 0xFFFFFFFFu;
-    }
 
     uint32_t cnt_a = 0, cnt_b = 0, cnt_tiles = 0, my_tc_total = 0;   // packed per-lane run counters (10-bit fields), see below
     auto flush_counts = [&]() {
@@ -149,243 +108,264 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_LEAN_MIN_CTAS(W)) sd_lean_k
         }
         cnt_a = cnt_b = cnt_tiles = 0u;
     };
-
-    // Counters of the annotation row the warp is in: consecutive tiles of a sorted batch hit the same UTR, so its five sums are kept
-    // in (warp-uniform) registers and go to global memory when the row changes -- five atomics per row change instead of per tile.
-    uint32_t cur_row = 0xFFFFFFFFu, acc_n = 0u, acc_tc = 0u, acc_mm = 0u, acc_cov = 0u, acc_conv = 0u;
+    // Counters of the annotation row the warp is in: consecutive tiles of a sorted batch hit the same UTR, so every lane keeps its own
+    // part of the row's five sums in registers (reads | T>C reads << 10 | multimappers << 20 in one word: a lane adds at most one
+    // of each per tile) and the warp adds them up when the row changes -- five reductions and atomics per row change, not per tile.
+    uint32_t cur_row = 0xFFFFFFFFu, acc_pk = 0u, acc_cov = 0u, acc_conv = 0u;
     auto flush_row = [&]() {
-        if (cur_row != 0xFFFFFFFFu && lane == 0u) {
-            SD_CHECK(cur_row < A.n_utr);
-            unsigned long long *c = A.counters + (size_t)cur_row * SD_NCOUNTER;
-            atomicAdd(c + SD_C_READS, (unsigned long long)acc_n);
-            if (acc_tc) atomicAdd(c + SD_C_TCREADS, (unsigned long long)acc_tc);
-            if (acc_mm) atomicAdd(c + SD_C_MULTIMAP, (unsigned long long)acc_mm);
-            if (acc_cov) atomicAdd(c + SD_C_COV_ON_T, (unsigned long long)acc_cov);
-            if (acc_conv) atomicAdd(c + SD_C_CONV_ON_T, (unsigned long long)acc_conv);
+        if (cur_row != 0xFFFFFFFFu) {
+            const uint32_t n = __reduce_add_sync(0xFFFFFFFFu, acc_pk & 1023u), n_tc = __reduce_add_sync(0xFFFFFFFFu, (acc_pk >> 10) & 1023u),
+                           n_mm = __reduce_add_sync(0xFFFFFFFFu, acc_pk >> 20);
+            const uint32_t cov = __reduce_add_sync(0xFFFFFFFFu, acc_cov), conv = __reduce_add_sync(0xFFFFFFFFu, acc_conv);
+            if (lane == 0u) {
+                SD_CHECK(cur_row < A.n_utr);
+                unsigned long long *c = A.counters + (size_t)cur_row * SD_NCOUNTER;
+                if (n) atomicAdd(c + SD_C_READS, (unsigned long long)n);
+                if (n_tc) atomicAdd(c + SD_C_TCREADS, (unsigned long long)n_tc);
+                if (n_mm) atomicAdd(c + SD_C_MULTIMAP, (unsigned long long)n_mm);
+                if (cov) atomicAdd(c + SD_C_COV_ON_T, (unsigned long long)cov);
+                if (conv) atomicAdd(c + SD_C_CONV_ON_T, (unsigned long long)conv);
+            }
         }
-        acc_n = acc_tc = acc_mm = acc_cov = acc_conv = 0u;
+        acc_pk = acc_cov = acc_conv = 0u;
     };
 
-    uint32_t phase = 0u;   // bit st: parity the next wait on stage st looks for (a stage's barrier advances only when its tile was copied)
-    for (;;) {
-        // ------------------------------------------------------------------ stage 0, then stage 1 (unrolled by hand via the lambda)
-        bool done = false;
-#pragma unroll
-        for (int st = 0; st < SD_LEAN_STAGES; st++) {
-            if (lq_[st] == 0xFFFFFFFFu) { done = true; break; }   // claims are monotonic: nothing behind it either
-            const uint32_t lseq = lq_[st];
-            // the tile that will take this stage over: claimed now, its description on the way into registers while this tile is counted
-            const uint32_t next = claim();
-            const unsigned long long next_desc = fetch_desc(next);
-            if (lseq == 0u) {
-                if (lane == 0) A.leftover[atomicAdd(A.n_leftover, 1u)] = s_info[2 * st + 1].z;
-            } else {
-                const unsigned char *base = mine + st * stage_bytes;
-                mbar_wait(&full[st], (phase >> st) & 1u);
-                phase ^= 1u << st;
-                const uint4 info = s_info[2 * st], info2 = s_info[2 * st + 1];   // {lean, g0, win lo, win hi}, {ent lo, ent hi, tile, .}
-                const uint32_t tile = info2.z, ne = (info2.x & 0xFFFFu) >> 5;
-                const uint32_t w0 = (info.z >> 20) | (info.w << 12);   // win = first window byte << 16 | bytes; 16 bytes per word
-                // --- the record
-                const uint32_t *rw = reinterpret_cast<const uint32_t *>(base) + 5u * lane;
-                const int32_t pos = (int32_t)rw[0];
-                const uint32_t rmf = rw[1];
-                const float xi = __uint_as_float(rw[2]);
-                const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu;
-                const bool real = !(flags & SD_F_PAD);
-                const bool cand = !(flags & (SD_F_PAD | SD_F_UNMAPPED | SD_F_SKIP)) && (rmf & 0xFFFFu) < A.n_chrom;
-                // --- filter.py:235-256; run counters as 10-bit fields of two registers (cnt_a: mapped | kept | counted,
-                // cnt_b: unmapped | MQ | identity), added up by flush_counts() before a field can overflow
-                bool go = real;
-                if (A.filter_on) {
-                    const bool primary = real && !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
-                    const bool mapped = real && !(flags & SD_F_UNMAPPED);
-                    const bool f_mq = mapped && (int)mapq < A.filter_mq;
-                    const bool f_id = mapped && !f_mq && xi < A.filter_min_identity;
-                    bool f_nm = false;
-                    if (A.filter_max_nm > -1) {
-                        f_nm = mapped && !f_mq && !f_id && (int)(rw[4] & 0xFFFFu) > A.filter_max_nm;
-                        if (f_nm) atomicAdd(&s_stats[SD_S_NMFILTERED], 1u);
-                    }
-                    go = mapped && !f_mq && !f_id && !f_nm;
-                    cnt_a += (uint32_t)(primary && mapped) | ((uint32_t)(go && primary) << 10);
-                    cnt_b += (uint32_t)(primary && !mapped) | ((uint32_t)f_mq << 10) | ((uint32_t)f_id << 20);
-                }
-                const bool live = go && cand;
-                cnt_a += (uint32_t)live << 20;
-                const uint32_t s = flags & SD_F_REVERSE;   // 0 '+', 1 '-'
-                const uint32_t lm = live ? 0xFFFFFFFFu : 0u;
-                // --- geometry: one match block of lseq bases at linear position g
-                const uint32_t g = info.y + (uint32_t)pos, e = g + lseq;
-                const uint32_t dword = live ? (g >> 5) - w0 : 0u;   // window word of the read among the staged ones
-                const uint32_t sh = g & 31u;
-                // --- reference window of this strand, shifted to the read's start: T = is T / A inside the read, S = SNPs
-                uint32_t T[W], S[W];
-                {
-                    const uint2 *wp = reinterpret_cast<const uint2 *>(base + off_win) + 2u * dword + s;
-                    uint2 x[W + 1];
-#pragma unroll
-                    for (int k = 0; k <= W; k++) x[k] = wp[2 * k];
-#pragma unroll
-                    for (int k = 0; k < W; k++) {
-                        T[k] = __funnelshift_r(x[k].x, x[k + 1].x, sh) & prefix_word(k, (int)lseq) & lm;
-                        S[k] = __funnelshift_r(x[k].y, x[k + 1].y, sh);
-                    }
-                }
-                // --- read mask: base is C ('+') / G ('-') and its quality passes; candidates H = M & T & ~S
-                uint32_t H[W], D[VERIFY ? W : 1];
-                {
-                    const uint32_t sm = 0u - s;
-                    const uint2 *sq = reinterpret_cast<const uint2 *>(base + off_seq) + lane;
-                    const uint32_t *ql = reinterpret_cast<const uint32_t *>(base + off_qual) + QB * lane;
-                    const uint32_t hm = (flags & SD_F_HAS_MP) ? 0xFFFFFFFFu : 0u;   // no MP tag: the reference sees no mismatches (SlamSeqFile.py:318)
-#pragma unroll
-                    for (int k = 0; k < W; k++) {
-                        // groups behind the read's last one hold whatever an earlier tile left in the stage: T is zero there
-                        const uint32_t m = group_is_base2(sq[k * SD_TILE_READS], sm);
-                        const uint32_t q = row_group_qual_ok<QB, true>(ql, (uint32_t)k, A);
-                        if (VERIFY) D[k] = m & T[k] & hm;   // before quality / SNP masking: what NextGenMap lists
-                        H[k] = m & q & T[k] & ~S[k] & hm;
-                    }
-                }
-                bool bad = false;
-                if (VERIFY) {
-                    // the read's T>C / A>G candidates against its MP entries (reference offset and read index; plain match: equal)
-                    const uint32_t nmp_all = live ? (rw[4] >> 16) : 0u;
-                    uint32_t ms = rw[4] >> 16;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ms, d);
-                        if (lane >= (uint32_t)d) ms += t;
-                    }
-                    const uint32_t *mp = reinterpret_cast<const uint32_t *>(base + off_mp) + (ms - (rw[4] >> 16));
-                    if (flags & SD_F_HAS_MP) {
-                        for (uint32_t i = 0; i < nmp_all; i++) {
-                            const uint32_t en = mp[i];
-                            const uint32_t rp = en & 0xFFFFu, o = en >> 16;
-                            bool found = false;
-#pragma unroll
-                            for (int k = 0; k < W; k++)
-                                if ((o >> 5) == (uint32_t)k && ((D[k] >> (o & 31u)) & 1u)) {
-                                    D[k] &= ~(1u << (o & 31u));
-                                    found = true;
-                                }
-                            if (!found || o != rp) bad = true;
-                        }
-#pragma unroll
-                        for (int k = 0; k < W; k++) bad |= (D[k] != 0u);
-                    }
-                    if (bad) atomicAdd(&A.stats[SD_S_MP_DISAGREE], 1ull);
-                }
-                int tc = 0;
-                uint32_t pop_t = 0;
+    // the three record words the scan needs (pos, chromosome | MAPQ | flags, XI), loaded one tile ahead like the description
+    auto fetch_rec = [&](uint32_t tile, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
+        w0 = w1 = w2 = 0u;
+        if (tile != 0xFFFFFFFFu) {
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(A.rec + (size_t)tile * SD_TILE_READS + lane);
+            w0 = __ldcs(rw);
+            w1 = __ldcs(rw + 1);
+            w2 = __ldcs(rw + 2);
+        }
+    };
+    uint32_t tile = claim();
+    unsigned long long desc = fetch_desc(tile);
+    uint32_t r_pos, r_rmf, r_xi;
+    fetch_rec(tile, r_pos, r_rmf, r_xi);
+    while (tile != 0xFFFFFFFFu) {   // claims are monotonic: nothing behind the first empty one
+        // the next tile: claimed now, its description and records on the way into registers while this tile is counted
+        const uint32_t next = claim();
+        const unsigned long long next_desc = fetch_desc(next);
+        uint32_t n_pos, n_rmf, n_xi;
+        fetch_rec(next, n_pos, n_rmf, n_xi);
+        const uint32_t lseq = __shfl_sync(0xFFFFFFFFu, (uint32_t)desc, 0);
+        if (lseq == 0u) {
+            if (lane == 0) A.leftover[atomicAdd(A.n_leftover, 1u)] = tile;
+        } else {
+            const uint32_t g0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)(desc >> 32), 0);
+            const unsigned long long seq_off = bcast64(desc, 1), qual_off = bcast64(desc, 2), entw = bcast64(desc, 3);
+            const uint32_t ne = ((uint32_t)entw & 0xFFFFu) >> 5;
+            const uint4 *ent = A.ment + (size_t)(entw >> 20);   // entw = byte offset << 16 | bytes; 16 bytes per uint4
+            const uint32_t G = (lseq + 31u) >> 5;
+            // --- the tile's column loads up front: the read's SEQ groups and quality planes (streamed: evict first).  The blocks of the
+            // tile two ahead are pulled into L2 by address: tiles of a chunk follow each other in every column, and tiles of equal
+            // l_seq have blocks of equal size (a guess that is wrong costs a useless prefetch, nothing else; the guard keeps it
+            // inside the columns -- at least 64 tiles of at least 256 bytes follow)
+            if (tile + 66u < A.n_tiles) {
+                const unsigned char *ps = A.seq + seq_off + 2u * G * (8u * SD_TILE_READS), *pq = A.qual + qual_off + 2u * G * (4u * QB * SD_TILE_READS);
+                for (uint32_t l = lane; l < 2u * G; l += 32u) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + 128u * l));
+                for (uint32_t l = lane; l < (uint32_t)QB * G; l += 32u) asm volatile("prefetch.global.L2 [%0];" ::"l"(pq + 128u * l));
+            }
+            const int32_t pos = (int32_t)r_pos;
+            const uint32_t rmf = r_rmf;
+            const float xi = __uint_as_float(r_xi);
+            const uint32_t nm_nmp = (VERIFY || A.filter_max_nm > -1) ? __ldcs(reinterpret_cast<const uint32_t *>(A.rec + (size_t)tile * SD_TILE_READS + lane) + 4) : 0u;
+            uint2 xs[W];
+            uint32_t xq[W][QB];
+            {
+                const uint2 *sq = reinterpret_cast<const uint2 *>(A.seq + seq_off) + lane;
 #pragma unroll
                 for (int k = 0; k < W; k++) {
-                    tc += __popc(H[k]);
-                    pop_t += __popc(T[k]);
-                }
-                if (tc < A.conv_threshold) {   // not a T>C read: its conversions are dropped (tcounter.py:210-214)
-                    tc = 0;
-#pragma unroll
-                    for (int k = 0; k < W; k++) H[k] = 0u;
-                }
-                my_tc_total += (uint32_t)tc;
-                if (A.read_tc) A.read_tc[(size_t)tile * SD_TILE_READS + lane] = (uint8_t)(tc > 255 ? 255 : tc);
-
-                // --- interval join over the tile's annotation entries (warp-uniform loop)
-                const uint4 *ent = reinterpret_cast<const uint4 *>(base + off_ent);
-                uint32_t last_seg = 0xFFFFFFFFu;
-                for (uint32_t j = 0; j < ne; j++) {
-                    const uint4 u = ent[2 * j];   // {start, end, row | strand << 31, segment}: broadcast
-                    const bool hit = live && (u.z >> 31) == s && u.x < e && u.y > g;
-                    const unsigned hmask = __ballot_sync(0xFFFFFFFFu, hit);
-                    if (hmask == 0u) continue;
-                    uint32_t cov_t = hit ? pop_t : 0u, conv = hit ? (uint32_t)tc : 0u;
-                    const bool partial = hit && (u.x > g || u.y < e);
-                    if (__any_sync(0xFFFFFFFFu, partial)) {
-                        if (partial) {   // the UTR covers only part of the read
-                            const int lo = u.x > g ? (int)(u.x - g) : 0;
-                            const int hi = u.y < e ? (int)(u.y - g) : (int)lseq;
-                            cov_t = 0u;
-                            conv = 0u;
-#pragma unroll
-                            for (int k = 0; k < W; k++) {
-                                const uint32_t m = prefix_word(k, hi) & ~prefix_word(k, lo);
-                                cov_t += __popc(T[k] & m);
-                                conv += __popc(H[k] & m);
-                            }
-                        }
-                    }
-                    const unsigned b_tc = __ballot_sync(0xFFFFFFFFu, hit && tc > 0), b_mm = __ballot_sync(0xFFFFFFFFu, hit && mapq == 0u);
-                    const uint32_t s_cov = __reduce_add_sync(0xFFFFFFFFu, cov_t), s_conv = __reduce_add_sync(0xFFFFFFFFu, conv);
-                    const uint32_t row = u.z & 0x7FFFFFFFu;
-                    if (row != cur_row) {   // warp-uniform
-                        flush_row();
-                        cur_row = row;
-                    }
-                    acc_n += __popc(hmask);
-                    acc_tc += __popc(b_tc);
-                    acc_mm += __popc(b_mm);
-                    acc_cov += s_cov;
-                    acc_conv += s_conv;
-                    // per-position outputs, once per (read, merged segment).  The reads of a sorted tile start and end at few
-                    // distinct positions in lane order, so equal addresses sit in runs of neighbouring lanes: the first lane of a
-                    // run adds the run's length
-                    const bool part = hit && u.w != last_seg;
-                    const unsigned pm = __ballot_sync(0xFFFFFFFFu, part);
-                    if (pm == 0u) continue;
-                    if (part) last_seg = u.w;
-                    const uint4 sg = ent[2 * j + 1];   // {segment start, end, posbase lo, hi}: position p lives at index posbase + p
-                    const unsigned long long posbase = (unsigned long long)sg.z | ((unsigned long long)sg.w << 32);
-                    const uint32_t pa = sg.x > g ? sg.x : g, pb = sg.y < e ? sg.y : e;
-                    const bool sticks_out = part && !(pa == g && pb == e);
-                    if (!__any_sync(0xFFFFFFFFu, sticks_out)) {
-                        // every read lies inside the segment: ends are starts + l_seq, so runs of equal starts are runs of equal ends
-                        const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, pa, 1);
-                        const bool lead = part && !(lane > 0u && ((pm >> (lane - 1u)) & 1u) && prev == pa);
-                        const unsigned lmk = __ballot_sync(0xFFFFFFFFu, lead);
-                        if (lead) {
-                            const unsigned stop = (~pm | lmk) & ~((2u << lane) - 1u);   // first lane after this one that is not in its run
-                            const int run = (stop ? __ffs((int)stop) - 1 : 32) - (int)lane;
-                            SD_CHECK(posbase + pb < A.n_positions);
-                            int *cp = A.pos_cov + (long long)(posbase + pa);
-                            atomicAdd(cp, run);
-                            atomicAdd(cp + lseq, -run);
-                        }
+                    const uint32_t kc = min((uint32_t)k, G - 1u);   // an existing group; behind the read's last one T is zero anyway
+                    xs[k] = __ldcs(sq + kc * SD_TILE_READS);
+                    if (QB == 2) {
+                        const uint2 q = __ldcs(reinterpret_cast<const uint2 *>(A.qual + qual_off) + lane + kc * SD_TILE_READS);
+                        xq[k][0] = q.x; xq[k][1] = q.y;
                     } else {
-#pragma unroll
-                        for (int side = 0; side < 2; side++) {
-                            const uint32_t p = side ? pb : pa;
-                            const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, p, 1);
-                            const bool lead = part && !(lane > 0u && ((pm >> (lane - 1u)) & 1u) && prev == p);
-                            const unsigned lmk = __ballot_sync(0xFFFFFFFFu, lead);
-                            if (lead) {
-                                const unsigned stop = (~pm | lmk) & ~((2u << lane) - 1u);
-                                const int run = (stop ? __ffs((int)stop) - 1 : 32) - (int)lane;
-                                SD_CHECK(pb >= pa && posbase + p < A.n_positions);
-                                atomicAdd(&A.pos_cov[posbase + p], side ? -run : run);
-                            }
-                        }
+                        const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(A.qual + qual_off) + lane + kc * SD_TILE_READS);
+                        xq[k][0] = q.x; xq[k][1] = q.y; xq[k][QB > 2 ? 2 : 0] = q.z; xq[k][QB > 2 ? 3 : 1] = q.w;
                     }
-                    const bool conv_here = part && tc > 0;
-                    int *tcbase = A.pos_tc + (long long)(posbase + g);   // may point before the segment; only in-range bits are used
-                    asm volatile("" : "+l"(tcbase));
-                    if (__any_sync(0xFFFFFFFFu, conv_here && sticks_out)) {   // some read sticks out of the segment (rare)
-                        if (conv_here) {
+                }
+            }
+            const uint32_t flags = rmf >> 24, mapq = (rmf >> 16) & 0xFFu;
+            const bool real = !(flags & SD_F_PAD);
+            const bool cand = !(flags & (SD_F_PAD | SD_F_UNMAPPED | SD_F_SKIP)) && (rmf & 0xFFFFu) < A.n_chrom;
+            // --- filter.py:235-256; run counters as 10-bit fields of two registers (cnt_a: mapped | kept | counted,
+            // cnt_b: unmapped | MQ | identity), added up by flush_counts() before a field can overflow
+            bool go = real;
+            if (A.filter_on) {
+                const bool primary = real && !(flags & (SD_F_SECONDARY | SD_F_SUPPLEMENTARY));
+                const bool mapped = real && !(flags & SD_F_UNMAPPED);
+                const bool f_mq = mapped && (int)mapq < A.filter_mq;
+                const bool f_id = mapped && !f_mq && xi < A.filter_min_identity;
+                bool f_nm = false;
+                if (A.filter_max_nm > -1) {
+                    f_nm = mapped && !f_mq && !f_id && (int)(nm_nmp & 0xFFFFu) > A.filter_max_nm;
+                    if (f_nm) atomicAdd(&s_stats[SD_S_NMFILTERED], 1u);
+                }
+                go = mapped && !f_mq && !f_id && !f_nm;
+                cnt_a += (uint32_t)(primary && mapped) | ((uint32_t)(go && primary) << 10);
+                cnt_b += (uint32_t)(primary && !mapped) | ((uint32_t)f_mq << 10) | ((uint32_t)f_id << 20);
+            }
+            const bool live = go && cand;
+            cnt_a += (uint32_t)live << 20;
+            const uint32_t s = flags & SD_F_REVERSE;   // 0 '+', 1 '-'
+            const uint32_t lm = live ? 0xFFFFFFFFu : 0u;
+            // --- geometry: one match block of lseq bases at linear position g
+            const uint32_t g = g0 + (live ? (uint32_t)pos : 0u), e = g + lseq;
+            const uint32_t sh = g & 31u;
+            // --- reference window of this strand, shifted to the read's start: T = is T / A inside the read, S = SNPs
+            uint32_t T[W], S[W];
+            {
+                const uint2 *wp = reinterpret_cast<const uint2 *>(A.refm + (g >> 5)) + s;
+                uint2 x[W + 1];
 #pragma unroll
-                            for (int k = 0; k < W; k++) {
-                                uint32_t h = H[k] & prefix_word(k, (int)(pb - g)) & ~prefix_word(k, (int)(pa - g));
-                                while (h) {
-                                    SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
-                                    atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
-                                    h &= h - 1u;
-                                }
+                for (int k = 0; k <= W; k++) x[k] = (SD_LEAN_DIAG & 8) ? make_uint2(0x11111111u * (uint32_t)(k + 1) + g, 0u) : __ldg(wp + 2 * k);
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    T[k] = __funnelshift_r(x[k].x, x[k + 1].x, sh) & prefix_word(k, (int)lseq) & lm;
+                    S[k] = __funnelshift_r(x[k].y, x[k + 1].y, sh);
+                }
+            }
+            // --- read mask: base is C ('+') / G ('-') and its quality passes; candidates H = M & T & ~S
+            uint32_t H[W], D[VERIFY ? W : 1];
+            {
+                const uint32_t sm = 0u - s;
+                const uint32_t hm = (flags & SD_F_HAS_MP) ? 0xFFFFFFFFu : 0u;   // no MP tag: the reference sees no mismatches (SlamSeqFile.py:318)
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    const uint32_t m = group_is_base2(xs[k], sm);
+                    const uint32_t q = planes_ge<QB, true>(xq[k], A);
+                    if (VERIFY) D[k] = m & T[k] & hm;   // before quality / SNP masking: what NextGenMap lists
+                    H[k] = m & q & T[k] & ~S[k] & hm;
+                }
+            }
+            if (VERIFY) {
+                // the read's T>C / A>G candidates against its MP entries (reference offset and read index; plain match: equal)
+                const unsigned long long mp_off = bcast64(desc, 4);
+                const uint32_t nmp = nm_nmp >> 16;
+                uint32_t ms = nmp;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ms, d);
+                    if (lane >= (uint32_t)d) ms += t;
+                }
+                bool bad = false;
+                if (live && (flags & SD_F_HAS_MP)) {
+                    const uint32_t *mp = reinterpret_cast<const uint32_t *>(A.mp + mp_off) + (ms - nmp);
+                    for (uint32_t i = 0; i < nmp; i++) {
+                        const uint32_t en = __ldcs(mp + i);
+                        const uint32_t rp = en & 0xFFFFu, o = en >> 16;
+                        bool found = false;
+#pragma unroll
+                        for (int k = 0; k < W; k++)
+                            if ((o >> 5) == (uint32_t)k && ((D[k] >> (o & 31u)) & 1u)) {
+                                D[k] &= ~(1u << (o & 31u));
+                                found = true;
                             }
-                        }
-                    } else if (conv_here) {
+                        if (!found || o != rp) bad = true;
+                    }
+#pragma unroll
+                    for (int k = 0; k < W; k++) bad |= (D[k] != 0u);
+                }
+                if (bad) atomicAdd(&A.stats[SD_S_MP_DISAGREE], 1ull);
+            }
+            int tc = 0;
+            uint32_t pop_t = 0;
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                tc += __popc(H[k]);
+                pop_t += __popc(T[k]);
+            }
+            if (tc < A.conv_threshold) {   // not a T>C read: its conversions are dropped (tcounter.py:210-214)
+                tc = 0;
+#pragma unroll
+                for (int k = 0; k < W; k++) H[k] = 0u;
+            }
+            my_tc_total += (uint32_t)tc;
+            if (A.read_tc) A.read_tc[(size_t)tile * SD_TILE_READS + lane] = (uint8_t)(tc > 255 ? 255 : tc);
+
+            // --- interval join over the tile's annotation entries (warp-uniform loop)
+            uint32_t last_seg = 0xFFFFFFFFu;
+            for (uint32_t j = 0; j < ((SD_LEAN_DIAG & 4) ? 0u : ne); j++) {
+                const uint4 u = __ldg(ent + 2 * j);   // {start, end, row | strand << 31, segment}: one address for the warp
+                const bool hit = live && (u.z >> 31) == s && u.x < e && u.y > g;
+                const unsigned hmask = __ballot_sync(0xFFFFFFFFu, hit);
+                if (hmask == 0u) continue;
+                uint32_t cov_t = hit ? pop_t : 0u, conv = hit ? (uint32_t)tc : 0u;
+                const bool partial = hit && (u.x > g || u.y < e);
+                if (__any_sync(0xFFFFFFFFu, partial)) {
+                    if (partial) {   // the UTR covers only part of the read
+                        const int lo = u.x > g ? (int)(u.x - g) : 0;
+                        const int hi = u.y < e ? (int)(u.y - g) : (int)lseq;
+                        cov_t = 0u;
+                        conv = 0u;
 #pragma unroll
                         for (int k = 0; k < W; k++) {
-                            uint32_t h = H[k];
+                            const uint32_t m = prefix_word(k, hi) & ~prefix_word(k, lo);
+                            cov_t += __popc(T[k] & m);
+                            conv += __popc(H[k] & m);
+                        }
+                    }
+                }
+                const uint32_t row = u.z & 0x7FFFFFFFu;
+                if (row != cur_row) {   // warp-uniform
+                    flush_row();
+                    cur_row = row;
+                }
+                acc_pk += (uint32_t)hit | ((uint32_t)(hit && tc > 0) << 10) | ((uint32_t)(hit && mapq == 0u) << 20);
+                acc_cov += cov_t;
+                acc_conv += conv;
+                // per-position outputs, once per (read, merged segment).  The reads of a sorted tile start and end at few
+                // distinct positions in lane order, so equal addresses sit in runs of neighbouring lanes: the first lane of a
+                // run adds the run's length
+                const bool part = hit && u.w != last_seg;
+                const unsigned pm = __ballot_sync(0xFFFFFFFFu, part);
+                if (pm == 0u) continue;
+                if (part) last_seg = u.w;
+                const uint4 sg = __ldg(ent + 2 * j + 1);   // {segment start, end, posbase lo, hi}: position p lives at index posbase + p
+                const unsigned long long posbase = (unsigned long long)sg.z | ((unsigned long long)sg.w << 32);
+                const uint32_t pa = sg.x > g ? sg.x : g, pb = sg.y < e ? sg.y : e;
+                const bool sticks_out = part && !(pa == g && pb == e);
+                if (SD_LEAN_DIAG & 2) {
+                } else if (!__any_sync(0xFFFFFFFFu, sticks_out)) {
+                    // every read lies inside the segment: ends are starts + l_seq, so runs of equal starts are runs of equal ends
+                    const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, pa, 1);
+                    const bool lead = part && !(lane > 0u && ((pm >> (lane - 1u)) & 1u) && prev == pa);
+                    const unsigned lmk = __ballot_sync(0xFFFFFFFFu, lead);
+                    if (lead) {
+                        const unsigned stop = (~pm | lmk) & ~((2u << lane) - 1u);   // first lane after this one that is not in its run
+                        const int run = (stop ? __ffs((int)stop) - 1 : 32) - (int)lane;
+                        SD_CHECK(posbase + pb < A.n_positions);
+                        int *cp = A.pos_cov + (long long)(posbase + pa);
+                        atomicAdd(cp, run);
+                        atomicAdd(cp + lseq, -run);
+                    }
+                } else {
+#pragma unroll
+                    for (int side = 0; side < 2; side++) {
+                        const uint32_t p = side ? pb : pa;
+                        const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, p, 1);
+                        const bool lead = part && !(lane > 0u && ((pm >> (lane - 1u)) & 1u) && prev == p);
+                        const unsigned lmk = __ballot_sync(0xFFFFFFFFu, lead);
+                        if (lead) {
+                            const unsigned stop = (~pm | lmk) & ~((2u << lane) - 1u);
+                            const int run = (stop ? __ffs((int)stop) - 1 : 32) - (int)lane;
+                            SD_CHECK(pb >= pa && posbase + p < A.n_positions);
+                            atomicAdd(&A.pos_cov[posbase + p], side ? -run : run);
+                        }
+                    }
+                }
+                const bool conv_here = part && tc > 0 && !(SD_LEAN_DIAG & 1);
+                int *tcbase = A.pos_tc + (long long)(posbase + g);   // may point before the segment; only in-range bits are used
+                asm volatile("" : "+l"(tcbase));
+                if (__any_sync(0xFFFFFFFFu, conv_here && sticks_out)) {   // some read sticks out of the segment (rare)
+                    if (conv_here) {
+#pragma unroll
+                        for (int k = 0; k < W; k++) {
+                            uint32_t h = H[k] & prefix_word(k, (int)(pb - g)) & ~prefix_word(k, (int)(pa - g));
                             while (h) {
                                 SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
                                 atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
@@ -393,18 +373,27 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_LEAN_MIN_CTAS(W)) sd_lean_k
                             }
                         }
                     }
-                }
-                if (++cnt_tiles == 1000u) {   // before a 10-bit field of the run counters (or a 32-bit row sum) can overflow
-                    flush_counts();
-                    flush_row();
-                    cur_row = 0xFFFFFFFFu;
+                } else if (conv_here) {
+#pragma unroll
+                    for (int k = 0; k < W; k++) {
+                        uint32_t h = H[k];
+                        while (h) {
+                            SD_CHECK((unsigned long long)(tcbase + (32 * k + __ffs((int)h) - 1) - A.pos_tc) < A.n_positions);
+                            atomicAdd(tcbase + (32 * k + __ffs((int)h) - 1), 1);
+                            h &= h - 1u;
+                        }
+                    }
                 }
             }
-            // --- refill this stage
-            __syncwarp();
-            lq_[st] = next != 0xFFFFFFFFu ? issue(next, (uint32_t)st, next_desc) : 0xFFFFFFFFu;
+            if (++cnt_tiles == 1000u) {   // before a 10-bit field of the run counters (or a 32-bit row sum) can overflow
+                flush_counts();
+                flush_row();
+                cur_row = 0xFFFFFFFFu;
+            }
         }
-        if (done) break;
+        tile = next;
+        desc = next_desc;
+        r_pos = n_pos; r_rmf = n_rmf; r_xi = n_xi;
     }
 
     flush_counts();
@@ -429,15 +418,10 @@ int launch_lean(sd_ctx *ctx, const CountArgs &C, cudaStream_t stream, uint32_t *
     A.mp = VERIFY ? reinterpret_cast<const unsigned char *>(C.mp) : nullptr;
     A.tiles = C.tiles;
     A.spans = reinterpret_cast<const sd_tile_span *>(C.spans);
-    A.refm = reinterpret_cast<const unsigned char *>(C.refm);
-    A.ment = reinterpret_cast<const unsigned char *>(C.ment);
+    A.refm = C.refm;
+    A.ment = C.ment;
     A.n_tiles = C.n_tiles;
     A.n_chrom = C.n_chrom;
-    A.cap_seq = align128(8u * SD_TILE_READS * W);
-    A.cap_qual = align128(4u * QB * SD_TILE_READS * W);
-    A.cap_win = C.cap_win;
-    A.cap_ent = C.cap_ent;
-    A.cap_mp = VERIFY ? align128(C.cap_mp) : 0u;
     A.q_cmin = C.q_cmin;
     for (int k = 0; k < 4; k++) A.q_m[k] = C.q_m[k];
     A.conv_threshold = C.conv_threshold;
@@ -449,27 +433,19 @@ int launch_lean(sd_ctx *ctx, const CountArgs &C, cudaStream_t stream, uint32_t *
     A.n_leftover = n_out;
     A.n_positions = C.n_positions;
     A.n_utr = C.n_utr;
-    const uint32_t stage_bytes = SD_LEAN_REC_BYTES + A.cap_seq + A.cap_qual + A.cap_win + A.cap_ent + A.cap_mp;
-    int max_smem = 0;
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    uint32_t warps = SD_CTA_THREADS / 32;
-    auto need = [&](uint32_t w) { return 128u + (size_t)w * (SD_LEAN_STAGES * stage_bytes + 128u); };
-    while (warps > 1 && need(warps) > (size_t)max_smem / 2) warps--;   // at least two CTAs per SM
-    if (need(warps) > (size_t)max_smem) return sd_fail(ctx, SD_ERR_LIMIT, "a lean tile needs %u bytes of shared memory per stage", stage_bytes);
-    const size_t smem = need(warps);
-    struct Planned { uint32_t stage_bytes; int device; int per_sm; };
-    static Planned last = {0, -1, 0};
-    if (last.device != ctx->device || last.stage_bytes != stage_bytes) {
-        int per_sm = 0;
-        SD_CUDA(ctx, cudaFuncSetAttribute(sd_lean_kernel<W, QB, VERIFY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_lean_kernel<W, QB, VERIFY>, (int)warps * 32, smem));
-        if (per_sm < 1) return sd_fail(ctx, SD_ERR_LIMIT, "lean count kernel does not fit on an SM (smem %zu)", smem);
-        last = {stage_bytes, ctx->device, per_sm};
+    static int per_sm = 0, device = -1;
+    if (device != ctx->device) {
+        SD_CUDA(ctx, cudaFuncSetAttribute(sd_lean_kernel<W, QB, VERIFY>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));   // all of it L1
+        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sd_lean_kernel<W, QB, VERIFY>, SD_CTA_THREADS, 0));
+        if (per_sm < 1) return sd_fail(ctx, SD_ERR_LIMIT, "lean count kernel does not fit on an SM");
+        device = ctx->device;
     }
+    const uint32_t warps = SD_CTA_THREADS / 32;
     const uint64_t want_ctas = ((uint64_t)A.n_tiles + warps - 1) / warps;
-    uint32_t grid = (uint32_t)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * last.per_sm);
+    uint32_t grid = (uint32_t)std::min<uint64_t>(want_ctas, (uint64_t)ctx->num_sms * per_sm);
     if (grid == 0) grid = 1;
-    sd_lean_kernel<W, QB, VERIFY><<<grid, (int)warps * 32, smem, stream>>>(A);
+    A.claim = (uint32_t)std::min<uint64_t>(SD_LEAN_CLAIM, std::max<uint64_t>(1, (uint64_t)A.n_tiles / ((uint64_t)grid * warps * 8u)));
+    sd_lean_kernel<W, QB, VERIFY><<<grid, SD_CTA_THREADS, 0, stream>>>(A);
     ctx->launches++;
     SD_CUDA(ctx, cudaGetLastError());
     return SD_OK;
