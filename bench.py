@@ -479,8 +479,10 @@ def e2e_leg(bench, barrier, reps):
             h2d += hw.h2d_bytes(bench.params)
             qbits = int(hw.wire.qual_bits)
             eng.reset_outputs()
-            eng.count_wire(hw.wire, bench.params)      # warm
+            eng.count_wire(hw.wire, bench.params)      # warm; also tells how many reads this wire gets counted
             eng.synchronize()
+            if not bench.per_sample:
+                counted += int(eng.stats.cpu()[L.SD_S_COUNTED])
             t0 = time.perf_counter()
             for _ in range(reps):
                 if bench.per_sample:
