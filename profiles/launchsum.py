@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kernel totals of an `ncu --metrics gpu__time_duration.sum --csv` launch list, and the share of one bench step
-(sd_count_kernel + sd_finalize_kernel + sd_tcontent_kernel) taken by each of its kernels.
+(sd_lean_kernel + sd_count_kernel + sd_finalize_kernel + sd_tcontent_kernel) taken by each of its kernels.
 usage: launchsum.py launches.csv"""
 import csv
 import sys
@@ -22,8 +22,8 @@ total = sum(v[1] for v in tot.values())
 print("ncu --metrics gpu__time_duration.sum --clock-control none; per-launch times are cold-cache and serialised: compare shares\n")
 for k, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print("%-62s n=%3d %11.1f us  %5.1f%%" % (k, n, us, 100 * us / total))
-step = {k: v for k, v in tot.items() if any(s in k for s in ("sd_count_kernel", "sd_finalize_kernel", "sd_tcontent_kernel"))}
+step = {k: v for k, v in tot.items() if any(s in k for s in ("sd_lean_kernel", "sd_count_kernel", "sd_finalize_kernel", "sd_tcontent_kernel"))}
 st = sum(v[1] / v[0] for v in step.values())
-print("\none step = sd_count_kernel + sd_finalize_kernel + sd_tcontent_kernel (+ memset fills of the outputs):")
+print("\none step = sd_lean_kernel + sd_count_kernel (staged, plain) + sd_finalize_kernel + sd_tcontent_kernel (+ memset fills of the outputs):")
 for k, (n, us) in sorted(step.items(), key=lambda kv: -kv[1][1]):
     print("  %-42s %8.1f us per launch  share of step %5.1f%%" % (k, us / n, 100 * (us / n) / st))
