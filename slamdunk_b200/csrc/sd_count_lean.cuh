@@ -159,19 +159,13 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_LEAN_MIN_CTAS(W)) sd_lean_k
             const uint32_t ne = ((uint32_t)entw & 0xFFFFu) >> 5;
             const uint4 *ent = A.ment + (size_t)(entw >> 20);   // entw = byte offset << 16 | bytes; 16 bytes per uint4
             const uint32_t G = (lseq + 31u) >> 5;
-            // --- the tile's column loads up front: the read's SEQ groups and quality planes (streamed: evict first).  The blocks of the
-            // tile two ahead are pulled into L2 by address: tiles of a chunk follow each other in every column, and tiles of equal
-            // l_seq have blocks of equal size (a guess that is wrong costs a useless prefetch, nothing else; the guard keeps it
-            // inside the columns -- at least 64 tiles of at least 256 bytes follow)
-            if (tile + 66u < A.n_tiles) {
-                const unsigned char *ps = A.seq + seq_off + 2u * G * (8u * SD_TILE_READS), *pq = A.qual + qual_off + 2u * G * (4u * QB * SD_TILE_READS);
-                for (uint32_t l = lane; l < 2u * G; l += 32u) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + 128u * l));
-                for (uint32_t l = lane; l < (uint32_t)QB * G; l += 32u) asm volatile("prefetch.global.L2 [%0];" ::"l"(pq + 128u * l));
-            }
+            // --- the tile's column loads up front: the read's SEQ groups and quality planes (streamed: evict first).  (Pulling the blocks of
+            // the tile two ahead into L2 with prefetch.global.L2 was measured: 50 more instructions per tile, no gain.)
             const int32_t pos = (int32_t)r_pos;
             const uint32_t rmf = r_rmf;
             const float xi = __uint_as_float(r_xi);
-            const uint32_t nm_nmp = (VERIFY || A.filter_max_nm > -1) ? __ldcs(reinterpret_cast<const uint32_t *>(A.rec + (size_t)tile * SD_TILE_READS + lane) + 4) : 0u;
+            uint32_t nm_nmp = 0u;   // NM | MP entries << 16: only the NM filter and the MP cross-check look at it
+            if (VERIFY || A.filter_max_nm > -1) nm_nmp = __ldcs(reinterpret_cast<const uint32_t *>(A.rec + (size_t)tile * SD_TILE_READS + lane) + 4);
             uint2 xs[W];
             uint32_t xq[W][QB];
             {

@@ -12,6 +12,7 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -515,6 +516,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     const bool want_mp = (options & SD_DECODE_MP) != 0 || mp_all, group = (options & SD_DECODE_GROUP) != 0;
     const uint64_t mp_entry_bytes = mp_all ? 8 : 4;
     const bool seq2 = (options & SD_DECODE_SEQ2) != 0;      // 2-bit SEQ column (count path only)
+    const bool want_wire = (options & SD_DECODE_WIRE) != 0;  // also the packed form sd_count_wire sends over PCIe
     if (seq2 && mp_all) return fail(err, errlen, SD_ERR_ARG, "SD_DECODE_SEQ2 and SD_DECODE_MP_ALL exclude each other (sd_read_stats needs the 4-plane SEQ column)");
     const uint64_t group_bytes = seq2 ? 8 : 16;
     const bool raw_qual = (options & SD_DECODE_RAW_QUAL) != 0;
@@ -868,6 +870,199 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     });
     const double t2 = now_s();
     lap("pass B");
+
+    // ---- optional: the wire form of the same batch (sd_wire, include/slamdunk_b200.h) -- every record field in its own column,
+    // SEQ and the base qualities as back-to-back rows of 2-bit base codes / dictionary codes straight from the BAM records, no
+    // l_seq / CIGAR for tiles of plain-match reads of one length.  Same layout as sd_wire_plan + sd_wire_fill make on the device.
+    memset(&hb->wire, 0, sizeof hb->wire);
+    if (want_wire && n_tiles > 0) {
+        if (mp_all) return bail(SD_ERR_ARG, "SD_DECODE_WIRE and SD_DECODE_MP_ALL exclude each other");
+        const size_t slots = n_tiles * (size_t)tile_reads;
+        sd_wire_tile *wt = (sd_wire_tile *)own->mem.get((n_tiles + 1) * sizeof(sd_wire_tile));
+        uint16_t *pos16 = (uint16_t *)own->mem.get(slots * 2), *mqf = (uint16_t *)own->mem.get(slots * 2);
+        uint16_t *nm16 = (uint16_t *)own->mem.get(slots * 2), *nmp16 = want_mp ? (uint16_t *)own->mem.get(slots * 2) : nullptr;
+        if (!wt || !pos16 || !mqf || !nm16 || (want_mp && !nmp16)) return bail(SD_ERR_NOMEM, "out of host memory");
+        // tile shapes and sizes
+        std::atomic<uint32_t> w_max_cig(0);
+        parallel_for(n_tiles, threads, [&](size_t t) {
+            const sd_read_rec *r = rec + t * (size_t)tile_reads;
+            const uint32_t *cg = cigc + tiles[t].cig_off / 4;
+            uint32_t lseq_u = 0, ref_u = SD_REF_NONE, flags = 0, sum_c = 0, bases = 0;
+            int32_t pmin = 0x7FFFFFFF, pmax = (int32_t)0x80000000;
+            bool first = true, plain = true, same_ref = true;
+            for (uint32_t k = 0; k < tile_reads; k++) {
+                const uint32_t fl = r[k].ref_mapq_flag >> 24, ref = r[k].ref_mapq_flag & 0xFFFFu;
+                const uint32_t lseq = r[k].lseq_ncig & 0xFFFFu, ncig = r[k].lseq_ncig >> 16;
+                if (!(fl & SD_F_PAD)) {
+                    if (first) { lseq_u = lseq; ref_u = ref; first = false; }
+                    if (!(lseq == lseq_u && ncig == 1u && cg[sum_c] == (lseq << 4))) plain = false;
+                    if (ref != ref_u) same_ref = false;
+                    pmin = std::min(pmin, r[k].pos);
+                    pmax = std::max(pmax, r[k].pos);
+                    bases += lseq;
+                }
+                sum_c += ncig;
+            }
+            if (!plain) flags |= SD_WT_SHAPE;
+            if (!same_ref) flags |= SD_WT_REFS;
+            if (!first && (long long)pmax - (long long)pmin > 65535ll) flags |= SD_WT_POS32;
+            uint32_t var_words = ((flags & SD_WT_POS32) ? 32u : 0u) + ((flags & SD_WT_REFS) ? 16u : 0u) + ((flags & SD_WT_SHAPE) ? 32u + sum_c : 0u);
+            var_words = (var_words + 3u) & ~3u;
+            sd_wire_tile w;
+            memset(&w, 0, sizeof w);
+            w.base_off = ((uint64_t)bases + 63ull) & ~63ull;      // sizes for now, offsets after the scan below
+            w.var_off = var_words;
+            w.mp_off = want_mp ? (uint32_t)((tiles[t + 1].mp_off - tiles[t].mp_off) / 4u) : 0u;
+            w.base_pos = first ? 0 : pmin;
+            w.ref = (uint16_t)ref_u;
+            w.flags = (uint16_t)flags;
+            w.lseq = (uint16_t)lseq_u;
+            wt[t] = w;
+            if (flags & SD_WT_SHAPE) {
+                const uint32_t cb = (4u * sum_c + 15u) & ~15u;
+                uint32_t cur = w_max_cig.load(std::memory_order_relaxed);
+                while (cb > cur && !w_max_cig.compare_exchange_weak(cur, cb, std::memory_order_relaxed)) {}
+            }
+        });
+        uint64_t run_b = 0, run_v = 0, run_m = 0;
+        for (size_t t = 0; t < n_tiles; t++) {
+            const uint64_t nb = wt[t].base_off, nv = wt[t].var_off, nm_ = wt[t].mp_off;
+            wt[t].base_off = run_b; wt[t].var_off = (uint32_t)run_v; wt[t].mp_off = (uint32_t)run_m;
+            run_b += nb; run_v += nv; run_m += nm_;
+        }
+        if (run_v >> 32 || run_m >> 32) return bail(SD_ERR_LIMIT, "batch too large for the wire form's 32-bit word offsets");
+        memset(&wt[n_tiles], 0, sizeof(sd_wire_tile));
+        wt[n_tiles].base_off = run_b; wt[n_tiles].var_off = (uint32_t)run_v; wt[n_tiles].mp_off = (uint32_t)run_m;
+        uint8_t *wseq = (uint8_t *)own->mem.get(run_b / 4 + 16), *wqual = (uint8_t *)own->mem.get(run_b * qual_bits / 8 + 16);
+        uint32_t *wvar = (uint32_t *)own->mem.get((run_v + 4) * 4);
+        if (!wseq || !wqual || !wvar) return bail(SD_ERR_NOMEM, "out of host memory");
+        // XI dictionary: a file has a few thousand distinct identities (1 - mismatches / length); beyond 65536 the floats travel
+        std::vector<uint32_t> xi_vals;
+        bool xi_small = true;
+        {
+            const size_t n_chunks = (size_t)std::max(1, threads) * 4, chunk = (n + n_chunks - 1) / n_chunks;
+            std::vector<std::vector<uint32_t>> part(n_chunks);
+            std::atomic<int> big(0);
+            parallel_for(n_chunks, threads, [&](size_t c) {
+                const size_t b = c * chunk, e = std::min(n, b + chunk);
+                std::vector<uint32_t> &v = part[c];
+                for (size_t i = b; i < e && !big.load(std::memory_order_relaxed); i++) {
+                    uint32_t x;
+                    memcpy(&x, &rec[i].xi, 4);
+                    v.push_back(x);
+                    if (v.size() >= (1u << 20)) {
+                        std::sort(v.begin(), v.end());
+                        v.erase(std::unique(v.begin(), v.end()), v.end());
+                        if (v.size() > 65536) big = 1;
+                    }
+                }
+                std::sort(v.begin(), v.end());
+                v.erase(std::unique(v.begin(), v.end()), v.end());
+            });
+            if (!big) {
+                for (auto &v : part) xi_vals.insert(xi_vals.end(), v.begin(), v.end());
+                std::sort(xi_vals.begin(), xi_vals.end());
+                xi_vals.erase(std::unique(xi_vals.begin(), xi_vals.end()), xi_vals.end());
+            }
+            { uint32_t zero = 0; if (!big && !std::binary_search(xi_vals.begin(), xi_vals.end(), zero)) xi_vals.insert(std::lower_bound(xi_vals.begin(), xi_vals.end(), zero), zero); }
+            xi_small = !big && xi_vals.size() <= 65536;
+        }
+        uint16_t *xi16 = xi_small ? (uint16_t *)own->mem.get(slots * 2) : nullptr;
+        float *xi32 = xi_small ? nullptr : (float *)own->mem.get(slots * 4);
+        float *xi_dict = xi_small ? (float *)own->mem.get(std::max<size_t>(1, xi_vals.size()) * 4) : nullptr;
+        if ((xi_small && (!xi16 || !xi_dict)) || (!xi_small && !xi32)) return bail(SD_ERR_NOMEM, "out of host memory");
+        if (xi_small) memcpy(xi_dict, xi_vals.data(), xi_vals.size() * 4);
+        // columns, one tile per task (rows of a tile share bytes of the per-base columns, tiles do not: they start at multiples of 64 bases)
+        parallel_for(n_tiles, threads, [&](size_t t) {
+            const sd_read_rec *r = rec + t * (size_t)tile_reads;
+            const sd_wire_tile h = wt[t];
+            const size_t s0 = t * (size_t)tile_reads;
+            uint32_t v = h.var_off;
+            if (h.flags & SD_WT_POS32) v += 32u;
+            uint16_t *refs = nullptr;
+            if (h.flags & SD_WT_REFS) { refs = (uint16_t *)(wvar + v); v += 16u; }
+            uint32_t *shape = nullptr, *ops = nullptr;
+            if (h.flags & SD_WT_SHAPE) { shape = wvar + v; v += 32u; ops = wvar + v; }
+            const uint32_t *cg = cigc + tiles[t].cig_off / 4;
+            uint32_t sum_c = 0;
+            // bit writers of the two per-base columns; the tile starts byte aligned
+            uint8_t *ps = wseq + h.base_off / 4, *pq = wqual + h.base_off * qual_bits / 8;
+            uint64_t acc_s = 0, acc_q = 0;
+            uint32_t nb_s = 0, nb_q = 0;
+            for (uint32_t k = 0; k < tile_reads; k++) {
+                const uint32_t fl = r[k].ref_mapq_flag >> 24, ref = r[k].ref_mapq_flag & 0xFFFFu, mapq = (r[k].ref_mapq_flag >> 16) & 0xFFu;
+                const uint32_t lseq = r[k].lseq_ncig & 0xFFFFu, ncig = r[k].lseq_ncig >> 16;
+                const bool pad = (fl & SD_F_PAD) != 0;
+                pos16[s0 + k] = (pad || (h.flags & SD_WT_POS32)) ? (uint16_t)0 : (uint16_t)(r[k].pos - h.base_pos);
+                mqf[s0 + k] = (uint16_t)(mapq | (fl << 8));
+                uint32_t xb;
+                memcpy(&xb, &r[k].xi, 4);
+                if (xi16) xi16[s0 + k] = (uint16_t)(std::lower_bound(xi_vals.begin(), xi_vals.end(), pad ? 0u : xb) - xi_vals.begin());
+                else xi32[s0 + k] = r[k].xi;
+                nm16[s0 + k] = (uint16_t)(r[k].nm_nmp & 0xFFFFu);
+                if (nmp16) nmp16[s0 + k] = (uint16_t)(r[k].nm_nmp >> 16);
+                if (h.flags & SD_WT_POS32) wvar[h.var_off + k] = (uint32_t)r[k].pos;
+                if (refs) refs[k] = (uint16_t)ref;
+                if (shape) {
+                    shape[k] = pad ? 0u : r[k].lseq_ncig;
+                    for (uint32_t i = 0; i < ncig; i++) ops[sum_c + i] = cg[sum_c + i];
+                }
+                sum_c += ncig;
+                if (pad) continue;
+                const size_t i = order[s0 + k];
+                const uint8_t *rr = raw.data() + recoff[i];
+                const uint8_t *seq = rr + 32 + rr[8] + 4 * (size_t)rd16(rr + 12);
+                const uint8_t *qual = seq + ((size_t)lseq + 1) / 2;
+                for (uint32_t j = 0; j < lseq; j++) {
+                    const uint32_t nib = (j & 1) ? (seq[j >> 1] & 15u) : (seq[j >> 1] >> 4);
+                    const uint32_t code = nib == 2u ? 1u : (nib == 4u ? 2u : (nib == 8u ? 3u : 0u));   // A=0 C=1 G=2 T=3, anything else A
+                    acc_s |= (uint64_t)code << nb_s;
+                    nb_s += 2;
+                    if (nb_s == 64) { memcpy(ps, &acc_s, 8); ps += 8; acc_s = 0; nb_s = 0; }
+                }
+                if (qual_bits == 8) {
+                    memcpy(pq, qual, lseq);
+                    pq += lseq;
+                } else {
+                    for (uint32_t j = 0; j < lseq; j++) {
+                        acc_q |= (uint64_t)qual_code[qual[j]] << nb_q;
+                        nb_q += qual_bits;
+                        if (nb_q == 64) { memcpy(pq, &acc_q, 8); pq += 8; acc_q = 0; nb_q = 0; }
+                    }
+                }
+            }
+            // flush the writers and zero the padding up to the next tile (64 bases = 16 / 16 / 32 / 64 bytes: the accumulators never straddle it)
+            const uint8_t *es = wseq + wt[t + 1].base_off / 4, *eq = wqual + wt[t + 1].base_off * qual_bits / 8;
+            if (nb_s) { memcpy(ps, &acc_s, (nb_s + 7) / 8); ps += (nb_s + 7) / 8; }
+            if (nb_q) { memcpy(pq, &acc_q, (nb_q + 7) / 8); pq += (nb_q + 7) / 8; }
+            memset(ps, 0, (size_t)(es - ps));
+            memset(pq, 0, (size_t)(eq - pq));
+            if (shape)      // pad words of the var block
+                for (uint32_t i = (uint32_t)(ops - wvar) + sum_c; i < wt[t + 1].var_off; i++) wvar[i] = 0u;
+        });
+        memset(wseq + run_b / 4, 0, 16);
+        memset(wqual + run_b * qual_bits / 8, 0, 16);
+        memset(wvar + run_v, 0, 16);
+        sd_wire &W = hb->wire;
+        W.n_reads = n;
+        W.n_tiles = (uint32_t)n_tiles;
+        W.tile_reads = tile_reads;
+        W.tiles = wt;
+        W.pos16 = pos16; W.mqf = mqf; W.xi16 = xi16; W.nm16 = nm16; W.nmp16 = nmp16;
+        W.xi32 = xi32;
+        W.seq = wseq; W.qual = wqual;
+        W.var = wvar;
+        W.mp = mpc;     // same blocks as the batch's mp column: the tile offsets are its tile table's, in words
+        W.xi_dict = xi_dict;
+        W.n_xi_dict = xi_small ? (uint32_t)xi_vals.size() : 0u;
+        W.qual_bits = qual_bits;
+        memcpy(W.qual_dict, qual_dict, 16);
+        W.max_lseq = max_lseq;
+        W.max_span = max_span.load();
+        W.max_tile_cig = w_max_cig.load();
+        W.max_tile_mp = want_mp ? mt_mp : 0u;
+        lap("wire");
+    }
 
     hb->batch.n_reads = n;
     hb->batch.n_tiles = (uint32_t)n_tiles;

@@ -51,6 +51,7 @@ OPTIONS = {
     "threads": 0,                       # host decode threads (0 = all cores)
     "mismatch_source": "verify",        # "cigar" | "mp" | "verify" (CIGAR walk cross-checked against MP)
     "seq_bits": 2,                      # SEQ column handed to sd_count: 2 = 2-bit base codes (half the bytes), 4 = BAM nibble planes
+    "wire": True,                       # send the reads over PCIe in the packed form (sd_wire / sd_count_wire); False: the columnar batch
     "timings": None,                    # last run's CountTimings
 }
 
@@ -84,8 +85,10 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
     genome, cached = _genome(ref)
     tm["fasta_decode_s"] = 0.0 if cached else genome.seconds
     mode = {"cigar": L.SD_MISMATCH_CIGAR, "mp": L.SD_MISMATCH_MP, "verify": L.SD_MISMATCH_VERIFY}[OPTIONS["mismatch_source"]]
+    # the decoder also writes the packed form that crosses PCIe (sd_wire: 58 instead of 82 bytes per 100 bp read); sd_count_wire
+    # expands it on the device
     hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True,
-                       seq2=OPTIONS["seq_bits"] == 2)
+                       seq2=OPTIONS["seq_bits"] == 2, wire=OPTIONS["seq_bits"] == 2 and OPTIONS.get("wire", True))
     tm["bam_inflate_s"] = hbatch.seconds_inflate
     tm["bam_decode_s"] = hbatch.seconds_decode
     tm["bam_reads"] = hbatch.n_reads
@@ -156,10 +159,18 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
         params = make_params(min_qual=minQual, conversion_threshold=conversionThreshold, mismatch_source=mode)
         eng.synchronize()
         t2 = time.time()
-        my_batch = hbatch.batch
+        my_batch, my_wire = hbatch.batch, hbatch.wire
         if world > 1:
-            my_batch = parallel.sub_batch(hbatch.batch, *parallel.shard_range(hbatch.batch.n_tiles, rank, world))
-        eng.count_host(my_batch, params)
+            t0_, t1_ = parallel.shard_range(hbatch.batch.n_tiles, rank, world)
+            my_batch = parallel.sub_batch(hbatch.batch, t0_, t1_)
+            my_wire = parallel.sub_wire(hbatch.wire, t0_, t1_) if hbatch.wire is not None else None
+
+        def count_mine(p):
+            if my_wire is not None:
+                eng.count_wire(my_wire, p)
+            else:
+                eng.count_host(my_batch, p)
+        count_mine(params)
         if world > 1:
             parallel.reduce_engine_outputs(eng, positions=True)
         eng.synchronize()              # the all-reduce runs on eng.stream: every rank must branch on the REDUCED counter
@@ -171,7 +182,7 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
                   % (int(stats[L.SD_S_MP_DISAGREE]), os.path.basename(ref)), file=log)
             eng.reset_outputs()
             params = make_params(min_qual=minQual, conversion_threshold=conversionThreshold, mismatch_source=L.SD_MISMATCH_MP)
-            eng.count_host(my_batch, params)
+            count_mine(params)
             if world > 1:
                 parallel.reduce_engine_outputs(eng, positions=True)
         eng.finalize()
@@ -300,8 +311,10 @@ def genomewideConversionRates(referenceFile, snpsFile, bam, minBaseQual, outputB
     genome, cached = _genome(referenceFile)
     tm["fasta_decode_s"] = 0.0 if cached else genome.seconds
     mode = {"cigar": L.SD_MISMATCH_CIGAR, "mp": L.SD_MISMATCH_MP, "verify": L.SD_MISMATCH_VERIFY}[OPTIONS["mismatch_source"]]
+    # the decoder also writes the packed form that crosses PCIe (sd_wire: 58 instead of 82 bytes per 100 bp read); sd_count_wire
+    # expands it on the device
     hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True,
-                       seq2=OPTIONS["seq_bits"] == 2)
+                       seq2=OPTIONS["seq_bits"] == 2, wire=OPTIONS["seq_bits"] == 2 and OPTIONS.get("wire", True))
     tm["bam_inflate_s"], tm["bam_decode_s"], tm["bam_reads"] = hbatch.seconds_inflate, hbatch.seconds_decode, hbatch.n_reads
     tc_mask, ag_mask = build_snp_masks(snpsFile, genome.names, genome.chrom_off, genome.chrom_len, genome.n_words, warn=print)
 
@@ -393,8 +406,10 @@ def genomewideReadSeparation(referenceFile, snpsFile, bam, minBaseQual, outputBA
     t0 = time.time()
     genome, cached = _genome(referenceFile)
     mode = {"cigar": L.SD_MISMATCH_CIGAR, "mp": L.SD_MISMATCH_MP, "verify": L.SD_MISMATCH_VERIFY}[OPTIONS["mismatch_source"]]
+    # the decoder also writes the packed form that crosses PCIe (sd_wire: 58 instead of 82 bytes per 100 bp read); sd_count_wire
+    # expands it on the device
     hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True,
-                       seq2=OPTIONS["seq_bits"] == 2)
+                       seq2=OPTIONS["seq_bits"] == 2, wire=OPTIONS["seq_bits"] == 2 and OPTIONS.get("wire", True))
     tm["bam_inflate_s"], tm["bam_decode_s"], tm["bam_reads"] = hbatch.seconds_inflate, hbatch.seconds_decode, hbatch.n_reads
     tc_mask, ag_mask = build_snp_masks(snpsFile, genome.names, genome.chrom_off, genome.chrom_len, genome.n_words, warn=print)
     n = hbatch.n_reads

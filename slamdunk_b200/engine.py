@@ -72,14 +72,16 @@ class HostBatch(object):
     """A BAM file decoded into the columnar batch (sd_decode_bam); buffers are page-locked."""
 
     def __init__(self, path: str, fasta_names: Sequence[str], want_mp: bool = True, tile_reads: int = 0,
-                 threads: int = 0, group: bool = False, raw_qual: bool = False, mp_all: bool = False, seq2: bool = False):
+                 threads: int = 0, group: bool = False, raw_qual: bool = False, mp_all: bool = False, seq2: bool = False,
+                 wire: bool = False):
         lib = L.load()
         err = ctypes.create_string_buffer(512)
         out = ctypes.POINTER(L.HBatch)()
         names = (ctypes.c_char_p * max(1, len(fasta_names)))(*[n.encode() for n in fasta_names])
         rc = lib.sd_decode_bam(os.fsencode(path), names, len(fasta_names),
                                (L.SD_DECODE_MP if want_mp else 0) | (L.SD_DECODE_GROUP if group else 0) |
-                               (L.SD_DECODE_RAW_QUAL if raw_qual else 0) | (L.SD_DECODE_MP_ALL if mp_all else 0) | (L.SD_DECODE_SEQ2 if seq2 else 0), int(tile_reads),
+                               (L.SD_DECODE_RAW_QUAL if raw_qual else 0) | (L.SD_DECODE_MP_ALL if mp_all else 0) | (L.SD_DECODE_SEQ2 if seq2 else 0) |
+                               (L.SD_DECODE_WIRE if wire else 0), int(tile_reads),
                                int(threads), ctypes.byref(out), err, len(err))
         if rc != L.SD_OK:
             raise L.NativeError("sd_decode_bam(%s) failed (%d): %s" % (path, rc, err.value.decode("utf-8", "replace")))
@@ -96,6 +98,7 @@ class HostBatch(object):
         self.inflated_bytes = int(h.inflated_bytes)
         self.n_mapped_no_xi = int(h.n_mapped_no_xi)
         self.n_mapped_no_nm = int(h.n_mapped_no_nm)
+        self.wire = h.wire if (wire and int(h.wire.n_tiles)) else None      # sd_wire with host pointers (SD_DECODE_WIRE)
 
     # numpy views (tests, diagnostics)
     def rec_array(self) -> np.ndarray:
@@ -133,6 +136,25 @@ class HostBatch(object):
         if not n or not addr:
             return np.zeros(0, dtype=np.dtype(dt))
         return np.frombuffer((dt * n).from_address(addr), dtype=np.dtype(dt))
+
+    def wire_arrays(self) -> dict:
+        """numpy views of the wire form's columns (tests, diagnostics)"""
+        w = self.wire
+        nt = int(w.n_tiles)
+        def view(addr, count, dt):
+            if not addr or not count:
+                return np.zeros(0, dtype=dt)
+            return np.frombuffer((ctypes.c_uint8 * (count * np.dtype(dt).itemsize)).from_address(addr), dtype=dt)
+        tiles = view(w.tiles, (nt + 1) * 32, np.uint8).view(np.dtype([("base_off", "<u8"), ("var_off", "<u4"), ("mp_off", "<u4"), ("base_pos", "<i4"),
+                                                                     ("ref", "<u2"), ("flags", "<u2"), ("lseq", "<u2"), ("r0", "<u2"), ("r1", "<u4")]))
+        bases, var_words, mp_words = int(tiles[nt]["base_off"]), int(tiles[nt]["var_off"]), int(tiles[nt]["mp_off"])
+        qb = int(w.qual_bits)
+        return {"tiles": tiles, "pos16": view(w.pos16, nt * 32, np.uint16), "mqf": view(w.mqf, nt * 32, np.uint16),
+                "xi16": view(w.xi16, nt * 32, np.uint16), "xi32": view(w.xi32, nt * 32, np.float32),
+                "nm16": view(w.nm16, nt * 32, np.uint16), "nmp16": view(w.nmp16, nt * 32, np.uint16),
+                "seq": view(w.seq, bases // 4, np.uint8), "qual": view(w.qual, bases * qb // 8, np.uint8),
+                "var": view(w.var, var_words, np.uint32), "mp": view(w.mp, mp_words, np.uint32),
+                "xi_dict": view(w.xi_dict, int(w.n_xi_dict), np.float32), "qual_bits": qb, "qual_dict": list(w.qual_dict)}
 
     def order(self) -> np.ndarray:
         """batch slot -> record index in the file"""

@@ -62,6 +62,22 @@ def sub_batch(batch, t0, t1):
     return b
 
 
+def sub_wire(wire, t0, t1):
+    """View of tiles [t0, t1) of a HOST sd_wire (no copy): the tile table and the per-record columns advance, the per-base,
+    var and mp columns stay because the tile offsets into them are absolute."""
+    w = L.Wire()
+    ctypes.memmove(ctypes.byref(w), ctypes.byref(wire), ctypes.sizeof(L.Wire))
+    t0, t1 = int(t0), int(t1)
+    w.n_tiles = t1 - t0
+    first = t0 * wire.tile_reads
+    w.n_reads = max(0, min(int(wire.n_reads), t1 * wire.tile_reads) - first)
+    w.tiles = wire.tiles + t0 * ctypes.sizeof(L.WireTile)
+    for name, size in (("pos16", 2), ("mqf", 2), ("xi16", 2), ("nm16", 2), ("nmp16", 2), ("xi32", 4)):
+        p = getattr(wire, name)
+        setattr(w, name, p + first * size if p else None)
+    return w
+
+
 def allreduce_sum_(tensors, group=None):
     """In-place SUM all-reduce of integer tensors (NCCL on GPU tensors, gloo on CPU tensors)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:

@@ -18,6 +18,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SMALL = ["--genome-bp", "6000000", "--utrs", "1200", "--steps", "2", "--warmup", "1", "--cpu-sample", "60000"]
 
 
+def _free_port():
+    """a rendezvous port of its own for every torchrun: a port still in TIME_WAIT from the previous run stalls the static rendezvous"""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _bench(extra, gpus=1, timeout=900):
     env = dict(os.environ)
     if gpus == 1:
@@ -26,7 +34,7 @@ def _bench(extra, gpus=1, timeout=900):
             env.pop(k, None)
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(gpus), "--master-addr", "127.0.0.1",
-               "--master-port", "29571", os.path.join(ROOT, "bench.py"), "--gpus", str(gpus)] + SMALL + extra
+               "--master-port", str(_free_port()), os.path.join(ROOT, "bench.py"), "--gpus", str(gpus)] + SMALL + extra
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stderr.decode()[-3000:]
     lines = [l for l in out.stdout.decode().splitlines() if l.startswith("{")]

@@ -267,3 +267,48 @@ def test_records_without_seq_are_counted_but_convert_nothing(tmp_path, mode):
     assert _read(out + ".tsv") == _read(o + ".tsv")
     assert _read(out + "_plus.bedgraph") == _read(o + "_p.bg")
     assert _read(out + "_mins.bedgraph") == _read(o + "_m.bg")
+
+
+@pytest.mark.parametrize("name", ["cfg1", "case_a", "case_b", "case_d", "case_e"])
+@pytest.mark.parametrize("mode", [0, 2])
+def test_decoder_wire_counts_like_the_columnar_batch(name, mode):
+    """The product path sends the decoder's packed form (SD_DECODE_WIRE -> sd_count_wire); the same file through the columnar host
+    batch (sd_count_host) must give identical outputs -- and so must rank-style slices of the wire (parallel.sub_wire) added up."""
+    import torch
+    from slamdunk_b200 import _lib as L, parallel
+    from slamdunk_b200.engine import CountEngine, HostBatch, HostGenome, make_params
+    from slamdunk_b200.utils.bed import BedIterator
+    c = goldens.CountCase(name)
+    genome = HostGenome(c.ref)
+    hb = HostBatch(c.bam, genome.names, want_mp=True, group=True, seq2=True, wire=True)
+    assert hb.wire is not None
+    utrs = list(BedIterator(c.bed))
+    eng = CountEngine(0)
+    eng.set_reference(genome.lo, genome.hi, genome.nmask, genome.chrom_off, genome.chrom_len)
+    eng.set_utrs(np.array([genome.index.get(u.chromosome, L.SD_REF_NONE) for u in utrs], dtype=np.uint32), np.array([u.start for u in utrs]),
+                 np.array([u.stop for u in utrs]), np.array([1 if u.strand == "-" else 0 for u in utrs], dtype=np.uint8), None)
+    params = make_params(27, 1, mode, filter_on=True, filter_mq=0, filter_min_identity=0.5)
+    eng.count_host(hb.batch, params)
+    eng.finalize()
+    want = eng.results()
+    eng.reset_outputs()
+    eng.count_wire(hb.wire, params)
+    eng.finalize()
+    got = eng.results()
+    for k in ("counters", "stats", "pos_cov", "pos_tc"):
+        assert np.array_equal(want[k], got[k]), k
+    assert want["stats"][L.SD_S_COUNTED] > 0
+    nt = int(hb.batch.n_tiles)
+    if nt >= 2:
+        eng.reset_outputs()
+        for r in range(3):
+            t0, t1 = parallel.shard_range(nt, r, 3)
+            if t1 > t0:
+                eng.count_wire(parallel.sub_wire(hb.wire, t0, t1), params)
+        eng.finalize()
+        got = eng.results()
+        for k in ("counters", "stats", "pos_cov", "pos_tc"):
+            assert np.array_equal(want[k], got[k]), "slices " + k
+    eng.close()
+    hb.close()
+    genome.close()

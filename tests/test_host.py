@@ -548,3 +548,128 @@ def test_utrrates_percentages_and_checkstep_host_logic(tmp_path):
     assert stats.checkStep([src], [out], force=True) is True           # ... unless forced
     with pytest.raises(RuntimeError, match="don't exist"):
         stats.checkStep([src, str(tmp_path / "missing")], [out])
+
+
+def _unpack_wire(hb):
+    """Plain-numpy reading of the wire form (include/slamdunk_b200.h, sd_wire): -> per slot (pos, ref, mapq, flags, xi, nm, nmp,
+    lseq, cigar ops, 2-bit base codes, qualities) -- the format's second implementation, next to wire_expand_kernel."""
+    w = hb.wire_arrays()
+    T = w["tiles"]
+    nt = len(T) - 1
+    qb = w["qual_bits"]
+    out = []
+    for t in range(nt):
+        h = T[t]
+        v = int(h["var_off"])
+        fl = int(h["flags"])
+        pos32 = refs = shape = None
+        if fl & 1:
+            pos32 = w["var"][v:v + 32].view(np.int32); v += 32
+        if fl & 2:
+            refs = w["var"][v:v + 16].view(np.uint16); v += 16
+        if fl & 4:
+            shape = w["var"][v:v + 32]; v += 32
+        base = int(h["base_off"])
+        cig_at = v
+        for k in range(32):
+            s = t * 32 + k
+            m = int(w["mqf"][s])
+            mapq, flags = m & 0xFF, m >> 8
+            pad = bool(flags & 0x80)
+            pos = int(pos32[k]) if pos32 is not None else int(h["base_pos"]) + int(w["pos16"][s])
+            ref = int(refs[k]) if refs is not None else int(h["ref"])
+            if shape is not None:
+                lseq, ncig = int(shape[k]) & 0xFFFF, int(shape[k]) >> 16
+                ops = [int(x) for x in w["var"][cig_at:cig_at + ncig]]
+                cig_at += ncig
+            else:
+                lseq, ncig = (0, 0) if pad else (int(h["lseq"]), 1)
+                ops = [] if pad else [lseq << 4]
+            xi = float(w["xi_dict"][w["xi16"][s]]) if len(w["xi16"]) else float(w["xi32"][s])
+            if pad:
+                out.append(None)
+                continue
+            idx = base + np.arange(lseq)
+            codes = (w["seq"][idx // 4] >> (2 * (idx % 4))) & 3
+            if qb == 8:
+                q = w["qual"][base:base + lseq]
+            else:
+                per = 8 // qb
+                q = np.array(w["qual_dict"], dtype=np.uint8)[(w["qual"][idx // per] >> (qb * (idx % per))) & ((1 << qb) - 1)]
+            base += lseq
+            out.append(dict(pos=pos, ref=ref, mapq=mapq, flags=flags, xi=xi, nm=int(w["nm16"][s]), nmp=int(w["nmp16"][s]) if len(w["nmp16"]) else 0,
+                            lseq=lseq, ops=ops, codes=codes.tolist(), qual=[int(x) for x in q]))
+    return out, w
+
+
+def _uniform_bam(path, n_reads, L=40):
+    """plain reads of one length on two chromosomes, positions up to 200 kb apart inside one tile, three distinct qualities:
+    tiles without l_seq / CIGAR, with 32-bit positions, with per-read chromosomes"""
+    from slamdunk_b200.io import bam as bamio
+    rng = np.random.RandomState(3)
+    refs = [("c1", 400000), ("c2", 300000)]
+    recs = []
+    for i in range(n_reads):
+        ref = 0 if i < n_reads * 2 // 3 else 1
+        pos = int(rng.randint(0, 1000)) + (200000 if (i // 8) % 5 == 4 and i % 2 else 0)
+        seq = "".join(rng.choice(list("ACGTN"), p=[0.24, 0.24, 0.24, 0.24, 0.04]) for _ in range(L))
+        recs.append(bamio.BamRecord("u%04d" % i, 16 if i % 3 == 0 else 0, ref, pos, 60 if i % 7 else 0, [(0, L)], seq,
+                                    [int(rng.choice([20, 30, 37])) for _ in range(L)],
+                                    [("NM", "i", i % 4), ("XI", "f", 1.0 - (i % 4) / L), ("MP", "Z", "16:3:3" if i % 3 else "2:5:5")]))
+    recs = bamio.sort_records(recs)
+    hdr = "@HD\tVN:1.0\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % r for r in refs)
+    bamio.write_bam(path, hdr, refs, recs)
+    return [r[0] for r in refs]
+
+
+@pytest.mark.parametrize("seed,n_reads,group,complexity", [(5, 700, True, 2.0), (6, 333, False, 1.0), (7, 64, True, 0.0), (0, 250, True, -1.0)])
+def test_decoder_wire_form_holds_the_same_records_as_the_batch(tmp_path, seed, n_reads, group, complexity):
+    """SD_DECODE_WIRE: the packed form sd_count_wire sends over PCIe, written by the decoder straight from the BAM records, read
+    back with plain numpy and compared field by field with the columnar batch of the same call (and with the Python codec's
+    records): positions incl. tiles on several chromosomes / wide position ranges, XI dictionary, CIGAR ops of the shaped
+    tiles only, 2-bit base codes, quality codes, MP blocks."""
+    from slamdunk_b200.engine import HostBatch
+    from slamdunk_b200.io import bam as bamio
+    if complexity < 0:
+        bam_path = str(tmp_path / "uniform.bam")
+        names = _uniform_bam(bam_path, n_reads)
+    else:
+        c = simdata.make_case(str(tmp_path), seed=seed, n_reads=n_reads, complexity=complexity)
+        names, bam_path = list(c.genome.keys()), c.bam
+    hb = HostBatch(bam_path, names, want_mp=True, group=group, seq2=True, wire=True)
+    assert hb.wire is not None and int(hb.wire.n_tiles) == int(hb.batch.n_tiles) and int(hb.wire.n_reads) == n_reads
+    rows, w = _unpack_wire(hb)
+    rec, tiles, order = hb.rec_array(), hb.tiles_array(), hb.order()
+    _, _, recs = bamio.read_bam(bam_path)
+    cig, qual = hb.column("cigar"), hb.column("qual")
+    code_of = {"A": 0, "C": 1, "G": 2, "T": 3}
+    T = w["tiles"]
+    n_shape = 0
+    for t in range(int(hb.batch.n_tiles)):
+        assert int(T[t]["base_off"]) % 64 == 0 and int(T[t]["var_off"]) % 4 == 0
+        n_shape += bool(int(T[t]["flags"]) & 4)
+        co, qo = int(tiles[t][2]) // 4, int(tiles[t][1])
+        assert int(T[t]["mp_off"]) == int(tiles[t][3]) // 4
+        for k in range(32):
+            s = t * 32 + k
+            if s >= n_reads:
+                assert rows[s] is None
+                continue
+            r, b = rows[s], rec[s]
+            lseq, ncig = int(b[3]) & 0xFFFF, int(b[3]) >> 16
+            assert (r["pos"], r["ref"], r["mapq"], r["flags"]) == (int(np.int32(b[0])), int(b[1]) & 0xFFFF, (int(b[1]) >> 16) & 0xFF, int(b[1]) >> 24)
+            assert np.float32(r["xi"]).tobytes() == np.uint32(b[2]).tobytes() or (np.isnan(r["xi"]) and np.isnan(np.uint32(b[2]).view(np.float32)))
+            assert (r["nm"], r["nmp"], r["lseq"]) == (int(b[4]) & 0xFFFF, int(b[4]) >> 16, lseq)
+            assert r["ops"] == [int(x) for x in cig[co:co + ncig]]
+            src = recs[order[s]]
+            assert r["codes"] == [code_of.get(ch, 0) for ch in src.seq.upper()]
+            assert r["qual"] == list(qual[qo:qo + lseq]) == src.qual
+            co += ncig
+            qo += lseq
+    if complexity < 0:      # plain-match tiles of one read length carry neither l_seq nor CIGAR
+        assert n_shape == 0 and w["qual_bits"] == 2 and len(w["xi_dict"]) <= 5
+        assert any(int(x) & 1 for x in T["flags"][:-1]) and any(int(x) & 2 for x in T["flags"][:-1])      # 32-bit positions, per-read chromosomes
+    else:
+        assert n_shape > 0
+    assert np.array_equal(w["mp"], hb.column("mp")[:len(w["mp"])])
+    hb.close()

@@ -117,3 +117,37 @@ def test_sub_batch_views(tmp_path):
         total += sb.n_reads
     assert total == hb.n_reads
     hb.close()
+
+
+def test_region_bounds_cut_between_utrs_no_read_can_cross():
+    """bench.Bench.region_bounds (BASELINE.json config 5, chromosome-region sharding): the cuts tile the linear genome, each cut
+    lies a read length before a UTR that no earlier UTR of its chromosome reaches, so a read -- placed within a read length of
+    its UTR -- starts in the stretch that owns the UTR and never touches a UTR of another stretch."""
+    import argparse
+    import bench
+    from slamdunk_b200.synth import genome_layout, make_annotation
+
+    class FakeWorkload(object):
+        def __init__(self, seed):
+            self.chrom_len = np.array([300_000, 250_000, 180_000, 90_000], dtype=np.uint32)
+            self.chrom_off, self.n_words = genome_layout(self.chrom_len)
+            self.ann = make_annotation(seed, self.chrom_len, 400, overlap_frac=0.2)
+            self.cum_weight = np.cumsum(self.ann.weight)
+        region_split = __import__("slamdunk_b200.synth", fromlist=["SynthWorkload"]).SynthWorkload.region_split
+
+    for seed in (1, 2, 3):
+        wl = FakeWorkload(seed)
+        b = bench.Bench.__new__(bench.Bench)
+        b.wl, b.args = wl, argparse.Namespace(read_len=100)
+        a = wl.ann
+        gs = wl.chrom_off[a.chrom].astype(np.int64) + a.start
+        ge = wl.chrom_off[a.chrom].astype(np.int64) + a.stop
+        for n_parts in (2, 3, 8):
+            bounds = b.region_bounds(n_parts)
+            assert len(bounds) == n_parts and bounds[0][0] == 0 and bounds[-1][1] >= (1 << 32)
+            assert all(bounds[k][1] == bounds[k + 1][0] and bounds[k][0] <= bounds[k][1] for k in range(n_parts - 1))
+            for lo, hi in bounds[:-1]:
+                cut = hi
+                # reads of a UTR start in [start - 103, stop) and end before stop + 103: no UTR may straddle the cut with that margin
+                left = gs - 103 < cut
+                assert np.all((ge[left] + 103 <= cut) | ~left[left]) and np.all(gs[~left] - 103 >= cut)
