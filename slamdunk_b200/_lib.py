@@ -66,6 +66,12 @@ class Wire(ctypes.Structure):
 
 
 SD_WT_POS32, SD_WT_REFS, SD_WT_SHAPE = 1, 2, 4
+try:
+    import numpy as _np
+    WIRE_TILE_DT = _np.dtype([("base_off", "<u8"), ("var_off", "<u4"), ("mp_off", "<u4"), ("base_pos", "<i4"), ("ref", "<u2"),
+                              ("flags", "<u2"), ("lseq", "<u2"), ("reserved0", "<u2"), ("reserved1", "<u4")])      # sd_wire_tile
+except ImportError:      # numpy is only needed for the array views
+    WIRE_TILE_DT = None
 SD_DECODE_WIRE = 32
 
 

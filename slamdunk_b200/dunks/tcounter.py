@@ -52,6 +52,7 @@ OPTIONS = {
     "mismatch_source": "verify",        # "cigar" | "mp" | "verify" (CIGAR walk cross-checked against MP)
     "seq_bits": 2,                      # SEQ column handed to sd_count: 2 = 2-bit base codes (half the bytes), 4 = BAM nibble planes
     "wire": True,                       # send the reads over PCIe in the packed form (sd_wire / sd_count_wire); False: the columnar batch
+    "decode_on_rank0": True,            # under torchrun: rank 0 decodes the BAM and scatters the wire slices (False: every rank decodes)
     "timings": None,                    # last run's CountTimings
 }
 
@@ -86,14 +87,24 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
     tm["fasta_decode_s"] = 0.0 if cached else genome.seconds
     mode = {"cigar": L.SD_MISMATCH_CIGAR, "mp": L.SD_MISMATCH_MP, "verify": L.SD_MISMATCH_VERIFY}[OPTIONS["mismatch_source"]]
     # the decoder also writes the packed form that crosses PCIe (sd_wire: 58 instead of 82 bytes per 100 bp read); sd_count_wire
-    # expands it on the device
-    hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True,
-                       seq2=OPTIONS["seq_bits"] == 2, wire=OPTIONS["seq_bits"] == 2 and OPTIONS.get("wire", True))
-    tm["bam_inflate_s"] = hbatch.seconds_inflate
-    tm["bam_decode_s"] = hbatch.seconds_decode
-    tm["bam_reads"] = hbatch.n_reads
+    # expands it on the device.  Under torchrun ONE rank inflates and decodes the file and hands the others their tile slices
+    # (parallel.scatter_wire): N ranks decoding the same BAM on the same cores is N times the host work for nothing.
+    use_wire = OPTIONS["seq_bits"] == 2 and OPTIONS.get("wire", True)
+    scatter = world > 1 and use_wire and OPTIONS.get("decode_on_rank0", True)
+    hbatch = None
+    if rank == 0 or not scatter:
+        hbatch = HostBatch(bam, genome.names, want_mp=(mode != L.SD_MISMATCH_CIGAR), threads=OPTIONS["threads"], group=True,
+                           seq2=OPTIONS["seq_bits"] == 2, wire=use_wire)
+    info = [dict(header_text=hbatch.header_text, ref_names=hbatch.ref_names, n_reads=hbatch.n_reads, inflate=hbatch.seconds_inflate,
+                 decode=hbatch.seconds_decode) if hbatch is not None else None]
+    if scatter:
+        parallel.dist.broadcast_object_list(info, src=0, group=parallel.host_group())
+    info = info[0]
+    tm["bam_inflate_s"] = info["inflate"]
+    tm["bam_decode_s"] = info["decode"]
+    tm["bam_reads"] = info["n_reads"]
 
-    header = parse_sam_header(hbatch.header_text)
+    header = parse_sam_header(info["header_text"])
     sampleInfo = getSampleInfo(header)                       # tcounter.py:129
     slamseqInfo = SlamSeqInfo(header)                        # tcounter.py:131
     readNumber = slamseqInfo.FilteredReads                   # tcounter.py:133
@@ -140,7 +151,7 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
             pending_error = NegativeStartError("Negativ start coordinate found. Please check the following entry in your BED file: " + repr(utr))
             break
         utrs.append(utr)
-    bam_names = set(hbatch.ref_names)
+    bam_names = set(info["ref_names"])
     n = len(utrs)
     chrom_idx = np.array([genome.index.get(u.chromosome, L.SD_REF_NONE) for u in utrs], dtype=np.uint32)
     start = np.array([u.start for u in utrs], dtype=np.int64)
@@ -159,11 +170,18 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
         params = make_params(min_qual=minQual, conversion_threshold=conversionThreshold, mismatch_source=mode)
         eng.synchronize()
         t2 = time.time()
-        my_batch, my_wire = hbatch.batch, hbatch.wire
-        if world > 1:
-            t0_, t1_ = parallel.shard_range(hbatch.batch.n_tiles, rank, world)
-            my_batch = parallel.sub_batch(hbatch.batch, t0_, t1_)
-            my_wire = parallel.sub_wire(hbatch.wire, t0_, t1_) if hbatch.wire is not None else None
+        t_sc = time.time()
+        keep_alive = None
+        if scatter:
+            my_batch = None
+            my_wire, keep_alive = parallel.scatter_wire(hbatch.wire if hbatch is not None else None, rank, world)
+        else:
+            my_batch, my_wire = hbatch.batch, hbatch.wire
+            if world > 1:
+                t0_, t1_ = parallel.shard_range(hbatch.batch.n_tiles, rank, world)
+                my_batch = parallel.sub_batch(hbatch.batch, t0_, t1_)
+                my_wire = parallel.sub_wire(hbatch.wire, t0_, t1_) if hbatch.wire is not None else None
+        tm["scatter_s"] = time.time() - t_sc
 
         def count_mine(p):
             if my_wire is not None:
@@ -207,7 +225,7 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
         rs.utrs, rs.has_bed = utrs, True
         try:
             pairs = rs.run(minQual, conversion_threshold=conversionThreshold, strict=True, want=("pairs",),
-                           pair_capacity=2 * hbatch.n_reads + 1024)["pairs"]
+                           pair_capacity=2 * info["n_reads"] + 1024)["pairs"]
         finally:
             rs.close()
         pair_lo = np.searchsorted(pairs["row"], np.arange(n), side="left")
@@ -247,7 +265,8 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
     tm["write_s"] = time.time() - t3
     tm["total_s"] = time.time() - t0
     OPTIONS["timings"] = tm
-    hbatch.close()
+    if hbatch is not None:
+        hbatch.close()
 
 
 def _write_bedgraphs(utrs, chrom_idx, genome, res, pos_off, pos_len, counters, out_plus, out_minus):
@@ -376,14 +395,15 @@ def genomewideConversionRates(referenceFile, snpsFile, bam, minBaseQual, outputB
         eng.close()
     tm["total_s"] = time.time() - t0
     OPTIONS["timings"] = tm
-    hbatch.close()
+    if hbatch is not None:
+        hbatch.close()
 
 
 def _chromosome_rows(genome, hbatch):
     """Annotation rows 2c (+) and 2c + 1 (-) for FASTA chromosome c, [1, chrLen + 1) as the reference's whole-chromosome
     iterator sees it (readsInChromosome, SlamSeqFile.py:447-453)."""
     n_chrom = len(genome.names)
-    bam_names = set(hbatch.ref_names)
+    bam_names = set(info["ref_names"])
     lengths = np.asarray(genome.chrom_len, dtype=np.int64)
     return (np.repeat(np.arange(n_chrom, dtype=np.uint32), 2), np.ones(2 * n_chrom, dtype=np.int64), np.repeat(lengths + 1, 2),
             np.tile(np.array([0, 1], dtype=np.uint8), n_chrom),

@@ -68,6 +68,28 @@ class HostGenome(object):
         return ~self.lo & ~self.hi & ~self.nmask
 
 
+def wire_arrays(w: "L.Wire") -> dict:
+    """numpy views of a HOST sd_wire's columns (tests, diagnostics, the multi-rank scatter)"""
+    nt = int(w.n_tiles)
+
+    def view(addr, count, dt):
+        if not addr or not count:
+            return np.zeros(0, dtype=dt)
+        return np.frombuffer((ctypes.c_uint8 * (count * np.dtype(dt).itemsize)).from_address(addr), dtype=dt)
+    tiles = view(w.tiles, (nt + 1) * 32, np.uint8).view(L.WIRE_TILE_DT)
+    b0, v0, m0 = (int(tiles[0][k]) for k in ("base_off", "var_off", "mp_off")) if nt else (0, 0, 0)
+    b1, v1, m1 = (int(tiles[nt][k]) for k in ("base_off", "var_off", "mp_off")) if nt else (0, 0, 0)
+    qb = int(w.qual_bits)
+    # the per-base, var and mp columns are addressed by the tiles' absolute offsets: the views start at the column bases
+    return {"tiles": tiles, "pos16": view(w.pos16, nt * 32, np.uint16), "mqf": view(w.mqf, nt * 32, np.uint16),
+            "xi16": view(w.xi16, nt * 32, np.uint16), "xi32": view(w.xi32, nt * 32, np.float32),
+            "nm16": view(w.nm16, nt * 32, np.uint16), "nmp16": view(w.nmp16, nt * 32, np.uint16),
+            "seq": view(w.seq, b1 // 4, np.uint8), "qual": view(w.qual, b1 * qb // 8, np.uint8),
+            "var": view(w.var, v1, np.uint32), "mp": view(w.mp, m1, np.uint32),
+            "xi_dict": view(w.xi_dict, int(w.n_xi_dict), np.float32), "qual_bits": qb, "qual_dict": list(w.qual_dict),
+            "first": (b0, v0, m0)}
+
+
 class HostBatch(object):
     """A BAM file decoded into the columnar batch (sd_decode_bam); buffers are page-locked."""
 
@@ -139,22 +161,7 @@ class HostBatch(object):
 
     def wire_arrays(self) -> dict:
         """numpy views of the wire form's columns (tests, diagnostics)"""
-        w = self.wire
-        nt = int(w.n_tiles)
-        def view(addr, count, dt):
-            if not addr or not count:
-                return np.zeros(0, dtype=dt)
-            return np.frombuffer((ctypes.c_uint8 * (count * np.dtype(dt).itemsize)).from_address(addr), dtype=dt)
-        tiles = view(w.tiles, (nt + 1) * 32, np.uint8).view(np.dtype([("base_off", "<u8"), ("var_off", "<u4"), ("mp_off", "<u4"), ("base_pos", "<i4"),
-                                                                     ("ref", "<u2"), ("flags", "<u2"), ("lseq", "<u2"), ("r0", "<u2"), ("r1", "<u4")]))
-        bases, var_words, mp_words = int(tiles[nt]["base_off"]), int(tiles[nt]["var_off"]), int(tiles[nt]["mp_off"])
-        qb = int(w.qual_bits)
-        return {"tiles": tiles, "pos16": view(w.pos16, nt * 32, np.uint16), "mqf": view(w.mqf, nt * 32, np.uint16),
-                "xi16": view(w.xi16, nt * 32, np.uint16), "xi32": view(w.xi32, nt * 32, np.float32),
-                "nm16": view(w.nm16, nt * 32, np.uint16), "nmp16": view(w.nmp16, nt * 32, np.uint16),
-                "seq": view(w.seq, bases // 4, np.uint8), "qual": view(w.qual, bases * qb // 8, np.uint8),
-                "var": view(w.var, var_words, np.uint32), "mp": view(w.mp, mp_words, np.uint32),
-                "xi_dict": view(w.xi_dict, int(w.n_xi_dict), np.float32), "qual_bits": qb, "qual_dict": list(w.qual_dict)}
+        return wire_arrays(self.wire)
 
     def order(self) -> np.ndarray:
         """batch slot -> record index in the file"""

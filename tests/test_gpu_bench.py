@@ -198,3 +198,16 @@ def test_sample_snps_reach_the_reads_and_are_masked():
         oracle.free_snps(h)
     assert ob.compare(masked, rows, bg, wl.ann, eng.pos_off, wl.chrom_off) == []
     eng.close()
+
+
+def test_file_path_on_two_gpus_writes_the_golden_files():
+    """computeTconversions under torchrun on 2 GPUs (rank 0 decodes, the wire slices are scattered, NCCL all-reduce of the outputs,
+    rank 0 writes): every golden case byte for byte, and the region-sharded atlas check (tests/mgpu_count_check.py)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_count_check.py")]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900, cwd=ROOT)
+    text = out.stdout.decode()
+    assert out.returncode == 0 and "MGPU_CHECK PASS" in text, text[-3000:]

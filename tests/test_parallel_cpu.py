@@ -151,3 +151,55 @@ def test_region_bounds_cut_between_utrs_no_read_can_cross():
                 # reads of a UTR start in [start - 103, stop) and end before stop + 103: no UTR may straddle the cut with that margin
                 left = gs - 103 < cut
                 assert np.all((ge[left] + 103 <= cut) | ~left[left]) and np.all(gs[~left] - 103 >= cut)
+
+
+def _scatter_worker(rank, world, port, bam_path, names, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import pickle
+    from slamdunk_b200 import parallel
+    from slamdunk_b200.engine import HostBatch, wire_arrays
+    from wireutil import unpack_wire
+    parallel.init("gloo")
+    hb = HostBatch(bam_path, names, want_mp=True, group=True, seq2=True, wire=True) if rank == 0 else None
+    mine, keep = parallel.scatter_wire(hb.wire if hb is not None else None, rank, world)
+    rows, arrays = unpack_wire(wire_arrays(mine))
+    with open(os.path.join(out_dir, "rank%d.pkl" % rank), "wb") as fh:
+        pickle.dump({"rows": rows, "n_tiles": int(mine.n_tiles), "n_reads": int(mine.n_reads), "mp": arrays["mp"][arrays["first"][2]:].tolist(),
+                     "scalars": (int(mine.qual_bits), list(mine.qual_dict), int(mine.max_lseq), int(mine.max_span), int(mine.max_tile_cig),
+                                 int(mine.max_tile_mp), int(mine.n_xi_dict))}, fh)
+    if rank == 0:
+        whole, warr = unpack_wire(hb)
+        with open(os.path.join(out_dir, "whole.pkl"), "wb") as fh:
+            pickle.dump({"rows": whole, "n_tiles": int(hb.wire.n_tiles), "mp": warr["mp"].tolist()}, fh)
+    dist.barrier()
+    del keep
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_wire_scatter_gives_every_rank_its_tile_slice(tmp_path, world):
+    """computeTconversions under torchrun: rank 0 decodes the BAM, parallel.scatter_wire hands every rank the tile slice
+    shard_range() assigns it (gloo, CPU).  The slices, read back with the numpy unpacker, are the whole wire cut at the tile
+    boundaries -- records, base codes, qualities, CIGAR ops, MP blocks -- and the scalars travel too."""
+    import pickle
+    from slamdunk_b200 import parallel
+    c = simdata.make_case(str(tmp_path), seed=77, n_reads=900, complexity=1.5, name="c")
+    names = list(c.genome.keys())
+    port = _free_port()
+    mp.spawn(_scatter_worker, args=(world, port, c.bam, names, str(tmp_path)), nprocs=world, join=True)
+    whole = pickle.load(open(str(tmp_path / "whole.pkl"), "rb"))
+    nt = whole["n_tiles"]
+    got_rows, got_mp, scalars = [], [], None
+    for r in range(world):
+        d = pickle.load(open(str(tmp_path / ("rank%d.pkl" % r)), "rb"))
+        t0, t1 = parallel.shard_range(nt, r, world)
+        assert d["n_tiles"] == t1 - t0 and d["n_reads"] == min(900, t1 * 32) - t0 * 32
+        assert scalars is None or scalars == d["scalars"]
+        scalars = d["scalars"]
+        got_rows += d["rows"]
+        got_mp += d["mp"]
+    assert len(got_rows) == len(whole["rows"]) == nt * 32
+    assert got_rows == whole["rows"]
+    assert got_mp == whole["mp"]
