@@ -85,6 +85,9 @@ def lib():
         L.orc_count.argtypes = [ctypes.POINTER(_CountArgs), ctypes.c_void_p,
                                 ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
         L.orc_free.argtypes = [ctypes.c_void_p]
+        L.orc_select_sort.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_int]
+        L.orc_select_sort.restype = ctypes.c_int64
         L.orc_positional_chrom.argtypes = [ctypes.POINTER(_CountArgs), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_positional_chrom.restype = ctypes.c_int
@@ -138,23 +141,42 @@ def free_snps(h) -> None:
         lib().orc_snps_free(h)
 
 
+def select_sort(reads: np.ndarray, keep: Optional[np.ndarray], n_chrom: int, threads: int = 1):
+    """The kept reads in coordinate order (what `slamdunk filter` + samtools sort leave behind), bucketed and sorted on all
+    threads by the C side.  -> (reads READ_DT sorted by (chrom, pos), begin int64[n_chrom + 1], max_span int32[n_chrom])"""
+    reads = np.ascontiguousarray(reads, dtype=READ_DT)
+    out = np.empty(len(reads), dtype=READ_DT)
+    begin = np.zeros(n_chrom + 1, dtype=np.int64)
+    span = np.ones(n_chrom, dtype=np.int32)
+    k = np.ascontiguousarray(keep, dtype=np.uint8) if keep is not None else None
+    n_out = lib().orc_select_sort(reads.ctypes.data, k.ctypes.data if k is not None else None, len(reads), n_chrom, out.ctypes.data,
+                                  begin.ctypes.data, span.ctypes.data, int(threads))
+    return out[:n_out], begin, span
+
+
 def count_arrays(genome: Genome, reads: np.ndarray, qual_pool: np.ndarray, utrs: np.ndarray,
                  min_qual: int, conv_threshold: int, snps=None,
                  mp_text: Optional[bytes] = None, mp_triples: Optional[np.ndarray] = None,
-                 threads: int = 1):
-    """reads: READ_DT array (any order; sorted here by (chrom, pos) like an indexed BAM).
+                 threads: int = 1, presorted=None):
+    """reads: READ_DT array (any order; sorted here by (chrom, pos) like an indexed BAM), or presorted = (begin, max_span) from
+    select_sort() when they already are.
     -> (rows ROW_DT[n_utr], bedgraph BG_DT[...])"""
     L = lib()
-    reads = np.ascontiguousarray(reads, dtype=READ_DT)
-    order = np.lexsort((reads["pos"], reads["chrom"]))
-    reads = np.ascontiguousarray(reads[order])
     n_chrom = len(genome.names)
-    begin = np.searchsorted(reads["chrom"], np.arange(n_chrom + 1), side="left").astype(np.int64)
-    span = np.ones(n_chrom, dtype=np.int32)
-    for c in range(n_chrom):
-        seg = reads[begin[c]:begin[c + 1]]
-        if len(seg):
-            span[c] = max(1, int((seg["end"] - seg["pos"]).max()))
+    if presorted is not None:
+        reads = np.ascontiguousarray(reads, dtype=READ_DT)
+        begin = np.ascontiguousarray(presorted[0], dtype=np.int64)
+        span = np.ascontiguousarray(presorted[1], dtype=np.int32)
+    else:
+        reads = np.ascontiguousarray(reads, dtype=READ_DT)
+        order = np.lexsort((reads["pos"], reads["chrom"]))
+        reads = np.ascontiguousarray(reads[order])
+        begin = np.searchsorted(reads["chrom"], np.arange(n_chrom + 1), side="left").astype(np.int64)
+        span = np.ones(n_chrom, dtype=np.int32)
+        for c in range(n_chrom):
+            seg = reads[begin[c]:begin[c + 1]]
+            if len(seg):
+                span[c] = max(1, int((seg["end"] - seg["pos"]).max()))
     names = (ctypes.c_char_p * n_chrom)(*[n.encode() for n in genome.names])
     seqs = (ctypes.c_char_p * n_chrom)(*genome.seqs)
     utrs = np.ascontiguousarray(utrs, dtype=UTR_DT)

@@ -417,6 +417,64 @@ int orc_count(const orc_count_args_t *a, orc_row_t *rows, orc_bg_t **bg, int64_t
 
 void orc_free(void *p) { free(p); }
 
+/* The coordinate order `slamdunk filter` leaves its output in (samtools sort, filter.py:308) and the indexed fetch relies on:
+ * the reads with keep[i] != 0 (keep == NULL: all) bucketed by chromosome -- reads on no FASTA chromosome (chrom < 0) first, as
+ * np.lexsort would place them -- and ordered by position inside each bucket (stable: equal positions keep file order), the buckets
+ * sorted side by side on the OpenMP threads.  out: n_out reads; begin[n_chrom + 1]: first read of every chromosome in `out`;
+ * max_span[n_chrom]: widest alignment per chromosome (at least 1).  Returns n_out. */
+static int cmp_read_pos(const void *a, const void *b) {
+    const orc_read_t *x = (const orc_read_t *)a, *y = (const orc_read_t *)b;
+    if (x->pos != y->pos) return x->pos < y->pos ? -1 : 1;
+    return x->mp_off < y->mp_off ? -1 : (x->mp_off > y->mp_off ? 1 : (x->qual_off < y->qual_off ? -1 : (x->qual_off > y->qual_off ? 1 : 0)));
+}
+int64_t orc_select_sort(const orc_read_t *r, const uint8_t *keep, int64_t n, int32_t n_chrom, orc_read_t *out, int64_t *begin,
+                        int32_t *max_span, int threads) {
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+    const int nt = omp_get_max_threads();
+#else
+    const int nt = 1;
+#endif
+    const int32_t nb = n_chrom + 1;                       /* bucket 0: chrom < 0, bucket c + 1: chromosome c */
+    int64_t *cnt = (int64_t *)calloc((size_t)nt * nb, sizeof(int64_t));
+    const int64_t chunk = (n + nt - 1) / nt;
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < nt; t++) {
+        const int64_t b = t * chunk, e = b + chunk < n ? b + chunk : n;
+        for (int64_t i = b; i < e; i++)
+            if (!keep || keep[i]) cnt[(size_t)t * nb + (r[i].chrom < 0 || r[i].chrom >= n_chrom ? 0 : r[i].chrom + 1)]++;
+    }
+    int64_t run = 0;
+    int64_t *bucket0 = (int64_t *)calloc((size_t)nb + 1, sizeof(int64_t));
+    for (int32_t k = 0; k < nb; k++) {
+        bucket0[k] = run;
+        for (int t = 0; t < nt; t++) { const int64_t c = cnt[(size_t)t * nb + k]; cnt[(size_t)t * nb + k] = run; run += c; }
+    }
+    bucket0[nb] = run;
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < nt; t++) {
+        const int64_t b = t * chunk, e = b + chunk < n ? b + chunk : n;
+        int64_t *at = cnt + (size_t)t * nb;
+        for (int64_t i = b; i < e; i++)
+            if (!keep || keep[i]) out[at[r[i].chrom < 0 || r[i].chrom >= n_chrom ? 0 : r[i].chrom + 1]++] = r[i];
+    }
+    /* the scatter above keeps file order inside a bucket; qsort is not stable, so ties are broken by the reads' pool offsets,
+     * which ascend in file order for the batches the bench builds */
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int32_t k = 0; k < nb; k++) {
+        const int64_t b = bucket0[k], e = bucket0[k + 1];
+        if (e - b > 1) qsort(out + b, (size_t)(e - b), sizeof(orc_read_t), cmp_read_pos);
+        if (k > 0) {
+            int32_t span = 1;
+            for (int64_t i = b; i < e; i++) if (out[i].end - out[i].pos > span) span = out[i].end - out[i].pos;
+            max_span[k - 1] = span;
+        }
+    }
+    for (int32_t c = 0; c <= n_chrom; c++) begin[c] = bucket0[c + 1];
+    free(cnt); free(bucket0);
+    return run;
+}
+
 /* ---------------------------------------------------------------- filter
  * dunks/filter.py.  Input in FILE order. */
 typedef struct {

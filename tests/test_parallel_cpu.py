@@ -203,3 +203,48 @@ def test_wire_scatter_gives_every_rank_its_tile_slice(tmp_path, world):
     assert len(got_rows) == len(whole["rows"]) == nt * 32
     assert got_rows == whole["rows"]
     assert got_mp == whole["mp"]
+
+
+def test_parallel_select_sort_counts_like_the_lexsort_path(tmp_path):
+    """oracle.select_sort (C, OpenMP: the bench's CPU arm uses it so that the coordinate sort standing in for the indexed BAM
+    runs on all threads) gives count_arrays the same rows and bedgraph entries as numpy's lexsort of the kept reads."""
+    from oracle import oracle
+    from slamdunk_b200.io import bam as bamio
+    simdata.make_case(str(tmp_path), seed=31, n_reads=4000, name="c", complexity=1.5)
+    ref, bed, bam = (os.path.join(str(tmp_path), "c" + e) for e in (".fa", ".bed", ".bam"))
+    text, refs, records = bamio.read_bam(bam)
+    fasta = bamio.read_fasta(ref)
+    genome = oracle.Genome(list(fasta.keys()), [s.encode() for s in fasta.values()])
+    names = [n for n, _ in refs]
+    rng = np.random.RandomState(1)
+    perm = rng.permutation(len(records))            # mapper order
+    reads = np.zeros(len(records), dtype=oracle.READ_DT)
+    quals, mps = [], []
+    qo = mo = 0
+    for k, i in enumerate(perm):
+        r = records[i]
+        reads[k]["chrom"] = genome.index.get(names[r.ref_id], -1) if r.ref_id >= 0 else -1
+        reads[k]["pos"], reads[k]["end"] = r.pos, r.reference_end
+        reads[k]["l_qual"], reads[k]["flag"], reads[k]["mapq"] = len(r.qual), r.flag, r.mapq
+        reads[k]["qual_off"] = qo
+        quals.append(bytes(r.qual)); qo += len(r.qual)
+        if r.has_tag("MP"):
+            t = r.get_tag("MP").encode()
+            reads[k]["has_mp"], reads[k]["mp_off"], reads[k]["mp_len"] = 1, mo, len(t)
+            mps.append(t); mo += len(t)
+    rows_bed = oracle.read_bed(bed)
+    utrs = np.zeros(len(rows_bed), dtype=oracle.UTR_DT)
+    ids = {}
+    for i, (ch, s, e, _n, st) in enumerate(rows_bed):
+        utrs[i] = (genome.index.get(ch, -1), 1 if ch in names else 0, s, e, 1 if st == "-" else 0, ids.setdefault(ch, len(ids)))
+    keep = (rng.rand(len(reads)) < 0.8).astype(np.uint8)
+    qual_pool, mp_text = np.frombuffer(b"".join(quals), dtype=np.uint8), b"".join(mps)
+    want_rows, want_bg = oracle.count_arrays(genome, reads[keep.astype(bool)], qual_pool, utrs, 27, 1, None, mp_text=mp_text)
+    for threads in (1, 4):
+        srt, begin, span = oracle.select_sort(reads, keep, len(genome.names), threads=threads)
+        assert len(srt) == int(keep.sum()) and begin[-1] == len(srt)
+        key = srt["chrom"].astype(np.int64) * (1 << 32) + srt["pos"]
+        assert np.all(np.diff(key) >= 0)
+        rows, bg = oracle.count_arrays(genome, srt, qual_pool, utrs, 27, 1, None, mp_text=mp_text, threads=threads, presorted=(begin, span))
+        assert rows.tobytes() == want_rows.tobytes() and bg.tobytes() == want_bg.tobytes()
+    assert want_rows["read_count"].sum() > 1000
