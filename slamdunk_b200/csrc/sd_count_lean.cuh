@@ -131,25 +131,27 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_LEAN_MIN_CTAS(W)) sd_lean_k
     };
 
     // the three record words the scan needs (pos, chromosome | MAPQ | flags, XI), loaded one tile ahead like the description
-    auto fetch_rec = [&](uint32_t tile, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
-        w0 = w1 = w2 = 0u;
+    const bool want_w4 = VERIFY || A.filter_max_nm > -1;   // NM | MP entries << 16: only the NM filter and the MP cross-check look at it
+    auto fetch_rec = [&](uint32_t tile, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w4) {
+        w0 = w1 = w2 = w4 = 0u;
         if (tile != 0xFFFFFFFFu) {
             const uint32_t *rw = reinterpret_cast<const uint32_t *>(A.rec + (size_t)tile * SD_TILE_READS + lane);
             w0 = __ldcs(rw);
             w1 = __ldcs(rw + 1);
             w2 = __ldcs(rw + 2);
+            if (want_w4) w4 = __ldcs(rw + 4);
         }
     };
     uint32_t tile = claim();
     unsigned long long desc = fetch_desc(tile);
-    uint32_t r_pos, r_rmf, r_xi;
-    fetch_rec(tile, r_pos, r_rmf, r_xi);
+    uint32_t r_pos, r_rmf, r_xi, r_w4;
+    fetch_rec(tile, r_pos, r_rmf, r_xi, r_w4);
     while (tile != 0xFFFFFFFFu) {   // claims are monotonic: nothing behind the first empty one
         // the next tile: claimed now, its description and records on the way into registers while this tile is counted
         const uint32_t next = claim();
         const unsigned long long next_desc = fetch_desc(next);
-        uint32_t n_pos, n_rmf, n_xi;
-        fetch_rec(next, n_pos, n_rmf, n_xi);
+        uint32_t n_pos, n_rmf, n_xi, n_w4;
+        fetch_rec(next, n_pos, n_rmf, n_xi, n_w4);
         const uint32_t lseq = __shfl_sync(0xFFFFFFFFu, (uint32_t)desc, 0);
         if (lseq == 0u) {
             if (lane == 0) A.leftover[atomicAdd(A.n_leftover, 1u)] = tile;
@@ -164,8 +166,24 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_LEAN_MIN_CTAS(W)) sd_lean_k
             const int32_t pos = (int32_t)r_pos;
             const uint32_t rmf = r_rmf;
             const float xi = __uint_as_float(r_xi);
-            uint32_t nm_nmp = 0u;   // NM | MP entries << 16: only the NM filter and the MP cross-check look at it
-            if (VERIFY || A.filter_max_nm > -1) nm_nmp = __ldcs(reinterpret_cast<const uint32_t *>(A.rec + (size_t)tile * SD_TILE_READS + lane) + 4);
+            const uint32_t nm_nmp = r_w4;
+            // VERIFY: where this read's MP entries sit in the tile's block (exclusive scan of the entry counts), and its first two
+            // entries on their way now, next to the SEQ / quality loads -- most reads list at most two conversions
+            const uint32_t nmp = nm_nmp >> 16;
+            const uint32_t *mp = nullptr;
+            uint32_t en0 = 0u, en1 = 0u;
+            if (VERIFY) {
+                const unsigned long long mp_off = bcast64(desc, 4);
+                uint32_t ms = nmp;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ms, d);
+                    if (lane >= (uint32_t)d) ms += t;
+                }
+                mp = reinterpret_cast<const uint32_t *>(A.mp + mp_off) + (ms - nmp);
+                if (nmp > 0u) en0 = __ldcs(mp);
+                if (nmp > 1u) en1 = __ldcs(mp + 1);
+            }
             uint2 xs[W];
             uint32_t xq[W][QB];
             {
@@ -238,19 +256,10 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_LEAN_MIN_CTAS(W)) sd_lean_k
             }
             if (VERIFY) {
                 // the read's T>C / A>G candidates against its MP entries (reference offset and read index; plain match: equal)
-                const unsigned long long mp_off = bcast64(desc, 4);
-                const uint32_t nmp = nm_nmp >> 16;
-                uint32_t ms = nmp;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ms, d);
-                    if (lane >= (uint32_t)d) ms += t;
-                }
                 bool bad = false;
                 if (live && (flags & SD_F_HAS_MP)) {
-                    const uint32_t *mp = reinterpret_cast<const uint32_t *>(A.mp + mp_off) + (ms - nmp);
                     for (uint32_t i = 0; i < nmp; i++) {
-                        const uint32_t en = __ldcs(mp + i);
+                        const uint32_t en = i == 0u ? en0 : (i == 1u ? en1 : __ldcs(mp + i));
                         const uint32_t rp = en & 0xFFFFu, o = en >> 16;
                         bool found = false;
 #pragma unroll
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(SD_CTA_THREADS, SD_LEAN_MIN_CTAS(W)) sd_lean_k
         }
         tile = next;
         desc = next_desc;
-        r_pos = n_pos; r_rmf = n_rmf; r_xi = n_xi;
+        r_pos = n_pos; r_rmf = n_rmf; r_xi = n_xi; r_w4 = n_w4;
     }
 
     flush_counts();

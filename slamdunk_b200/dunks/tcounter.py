@@ -403,7 +403,7 @@ def _chromosome_rows(genome, hbatch):
     """Annotation rows 2c (+) and 2c + 1 (-) for FASTA chromosome c, [1, chrLen + 1) as the reference's whole-chromosome
     iterator sees it (readsInChromosome, SlamSeqFile.py:447-453)."""
     n_chrom = len(genome.names)
-    bam_names = set(info["ref_names"])
+    bam_names = set(hbatch.ref_names)
     lengths = np.asarray(genome.chrom_len, dtype=np.int64)
     return (np.repeat(np.arange(n_chrom, dtype=np.uint32), 2), np.ones(2 * n_chrom, dtype=np.int64), np.repeat(lengths + 1, 2),
             np.tile(np.array([0, 1], dtype=np.uint8), n_chrom),
