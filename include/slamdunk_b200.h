@@ -41,7 +41,7 @@ extern "C" {
 #define SD_ERR_LIMIT (-6)
 #define SD_ERR_NOMEM (-7)
 
-#define SD_ABI_VERSION 8
+#define SD_ABI_VERSION 9
 
 typedef struct sd_ctx sd_ctx;
 
@@ -140,6 +140,9 @@ typedef struct sd_batch {
                                window and the annotation entries its reads can overlap together with the tile's columns
                                (two more bulk copies per tile) instead of one lookup chain per read. */
     uint32_t spans_epoch;   /* set by sd_tile_spans; descriptors made before a later sd_set_reference / sd_set_utrs are ignored */
+    uint32_t spans_counted; /* 1: the two counts below are valid (sd_tile_spans sets them; 0 = not known, every launch is made) */
+    uint32_t spans_lean_tiles;   /* tiles the lean kernel takes */
+    uint32_t spans_staged_tiles; /* tiles whose reference window and annotation entries fit a stage (the lean ones included) */
 } sd_batch;
 
 /* What the staged count kernels copy for one tile besides its columns, as [begin, end) byte offsets into two
@@ -261,9 +264,10 @@ int sd_bind_outputs(sd_ctx *ctx, int64_t *d_counters, int32_t *d_pos_cov, int32_
  */
 int sd_count(sd_ctx *ctx, const sd_batch *d_batch, const sd_params *params);
 /* Fill d_spans (device, n_tiles * sizeof(sd_tile_span)) for a device-resident batch and attach it (d_batch->spans,
- * d_batch->spans_epoch).  Call after sd_set_reference and sd_set_utrs; part of building the batch, like its tile table.
+ * d_batch->spans_epoch, and how many tiles each kind of kernel will take: sd_count skips a launch that would take next to
+ * none -- unsorted input goes straight to the per-read kernel).  Call after sd_set_reference and sd_set_utrs; part of building the batch, like its tile table.
  * A tile whose CIGAR block is empty (tiles[t + 1].cig_off == tiles[t].cig_off) is read as: every record with one CIGAR op
- * is a single M block of l_seq bases -- plain-match tiles need not carry the column.  Asynchronous. */
+ * is a single M block of l_seq bases -- plain-match tiles need not carry the column.  Synchronous (the two counts are read back). */
 int sd_tile_spans(sd_ctx *ctx, sd_batch *d_batch, void *d_spans);
 /* sd_count that also writes every record's tcCount (after the conversionThreshold rule, saturated at
  * 255; 0 for records that were not counted) to d_read_tc[n_tiles * tile_reads] -- the per-read

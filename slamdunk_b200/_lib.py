@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SLAMDUNK_B200_LIB") or os.path.join(HERE, "libslamdunk_b200.so")   # env: kernel experiments
 
 SD_OK = 0
-SD_ABI_VERSION = 8   # 8 = 64-byte sd_tile_span (lean-kernel tile description); 7 = SNP alleles in the generator (sd_synth_tables); 6 = sd_hbatch.n_mapped_no_xi/nm, wire form; include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual; 4 = BAI writer; 5 = sd_read_stats
+SD_ABI_VERSION = 9   # 9 = tile-class counts in sd_batch; 8 = 64-byte sd_tile_span (lean-kernel tile description); 7 = SNP alleles in the generator (sd_synth_tables); 6 = sd_hbatch.n_mapped_no_xi/nm, wire form; include/slamdunk_b200.h: 2 = group-major plane-sliced SEQ column, sd_params.flags, sd_batch.max_span; 3 = coded qual; 4 = BAI writer; 5 = sd_read_stats
 SD_F_REVERSE, SD_F_UNMAPPED, SD_F_SECONDARY, SD_F_SUPPLEMENTARY = 0x01, 0x02, 0x04, 0x08
 SD_F_HAS_MP, SD_F_SKIP, SD_F_NEWNAME, SD_F_PAD = 0x10, 0x20, 0x40, 0x80
 SD_REF_NONE = 0xFFFF
@@ -47,7 +47,8 @@ class Batch(ctypes.Structure):
                 ("max_lseq", ctypes.c_uint32), ("max_tile_seq", ctypes.c_uint32), ("max_tile_qual", ctypes.c_uint32),
                 ("max_tile_cig", ctypes.c_uint32), ("max_tile_mp", ctypes.c_uint32), ("max_span", ctypes.c_uint32), ("qual_bits", ctypes.c_uint32),
                 ("qual_dict", ctypes.c_uint8 * 16), ("seq_bits", ctypes.c_uint32), ("qual_form", ctypes.c_uint32),
-                ("spans", ctypes.c_void_p), ("spans_epoch", ctypes.c_uint32)]
+                ("spans", ctypes.c_void_p), ("spans_epoch", ctypes.c_uint32), ("spans_counted", ctypes.c_uint32),
+                ("spans_lean_tiles", ctypes.c_uint32), ("spans_staged_tiles", ctypes.c_uint32)]
 
 
 class WireTile(ctypes.Structure):
@@ -206,7 +207,7 @@ def load():
     if missing:
         raise RuntimeError("libslamdunk_b200.so is stale, it lacks %s; rebuild with `python -m slamdunk_b200.build`"
                            % ", ".join(missing))
-    assert ctypes.sizeof(ReadRec) == 20 and ctypes.sizeof(Tile) == 32 and ctypes.sizeof(Batch) == 136
+    assert ctypes.sizeof(ReadRec) == 20 and ctypes.sizeof(Tile) == 32 and ctypes.sizeof(Batch) == 144
     if L.sd_abi_version() != SD_ABI_VERSION:
         raise RuntimeError("libslamdunk_b200.so has ABI version %d, these bindings expect %d; rebuild with `python -m slamdunk_b200.build`"
                            % (L.sd_abi_version(), SD_ABI_VERSION))

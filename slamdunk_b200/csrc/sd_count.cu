@@ -126,6 +126,7 @@ struct SpanArgs {
     sd_tile_span *out;
     uint64_t n_refm;
     uint32_t W, cap_win, cap_ent;   // the count kernels' window words and stage room for this batch (span_caps)
+    unsigned int *counts;           // optional: [0] tiles the lean kernel takes, [1] tiles that fit a stage
 };
 
 __global__ void sd_tile_spans_kernel(const SpanArgs A) {
@@ -200,7 +201,13 @@ __global__ void sd_tile_spans_kernel(const SpanArgs A) {
             out.g0 = A.chrom_off[ref0];
         }
     }
-    if (lane == 0) A.out[tile] = out;
+    if (lane == 0) {
+        A.out[tile] = out;
+        if (A.counts) {
+            if (out.lean) atomicAdd(&A.counts[0], 1u);
+            if (gend != 0u && out.win_end - out.win_begin + 16ull * A.W <= A.cap_win && out.ent_end - out.ent_begin <= A.cap_ent) atomicAdd(&A.counts[1], 1u);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -584,6 +591,8 @@ int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, cudaStre
     static int spans_env = -1;
     if (spans_env < 0) { const char *e = getenv("SD_SPANS"); spans_env = e ? atoi(e) : 1; }
     A.spans = (b->spans && b->spans_epoch == ctx->ann_epoch && spans_env) ? b->spans : nullptr;
+    A.hint_lean = (A.spans && b->spans_counted) ? b->spans_lean_tiles : 0xFFFFFFFFu;       // 0xFFFFFFFF: not known
+    A.hint_staged = (A.spans && b->spans_counted) ? b->spans_staged_tiles : 0xFFFFFFFFu;
     A.refm = ctx->refm;
     A.ment = ctx->d_ment;
     for (int s = 0; s < 2; s++) {
@@ -655,9 +664,10 @@ int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, cudaStre
 #undef SD_DISPATCH_W
 }
 
-int tile_spans_on(sd_ctx *ctx, cudaStream_t stream, const sd_batch *b, void *d_spans) {
+int tile_spans_on(sd_ctx *ctx, cudaStream_t stream, const sd_batch *b, void *d_spans, unsigned int *d_counts) {
     if (b->n_tiles == 0) return SD_OK;
     SpanArgs S;
+    S.counts = d_counts;
     S.rec = b->rec; S.cigar = b->cigar; S.tiles = b->tiles; S.n_tiles = b->n_tiles;
     S.chrom_off = ctx->d_chrom_off; S.chrom_len = ctx->d_chrom_len; S.n_chrom = ctx->n_chrom;
     S.ment = ctx->d_ment; S.bin_first_m = ctx->d_bin_first_m; S.n_ment = ctx->n_ment;
@@ -677,10 +687,20 @@ extern "C" int sd_tile_spans(sd_ctx *ctx, sd_batch *d_batch, void *d_spans) {
     if (!ctx->refx[0] || !ctx->d_ment) return sd_fail(ctx, SD_ERR_STATE, "sd_tile_spans before sd_set_reference / sd_set_utrs");
     if (d_batch->tile_reads != 32) return sd_fail(ctx, SD_ERR_ARG, "tile_reads must be 32");
     SD_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int rc = tile_spans_on(ctx, ctx->stream, d_batch, d_spans);
+    // how many tiles each kind of kernel will take: two counters behind the queue heads of the count launches
+    if (!ctx->d_tile_counter) SD_CUDA(ctx, cudaMalloc(&ctx->d_tile_counter, 8 * sizeof(unsigned int)));
+    unsigned int *d_counts = ctx->d_tile_counter + 6;
+    SD_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned int), ctx->stream));
+    const int rc = tile_spans_on(ctx, ctx->stream, d_batch, d_spans, d_counts);
     if (rc) return rc;
+    unsigned int h[2] = {0, 0};
+    SD_CUDA(ctx, cudaMemcpyAsync(h, d_counts, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     d_batch->spans = d_spans;
     d_batch->spans_epoch = ctx->ann_epoch;
+    d_batch->spans_counted = 1;
+    d_batch->spans_lean_tiles = h[0];
+    d_batch->spans_staged_tiles = h[1];
     return SD_OK;
 }
 
@@ -863,7 +883,7 @@ extern "C" int sd_count_host(sd_ctx *ctx, const sd_batch *hb, const sd_params *p
         if (ctx->d_ment) {   // span descriptors of the chunk's tiles (the staged count kernel)
             void *d_spans = d + o;
             o = up256(o + (size_t)nt * sizeof(sd_tile_span));
-            if ((rc = tile_spans_on(ctx, ctx->stream, &db, d_spans))) return rc;
+            if ((rc = tile_spans_on(ctx, ctx->stream, &db, d_spans, nullptr))) return rc;
             db.spans = d_spans;
             db.spans_epoch = ctx->ann_epoch;
         }

@@ -103,7 +103,8 @@ struct CountArgs {
     uint32_t n_stages;
     uint32_t qual_prefetch;   // L2-prefetch each tile's qual bytes when the tile is issued
     // per-tile span descriptors (sd_batch.spans) and what they index: the strand-merged reference and annotation tables
-    const void *spans;        // sd_tile_span per tile (four 64-bit byte offsets) or null
+    const void *spans;        // sd_tile_span per tile or null
+    uint32_t hint_lean, hint_staged;   // tiles the lean kernel will take / that fit a stage (sd_batch.spans_*), 0xFFFFFFFF: not known
     const uint4 *refm;        // per 32 bp {isT, T>C SNPs, isA, A>G SNPs}
     const uint4 *ment;        // two uint4 per entry, see StageView
     // reference
@@ -1386,7 +1387,11 @@ int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
         static int lean_env = -1;
         if (lean_env < 0) { const char *e = getenv("SD_LEAN"); lean_env = e ? atoi(e) : 1; }
         uint32_t *list1 = A.leftover, *list2 = A.leftover + A.n_tiles;
-        if constexpr (SB == 2 && QB > 0) if (lean_env && !A.force_slow && (A.mismatch_source == SD_MISMATCH_CIGAR || A.mismatch_source == SD_MISMATCH_VERIFY)) {
+        // a launch that would take next to nothing (unsorted input: no tile fits a stage, none is lean) is not made; its tiles go on
+        const uint32_t few = A.n_tiles / 64u;
+        const bool skip_lean = A.hint_lean != 0xFFFFFFFFu && A.hint_lean <= few;
+        const bool skip_staged = A.hint_staged != 0xFFFFFFFFu && A.hint_staged <= few && (skip_lean || A.hint_lean >= A.hint_staged);
+        if constexpr (SB == 2 && QB > 0) if (lean_env && !skip_lean && !A.force_slow && (A.mismatch_source == SD_MISMATCH_CIGAR || A.mismatch_source == SD_MISMATCH_VERIFY)) {
             if (A.mismatch_source == SD_MISMATCH_CIGAR) rc = launch_lean<W, (QB > 0 ? QB : 2), false>(ctx, A, stream, list1, words + 3);
             else rc = launch_lean<W, (QB > 0 ? QB : 2), true>(ctx, A, stream, list1, words + 3);
             if (rc != SD_OK) return rc;
@@ -1394,13 +1399,15 @@ int launch_count(sd_ctx *ctx, CountArgs &A, cudaStream_t stream, bool timed) {
             A.n_list = words + 3;
             if (timed) { SD_CUDA(ctx, cudaEventRecord(ctx->ev_split[0], stream)); marks = 2; }
         }
-        A.tile_counter = words + 1;
-        A.leftover = list2;
-        A.n_leftover = words + 4;
-        if ((rc = launch_one<W, SB, QB, true>(ctx, A, stream)) != SD_OK) return rc;
+        if (!skip_staged) {
+            A.tile_counter = words + 1;
+            A.leftover = list2;
+            A.n_leftover = words + 4;
+            if ((rc = launch_one<W, SB, QB, true>(ctx, A, stream)) != SD_OK) return rc;
+            A.tile_list = list2;
+            A.n_list = words + 4;
+        }
         if (timed) { SD_CUDA(ctx, cudaEventRecord(ctx->ev_split[1], stream)); if (!marks) marks = 1; }
-        A.tile_list = list2;
-        A.n_list = words + 4;
         A.tile_counter = words + 2;
         A.spans = nullptr;
         A.cap_win = A.cap_ent = 0;

@@ -12,7 +12,7 @@
 #include "sd_internal.h"
 
 int count_on_stream(sd_ctx *ctx, const sd_batch *b, const sd_params *p, cudaStream_t stream, uint8_t *read_tc, bool timed);   // sd_count.cu
-int tile_spans_on(sd_ctx *ctx, cudaStream_t stream, const sd_batch *b, void *d_spans);                                         // sd_count.cu
+int tile_spans_on(sd_ctx *ctx, cudaStream_t stream, const sd_batch *b, void *d_spans, unsigned int *d_counts);                                         // sd_count.cu
 
 namespace {
 
@@ -656,7 +656,7 @@ extern "C" int sd_count_wire(sd_ctx *ctx, const sd_wire *w, const sd_params *par
         memcpy(db.qual_dict, w->qual_dict, 16);
         int rc;
         if (ctx->d_ment) {
-            if ((rc = tile_spans_on(ctx, ctx->stream, &db, d + L.spans))) return rc;
+            if ((rc = tile_spans_on(ctx, ctx->stream, &db, d + L.spans, nullptr))) return rc;
             db.spans = d + L.spans;
             db.spans_epoch = ctx->ann_epoch;
         }

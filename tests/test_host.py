@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "library does not export " + name
     assert declared == set(L.PROTOTYPES.keys())
-    assert lib.sd_abi_version() == L.SD_ABI_VERSION == 8
+    assert lib.sd_abi_version() == L.SD_ABI_VERSION == 9
 
 
 def _decode(path, fasta_names, want_mp=True, tile_reads=32, threads=3):
