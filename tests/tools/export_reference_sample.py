@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """GPU box: write a cfg2-shaped sample as the FILES the reference reads (FASTA, BED, filtered sorted BAM) into
 gpurun_out/refsample/, together with what computeTconversions of this package makes of them, so that the unmodified
-reference can be timed on the same files in the build container (tools/reference_cpu_baseline.py; /root/reference
+reference can be timed on the same files in the build container (tests/tools/reference_cpu_baseline.py; /root/reference
 does not exist on the GPU box).  The sample is cfg2 scaled 1 : 5 -- 20 Mb genome, 4 000 UTRs of the same length
 distribution, 200 000 reads: the reads per UTR of the 1 M-read prefix SURVEY.md 8(d) names -- to fit the 64 MiB that
 travel back.
-   python tools/export_reference_sample.py [reads] [genome_bp] [utrs]"""
+   python tests/tools/export_reference_sample.py [reads] [genome_bp] [utrs]"""
 import gzip
 import io
 import json
@@ -14,7 +14,7 @@ import shutil
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

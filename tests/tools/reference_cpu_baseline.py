@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """Build container (where /root/reference exists): time the UNMODIFIED reference -- slamdunk.dunks.tcounter.
 computeTconversions imported verbatim, pysam / pybedtools / intervaltree replaced by the I/O-only shims of tests/shims --
-on the cfg2-shaped sample tools/export_reference_sample.py wrote on the GPU box, next to the oracle port on the same
+on the cfg2-shaped sample tests/tools/export_reference_sample.py wrote on the GPU box, next to the oracle port on the same
 files and cores, and compare all outputs byte for byte (reference == port == GPU).  SURVEY.md 8(d) "CPU reference timed
 beside it"; the result is kept in profiles/.
-   python tools/reference_cpu_baseline.py [gpurun_out/refsample] [out.json]"""
+   python tests/tools/reference_cpu_baseline.py [gpurun_out/refsample] [out.json]"""
 import gzip
 import io
 import json
@@ -14,7 +14,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -58,7 +58,7 @@ def main():
     best = min(runs)
     res = {
         "what": "unmodified reference computeTconversions (tcounter.py:125) through tests/shims on the cfg2-shaped sample written by "
-                "tools/export_reference_sample.py on the GPU box; build container, Python %s" % sys.version.split()[0],
+                "tests/tools/export_reference_sample.py on the GPU box; build container, Python %s" % sys.version.split()[0],
         "sample": meta, "host_cpus": oracle.max_threads(),
         "reference_seconds": runs, "reference_reads_per_s_per_core": n / best,
         "reference_parallelism": "one process per BAM (slamdunk.py:516): a single sample runs on 1 core",
