@@ -7,6 +7,11 @@ the reference -- only build the command lines of the external NextGenMap / samto
 binaries and shell out; they are not part of the accelerated path).  `-t` is the number of host
 decode threads: samples are processed one after the other on the GPU instead of one joblib worker
 process per BAM (slamdunk.py:516).  Extra, opt-in: `--device`, `--mismatch-source`.
+
+Several GPUs: `torchrun --nproc-per-node N -m slamdunk_b200 count ...` (one process per GPU).  With at least as many BAMs as
+ranks the SAMPLES are dealt out over the ranks -- the reference's one-worker-per-BAM fan-out (slamdunk.py:516), no collective
+(partitioning B); with fewer BAMs than ranks every BAM is counted by all ranks together (tile slices, one
+all-reduce of the integer outputs, rank 0 writes).  `filter` deals out samples the same way.
 """
 from __future__ import print_function
 
@@ -380,10 +385,38 @@ def build_parser():
     return parser
 
 
+def plan_samples(n_samples, rank, world):
+    """How `count` / `filter` use several ranks -> (mode, sample indices of this rank):
+    "samples": at least one sample per rank -- this rank takes every world-th sample, alone, on its own GPU;
+    "tiles":   fewer samples than ranks -- every rank takes part in every sample (tile slices + all-reduce);
+    "single":  one process."""
+    if world <= 1:
+        return "single", list(range(n_samples))
+    if n_samples >= world:
+        return "samples", list(range(rank, n_samples, world))
+    return "tiles", list(range(n_samples))
+
+
 def run(argv=None):
     parser = build_parser()
     args = parser.parse_args(argv)
     command = args.command
+    rank, world, local_rank = 0, 1, 0
+    mode = "single"
+    if command in ("count", "filter"):
+        from . import parallel
+        rank, world, local_rank = parallel.env()
+        mode, mine = plan_samples(len(args.bam), rank, world)
+        if world > 1:
+            args.device = local_rank
+            if mode == "tiles" and command == "count":
+                parallel.init()                      # computeTconversions sees the process group and slices the tiles
+            elif mode == "tiles":
+                mine = mine if rank == 0 else []     # filter has no multi-rank form: rank 0 does the few samples
+        args.bam = [args.bam[i] for i in mine]
+        if world > 1 and rank != 0:
+            global mainOutput
+            mainOutput = open(os.devnull, "w")       # one voice on stderr
     if command in ("count", "filter", "all"):
         from .dunks import filter as gfilter
         from .dunks import tcounter

@@ -149,3 +149,21 @@ def test_summary_and_merge(tmp_path):
     with pytest.raises(SystemExit) as e:
         alleyoop.run(["dedup", "-o", "x", "y.bam"])
     assert "not provided" in str(e.value)
+
+
+def test_samples_are_dealt_out_over_ranks_or_tiles_are():
+    """`torchrun -m slamdunk_b200 count`: at least one BAM per rank -> every rank takes its own samples (the reference's
+    one-worker-per-BAM fan-out, no collective); fewer BAMs than ranks -> all ranks share every BAM (tile slices)."""
+    from slamdunk_b200.cli import plan_samples
+    assert plan_samples(3, 0, 1) == ("single", [0, 1, 2])
+    for world in (2, 4, 8):
+        seen = []
+        for r in range(world):
+            mode, mine = plan_samples(12, r, world)
+            assert mode == "samples"
+            seen += mine
+        assert sorted(seen) == list(range(12))                 # every sample exactly once
+        sizes = [len(plan_samples(12, r, world)[1]) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+    for r in range(8):
+        assert plan_samples(3, r, 8) == ("tiles", [0, 1, 2])
