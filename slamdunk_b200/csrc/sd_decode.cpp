@@ -868,7 +868,6 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         memset(pc, 0, (size_t)(((uint8_t *)cigc + tiles[t + 1].cig_off) - pc));
         if (pm) memset(pm, 0, (size_t)(((uint8_t *)mpc + tiles[t + 1].mp_off) - pm));
     });
-    const double t2 = now_s();
     lap("pass B");
 
     // ---- optional: the wire form of the same batch (sd_wire, include/slamdunk_b200.h) -- every record field in its own column,
@@ -1085,7 +1084,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     hb->name_hash = name_hash;
     hb->order = order;
     hb->seconds_inflate = t1 - t0;
-    hb->seconds_decode = t2 - t1;
+    hb->seconds_decode = now_s() - t1;      // record decode incl. the wire form when it was asked for
     hb->compressed_bytes = compressed;
     hb->inflated_bytes = raw.size();
     hb->n_mapped_no_xi = no_xi.load();
