@@ -553,7 +553,7 @@ def test_utrrates_percentages_and_checkstep_host_logic(tmp_path):
 from wireutil import unpack_wire as _unpack_wire      # noqa: E402
 
 
-def _uniform_bam(path, n_reads, L=40):
+def _uniform_bam(path, n_reads, L=40, quals=(20, 30, 37)):
     """plain reads of one length on two chromosomes, positions up to 200 kb apart inside one tile, three distinct qualities:
     tiles without l_seq / CIGAR, with 32-bit positions, with per-read chromosomes"""
     from slamdunk_b200.io import bam as bamio
@@ -565,7 +565,7 @@ def _uniform_bam(path, n_reads, L=40):
         pos = int(rng.randint(0, 1000)) + (200000 if (i // 8) % 5 == 4 and i % 2 else 0)
         seq = "".join(rng.choice(list("ACGTN"), p=[0.24, 0.24, 0.24, 0.24, 0.04]) for _ in range(L))
         recs.append(bamio.BamRecord("u%04d" % i, 16 if i % 3 == 0 else 0, ref, pos, 60 if i % 7 else 0, [(0, L)], seq,
-                                    [int(rng.choice([20, 30, 37])) for _ in range(L)],
+                                    [int(rng.choice(list(quals))) for _ in range(L)],
                                     [("NM", "i", i % 4), ("XI", "f", 1.0 - (i % 4) / L), ("MP", "Z", "16:3:3" if i % 3 else "2:5:5")]))
     recs = bamio.sort_records(recs)
     hdr = "@HD\tVN:1.0\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % r for r in refs)
@@ -573,7 +573,8 @@ def _uniform_bam(path, n_reads, L=40):
     return [r[0] for r in refs]
 
 
-@pytest.mark.parametrize("seed,n_reads,group,complexity", [(5, 700, True, 2.0), (6, 333, False, 1.0), (7, 64, True, 0.0), (0, 250, True, -1.0)])
+@pytest.mark.parametrize("seed,n_reads,group,complexity", [(5, 700, True, 2.0), (6, 333, False, 1.0), (7, 64, True, 0.0), (0, 250, True, -1.0),
+                                                           (0, 130, True, -2.0)])
 def test_decoder_wire_form_holds_the_same_records_as_the_batch(tmp_path, seed, n_reads, group, complexity):
     """SD_DECODE_WIRE: the packed form sd_count_wire sends over PCIe, written by the decoder straight from the BAM records, read
     back with plain numpy and compared field by field with the columnar batch of the same call (and with the Python codec's
@@ -583,7 +584,8 @@ def test_decoder_wire_form_holds_the_same_records_as_the_batch(tmp_path, seed, n
     from slamdunk_b200.io import bam as bamio
     if complexity < 0:
         bam_path = str(tmp_path / "uniform.bam")
-        names = _uniform_bam(bam_path, n_reads)
+        names = _uniform_bam(bam_path, n_reads, L=40 if complexity == -1.0 else 37,      # 37: rows end inside a byte of either column
+                             quals=(20, 30, 37) if complexity == -1.0 else (2, 8, 11, 15, 20, 22, 25, 27, 30, 33, 37))
     else:
         c = simdata.make_case(str(tmp_path), seed=seed, n_reads=n_reads, complexity=complexity)
         names, bam_path = list(c.genome.keys()), c.bam
@@ -618,7 +620,7 @@ def test_decoder_wire_form_holds_the_same_records_as_the_batch(tmp_path, seed, n
             co += ncig
             qo += lseq
     if complexity < 0:      # plain-match tiles of one read length carry neither l_seq nor CIGAR
-        assert n_shape == 0 and w["qual_bits"] == 2 and len(w["xi_dict"]) <= 5
+        assert n_shape == 0 and w["qual_bits"] == (2 if complexity == -1.0 else 4) and len(w["xi_dict"]) <= 5
         assert any(int(x) & 1 for x in T["flags"][:-1]) and any(int(x) & 2 for x in T["flags"][:-1])      # 32-bit positions, per-read chromosomes
     else:
         assert n_shape > 0
