@@ -246,6 +246,7 @@ class Bench(object):
             if rows is None:
                 continue
             db = self.code(rows)
+            self.eng.attach_spans(db)     # the span table is part of a device batch, like its tile table: made here, not in the first step
             if len(specs) == 1 and not self.args.no_e2e:
                 keep_rows = rows          # one batch: the e2e leg packs its wire form from these rows
             elif db is not rows:
