@@ -477,13 +477,14 @@ int sd_rewrite_bam_indexed(const char *in_path, const char *out_path, const char
  * sd_write_bedgraphs: the two per-position conversion bedgraphs (tcounter.py:277-285, 315-326) from host copies of
  * the per-position arrays.  Per BED row: chromosome text, first in-chromosome position max(0, start), strand,
  * whether the row had reads, its offset / length in the position arrays (sd_utr_layout) and the linear genome
- * coordinate of its first position; isx_plus / isx_minus: host bit-planes "base is T" / "base is A". */
+ * coordinate of its first position; isx_plus / isx_minus: host bit-planes "base is T" / "base is A".  The rows are
+ * formatted by `threads` host threads (0 = all cores) and written in BED order. */
 int sd_format_repr(double x, char *buf);
 int sd_write_bedgraphs(const char *path_plus, const char *path_minus, uint32_t n_utr, const char *const *row_chrom,
                        const int64_t *row_first_pos, const uint8_t *row_strand, const uint8_t *row_has_reads,
                        const uint64_t *row_pos_off, const uint32_t *row_pos_len, const uint64_t *row_gstart,
                        const uint32_t *isx_plus, const uint32_t *isx_minus, const int32_t *pos_cov,
-                       const int32_t *pos_tc, uint64_t n_positions);
+                       const int32_t *pos_tc, uint64_t n_positions, int threads);
 
 /* ------------------------------------------------------------------ genome-wide per-position tracks
  * `alleyoop positional-tracks` (dunks/tcounter.py:332-487 genomewideConversionRates).  The per-position arrays come from

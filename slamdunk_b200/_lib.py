@@ -171,7 +171,7 @@ PROTOTYPES = {
     "sd_hgenome_free": (None, [ctypes.POINTER(HGenome)]),
     "sd_format_repr": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p]),
     "sd_write_bedgraphs": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p), _VP, _VP,
-                                          _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_uint64]),
+                                          _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_uint64, ctypes.c_int]),
     "sd_track_runs": (ctypes.c_int, [_VP, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, _VP, _VP, _VP, ctypes.c_uint64, c_u64p]),
     "sd_write_track": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint64, _VP, _VP, _VP]),
     "sd_read_stats": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(StatsArgs)]),

@@ -7,7 +7,12 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "slamdunk_b200.h"
@@ -67,70 +72,148 @@ extern "C" int sd_format_repr(double x, char *buf) {
 }
 
 namespace {
-struct Out {
+struct Fd {
     FILE *fh;
-    std::vector<char> buf;
-    explicit Out(const char *path) : fh(fopen(path, "w")) { buf.reserve(1 << 20); }
-    void flush() {
-        if (fh && !buf.empty()) fwrite(buf.data(), 1, buf.size(), fh);
-        buf.clear();
+    explicit Fd(const char *path) : fh(fopen(path, "w")) {}
+    bool put(const std::string &s) { return s.empty() || fwrite(s.data(), 1, s.size(), fh) == s.size(); }
+    int close() {
+        const int rc = fh ? fclose(fh) : 0;
+        fh = nullptr;
+        return rc;
     }
-    void put(const char *s, size_t n) {
-        buf.insert(buf.end(), s, s + n);
-        if (buf.size() > (1 << 20) - 256) flush();
-    }
-    ~Out() {
-        flush();
+    ~Fd() {
         if (fh) fclose(fh);
     }
 };
-int put_int(char *o, long long v) { return sprintf(o, "%lld", v); }
+
+inline char *put_int(char *o, long long v) { return std::to_chars(o, o + 24, v).ptr; }
 }  // namespace
 
 // One line "chrom pos pos+1 rate" per covered T (A on '-') position of every BED row that had reads, in the
-// reference's dict order: BED order, ascending position, a position keeps the place of its first insertion.
+// reference's dict order: BED order, ascending position, a position keeps the place of its first insertion
+// (the row that owns it = the first row in BED order that prints it; only rows that share positions -- overlapping
+// same-strand UTRs -- need that table).  Rows are cut into chunks, `threads` workers (0 = all cores) format them and every
+// chunk is appended to the files in its turn, so the text held in memory is two buffers per worker.
 extern "C" int sd_write_bedgraphs(const char *path_plus, const char *path_minus, uint32_t n_utr, const char *const *row_chrom,
                                   const int64_t *row_first_pos, const uint8_t *row_strand, const uint8_t *row_has_reads,
                                   const uint64_t *row_pos_off, const uint32_t *row_pos_len, const uint64_t *row_gstart,
                                   const uint32_t *isx_plus, const uint32_t *isx_minus, const int32_t *pos_cov,
-                                  const int32_t *pos_tc, uint64_t n_positions) {
+                                  const int32_t *pos_tc, uint64_t n_positions, int threads) {
     if (!path_plus || !path_minus) return SD_ERR_ARG;
-    Out out[2] = {Out(path_plus), Out(path_minus)};
+    Fd out[2] = {Fd(path_plus), Fd(path_minus)};
     if (!out[0].fh || !out[1].fh) return SD_ERR_IO;
-    std::vector<uint8_t> emitted((size_t)n_positions, 0);
-    char line[512], rate[40];
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+
+    auto active = [&](uint32_t i) { return row_has_reads[i] && row_pos_len[i] != 0 && row_pos_off[i] != UINT64_MAX; };
+    // rows that share positions with another row: sort the active rows by offset and look at neighbours
+    std::vector<uint32_t> rows;
     for (uint32_t i = 0; i < n_utr; i++) {
-        if (!row_has_reads[i] || row_pos_len[i] == 0 || row_pos_off[i] == UINT64_MAX) continue;
-        const int s = row_strand[i] ? 1 : 0;
-        const uint32_t *isx = s ? isx_minus : isx_plus;
-        const size_t name_len = strlen(row_chrom[i]);
-        if (name_len > 400) return SD_ERR_LIMIT;
-        for (uint32_t p = 0; p < row_pos_len[i]; p++) {
-            const uint64_t idx = row_pos_off[i] + p;
-            const int32_t cov = pos_cov[idx];
-            if (cov <= 0 || emitted[idx]) continue;
-            const uint64_t g = row_gstart[i] + p;
-            if (!((isx[g >> 5] >> (g & 31)) & 1u)) continue;
-            emitted[idx] = 1;
-            const int32_t tc = pos_tc[idx];
-            int rl;
-            if (tc == 0) { memcpy(rate, "0.0", 4); rl = 3; }
-            else rl = sd_format_repr((double)tc * 100.0 / (double)cov, rate);   // tcounter.py:252
-            char *o = line;
-            memcpy(o, row_chrom[i], name_len);
-            o += name_len;
-            *o++ = ' ';
-            o += put_int(o, row_first_pos[i] + p);
-            *o++ = ' ';
-            o += put_int(o, row_first_pos[i] + p + 1);
-            *o++ = ' ';
-            memcpy(o, rate, (size_t)rl);
-            o += rl;
-            *o++ = '\n';
-            out[s].put(line, (size_t)(o - line));
+        if (!active(i)) continue;
+        if (strlen(row_chrom[i]) > 400) return SD_ERR_LIMIT;
+        if (row_pos_off[i] + row_pos_len[i] > n_positions) return SD_ERR_ARG;
+        rows.push_back(i);
+    }
+    std::vector<uint8_t> shares(n_utr, 0);
+    {
+        std::vector<uint32_t> by_off(rows);
+        std::sort(by_off.begin(), by_off.end(), [&](uint32_t x, uint32_t y) { return row_pos_off[x] < row_pos_off[y]; });
+        uint64_t reach = 0;     // furthest end among the rows before by_off[k], and the row that has it
+        uint32_t reach_row = 0;
+        for (size_t k = 0; k < by_off.size(); k++) {
+            const uint32_t i = by_off[k];
+            const uint64_t end = row_pos_off[i] + row_pos_len[i];
+            if (k && row_pos_off[i] < reach) shares[i] = shares[reach_row] = 1;
+            if (!k || end > reach) {
+                reach = end;
+                reach_row = i;
+            }
         }
     }
-    return SD_OK;
+    bool any_shared = false;
+    for (uint32_t i : rows) any_shared |= shares[i] != 0;
+
+    auto prints = [&](uint32_t i, uint32_t p) {     // tcounter.py:277-285: covered, and the reference base is T ('+') / A ('-')
+        const uint64_t idx = row_pos_off[i] + p;
+        if (pos_cov[idx] <= 0) return false;
+        const uint64_t g = row_gstart[i] + p;
+        return (((row_strand[i] ? isx_minus : isx_plus)[g >> 5] >> (g & 31)) & 1u) != 0;
+    };
+    // owner[idx] = first row in BED order that prints position idx (only filled under rows that share positions)
+    std::vector<uint32_t> owner;
+    if (any_shared) {
+        owner.assign((size_t)n_positions, UINT32_MAX);
+        for (uint32_t i : rows) {
+            if (!shares[i]) continue;
+            for (uint32_t p = 0; p < row_pos_len[i]; p++)
+                if (prints(i, p) && owner[row_pos_off[i] + p] == UINT32_MAX) owner[row_pos_off[i] + p] = i;
+        }
+    }
+
+    // chunks of consecutive rows holding ~128k positions each, claimed in order; a worker formats its chunk into its own
+    // two buffers (reused from chunk to chunk) and appends them to the files when every earlier chunk has been written
+    std::vector<uint32_t> cut(1, 0);
+    {
+        uint64_t acc = 0;
+        for (uint32_t k = 0; k < rows.size(); k++) {
+            acc += row_pos_len[rows[k]];
+            if (acc >= (128u << 10) || k + 1 == rows.size()) {
+                cut.push_back(k + 1);
+                acc = 0;
+            }
+        }
+    }
+    const size_t n_chunks = cut.size() - 1;
+    std::atomic<size_t> next(0);
+    std::mutex turn_mutex;              // guards `written` (chunks appended to the files so far) and `failed`
+    std::condition_variable turn_cv;
+    size_t written = 0;
+    bool failed = false;
+    auto work = [&]() {
+        std::string text[2];
+        char line[512], rate[40];
+        for (size_t c; (c = next.fetch_add(1, std::memory_order_relaxed)) < n_chunks;) {
+            text[0].clear();
+            text[1].clear();
+            for (uint32_t k = cut[c]; k < cut[c + 1]; k++) {
+                const uint32_t i = rows[k];
+                std::string &dst = text[row_strand[i] ? 1 : 0];
+                const size_t name_len = strlen(row_chrom[i]);
+                memcpy(line, row_chrom[i], name_len);
+                line[name_len] = ' ';
+                const bool shared = shares[i] != 0;
+                for (uint32_t p = 0; p < row_pos_len[i]; p++) {
+                    if (!prints(i, p)) continue;
+                    const uint64_t idx = row_pos_off[i] + p;
+                    if (shared && owner[idx] != i) continue;
+                    const int32_t cov = pos_cov[idx], tc = pos_tc[idx];
+                    int rl;
+                    if (tc == 0) { memcpy(rate, "0.0", 4); rl = 3; }
+                    else rl = sd_format_repr((double)tc * 100.0 / (double)cov, rate);   // tcounter.py:252
+                    char *o = put_int(line + name_len + 1, row_first_pos[i] + p);
+                    *o++ = ' ';
+                    o = put_int(o, row_first_pos[i] + p + 1);
+                    *o++ = ' ';
+                    memcpy(o, rate, (size_t)rl);
+                    o += rl;
+                    *o++ = '\n';
+                    dst.append(line, (size_t)(o - line));
+                }
+            }
+            std::unique_lock<std::mutex> lk(turn_mutex);
+            turn_cv.wait(lk, [&] { return written == c; });
+            if (!out[0].put(text[0]) || !out[1].put(text[1])) failed = true;
+            written = c + 1;
+            lk.unlock();
+            turn_cv.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    const size_t n_workers = std::min((size_t)threads, (n_chunks + 1) / 2);
+    for (size_t t = 1; t < n_workers; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    const bool closed = (out[0].close() == 0) & (out[1].close() == 0);
+    return (closed && !failed) ? SD_OK : SD_ERR_IO;
 }
 
 

@@ -289,7 +289,7 @@ def _write_bedgraphs(utrs, chrom_idx, genome, res, pos_off, pos_len, counters, o
     tc = np.ascontiguousarray(res["pos_tc"], dtype=np.int32)
     ptr = lambda a: ctypes.c_void_p(a.ctypes.data)    # noqa: E731
     rc = lib.sd_write_bedgraphs(os.fsencode(out_plus), os.fsencode(out_minus), n, names, ptr(first), ptr(strand), ptr(has), ptr(po),
-                                ptr(pl), ptr(gstart), ptr(isx[0]), ptr(isx[1]), ptr(cov), ptr(tc), len(cov))
+                                ptr(pl), ptr(gstart), ptr(isx[0]), ptr(isx[1]), ptr(cov), ptr(tc), len(cov), int(OPTIONS["threads"]))
     if rc != L.SD_OK:
         raise L.NativeError("sd_write_bedgraphs failed with code %d" % rc)
 

@@ -294,6 +294,78 @@ def test_native_float_repr_equals_python_repr():
         assert fmt(x) == repr(x), (x, fmt(x), repr(x))
 
 
+def _bedgraph_text_like_the_reference(names, first, strand, has, po, pl, gstart, isx, cov, tc):
+    """The reference's loop (tcounter.py:277-285, 315-326): per strand one dict position -> rate filled UTR by UTR, printed
+    in insertion order; a position already in the dict keeps its place (and gets the same value again)."""
+    graphs = ({}, {})
+    for i in range(len(names)):
+        if not has[i] or pl[i] == 0:
+            continue
+        s = int(strand[i])
+        for p in range(int(pl[i])):
+            idx = int(po[i]) + p
+            g = int(gstart[i]) + p
+            if cov[idx] > 0 and (int(isx[s][g >> 5]) >> (g & 31)) & 1:
+                rate = 0.0 if tc[idx] == 0 else int(tc[idx]) * 100.0 / int(cov[idx])
+                graphs[s][(names[i], int(first[i]) + p, idx)] = rate
+    return ["".join("%s %d %d %s\n" % (nm.decode(), pos, pos + 1, repr(rate)) for (nm, pos, _idx), rate in graph.items()) for graph in graphs]
+
+
+@pytest.mark.parametrize("threads", [1, 3, 0])
+@pytest.mark.parametrize("layout", ["disjoint", "overlapping"])
+def test_native_bedgraph_writer_keeps_the_reference_order(tmp_path, threads, layout):
+    """sd_write_bedgraphs on several threads == the reference's dict loop, also where same-strand rows share positions
+    (nested, chained and identical UTRs: the first row in BED order prints a shared position)."""
+    import ctypes
+    lib = L.load()
+    rng = np.random.default_rng(11)
+    n, glen = 300, 600000
+    chrom = np.arange(n) % 5
+    strand = (rng.random(n) < 0.4).astype(np.uint8)
+    has = (rng.random(n) < 0.85).astype(np.uint8)
+    if layout == "disjoint":
+        first = np.sort(rng.choice(glen // 1400, size=n, replace=False)).astype(np.int64) * 1400
+        length = rng.integers(1, 1300, size=n)
+        order = rng.permutation(n)                     # BED order is not position order
+        first, length = first[order], length[order]
+        po = np.zeros(n, dtype=np.uint64)
+        po[np.argsort(first)] = np.concatenate([[0], np.cumsum(length[np.argsort(first)] + 1)[:-1]])
+        pl = (length + 1).astype(np.uint32)
+        n_pos = int((length + 1).sum())
+    else:
+        # rows of one strand share one position array indexed by genome position (what merged segments amount to)
+        first = rng.integers(0, 5000, size=n).astype(np.int64)
+        length = rng.integers(1, 1500, size=n)
+        first[9], length[9] = first[4], length[4]      # identical rows (same chromosome: 9 % 5 == 4 % 5)
+        strand[9] = strand[4]
+        has[4] = has[9] = 1
+        po = (first + (chrom * 2 + strand) * 8000).astype(np.uint64)
+        pl = length.astype(np.uint32)
+        n_pos = 80000
+    pl[7] = 0
+    gstart = (first + chrom * 100000 + 64).astype(np.uint64)
+    words = (glen + 500000) // 32 + 8
+    isx = [rng.integers(0, 2 ** 32, size=words, dtype=np.uint32) & rng.integers(0, 2 ** 32, size=words, dtype=np.uint32) for _ in range(2)]
+    cov = rng.integers(-1, 40, size=n_pos).astype(np.int32)
+    tc = np.where(rng.random(n_pos) < 0.3, rng.integers(0, 6, size=n_pos), 0).astype(np.int32)
+    names = [("chr%d" % (c + 1)).encode() for c in chrom]
+    want = _bedgraph_text_like_the_reference(names, first, strand, has, po, pl, gstart, isx, cov, tc)
+    assert len(want[0]) > 1000 and len(want[1]) > 1000
+    cn = (ctypes.c_char_p * n)(*names)
+    ptr = lambda a: ctypes.c_void_p(a.ctypes.data)    # noqa: E731
+    outs = [str(tmp_path / "plus.bedgraph"), str(tmp_path / "minus.bedgraph")]
+    rc = lib.sd_write_bedgraphs(outs[0].encode(), outs[1].encode(), n, cn, ptr(first), ptr(strand), ptr(has), ptr(po), ptr(pl), ptr(gstart),
+                                ptr(isx[0]), ptr(isx[1]), ptr(cov), ptr(tc), n_pos, threads)
+    assert rc == L.SD_OK
+    for path, text in zip(outs, want):
+        assert open(path).read() == text
+    # an offset past the arrays is refused, not read
+    po[0] = n_pos
+    has[0], pl[0] = 1, 5
+    assert lib.sd_write_bedgraphs(outs[0].encode(), outs[1].encode(), n, cn, ptr(first), ptr(strand), ptr(has), ptr(po), ptr(pl), ptr(gstart),
+                                  ptr(isx[0]), ptr(isx[1]), ptr(cov), ptr(tc), n_pos, threads) == -2   # SD_ERR_ARG
+
+
 def _filter_states(records, bam_names, bed_rows, min_identity, nm):
     """What sd_filter reports next to keep[]: survivor class (0 / 1 unique / 2 multimapper) | 4 when a multimapper overlaps a
     UTR (filter.py:137) -- here derived on the host from the decoded records, for the writer test."""
