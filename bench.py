@@ -29,7 +29,9 @@ from pinned HOST buffers (H2D inside the timed region, counters read back), `roo
 algorithmic bytes to the measured HBM copy peak, `cpu_baseline` is the oracle port of the reference's algorithm timed on
 this box's host cores on a bounded sample of the same workload, `parity` says what was compared in this very run: the
 GPU path on the benchmarked column form against the oracle (N = 1), and the sharded run against the unsharded one on a
-10 M-read subsample of the same read stream (N > 1).
+10 M-read subsample of the same read stream (N > 1).  `decode` (N = 1) is the host side of the file path, reported
+separately from the metric: sd_load_fasta / sd_decode_bam on a bounded sample written out as FASTA + BED + BAM, and one
+whole file-level computeTconversions on those files.
 """
 import argparse
 import ctypes
@@ -591,6 +593,59 @@ def oracle_check(bench, sample):
     return parity, cpu
 
 
+def decode_leg(bench, sample):
+    """The host side of the file path, reported next to the metric and not inside it (north star: "the decode cost reported
+    separately"): the first `sample` reads of the workload's read stream written out as the files `slamdunk count` reads --
+    FASTA, BED, a coordinate-sorted BAM with NextGenMap's tags (tests/synth_files.py, a Python writer: that is what bounds
+    the sample) -- then sd_load_fasta, sd_decode_bam into the wire form on all host threads, and one whole file-level
+    computeTconversions (decode + H2D + kernels + the three text files).  Never raises: a failure is reported in the line."""
+    import io
+    import shutil
+    d = tempfile.mkdtemp(prefix="sd_decode_leg_")
+    try:
+        import synth_files
+        from slamdunk_b200.dunks import tcounter
+        from slamdunk_b200.engine import HostBatch, HostGenome
+        wl, a = bench.wl, bench.args
+        spec = cpu_sample_spec(bench, sample)
+        wl.set_time_point(spec["minutes"])
+        db, triples = wl.generate(wl.params(**spec["kw"]), want_triples=True, coordinate_sorted=True, group=False)
+        wl.set_time_point(None)
+        t0 = time.perf_counter()
+        ref, bed, bam, n = synth_files.write_workload_files(d, wl, db, triples)
+        t_write = time.perf_counter() - t0
+        del db, triples
+        out = {"sample": "first %d reads of the %s read stream as FASTA + BED + coordinate-sorted BAM (written by the Python test "
+                         "writer in %.1f s, not timed)" % (n, a.workload, t_write),
+               "reads": int(n), "bam_bytes": os.path.getsize(bam), "fasta_bytes": os.path.getsize(ref),
+               "host_threads": len(os.sched_getaffinity(0))}
+        g = HostGenome(ref)
+        out["fasta_decode_s"] = g.seconds
+        hb = HostBatch(bam, g.names, want_mp=True, group=True, seq2=True, wire=True)      # what computeTconversions asks for
+        out.update(bam_inflate_s=hb.seconds_inflate, bam_records_s=hb.seconds_decode, inflated_bytes=hb.inflated_bytes,
+                   bam_reads_per_s=n / max(1e-9, hb.seconds_inflate + hb.seconds_decode),
+                   bam_compressed_MBps=hb.compressed_bytes / 1e6 / max(1e-9, hb.seconds_inflate + hb.seconds_decode))
+        hb.close()
+        g.close()
+        o = os.path.join(d, "count")
+        runs = []
+        for _ in range(2):      # the second run finds the FASTA decoded (a multi-sample `slamdunk count` decodes it once)
+            t0 = time.perf_counter()
+            tcounter.computeTconversions(ref, bed, None, bam, a.read_len, MIN_QUAL, o + ".tsv", o + "_plus.bedgraph", o + "_minus.bedgraph",
+                                         CONV_THRESHOLD, io.StringIO())
+            runs.append((time.perf_counter() - t0, {k: v for k, v in tcounter.OPTIONS["timings"].items() if k != "stats"}))
+        out["file_level"] = {"what": "computeTconversions(FASTA, BED, BAM) -> tcount TSV + two bedgraphs, mismatch source verify (its default)",
+                             "first_run_s": runs[0][0], "first_run_stages": runs[0][1],
+                             "second_run_s": runs[1][0], "second_run_stages": runs[1][1],
+                             "reads_per_s": n / runs[1][0],
+                             "output_bytes": sum(os.path.getsize(o + e) for e in (".tsv", "_plus.bedgraph", "_minus.bedgraph"))}
+        return out
+    except Exception as e:      # noqa: BLE001 -- the bench line must come out whatever happens in this side measurement
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -620,6 +675,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-shard-check", action="store_true")
+    ap.add_argument("--decode-sample", type=int, default=200_000, dest="decode_sample",
+                    help="reads of the stream written out as files for the `decode` object (host decode + one file-level "
+                         "computeTconversions, reported separately from the metric); 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.reads is None:
@@ -750,6 +808,9 @@ def main():
             parity["sharding"] = msg
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         parity["oracle"], cpu = oracle_check(bench, min(args.reads, args.cpu_sample))
+    decode = None
+    if rank == 0 and world == 1 and args.decode_sample > 0:
+        decode = decode_leg(bench, min(args.reads, args.decode_sample))
     if world > 1:
         barrier()
 
@@ -761,7 +822,7 @@ def main():
             "dtype": "u8/int64 (integer bit ops)",
             "data": "synthetic", "config": workload_config(args),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "parity": parity or None,
+            "parity": parity or None, "decode": decode,
             "reads_per_step": n_total, "reads_rank0": n_mine, "batches_rank0": len(bench.parts),
             "counted_reads_last_step": counted, "filtered_reads_last_step": filtered,
             "slow_path_reads": slow,

@@ -13,6 +13,7 @@ from __future__ import print_function
 import os
 import re
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -230,12 +231,15 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
             rs.close()
         pair_lo = np.searchsorted(pairs["row"], np.arange(n), side="left")
         pair_hi = np.searchsorted(pairs["row"], np.arange(n), side="right")
+    counter_rows = counters[:n].tolist()                     # Python ints once, not one numpy scalar per cell
+    tcontent_rows = tcontent[:n].tolist()
     for i, utr in enumerate(utrs):
-        readCount = int(counters[i, L.SD_C_READS])
-        Tcontent = int(tcontent[i])
+        row = counter_rows[i]
+        readCount = row[L.SD_C_READS]
+        Tcontent = tcontent_rows[i]
         if readCount > 0:                                    # tcounter.py:251
-            coverageOnTs = int(counters[i, L.SD_C_COV_ON_T])
-            conversionsOnTs = int(counters[i, L.SD_C_CONV_ON_T])
+            coverageOnTs = row[L.SD_C_COV_ON_T]
+            conversionsOnTs = row[L.SD_C_CONV_ON_T]
             readsCPM = 0
             if readNumber > 0:                               # tcounter.py:295-297
                 readsCPM = readCount * 1000000.0 / readNumber
@@ -243,12 +247,12 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
             if coverageOnTs > 0:                             # tcounter.py:301-303
                 conversionRate = float(conversionsOnTs) / float(coverageOnTs)
             print(_row(utr, conversionRate, readsCPM, Tcontent, coverageOnTs, conversionsOnTs, readCount,
-                       int(counters[i, L.SD_C_TCREADS]), int(counters[i, L.SD_C_MULTIMAP])), file=fileCSV)
+                       row[L.SD_C_TCREADS], row[L.SD_C_MULTIMAP]), file=fileCSV)
             if mle:                                          # tcounter.py:305: the two lists in the ReadCount / TcReadCount columns
                 p = pairs[pair_lo[i]:pair_hi[i]]
                 print(_row(utr, conversionRate, readsCPM, Tcontent, coverageOnTs, conversionsOnTs,
                            ",".join(str(int(x)) for x in p["t_count"]), ",".join(str(int(x)) for x in p["tc_count"]),
-                           int(counters[i, L.SD_C_MULTIMAP])), file=fileTest)
+                           row[L.SD_C_MULTIMAP]), file=fileTest)
         else:
             print(_row(utr, 0, 0, Tcontent, 0, 0, 0, 0, 0), file=fileCSV)
             if mle:                                          # tcounter.py:168: the default MLE row never gets its Tcontent
@@ -280,8 +284,9 @@ def _write_bedgraphs(utrs, chrom_idx, genome, res, pos_off, pos_len, counters, o
     first = np.array([max(0, u.start) for u in utrs], dtype=np.int64)
     strand = np.array([1 if u.strand == "-" else 0 for u in utrs], dtype=np.uint8)
     has = np.ascontiguousarray(counters[:n, L.SD_C_READS] > 0, dtype=np.uint8) if n else np.zeros(0, np.uint8)
-    gstart = np.array([(int(genome.chrom_off[chrom_idx[i]]) + int(first[i])) if chrom_idx[i] != L.SD_REF_NONE else 0
-                       for i in range(n)], dtype=np.uint64)
+    known = np.asarray(chrom_idx[:n]) != L.SD_REF_NONE
+    off = np.asarray(genome.chrom_off, dtype=np.int64)
+    gstart = np.where(known, off[np.where(known, chrom_idx[:n], 0).astype(np.int64)] + first, 0).astype(np.uint64) if n else np.zeros(0, np.uint64)
     po = np.ascontiguousarray(pos_off, dtype=np.uint64)
     pl = np.ascontiguousarray(pos_len, dtype=np.uint32)
     isx = (np.ascontiguousarray(genome.is_base_mask(0)), np.ascontiguousarray(genome.is_base_mask(1)))
@@ -377,17 +382,31 @@ def genomewideConversionRates(referenceFile, snpsFile, bam, minBaseQual, outputB
         tm["gpu_count_s"] = time.time() - t2
         t3 = time.time()
         n_lines = 0
-        for chromosome in chromosomes:
-            c = genome.index[chromosome]
-            for path, (_suffix, _name, _desc, s, kind) in zip(paths, TRACKS):
-                pos, val, isf = eng.track_runs(2 * c + s, kind, int(coverageCutoff), int(lengths[c]))
-                if len(pos) == 0:
-                    continue
-                rc = lib.sd_write_track(os.fsencode(path), chromosome.encode(), kind, len(pos), pos.ctypes.data, val.ctypes.data,
-                                        isf.ctypes.data)
-                if rc != L.SD_OK:
-                    raise IOError("sd_write_track failed with code %d on %s" % (rc, path))
-                n_lines += len(pos)
+
+        def write_runs(path, chromosome, kind, pos, val, isf):     # the arrays stay referenced until the text is out
+            rc = lib.sd_write_track(os.fsencode(path), chromosome.encode(), kind, len(pos), pos.ctypes.data, val.ctypes.data,
+                                    isf.ctypes.data)
+            if rc != L.SD_OK:
+                raise IOError("sd_write_track failed with code %d on %s" % (rc, path))
+
+        # one writer thread per track file: a file's chromosomes are appended in order, the eight files side by side
+        # and under the next compaction on the device (the native writer runs without the GIL)
+        writers = [ThreadPoolExecutor(max_workers=1) for _ in paths]
+        pending = []
+        try:
+            for chromosome in chromosomes:
+                c = genome.index[chromosome]
+                for k, (path, (_suffix, _name, _desc, s, kind)) in enumerate(zip(paths, TRACKS)):
+                    pos, val, isf = eng.track_runs(2 * c + s, kind, int(coverageCutoff), int(lengths[c]))
+                    if len(pos) == 0:
+                        continue
+                    pending.append(writers[k].submit(write_runs, path, chromosome, kind, pos, val, isf))
+                    n_lines += len(pos)
+        finally:
+            for w in writers:
+                w.shutdown(wait=True)
+        for f in pending:
+            f.result()                                             # re-raises a writer's IOError
         tm["tracks_s"] = time.time() - t3
         tm["track_lines"] = n_lines
         tm["gpu_launches"] = eng.launch_count()
