@@ -163,6 +163,13 @@ void parallel_for(size_t n, int threads, F f) {
     for (auto &th : pool) th.join();
 }
 
+// the same over ranges [b, e): per-range state (a local table folded into the shared result once per range)
+template <class F>
+void parallel_ranges(size_t n, int threads, F f) {
+    const size_t grain = std::max<size_t>(1, n / ((size_t)std::max(1, threads) * 16));
+    parallel_for((n + grain - 1) / grain, threads, [&](size_t c) { f(c * grain, std::min(n, (c + 1) * grain)); });
+}
+
 inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 inline int32_t rdi32(const uint8_t *p) { return (int32_t)rd32(p); }
@@ -305,6 +312,107 @@ struct SliceLut {
     }
 };
 const SliceLut kSlice;
+
+// ---- word-at-a-time packers of the per-base columns (sixteen bases / eight qualities per step instead of one) ----
+inline uint64_t ld64(const uint8_t *p) { uint64_t x; memcpy(&x, p, 8); return x; }
+// up to 8 bytes, the rest zero
+inline uint64_t ld_tail(const uint8_t *p, uint32_t nbytes) { uint64_t x = 0; memcpy(&x, p, nbytes); return x; }
+// BAM packs the first base of a byte in the HIGH nibble: after this, nibble i of the word is base i
+inline uint64_t nibble_swap(uint64_t x) { return ((x & 0x0F0F0F0F0F0F0F0FULL) << 4) | ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL); }
+// bit 4i of x (i = 0..15) -> bit i
+inline uint32_t gather_every_4th(uint64_t x) {
+    x &= 0x1111111111111111ULL;
+    x = (x | (x >> 3)) & 0x0303030303030303ULL;
+    x = (x | (x >> 6)) & 0x000F000F000F000FULL;
+    x = (x | (x >> 12)) & 0x000000FF000000FFULL;
+    x = (x | (x >> 24)) & 0xFFFFULL;
+    return (uint32_t)x;
+}
+// sixteen nibbles (base i in nibble i) -> per-nibble flags at bit 4i: low / high bit of the 2-bit base code A=0 C=1 G=2 T=3,
+// anything that is not exactly one of C (2), G (4), T (8) coded A
+inline void code_flags(uint64_t x, uint64_t &lo, uint64_t &hi) {
+    const uint64_t m = 0x1111111111111111ULL;
+    const uint64_t b0 = x & m, b1 = (x >> 1) & m, b2 = (x >> 2) & m, b3 = (x >> 3) & m;
+    const uint64_t n0 = b0 ^ m, n1 = b1 ^ m, n2 = b2 ^ m, n3 = b3 ^ m;
+    const uint64_t onlyC = n0 & b1 & n2 & n3, onlyG = n0 & n1 & b2 & n3, onlyT = n0 & n1 & n2 & b3;
+    lo = onlyC | onlyT;
+    hi = onlyG | onlyT;
+}
+// sixteen nibbles -> sixteen 2-bit codes, base i at bits 2i
+inline uint32_t codes16(uint64_t x) {
+    uint64_t lo, hi;
+    code_flags(x, lo, hi);
+    uint64_t c = lo | (hi << 1);
+    c = (c | (c >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
+    c = (c | (c >> 4)) & 0x00FF00FF00FF00FFULL;
+    c = (c | (c >> 8)) & 0x0000FFFF0000FFFFULL;
+    c = (c | (c >> 16)) & 0x00000000FFFFFFFFULL;
+    return (uint32_t)c;
+}
+// eight dictionary codes, one per byte -> 8 x bits (bits = 2 or 4), quality j at bits j * bits
+inline uint32_t squeeze8(uint64_t w, uint32_t bits) {
+    if (bits == 2) {
+        w = (w | (w >> 6)) & 0x000F000F000F000FULL;
+        w = (w | (w >> 12)) & 0x000000FF000000FFULL;
+        w = (w | (w >> 24)) & 0xFFFFULL;
+    } else {
+        w = (w | (w >> 4)) & 0x00FF00FF00FF00FFULL;
+        w = (w | (w >> 8)) & 0x0000FFFF0000FFFFULL;
+        w = (w | (w >> 16)) & 0xFFFFFFFFULL;
+    }
+    return (uint32_t)w;
+}
+// little-endian bit stream: put() appends the low nbits (<= 32) of v; the bytes come out as if every field had been
+// OR-ed into place one by one
+struct BitWriter {
+    uint8_t *p;
+    uint64_t acc = 0;
+    uint32_t nb = 0;
+    explicit BitWriter(uint8_t *dst) : p(dst) {}
+    inline void put(uint32_t v, uint32_t nbits) {
+        acc |= (uint64_t)v << nb;
+        nb += nbits;
+        if (nb >= 64) {
+            memcpy(p, &acc, 8);
+            p += 8;
+            nb -= 64;
+            acc = nb ? (uint64_t)v >> (nbits - nb) : 0;
+        }
+    }
+    // whole bytes written so far go out, a partly filled last byte too; returns the end of the written bytes
+    inline uint8_t *finish() {
+        const uint32_t bytes = (nb + 7) / 8;
+        memcpy(p, &acc, bytes);
+        p += bytes;
+        acc = 0;
+        nb = 0;
+        return p;
+    }
+};
+// l_seq BAM bases -> 2-bit codes appended to the stream
+inline void put_seq_codes(BitWriter &w, const uint8_t *seq, uint32_t l_seq) {
+    uint32_t j = 0;
+    for (; j + 16 <= l_seq; j += 16) w.put(codes16(nibble_swap(ld64(seq + (j >> 1)))), 32);
+    if (j < l_seq) {
+        const uint32_t rem = l_seq - j;     // 1..15 bases; an odd length leaves a pad nibble that the mask drops
+        w.put(codes16(nibble_swap(ld_tail(seq + (j >> 1), (rem + 1) / 2))) & ((1u << (2 * rem)) - 1u), 2 * rem);
+    }
+}
+// l_seq qualities -> dictionary codes of `bits` bits appended to the stream
+inline void put_qual_codes(BitWriter &w, const uint8_t *qual, uint32_t l_seq, const uint8_t *code, uint32_t bits) {
+    uint32_t j = 0;
+    for (; j + 8 <= l_seq; j += 8) {
+        const uint8_t *q = qual + j;
+        const uint64_t c = (uint64_t)code[q[0]] | ((uint64_t)code[q[1]] << 8) | ((uint64_t)code[q[2]] << 16) | ((uint64_t)code[q[3]] << 24) |
+                           ((uint64_t)code[q[4]] << 32) | ((uint64_t)code[q[5]] << 40) | ((uint64_t)code[q[6]] << 48) | ((uint64_t)code[q[7]] << 56);
+        w.put(squeeze8(c, bits), 8 * bits);
+    }
+    if (j < l_seq) {
+        uint64_t c = 0;
+        for (uint32_t k = 0; j + k < l_seq; k++) c |= (uint64_t)code[qual[j + k]] << (8 * k);
+        w.put(squeeze8(c, bits), (l_seq - j) * bits);
+    }
+}
 
 struct Owner {
     HostAlloc mem;
@@ -607,7 +715,10 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
 
     lap("alloc");
     // ---- pass A: fixed-size fields, tags, sizes
-    parallel_for(n, threads, [&](size_t i) {
+    parallel_ranges(n, threads, [&](size_t range_b, size_t range_e) {
+      uint8_t qual_tab[256];      // quality values met in this range
+      memset(qual_tab, 0, sizeof qual_tab);
+      for (size_t i = range_b; i < range_e; i++) {
         const uint8_t *r = raw.data() + recoff[i];
         const uint32_t bs = rd32(r - 4);
         const int32_t ref_id = rdi32(r), pos = rdi32(r + 4);
@@ -674,18 +785,22 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
                 while (span > cur && !max_span.compare_exchange_weak(cur, span, std::memory_order_relaxed)) {}
             }
         }
-        if (!raw_qual && l_seq > 0) {
-            uint64_t seen[4] = {0, 0, 0, 0};
-            for (int32_t k = 0; k < l_seq; k++) seen[qual[k] >> 6] |= 1ull << (qual[k] & 63);
-            for (int w = 0; w < 4; w++)
-                if (seen[w] & ~qual_seen[w].load(std::memory_order_relaxed)) qual_seen[w].fetch_or(seen[w], std::memory_order_relaxed);
-        }
+        if (!raw_qual)
+            for (int32_t k = 0; k < l_seq; k++) qual_tab[qual[k]] = 1;
         sd_read_rec &o = rec[i];
         o.pos = pos;
         o.ref_mapq_flag = (ref & 0xFFFFu) | (mapq << 16) | (f << 24);
         o.xi = a.xi;
         o.lseq_ncig = (uint32_t)l_seq | (n_cig << 16);
         o.nm_nmp = a.nm | (nmp << 16);
+      }
+      if (!raw_qual) {
+          uint64_t seen[4] = {0, 0, 0, 0};
+          for (int v = 0; v < 256; v++)
+              if (qual_tab[v]) seen[v >> 6] |= 1ull << (v & 63);
+          for (int w = 0; w < 4; w++)
+              if (seen[w] & ~qual_seen[w].load(std::memory_order_relaxed)) qual_seen[w].fetch_or(seen[w], std::memory_order_relaxed);
+      }
     });
     if (fmt_err) return bail(SD_ERR_FORMAT, "malformed alignment record or tag");
     if (limit_err) return bail(SD_ERR_LIMIT, "read longer than 65535 bases (or MP position out of range)");
@@ -798,7 +913,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
         uint8_t *ps = (uint8_t *)seqc + tiles[t].seq_off;   // group-major block: slot (g, row) at 16 * (g * tile_reads + row)
         memset(ps, 0, (size_t)(tiles[t + 1].seq_off - tiles[t].seq_off));
         uint8_t *pq = qualc + tiles[t].qual_off * qual_bits / 8;   // tile offsets are in bases, a multiple of 16: byte aligned at any coding
-        uint64_t qn = 0;                                            // bases of this tile written so far (coded form)
+        BitWriter wq(pq);                                           // coded form: one bit stream per tile
         uint8_t *pc = (uint8_t *)cigc + tiles[t].cig_off;
         uint8_t *pm = mpc ? (uint8_t *)mpc + tiles[t].mp_off : nullptr;
         const size_t e = std::min(n, (t + 1) * (size_t)tile_reads);
@@ -813,40 +928,41 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
             memcpy(pc, cig, 4 * (size_t)n_cig);
             pc += 4 * (size_t)n_cig;
             if (qual_bits == 8) {
-                memcpy(pq, qual, l_seq);
-                pq += l_seq;
-            } else if (qual_bits == 4) {
-                for (uint32_t j = 0; j < l_seq; j++, qn++) {
-                    if (!(qn & 1)) pq[qn >> 1] = qual_code[qual[j]];
-                    else pq[qn >> 1] |= (uint8_t)(qual_code[qual[j]] << 4);
-                }
+                memcpy(wq.p, qual, l_seq);
+                wq.p += l_seq;
             } else {
-                for (uint32_t j = 0; j < l_seq; j++, qn++) {
-                    if (!(qn & 3)) pq[qn >> 2] = qual_code[qual[j]];
-                    else pq[qn >> 2] |= (uint8_t)(qual_code[qual[j]] << (2 * (qn & 3)));
-                }
+                put_qual_codes(wq, qual, l_seq, qual_code, qual_bits);
             }
             const uint32_t nbytes = (l_seq + 1) / 2;
-            for (uint32_t g = 0; g < (l_seq + 31) / 32; g++) {   // one group = 32 bases = 16 packed bytes -> 4 plane words
-                uint32_t pl[4] = {0, 0, 0, 0};
-                for (uint32_t j = 0; j < 16; j++) {
-                    const uint32_t bi = 16 * g + j;
-                    if (bi >= nbytes) break;
-                    uint8_t b = seq[bi];
-                    if (2 * bi + 1 >= l_seq) b &= 0xF0;  // odd length: ignore the pad nibble
-                    const uint32_t v = kSlice.v[b];     // byte p = plane p of the two bases (bit 0 first base)
-                    pl[0] |= (v & 3u) << (2 * j);
-                    pl[1] |= ((v >> 8) & 3u) << (2 * j);
-                    pl[2] |= ((v >> 16) & 3u) << (2 * j);
-                    pl[3] |= ((v >> 24) & 3u) << (2 * j);
+            const size_t row = k - t * (size_t)tile_reads;
+            for (uint32_t g = 0; g < (l_seq + 31) / 32; g++) {   // one group = 32 bases = 16 packed bytes -> 2 code words / 4 plane words
+                const uint32_t have = std::min(16u, nbytes - 16 * g);          // bytes of this group present in the record
+                uint64_t x[2];
+                if (have == 16) {
+                    x[0] = ld64(seq + 16 * g);
+                    x[1] = ld64(seq + 16 * g + 8);
+                } else {
+                    x[0] = ld_tail(seq + 16 * g, std::min(8u, have));
+                    x[1] = have > 8 ? ld_tail(seq + 16 * g + 8, have - 8) : 0;
+                }
+                x[0] = nibble_swap(x[0]);
+                x[1] = nibble_swap(x[1]);
+                if (32 * g + 2 * have > l_seq) {   // odd length: ignore the pad nibble (the last one present)
+                    const uint32_t nib = 2 * have - 1;
+                    x[nib >> 4] &= ~(0xFULL << (4 * (nib & 15)));
                 }
                 if (seq2) {   // A=0 C=1 G=2 T=3, anything else A
-                    const uint32_t onlyC = ~pl[0] & pl[1] & ~pl[2] & ~pl[3], onlyG = ~pl[0] & ~pl[1] & pl[2] & ~pl[3],
-                                   onlyT = ~pl[0] & ~pl[1] & ~pl[2] & pl[3];
-                    const uint32_t two[2] = {onlyC | onlyT, onlyG | onlyT};
-                    memcpy(ps + 8 * ((size_t)g * tile_reads + (k - t * (size_t)tile_reads)), two, 8);
-                } else
-                    memcpy(ps + 16 * ((size_t)g * tile_reads + (k - t * (size_t)tile_reads)), pl, 16);
+                    uint64_t lo0, hi0, lo1, hi1;
+                    code_flags(x[0], lo0, hi0);
+                    code_flags(x[1], lo1, hi1);
+                    const uint32_t two[2] = {gather_every_4th(lo0) | (gather_every_4th(lo1) << 16),
+                                             gather_every_4th(hi0) | (gather_every_4th(hi1) << 16)};
+                    memcpy(ps + 8 * ((size_t)g * tile_reads + row), two, 8);
+                } else {      // bit-planes of the BAM nibble
+                    uint32_t pl[4];
+                    for (int b = 0; b < 4; b++) pl[b] = gather_every_4th(x[0] >> b) | (gather_every_4th(x[1] >> b) << 16);
+                    memcpy(ps + 16 * ((size_t)g * tile_reads + row), pl, 16);
+                }
             }
             if (pm && mp_ptr[i] && mp_all) {
                 mp_for_all(mp_ptr[i], [&](long conv, long rp, long fp) {
@@ -863,7 +979,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
             }
         }
         // zero the 16-byte tile padding so the columns are deterministic
-        if (qual_bits != 8) pq += (qn * qual_bits + 7) / 8;
+        pq = wq.finish();
         memset(pq, 0, (size_t)((qualc + tiles[t + 1].qual_off * qual_bits / 8) - pq));
         memset(pc, 0, (size_t)(((uint8_t *)cigc + tiles[t + 1].cig_off) - pc));
         if (pm) memset(pm, 0, (size_t)(((uint8_t *)mpc + tiles[t + 1].mp_off) - pm));
@@ -923,6 +1039,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
                 while (cb > cur && !w_max_cig.compare_exchange_weak(cur, cb, std::memory_order_relaxed)) {}
             }
         });
+        lap("wire:shapes");
         uint64_t run_b = 0, run_v = 0, run_m = 0;
         for (size_t t = 0; t < n_tiles; t++) {
             const uint64_t nb = wt[t].base_off, nv = wt[t].var_off, nm_ = wt[t].mp_off;
@@ -966,6 +1083,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
             { uint32_t zero = 0; if (!big && !std::binary_search(xi_vals.begin(), xi_vals.end(), zero)) xi_vals.insert(std::lower_bound(xi_vals.begin(), xi_vals.end(), zero), zero); }
             xi_small = !big && xi_vals.size() <= 65536;
         }
+        lap("wire:xi dict");
         uint16_t *xi16 = xi_small ? (uint16_t *)own->mem.get(slots * 2) : nullptr;
         float *xi32 = xi_small ? nullptr : (float *)own->mem.get(slots * 4);
         float *xi_dict = xi_small ? (float *)own->mem.get(std::max<size_t>(1, xi_vals.size()) * 4) : nullptr;
@@ -985,9 +1103,7 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
             const uint32_t *cg = cigc + tiles[t].cig_off / 4;
             uint32_t sum_c = 0;
             // bit writers of the two per-base columns; the tile starts byte aligned
-            uint8_t *ps = wseq + h.base_off / 4, *pq = wqual + h.base_off * qual_bits / 8;
-            uint64_t acc_s = 0, acc_q = 0;
-            uint32_t nb_s = 0, nb_q = 0;
+            BitWriter ws(wseq + h.base_off / 4), wq(wqual + h.base_off * qual_bits / 8);
             for (uint32_t k = 0; k < tile_reads; k++) {
                 const uint32_t fl = r[k].ref_mapq_flag >> 24, ref = r[k].ref_mapq_flag & 0xFFFFu, mapq = (r[k].ref_mapq_flag >> 16) & 0xFFu;
                 const uint32_t lseq = r[k].lseq_ncig & 0xFFFFu, ncig = r[k].lseq_ncig >> 16;
@@ -1012,28 +1128,17 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
                 const uint8_t *rr = raw.data() + recoff[i];
                 const uint8_t *seq = rr + 32 + rr[8] + 4 * (size_t)rd16(rr + 12);
                 const uint8_t *qual = seq + ((size_t)lseq + 1) / 2;
-                for (uint32_t j = 0; j < lseq; j++) {
-                    const uint32_t nib = (j & 1) ? (seq[j >> 1] & 15u) : (seq[j >> 1] >> 4);
-                    const uint32_t code = nib == 2u ? 1u : (nib == 4u ? 2u : (nib == 8u ? 3u : 0u));   // A=0 C=1 G=2 T=3, anything else A
-                    acc_s |= (uint64_t)code << nb_s;
-                    nb_s += 2;
-                    if (nb_s == 64) { memcpy(ps, &acc_s, 8); ps += 8; acc_s = 0; nb_s = 0; }
-                }
+                put_seq_codes(ws, seq, lseq);       // A=0 C=1 G=2 T=3, anything else A
                 if (qual_bits == 8) {
-                    memcpy(pq, qual, lseq);
-                    pq += lseq;
+                    memcpy(wq.p, qual, lseq);
+                    wq.p += lseq;
                 } else {
-                    for (uint32_t j = 0; j < lseq; j++) {
-                        acc_q |= (uint64_t)qual_code[qual[j]] << nb_q;
-                        nb_q += qual_bits;
-                        if (nb_q == 64) { memcpy(pq, &acc_q, 8); pq += 8; acc_q = 0; nb_q = 0; }
-                    }
+                    put_qual_codes(wq, qual, lseq, qual_code, qual_bits);
                 }
             }
             // flush the writers and zero the padding up to the next tile (64 bases = 16 / 16 / 32 / 64 bytes: the accumulators never straddle it)
             const uint8_t *es = wseq + wt[t + 1].base_off / 4, *eq = wqual + wt[t + 1].base_off * qual_bits / 8;
-            if (nb_s) { memcpy(ps, &acc_s, (nb_s + 7) / 8); ps += (nb_s + 7) / 8; }
-            if (nb_q) { memcpy(pq, &acc_q, (nb_q + 7) / 8); pq += (nb_q + 7) / 8; }
+            uint8_t *ps = ws.finish(), *pq = wq.finish();
             memset(ps, 0, (size_t)(es - ps));
             memset(pq, 0, (size_t)(eq - pq));
             if (shape)      // pad words of the var block
