@@ -472,6 +472,14 @@ int sd_rewrite_bam_indexed(const char *in_path, const char *out_path, const char
                            const uint8_t *keep, const uint8_t *state, uint64_t n_records, int sort, int level, int threads,
                            uint64_t *n_written, char *err, int errlen);
 
+/* ------------------------------------------------------------------ BGZF block inflate
+ * sd_inflate_raw: one raw DEFLATE stream (RFC 1951; the payload of a BGZF block, htslib's bgzf.c inflate_block) decoded
+ * into exactly out_len bytes.  Returns 1 on success and 0 when the stream is malformed, does not produce exactly
+ * out_len bytes, or uses a form this decoder leaves to zlib (an incomplete Huffman code other than a single one-bit
+ * code); it never reads or writes outside the two buffers.  sd_decode_bam tries it on every block, checks the block's
+ * CRC32 and falls back to zlib's inflate on a 0 or a CRC mismatch.  Host pointers. */
+int sd_inflate_raw(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_len);
+
 /* ------------------------------------------------------------------ host text output
  * sd_format_repr: x printed like Python's repr(float) (what the reference's print() of a rate produces); buf >= 32 bytes.
  * sd_write_bedgraphs: the two per-position conversion bedgraphs (tcounter.py:277-285, 315-326) from host copies of

@@ -467,9 +467,17 @@ int sd_bam_inflate_file(const char *path, int threads, RawBuf &raw, size_t *comp
     raw.reset(utotal);
     if (!raw.data()) return fail(err, errlen, SD_ERR_NOMEM, "out of host memory");
     std::atomic<int> bad(0);
+    std::atomic<size_t> zlib_blocks(0);
+    const char *env_inflate = getenv("SD_INFLATE");                 // SD_INFLATE=zlib: every block through zlib (A/B timing, tests)
+    const bool use_own_inflate = !(env_inflate && strcmp(env_inflate, "zlib") == 0);
     parallel_for(blks.size(), threads, [&](size_t i) {
         const Blk &b = blks[i];
         if (b.ulen == 0) return;
+        const uint32_t crc = rd32(file.data() + b.coff + b.clen);
+        // the block decoder of sd_inflate.cpp first; zlib for whatever it turns down or gets wrong by the block's CRC
+        if (use_own_inflate && sd_inflate_raw(file.data() + b.coff, b.clen, raw.data() + b.uoff, b.ulen) &&
+            (uint32_t)crc32(crc32(0L, Z_NULL, 0), raw.data() + b.uoff, (uInt)b.ulen) == crc)
+            return;
         z_stream zs;
         memset(&zs, 0, sizeof zs);
         if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
@@ -480,10 +488,11 @@ int sd_bam_inflate_file(const char *path, int threads, RawBuf &raw, size_t *comp
         const int rc = inflate(&zs, Z_FINISH);
         if (rc != Z_STREAM_END || zs.avail_out != 0) bad = 1;
         inflateEnd(&zs);
-        const uint32_t crc = rd32(file.data() + b.coff + b.clen);
         if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), raw.data() + b.uoff, (uInt)b.ulen) != crc) bad = 1;
+        if (use_own_inflate) zlib_blocks.fetch_add(1, std::memory_order_relaxed);
     });
     if (bad) return fail(err, errlen, SD_ERR_FORMAT, "%s: corrupt BGZF block", path);
+    if (getenv("SD_DECODE_TIMING")) fprintf(stderr, "[sd_bam_inflate_file] %zu blocks, %zu left to zlib\n", blks.size(), zlib_blocks.load());
     const size_t compressed = file.size();
     file.release();
     if (compressed_bytes) *compressed_bytes = compressed;

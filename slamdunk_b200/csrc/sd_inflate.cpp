@@ -1,0 +1,367 @@
+// sd_inflate.cpp -- raw DEFLATE (RFC 1951) decoder for BGZF blocks: whole block in, whole block out.
+//
+// Every BGZF block of a BAM is an independent DEFLATE stream of at most 64 KiB with its CRC32 and size in the
+// trailer, so the decoder needs no streaming state, no window and no checksum of its own: sd_bam_inflate_file
+// (sd_decode.cpp) checks the CRC of what comes out and falls back to zlib's inflate for any block this decoder turns
+// down (it returns 0 rather than guess on anything unusual).  What makes it faster than a general-purpose inflate:
+// a 64-bit bit buffer refilled with one unaligned load, 11-bit first-level tables whose entries carry literal /
+// length base / extra-bit count ready to use, up to three literals per refill, 8-byte match copies.
+#include <stdint.h>
+#include <string.h>
+
+#include "slamdunk_b200.h"
+
+namespace {
+
+constexpr int kLitBits = 11;    // first-level index width of the literal/length table
+constexpr int kDistBits = 8;    // ... of the distance table
+constexpr int kPreBits = 7;     // code-length code: at most 7 bits, no second level
+constexpr int kLitCap = (1 << kLitBits) + 2048;
+constexpr int kDistCap = (1 << kDistBits) + 1024;
+
+// table entry: [31] literal  [30] end of block  [29] second-level pointer  [28] invalid
+//              [27:12] literal byte / base value / second-level start index
+//              [11:8]  number of extra bits (or second-level index width)
+//              [7:0]   code bits to drop at this level
+constexpr uint32_t kLit = 1u << 31, kEob = 1u << 30, kSub = 1u << 29, kBad = 1u << 28;
+
+struct Tables {
+    uint32_t lit[kLitCap];
+    uint32_t dist[kDistCap];
+    uint32_t pre[1 << kPreBits];
+};
+
+const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+const uint8_t kPreOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+inline uint32_t lit_entry(uint32_t sym) {
+    if (sym < 256) return kLit | (sym << 12);
+    if (sym == 256) return kEob;
+    if (sym > 285) return kBad;     // 286, 287 take part in the fixed code but never occur
+    return ((uint32_t)kLenBase[sym - 257] << 12) | ((uint32_t)kLenExtra[sym - 257] << 8);
+}
+inline uint32_t dist_entry(uint32_t sym) {
+    if (sym > 29) return kBad;
+    return ((uint32_t)kDistBase[sym] << 12) | ((uint32_t)kDistExtra[sym] << 8);
+}
+inline uint32_t pre_entry(uint32_t sym) { return sym << 12; }
+
+inline uint32_t reverse_bits(uint32_t code, int len) {
+    uint32_t r = 0;
+    for (int i = 0; i < len; i++) r |= ((code >> i) & 1u) << (len - 1 - i);
+    return r;
+}
+
+// Canonical Huffman code (lens[0..n), 0 = unused, at most 15 bits) -> decode table read with the NEXT bits of the
+// stream (DEFLATE packs codes starting from their most significant bit, so entries sit at the bit-reversed code).
+// Only complete codes are taken, plus the one incomplete form DEFLATE permits in practice: a single code of one bit
+// (a block with one distance code, or none).  Anything else -> false, and the caller leaves the block to zlib.
+template <class EntryFn>
+bool build_table(uint32_t *table, int cap, int root, const uint8_t *lens, int n, EntryFn entry_of) {
+    int count[16] = {0};
+    for (int i = 0; i < n; i++) count[lens[i]]++;
+    if (count[0] == n) {            // no code at all (a block of literals only has no distance code): every lookup is invalid
+        for (int k = 0; k < (1 << root); k++) table[k] = kBad | 1u;
+        return true;
+    }
+    int left = 1, max_len = 0, used = 0;
+    for (int len = 1; len <= 15; len++) {
+        left = (left << 1) - count[len];
+        if (left < 0) return false;                     // over-subscribed
+        if (count[len]) max_len = len;
+        used += count[len];
+    }
+    const bool single = used == 1 && count[1] == 1;
+    if (left != 0 && !single) return false;             // incomplete
+    uint32_t next_code[16];
+    {
+        uint32_t code = 0;
+        for (int len = 1; len <= 15; len++) {
+            code = (code + (uint32_t)count[len - 1] * (len > 1)) << 1;
+            next_code[len] = code;
+        }
+    }
+    const uint32_t root_mask = (1u << root) - 1u;
+    for (int k = 0; k < (1 << root); k++) table[k] = kBad | 1u;
+    // codes longer than the first level: width of each prefix's second level = its longest code - root
+    uint8_t sub_len[1 << kLitBits];
+    if (max_len > root) memset(sub_len, 0, (size_t)1 << root);
+    // first pass: assign codes in canonical order (by length, then by symbol), remember each symbol's reversed code
+    uint16_t rev_code[320];
+    {
+        uint32_t nc[16];
+        memcpy(nc, next_code, sizeof nc);
+        for (int i = 0; i < n; i++) {
+            const int len = lens[i];
+            if (!len) continue;
+            const uint32_t rev = reverse_bits(nc[len]++, len);
+            rev_code[i] = (uint16_t)rev;
+            if (len > root) {
+                uint8_t &m = sub_len[rev & root_mask];
+                if ((int)m < len - root) m = (uint8_t)(len - root);
+            }
+        }
+    }
+    int next_free = 1 << root;
+    if (max_len > root) {
+        for (uint32_t pfx = 0; pfx <= root_mask; pfx++) {
+            if (!sub_len[pfx]) continue;
+            const int width = sub_len[pfx];
+            if (next_free + (1 << width) > cap) return false;
+            table[pfx] = kSub | ((uint32_t)next_free << 12) | ((uint32_t)width << 8) | (uint32_t)root;
+            for (int k = 0; k < (1 << width); k++) table[next_free + k] = kBad | 1u;
+            next_free += 1 << width;
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        const int len = lens[i];
+        if (!len) continue;
+        const uint32_t rev = rev_code[i];
+        const uint32_t e = entry_of((uint32_t)i);
+        if (len <= root) {
+            for (uint32_t k = rev; k <= root_mask; k += 1u << len) table[k] = e | (uint32_t)len;
+        } else {
+            const uint32_t head = table[rev & root_mask];
+            if (!(head & kSub)) return false;           // a shorter code owns this prefix: not a prefix code
+            const uint32_t start = (head >> 12) & 0xFFFFu, width = (head >> 8) & 15u;
+            for (uint32_t k = rev >> root; k < (1u << width); k += 1u << (len - root)) table[start + k] = e | (uint32_t)(len - root);
+        }
+    }
+    return true;
+}
+
+struct Fixed {
+    uint32_t lit[kLitCap];
+    uint32_t dist[kDistCap];
+    bool ok;
+    Fixed() {
+        uint8_t l[288], d[32];
+        for (int i = 0; i < 144; i++) l[i] = 8;
+        for (int i = 144; i < 256; i++) l[i] = 9;
+        for (int i = 256; i < 280; i++) l[i] = 7;
+        for (int i = 280; i < 288; i++) l[i] = 8;
+        for (int i = 0; i < 32; i++) d[i] = 5;
+        ok = build_table(lit, kLitCap, kLitBits, l, 288, lit_entry) && build_table(dist, kDistCap, kDistBits, d, 32, dist_entry);
+    }
+};
+const Fixed kFixed;
+
+struct Bits {
+    const uint8_t *in, *in_end;
+    uint64_t buf = 0;
+    int cnt = 0;            // valid bits in buf; goes negative when the stream is read past its end
+    Bits(const uint8_t *p, size_t n) : in(p), in_end(p + n) {}
+    inline void refill() {
+        if (in_end - in >= 8) {
+            uint64_t x;
+            memcpy(&x, in, 8);
+            buf |= x << cnt;
+            in += (63 - cnt) >> 3;
+            cnt |= 56;
+        } else {
+            while (cnt <= 56 && in < in_end) {
+                buf |= (uint64_t)*in++ << cnt;
+                cnt += 8;
+            }
+        }
+    }
+    inline uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1ull)); }
+    inline void drop(int n) {
+        buf >>= n;
+        cnt -= n;
+    }
+    inline uint32_t take(int n) {
+        const uint32_t v = peek(n);
+        drop(n);
+        return v;
+    }
+};
+
+// next symbol of a two-level table: returns the entry, its code bits already dropped
+inline uint32_t decode(Bits &b, const uint32_t *table, int root) {
+    uint32_t e = table[b.peek(root)];
+    if (e & kSub) {
+        b.drop((int)(e & 0xFFu));
+        e = table[((e >> 12) & 0xFFFFu) + b.peek((int)((e >> 8) & 15u))];
+    }
+    b.drop((int)(e & 0xFFu));
+    return e;
+}
+
+}  // namespace
+
+extern "C" int sd_inflate_raw(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_len) {
+    if ((!in && in_len) || (!out && out_len) || !kFixed.ok) return 0;
+    Bits b(in, (size_t)in_len);
+    uint8_t *const out_begin = out, *const out_end = out + out_len;
+    Tables T;
+    for (;;) {
+        b.refill();
+        const uint32_t final_block = b.take(1), type = b.take(2);
+        if (b.cnt < 0) return 0;
+        const uint32_t *lit = nullptr, *dist = nullptr;
+        if (type == 0) {            // stored: back to a byte boundary, LEN, ~LEN, bytes
+            b.drop(b.cnt & 7);
+            const uint8_t *p = b.in - (b.cnt >> 3);     // bytes still in the bit buffer have not been used
+            if (b.in_end - p < 4) return 0;
+            const uint32_t len = p[0] | ((uint32_t)p[1] << 8), nlen = p[2] | ((uint32_t)p[3] << 8);
+            p += 4;
+            if ((len ^ nlen) != 0xFFFFu || (uint64_t)(b.in_end - p) < len || (uint64_t)(out_end - out) < len) return 0;
+            memcpy(out, p, len);
+            out += len;
+            b.in = p + len;
+            b.buf = 0;
+            b.cnt = 0;
+            if (final_block) break;
+            continue;
+        } else if (type == 1) {
+            lit = kFixed.lit;
+            dist = kFixed.dist;
+        } else if (type == 2) {
+            const uint32_t hlit = b.take(5) + 257, hdist = b.take(5) + 1, hclen = b.take(4) + 4;
+            if (hlit > 286 || hdist > 30) return 0;
+            uint8_t pre_lens[19] = {0};
+            for (uint32_t i = 0; i < hclen; i++) {
+                if (b.cnt < 3) b.refill();
+                pre_lens[kPreOrder[i]] = (uint8_t)b.take(3);
+            }
+            if (b.cnt < 0 || !build_table(T.pre, 1 << kPreBits, kPreBits, pre_lens, 19, pre_entry)) return 0;
+            uint8_t lens[286 + 30 + 138];
+            uint32_t i = 0;
+            while (i < hlit + hdist) {
+                b.refill();
+                const uint32_t e = T.pre[b.peek(kPreBits)];
+                if (e & kBad) return 0;
+                b.drop((int)(e & 0xFFu));
+                const uint32_t sym = (e >> 12) & 0xFFFFu;
+                if (sym < 16) {
+                    lens[i++] = (uint8_t)sym;
+                } else {
+                    uint32_t rep, val = 0;
+                    if (sym == 16) {
+                        if (i == 0) return 0;
+                        val = lens[i - 1];
+                        rep = 3 + b.take(2);
+                    } else if (sym == 17) {
+                        rep = 3 + b.take(3);
+                    } else {
+                        rep = 11 + b.take(7);
+                    }
+                    if (i + rep > hlit + hdist) return 0;
+                    memset(lens + i, (int)val, rep);
+                    i += rep;
+                }
+                if (b.cnt < 0) return 0;
+            }
+            if (lens[256] == 0) return 0;       // no end-of-block code
+            if (!build_table(T.lit, kLitCap, kLitBits, lens, (int)hlit, lit_entry)) return 0;
+            if (!build_table(T.dist, kDistCap, kDistBits, lens + hlit, (int)hdist, dist_entry)) return 0;
+            lit = T.lit;
+            dist = T.dist;
+        } else {
+            return 0;
+        }
+
+        // ---- symbols of the block
+        for (;;) {
+            uint32_t e;
+            // fast loop: at least 8 input bytes for every refill, room for the longest match plus the slack of 8-byte copies
+            while (b.in_end - b.in >= 8 && out_end - out >= 258 + 16) {
+                b.refill();                                 // >= 56 bits
+                e = lit[b.peek(kLitBits)];
+                // literals whose code fits the first level (<= 11 bits each): three of them and the symbol after fit one refill
+                if (e & kLit) {
+                    b.drop((int)(e & 0xFFu));
+                    *out++ = (uint8_t)(e >> 12);
+                    e = lit[b.peek(kLitBits)];
+                    if (e & kLit) {
+                        b.drop((int)(e & 0xFFu));
+                        *out++ = (uint8_t)(e >> 12);
+                        e = lit[b.peek(kLitBits)];
+                        if (e & kLit) {
+                            b.drop((int)(e & 0xFFu));
+                            *out++ = (uint8_t)(e >> 12);
+                            e = lit[b.peek(kLitBits)];
+                        }
+                    }
+                }
+                if (e & kSub) {                             // second level: codes of 12 to 15 bits
+                    b.drop((int)(e & 0xFFu));
+                    e = lit[((e >> 12) & 0xFFFFu) + b.peek((int)((e >> 8) & 15u))];
+                }
+                b.drop((int)(e & 0xFFu));                   // <= 33 + 15 bits so far
+                if (e & kLit) {
+                    *out++ = (uint8_t)(e >> 12);
+                    continue;
+                }
+                if (e & (kEob | kBad)) goto block_done;
+                {
+                    const uint32_t len = ((e >> 12) & 0xFFFFu) + b.take((int)((e >> 8) & 15u));      // <= 53 bits so far
+                    b.refill();
+                    uint32_t d = dist[b.peek(kDistBits)];
+                    if (d & kSub) {
+                        b.drop((int)(d & 0xFFu));
+                        d = dist[((d >> 12) & 0xFFFFu) + b.peek((int)((d >> 8) & 15u))];
+                    }
+                    b.drop((int)(d & 0xFFu));
+                    if (d & kBad) return 0;
+                    const uint32_t distance = ((d >> 12) & 0xFFFFu) + b.take((int)((d >> 8) & 15u));
+                    if (distance > (uint32_t)(out - out_begin)) return 0;
+                    const uint8_t *src = out - distance;
+                    uint8_t *dst = out;
+                    out += len;
+                    if (distance >= 8) {
+                        memcpy(dst, src, 8);
+                        memcpy(dst + 8, src + 8, 8);
+                        if (len > 16) {
+                            dst += 16;
+                            src += 16;
+                            do {
+                                memcpy(dst, src, 8);
+                                dst += 8;
+                                src += 8;
+                            } while (dst < out);
+                        }
+                    } else if (distance == 1) {
+                        memset(dst, *src, len);
+                    } else {
+                        do {
+                            *dst++ = *src++;
+                        } while (dst < out);
+                    }
+                }
+            }
+            // careful loop: near the end of the input or of the output
+            b.refill();
+            e = decode(b, lit, kLitBits);
+            if (b.cnt < 0) return 0;
+            if (e & kLit) {
+                if (out >= out_end) return 0;
+                *out++ = (uint8_t)(e >> 12);
+                continue;
+            }
+            if (e & (kEob | kBad)) goto block_done;
+            {
+                const uint32_t len = ((e >> 12) & 0xFFFFu) + b.take((int)((e >> 8) & 15u));
+                b.refill();
+                const uint32_t d = decode(b, dist, kDistBits);
+                if (d & (kBad | kLit | kEob)) return 0;
+                const uint32_t distance = ((d >> 12) & 0xFFFFu) + b.take((int)((d >> 8) & 15u));
+                if (b.cnt < 0 || distance > (uint32_t)(out - out_begin) || len > (uint64_t)(out_end - out)) return 0;
+                const uint8_t *src = out - distance;
+                for (uint32_t k = 0; k < len; k++) out[k] = src[k];
+                out += len;
+            }
+            continue;
+        block_done:
+            if (e & kBad) return 0;
+            break;
+        }
+        if (b.cnt < 0) return 0;
+        if (final_block) break;
+    }
+    return out == out_end ? 1 : 0;
+}

@@ -294,6 +294,74 @@ def test_native_float_repr_equals_python_repr():
         assert fmt(x) == repr(x), (x, fmt(x), repr(x))
 
 
+def test_block_inflate_matches_zlib_and_refuses_what_it_cannot_decode(tmp_path, monkeypatch):
+    """sd_inflate_raw (the decoder sd_decode_bam tries on every BGZF block before zlib): round trips over levels,
+    strategies (stored, fixed, dynamic, Huffman-only, RLE), multi-block streams and sizes around the fast-loop margins;
+    wrong sizes, truncated and corrupted streams come back as 0 or as bytes the block's CRC would reject -- never past
+    the buffers.  Then a whole BAM decoded through it equals the same BAM decoded through zlib alone."""
+    import ctypes
+    import random
+    import zlib
+    lib = L.load()
+    rng = random.Random(5)
+
+    def own(comp, n):
+        out = ctypes.create_string_buffer(n + 64)
+        ctypes.memset(out, 0xAA, n + 64)
+        ok = lib.sd_inflate_raw(comp, len(comp), ctypes.cast(out, ctypes.c_void_p), n)
+        assert out.raw[n:] == b"\xAA" * 64, "wrote past the end"
+        return ok, out.raw[:n]
+
+    def deflate(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, memlevel=8):
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, memlevel, strategy)
+        return c.compress(data) + c.flush()
+
+    samples = [b"", b"a", bytes(1000), bytes(range(256)) * 250, os.urandom(65280),
+               b"".join(rng.choice([b"ACGT", b"AAAA", b"FFFFFFFF", b"chr1", os.urandom(3)]) for _ in range(9000))[:65280],
+               ("".join("%d:%d:%d," % (rng.randint(0, 24), rng.randint(1, 100), rng.randint(1, 100)) for _ in range(6000))).encode()]
+    for n in (1, 2, 7, 8, 9, 16, 17, 257, 258, 259, 265, 266, 267, 273, 274, 275, 600):
+        samples += [bytes(rng.randrange(4) for _ in range(n)), b"x" * n]
+    decoded = 0
+    for data in samples:
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED):
+                comp = deflate(data, level, strategy, memlevel=rng.choice((1, 8)))
+                ok, got = own(comp, len(data))
+                if ok:                                   # a 0 would only mean "left to zlib"
+                    decoded += 1
+                    assert got == data
+                assert own(comp, len(data) + 1)[0] == 0
+                if data:
+                    assert own(comp, len(data) - 1)[0] == 0
+                    own(comp[:len(comp) // 2], len(data))
+    assert decoded >= 0.9 * len(samples) * 16
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)          # several blocks, empty stored blocks in between
+    parts = [os.urandom(500), b"A" * 3000, b"ACGT" * 500]
+    comp = b"".join(c.compress(t) + c.flush(fl) for t, fl in zip(parts, (zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH, zlib.Z_FINISH)))
+    assert own(comp, 5500) == (1, b"".join(parts))
+    base = os.urandom(1000) + b"ACGTTGCA" * 1500 + bytes(2000)
+    comp = deflate(base)
+    for _ in range(3000):
+        b = bytearray(comp)
+        for _k in range(rng.randint(1, 4)):
+            b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+        own(bytes(b), len(base))
+    for _ in range(1000):
+        own(os.urandom(rng.randint(0, 300)), rng.randint(0, 1000))
+
+    case = simdata.make_case(str(tmp_path), 77, n_reads=1500, read_len=(20, 120), name="inf")
+    from slamdunk_b200.engine import HostBatch
+    views = []
+    for mode in ("own", "zlib"):
+        monkeypatch.setenv("SD_INFLATE", mode)
+        hb = HostBatch(case.bam, [n for n, _l in case.bam_refs], want_mp=True, group=True, seq2=True, wire=True)
+        views.append((hb.rec_array().copy(), hb.column("seq").copy(), hb.column("qual").copy(), hb.column("cigar").copy(),
+                      hb.column("mp").copy(), hb.inflated_bytes))
+        hb.close()
+    for a, b in zip(*views):
+        assert np.array_equal(a, b)
+
+
 def _bedgraph_text_like_the_reference(names, first, strand, has, po, pl, gstart, isx, cov, tc):
     """The reference's loop (tcounter.py:277-285, 315-326): per strand one dict position -> rate filled UTR by UTR, printed
     in insertion order; a position already in the dict keeps its place (and gets the same value again)."""
