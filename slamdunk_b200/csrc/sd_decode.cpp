@@ -5,11 +5,15 @@
 // dunks/filter.py:225-256).  Written against the SAM/BAM specification; C++17 threads + zlib.
 // The decode cost is reported separately from the counting kernels (sd_hbatch.seconds_*).
 #include <cuda_runtime.h>
+#include <fcntl.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -1225,56 +1229,112 @@ extern "C" void sd_hgenome_free(sd_hgenome *g) {
     delete g;
 }
 
+namespace {
+// the FASTA file as one read-only span: mapped when the path can be mapped, read otherwise
+struct FileSpan {
+    const char *p = nullptr;
+    size_t n = 0;
+    void *map = nullptr;
+    std::vector<char> buf;
+    bool open(const char *path) {
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                map = m;
+                p = (const char *)m;
+                n = (size_t)st.st_size;
+                ::close(fd);
+                return true;
+            }
+        }
+        bool ok = true;     // pipes, empty files, file systems without mmap
+        char chunk[1 << 16];
+        for (;;) {
+            const ssize_t got = ::read(fd, chunk, sizeof chunk);
+            if (got < 0) { ok = false; break; }
+            if (got == 0) break;
+            buf.insert(buf.end(), chunk, chunk + got);
+        }
+        ::close(fd);
+        p = buf.data();
+        n = buf.size();
+        return ok;
+    }
+    ~FileSpan() {
+        if (map) munmap(map, n);
+    }
+};
+
+// byte -> 0..3 = A C G T (either case, tcounter.py:181 upper-cases the slice), 4 = any other base letter (N, IUPAC, ...),
+// 5 = white space inside sequence lines (skipped)
+struct BaseLut {
+    uint8_t v[256];
+    BaseLut() {
+        memset(v, 4, sizeof v);
+        v[(uint8_t)'\n'] = v[(uint8_t)'\r'] = v[(uint8_t)' '] = v[(uint8_t)'\t'] = 5;
+        const char *acgt = "ACGT";
+        for (int k = 0; k < 4; k++) v[(uint8_t)acgt[k]] = v[(uint8_t)(acgt[k] | 0x20)] = (uint8_t)k;
+    }
+};
+const BaseLut kBase;
+}  // namespace
+
 extern "C" int sd_load_fasta(const char *path, int threads, sd_hgenome **out, char *err, int errlen) {
     if (!path || !out) return fail(err, errlen, SD_ERR_ARG, "sd_load_fasta: null argument");
     *out = nullptr;
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     const double t0 = now_s();
-    FILE *fh = fopen(path, "rb");
-    if (!fh) return fail(err, errlen, SD_ERR_IO, "cannot open %s", path);
-    fseek(fh, 0, SEEK_END);
-    const long fsz = ftell(fh);
-    fseek(fh, 0, SEEK_SET);
-    std::vector<char> txt((size_t)fsz + 1);
-    if (fsz > 0 && fread(txt.data(), 1, (size_t)fsz, fh) != (size_t)fsz) {
-        fclose(fh);
-        return fail(err, errlen, SD_ERR_IO, "short read on %s", path);
-    }
-    fclose(fh);
-    txt[(size_t)fsz] = '\n';
+    FileSpan file;
+    if (!file.open(path)) return fail(err, errlen, SD_ERR_IO, "cannot read %s", path);
+    const char *txt = file.p;
+    const size_t n = file.n;
 
-    // pass 1: record boundaries and lengths (whitespace inside sequence lines is skipped)
+    // pass 1: the header lines ('>' at the start of a line); a record's body runs to the next header
     struct Rec { size_t body, end; uint64_t len; };
     std::vector<Rec> recs;
     GenomeOwner *own = new GenomeOwner();
-    {
-        size_t i = 0;
-        const size_t n = (size_t)fsz;
-        while (i < n) {
-            if (txt[i] == '>') {
-                size_t e = i + 1;
-                while (e < n && txt[e] != '\n') e++;
-                size_t ne = i + 1;
-                while (ne < e && txt[ne] != ' ' && txt[ne] != '\t' && txt[ne] != '\r') ne++;
-                own->names.emplace_back(txt.data() + i + 1, ne - i - 1);
-                recs.push_back({e + 1, n, 0});
-                if (recs.size() > 1) recs[recs.size() - 2].end = i;
-                i = e + 1;
-            } else {
-                while (i < n && txt[i] != '\n') i++;
-                i++;
-            }
+    for (size_t i = 0; i < n;) {
+        const char *gt = (const char *)memchr(txt + i, '>', n - i);
+        if (!gt) break;
+        const size_t k = (size_t)(gt - txt);
+        if (k != 0 && txt[k - 1] != '\n') {     // a '>' inside a line (descriptions may hold them)
+            i = k + 1;
+            continue;
         }
+        const char *nl = (const char *)memchr(gt, '\n', n - k);
+        const size_t e = nl ? (size_t)(nl - txt) : n;
+        size_t ne = k + 1;
+        while (ne < e && txt[ne] != ' ' && txt[ne] != '\t' && txt[ne] != '\r') ne++;
+        own->names.emplace_back(txt + k + 1, ne - k - 1);
+        if (!recs.empty()) recs.back().end = k;
+        recs.push_back({std::min(n, e + 1), n, 0});
+        i = e + 1;
     }
     if (recs.empty()) { delete own; return fail(err, errlen, SD_ERR_FORMAT, "%s: no FASTA records", path); }
-    parallel_for(recs.size(), threads, [&](size_t r) {
-        uint64_t L = 0;
-        for (size_t i = recs[r].body; i < recs[r].end && i < (size_t)fsz; i++) {
-            const char c = txt[i];
-            if (c != '\n' && c != '\r' && c != ' ' && c != '\t') L++;
+
+    // the bodies cut into pieces of about 1 MB of text, so that one long chromosome is spread over all threads
+    struct Piece { uint32_t rec; size_t b, e; uint64_t bases, first; };
+    std::vector<Piece> pieces;
+    const size_t piece_bytes = 1u << 20;
+    for (size_t r = 0; r < recs.size(); r++)
+        for (size_t b = recs[r].body; b < recs[r].end || b == recs[r].body; b += piece_bytes) {
+            pieces.push_back({(uint32_t)r, b, std::min(recs[r].end, b + piece_bytes), 0, 0});
+            if (b + piece_bytes >= recs[r].end) break;
         }
-        recs[r].len = L;
+    parallel_for(pieces.size(), threads, [&](size_t k) {
+        uint64_t L = 0;
+        const char *q = txt + pieces[k].b, *qe = txt + pieces[k].e;
+        for (; q < qe; q++) L += (uint64_t)((*q != '\n') & (*q != '\r') & (*q != ' ') & (*q != '\t'));
+        pieces[k].bases = L;
     });
+    for (auto &pc : pieces) {
+        pc.first = recs[pc.rec].len;
+        recs[pc.rec].len += pc.bases;
+    }
     uint64_t bits = 32;  // leading pad so that no chromosome starts at linear position 0
     for (auto &r : recs) {
         if (r.len > 0xFFFFFFF0ull) { delete own; return fail(err, errlen, SD_ERR_LIMIT, "chromosome too long"); }
@@ -1287,36 +1347,46 @@ extern "C" int sd_load_fasta(const char *path, int threads, sd_hgenome **out, ch
     uint32_t *lo = (uint32_t *)own->mem.get(n_words * 4), *hi = (uint32_t *)own->mem.get(n_words * 4),
              *nm = (uint32_t *)own->mem.get(n_words * 4);
     if (!lo || !hi || !nm) { delete own; return fail(err, errlen, SD_ERR_NOMEM, "out of host memory"); }
-    memset(lo, 0, n_words * 4);
-    memset(hi, 0, n_words * 4);
-    memset(nm, 0xFF, n_words * 4);
-    // pass 2: encode (chromosomes start on word boundaries, so records are independent)
-    parallel_for(recs.size(), threads, [&](size_t r) {
-        uint64_t g = own->off[r];
-        uint32_t wl = 0, wh = 0, wn = 0;
-        int nb = 0;
-        auto flush = [&](uint64_t word) {
-            lo[word] = wl;
-            hi[word] = wh;
-            nm[word] = wn | (nb < 32 ? (0xFFFFFFFFu << nb) : 0u);
-            wl = wh = wn = 0;
+    parallel_ranges((size_t)n_words, threads, [&](size_t b, size_t e) {
+        memset(lo + b, 0, (e - b) * 4);
+        memset(hi + b, 0, (e - b) * 4);
+        memset(nm + b, 0xFF, (e - b) * 4);     // N / pad until a base says otherwise
+    });
+    // pass 2: encode.  A piece starts at base `first` of its chromosome, in general in the middle of a 32-base word: the
+    // word a piece shares with its neighbour is merged with atomic OR / AND, every other word is written whole.
+    parallel_for(pieces.size(), threads, [&](size_t k) {
+        const Piece &pc = pieces[k];
+        if (!pc.bases) return;
+        const uint64_t g0 = (uint64_t)own->off[pc.rec] + pc.first;
+        uint64_t word = g0 >> 5;
+        uint32_t nb = (uint32_t)(g0 & 31u);
+        uint32_t wl = 0, wh = 0, wa = 0;        // low / high bit of the base code, "is one of ACGT"
+        bool shared = nb != 0;                  // the first word may hold the previous piece's last bases
+        auto flush = [&](bool merge) {
+            if (merge) {
+                __atomic_fetch_or(&lo[word], wl, __ATOMIC_RELAXED);
+                __atomic_fetch_or(&hi[word], wh, __ATOMIC_RELAXED);
+                __atomic_fetch_and(&nm[word], ~wa, __ATOMIC_RELAXED);
+            } else {
+                lo[word] = wl;
+                hi[word] = wh;
+                nm[word] = ~wa;
+            }
+            wl = wh = wa = 0;
             nb = 0;
+            word++;
+            shared = false;
         };
-        for (size_t i = recs[r].body; i < recs[r].end && i < (size_t)fsz; i++) {
-            char c = txt[i];
-            if (c == '\n' || c == '\r' || c == ' ' || c == '\t') continue;
-            c = (char)(c & ~0x20);  // upper-case ASCII letters (tcounter.py:181)
-            uint32_t code = 4;
-            if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2; else if (c == 'T') code = 3;
-            if (code < 4) {
-                wl |= (code & 1u) << nb;
-                wh |= (code >> 1) << nb;
-            } else wn |= 1u << nb;
-            nb++;
-            g++;
-            if (nb == 32) flush((g - 1) >> 5);
+        const uint8_t *q = (const uint8_t *)txt + pc.b, *qe = (const uint8_t *)txt + pc.e;
+        for (; q < qe; q++) {
+            const uint32_t v = kBase.v[*q];
+            if (v == 5) continue;
+            wl |= (v & 1u) << nb;
+            wh |= ((v >> 1) & 1u) << nb;
+            wa |= (uint32_t)(v < 4) << nb;
+            if (++nb == 32) flush(shared);
         }
-        if (nb) flush(g >> 5);
+        if (nb) flush(true);                    // the last, partly filled word: the next piece (or nobody) has the rest
     });
     for (auto &s : own->names) own->name_ptrs.push_back(const_cast<char *>(s.c_str()));
     sd_hgenome *G = new sd_hgenome();
