@@ -1116,7 +1116,8 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
             const uint32_t *cg = cigc + tiles[t].cig_off / 4;
             uint32_t sum_c = 0;
             // bit writers of the two per-base columns; the tile starts byte aligned
-            BitWriter ws(wseq + h.base_off / 4), wq(wqual + h.base_off * qual_bits / 8);
+            BitWriter ws(wseq + h.base_off / 4);
+            uint64_t tile_bases = 0;
             for (uint32_t k = 0; k < tile_reads; k++) {
                 const uint32_t fl = r[k].ref_mapq_flag >> 24, ref = r[k].ref_mapq_flag & 0xFFFFu, mapq = (r[k].ref_mapq_flag >> 16) & 0xFFu;
                 const uint32_t lseq = r[k].lseq_ncig & 0xFFFFu, ncig = r[k].lseq_ncig >> 16;
@@ -1140,18 +1141,18 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
                 const size_t i = order[s0 + k];
                 const uint8_t *rr = raw.data() + recoff[i];
                 const uint8_t *seq = rr + 32 + rr[8] + 4 * (size_t)rd16(rr + 12);
-                const uint8_t *qual = seq + ((size_t)lseq + 1) / 2;
                 put_seq_codes(ws, seq, lseq);       // A=0 C=1 G=2 T=3, anything else A
-                if (qual_bits == 8) {
-                    memcpy(wq.p, qual, lseq);
-                    wq.p += lseq;
-                } else {
-                    put_qual_codes(wq, qual, lseq, qual_code, qual_bits);
-                }
+                tile_bases += lseq;
             }
-            // flush the writers and zero the padding up to the next tile (64 bases = 16 / 16 / 32 / 64 bytes: the accumulators never straddle it)
+            // the tile's qualities: the batch column already holds them as the same back-to-back stream of bytes / dictionary
+            // codes (pass B), only the tile starts differ (multiples of 16 bases there, of 64 here) -- both byte aligned
+            const size_t qual_bytes = (size_t)((tile_bases * qual_bits + 7) / 8);
+            uint8_t *pq = wqual + h.base_off * qual_bits / 8;
+            memcpy(pq, qualc + tiles[t].qual_off * qual_bits / 8, qual_bytes);
+            pq += qual_bytes;
+            // flush the writer and zero the padding up to the next tile (64 bases = 16 / 16 / 32 / 64 bytes)
             const uint8_t *es = wseq + wt[t + 1].base_off / 4, *eq = wqual + wt[t + 1].base_off * qual_bits / 8;
-            uint8_t *ps = ws.finish(), *pq = wq.finish();
+            uint8_t *ps = ws.finish();
             memset(ps, 0, (size_t)(es - ps));
             memset(pq, 0, (size_t)(eq - pq));
             if (shape)      // pad words of the var block
