@@ -479,6 +479,9 @@ int sd_rewrite_bam_indexed(const char *in_path, const char *out_path, const char
  * code); it never reads or writes outside the two buffers.  sd_decode_bam tries it on every block, checks the block's
  * CRC32 and falls back to zlib's inflate on a 0 or a CRC mismatch.  Host pointers. */
 int sd_inflate_raw(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_len);
+/* CRC-32 of a buffer as gzip / BGZF define it (zlib's crc32(0, p, n)); carry-less-multiply folding where the CPU has
+ * PCLMULQDQ, zlib's table code otherwise and for the last n % 16 bytes. */
+uint32_t sd_crc32(const uint8_t *p, uint64_t n);
 
 /* ------------------------------------------------------------------ host text output
  * sd_format_repr: x printed like Python's repr(float) (what the reference's print() of a rate produces); buf >= 32 bytes.

@@ -299,7 +299,7 @@ extern "C" int sd_rewrite_bam_indexed(const char *in_path, const char *out_path,
         memcpy(out.data(), hd, 12);
         out[12] = 66; out[13] = 67; out[14] = 2; out[15] = 0;
         p16(out.data() + 16, (uint32_t)bsize - 1);
-        p32(out.data() + 18 + clen, (uint32_t)crc32(crc32(0L, Z_NULL, 0), in.data(), (uInt)len));
+        p32(out.data() + 18 + clen, sd_crc32(in.data(), len));
         p32(out.data() + 18 + clen + 4, (uint32_t)len);
         out.resize(bsize);
     });

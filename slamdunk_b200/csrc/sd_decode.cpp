@@ -480,7 +480,7 @@ int sd_bam_inflate_file(const char *path, int threads, RawBuf &raw, size_t *comp
         const uint32_t crc = rd32(file.data() + b.coff + b.clen);
         // the block decoder of sd_inflate.cpp first; zlib for whatever it turns down or gets wrong by the block's CRC
         if (use_own_inflate && sd_inflate_raw(file.data() + b.coff, b.clen, raw.data() + b.uoff, b.ulen) &&
-            (uint32_t)crc32(crc32(0L, Z_NULL, 0), raw.data() + b.uoff, (uInt)b.ulen) == crc)
+            sd_crc32(raw.data() + b.uoff, b.ulen) == crc)
             return;
         z_stream zs;
         memset(&zs, 0, sizeof zs);

@@ -349,6 +349,10 @@ def test_block_inflate_matches_zlib_and_refuses_what_it_cannot_decode(tmp_path, 
     for _ in range(1000):
         own(os.urandom(rng.randint(0, 300)), rng.randint(0, 1000))
 
+    for _ in range(300):                                  # the block checksum: carry-less-multiply CRC-32 == zlib's
+        blob = os.urandom(rng.choice((0, 1, 15, 16, 63, 64, 65, 79, 80, 127, 128, rng.randint(0, 70000))))
+        assert lib.sd_crc32(blob, len(blob)) == zlib.crc32(blob)
+
     case = simdata.make_case(str(tmp_path), 77, n_reads=1500, read_len=(20, 120), name="inf")
     from slamdunk_b200.engine import HostBatch
     views = []
