@@ -168,6 +168,13 @@ struct Bits {
             }
         }
     }
+    inline void refill_fast() {     // the caller knows that 8 bytes can be read
+        uint64_t x;
+        memcpy(&x, in, 8);
+        buf |= x << cnt;
+        in += (63 - cnt) >> 3;
+        cnt |= 56;
+    }
     inline uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1ull)); }
     inline void drop(int n) {
         buf >>= n;
@@ -268,9 +275,9 @@ extern "C" int sd_inflate_raw(const uint8_t *in, uint64_t in_len, uint8_t *out, 
         // ---- symbols of the block
         for (;;) {
             uint32_t e;
-            // fast loop: at least 8 input bytes for every refill, room for the longest match plus the slack of 8-byte copies
-            while (b.in_end - b.in >= 8 && out_end - out >= 258 + 16) {
-                b.refill();                                 // >= 56 bits
+            // fast loop: input for two 8-byte refills, room for the longest match plus the slack of the 8-byte copies
+            while (b.in_end - b.in >= 16 && out_end - out >= 258 + 16) {
+                b.refill_fast();                            // >= 56 bits
                 e = lit[b.peek(kLitBits)];
                 // literals whose code fits the first level (<= 11 bits each): three of them and the symbol after fit one refill
                 if (e & kLit) {
@@ -300,7 +307,7 @@ extern "C" int sd_inflate_raw(const uint8_t *in, uint64_t in_len, uint8_t *out, 
                 if (e & (kEob | kBad)) goto block_done;
                 {
                     const uint32_t len = ((e >> 12) & 0xFFFFu) + b.take((int)((e >> 8) & 15u));      // <= 53 bits so far
-                    b.refill();
+                    b.refill_fast();                        // the first refill took at most 7 of the 16 bytes
                     uint32_t d = dist[b.peek(kDistBits)];
                     if (d & kSub) {
                         b.drop((int)(d & 0xFFu));
@@ -325,11 +332,18 @@ extern "C" int sd_inflate_raw(const uint8_t *in, uint64_t in_len, uint8_t *out, 
                                 src += 8;
                             } while (dst < out);
                         }
-                    } else if (distance == 1) {
-                        memset(dst, *src, len);
-                    } else {
+                    } else if (distance == 1) {             // a run of one byte
+                        const uint64_t rep = 0x0101010101010101ULL * *src;
                         do {
-                            *dst++ = *src++;
+                            memcpy(dst, &rep, 8);
+                            dst += 8;
+                        } while (dst < out);
+                    } else {
+                        // period 2..7: every 8-byte copy from the start of the pattern lays down `distance` good bytes (the
+                        // rest is overwritten by the next one)
+                        do {
+                            memcpy(dst, src, 8);
+                            dst += distance;
                         } while (dst < out);
                     }
                 }
