@@ -677,7 +677,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-shard-check", action="store_true")
-    ap.add_argument("--decode-sample", type=int, default=200_000, dest="decode_sample",
+    ap.add_argument("--decode-sample", type=int, default=1_000_000, dest="decode_sample",
                     help="reads of the stream written out as files for the `decode` object (host decode + one file-level "
                          "computeTconversions, reported separately from the metric); 0 = skip")
     args = ap.parse_args()

@@ -366,6 +366,45 @@ def test_block_inflate_matches_zlib_and_refuses_what_it_cannot_decode(tmp_path, 
         assert np.array_equal(a, b)
 
 
+def test_synthetic_workload_writer_fast_path_writes_the_same_bam(tmp_path):
+    """tests/synth_files.py writes a device batch out as FASTA + BED + BAM (the files the file-level benchmarks read).  Its
+    chunk-wise writer must produce the bytes of the record-by-record one: checked on batches decoded from simulated BAMs and
+    held in CPU tensors, with reads of one length, of 1..70 and of 33..129 bases."""
+    import types
+
+    import torch
+
+    import synth_files
+    from slamdunk_b200.engine import DeviceBatch, HostBatch, HostGenome
+    for seed, read_len, complexity in ((11, (100, 100), 0.3), (12, (1, 70), 1.0), (13, (33, 129), 1.0)):
+        c = simdata.make_case(str(tmp_path), seed, n_reads=1200, read_len=read_len, complexity=complexity, name="w%d" % seed)
+        g = HostGenome(c.ref)
+        hb = HostBatch(c.bam, g.names, want_mp=True, mp_all=True, group=False, seq2=False, raw_qual=True)
+        db = DeviceBatch.from_host(hb.batch, torch.device("cpu"))
+        rng = np.random.default_rng(seed)
+        tri = np.zeros((hb.n_reads, 19), dtype=np.int32)
+        tri[:, 0] = rng.integers(0, 7, size=hb.n_reads)
+        tri[:, 1:] = rng.integers(0, 300, size=(hb.n_reads, 18))
+
+        class Ann:
+            chrom, start, stop, strand = np.array([0, 1]), np.array([10, 20]), np.array([500, 700]), np.array([0, 1])
+
+            def __len__(self):
+                return 2
+        wl = types.SimpleNamespace(lo=torch.from_numpy(g.lo.copy().view(np.int32)), hi=torch.from_numpy(g.hi.copy().view(np.int32)),
+                                   nmask=torch.from_numpy(g.nmask.copy().view(np.int32)), names=g.names, chrom_off=g.chrom_off,
+                                   chrom_len=g.chrom_len, ann=Ann())
+        for sort in (True, False):
+            a = synth_files.write_workload_files(str(tmp_path / ("slow%d%d" % (seed, sort))), wl, db, torch.from_numpy(tri), slow=True, sort=sort)
+            b = synth_files.write_workload_files(str(tmp_path / ("fast%d%d" % (seed, sort))), wl, db, torch.from_numpy(tri), sort=sort)
+            for x, y in zip(a[:3], b[:3]):
+                assert open(x, "rb").read() == open(y, "rb").read()
+        # and the FASTA it writes reads back as the genome it was given
+        g2 = HostGenome(b[0])
+        assert g2.names == g.names and np.array_equal(g2.lo, g.lo) and np.array_equal(g2.hi, g.hi)
+        hb.close()
+
+
 def _bedgraph_text_like_the_reference(names, first, strand, has, po, pl, gstart, isx, cov, tc):
     """The reference's loop (tcounter.py:277-285, 315-326): per strand one dict position -> rate filled UTR by UTR, printed
     in insertion order; a position already in the dict keeps its place (and gets the same value again)."""
