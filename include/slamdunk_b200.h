@@ -482,6 +482,11 @@ int sd_inflate_raw(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t ou
 /* CRC-32 of a buffer as gzip / BGZF define it (zlib's crc32(0, p, n)); carry-less-multiply folding where the CPU has
  * PCLMULQDQ, zlib's table code otherwise and for the last n % 16 bytes. */
 uint32_t sd_crc32(const uint8_t *p, uint64_t n);
+/* sd_deflate_raw: the other direction, for the BAM writer -- at most 65 535 bytes in, one complete raw DEFLATE stream out
+ * (a single dynamic-Huffman block, or a stored block when that is smaller); level 1..9 sets the depth of the match search
+ * (1: two candidates per position, greedy ... 6: 12 candidates with one step of lazy evaluation ... 9: 96).  Returns the
+ * number of bytes written, 0 when n > 65535 or the stream does not fit `cap` (the writer then uses zlib's deflate). */
+uint64_t sd_deflate_raw(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, int level);
 
 /* ------------------------------------------------------------------ host text output
  * sd_format_repr: x printed like Python's repr(float) (what the reference's print() of a rate produces); buf >= 32 bytes.

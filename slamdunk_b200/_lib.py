@@ -171,6 +171,7 @@ PROTOTYPES = {
     "sd_hgenome_free": (None, [ctypes.POINTER(HGenome)]),
     "sd_inflate_raw": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_uint64, _VP, ctypes.c_uint64]),
     "sd_crc32": (ctypes.c_uint32, [ctypes.c_char_p, ctypes.c_uint64]),
+    "sd_deflate_raw": (ctypes.c_uint64, [ctypes.c_char_p, ctypes.c_uint64, _VP, ctypes.c_uint64, ctypes.c_int]),
     "sd_format_repr": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p]),
     "sd_write_bedgraphs": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p), _VP, _VP,
                                           _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_uint64, ctypes.c_int]),

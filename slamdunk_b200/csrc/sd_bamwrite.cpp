@@ -270,6 +270,8 @@ extern "C" int sd_rewrite_bam_indexed(const char *in_path, const char *out_path,
     const size_t n_blocks = (total + payload - 1) / payload;
     std::vector<std::vector<uint8_t>> blocks(n_blocks);
     std::atomic<int> bad(0);
+    const char *env_deflate = getenv("SD_DEFLATE");
+    const bool use_own_deflate = !(env_deflate && strcmp(env_deflate, "zlib") == 0);
     pfor(n_blocks, threads, [&](size_t b) {
         const size_t lo = b * payload, hi = std::min(total, lo + payload), len = hi - lo;
         std::vector<uint8_t> in(len);
@@ -283,17 +285,21 @@ extern "C" int sd_rewrite_bam_indexed(const char *in_path, const char *out_path,
         }
         std::vector<uint8_t> &out = blocks[b];
         out.resize(0x10000 + 64);
-        z_stream zs;
-        memset(&zs, 0, sizeof zs);
-        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = 1; return; }
-        zs.next_in = in.data();
-        zs.avail_in = (uInt)len;
-        zs.next_out = out.data() + 18;
-        zs.avail_out = (uInt)(0x10000 - 18 - 8);
-        const int zr = deflate(&zs, Z_FINISH);
-        const size_t clen = zs.total_out;
-        deflateEnd(&zs);
-        if (zr != Z_STREAM_END) { bad = 1; return; }
+        // the block compressor of sd_deflate.cpp; zlib when it declines (or with SD_DEFLATE=zlib, level 0)
+        size_t clen = (use_own_deflate && level > 0) ? (size_t)sd_deflate_raw(in.data(), len, out.data() + 18, 0x10000 - 18 - 8, level) : 0;
+        if (!clen) {
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = 1; return; }
+            zs.next_in = in.data();
+            zs.avail_in = (uInt)len;
+            zs.next_out = out.data() + 18;
+            zs.avail_out = (uInt)(0x10000 - 18 - 8);
+            const int zr = deflate(&zs, Z_FINISH);
+            clen = zs.total_out;
+            deflateEnd(&zs);
+            if (zr != Z_STREAM_END) { bad = 1; return; }
+        }
         const size_t bsize = 18 + clen + 8;
         static const uint8_t hd[12] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0};
         memcpy(out.data(), hd, 12);

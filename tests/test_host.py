@@ -366,6 +366,67 @@ def test_block_inflate_matches_zlib_and_refuses_what_it_cannot_decode(tmp_path, 
         assert np.array_equal(a, b)
 
 
+def test_block_deflate_round_trips_through_zlib_and_the_own_inflate(tmp_path, monkeypatch):
+    """sd_deflate_raw (what the BAM writer compresses its BGZF payloads with): every stream it writes must inflate to the
+    input with zlib AND with sd_inflate_raw, at every level, on empty / tiny / incompressible (stored block) / repetitive
+    inputs and on real BAM payloads, and must come out within a few percent of zlib's size at level 6; an output buffer
+    that is too small is refused without a byte written past it.  Then the native BAM writer with it against the writer
+    with zlib alone: same records."""
+    import ctypes
+    import random
+    import zlib
+    lib = L.load()
+    rng = random.Random(3)
+
+    def deflate(data, level=6, cap=None):
+        cap = cap if cap is not None else len(data) + 1024
+        out = ctypes.create_string_buffer(cap + 64)
+        ctypes.memset(out, 0xAA, cap + 64)
+        n = lib.sd_deflate_raw(data, len(data), ctypes.cast(out, ctypes.c_void_p), cap, level)
+        assert out.raw[cap:] == b"\xAA" * 64
+        return out.raw[:n] if n else None
+
+    def inflate(comp, n):
+        out = ctypes.create_string_buffer(n + 8)
+        return out.raw[:n] if lib.sd_inflate_raw(comp, len(comp), ctypes.cast(out, ctypes.c_void_p), n) else None
+
+    case = simdata.make_case(str(tmp_path), 91, n_reads=2500, read_len=(60, 100), name="defl")
+    raw = bamio.bgzf_decompress(open(case.bam, "rb").read())
+    samples = [b"", b"a", b"ab", b"abc", b"abcd", b"aaaa", b"abcabcabcabc", bytes(1000), bytes(65535), os.urandom(65535), os.urandom(100),
+               bytes(range(256)) * 255, ("".join("%d:%d:%d," % (rng.randint(0, 24), rng.randint(1, 100), rng.randint(1, 100)) for _ in range(8000))).encode()[:65280]]
+    samples += [bytes(rng.randrange(3) for _ in range(n)) for n in range(1, 40)]
+    samples += [raw[k:k + 0xFF00] for k in range(0, len(raw), 0xFF00)]
+    own6 = z6 = 0
+    for data in samples:
+        for level in (1, 3, 6, 9):
+            comp = deflate(data, level)
+            assert comp is not None
+            d = zlib.decompressobj(-15)
+            assert d.decompress(comp) + d.flush() == data and d.eof and d.unused_data == b""
+            assert inflate(comp, len(data)) == data
+        if len(data) > 20000:
+            own6 += len(deflate(data, 6))
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            z6 += len(c.compress(data) + c.flush())
+        assert deflate(data, 6, cap=16) is None or len(data) <= 11
+    assert own6 <= 1.03 * z6
+    assert lib.sd_deflate_raw(bytes(70000), 70000, ctypes.cast(ctypes.create_string_buffer(80000), ctypes.c_void_p), 80000, 6) == 0
+
+    hb_n = len(bamio.read_bam(case.bam)[2])
+    keep = np.ones(hb_n, dtype=np.uint8)
+    outs = []
+    for mode in ("own", "zlib"):
+        monkeypatch.setenv("SD_DEFLATE", mode)
+        out = str(tmp_path / ("rw_%s.bam" % mode))
+        err = ctypes.create_string_buffer(512)
+        nw = ctypes.c_uint64(0)
+        text = bamio.read_bam(case.bam)[0]
+        rc = lib.sd_rewrite_bam(case.bam.encode(), out.encode(), text.encode(), keep.ctypes.data, None, hb_n, 1, 6, 2, ctypes.byref(nw), err, len(err))
+        assert rc == L.SD_OK, err.value
+        outs.append(bamio.bgzf_decompress(open(out, "rb").read()))
+    assert outs[0] == outs[1] and int(nw.value) == hb_n
+
+
 def test_synthetic_workload_writer_fast_path_writes_the_same_bam(tmp_path):
     """tests/synth_files.py writes a device batch out as FASTA + BED + BAM (the files the file-level benchmarks read).  Its
     chunk-wise writer must produce the bytes of the record-by-record one: checked on batches decoded from simulated BAMs and
