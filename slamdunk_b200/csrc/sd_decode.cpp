@@ -428,21 +428,60 @@ struct Owner {
 
 }  // namespace
 
+namespace {
+// an input file (BAM, FASTA) as one read-only span: mapped when the path can be mapped, read otherwise
+struct FileSpan {
+    const char *p = nullptr;
+    size_t n = 0;
+    void *map = nullptr;
+    std::vector<char> buf;
+    bool open(const char *path) {
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                map = m;
+                p = (const char *)m;
+                n = (size_t)st.st_size;
+                ::close(fd);
+                return true;
+            }
+        }
+        bool ok = true;     // pipes, empty files, file systems without mmap
+        char chunk[1 << 16];
+        for (;;) {
+            const ssize_t got = ::read(fd, chunk, sizeof chunk);
+            if (got < 0) { ok = false; break; }
+            if (got == 0) break;
+            buf.insert(buf.end(), chunk, chunk + got);
+        }
+        ::close(fd);
+        p = buf.data();
+        n = buf.size();
+        return ok;
+    }
+    const uint8_t *data() const { return (const uint8_t *)p; }
+    size_t size() const { return n; }
+    void release() {
+        if (map) munmap(map, n);
+        map = nullptr;
+        std::vector<char>().swap(buf);
+        p = nullptr;
+    }
+    ~FileSpan() {
+        if (map) munmap(map, n);
+    }
+};
+}  // namespace
+
 int sd_bam_inflate_file(const char *path, int threads, RawBuf &raw, size_t *compressed_bytes, char *err, int errlen) {
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    // ---- read the file
-    FILE *fh = fopen(path, "rb");
-    if (!fh) return fail(err, errlen, SD_ERR_IO, "cannot open %s", path);
-    fseek(fh, 0, SEEK_END);
-    const long fsz = ftell(fh);
-    fseek(fh, 0, SEEK_SET);
-    RawBuf file((size_t)fsz);
-    if (!file.data()) { fclose(fh); return fail(err, errlen, SD_ERR_NOMEM, "out of host memory"); }
-    if (fsz > 0 && fread(file.data(), 1, (size_t)fsz, fh) != (size_t)fsz) {
-        fclose(fh);
-        return fail(err, errlen, SD_ERR_IO, "short read on %s", path);
-    }
-    fclose(fh);
+    // ---- the file: mapped, so that the inflating threads read it straight from the page cache
+    FileSpan file;
+    if (!file.open(path)) return fail(err, errlen, SD_ERR_IO, "cannot open %s", path);
 
     // ---- BGZF block table
     struct Blk { size_t coff, clen, uoff, ulen; };
@@ -485,7 +524,7 @@ int sd_bam_inflate_file(const char *path, int threads, RawBuf &raw, size_t *comp
         z_stream zs;
         memset(&zs, 0, sizeof zs);
         if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
-        zs.next_in = file.data() + b.coff;
+        zs.next_in = const_cast<Bytef *>(file.data() + b.coff);
         zs.avail_in = (uInt)b.clen;
         zs.next_out = raw.data() + b.uoff;
         zs.avail_out = (uInt)b.ulen;
@@ -867,7 +906,10 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
             size_t pos[4] = {start[c * 4 + 0], start[c * 4 + 1], start[c * 4 + 2], start[c * 4 + 3]};
             for (size_t i = b; i < e; i++) order[pos[cl[i]]++] = (uint32_t)i;
         });
-        std::vector<sd_read_rec> tmp(rec, rec + n);
+        RawBuf tmp_buf(n * sizeof(sd_read_rec));
+        sd_read_rec *tmp = (sd_read_rec *)tmp_buf.data();
+        if (!tmp) return bail(SD_ERR_NOMEM, "out of host memory");
+        parallel_ranges(n, threads, [&](size_t b, size_t e) { memcpy(tmp + b, rec + b, (e - b) * sizeof(sd_read_rec)); });
         parallel_for(n, threads, [&](size_t k) { rec[k] = tmp[order[k]]; });
     }
 
@@ -1231,45 +1273,6 @@ extern "C" void sd_hgenome_free(sd_hgenome *g) {
 }
 
 namespace {
-// the FASTA file as one read-only span: mapped when the path can be mapped, read otherwise
-struct FileSpan {
-    const char *p = nullptr;
-    size_t n = 0;
-    void *map = nullptr;
-    std::vector<char> buf;
-    bool open(const char *path) {
-        const int fd = ::open(path, O_RDONLY);
-        if (fd < 0) return false;
-        struct stat st;
-        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
-            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-            if (m != MAP_FAILED) {
-                madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
-                map = m;
-                p = (const char *)m;
-                n = (size_t)st.st_size;
-                ::close(fd);
-                return true;
-            }
-        }
-        bool ok = true;     // pipes, empty files, file systems without mmap
-        char chunk[1 << 16];
-        for (;;) {
-            const ssize_t got = ::read(fd, chunk, sizeof chunk);
-            if (got < 0) { ok = false; break; }
-            if (got == 0) break;
-            buf.insert(buf.end(), chunk, chunk + got);
-        }
-        ::close(fd);
-        p = buf.data();
-        n = buf.size();
-        return ok;
-    }
-    ~FileSpan() {
-        if (map) munmap(map, n);
-    }
-};
-
 // byte -> 0..3 = A C G T (either case, tcounter.py:181 upper-cases the slice), 4 = any other base letter (N, IUPAC, ...),
 // 5 = white space inside sequence lines (skipped)
 struct BaseLut {
