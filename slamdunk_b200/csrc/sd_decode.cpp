@@ -918,27 +918,33 @@ extern "C" int sd_decode_bam(const char *path, const char *const *fasta_names, u
     auto up16 = [](uint64_t x) { return (x + 15ull) & ~15ull; };
     uint32_t max_lseq = 0, mt_seq = 0, mt_qual = 0, mt_cig = 0, mt_mp = 0;
     {
-        sd_tile cur = {0, 0, 0, 0};
-        for (size_t t = 0; t < n_tiles; t++) {
-            tiles[t] = cur;
-            uint64_t bs = 0, bq = 0, bc = 0, bm = 0;
+        // sizes of every tile's blocks on all threads (tiles[t] holds sizes for a moment), then one running sum over the tiles
+        std::vector<uint32_t> tile_lseq_of(n_tiles, 0);
+        parallel_for(n_tiles, threads, [&](size_t t) {
+            uint64_t bq = 0, bc = 0, bm = 0;
             uint32_t tile_lseq = 0;
             const size_t e = std::min(n, (t + 1) * (size_t)tile_reads);
             for (size_t i = t * (size_t)tile_reads; i < e; i++) {
                 const uint32_t ls = rec[i].lseq_ncig & 0xFFFFu;
-                max_lseq = std::max(max_lseq, ls);
                 tile_lseq = std::max(tile_lseq, ls);
                 bq += ls;
                 bc += 4ull * (rec[i].lseq_ncig >> 16);
                 bm += mp_entry_bytes * (rec[i].nm_nmp >> 16);
             }
-            bs = group_bytes * tile_reads * ((tile_lseq + 31u) >> 5);   // group-major: every row slot of the tile, longest read's groups
-            bq = up16(bq); bc = up16(bc); bm = up16(bm);
-            mt_seq = std::max<uint32_t>(mt_seq, (uint32_t)bs);
-            mt_qual = std::max<uint32_t>(mt_qual, (uint32_t)bq);
-            mt_cig = std::max<uint32_t>(mt_cig, (uint32_t)bc);
-            mt_mp = std::max<uint32_t>(mt_mp, (uint32_t)bm);
-            cur.seq_off += bs; cur.qual_off += bq; cur.cig_off += bc; cur.mp_off += bm;
+            tile_lseq_of[t] = tile_lseq;
+            // group-major SEQ block: every row slot of the tile, the longest read's groups
+            tiles[t] = {group_bytes * tile_reads * ((tile_lseq + 31u) >> 5), up16(bq), up16(bc), up16(bm)};
+        });
+        sd_tile cur = {0, 0, 0, 0};
+        for (size_t t = 0; t < n_tiles; t++) {
+            const sd_tile sz = tiles[t];
+            tiles[t] = cur;
+            max_lseq = std::max(max_lseq, tile_lseq_of[t]);
+            mt_seq = std::max<uint32_t>(mt_seq, (uint32_t)sz.seq_off);
+            mt_qual = std::max<uint32_t>(mt_qual, (uint32_t)sz.qual_off);
+            mt_cig = std::max<uint32_t>(mt_cig, (uint32_t)sz.cig_off);
+            mt_mp = std::max<uint32_t>(mt_mp, (uint32_t)sz.mp_off);
+            cur.seq_off += sz.seq_off; cur.qual_off += sz.qual_off; cur.cig_off += sz.cig_off; cur.mp_off += sz.mp_off;
         }
         tiles[n_tiles] = cur;
     }
