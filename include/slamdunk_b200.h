@@ -496,6 +496,13 @@ uint64_t sd_deflate_raw(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t ca
  * coordinate of its first position; isx_plus / isx_minus: host bit-planes "base is T" / "base is A".  The rows are
  * formatted by `threads` host threads (0 = all cores) and written in BED order. */
 int sd_format_repr(double x, char *buf);
+/* The per-UTR rows of the tcount TSV (SlamSeqFile.py:99-100 as filled by tcounter.py:251-307) for BED rows in file order:
+ * counters = int64 [n_utr][SD_NCOUNTER] and tcontent = int64 [n_utr] as read back from the device, read_number = the
+ * header's FilteredReads (CPM denominator), row_strand 0 = '+', 1 = '-'.  *text is malloc'ed (release: sd_free_text). */
+int sd_format_tcount_rows(uint32_t n_utr, const char *const *row_chrom, const int64_t *row_start, const int64_t *row_stop,
+                          const char *const *row_name, const uint8_t *row_strand, const int64_t *counters,
+                          const int64_t *tcontent, int64_t read_number, char **text, uint64_t *text_len);
+void sd_free_text(char *text);
 int sd_write_bedgraphs(const char *path_plus, const char *path_minus, uint32_t n_utr, const char *const *row_chrom,
                        const int64_t *row_first_pos, const uint8_t *row_strand, const uint8_t *row_has_reads,
                        const uint64_t *row_pos_off, const uint32_t *row_pos_len, const uint64_t *row_gstart,

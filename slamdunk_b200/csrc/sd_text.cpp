@@ -5,6 +5,7 @@
 // d.ddde[+-]XX), so the files are byte-identical to the reference's `print(..., conversionBedGraph[position])`.
 #include <charconv>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -216,6 +217,71 @@ extern "C" int sd_write_bedgraphs(const char *path_plus, const char *path_minus,
     return (closed && !failed) ? SD_OK : SD_ERR_IO;
 }
 
+
+// The per-UTR rows of the tcount table (SlamSeqInterval.__repr__, slamseq/SlamSeqFile.py:99-100, filled in by
+// tcounter.py:251-307): 16 tab-separated columns, every value printed as Python's str() prints it -- the two rates are
+// the int 0 or a float (repr), the last two columns always -1.0.  counters = [n][5] in SD_C_* order.  The text comes back
+// in a malloc'ed buffer (*text, *text_len) that the caller releases with sd_free_text.
+extern "C" int sd_format_tcount_rows(uint32_t n_utr, const char *const *row_chrom, const int64_t *row_start, const int64_t *row_stop,
+                                     const char *const *row_name, const uint8_t *row_strand, const int64_t *counters,
+                                     const int64_t *tcontent, int64_t read_number, char **text, uint64_t *text_len) {
+    if (!text || !text_len || (n_utr && (!row_chrom || !row_start || !row_stop || !row_name || !row_strand || !counters || !tcontent)))
+        return SD_ERR_ARG;
+    std::string out;
+    out.reserve((size_t)n_utr * 96 + 16);
+    char num[40];
+    auto put_i = [&](long long v) { out.append(num, (size_t)(put_int(num, v) - num)); };
+    for (uint32_t i = 0; i < n_utr; i++) {
+        const int64_t *c = counters + (size_t)i * SD_NCOUNTER;
+        const int64_t reads = c[SD_C_READS];
+        out.append(row_chrom[i]);
+        out.push_back('\t');
+        put_i(row_start[i]);
+        out.push_back('\t');
+        put_i(row_stop[i]);
+        out.push_back('\t');
+        out.append(row_name[i]);
+        out.push_back('\t');
+        put_i(row_stop[i] - row_start[i]);
+        out.push_back('\t');
+        out.push_back(row_strand[i] ? '-' : '+');
+        out.push_back('\t');
+        if (reads > 0) {                                    // tcounter.py:251
+            const int64_t cov = c[SD_C_COV_ON_T], conv = c[SD_C_CONV_ON_T];
+            if (cov > 0) out.append(num, (size_t)sd_format_repr((double)conv / (double)cov, num));     // tcounter.py:301-303
+            else out.push_back('0');
+            out.push_back('\t');
+            if (read_number > 0) out.append(num, (size_t)sd_format_repr((double)reads * 1000000.0 / (double)read_number, num));   // :295-297
+            else out.push_back('0');
+            out.push_back('\t');
+            put_i(tcontent[i]);
+            out.push_back('\t');
+            put_i(cov);
+            out.push_back('\t');
+            put_i(conv);
+            out.push_back('\t');
+            put_i(reads);
+            out.push_back('\t');
+            put_i(c[SD_C_TCREADS]);
+            out.push_back('\t');
+            put_i(c[SD_C_MULTIMAP]);
+        } else {                                            // the default row: ints, Tcontent kept (tcounter.py:167, 307)
+            out.append("0\t0\t");
+            put_i(tcontent[i]);
+            out.append("\t0\t0\t0\t0\t0");
+        }
+        out.append("\t-1.0\t-1.0\n");
+    }
+    char *buf = (char *)malloc(out.size() + 1);
+    if (!buf) return SD_ERR_NOMEM;
+    memcpy(buf, out.data(), out.size());
+    buf[out.size()] = 0;
+    *text = buf;
+    *text_len = out.size();
+    return SD_OK;
+}
+
+extern "C" void sd_free_text(char *text) { free(text); }
 
 // Run-length lines of one genome-wide track of one chromosome (tcounter.py:417-476): a line is printed whenever the value
 // changes, holding the run that just ended; the first run is the implicit "0 from position 0".

@@ -231,9 +231,14 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
             rs.close()
         pair_lo = np.searchsorted(pairs["row"], np.arange(n), side="left")
         pair_hi = np.searchsorted(pairs["row"], np.arange(n), side="right")
-    counter_rows = counters[:n].tolist()                     # Python ints once, not one numpy scalar per cell
-    tcontent_rows = tcontent[:n].tolist()
-    for i, utr in enumerate(utrs):
+    # the table as text in one native call (sd_format_tcount_rows: the same str() forms, tcounter.py:251-307); row by row in
+    # Python for the mle lists and for a FilteredReads value that is not a plain int a double holds exactly
+    native_rows = not mle and type(readNumber) is int and abs(readNumber) < 2 ** 53
+    if native_rows:
+        fileCSV.write(format_rows(utrs, counters, tcontent, readNumber))
+    counter_rows = [] if native_rows else counters[:n].tolist()      # Python ints once, not one numpy scalar per cell
+    tcontent_rows = [] if native_rows else tcontent[:n].tolist()
+    for i, utr in enumerate([] if native_rows else utrs):
         row = counter_rows[i]
         readCount = row[L.SD_C_READS]
         Tcontent = tcontent_rows[i]
@@ -271,6 +276,32 @@ def computeTconversions(ref, bed, snpsFile, bam, maxReadLength, minQual, outputC
     OPTIONS["timings"] = tm
     if hbatch is not None:
         hbatch.close()
+
+
+def format_rows(utrs, counters, tcontent, readNumber):
+    """The per-UTR rows of the tcount table as one string: what `print(_row(...), file=fileCSV)` writes row by row."""
+    import ctypes
+    lib = L.load()
+    n = len(utrs)
+    if n == 0:
+        return ""
+    chroms = (ctypes.c_char_p * n)(*[u.chromosome.encode() for u in utrs])
+    names = (ctypes.c_char_p * n)(*[u.name.encode() for u in utrs])
+    start = np.array([u.start for u in utrs], dtype=np.int64)
+    stop = np.array([u.stop for u in utrs], dtype=np.int64)
+    strand = np.array([1 if u.strand == "-" else 0 for u in utrs], dtype=np.uint8)
+    c = np.ascontiguousarray(np.asarray(counters)[:n], dtype=np.int64)
+    t = np.ascontiguousarray(np.asarray(tcontent)[:n], dtype=np.int64)
+    text = ctypes.c_void_p()
+    length = ctypes.c_uint64(0)
+    rc = lib.sd_format_tcount_rows(n, chroms, start.ctypes.data, stop.ctypes.data, names, strand.ctypes.data, c.ctypes.data, t.ctypes.data,
+                                   int(readNumber), ctypes.byref(text), ctypes.byref(length))
+    if rc != L.SD_OK:
+        raise L.NativeError("sd_format_tcount_rows failed with code %d" % rc)
+    try:
+        return ctypes.string_at(text, length.value).decode()
+    finally:
+        lib.sd_free_text(text)
 
 
 def _write_bedgraphs(utrs, chrom_idx, genome, res, pos_off, pos_len, counters, out_plus, out_minus):

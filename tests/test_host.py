@@ -466,6 +466,42 @@ def test_synthetic_workload_writer_fast_path_writes_the_same_bam(tmp_path):
         hb.close()
 
 
+def test_native_tcount_rows_equal_the_python_rows():
+    """sd_format_tcount_rows == SlamSeqInterval.__repr__ row by row (tcounter._row): int 0 against float forms of the two
+    rates, the default row of a UTR without reads, FilteredReads 0, names outside ASCII, negative lengths."""
+    import io
+
+    from slamdunk_b200.dunks import tcounter
+
+    class U(object):
+        pass
+    rng = np.random.default_rng(0)
+    utrs = []
+    for i in range(3000):
+        u = U()
+        u.chromosome, u.start, u.name, u.strand = "chr%d" % (i % 21), int(rng.integers(0, 10 ** 8)), ("g\u00e9ne%d" if i % 50 == 0 else "gene%d") % i, "+-"[i % 2]
+        u.stop = u.start + int(rng.integers(-5, 5000))
+        utrs.append(u)
+    counters = rng.integers(0, 50000, size=(3000, 5)).astype(np.int64)
+    counters[::7] = 0
+    counters[1::11, L.SD_C_COV_ON_T] = 0
+    counters[::13, L.SD_C_READS] = 1
+    tcontent = rng.integers(0, 5000, size=3000).astype(np.int64)
+    for readNumber in (50000000, 0, 1, 12345677):
+        want = io.StringIO()
+        for i, utr in enumerate(utrs):
+            row = counters[i].tolist()
+            if row[L.SD_C_READS] > 0:
+                cov, conv = row[L.SD_C_COV_ON_T], row[L.SD_C_CONV_ON_T]
+                cpm = row[L.SD_C_READS] * 1000000.0 / readNumber if readNumber > 0 else 0
+                rate = float(conv) / float(cov) if cov > 0 else 0
+                print(tcounter._row(utr, rate, cpm, int(tcontent[i]), cov, conv, row[L.SD_C_READS], row[L.SD_C_TCREADS], row[L.SD_C_MULTIMAP]), file=want)
+            else:
+                print(tcounter._row(utr, 0, 0, int(tcontent[i]), 0, 0, 0, 0, 0), file=want)
+        assert tcounter.format_rows(utrs, counters, tcontent, readNumber) == want.getvalue()
+    assert tcounter.format_rows([], counters, tcontent, 5) == ""
+
+
 def _bedgraph_text_like_the_reference(names, first, strand, has, po, pl, gstart, isx, cov, tc):
     """The reference's loop (tcounter.py:277-285, 315-326): per strand one dict position -> rate filled UTR by UTR, printed
     in insertion order; a position already in the dict keeps its place (and gets the same value again)."""
