@@ -502,6 +502,155 @@ def test_native_tcount_rows_equal_the_python_rows():
     assert tcounter.format_rows([], counters, tcontent, 5) == ""
 
 
+def test_compute_tconversions_host_side_with_a_stub_engine(tmp_path, monkeypatch):
+    """The host half of computeTconversions (decode into the wire form, BED / VCF / header handling, the native row and
+    bedgraph writers) run on the CPU with the device replaced by a stub that counts nothing: every UTR must come out as
+    the reference's default row, the bedgraphs empty, the timings filled in.  (What the device adds is the GPU suite's job.)"""
+    import io
+
+    from slamdunk_b200.dunks import tcounter
+
+    class Zeros(object):
+        def __init__(self, n):
+            self.a = np.zeros(n, dtype=np.int64)
+
+        def cpu(self):
+            return self
+
+        def numpy(self):
+            return self.a
+
+    class StubEngine(object):
+        def __init__(self, device):
+            self.stats = Zeros(L.SD_NSTAT)
+            self.calls = []
+
+        def set_reference(self, *a):
+            self.calls.append("ref")
+
+        def set_snps(self, *a):
+            self.calls.append("snps")
+
+        def set_utrs(self, chrom_idx, start, stop, strand, in_bam=None):
+            self.n = len(chrom_idx)
+            self.pos_off = np.zeros(self.n, dtype=np.uint64)
+            self.pos_len = np.zeros(self.n, dtype=np.uint32)
+
+        def synchronize(self):
+            pass
+
+        def count_wire(self, wire, params):
+            assert int(wire.n_tiles) > 0
+            self.calls.append("count_wire")
+
+        def count_host(self, batch, params):
+            self.calls.append("count_host")
+
+        def reset_outputs(self):
+            pass
+
+        def finalize(self):
+            self.calls.append("finalize")
+
+        def results(self):
+            return {"counters": np.zeros((self.n, L.SD_NCOUNTER), dtype=np.int64), "tcontent": np.arange(self.n, dtype=np.int64),
+                    "stats": np.zeros(L.SD_NSTAT, dtype=np.int64), "pos_cov": np.zeros(1, dtype=np.int32), "pos_tc": np.zeros(1, dtype=np.int32)}
+
+        def launch_count(self):
+            return 0
+
+        def close(self):
+            self.calls.append("close")
+
+    engines = []
+
+    def make(device):
+        engines.append(StubEngine(device))
+        return engines[-1]
+    monkeypatch.setattr(tcounter, "CountEngine", make)
+    c = simdata.make_case(str(tmp_path), 5, n_reads=400, name="stub")
+    out = str(tmp_path / "o")
+    log = io.StringIO()
+    tcounter.computeTconversions(c.ref, c.bed, c.vcf, c.bam, 100, 27, out + ".tsv", out + ".p", out + ".m", 1, log)
+    assert engines[0].calls[-2:] == ["finalize", "close"] and "count_wire" in engines[0].calls
+    lines = open(out + ".tsv").read().splitlines()
+    assert lines[0].startswith("#slamdunk v") and lines[1].startswith("#annotation:") and lines[2] == tcounter.HEADER
+    rows = [ln.split("\t") for ln in lines[3:]]
+    utrs = [ln.rstrip("\n").split("\t") for ln in open(c.bed)]
+    stranded = [u for u in utrs if len(u) > 5 and u[5] in "+-"]
+    assert len(rows) == len(stranded) > 0
+    for k, (row, u) in enumerate(zip(rows, stranded)):
+        assert row[:4] == u[:4] and row[5] == u[5]
+        assert row[6:] == ["0", "0", str(k), "0", "0", "0", "0", "0", "-1.0", "-1.0"]
+    assert open(out + ".p").read() == "" and open(out + ".m").read() == ""
+    tm = tcounter.OPTIONS["timings"]
+    assert tm["bam_reads"] == 400 and tm["write_s"] >= 0 and tm["total_s"] > 0
+
+
+def test_positional_tracks_host_side_with_a_stub_engine(tmp_path, monkeypatch):
+    """genomewideConversionRates with the device replaced by a stub whose track_runs hands out made-up change points: the
+    eight files, written by one thread per file, must hold the header line and then every chromosome's runs in the
+    reference's chromosome order -- the same bytes as sequential sd_write_track calls."""
+    import io
+
+    from slamdunk_b200.dunks import tcounter
+
+    def runs_of(row, kind):
+        rng = np.random.default_rng(1000 * row + kind)
+        n = int(rng.integers(0, 400))
+        pos = np.sort(rng.choice(5000, size=n, replace=False)).astype(np.uint32)
+        val = rng.integers(0, 50, size=n).astype(np.float64)
+        isf = np.zeros(n, dtype=np.uint8)
+        if kind == L.SD_TRACK_RATE:
+            isf = (rng.random(n) < 0.7).astype(np.uint8)
+            val = np.where(isf == 1, rng.random(n), 0.0)
+        return pos, val, isf
+
+    class Zeros(object):
+        def cpu(self):
+            return self
+
+        def numpy(self):
+            return np.zeros(L.SD_NSTAT, dtype=np.int64)
+
+    class StubEngine(object):
+        def __init__(self, device):
+            self.stats = Zeros()
+
+        def set_reference(self, *a):
+            pass
+
+        set_snps = set_utrs = count_host = set_reference
+
+        def synchronize(self):
+            pass
+
+        reset_outputs = finalize = close = synchronize
+
+        def track_runs(self, row, kind, cutoff, track_len):
+            return runs_of(row, kind)
+
+        def launch_count(self):
+            return 0
+    monkeypatch.setattr(tcounter, "CountEngine", StubEngine)
+    c = simdata.make_case(str(tmp_path), 6, n_reads=300, name="pstub")
+    prefix = str(tmp_path / "pstub_slamdunk_mapped_filtered")
+    tcounter.genomewideConversionRates(c.ref, c.vcf, c.bam, 27, prefix, 1, 2, io.StringIO())
+    genome = bamio.read_fasta(c.ref)
+    names = list(genome.keys())
+    lib = L.load()
+    for suffix, tname, desc, strand, kind in tcounter.TRACKS:
+        want = str(tmp_path / ("want" + suffix))
+        with open(want, "w") as fh:
+            print("track type=bedGraph name=\"pstub" + tname + "\" description=\"" + desc + "\"", file=fh)
+        for chrom in sorted(names, key=tcounter._natural_keys):
+            pos, val, isf = runs_of(2 * names.index(chrom) + strand, kind)
+            if len(pos):
+                assert lib.sd_write_track(want.encode(), chrom.encode(), kind, len(pos), pos.ctypes.data, val.ctypes.data, isf.ctypes.data) == L.SD_OK
+        assert open(prefix + suffix).read() == open(want).read(), suffix
+    assert tcounter.OPTIONS["timings"]["track_lines"] > 0
+
+
 def _bedgraph_text_like_the_reference(names, first, strand, has, po, pl, gstart, isx, cov, tc):
     """The reference's loop (tcounter.py:277-285, 315-326): per strand one dict position -> rate filled UTR by UTR, printed
     in insertion order; a position already in the dict keeps its place (and gets the same value again)."""
