@@ -259,6 +259,31 @@ bool parse_aux(const uint8_t *p, const uint8_t *end, AuxInfo &a) {
     return true;
 }
 
+// One decimal number of an MP entry: plain digits are read directly; anything else strtol accepts (leading blanks, a
+// sign, more than 18 digits) goes through strtol itself, so the accepted texts and their values are strtol's.
+inline bool mp_number(const char *&s, long &v) {
+    const char *p = s;
+    if (*p >= '0' && *p <= '9') {
+        long x = 0;
+        int digits = 0;
+        do {
+            x = x * 10 + (*p - '0');
+            p++;
+            digits++;
+        } while (*p >= '0' && *p <= '9' && digits < 18);
+        if (!(*p >= '0' && *p <= '9')) {
+            v = x;
+            s = p;
+            return true;
+        }
+    }
+    char *e;
+    v = strtol(s, &e, 10);
+    if (e == s) return false;
+    s = e;
+    return true;
+}
+
 // MP:Z is "conv:readPos:refPos,..." (slamseq/SlamSeqFile.py:321-324).  Calls f(readPos-1, refPos-1)
 // for entries whose conv equals `want`.  Returns false on malformed text.
 template <class F>
@@ -266,10 +291,7 @@ bool mp_for_each(const char *s, int want, F f) {
     while (*s) {
         long v[3];
         for (int k = 0; k < 3; k++) {
-            char *e;
-            v[k] = strtol(s, &e, 10);
-            if (e == s) return false;
-            s = e;
+            if (!mp_number(s, v[k])) return false;
             if (k < 2) {
                 if (*s != ':') return false;
                 s++;
@@ -288,10 +310,7 @@ bool mp_for_all(const char *s, F f) {
     while (*s) {
         long v[3];
         for (int k = 0; k < 3; k++) {
-            char *e;
-            v[k] = strtol(s, &e, 10);
-            if (e == s) return false;
-            s = e;
+            if (!mp_number(s, v[k])) return false;
             if (k < 2) {
                 if (*s != ':') return false;
                 s++;
