@@ -493,7 +493,8 @@ uint64_t sd_deflate_raw(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t ca
  * sd_write_bedgraphs: the two per-position conversion bedgraphs (tcounter.py:277-285, 315-326) from host copies of
  * the per-position arrays.  Per BED row: chromosome text, first in-chromosome position max(0, start), strand,
  * whether the row had reads, its offset / length in the position arrays (sd_utr_layout) and the linear genome
- * coordinate of its first position; isx_plus / isx_minus: host bit-planes "base is T" / "base is A".  The rows are
+ * coordinate of its first position; ref_lo / ref_hi / ref_nmask: the host planes of sd_load_fasta ("base is T" = lo & hi & ~nmask
+ * on '+' rows, "base is A" = ~lo & ~hi & ~nmask on '-' rows).  The rows are
  * formatted by `threads` host threads (0 = all cores) and written in BED order. */
 int sd_format_repr(double x, char *buf);
 /* The per-UTR rows of the tcount TSV (SlamSeqFile.py:99-100 as filled by tcounter.py:251-307) for BED rows in file order:
@@ -506,7 +507,7 @@ void sd_free_text(char *text);
 int sd_write_bedgraphs(const char *path_plus, const char *path_minus, uint32_t n_utr, const char *const *row_chrom,
                        const int64_t *row_first_pos, const uint8_t *row_strand, const uint8_t *row_has_reads,
                        const uint64_t *row_pos_off, const uint32_t *row_pos_len, const uint64_t *row_gstart,
-                       const uint32_t *isx_plus, const uint32_t *isx_minus, const int32_t *pos_cov,
+                       const uint32_t *ref_lo, const uint32_t *ref_hi, const uint32_t *ref_nmask, const int32_t *pos_cov,
                        const int32_t *pos_tc, uint64_t n_positions, int threads);
 
 /* ------------------------------------------------------------------ genome-wide per-position tracks

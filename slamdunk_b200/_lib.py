@@ -177,7 +177,7 @@ PROTOTYPES = {
                                              _VP, _VP, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), c_u64p]),
     "sd_free_text": (None, [ctypes.c_void_p]),
     "sd_write_bedgraphs": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_char_p), _VP, _VP,
-                                          _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_uint64, ctypes.c_int]),
+                                          _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_uint64, ctypes.c_int]),
     "sd_track_runs": (ctypes.c_int, [_VP, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, _VP, _VP, _VP, ctypes.c_uint64, c_u64p]),
     "sd_write_track": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint64, _VP, _VP, _VP]),
     "sd_read_stats": (ctypes.c_int, [_VP, ctypes.POINTER(Batch), ctypes.POINTER(StatsArgs)]),

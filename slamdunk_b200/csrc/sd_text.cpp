@@ -98,9 +98,9 @@ inline char *put_int(char *o, long long v) { return std::to_chars(o, o + 24, v).
 extern "C" int sd_write_bedgraphs(const char *path_plus, const char *path_minus, uint32_t n_utr, const char *const *row_chrom,
                                   const int64_t *row_first_pos, const uint8_t *row_strand, const uint8_t *row_has_reads,
                                   const uint64_t *row_pos_off, const uint32_t *row_pos_len, const uint64_t *row_gstart,
-                                  const uint32_t *isx_plus, const uint32_t *isx_minus, const int32_t *pos_cov,
+                                  const uint32_t *ref_lo, const uint32_t *ref_hi, const uint32_t *ref_nmask, const int32_t *pos_cov,
                                   const int32_t *pos_tc, uint64_t n_positions, int threads) {
-    if (!path_plus || !path_minus) return SD_ERR_ARG;
+    if (!path_plus || !path_minus || (n_utr && (!ref_lo || !ref_hi || !ref_nmask))) return SD_ERR_ARG;
     Fd out[2] = {Fd(path_plus), Fd(path_minus)};
     if (!out[0].fh || !out[1].fh) return SD_ERR_IO;
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -136,8 +136,10 @@ extern "C" int sd_write_bedgraphs(const char *path_plus, const char *path_minus,
     auto prints = [&](uint32_t i, uint32_t p) {     // tcounter.py:277-285: covered, and the reference base is T ('+') / A ('-')
         const uint64_t idx = row_pos_off[i] + p;
         if (pos_cov[idx] <= 0) return false;
-        const uint64_t g = row_gstart[i] + p;
-        return (((row_strand[i] ? isx_minus : isx_plus)[g >> 5] >> (g & 31)) & 1u) != 0;
+        const uint64_t g = row_gstart[i] + p, w = g >> 5;
+        // upper-cased FASTA base is T (code 3, '+' rows) / A (code 0, '-' rows) and not N
+        const uint32_t is_base = (row_strand[i] ? ~ref_lo[w] & ~ref_hi[w] : ref_lo[w] & ref_hi[w]) & ~ref_nmask[w];
+        return ((is_base >> (g & 31)) & 1u) != 0;
     };
     // owner[idx] = first row in BED order that prints position idx (only filled under rows that share positions)
     std::vector<uint32_t> owner;

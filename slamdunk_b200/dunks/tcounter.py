@@ -320,12 +320,12 @@ def _write_bedgraphs(utrs, chrom_idx, genome, res, pos_off, pos_len, counters, o
     gstart = np.where(known, off[np.where(known, chrom_idx[:n], 0).astype(np.int64)] + first, 0).astype(np.uint64) if n else np.zeros(0, np.uint64)
     po = np.ascontiguousarray(pos_off, dtype=np.uint64)
     pl = np.ascontiguousarray(pos_len, dtype=np.uint32)
-    isx = (np.ascontiguousarray(genome.is_base_mask(0)), np.ascontiguousarray(genome.is_base_mask(1)))
+    planes = [np.ascontiguousarray(a, dtype=np.uint32) for a in (genome.lo, genome.hi, genome.nmask)]    # views, no copies
     cov = np.ascontiguousarray(res["pos_cov"], dtype=np.int32)
     tc = np.ascontiguousarray(res["pos_tc"], dtype=np.int32)
     ptr = lambda a: ctypes.c_void_p(a.ctypes.data)    # noqa: E731
     rc = lib.sd_write_bedgraphs(os.fsencode(out_plus), os.fsencode(out_minus), n, names, ptr(first), ptr(strand), ptr(has), ptr(po),
-                                ptr(pl), ptr(gstart), ptr(isx[0]), ptr(isx[1]), ptr(cov), ptr(tc), len(cov), int(OPTIONS["threads"]))
+                                ptr(pl), ptr(gstart), ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), ptr(cov), ptr(tc), len(cov), int(OPTIONS["threads"]))
     if rc != L.SD_OK:
         raise L.NativeError("sd_write_bedgraphs failed with code %d" % rc)
 

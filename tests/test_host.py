@@ -525,16 +525,23 @@ def test_compute_tconversions_host_side_with_a_stub_engine(tmp_path, monkeypatch
             self.stats = Zeros(L.SD_NSTAT)
             self.calls = []
 
-        def set_reference(self, *a):
-            self.calls.append("ref")
-
         def set_snps(self, *a):
             self.calls.append("snps")
 
+        def set_reference(self, lo, hi, nmask, chrom_off, chrom_len):
+            self.calls.append("ref")
+            self.chrom_len = np.asarray(chrom_len, dtype=np.int64)
+
         def set_utrs(self, chrom_idx, start, stop, strand, in_bam=None):
+            # a layout of its own: every row on a FASTA chromosome gets a private slice as long as its clipped interval
             self.n = len(chrom_idx)
-            self.pos_off = np.zeros(self.n, dtype=np.uint64)
-            self.pos_len = np.zeros(self.n, dtype=np.uint32)
+            known = np.asarray(chrom_idx) != L.SD_REF_NONE
+            clen = self.chrom_len[np.where(known, chrom_idx, 0).astype(np.int64)]
+            length = np.where(known, np.maximum(0, np.minimum(np.asarray(stop), clen) - np.maximum(0, np.asarray(start))), 0)
+            self.pos_len = length.astype(np.uint32)
+            self.pos_off = (np.cumsum(length) - length).astype(np.uint64)
+            self.pos_off[~known] = np.uint64(0xFFFFFFFFFFFFFFFF)
+            self.n_pos = int(length.sum())
 
         def synchronize(self):
             pass
@@ -553,8 +560,13 @@ def test_compute_tconversions_host_side_with_a_stub_engine(tmp_path, monkeypatch
             self.calls.append("finalize")
 
         def results(self):
-            return {"counters": np.zeros((self.n, L.SD_NCOUNTER), dtype=np.int64), "tcontent": np.arange(self.n, dtype=np.int64),
-                    "stats": np.zeros(L.SD_NSTAT, dtype=np.int64), "pos_cov": np.zeros(1, dtype=np.int32), "pos_tc": np.zeros(1, dtype=np.int32)}
+            rng = np.random.default_rng(3)
+            counters = np.zeros((self.n, L.SD_NCOUNTER), dtype=np.int64)
+            counters[1::2, L.SD_C_READS] = 3                  # odd rows "had reads": only they reach the bedgraphs
+            self.cov = rng.integers(0, 4, size=max(1, self.n_pos)).astype(np.int32)
+            self.tc = np.minimum(self.cov, rng.integers(0, 3, size=max(1, self.n_pos))).astype(np.int32)
+            return {"counters": counters, "tcontent": np.arange(self.n, dtype=np.int64), "stats": np.zeros(L.SD_NSTAT, dtype=np.int64),
+                    "pos_cov": self.cov, "pos_tc": self.tc}
 
         def launch_count(self):
             return 0
@@ -579,10 +591,28 @@ def test_compute_tconversions_host_side_with_a_stub_engine(tmp_path, monkeypatch
     utrs = [ln.rstrip("\n").split("\t") for ln in open(c.bed)]
     stranded = [u for u in utrs if len(u) > 5 and u[5] in "+-"]
     assert len(rows) == len(stranded) > 0
+    filtered = tcounter.SlamSeqInfo(tcounter.parse_sam_header(bamio.read_bam(c.bam)[0])).FilteredReads      # the CPM denominator
     for k, (row, u) in enumerate(zip(rows, stranded)):
         assert row[:4] == u[:4] and row[5] == u[5]
-        assert row[6:] == ["0", "0", str(k), "0", "0", "0", "0", "0", "-1.0", "-1.0"]
-    assert open(out + ".p").read() == "" and open(out + ".m").read() == ""
+        if k % 2 == 0:
+            assert row[6:] == ["0", "0", str(k), "0", "0", "0", "0", "0", "-1.0", "-1.0"]
+        else:       # reads but no coverage on Ts: int 0 rate, CPM from the header's FilteredReads
+            assert row[6] == "0" and row[7] == repr(3 * 1000000.0 / filtered) and row[8:] == [str(k), "0", "0", "3", "0", "0", "-1.0", "-1.0"]
+    # the bedgraphs: rows with reads, positions with coverage whose FASTA base is T ('+') / A ('-'), rate = tc * 100.0 / cov
+    eng = engines[0]
+    genome = {n_: s_.upper() for n_, s_ in bamio.read_fasta(c.ref).items()}
+    want = {"+": [], "-": []}
+    for k, u in enumerate(stranded):
+        if k % 2 == 0 or u[0] not in genome:
+            continue
+        first = max(0, int(u[1]))
+        for p_ in range(int(eng.pos_len[k])):
+            idx = int(eng.pos_off[k]) + p_
+            if eng.cov[idx] > 0 and genome[u[0]][first + p_] == ("T" if u[5] == "+" else "A"):
+                rate = 0.0 if eng.tc[idx] == 0 else int(eng.tc[idx]) * 100.0 / int(eng.cov[idx])
+                want[u[5]].append("%s %d %d %s\n" % (u[0], first + p_, first + p_ + 1, repr(rate)))
+    assert len(want["+"]) > 50 and len(want["-"]) > 50
+    assert open(out + ".p").read() == "".join(want["+"]) and open(out + ".m").read() == "".join(want["-"])
     tm = tcounter.OPTIONS["timings"]
     assert tm["bam_reads"] == 400 and tm["write_s"] >= 0 and tm["total_s"] > 0
 
@@ -702,7 +732,10 @@ def test_native_bedgraph_writer_keeps_the_reference_order(tmp_path, threads, lay
     pl[7] = 0
     gstart = (first + chrom * 100000 + 64).astype(np.uint64)
     words = (glen + 500000) // 32 + 8
-    isx = [rng.integers(0, 2 ** 32, size=words, dtype=np.uint32) & rng.integers(0, 2 ** 32, size=words, dtype=np.uint32) for _ in range(2)]
+    # random reference planes (2-bit base codes + N mask); "is T" / "is A" are what the reference's refSeq[position] test asks
+    lo, hi, nm = (rng.integers(0, 2 ** 32, size=words, dtype=np.uint32) for _ in range(3))
+    nm &= rng.integers(0, 2 ** 32, size=words, dtype=np.uint32)
+    isx = [lo & hi & ~nm, ~lo & ~hi & ~nm]
     cov = rng.integers(-1, 40, size=n_pos).astype(np.int32)
     tc = np.where(rng.random(n_pos) < 0.3, rng.integers(0, 6, size=n_pos), 0).astype(np.int32)
     names = [("chr%d" % (c + 1)).encode() for c in chrom]
@@ -712,7 +745,7 @@ def test_native_bedgraph_writer_keeps_the_reference_order(tmp_path, threads, lay
     ptr = lambda a: ctypes.c_void_p(a.ctypes.data)    # noqa: E731
     outs = [str(tmp_path / "plus.bedgraph"), str(tmp_path / "minus.bedgraph")]
     rc = lib.sd_write_bedgraphs(outs[0].encode(), outs[1].encode(), n, cn, ptr(first), ptr(strand), ptr(has), ptr(po), ptr(pl), ptr(gstart),
-                                ptr(isx[0]), ptr(isx[1]), ptr(cov), ptr(tc), n_pos, threads)
+                                ptr(lo), ptr(hi), ptr(nm), ptr(cov), ptr(tc), n_pos, threads)
     assert rc == L.SD_OK
     for path, text in zip(outs, want):
         assert open(path).read() == text
@@ -720,7 +753,7 @@ def test_native_bedgraph_writer_keeps_the_reference_order(tmp_path, threads, lay
     po[0] = n_pos
     has[0], pl[0] = 1, 5
     assert lib.sd_write_bedgraphs(outs[0].encode(), outs[1].encode(), n, cn, ptr(first), ptr(strand), ptr(has), ptr(po), ptr(pl), ptr(gstart),
-                                  ptr(isx[0]), ptr(isx[1]), ptr(cov), ptr(tc), n_pos, threads) == -2   # SD_ERR_ARG
+                                  ptr(lo), ptr(hi), ptr(nm), ptr(cov), ptr(tc), n_pos, threads) == -2   # SD_ERR_ARG
 
 
 def _filter_states(records, bam_names, bed_rows, min_identity, nm):
