@@ -133,13 +133,24 @@ extern "C" int sd_write_bedgraphs(const char *path_plus, const char *path_minus,
     bool any_shared = false;
     for (uint32_t i : rows) any_shared |= shares[i] != 0;
 
-    auto prints = [&](uint32_t i, uint32_t p) {     // tcounter.py:277-285: covered, and the reference base is T ('+') / A ('-')
-        const uint64_t idx = row_pos_off[i] + p;
-        if (pos_cov[idx] <= 0) return false;
-        const uint64_t g = row_gstart[i] + p, w = g >> 5;
-        // upper-cased FASTA base is T (code 3, '+' rows) / A (code 0, '-' rows) and not N
-        const uint32_t is_base = (row_strand[i] ? ~ref_lo[w] & ~ref_hi[w] : ref_lo[w] & ref_hi[w]) & ~ref_nmask[w];
-        return ((is_base >> (g & 31)) & 1u) != 0;
+    // the positions of row i that get a line, ascending (tcounter.py:277-285: covered, and the upper-cased FASTA base is T on
+    // '+' rows / A on '-' rows): walked 32 positions at a time over the "is that base" bits of the reference planes, so that
+    // the coverage array is only looked at under a T / A
+    auto for_each_printed = [&](uint32_t i, auto &&f) {
+        const uint64_t g0 = row_gstart[i], g_end = g0 + row_pos_len[i], off = row_pos_off[i];
+        const bool minus = row_strand[i] != 0;
+        for (uint64_t g = g0; g < g_end;) {
+            const uint64_t w = g >> 5, word_end = (w + 1) << 5;
+            uint32_t bits = (minus ? ~ref_lo[w] & ~ref_hi[w] : ref_lo[w] & ref_hi[w]) & ~ref_nmask[w];
+            bits &= 0xFFFFFFFFu << (g & 31u);
+            if (word_end > g_end) bits &= 0xFFFFFFFFu >> (word_end - g_end);
+            while (bits) {
+                const uint32_t p = (uint32_t)((w << 5) + (uint64_t)__builtin_ctz(bits) - g0);
+                bits &= bits - 1u;
+                if (pos_cov[off + p] > 0) f(p);
+            }
+            g = word_end;
+        }
     };
     // owner[idx] = first row in BED order that prints position idx (only filled under rows that share positions)
     std::vector<uint32_t> owner;
@@ -147,8 +158,9 @@ extern "C" int sd_write_bedgraphs(const char *path_plus, const char *path_minus,
         owner.assign((size_t)n_positions, UINT32_MAX);
         for (uint32_t i : rows) {
             if (!shares[i]) continue;
-            for (uint32_t p = 0; p < row_pos_len[i]; p++)
-                if (prints(i, p) && owner[row_pos_off[i] + p] == UINT32_MAX) owner[row_pos_off[i] + p] = i;
+            for_each_printed(i, [&](uint32_t p) {
+                if (owner[row_pos_off[i] + p] == UINT32_MAX) owner[row_pos_off[i] + p] = i;
+            });
         }
     }
 
@@ -184,10 +196,9 @@ extern "C" int sd_write_bedgraphs(const char *path_plus, const char *path_minus,
                 memcpy(line, row_chrom[i], name_len);
                 line[name_len] = ' ';
                 const bool shared = shares[i] != 0;
-                for (uint32_t p = 0; p < row_pos_len[i]; p++) {
-                    if (!prints(i, p)) continue;
+                for_each_printed(i, [&](uint32_t p) {
                     const uint64_t idx = row_pos_off[i] + p;
-                    if (shared && owner[idx] != i) continue;
+                    if (shared && owner[idx] != i) return;
                     const int32_t cov = pos_cov[idx], tc = pos_tc[idx];
                     int rl;
                     if (tc == 0) { memcpy(rate, "0.0", 4); rl = 3; }
@@ -200,7 +211,7 @@ extern "C" int sd_write_bedgraphs(const char *path_plus, const char *path_minus,
                     o += rl;
                     *o++ = '\n';
                     dst.append(line, (size_t)(o - line));
-                }
+                });
             }
             std::unique_lock<std::mutex> lk(turn_mutex);
             turn_cv.wait(lk, [&] { return written == c; });
