@@ -196,15 +196,40 @@ extern "C" int sd_rewrite_bam_indexed(const char *in_path, const char *out_path,
     order.reserve(n_records);
     for (uint64_t i = 0; i < n_records; i++)
         if (keep[i]) order.push_back((uint32_t)i);
-    if (sort)   // samtools sort: (tid, pos, reverse strand), unmapped tid = -1 last; stable
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-            const uint8_t *ra = R + recoff[a], *rb = R + recoff[b];
-            const uint32_t ta = g32(ra), tb = g32(rb);   // -1 as unsigned sorts last
-            if (ta != tb) return ta < tb;
-            const int32_t pa = (int32_t)g32(ra + 4), pb = (int32_t)g32(rb + 4);
-            if (pa != pb) return pa < pb;
-            return ((g16(ra + 14) >> 4) & 1u) < ((g16(rb + 14) >> 4) & 1u);
+    if (sort && order.size() > 1) {
+        // samtools sort: (tid, pos, reverse strand), unmapped tid = -1 last (as unsigned), ties in input order.  The keys are
+        // pulled out of the records once (a comparator that follows two pointers into gigabytes of records misses the cache
+        // on every comparison); with the record index as the last key component every key is distinct, so runs sorted on
+        // their own threads and merged pairwise give exactly the stable order.
+        struct Key {
+            uint64_t a, b;      // a = tid << 32 | pos with the sign bit flipped; b = reverse strand << 32 | record index
+            bool operator<(const Key &o) const { return a != o.a ? a < o.a : b < o.b; }
+        };
+        const size_t m = order.size();
+        std::vector<Key> keys(m), spare(m);
+        const size_t n_runs = std::max<size_t>(1, std::min<size_t>((size_t)threads, m / 512));
+        std::vector<size_t> cut(n_runs + 1);
+        for (size_t c = 0; c <= n_runs; c++) cut[c] = m * c / n_runs;
+        pfor(n_runs, threads, [&](size_t c) {
+            for (size_t k = cut[c]; k < cut[c + 1]; k++) {
+                const uint8_t *r = R + recoff[order[k]];
+                keys[k].a = ((uint64_t)g32(r) << 32) | (uint64_t)(g32(r + 4) ^ 0x80000000u);
+                keys[k].b = ((uint64_t)((g16(r + 14) >> 4) & 1u) << 32) | (uint64_t)order[k];
+            }
+            std::sort(keys.begin() + (ptrdiff_t)cut[c], keys.begin() + (ptrdiff_t)cut[c + 1]);
         });
+        Key *src = keys.data(), *dst = spare.data();
+        for (size_t width = 1; width < n_runs; width *= 2) {
+            const size_t n_pairs = (n_runs + 2 * width - 1) / (2 * width);
+            pfor(n_pairs, threads, [&](size_t q) {
+                const size_t lo = cut[std::min(n_runs, 2 * width * q)], mid = cut[std::min(n_runs, 2 * width * q + width)],
+                             hi = cut[std::min(n_runs, 2 * width * (q + 1))];
+                std::merge(src + lo, src + mid, src + mid, src + hi, dst + lo);
+            });
+            std::swap(src, dst);
+        }
+        for (size_t k = 0; k < m; k++) order[k] = (uint32_t)(src[k].b & 0xFFFFFFFFu);
+    }
 
     // ---- modified copies of the retained multimappers
     std::vector<std::vector<uint8_t>> owned;
