@@ -103,6 +103,7 @@ struct BaiRef {
     std::map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins;   // bin -> chunks (begin, end)
     uint32_t last_bin = 0;
     bool has_last = false;
+    std::vector<std::pair<uint64_t, uint64_t>> *last_chunks = nullptr;
     std::vector<uint64_t> linear;
     uint64_t off_beg = 0, off_end = 0, n_mapped = 0, n_unmapped = 0;
     bool used = false;
@@ -368,8 +369,12 @@ extern "C" int sd_rewrite_bam_indexed(const char *in_path, const char *out_path,
             R2.off_end = v1;
             if (flag & 4) R2.n_unmapped++; else R2.n_mapped++;
             const uint32_t bin = reg2bin(beg, end);
-            if (R2.has_last && R2.last_bin == bin) R2.bins[bin].back().second = v1;   // consecutive records of one bin: one chunk
-            else R2.bins[bin].push_back({v0, v1});
+            if (R2.has_last && R2.last_bin == bin) {
+                R2.last_chunks->back().second = v1;   // consecutive records of one bin: one chunk
+            } else {
+                R2.last_chunks = &R2.bins[bin];       // (map nodes stay where they are)
+                R2.last_chunks->push_back({v0, v1});
+            }
             R2.has_last = true;
             R2.last_bin = bin;
             const size_t w0 = (size_t)(beg >> 14), w1 = (size_t)((end - 1) >> 14);
