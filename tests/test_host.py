@@ -821,6 +821,70 @@ def test_native_bam_writer_matches_python_codec(tmp_path, seed, use_bed, nm, thr
     assert rc != 0 and b"decisions" in err.value
 
 
+@pytest.mark.parametrize("use_bed,mq,mi,nm", [(True, 2, 0.9, -1), (False, 3, 0.95, 4)])
+def test_filter_host_side_with_the_decisions_of_the_oracle(tmp_path, monkeypatch, use_bed, mq, mi, nm):
+    """filter.Filter's host half on the CPU: the device is replaced by a stub that hands back the ORACLE's decisions, so the
+    test checks what the host does with them -- log lines, @RG DS / @PG rewrite, the sorted, compressed, indexed output with
+    its RD tags -- against the same expectations the GPU suite uses."""
+    import ast
+    import io
+
+    import torch
+    from oracle import oracle
+    from slamdunk_b200.dunks import filter as filter_mod
+    c = simdata.make_filter_case(str(tmp_path), seed=611, n_reads=3000, topn=4)
+    text, refs, records = bamio.read_bam(c.bam)
+    bam_names = [n for n, _ in refs]
+    bed_rows = oracle.read_bed(c.bed) if use_bed else None
+    keep, rd, stats = oracle.filter_records(records, bam_names, bed_rows, mq, mi, nm)
+
+    class StubEngine(object):
+        def __init__(self, device):
+            self.device = torch.device("cpu")
+
+        def filter(self, db, params, name_hash=None, utrs=None):
+            st = np.zeros(L.SD_NSTAT, dtype=np.int64)
+            for k, name in ((L.SD_S_MAPPED, "mapped"), (L.SD_S_UNMAPPED, "unmapped"), (L.SD_S_FILTERED, "filtered"),
+                            (L.SD_S_MQFILTERED, "mqfiltered"), (L.SD_S_IDFILTERED, "idfiltered"), (L.SD_S_NMFILTERED, "nmfiltered")):
+                st[k] = stats[name]
+            assert (utrs is None) == (not use_bed)
+            return keep.copy(), st, _filter_states(records, bam_names, bed_rows or [], mi, nm)
+
+        def close(self):
+            pass
+
+    class StubDeviceBatch(object):
+        @staticmethod
+        def from_host(batch, device, eng=None):
+            return None
+    monkeypatch.setattr(filter_mod, "CountEngine", StubEngine)
+    monkeypatch.setattr(filter_mod, "DeviceBatch", StubDeviceBatch)
+    out = str(tmp_path / "filtered.bam")
+    log = io.StringIO()
+    filter_mod.Filter(c.bam, out, log, c.bed if use_bed else None, mq, mi, nm)
+    want = []
+    for i, r in enumerate(records):
+        if keep[i] == 1:
+            want.append(r.copy())
+        elif keep[i] == 2:
+            w = r.copy()
+            w.flag &= ~0x900
+            w.set_tag("RD", rd[i], "Z")
+            want.append(w)
+    want = bamio.sort_records(want)
+    text2, refs2, got = bamio.read_bam(out)
+    assert refs2 == refs and [_rec_tuple(r) for r in got] == [_rec_tuple(r) for r in want]
+    hdr = bamio.parse_header_text(text2)
+    ds = ast.literal_eval(hdr["RG"][0]["DS"])
+    for k in ("mapped", "filtered", "mqfiltered", "idfiltered", "nmfiltered", "multimapper"):
+        assert ds[k] == stats[k], k
+    assert ds["sequenced"] == stats["mapped"] + stats["unmapped"]
+    assert hdr["PG"][-1]["ID"] == "slamdunk" and hdr["PG"][-1]["VN"] == "3"
+    assert ("MM\t%d" % stats["multimapper"]) in log.getvalue()
+    assert os.path.getsize(out + ".bai") > 8
+    assert filter_mod.OPTIONS["stats"]["written"] == len(want)
+
+
 def test_native_bam_writer_replaces_existing_rd_tag_and_handles_empty(tmp_path):
     import ctypes
     recs = [bamio.BamRecord("m1", 0x100, 0, 10, 0, "20M", "A" * 20, [30] * 20, [("RD", "Z", "old"), ("XI", "f", 1.0), ("NM", "C", 0),
