@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <map>
 #include <atomic>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -295,7 +297,34 @@ extern "C" int sd_rewrite_bam_indexed(const char *in_path, const char *out_path,
     const size_t payload = 0xFF00;
     const size_t n_blocks = (total + payload - 1) / payload;
     std::vector<std::vector<uint8_t>> blocks(n_blocks);
+    std::vector<uint32_t> block_size(n_blocks, 0);
     std::atomic<int> bad(0);
+    // the output file takes the blocks in order while later ones are still being compressed: whoever finishes a block and
+    // finds the file free writes every block that is ready (and releases its buffer); what is left goes out after the loop
+    FILE *fh = fopen(out_path, "wb");
+    if (!fh) return wfail(err, errlen, SD_ERR_IO, "cannot create %s", out_path);
+    struct OutputGuard {            // any early return closes the file and takes the partial output away
+        FILE *&f;
+        const char *path;
+        bool keep = false;
+        ~OutputGuard() {
+            if (f) fclose(f);
+            if (!keep) remove(path);
+        }
+    } guard{fh, out_path};
+    std::unique_ptr<std::atomic<uint8_t>[]> ready(new std::atomic<uint8_t>[n_blocks ? n_blocks : 1]);
+    for (size_t b = 0; b < n_blocks; b++) ready[b].store(0, std::memory_order_relaxed);
+    std::mutex file_mutex;
+    size_t next_write = 0;          // guarded by file_mutex
+    bool write_failed = false;      // guarded by file_mutex
+    auto write_ready = [&]() {      // call with file_mutex held
+        while (next_write < n_blocks && ready[next_write].load(std::memory_order_acquire)) {
+            std::vector<uint8_t> &blk = blocks[next_write];
+            if (!write_failed && fwrite(blk.data(), 1, blk.size(), fh) != blk.size()) write_failed = true;
+            std::vector<uint8_t>().swap(blk);
+            next_write++;
+        }
+    };
     const char *env_deflate = getenv("SD_DEFLATE");
     const bool use_own_deflate = !(env_deflate && strcmp(env_deflate, "zlib") == 0);
     pfor(n_blocks, threads, [&](size_t b) {
@@ -334,12 +363,28 @@ extern "C" int sd_rewrite_bam_indexed(const char *in_path, const char *out_path,
         p32(out.data() + 18 + clen, sd_crc32(in.data(), len));
         p32(out.data() + 18 + clen + 4, (uint32_t)len);
         out.resize(bsize);
+        block_size[b] = (uint32_t)bsize;
+        ready[b].store(1, std::memory_order_release);
+        while (ready[b].load(std::memory_order_relaxed) && file_mutex.try_lock()) {
+            const size_t before = next_write;
+            write_ready();
+            const bool advanced = next_write != before;
+            file_mutex.unlock();
+            if (!advanced) break;       // not this block's turn yet; a block marked ready meanwhile is picked up by the next pass
+        }
     });
-    if (bad) return wfail(err, errlen, SD_ERR_LIMIT, "BGZF compression failed (block does not fit 64 KiB)");
+    {
+        std::lock_guard<std::mutex> lk(file_mutex);
+        if (!bad) write_ready();
+    }
+    if (bad || write_failed || next_write != n_blocks) {
+        return bad ? wfail(err, errlen, SD_ERR_LIMIT, "BGZF compression failed (block does not fit 64 KiB)")
+                   : wfail(err, errlen, SD_ERR_IO, "short write on %s", out_path);
+    }
     if (bai_path) {
         // compressed start of every block (one more: the EOF block) -> virtual offset of a position in the record stream
         std::vector<uint64_t> coff(n_blocks + 1, 0);
-        for (size_t b = 0; b < n_blocks; b++) coff[b + 1] = coff[b] + blocks[b].size();
+        for (size_t b = 0; b < n_blocks; b++) coff[b + 1] = coff[b] + block_size[b];
         auto voff = [&](size_t u) { return (coff[u / payload] << 16) | (uint64_t)(u % payload); };
         std::vector<BaiRef> refs(names.size());
         uint64_t n_no_coor = 0;
@@ -407,13 +452,12 @@ extern "C" int sd_rewrite_bam_indexed(const char *in_path, const char *out_path,
         const bool ok = fwrite(bai.data(), 1, bai.size(), fb) == bai.size();
         if (fclose(fb) != 0 || !ok) return wfail(err, errlen, SD_ERR_IO, "short write on %s", bai_path);
     }
-    FILE *fh = fopen(out_path, "wb");
-    if (!fh) return wfail(err, errlen, SD_ERR_IO, "cannot create %s", out_path);
-    for (auto &b : blocks)
-        if (fwrite(b.data(), 1, b.size(), fh) != b.size()) { fclose(fh); return wfail(err, errlen, SD_ERR_IO, "short write on %s", out_path); }
     static const uint8_t eof_block[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 66, 67, 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    fwrite(eof_block, 1, sizeof eof_block, fh);
-    fclose(fh);
+    const bool eof_ok = fwrite(eof_block, 1, sizeof eof_block, fh) == sizeof eof_block;
+    const int close_rc = fclose(fh);
+    fh = nullptr;
+    if (close_rc != 0 || !eof_ok) return wfail(err, errlen, SD_ERR_IO, "short write on %s", out_path);
+    guard.keep = true;
     if (n_written) *n_written = order.size();
     return SD_OK;
 }
