@@ -681,6 +681,84 @@ def test_positional_tracks_host_side_with_a_stub_engine(tmp_path, monkeypatch):
     assert tcounter.OPTIONS["timings"]["track_lines"] > 0
 
 
+def test_bench_decode_object_runs_on_the_cpu_with_stubs(tmp_path, monkeypatch):
+    """bench.py's `decode` leg (sample written out as files, sd_load_fasta, sd_decode_bam, the filter's rewrite, two file-level
+    computeTconversions calls) end to end on the CPU: the workload generator hands out a batch decoded from a simulated BAM,
+    the device is a stub.  The leg must fill in every field and never report an error."""
+    import types
+
+    import torch
+
+    import bench
+    from slamdunk_b200.dunks import tcounter
+    from slamdunk_b200.engine import DeviceBatch, HostBatch, HostGenome
+    c = simdata.make_case(str(tmp_path), 21, n_reads=1500, read_len=(100, 100), complexity=0.3, name="leg")
+    g = HostGenome(c.ref)
+    hb = HostBatch(c.bam, g.names, want_mp=True, mp_all=True, group=False, seq2=False, raw_qual=True)
+    db = DeviceBatch.from_host(hb.batch, torch.device("cpu"))
+    tri = torch.from_numpy(np.zeros((hb.n_reads, 19), dtype=np.int32))
+
+    class Ann(object):
+        chrom, start, stop, strand = np.array([0, 1]), np.array([10, 20]), np.array([500, 700]), np.array([0, 1])
+
+        def __len__(self):
+            return 2
+
+    class Workload(object):
+        lo, hi, nmask = (torch.from_numpy(a.copy().view(np.int32)) for a in (g.lo, g.hi, g.nmask))
+        names, chrom_off, chrom_len, ann = g.names, g.chrom_off, g.chrom_len, Ann()
+
+        def set_time_point(self, minutes):
+            pass
+
+        def params(self, **kw):
+            assert set(kw) == {"seed", "first_read", "n_reads", "read_len", "frac_multimap"}
+            return kw
+
+        def generate(self, p, want_triples=False, coordinate_sorted=False, group=None):
+            assert want_triples and coordinate_sorted and group is False
+            return db, tri
+
+    class Zeros(object):
+        def cpu(self):
+            return self
+
+        def numpy(self):
+            return np.zeros(L.SD_NSTAT, dtype=np.int64)
+
+    class StubEngine(object):
+        def __init__(self, device):
+            self.stats = Zeros()
+
+        def set_reference(self, *a):
+            pass
+
+        set_snps = count_wire = count_host = set_reference
+
+        def set_utrs(self, chrom_idx, *a):
+            self.n = len(chrom_idx)
+            self.pos_len, self.pos_off = np.zeros(self.n, dtype=np.uint32), np.zeros(self.n, dtype=np.uint64)
+
+        def synchronize(self):
+            pass
+
+        reset_outputs = finalize = close = synchronize
+
+        def results(self):
+            return {"counters": np.zeros((self.n, L.SD_NCOUNTER), dtype=np.int64), "tcontent": np.zeros(self.n, dtype=np.int64),
+                    "stats": np.zeros(L.SD_NSTAT, dtype=np.int64), "pos_cov": np.zeros(1, dtype=np.int32), "pos_tc": np.zeros(1, dtype=np.int32)}
+
+        def launch_count(self):
+            return 0
+    monkeypatch.setattr(tcounter, "CountEngine", StubEngine)
+    fake = types.SimpleNamespace(wl=Workload(), args=types.SimpleNamespace(workload="cfg2", read_len=100))
+    out = bench.decode_leg(fake, 1500)
+    assert "error" not in out, out
+    assert out["reads"] == 1500 and out["bam_reads_per_s"] > 0 and out["fasta_decode_s"] > 0 and out["bam_rewrite_s"] > 0
+    assert out["file_level"]["second_run_stages"]["bam_reads"] == 1500 and out["file_level"]["output_bytes"] > 0
+    hb.close()
+
+
 def _bedgraph_text_like_the_reference(names, first, strand, has, po, pl, gstart, isx, cov, tc):
     """The reference's loop (tcounter.py:277-285, 315-326): per strand one dict position -> rate filled UTR by UTR, printed
     in insertion order; a position already in the dict keeps its place (and gets the same value again)."""
