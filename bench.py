@@ -650,8 +650,27 @@ def decode_leg(bench, sample):
             hb.close()
         out.update(bam_inflate_s=best[0], bam_records_s=best[1], inflated_bytes=best[2],
                    bam_reads_per_s=n / max(1e-9, best[0] + best[1]), bam_compressed_MBps=best[3] / 1e6 / max(1e-9, best[0] + best[1]))
+        # the same decode on ONE thread, with the own block inflate and with zlib alone: comparable between machines
+        one = {}
+        for mode in ("own", "zlib"):
+            os.environ["SD_INFLATE"] = mode
+            try:
+                hb = HostBatch(bam, g.names, want_mp=True, group=True, seq2=True, wire=True, threads=1)
+                one["inflate_" + mode] = {"inflate_s": hb.seconds_inflate, "records_s": hb.seconds_decode,
+                                          "reads_per_s": n / max(1e-9, hb.seconds_inflate + hb.seconds_decode),
+                                          "inflate_MBps": hb.inflated_bytes / 1e6 / max(1e-9, hb.seconds_inflate)}
+                hb.close()
+            finally:
+                os.environ.pop("SD_INFLATE", None)
+        out["bam_decode_one_thread"] = one
         g.close()
         out.update(bam_rewrite(bam, os.path.join(d, "rewritten.bam")))
+        os.environ["SD_DEFLATE"] = "zlib"       # the same rewrite with zlib's deflate instead of the own block compressor
+        try:
+            z = bam_rewrite(bam, os.path.join(d, "rewritten_zlib.bam"))
+            out["bam_rewrite_zlib_deflate"] = {"s": z["bam_rewrite_s"], "bytes": z["bam_rewrite_bytes"]}
+        finally:
+            os.environ.pop("SD_DEFLATE", None)
         o = os.path.join(d, "count")
         runs = []
         for _ in range(2):      # the second run finds the FASTA decoded (a multi-sample `slamdunk count` decodes it once)

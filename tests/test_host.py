@@ -756,6 +756,8 @@ def test_bench_decode_object_runs_on_the_cpu_with_stubs(tmp_path, monkeypatch):
     assert "error" not in out, out
     assert out["reads"] == 1500 and out["bam_reads_per_s"] > 0 and out["fasta_decode_s"] > 0 and out["bam_rewrite_s"] > 0
     assert out["file_level"]["second_run_stages"]["bam_reads"] == 1500 and out["file_level"]["output_bytes"] > 0
+    assert set(out["bam_decode_one_thread"]) == {"inflate_own", "inflate_zlib"} and out["bam_rewrite_zlib_deflate"]["bytes"] > 0
+    assert "SD_INFLATE" not in os.environ and "SD_DEFLATE" not in os.environ
     hb.close()
 
 
